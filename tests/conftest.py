@@ -1,0 +1,58 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    if _has_gpu():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for it in items:
+        if "gpu" in it.keywords:
+            it.add_marker(skip)
+
+
+@pytest.fixture(scope="session")
+def fx():
+    from magpie_tts_cpp_b200 import fixtures
+    return fixtures
+
+
+@pytest.fixture(scope="session")
+def tiny_model_path(fx):
+    return fx.ensure_fixture("model-tiny")
+
+
+@pytest.fixture(scope="session")
+def full_model_path(fx):
+    return fx.ensure_fixture("model-f32")
+
+
+@pytest.fixture(scope="session")
+def codec_path(fx):
+    return fx.ensure_fixture("codec-f32")
+
+
+@pytest.fixture(scope="session")
+def oracle_mod():
+    from oracle import oracle
+    oracle.build()
+    return oracle

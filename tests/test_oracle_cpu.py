@@ -1,0 +1,249 @@
+"""CPU tests: the oracle against (a) the analytically pinned pieces of the reference and (b) an
+independent float64 torch restatement (tests/torch_ref.py).  No GPU needed."""
+import numpy as np
+import pytest
+import torch
+
+import torch_ref as tr
+
+
+def rel_err(a, b):
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    return np.abs(a - b).max() / (np.sqrt(np.mean(b * b)) + 1e-30)
+
+
+HELLO = [2378, 7, 4, 11, 11, 14, 32, 26, 22, 14, 17, 11, 3, 32, 28, 2379]  # "Hello, world!" synthetic vocab
+
+
+@pytest.fixture(scope="module")
+def tiny(oracle_mod, tiny_model_path):
+    m = oracle_mod.OracleModel(tiny_model_path)
+    W = tr.load_tensors(tiny_model_path)
+    return m, W
+
+
+def test_all_tensors_mapped(oracle_mod, tiny_model_path, codec_path):
+    m = oracle_mod.OracleModel(tiny_model_path)
+    assert m.n_mapped == len(m._reader.tensors)
+    c = oracle_mod.OracleCodec(codec_path)
+    # vq.fsqs.* are loaded-but-unused by the reference too (nano-codec.cpp:729-730)
+    assert c.n_mapped == len(c._reader.tensors) - 16
+
+
+# ---- pinned: FSQ (nano-codec.cpp:729-742; tests/test_codec_fsq.cpp:42-74) -----------------------
+
+def test_fsq_known_values(oracle_mod):
+    # index -> digits in mixed radix (8,7,6,6); level sets from docs/CODEC_ARCHITECTURE.md:88-101
+    codes = np.zeros((8, 4), np.int32)
+    codes[0] = [0, 2015, 1, 8]
+    lat = oracle_mod.fsq_dequantize(codes)
+    assert lat.shape == (32, 4)
+    np.testing.assert_array_equal(lat[0:4, 0], np.float32([-1.0, -1.0, -1.0, -1.0]))
+    # 2015 = 7 + 8*6 + 56*5 + 336*5 -> digits (7,6,5,5) -> (3/4, 3/3, 2/3, 2/3)
+    np.testing.assert_array_equal(lat[0:4, 1], np.float32([0.75, 1.0, np.float32(2) / np.float32(3), np.float32(2) / np.float32(3)]))
+    np.testing.assert_array_equal(lat[0:4, 2], np.float32([-0.75, -1.0, -1.0, -1.0]))
+    np.testing.assert_array_equal(lat[0:4, 3], np.float32([-1.0, np.float32(-2) / np.float32(3), -1.0, -1.0]))
+
+
+def test_fsq_all_indices_vs_formula(oracle_mod):
+    idx = np.arange(2024, dtype=np.int32)      # includes the out-of-range specials, which wrap
+    codes = np.tile(idx, (8, 1))
+    lat = oracle_mod.fsq_dequantize(codes)
+    ref = tr.fsq_dequant(codes).numpy().astype(np.float32)
+    np.testing.assert_array_equal(lat, ref)
+    assert len(np.unique(lat[0])) == 8 and len(np.unique(lat[1])) == 7 and len(np.unique(lat[2])) == 6
+
+
+# ---- ggml-CPU elementwise semantics ------------------------------------------------------------
+
+def test_gelu_table_semantics(oracle_mod):
+    for x in [-11.0, -3.0, -0.5, 0.0, 0.3, 1.7, 9.9, 10.0, 25.0]:
+        y = oracle_mod.gelu(x, True)
+        if x <= -10:
+            assert y == 0.0
+        elif x >= 10:
+            assert y == x
+        else:
+            xh = float(np.float16(x))
+            g = 0.5 * xh * (1 + np.tanh(0.7978845608028654 * xh * (1 + 0.044715 * xh * xh)))
+            assert abs(y - float(np.float16(g))) <= abs(float(np.float16(g))) * 2e-3 + 1e-7
+        assert abs(oracle_mod.gelu(x, False) - float(tr.gelu(torch.tensor(x, dtype=tr.DT)))) < 1e-5
+
+
+def test_layer_norm(oracle_mod):
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(768).astype(np.float32) * 3 + 1
+    w = (1 + 0.1 * rng.standard_normal(768)).astype(np.float32)
+    y = oracle_mod.layer_norm(x, w, 1e-5)
+    ref = tr.layer_norm(tr._t(x), tr._t(w), 1e-5).numpy()
+    assert rel_err(y, ref) < 1e-6
+
+
+def test_sample_top_k_properties(oracle_mod):
+    rng = np.random.default_rng(1)
+    logits = rng.standard_normal(2024).astype(np.float32)
+    am = int(np.argmax(logits))
+    assert oracle_mod.sample_top_k(logits, 0.7, 1, 0.99) == am          # k=1 -> argmax
+    assert oracle_mod.sample_top_k(logits, 0.7, 80, 0.0) == am          # u=0 -> first = max
+    order = np.argsort(-logits, kind="stable")
+    p = np.exp((logits[order[:80]] - logits[am]) / np.float32(0.7)); p /= p.sum()
+    cum = np.cumsum(p.astype(np.float32))
+    for u in [0.1, 0.35, 0.8, 0.999]:
+        want = order[np.searchsorted(cum, u, side="right")] if u < cum[-1] else order[79]
+        assert oracle_mod.sample_top_k(logits, 0.7, 80, u) == int(want)
+    # ties: lowest index first
+    t = np.zeros(16, np.float32)
+    assert oracle_mod.sample_top_k(t, 1.0, 4, 0.0) == 0
+    assert oracle_mod.sample_top_k(t, 1.0, 4, 0.30) == 1
+
+
+# ---- transformer path vs float64 torch ----------------------------------------------------------
+
+def test_encoder_vs_torch(tiny):
+    m, W = tiny
+    m.set_gelu_table(False)
+    enc = m.encode_text(HELLO)
+    ref = tr.encode_text(W, m.hp, HELLO).numpy()
+    assert enc.shape == ref.shape == (16, m.hp["d_model"])
+    assert rel_err(enc, ref) < 2e-5
+    m.set_gelu_table(True)
+    enc2 = m.encode_text(HELLO)
+    assert 0 < rel_err(enc2, ref) < 5e-3      # the f16 GELU table is a visible but small change
+
+
+def test_encoder_is_causal(tiny):
+    m, _ = tiny
+    a = m.encode_text(HELLO)
+    b = m.encode_text(HELLO[:9])
+    np.testing.assert_allclose(a[:9], b, rtol=0, atol=1e-5)
+
+
+def test_decoder_cached_vs_uncached_torch(tiny):
+    m, W = tiny
+    m.set_gelu_table(False)
+    hp = m.hp
+    enc = m.encode_text(HELLO)
+    st = m.new_state(enc, speaker=1)
+    assert st.pos == hp["context_frames"]
+    rng = np.random.default_rng(42)
+    frames = [np.full(8, hp["audio_bos_id"], np.int32)] + [rng.integers(0, 2016, 8).astype(np.int32) for _ in range(5)]
+    hid = np.stack([st.step(f) for f in frames])
+    ref = tr.decoder_teacher_forced(W, hp, tr._t(enc), 1, frames).numpy()
+    assert rel_err(hid, ref) < 5e-5
+    xk, xv = st.xkv()
+    mem = tr.layer_norm(tr._t(enc), W["decoder.layers.1.norm_xattn_memory.weight"], hp["eps"])
+    kv = (mem @ W["decoder.layers.1.cross_attention.kv_net.weight"].t()).numpy()
+    assert rel_err(xk[1], kv[:, :128]) < 1e-5 and rel_err(xv[1], kv[:, 128:]) < 1e-5
+    m.set_gelu_table(True)
+
+
+def test_audio_embedding_scale(tiny):
+    m, W = tiny
+    codes = np.array([5, 2016, 100, 2017, 0, 1, 2, 2023], np.int32)
+    e = m.audio_embedding(codes)
+    ref = tr.audio_embedding(W, codes).numpy()
+    assert rel_err(e, ref) < 1e-6
+
+
+def test_final_proj_vs_torch(tiny):
+    m, W = tiny
+    h = np.random.default_rng(3).standard_normal(m.hp["d_model"]).astype(np.float32)
+    lg = m.final_proj(h)
+    ref = (tr._t(h) @ W["final_proj.weight"].t() + W["final_proj.bias"]).numpy()
+    assert rel_err(lg, ref) < 1e-5
+
+
+def test_lt_teacher_forced_vs_torch(tiny):
+    m, W = tiny
+    m.set_gelu_table(False)
+    hp = m.hp
+    rng = np.random.default_rng(7)
+    h = rng.standard_normal(hp["d_model"]).astype(np.float32)
+    forced = rng.integers(0, 2016, 8).astype(np.int32)
+    s, a, lg = m.lt_sample(h, 0.0, 80, forbid_eos=True, forced_codes=forced)
+    ref = tr.lt_logits(W, hp, tr._t(h), forced).numpy()
+    masked = [2016, 2017, 2018, 2019, 2020, 2021, 2022, 2023]
+    assert np.all(np.isneginf(lg[:, masked]))
+    keep = np.ones(2024, bool); keep[masked] = False
+    assert rel_err(lg[:, keep], ref[:, keep]) < 2e-5
+    np.testing.assert_array_equal(a, np.argmax(np.where(keep, ref, -np.inf), 1))
+    np.testing.assert_array_equal(s, a)        # T < 0.01 -> sampled == argmax
+    s2, a2, lg2 = m.lt_sample(h, 0.0, 80, forbid_eos=False, forced_codes=forced)
+    assert np.all(np.isfinite(lg2[:, 2017])) and np.all(np.isneginf(lg2[:, 2016]))
+    m.set_gelu_table(True)
+
+
+def test_lt_free_running_feeds_back_sampled(tiny):
+    m, _ = tiny
+    h = np.random.default_rng(8).standard_normal(m.hp["d_model"]).astype(np.float32)
+    s, a, lg = m.lt_sample(h, 0.0, 80)
+    s2, a2, lg2 = m.lt_sample(h, 0.0, 80, forced_codes=s)
+    np.testing.assert_array_equal(s, s2)
+    np.testing.assert_allclose(lg, lg2)
+    u = np.full(8, 0.77, np.float32)
+    s3, a3, _ = m.lt_sample(h, 0.9, 50, uniforms=u)
+    assert s3[0] != a3[0] or True
+    assert np.all((s3 >= 0) & (s3 < 2024))
+
+
+def test_synthesize_loop_semantics(tiny):
+    m, _ = tiny
+    hp = m.hp
+    codes, hid = m.synthesize(HELLO, speaker=0, temperature=0.0, max_steps=12, want_hidden=True)
+    n = len(codes)
+    assert 4 <= n <= 12                          # EOS forbidden for the first 4 frames
+    assert np.all(codes != hp["audio_eos_id"]) and np.all(codes < 2018)
+    # replay by hand: encode -> prefill -> BOS step -> (LT, step)*
+    enc = m.encode_text(HELLO)
+    st = m.new_state(enc, 0)
+    h = st.step(np.full(8, hp["audio_bos_id"], np.int32))
+    for i in range(n):
+        np.testing.assert_allclose(h, hid[i], rtol=0, atol=0)
+        s, a, _ = m.lt_sample(h, 0.0, 80, forbid_eos=i < 4, want_logits=False)
+        np.testing.assert_array_equal(s, codes[i])
+        if i + 1 < n:
+            h = st.step(s)
+
+
+# ---- codec vs float64 torch ----------------------------------------------------------------------
+
+def test_codec_layers_vs_torch(oracle_mod):
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((54, 40)).astype(np.float32)
+    alpha = (0.5 + rng.random((1, 27, 1))).astype(np.float32)
+    y = oracle_mod.half_snake(x, alpha)
+    assert rel_err(y, tr.half_snake(tr._t(x), tr._t(alpha)).numpy()) < 1e-6
+    for K, dil in [(3, 1), (7, 3), (11, 5)]:
+        w = (rng.random((54, 54, K)).astype(np.float32) - 0.5) * 0.1
+        b = rng.standard_normal(54).astype(np.float32)
+        yc = oracle_mod.causal_conv1d(x, w, b, dil, f16=False)
+        ref = tr.causal_conv(tr._t(x), tr._t(w), tr._t(b), dil).numpy()
+        assert rel_err(yc, ref) < 1e-5
+        y16 = oracle_mod.causal_conv1d(x, w, b, dil, f16=True)
+        ref16 = tr.causal_conv(tr._t(x.astype(np.float16)), tr._t(w.astype(np.float16)), tr._t(b), dil).numpy()
+        assert rel_err(y16, ref16) < 1e-5
+    for s in (8, 4, 2):
+        w = rng.standard_normal((54, 1, 2 * s)).astype(np.float32)
+        b = rng.standard_normal(27).astype(np.float32)
+        yt = oracle_mod.conv_transpose1d(x, w, b, s)
+        ref = tr.conv_transpose(tr._t(x), tr._t(w), tr._t(b), s).numpy()
+        assert yt.shape == (27, 40 * s)
+        assert rel_err(yt, ref) < 1e-5
+
+
+def test_codec_decode_vs_torch(oracle_mod, codec_path):
+    rng = np.random.default_rng(42)
+    codes = rng.integers(0, 2016, (8, 5)).astype(np.int32)
+    W = tr.load_tensors(codec_path)
+    ref = tr.codec_decode(W, codes).numpy()
+    c32 = oracle_mod.OracleCodec(codec_path, conv_f16=False)
+    pcm = c32.decode(codes)
+    assert pcm.shape == (5 * 1024,)
+    assert rel_err(pcm, ref) < 1e-4
+    c16 = oracle_mod.OracleCodec(codec_path, conv_f16=True)
+    pcm16 = c16.decode(codes)
+    snr = 10 * np.log10(np.sum(ref ** 2) / np.sum((pcm16 - ref) ** 2))
+    assert snr > 40.0                             # f16 im2col rounding alone stays above the 40 dB bar
+    # causality: the first frames do not depend on later codes
+    pcm_short = c16.decode(codes[:, :3])
+    np.testing.assert_allclose(pcm_short, pcm16[: 3 * 1024], rtol=0, atol=1e-6)
