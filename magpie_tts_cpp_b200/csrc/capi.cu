@@ -1,0 +1,647 @@
+// C-ABI (include/magpie_b200.h): sessions, the encoder / prefill / decoder-step drivers and the
+// device-resident generation loops.  Every entry point only uploads inputs, launches sm_100a kernels
+// on the session's stream and downloads results; there is no host arithmetic on the data path.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+#include "../../include/magpie_b200.h"
+#include "common.cuh"
+#include "kernels.cuh"
+#include "model.h"
+
+namespace mgb {
+const std::string & get_error();
+
+struct Session {
+    Model * m = nullptr;
+    int B = 0, max_text = 0, max_seq = 0;
+    int Mcap = 0;                      // token capacity of the activation buffers
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<void *> allocs;
+    // activations
+    float * x = nullptr, * qbuf = nullptr, * attn = nullptr, * xq = nullptr, * xatt = nullptr, * ffh = nullptr;
+    float * hidden = nullptr;          // [B][d]
+    float * enc_out = nullptr;         // [M_enc][d] compact
+    // KV storage (model weight dtype)
+    void * kc = nullptr, * vc = nullptr;       // [L][B*max_seq][d]
+    void * xk = nullptr, * xv = nullptr;       // [L][B*max_text][dxa]
+    void * ek = nullptr, * ev = nullptr;       // encoder scratch [B*max_text][d]
+    // token maps
+    int32_t * tok_utt = nullptr, * tok_pos = nullptr, * tok_slot = nullptr;   // [Mcap] scratch (encoder / prefill)
+    int32_t * dec_utt = nullptr, * dec_pos = nullptr, * dec_slot = nullptr;   // [B] decode step
+    int32_t * d_tokens = nullptr;      // [Mcap]
+    int32_t * d_ntext = nullptr;       // [B]
+    int32_t * d_speakers = nullptr;    // [B]
+    int32_t * d_codes = nullptr, * d_sampled = nullptr, * d_argmax = nullptr;   // [B][8]
+    int32_t * d_step = nullptr;        // [1]
+    int32_t * d_done = nullptr;        // [B]
+    uint8_t * d_forbid = nullptr;      // [B]
+    int32_t * d_forced = nullptr; float * d_uniforms = nullptr;              // [B][8] single-shot
+    float * d_logits1 = nullptr;       // [B][8][V] single-shot
+    std::vector<int32_t> h_ntext, h_enc_off;
+    int M_enc = 0;
+    int pos = 0;                       // host mirror of the (uniform) decode position
+    bool encoded = false, prefilled = false;
+    // loop buffers (grown on demand)
+    int32_t * l_forced = nullptr, * l_sampled = nullptr, * l_argmax = nullptr; float * l_uniforms = nullptr;
+    float * l_logits = nullptr, * l_hidden = nullptr;
+    size_t l_cap_forced = 0, l_cap_sampled = 0, l_cap_argmax = 0, l_cap_uni = 0, l_cap_logits = 0, l_cap_hidden = 0;
+    float last_ms = 0.0f; int64_t last_launches = 0;
+
+    ~Session() {
+        if (m) cudaSetDevice(m->device);
+        for (void * p : allocs) cudaFree(p);
+        for (void * p : {(void *)l_forced, (void *)l_sampled, (void *)l_argmax, (void *)l_uniforms, (void *)l_logits, (void *)l_hidden})
+            if (p) cudaFree(p);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (stream) cudaStreamDestroy(stream);
+    }
+    template <typename T> bool alloc(T *& p, size_t n) {
+        void * d = nullptr;
+        if (cudaMalloc(&d, std::max<size_t>(n * sizeof(T), 16)) != cudaSuccess) { set_error("cudaMalloc failed (session)"); return false; }
+        allocs.push_back(d); p = (T *)d;
+        return true;
+    }
+};
+
+static bool grow(void ** p, size_t * cap, size_t bytes) {
+    if (bytes <= *cap) return true;
+    if (*p) cudaFree(*p);
+    *p = nullptr; *cap = 0;
+    MGB_CUDA_TRY(cudaMalloc(p, bytes));
+    *cap = bytes;
+    return true;
+}
+
+// ---- shared layer drivers -------------------------------------------------------------------------
+static bool decoder_layers(Session & s, Tokens tok, bool want_hidden) {
+    Model & m = *s.m; const mgb_hparams & hp = m.hp;
+    const int d = hp.d_model, dxa = hp.dec_xa_heads * hp.dec_xa_d_head, M = tok.M;
+    const size_t kv_layer = (size_t)s.B * s.max_seq * d * m.wsize, xkv_layer = (size_t)s.B * s.max_text * dxa * m.wsize;
+    for (int l = 0; l < hp.dec_layers; l++) {
+        const DecLayer & L = m.dec[l];
+        char * kl = (char *)s.kc + l * kv_layer, * vl = (char *)s.vc + l * kv_layer;
+        LinearArgs a;
+        a.precision = m.precision; a.eps = hp.eps; a.gelu_f16 = m.gelu_f16; a.M = M;
+        // self-attention: LN -> QKV (K,V written straight into the cache) -> attention -> O + residual
+        a.W = L.qkv; a.X = s.x; a.ldx = d; a.ln_w = L.norm_self; a.Y = s.qbuf; a.ldy = d;
+        a.n_q = d; a.dkv = d; a.kdst = kl; a.vdst = vl; a.tok_slot = tok.slot;
+        if (!launch_linear(a, s.stream)) return false;
+        AttnArgs at;
+        at.precision = m.precision; at.q = s.qbuf; at.ldq = d; at.K = kl; at.V = vl; at.rows_per_utt = s.max_seq;
+        at.H = hp.dec_sa_heads; at.dh = d / hp.dec_sa_heads; at.causal = 1; at.tok = tok; at.out = s.attn; at.ldo = d;
+        if (!launch_attention(at, s.stream)) return false;
+        LinearArgs o;
+        o.precision = m.precision; o.M = M; o.W = L.o; o.X = s.attn; o.ldx = d; o.res = s.x; o.ldr = d; o.Y = s.x; o.ldy = d;
+        if (!launch_linear(o, s.stream)) return false;
+        // cross-attention over the cached encoder K/V (no mask)
+        LinearArgs q;
+        q.precision = m.precision; q.eps = hp.eps; q.M = M; q.W = L.xq; q.X = s.x; q.ldx = d; q.ln_w = L.norm_xa_q; q.Y = s.xq; q.ldy = dxa;
+        if (!launch_linear(q, s.stream)) return false;
+        AttnArgs xt;
+        xt.precision = m.precision; xt.q = s.xq; xt.ldq = dxa; xt.K = (char *)s.xk + l * xkv_layer; xt.V = (char *)s.xv + l * xkv_layer;
+        xt.rows_per_utt = s.max_text; xt.H = hp.dec_xa_heads; xt.dh = hp.dec_xa_d_head; xt.causal = 0; xt.n_ctx = s.d_ntext;
+        xt.tok = tok; xt.out = s.xatt; xt.ldo = dxa;
+        if (!launch_attention(xt, s.stream)) return false;
+        LinearArgs xo;
+        xo.precision = m.precision; xo.M = M; xo.W = L.xo; xo.X = s.xatt; xo.ldx = dxa; xo.res = s.x; xo.ldr = d; xo.Y = s.x; xo.ldy = d;
+        if (!launch_linear(xo, s.stream)) return false;
+        // conv-FFN (kernel 1): LN -> W1 -> GELU -> W2 + residual
+        LinearArgs f1;
+        f1.precision = m.precision; f1.eps = hp.eps; f1.gelu_f16 = m.gelu_f16; f1.M = M; f1.W = L.ff1; f1.X = s.x; f1.ldx = d;
+        f1.ln_w = L.norm_ff; f1.act = ACT_GELU; f1.Y = s.ffh; f1.ldy = hp.d_ffn;
+        if (!launch_linear(f1, s.stream)) return false;
+        LinearArgs f2;
+        f2.precision = m.precision; f2.M = M; f2.W = L.ff2; f2.X = s.ffh; f2.ldx = hp.d_ffn; f2.res = s.x; f2.ldr = d; f2.Y = s.x; f2.ldy = d;
+        if (!launch_linear(f2, s.stream)) return false;
+    }
+    if (want_hidden) return launch_layer_norm(s.x, m.dec_norm_out, hp.eps, M, d, s.hidden, s.stream);
+    return true;
+}
+
+__global__ void advance_kernel(int32_t * pos, int32_t * slot, int B, int32_t * step) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B) { pos[i] += 1; slot[i] += 1; }
+    if (i == 0 && step) *step += 1;
+}
+
+static bool launch_advance(Session & s, bool with_step) {
+    advance_kernel<<<(s.B + 127) / 128, 128, 0, s.stream>>>(s.dec_pos, s.dec_slot, s.B, with_step ? s.d_step : nullptr);
+    MGB_LAUNCH_CHECK();
+    return true;
+}
+
+// one decoder step on the codes in s.d_codes; leaves hidden in s.hidden
+static bool decoder_step_device(Session & s) {
+    if (!launch_audio_embed(*s.m, s.d_codes, s.dec_pos, s.B, s.x, s.stream)) return false;
+    Tokens tok; tok.M = s.B; tok.utt = s.dec_utt; tok.pos = s.dec_pos; tok.slot = s.dec_slot;
+    return decoder_layers(s, tok, true);
+}
+
+static bool check_ready(Session * s, bool need_prefill) {
+    if (!s) { set_error("null session"); return false; }
+    if (cudaSetDevice(s->m->device) != cudaSuccess) { set_error("cudaSetDevice failed"); return false; }
+    if (need_prefill && !s->prefilled) { set_error("session: call mgb_encode_text and mgb_prefill first"); return false; }
+    return true;
+}
+
+}  // namespace mgb
+
+using namespace mgb;
+
+extern "C" {
+
+const char * mgb_last_error(void) { return get_error().c_str(); }
+const char * mgb_version(void) { return "magpie-b200 0.1 (sm_100a)"; }
+
+int mgb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+mgb_model * mgb_model_load(const char * path, int device, int precision) {
+    if (!path) { set_error("null path"); return nullptr; }
+    return reinterpret_cast<mgb_model *>(load_model(path, device, precision));
+}
+void mgb_model_free(mgb_model * m) { delete reinterpret_cast<Model *>(m); }
+int mgb_model_get_hparams(const mgb_model * m, mgb_hparams * out) {
+    if (!m || !out) return MGB_EINVAL;
+    *out = reinterpret_cast<const Model *>(m)->hp; return MGB_OK;
+}
+int mgb_model_set_max_dec_steps(mgb_model * m, int32_t n) {
+    if (!m || n <= 0) return MGB_EINVAL;
+    reinterpret_cast<Model *>(m)->hp.max_dec_steps = n; return MGB_OK;
+}
+int mgb_model_set_gelu_f16(mgb_model * m, int on) {
+    if (!m) return MGB_EINVAL;
+    reinterpret_cast<Model *>(m)->gelu_f16 = on ? 1 : 0; return MGB_OK;
+}
+int mgb_model_precision(const mgb_model * m) { return m ? reinterpret_cast<const Model *>(m)->precision : MGB_EINVAL; }
+int mgb_model_device(const mgb_model * m) { return m ? reinterpret_cast<const Model *>(m)->device : MGB_EINVAL; }
+int64_t mgb_model_step_weight_bytes(const mgb_model * m) { return m ? reinterpret_cast<const Model *>(m)->step_weight_bytes : 0; }
+const char * mgb_model_meta_str(const mgb_model * m, const char * key) {
+    if (!m || !key) return nullptr;
+    auto & ms = reinterpret_cast<const Model *>(m)->meta_str;
+    auto it = ms.find(key);
+    return it == ms.end() ? nullptr : it->second.c_str();
+}
+int32_t mgb_model_meta_u32(const mgb_model * m, const char * key, int32_t def) {
+    if (!m || !key) return def;
+    auto & mu = reinterpret_cast<const Model *>(m)->meta_u32;
+    auto it = mu.find(key);
+    return it == mu.end() ? def : it->second;
+}
+
+mgb_session * mgb_session_new(mgb_model * mm, int batch, int max_text, int max_seq) {
+    Model * m = reinterpret_cast<Model *>(mm);
+    if (!m || batch <= 0 || max_text <= 0) { set_error("mgb_session_new: invalid arguments"); return nullptr; }
+    const mgb_hparams & hp = m->hp;
+    if (max_seq <= 0) max_seq = hp.context_frames + hp.max_dec_steps + 16;       // magpie.cpp:4077
+    if (max_seq < hp.context_frames + 2) { set_error("mgb_session_new: max_seq too small"); return nullptr; }
+    if (max_seq > m->dec_pos_rows) { set_error("mgb_session_new: max_seq exceeds the decoder position table"); return nullptr; }
+    if (max_text > m->enc_pos_rows) { set_error("mgb_session_new: max_text exceeds the encoder position table"); return nullptr; }
+    if (cudaSetDevice(m->device) != cudaSuccess) { set_error("cudaSetDevice failed"); return nullptr; }
+    std::unique_ptr<Session> s(new Session());
+    s->m = m; s->B = batch; s->max_text = max_text; s->max_seq = max_seq;
+    const int d = hp.d_model, dxa = hp.dec_xa_heads * hp.dec_xa_d_head, L = hp.dec_layers, V = hp.vocab_per_cb;
+    s->Mcap = batch * std::max(std::max(hp.context_frames, max_text), 1);
+    const size_t M = (size_t)s->Mcap;
+    if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&s->ev0) != cudaSuccess || cudaEventCreate(&s->ev1) != cudaSuccess) {
+        set_error("mgb_session_new: stream/event creation failed"); return nullptr;
+    }
+    bool ok = s->alloc(s->x, M * d) && s->alloc(s->qbuf, M * d) && s->alloc(s->attn, M * d) && s->alloc(s->xq, M * dxa) &&
+              s->alloc(s->xatt, M * dxa) && s->alloc(s->ffh, M * hp.d_ffn) && s->alloc(s->hidden, (size_t)batch * d) &&
+              s->alloc(s->enc_out, (size_t)batch * max_text * d);
+    char * p = nullptr;
+    const size_t kvb = (size_t)L * batch * max_seq * d * m->wsize, xkvb = (size_t)L * batch * max_text * dxa * m->wsize;
+    const size_t ekb = (size_t)batch * max_text * d * m->wsize;
+    ok = ok && s->alloc(p, kvb); s->kc = p; ok = ok && s->alloc(p, kvb); s->vc = p;
+    ok = ok && s->alloc(p, xkvb); s->xk = p; ok = ok && s->alloc(p, xkvb); s->xv = p;
+    ok = ok && s->alloc(p, ekb); s->ek = p; ok = ok && s->alloc(p, ekb); s->ev = p;
+    ok = ok && s->alloc(s->tok_utt, M) && s->alloc(s->tok_pos, M) && s->alloc(s->tok_slot, M) && s->alloc(s->d_tokens, M) &&
+         s->alloc(s->dec_utt, batch) && s->alloc(s->dec_pos, batch) && s->alloc(s->dec_slot, batch) &&
+         s->alloc(s->d_ntext, batch) && s->alloc(s->d_speakers, batch) && s->alloc(s->d_codes, (size_t)batch * 8) &&
+         s->alloc(s->d_sampled, (size_t)batch * 8) && s->alloc(s->d_argmax, (size_t)batch * 8) && s->alloc(s->d_step, 1) &&
+         s->alloc(s->d_done, batch) && s->alloc(s->d_forbid, batch) && s->alloc(s->d_forced, (size_t)batch * 8) &&
+         s->alloc(s->d_uniforms, (size_t)batch * 8) && s->alloc(s->d_logits1, (size_t)batch * 8 * V);
+    if (!ok) return nullptr;
+    std::vector<int32_t> ids(batch);
+    for (int b = 0; b < batch; b++) ids[b] = b;
+    if (cudaMemcpy(s->dec_utt, ids.data(), batch * 4, cudaMemcpyHostToDevice) != cudaSuccess) { set_error("H2D failed"); return nullptr; }
+    return reinterpret_cast<mgb_session *>(s.release());
+}
+
+void mgb_session_free(mgb_session * s) { delete reinterpret_cast<Session *>(s); }
+int mgb_session_batch(const mgb_session * s) { return s ? reinterpret_cast<const Session *>(s)->B : MGB_EINVAL; }
+int mgb_session_max_seq(const mgb_session * s) { return s ? reinterpret_cast<const Session *>(s)->max_seq : MGB_EINVAL; }
+int mgb_session_positions(const mgb_session * ss, int32_t * pos_out) {
+    const Session * s = reinterpret_cast<const Session *>(ss);
+    if (!s || !pos_out) return MGB_EINVAL;
+    for (int b = 0; b < s->B; b++) pos_out[b] = s->pos;
+    return MGB_OK;
+}
+float mgb_session_last_loop_ms(const mgb_session * s) { return s ? reinterpret_cast<const Session *>(s)->last_ms : 0.0f; }
+int64_t mgb_session_last_loop_launches(const mgb_session * s) { return s ? reinterpret_cast<const Session *>(s)->last_launches : 0; }
+
+int mgb_encode_text(mgb_session * ss, const int32_t * tokens, const int32_t * n_tokens, float * enc_out) {
+    Session * s = reinterpret_cast<Session *>(ss);
+    if (!check_ready(s, false)) return MGB_EINVAL;
+    if (!tokens || !n_tokens) { set_error("magpie_encode_text: null tokens"); return MGB_EINVAL; }
+    Model & m = *s->m; const mgb_hparams & hp = m.hp; const int d = hp.d_model;
+    std::vector<int32_t> utt, pos, slot, tok;
+    s->h_ntext.assign(n_tokens, n_tokens + s->B);
+    s->h_enc_off.assign(s->B + 1, 0);
+    for (int b = 0; b < s->B; b++) {
+        const int n = n_tokens[b];
+        if (n <= 0 || n > s->max_text) { set_error("magpie_encode_text: token count out of range"); return MGB_EINVAL; }
+        s->h_enc_off[b + 1] = s->h_enc_off[b] + n;
+        for (int t = 0; t < n; t++) {
+            const int32_t id = tokens[(size_t)b * s->max_text + t];
+            if (id < 0 || id >= hp.text_vocab_size) { set_error("magpie_encode_text: token id out of range"); return MGB_EINVAL; }
+            utt.push_back(b); pos.push_back(t); slot.push_back(b * s->max_text + t); tok.push_back(id);
+        }
+    }
+    const int M = (int)tok.size();
+    s->M_enc = M;
+    cudaStream_t st = s->stream;
+    auto up = [&](int32_t * dst, const std::vector<int32_t> & v) {
+        return cudaMemcpyAsync(dst, v.data(), v.size() * 4, cudaMemcpyHostToDevice, st) == cudaSuccess;
+    };
+    if (!up(s->tok_utt, utt) || !up(s->tok_pos, pos) || !up(s->tok_slot, slot) || !up(s->d_tokens, tok) || !up(s->d_ntext, s->h_ntext)) {
+        set_error("magpie_encode_text: H2D failed"); return MGB_ECUDA;
+    }
+    Tokens T; T.M = M; T.utt = s->tok_utt; T.pos = s->tok_pos; T.slot = s->tok_slot;
+    if (!launch_text_embed(m, s->d_tokens, T, s->x, st)) return MGB_ECUDA;
+    for (int l = 0; l < hp.enc_layers; l++) {
+        const EncLayer & L = m.enc[l];
+        LinearArgs a;
+        a.precision = m.precision; a.eps = hp.eps; a.M = M; a.W = L.qkv; a.X = s->x; a.ldx = d; a.ln_w = L.norm_self;
+        a.Y = s->qbuf; a.ldy = d; a.n_q = d; a.dkv = d; a.kdst = s->ek; a.vdst = s->ev; a.tok_slot = T.slot;
+        if (!launch_linear(a, st)) return MGB_ECUDA;
+        AttnArgs at;     // the NeMo text encoder is causal (magpie.cpp:1948)
+        at.precision = m.precision; at.q = s->qbuf; at.ldq = d; at.K = s->ek; at.V = s->ev; at.rows_per_utt = s->max_text;
+        at.H = hp.enc_heads; at.dh = d / hp.enc_heads; at.causal = 1; at.tok = T; at.out = s->attn; at.ldo = d;
+        if (!launch_attention(at, st)) return MGB_ECUDA;
+        LinearArgs o;
+        o.precision = m.precision; o.M = M; o.W = L.o; o.X = s->attn; o.ldx = d; o.res = s->x; o.ldr = d; o.Y = s->x; o.ldy = d;
+        if (!launch_linear(o, st)) return MGB_ECUDA;
+        LinearArgs f1;   // causal conv k=3 as 3 shifted taps (magpie.cpp:1825-1914)
+        f1.precision = m.precision; f1.eps = hp.eps; f1.gelu_f16 = m.gelu_f16; f1.M = M; f1.W = L.ff1; f1.X = s->x; f1.ldx = d;
+        f1.ln_w = L.norm_ff; f1.act = ACT_GELU; f1.Y = s->ffh; f1.ldy = hp.d_ffn; f1.tok_pos = T.pos;
+        if (!launch_linear(f1, st)) return MGB_ECUDA;
+        LinearArgs f2;
+        f2.precision = m.precision; f2.M = M; f2.W = L.ff2; f2.X = s->ffh; f2.ldx = hp.d_ffn; f2.res = s->x; f2.ldr = d;
+        f2.Y = s->x; f2.ldy = d; f2.tok_pos = T.pos;
+        if (!launch_linear(f2, st)) return MGB_ECUDA;
+    }
+    if (!launch_layer_norm(s->x, m.enc_norm_out, hp.eps, M, d, s->enc_out, st)) return MGB_ECUDA;
+    if (enc_out) {
+        memset(enc_out, 0, (size_t)s->B * s->max_text * d * sizeof(float));
+        for (int b = 0; b < s->B; b++)
+            if (cudaMemcpyAsync(enc_out + (size_t)b * s->max_text * d, s->enc_out + (size_t)s->h_enc_off[b] * d,
+                                (size_t)s->h_ntext[b] * d * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) {
+                set_error("magpie_encode_text: D2H failed"); return MGB_ECUDA;
+            }
+    }
+    if (cudaStreamSynchronize(st) != cudaSuccess) { set_error(std::string("magpie_encode_text: ") + cudaGetErrorString(cudaGetLastError())); return MGB_ECUDA; }
+    s->encoded = true; s->prefilled = false;
+    return MGB_OK;
+}
+
+int mgb_prefill(mgb_session * ss, const int32_t * speakers) {
+    Session * s = reinterpret_cast<Session *>(ss);
+    if (!check_ready(s, false)) return MGB_EINVAL;
+    if (!s->encoded) { set_error("mgb_prefill: call mgb_encode_text first"); return MGB_EINVAL; }
+    Model & m = *s->m; const mgb_hparams & hp = m.hp;
+    const int d = hp.d_model, dxa = hp.dec_xa_heads * hp.dec_xa_d_head, C = hp.context_frames;
+    std::vector<int32_t> spk(s->B, 0);
+    for (int b = 0; b < s->B; b++) {
+        spk[b] = speakers ? speakers[b] : 0;
+        if (spk[b] < 0 || spk[b] >= hp.num_speakers) { set_error("mgb_prefill: speaker id out of range"); return MGB_EINVAL; }
+    }
+    cudaStream_t st = s->stream;
+    if (cudaMemcpyAsync(s->d_speakers, spk.data(), s->B * 4, cudaMemcpyHostToDevice, st) != cudaSuccess) { set_error("H2D failed"); return MGB_ECUDA; }
+    // per-layer cross-attention K/V from the (still resident) encoder output; tok_* hold the encoder map
+    const size_t xkv_layer = (size_t)s->B * s->max_text * dxa * m.wsize;
+    for (int l = 0; l < hp.dec_layers; l++) {
+        const DecLayer & L = m.dec[l];
+        LinearArgs a;
+        a.precision = m.precision; a.eps = hp.eps; a.M = s->M_enc; a.W = L.xkv; a.X = s->enc_out; a.ldx = d; a.ln_w = L.norm_xa_mem;
+        a.n_q = 0; a.dkv = dxa; a.kdst = (char *)s->xk + l * xkv_layer; a.vdst = (char *)s->xv + l * xkv_layer; a.tok_slot = s->tok_slot;
+        a.Y = s->qbuf; a.ldy = d;
+        if (!launch_linear(a, st)) return MGB_ECUDA;
+    }
+    // context prefill: B*C tokens, one batched causal pass (magpie.cpp:4170-4238)
+    const int M = s->B * C;
+    std::vector<int32_t> utt(M), pos(M), slot(M);
+    for (int b = 0; b < s->B; b++)
+        for (int c = 0; c < C; c++) { utt[b * C + c] = b; pos[b * C + c] = c; slot[b * C + c] = b * s->max_seq + c; }
+    if (cudaStreamSynchronize(st) != cudaSuccess) { set_error("mgb_prefill: xattn K/V failed"); return MGB_ECUDA; }
+    if (cudaMemcpyAsync(s->tok_utt, utt.data(), M * 4, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+        cudaMemcpyAsync(s->tok_pos, pos.data(), M * 4, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+        cudaMemcpyAsync(s->tok_slot, slot.data(), M * 4, cudaMemcpyHostToDevice, st) != cudaSuccess) { set_error("H2D failed"); return MGB_ECUDA; }
+    Tokens T; T.M = M; T.utt = s->tok_utt; T.pos = s->tok_pos; T.slot = s->tok_slot;
+    if (!launch_context_embed(m, s->d_speakers, T, s->x, st)) return MGB_ECUDA;
+    if (!decoder_layers(*s, T, false)) return MGB_ECUDA;
+    std::vector<int32_t> p0(s->B, C), s0(s->B);
+    for (int b = 0; b < s->B; b++) s0[b] = b * s->max_seq + C;
+    if (cudaMemcpyAsync(s->dec_pos, p0.data(), s->B * 4, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+        cudaMemcpyAsync(s->dec_slot, s0.data(), s->B * 4, cudaMemcpyHostToDevice, st) != cudaSuccess) { set_error("H2D failed"); return MGB_ECUDA; }
+    if (cudaStreamSynchronize(st) != cudaSuccess) { set_error(std::string("mgb_prefill: ") + cudaGetErrorString(cudaGetLastError())); return MGB_ECUDA; }
+    s->pos = C; s->prefilled = true; s->encoded = false;      // tok_* now hold the prefill map
+    return MGB_OK;
+}
+
+int mgb_decoder_step(mgb_session * ss, const int32_t * codes, float * hidden_out) {
+    Session * s = reinterpret_cast<Session *>(ss);
+    if (!check_ready(s, true)) return MGB_EINVAL;
+    if (s->pos + 1 > s->max_seq) { set_error("mgb_decoder_step: KV cache full"); return MGB_ERANGE; }
+    const mgb_hparams & hp = s->m->hp;
+    cudaStream_t st = s->stream;
+    if (codes) {
+        for (int i = 0; i < s->B * 8; i++)
+            if (codes[i] < 0 || codes[i] >= hp.vocab_per_cb) { set_error("mgb_decoder_step: code out of range"); return MGB_EINVAL; }
+        if (cudaMemcpyAsync(s->d_codes, codes, (size_t)s->B * 8 * 4, cudaMemcpyHostToDevice, st) != cudaSuccess) { set_error("H2D failed"); return MGB_ECUDA; }
+    }
+    if (!decoder_step_device(*s) || !launch_advance(*s, false)) return MGB_ECUDA;
+    if (hidden_out && cudaMemcpyAsync(hidden_out, s->hidden, (size_t)s->B * hp.d_model * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) {
+        set_error("D2H failed"); return MGB_ECUDA;
+    }
+    if (cudaStreamSynchronize(st) != cudaSuccess) { set_error(std::string("mgb_decoder_step: ") + cudaGetErrorString(cudaGetLastError())); return MGB_ECUDA; }
+    s->pos++;
+    return MGB_OK;
+}
+
+int mgb_final_proj(mgb_session * ss, const float * hidden, float * logits_out) {
+    Session * s = reinterpret_cast<Session *>(ss);
+    if (!check_ready(s, false) || !logits_out) return MGB_EINVAL;
+    Model & m = *s->m; const mgb_hparams & hp = m.hp;
+    const int N = hp.num_codebooks * hp.vocab_per_cb, d = hp.d_model;
+    cudaStream_t st = s->stream;
+    const float * hsrc = s->hidden;
+    if (hidden) {
+        if (cudaMemcpyAsync(s->attn, hidden, (size_t)s->B * d * 4, cudaMemcpyHostToDevice, st) != cudaSuccess) { set_error("H2D failed"); return MGB_ECUDA; }
+        hsrc = s->attn;
+    }
+    // output [B][N] does not fit the step buffers: use the loop logits buffer
+    if (!grow((void **)&s->l_logits, &s->l_cap_logits, (size_t)s->B * N * 4)) return MGB_ECUDA;
+    LinearArgs a;
+    a.precision = m.precision; a.M = s->B; a.W = m.final_w; a.X = hsrc; a.ldx = d; a.bias = m.final_b; a.Y = s->l_logits; a.ldy = N;
+    if (!launch_linear(a, st)) return MGB_ECUDA;
+    if (cudaMemcpyAsync(logits_out, s->l_logits, (size_t)s->B * N * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess) { set_error("mgb_final_proj: copy/sync failed"); return MGB_ECUDA; }
+    return MGB_OK;
+}
+
+int mgb_lt_sample(mgb_session * ss, const float * hidden, float temperature, int top_k, const uint8_t * forbid_eos,
+                  const int32_t * forced_codes, const float * uniforms, uint64_t seed,
+                  int32_t * sampled, int32_t * argmax, float * logits_out) {
+    Session * s = reinterpret_cast<Session *>(ss);
+    if (!check_ready(s, false)) return MGB_EINVAL;
+    Model & m = *s->m; const mgb_hparams & hp = m.hp;
+    const int d = hp.d_model, V = hp.vocab_per_cb, B = s->B;
+    cudaStream_t st = s->stream;
+    LtArgs a;
+    a.B = B; a.hidden = s->hidden; a.temperature = temperature; a.top_k = top_k; a.seed = seed; a.step = (uint32_t)s->pos;
+    bool ok = true;
+    if (hidden) { ok = ok && cudaMemcpyAsync(s->attn, hidden, (size_t)B * d * 4, cudaMemcpyHostToDevice, st) == cudaSuccess; a.hidden = s->attn; }
+    if (forbid_eos) { ok = ok && cudaMemcpyAsync(s->d_forbid, forbid_eos, B, cudaMemcpyHostToDevice, st) == cudaSuccess; a.forbid_eos = s->d_forbid; }
+    if (forced_codes) {
+        for (int i = 0; i < B * 8; i++)
+            if (forced_codes[i] < 0 || forced_codes[i] >= V) { set_error("mgb_lt_sample: forced code out of range"); return MGB_EINVAL; }
+        ok = ok && cudaMemcpyAsync(s->d_forced, forced_codes, (size_t)B * 8 * 4, cudaMemcpyHostToDevice, st) == cudaSuccess; a.forced = s->d_forced;
+    }
+    if (uniforms) { ok = ok && cudaMemcpyAsync(s->d_uniforms, uniforms, (size_t)B * 8 * 4, cudaMemcpyHostToDevice, st) == cudaSuccess; a.uniforms = s->d_uniforms; }
+    if (!ok) { set_error("mgb_lt_sample: H2D failed"); return MGB_ECUDA; }
+    a.sampled = s->d_sampled; a.argmax = s->d_argmax; a.next_codes = s->d_codes; a.logits = logits_out ? s->d_logits1 : nullptr;
+    if (!launch_local_transformer(m, a, st)) return MGB_ECUDA;
+    if (sampled) ok = ok && cudaMemcpyAsync(sampled, s->d_sampled, (size_t)B * 8 * 4, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+    if (argmax) ok = ok && cudaMemcpyAsync(argmax, s->d_argmax, (size_t)B * 8 * 4, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+    if (logits_out) ok = ok && cudaMemcpyAsync(logits_out, s->d_logits1, (size_t)B * 8 * V * 4, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+    if (!ok || cudaStreamSynchronize(st) != cudaSuccess) { set_error(std::string("mgb_lt_sample: ") + cudaGetErrorString(cudaGetLastError())); return MGB_ECUDA; }
+    return MGB_OK;
+}
+
+}  // extern "C"
+
+// ---- device-resident loops ---------------------------------------------------------------------------
+namespace mgb {
+
+struct LoopCfg {
+    int T = 0;                 // steps (array stride)
+    float temperature = 0.0f; int top_k = 80; uint64_t seed = 0;
+    bool teacher = false, want_logits = false, want_hidden = false, ignore_eos = false;
+    bool have_uniforms = false;
+};
+
+// One loop iteration = decoder step on d_codes -> LT (+sampling) -> advance; all per-step indexing is
+// done on the device from d_step, so the iteration is captured once as a CUDA graph and replayed.
+static bool enqueue_iteration(Session & s, const LoopCfg & c) {
+    if (!decoder_step_device(s)) return false;
+    LtArgs a;
+    a.B = s.B; a.hidden = s.hidden; a.temperature = c.temperature; a.top_k = c.top_k; a.seed = c.seed;
+    a.forced = c.teacher ? s.l_forced : nullptr;
+    a.uniforms = c.have_uniforms ? s.l_uniforms : nullptr;
+    a.sampled = s.l_sampled; a.argmax = s.l_argmax; a.next_codes = s.d_codes;
+    a.logits = c.want_logits ? s.l_logits : nullptr;
+    a.d_step = s.d_step; a.T_total = c.T; a.min_frames = c.teacher ? 0 : 4;      // magpie.cpp:4267, 4325
+    a.done_step = s.d_done; a.hidden_hist = c.want_hidden ? s.l_hidden : nullptr;
+    if (!launch_local_transformer(*s.m, a, s.stream)) return false;
+    return launch_advance(s, true);
+}
+
+static int run_loop(Session & s, const LoopCfg & c, int * steps_run) {
+    cudaStream_t st = s.stream;
+    const int B = s.B;
+    if (s.pos + c.T > s.max_seq) { set_error("generation loop: KV cache too small for the requested steps"); return MGB_ERANGE; }
+    std::vector<int32_t> neg(B, -1);
+    if (cudaMemsetAsync(s.d_step, 0, 4, st) != cudaSuccess ||
+        cudaMemcpyAsync(s.d_done, neg.data(), B * 4, cudaMemcpyHostToDevice, st) != cudaSuccess) { set_error("loop init failed"); return MGB_ECUDA; }
+    const bool use_graph = getenv("MGB_NO_GRAPH") == nullptr;
+    cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
+    const int64_t launches0 = g_launch_counter;
+    int64_t per_iter = 0;
+    if (use_graph) {
+        if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { set_error("graph capture begin failed"); return MGB_ECUDA; }
+        const bool okq = enqueue_iteration(s, c);
+        const cudaError_t e = cudaStreamEndCapture(st, &graph);
+        if (!okq || e != cudaSuccess || !graph) { if (graph) cudaGraphDestroy(graph); if (okq) set_error("graph capture failed"); return MGB_ECUDA; }
+        if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) { cudaGraphDestroy(graph); set_error("graph instantiate failed"); return MGB_ECUDA; }
+        per_iter = g_launch_counter - launches0;
+    }
+    int rc = MGB_OK, t = 0;
+    const int check_every = 8;
+    std::vector<int32_t> done(B);
+    cudaEventRecord(s.ev0, st);
+    while (t < c.T) {
+        const int n = std::min(check_every, c.T - t);
+        for (int i = 0; i < n && rc == MGB_OK; i++) {
+            if (use_graph) { if (cudaGraphLaunch(exec, st) != cudaSuccess) { set_error("graph launch failed"); rc = MGB_ECUDA; } }
+            else if (!enqueue_iteration(s, c)) rc = MGB_ECUDA;
+        }
+        if (rc != MGB_OK) break;
+        t += n;
+        if (!c.teacher && !c.ignore_eos) {
+            if (cudaMemcpyAsync(done.data(), s.d_done, B * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+                cudaStreamSynchronize(st) != cudaSuccess) { set_error("loop: EOS poll failed"); rc = MGB_ECUDA; break; }
+            bool all = true;
+            for (int b = 0; b < B; b++) all = all && done[b] >= 0;
+            if (all) break;
+        }
+    }
+    cudaEventRecord(s.ev1, st);
+    if (rc == MGB_OK && cudaStreamSynchronize(st) != cudaSuccess) {
+        set_error(std::string("generation loop: ") + cudaGetErrorString(cudaGetLastError())); rc = MGB_ECUDA;
+    }
+    if (rc == MGB_OK) cudaEventElapsedTime(&s.last_ms, s.ev0, s.ev1);
+    s.last_launches = use_graph ? per_iter * t : g_launch_counter - launches0;
+    if (exec) cudaGraphExecDestroy(exec);
+    if (graph) cudaGraphDestroy(graph);
+    s.pos += t;
+    *steps_run = t;
+    return rc;
+}
+
+static bool prepare_loop_buffers(Session & s, const LoopCfg & c) {
+    const size_t n = (size_t)s.B * c.T;
+    const mgb_hparams & hp = s.m->hp;
+    if (!grow((void **)&s.l_forced, &s.l_cap_forced, n * 32) || !grow((void **)&s.l_sampled, &s.l_cap_sampled, n * 32) ||
+        !grow((void **)&s.l_argmax, &s.l_cap_argmax, n * 32)) return false;
+    if (c.have_uniforms && !grow((void **)&s.l_uniforms, &s.l_cap_uni, n * 32)) return false;
+    if (c.want_logits && !grow((void **)&s.l_logits, &s.l_cap_logits, n * 8 * hp.vocab_per_cb * 4)) return false;
+    if (c.want_hidden && !grow((void **)&s.l_hidden, &s.l_cap_hidden, n * hp.d_model * 4)) return false;
+    return true;
+}
+
+}  // namespace mgb
+
+extern "C" {
+
+int mgb_generate(mgb_session * ss, int max_steps, float temperature, int top_k, const float * uniforms, uint64_t seed,
+                 int ignore_eos, int32_t * codes_out, int32_t * n_frames_out, float * hidden_out) {
+    Session * s = reinterpret_cast<Session *>(ss);
+    if (!check_ready(s, true)) return MGB_EINVAL;
+    const mgb_hparams & hp = s->m->hp;
+    if (max_steps <= 0) max_steps = hp.max_dec_steps;
+    if (!codes_out || !n_frames_out) { set_error("mgb_generate: null outputs"); return MGB_EINVAL; }
+    if (temperature >= 0.01f && top_k < 1) { set_error("mgb_generate: top_k must be >= 1 when sampling"); return MGB_EINVAL; }
+    LoopCfg c;
+    c.T = max_steps; c.temperature = temperature; c.top_k = top_k; c.seed = seed; c.ignore_eos = ignore_eos != 0;
+    c.want_hidden = hidden_out != nullptr; c.have_uniforms = uniforms != nullptr;
+    if (!prepare_loop_buffers(*s, c)) return MGB_ECUDA;
+    cudaStream_t st = s->stream;
+    const int B = s->B; const size_t n = (size_t)B * c.T;
+    std::vector<int32_t> bos((size_t)B * 8, hp.audio_bos_id);           // BOS frame (magpie.cpp:4271-4275)
+    bool ok = cudaMemcpyAsync(s->d_codes, bos.data(), bos.size() * 4, cudaMemcpyHostToDevice, st) == cudaSuccess;
+    if (uniforms) ok = ok && cudaMemcpyAsync(s->l_uniforms, uniforms, n * 32, cudaMemcpyHostToDevice, st) == cudaSuccess;
+    if (!ok) { set_error("mgb_generate: H2D failed"); return MGB_ECUDA; }
+    int steps = 0;
+    const int rc = run_loop(*s, c, &steps);
+    if (rc != MGB_OK) return rc;
+    std::vector<int32_t> done(B);
+    ok = cudaMemcpyAsync(codes_out, s->l_sampled, n * 32, cudaMemcpyDeviceToHost, st) == cudaSuccess &&
+         cudaMemcpyAsync(done.data(), s->d_done, B * 4, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+    if (hidden_out) ok = ok && cudaMemcpyAsync(hidden_out, s->l_hidden, n * hp.d_model * 4, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+    if (!ok || cudaStreamSynchronize(st) != cudaSuccess) { set_error("mgb_generate: D2H failed"); return MGB_ECUDA; }
+    for (int b = 0; b < B; b++) n_frames_out[b] = (ignore_eos || done[b] < 0) ? steps : std::min(done[b], steps);
+    return MGB_OK;
+}
+
+int mgb_teacher_forced(mgb_session * ss, const int32_t * codes_in, int T, float * hidden_out, float * lt_logits_out,
+                       int32_t * greedy_out) {
+    Session * s = reinterpret_cast<Session *>(ss);
+    if (!check_ready(s, true)) return MGB_EINVAL;
+    const mgb_hparams & hp = s->m->hp;
+    if (!codes_in || T <= 0) { set_error("mgb_teacher_forced: invalid arguments"); return MGB_EINVAL; }
+    const int B = s->B; const size_t n = (size_t)B * T;
+    for (size_t i = 0; i < n * 8; i++)
+        if (codes_in[i] < 0 || codes_in[i] >= hp.vocab_per_cb) { set_error("mgb_teacher_forced: code out of range"); return MGB_EINVAL; }
+    LoopCfg c;
+    c.T = T; c.teacher = true; c.want_logits = lt_logits_out != nullptr; c.want_hidden = hidden_out != nullptr;
+    if (!prepare_loop_buffers(*s, c)) return MGB_ECUDA;
+    cudaStream_t st = s->stream;
+    std::vector<int32_t> bos((size_t)B * 8, hp.audio_bos_id);
+    if (cudaMemcpyAsync(s->d_codes, bos.data(), bos.size() * 4, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+        cudaMemcpyAsync(s->l_forced, codes_in, n * 32, cudaMemcpyHostToDevice, st) != cudaSuccess) { set_error("mgb_teacher_forced: H2D failed"); return MGB_ECUDA; }
+    int steps = 0;
+    const int rc = run_loop(*s, c, &steps);
+    if (rc != MGB_OK) return rc;
+    bool ok = true;
+    if (greedy_out) ok = ok && cudaMemcpyAsync(greedy_out, s->l_argmax, n * 32, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+    if (hidden_out) ok = ok && cudaMemcpyAsync(hidden_out, s->l_hidden, n * hp.d_model * 4, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+    if (lt_logits_out) ok = ok && cudaMemcpyAsync(lt_logits_out, s->l_logits, n * 8 * hp.vocab_per_cb * 4, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+    if (!ok || cudaStreamSynchronize(st) != cudaSuccess) { set_error("mgb_teacher_forced: D2H failed"); return MGB_ECUDA; }
+    return MGB_OK;
+}
+
+// ---- codec ------------------------------------------------------------------------------------------
+mgb_codec * mgb_codec_load(const char * path, int device) {
+    if (!path) { set_error("null path"); return nullptr; }
+    return reinterpret_cast<mgb_codec *>(load_codec(path, device));
+}
+void mgb_codec_free(mgb_codec * c) { delete reinterpret_cast<Codec *>(c); }
+int mgb_codec_get_hparams(const mgb_codec * c, mgb_codec_hparams * out) {
+    if (!c || !out) return MGB_EINVAL;
+    *out = reinterpret_cast<const Codec *>(c)->hp; return MGB_OK;
+}
+float mgb_codec_last_ms(const mgb_codec * c) { return c ? reinterpret_cast<const Codec *>(c)->last_ms : 0.0f; }
+int64_t mgb_codec_last_launches(const mgb_codec * c) { return c ? reinterpret_cast<const Codec *>(c)->last_launches : 0; }
+
+static int codec_upload(Codec & c, const int32_t * codes, int B, int T) {
+    const size_t n = (size_t)B * 8 * T;
+    if (!grow((void **)&c.d_codes, &c.codes_cap, n * 4)) return MGB_ECUDA;
+    if (cudaMemcpyAsync(c.d_codes, codes, n * 4, cudaMemcpyHostToDevice, (cudaStream_t)c.stream) != cudaSuccess) { set_error("codec: H2D failed"); return MGB_ECUDA; }
+    return MGB_OK;
+}
+
+int mgb_codec_decode(mgb_codec * cc, const int32_t * codes, int batch, int n_frames, float * pcm_out) {
+    Codec * c = reinterpret_cast<Codec *>(cc);
+    if (!c || !codes || !pcm_out || batch <= 0 || n_frames <= 0) { set_error("magpie_codec_decode: invalid arguments"); return MGB_EINVAL; }
+    if (cudaSetDevice(c->device) != cudaSuccess) { set_error("cudaSetDevice failed"); return MGB_ECUDA; }
+    cudaStream_t st = (cudaStream_t)c->stream;
+    int rc = codec_upload(*c, codes, batch, n_frames);
+    if (rc != MGB_OK) return rc;
+    const size_t ns = (size_t)batch * n_frames * c->hp.hop_length;
+    if (!grow((void **)&c->d_pcm, &c->pcm_cap, ns * 4)) return MGB_ECUDA;
+    // bound scratch memory: decode utterances in groups of <= ~8K frames
+    const int per = std::max(1, 8192 / n_frames);
+    const int64_t l0 = g_launch_counter;
+    cudaEventRecord((cudaEvent_t)c->ev0, st);
+    for (int b0 = 0; b0 < batch; b0 += per) {
+        const int nb = std::min(per, batch - b0);
+        if (!codec_decode_device(*c, c->d_codes + (size_t)b0 * 8 * n_frames, nb, n_frames,
+                                 c->d_pcm + (size_t)b0 * n_frames * c->hp.hop_length, st)) return MGB_ECUDA;
+    }
+    cudaEventRecord((cudaEvent_t)c->ev1, st);
+    if (cudaMemcpyAsync(pcm_out, c->d_pcm, ns * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess) {
+        set_error(std::string("magpie_codec_decode: ") + cudaGetErrorString(cudaGetLastError())); return MGB_ECUDA;
+    }
+    cudaEventElapsedTime(&c->last_ms, (cudaEvent_t)c->ev0, (cudaEvent_t)c->ev1);
+    c->last_launches = g_launch_counter - l0;
+    return MGB_OK;
+}
+
+int mgb_codec_fsq_dequantize(mgb_codec * cc, const int32_t * codes, int batch, int n_frames, float * latent_out) {
+    Codec * c = reinterpret_cast<Codec *>(cc);
+    if (!c || !codes || !latent_out || batch <= 0 || n_frames <= 0) { set_error("fsq_dequantize: invalid arguments"); return MGB_EINVAL; }
+    if (cudaSetDevice(c->device) != cudaSuccess) { set_error("cudaSetDevice failed"); return MGB_ECUDA; }
+    cudaStream_t st = (cudaStream_t)c->stream;
+    int rc = codec_upload(*c, codes, batch, n_frames);
+    if (rc != MGB_OK) return rc;
+    const size_t n = (size_t)batch * 32 * n_frames;
+    if (!grow((void **)&c->d_pcm, &c->pcm_cap, n * 4)) return MGB_ECUDA;
+    if (!codec_fsq_device(c->d_codes, batch, n_frames, c->d_pcm, st)) return MGB_ECUDA;
+    if (cudaMemcpyAsync(latent_out, c->d_pcm, n * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess) { set_error("fsq_dequantize: D2H failed"); return MGB_ECUDA; }
+    return MGB_OK;
+}
+
+}  // extern "C"

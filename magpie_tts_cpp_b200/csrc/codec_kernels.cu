@@ -1,0 +1,355 @@
+// nano-codec decoder (reference src/nano-codec.cpp:376-845) as sm_100a kernels.
+//
+//   FSQ dequantisation   nano-codec.cpp:721-752   integer div/mod + 27-entry LUT built with the
+//                                                 reference's own C expression => bit-exact
+//   causal conv1d        nano-codec.cpp:429-466   ggml_conv_1d semantics: im2col and kernel rounded
+//                                                 to f16, f32 accumulation
+//   HalfSnake            nano-codec.cpp:376-426   fused into the PRODUCER's epilogue (activated copy)
+//   grouped ConvT        nano-codec.cpp:481-565   one kernel per stage, HalfSnake fused in front
+//   res-layer mean       nano-codec.cpp:601-641   fused into the last conv of each branch
+//
+// Activations are [B][C][T] f32, time fastest (the reference's layout, nano-codec.cpp:744-748).
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace mgb {
+
+namespace {
+
+__constant__ float c_fsq_lut[4][8];
+const int h_fsq_base[4] = {1, 8, 56, 336};
+const int h_fsq_levels[4] = {8, 7, 6, 6};
+__constant__ int c_fsq_base[4];
+__constant__ int c_fsq_levels[4];
+
+__device__ __forceinline__ float f16r(float x) { return __half2float(__float2half_rn(x)); }
+
+// x + sin^2(alpha x)/alpha for c < n_alpha, LeakyReLU(0.01) otherwise (nano-codec.cpp:386-417)
+__device__ __forceinline__ float half_snake(float x, int c, const float * alpha, int n_alpha) {
+    if (c < n_alpha) {
+        const float a = alpha[c];
+        const float sn = sinf(x * a);
+        return x + (sn * sn) / a;
+    }
+    return x > 0.0f ? x : 0.01f * x;
+}
+
+// codes [B][8][T] -> latent [B][32][T]; channel = cb*4 + d
+__global__ void fsq_kernel(const int32_t * codes, float * latent, int T, size_t total /* B*8*T */) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const size_t bc = i / T; const int t = (int)(i % T);
+    const int index = codes[i];
+#pragma unroll
+    for (int d = 0; d < 4; d++) {
+        const int nonneg = (index / c_fsq_base[d]) % c_fsq_levels[d];     // C semantics incl. negatives
+        float v;
+        if (nonneg >= 0) v = c_fsq_lut[d][nonneg];
+        else { const int half = c_fsq_levels[d] / 2; v = (float)(nonneg - half) / (float)half; }
+        latent[(bc * 4 + d) * T + t] = v;
+    }
+}
+
+struct ConvParams {
+    const float * xa;        // activated, f16-representable input [B][Cin][T]
+    const __half * w;        // [Cin][K][CoPad]
+    const float * bias;      // [Cout]
+    const float * res;       // optional residual [B][Cout][T]
+    float * y;               // optional raw output (conv + bias [+ res])
+    float * ya;              // optional activated output f16r(half_snake(y; alpha2))
+    const float * alpha2; int n_alpha2;
+    const float * sum_in; float * sum_out; int sum_mode;   // 0 none, 1 init, 2 add, 3 add and * 1/3
+    int round_in;            // apply f16 rounding when staging the input (input not pre-rounded)
+    int Cin, Cout, CoPad, K, dil, T;
+};
+
+constexpr int kConvTT = 128;      // time steps per CTA
+constexpr int kConvCI = 16;       // input channels per smem chunk
+
+// Direct causal conv: CTA = (CPT*8 output channels) x (128 time steps); thread = CPT channels x 4 steps.
+template <int CPT>
+__global__ void __launch_bounds__(256) conv1d_kernel(const ConvParams p) {
+    constexpr int CO_T = CPT * 8;
+    extern __shared__ __align__(16) unsigned char conv_smem[];
+    const int halo = (p.K - 1) * p.dil;
+    const int xw = kConvTT + halo;
+    float * xs = reinterpret_cast<float *>(conv_smem);                         // [kConvCI][xw]
+    __half * ws = reinterpret_cast<__half *>(xs + kConvCI * xw);               // [kConvCI][K][CO_T]
+    const int tid = threadIdx.x, cg = tid >> 5, tg = tid & 31;
+    const int b = blockIdx.z, co0 = blockIdx.y * CO_T, t0 = blockIdx.x * kConvTT;
+    const float * xb = p.xa + (size_t)b * p.Cin * p.T;
+
+    float acc[CPT][4];
+#pragma unroll
+    for (int r = 0; r < CPT; r++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[r][j] = 0.0f;
+
+    for (int ci0 = 0; ci0 < p.Cin; ci0 += kConvCI) {
+        const int nci = min(kConvCI, p.Cin - ci0);
+        __syncthreads();
+        for (int i = tid; i < nci * xw; i += 256) {
+            const int ci = i / xw, tt = i % xw;
+            const int t = t0 - halo + tt;
+            float v = (t >= 0 && t < p.T) ? xb[(size_t)(ci0 + ci) * p.T + t] : 0.0f;
+            xs[ci * xw + tt] = p.round_in ? f16r(v) : v;
+        }
+        for (int i = tid; i < nci * p.K * (CO_T / 8); i += 256) {      // 16-byte chunks of 8 halves
+            const int c8 = i % (CO_T / 8), rest = i / (CO_T / 8);
+            const uint4 v = *reinterpret_cast<const uint4 *>(p.w + ((size_t)(ci0 * p.K + rest)) * p.CoPad + co0 + c8 * 8);
+            *reinterpret_cast<uint4 *>(ws + (size_t)rest * CO_T + c8 * 8) = v;
+        }
+        __syncthreads();
+        for (int ci = 0; ci < nci; ci++) {
+            for (int k = 0; k < p.K; k++) {
+                const __half * wr = ws + ((size_t)ci * p.K + k) * CO_T + cg * CPT;
+                float w[CPT];
+#pragma unroll
+                for (int r = 0; r < CPT; r += 2) {
+                    const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(wr + r));
+                    w[r] = f.x; w[r + 1] = f.y;
+                }
+                const float * xr = xs + ci * xw + k * p.dil + tg;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const float xv = xr[j * 32];
+#pragma unroll
+                    for (int r = 0; r < CPT; r++) acc[r][j] = fmaf(w[r], xv, acc[r][j]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < CPT; r++) {
+        const int co = co0 + cg * CPT + r;
+        if (co >= p.Cout) continue;
+        const float bv = p.bias ? p.bias[co] : 0.0f;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int t = t0 + tg + j * 32;
+            if (t >= p.T) continue;
+            const size_t o = ((size_t)b * p.Cout + co) * p.T + t;
+            float v = acc[r][j] + bv;
+            if (p.res) v = p.res[o] + v;
+            if (p.y) p.y[o] = v;
+            if (p.ya) p.ya[o] = f16r(half_snake(v, co, p.alpha2, p.n_alpha2));
+            if (p.sum_mode == 1) p.sum_out[o] = v;
+            else if (p.sum_mode == 2) p.sum_out[o] = p.sum_in[o] + v;
+            else if (p.sum_mode == 3) p.sum_out[o] = (p.sum_in[o] + v) * (1.0f / 3.0f);
+        }
+    }
+}
+
+// ya = f16r(half_snake(x; alpha)) for up to 3 alpha sets at once (the three branch inputs)
+struct SnakeParams { const float * x; float * y[3]; const float * alpha[3]; int n_alpha; int n_out; int C, T; size_t total; };
+__global__ void snake_kernel(const SnakeParams p) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.total) return;
+    const int c = (int)((i / p.T) % p.C);
+    const float v = p.x[i];
+    for (int j = 0; j < p.n_out; j++) p.y[j][i] = f16r(half_snake(v, c, p.alpha[j], p.n_alpha));
+}
+
+// HalfSnake -> grouped ConvTranspose1d (groups = Cout, 2 inputs per group, K = 2*stride, keep T*stride)
+struct UpParams { const float * x; const float * alpha; int n_alpha; const float * w; const float * bias; float * y; int Cin, T, s; size_t total; };
+__global__ void snake_convt_kernel(const UpParams p) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.total) return;
+    const int To = p.T * p.s, Cout = p.Cin / 2, K = 2 * p.s;
+    const int n = (int)(i % To); const size_t bg = i / To;
+    const int g = (int)(bg % Cout); const size_t b = bg / Cout;
+    const int t = n / p.s, r = n - t * p.s;
+    const float * x0 = p.x + (b * p.Cin + 2 * g) * p.T, * x1 = x0 + p.T;
+    const float * w0 = p.w + (size_t)(2 * g) * K, * w1 = w0 + K;
+    float v = 0.0f;
+    if (t >= 1) {
+        const float a0 = half_snake(x0[t - 1], 2 * g, p.alpha, p.n_alpha), a1 = half_snake(x1[t - 1], 2 * g + 1, p.alpha, p.n_alpha);
+        v += w0[r + p.s] * a0 + w1[r + p.s] * a1;
+    }
+    {
+        const float a0 = half_snake(x0[t], 2 * g, p.alpha, p.n_alpha), a1 = half_snake(x1[t], 2 * g + 1, p.alpha, p.n_alpha);
+        v += w0[r] * a0 + w1[r] * a1;
+    }
+    p.y[i] = v + p.bias[g];
+}
+
+// HalfSnake -> causal conv (C -> 1, K taps) -> tanh  (nano-codec.cpp:703-712)
+struct PostParams { const float * x; const float * alpha; int n_alpha; const float * w; const float * bias; float * pcm; int C, K, T; size_t total; };
+__global__ void post_kernel(const PostParams p) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.total) return;
+    const int t = (int)(i % p.T); const size_t b = i / p.T;
+    float acc = 0.0f;
+    for (int c = 0; c < p.C; c++) {
+        const float * xr = p.x + (b * p.C + c) * p.T;
+        for (int k = 0; k < p.K; k++) {
+            const int tt = t - (p.K - 1 - k);
+            if (tt < 0) continue;
+            acc = fmaf(f16r(p.w[c * p.K + k]), f16r(half_snake(xr[tt], c, p.alpha, p.n_alpha)), acc);
+        }
+    }
+    p.pcm[i] = tanhf(acc + p.bias[0]);
+}
+
+bool ensure_consts() {
+    static uint64_t done = 0;
+    int dev = 0;
+    MGB_CUDA_TRY(cudaGetDevice(&dev));
+    if (done >> dev & 1) return true;
+    float lut[4][8] = {};
+    for (int d = 0; d < 4; d++) {
+        const int half = h_fsq_levels[d] / 2;
+        for (int n = 0; n < h_fsq_levels[d]; n++) lut[d][n] = (float)(n - half) / (float)half;   // nano-codec.cpp:739-741
+    }
+    MGB_CUDA_TRY(cudaMemcpyToSymbol(c_fsq_lut, lut, sizeof(lut)));
+    MGB_CUDA_TRY(cudaMemcpyToSymbol(c_fsq_base, h_fsq_base, sizeof(h_fsq_base)));
+    MGB_CUDA_TRY(cudaMemcpyToSymbol(c_fsq_levels, h_fsq_levels, sizeof(h_fsq_levels)));
+    done |= 1ull << dev;
+    return true;
+}
+
+inline int pad64(int c) { return (c + 63) / 64 * 64; }
+
+bool launch_conv(const ConvParams & p, int B, cudaStream_t stream) {
+    const int halo = (p.K - 1) * p.dil;
+    const bool big = p.Cout > 64;
+    const int CO_T = big ? 64 : 32;
+    const size_t smem = (size_t)kConvCI * (kConvTT + halo) * 4 + (size_t)kConvCI * p.K * CO_T * 2;
+    dim3 grid((p.T + kConvTT - 1) / kConvTT, (p.Cout + CO_T - 1) / CO_T, B);
+    if (big) conv1d_kernel<8><<<grid, 256, smem, stream>>>(p);
+    else conv1d_kernel<4><<<grid, 256, smem, stream>>>(p);
+    MGB_LAUNCH_CHECK();
+    return true;
+}
+
+}  // namespace
+
+bool codec_fsq_device(const int32_t * d_codes, int B, int T, float * d_latent, cudaStream_t stream) {
+    if (!ensure_consts()) return false;
+    const size_t total = (size_t)B * 8 * T;
+    fsq_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(d_codes, d_latent, T, total);
+    MGB_LAUNCH_CHECK();
+    return true;
+}
+
+// f16 tap-major copies of a conv weight (PyTorch (Cout, Cin, K) f32 on device) -> [Cin][K][CoPad] half
+__global__ void repack_conv_w_kernel(const float * w, __half * out, int Cout, int Cin, int K, int CoPad) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)Cin * K * CoPad;
+    if (i >= total) return;
+    const int co = (int)(i % CoPad); const size_t r = i / CoPad;
+    const int k = (int)(r % K), ci = (int)(r / K);
+    out[i] = co < Cout ? __float2half_rn(w[((size_t)co * Cin + ci) * K + k]) : __float2half_rn(0.0f);
+}
+
+static bool repack(Codec & c, const float * w, int Cout, int Cin, int K, void ** out, cudaStream_t stream) {
+    if (*out) return true;
+    const int CoPad = pad64(Cout);
+    const size_t total = (size_t)Cin * K * CoPad;
+    void * d = nullptr;
+    MGB_CUDA_TRY(cudaMalloc(&d, total * 2));
+    c.allocations.push_back(d);
+    repack_conv_w_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(w, (__half *)d, Cout, Cin, K, CoPad);
+    MGB_LAUNCH_CHECK();
+    *out = d;
+    return true;
+}
+
+// Decode B utterances of T frames each: codes [B][8][T] (device) -> pcm [B][T*1024] (device).
+bool codec_decode_device(Codec & c, const int32_t * d_codes, int B, int T, float * d_pcm, cudaStream_t stream) {
+    if (!ensure_consts()) return false;
+    // one-time f16 weight repack (ggml_conv_1d converts the kernel to f16)
+    if (!c.pre_w16) {
+        if (!repack(c, c.pre_w, c.base_ch, c.latent, c.pre_k, &c.pre_w16, stream)) return false;
+        int C = c.base_ch;
+        for (int i = 0; i < 5; i++) {
+            C /= 2;
+            for (int j = 0; j < 3; j++)
+                for (int k = 0; k < 3; k++) {
+                    CodecResBlock & b = c.rb[i][j][k];
+                    if (!repack(c, b.in_w, C, C, c.res_k[j], &b.in_w16, stream)) return false;
+                    if (!repack(c, b.sk_w, C, C, c.res_k[j], &b.sk_w16, stream)) return false;
+                }
+        }
+    }
+    // scratch: 6 buffers of the largest stage tensor (C*T is maximal, and equal, for stages 2-4)
+    size_t need = 0;
+    {
+        int C = c.base_ch, Tc = T;
+        need = (size_t)C * Tc;
+        for (int i = 0; i < 5; i++) { C /= 2; Tc *= c.up_rates[i]; need = std::max(need, (size_t)C * Tc); }
+        need *= (size_t)B;
+    }
+    if (need > c.buf_elems) {
+        for (auto & b : c.buf) { if (b) cudaFree(b); b = nullptr; }
+        c.buf_elems = 0;
+        for (auto & b : c.buf) MGB_CUDA_TRY(cudaMalloc((void **)&b, need * sizeof(float)));
+        c.buf_elems = need;
+    }
+    float * cur = c.buf[0], * up = c.buf[1], * o = c.buf[2], * act = c.buf[3], * act2 = c.buf[4], * sum = c.buf[5];
+
+    // FSQ -> latent (into `act`), pre-conv 32 -> 864 (im2col rounding applied while staging)
+    if (!codec_fsq_device(d_codes, B, T, act, stream)) return false;
+    {
+        ConvParams p = {};
+        p.xa = act; p.w = (const __half *)c.pre_w16; p.bias = c.pre_b; p.y = cur; p.round_in = 1;
+        p.Cin = c.latent; p.Cout = c.base_ch; p.CoPad = pad64(c.base_ch); p.K = c.pre_k; p.dil = 1; p.T = T;
+        if (!launch_conv(p, B, stream)) return false;
+    }
+    int C = c.base_ch, Tc = T;
+    for (int i = 0; i < 5; i++) {
+        const int s = c.up_rates[i], Co = C / 2, To = Tc * s;
+        {
+            UpParams u = {};
+            u.x = cur; u.alpha = c.act_alpha[i]; u.n_alpha = c.n_alpha_act[i]; u.w = c.up_w[i]; u.bias = c.up_b[i];
+            u.y = up; u.Cin = C; u.T = Tc; u.s = s; u.total = (size_t)B * Co * To;
+            snake_convt_kernel<<<(unsigned)((u.total + 255) / 256), 256, 0, stream>>>(u);
+            MGB_LAUNCH_CHECK();
+        }
+        const size_t total = (size_t)B * Co * To;
+        for (int j = 0; j < 3; j++) {
+            const float * oin = up;
+            {   // activated input of the first block of this branch
+                SnakeParams sp = {};
+                sp.x = up; sp.y[0] = act; sp.alpha[0] = c.rb[i][j][0].in_alpha; sp.n_alpha = c.n_alpha_rb[i]; sp.n_out = 1;
+                sp.C = Co; sp.T = To; sp.total = total;
+                snake_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(sp);
+                MGB_LAUNCH_CHECK();
+            }
+            for (int k = 0; k < 3; k++) {
+                const CodecResBlock & rb = c.rb[i][j][k];
+                ConvParams p1 = {};
+                p1.xa = act; p1.w = (const __half *)rb.in_w16; p1.bias = rb.in_b;
+                p1.ya = act2; p1.alpha2 = rb.sk_alpha; p1.n_alpha2 = c.n_alpha_rb[i];
+                p1.Cin = Co; p1.Cout = Co; p1.CoPad = pad64(Co); p1.K = c.res_k[j]; p1.dil = c.res_dil[k]; p1.T = To;
+                if (!launch_conv(p1, B, stream)) return false;
+                ConvParams p2 = {};
+                p2.xa = act2; p2.w = (const __half *)rb.sk_w16; p2.bias = rb.sk_b; p2.res = oin;
+                p2.Cin = Co; p2.Cout = Co; p2.CoPad = pad64(Co); p2.K = c.res_k[j]; p2.dil = 1; p2.T = To;
+                if (k < 2) {
+                    p2.y = o;      // for k = 1 res and y alias: each element is read then written by the same thread
+                    p2.ya = act; p2.alpha2 = c.rb[i][j][k + 1].in_alpha; p2.n_alpha2 = c.n_alpha_rb[i];
+                } else {
+                    p2.sum_in = sum; p2.sum_out = sum; p2.sum_mode = j == 0 ? 1 : (j == 1 ? 2 : 3);
+                }
+                if (!launch_conv(p2, B, stream)) return false;
+                oin = o;
+            }
+        }
+        std::swap(cur, sum);      // cur = mean of the three branches
+        C = Co; Tc = To;
+    }
+    {
+        PostParams pp = {};
+        pp.x = cur; pp.alpha = c.post_alpha; pp.n_alpha = c.n_alpha_post; pp.w = c.post_w; pp.bias = c.post_b;
+        pp.pcm = d_pcm; pp.C = C; pp.K = c.post_k; pp.T = Tc; pp.total = (size_t)B * Tc;
+        post_kernel<<<(unsigned)((pp.total + 255) / 256), 256, 0, stream>>>(pp);
+        MGB_LAUNCH_CHECK();
+    }
+    c.buf[0] = cur; c.buf[5] = sum;
+    return true;
+}
+
+}  // namespace mgb

@@ -1,0 +1,96 @@
+// Launch wrappers of the sm_100a kernels (host-callable). All launches are asynchronous on
+// `stream`; every wrapper returns false (with the thread error set) if the launch failed.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "model.h"
+
+namespace mgb {
+
+// ---- generic "tokens" view ---------------------------------------------------------------------
+// A launch processes M tokens (rows). tok_utt[t] = utterance, tok_pos[t] = position inside that
+// utterance's sequence, tok_slot[t] = row of the token in the per-layer KV storage.
+struct Tokens {
+    int M = 0;
+    const int32_t * utt = nullptr;
+    const int32_t * pos = nullptr;
+    const int32_t * slot = nullptr;
+};
+
+enum { ACT_NONE = 0, ACT_GELU = 1 };
+
+struct LinearArgs {
+    DevMat W;                       // [taps][N][K]
+    int precision = 0;
+    const float * X = nullptr; int ldx = 0;      // [M][ldx] (compact rows)
+    const float * ln_w = nullptr; float eps = 1e-5f;   // LayerNorm prologue (no bias) if non-null
+    const float * bias = nullptr;
+    const float * res = nullptr; int ldr = 0;    // residual added in the epilogue
+    float * Y = nullptr; int ldy = 0;
+    int act = ACT_NONE, gelu_f16 = 1;
+    const int32_t * tok_pos = nullptr;           // taps > 1: shifted rows valid iff tok_pos[t] >= shift
+    // split store (QKV / cross KV): outputs [0,n_q) -> Y, [n_q, n_q+dkv) -> kdst, rest -> vdst,
+    // at row tok_slot[t] of the KV storage (element type = model weight dtype)
+    int n_q = -1, dkv = 0;
+    void * kdst = nullptr; void * vdst = nullptr;
+    const int32_t * tok_slot = nullptr;
+    int M = 0;
+};
+bool launch_linear(const LinearArgs & a, cudaStream_t stream);
+
+struct AttnArgs {
+    int precision = 0;
+    const float * q = nullptr; int ldq = 0;      // [M][ldq], head h at column h*dh
+    const void * K = nullptr; const void * V = nullptr;   // [utt][rows_per_utt][H*dh]
+    int rows_per_utt = 0;
+    int H = 1, dh = 64;
+    int causal = 1;                              // keys 0..tok_pos[t]; else keys 0..n_ctx[utt]-1
+    const int32_t * n_ctx = nullptr;
+    Tokens tok;
+    float * out = nullptr; int ldo = 0;
+};
+bool launch_attention(const AttnArgs & a, cudaStream_t stream);
+
+// x[t] = (sum_cb E_cb[codes[utt][cb]]) * 1/8 + dec_pos[pos]        (magpie.cpp:2746-2787, 4376-4379)
+bool launch_audio_embed(const Model & m, const int32_t * codes /*[B][8] device*/, const int32_t * pos /*[B]*/,
+                        int B, float * x, cudaStream_t stream);
+// x[t] = baked_ctx[speaker[utt]][pos] + dec_pos[pos]               (magpie.cpp:4139-4165, 4228)
+bool launch_context_embed(const Model & m, const int32_t * speakers, Tokens tok, float * x, cudaStream_t stream);
+// x[t] = text_emb[token[t]] + enc_pos[pos]                         (magpie.cpp:1319-1345, 1974-1975)
+bool launch_text_embed(const Model & m, const int32_t * tokens /*[M] compact*/, Tokens tok, float * x, cudaStream_t stream);
+// y[t] = LN(x[t]) * w                                              (magpie.cpp:2237-2259)
+bool launch_layer_norm(const float * x, const float * w, float eps, int M, int d, float * y, cudaStream_t stream);
+bool launch_add_one(int32_t * v, int n, cudaStream_t stream);
+
+// ---- local transformer + sampler (magpie.cpp:946-1048, 1072-1317) ------------------------------
+struct LtArgs {
+    int B = 0;
+    const float * hidden = nullptr;      // [B][d] device
+    float temperature = 0.0f; int top_k = 80;
+    const uint8_t * forbid_eos = nullptr;   // [B] device or null
+    int forbid_eos_all = 0;                 // applies to every utterance (generation loop: step < 4)
+    const int32_t * forced = nullptr;    // [B][8] device or null
+    const float * uniforms = nullptr;    // [B][8] device or null
+    uint64_t seed = 0; uint32_t step = 0;
+    int32_t * sampled = nullptr;         // [B][8] device: the model's picks
+    int32_t * next_codes = nullptr;      // [B][8] device: codes the next decoder step consumes (forced or picked)
+    int32_t * argmax = nullptr;          // [B][8] device
+    float * logits = nullptr;            // [B][8][V] device or null
+    int32_t * eos_flag = nullptr;        // [B] device or null: set to 1 when sampled/argmax hits EOS
+    // loop mode (d_step != null): step = *d_step; per-step arrays are laid out [B][T_total][...] and
+    // forced / uniforms / logits / sampled / argmax are indexed at (utt*T_total + step); `next_codes`
+    // stays [B][8].  forbid_eos applies while step < min_frames.  done_step[utt] (init -1) records the
+    // first step at which EOS was hit; hidden_hist (optional) receives the hidden state [B][T_total][d].
+    const int32_t * d_step = nullptr;
+    int T_total = 0, min_frames = 0;
+    int32_t * done_step = nullptr;
+    float * hidden_hist = nullptr;
+};
+bool launch_local_transformer(const Model & m, const LtArgs & a, cudaStream_t stream);
+
+// ---- nano-codec ---------------------------------------------------------------------------------
+bool codec_decode_device(Codec & c, const int32_t * d_codes, int B, int T, float * d_pcm, cudaStream_t stream);
+bool codec_fsq_device(const int32_t * d_codes, int B, int T, float * d_latent, cudaStream_t stream);
+
+}  // namespace mgb

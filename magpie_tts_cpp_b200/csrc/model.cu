@@ -1,0 +1,319 @@
+// GGUF -> device weights.  Name mapping follows the reference loader's precedence
+// (src/magpie.cpp:501-562, 607-667 and src/nano-codec.cpp:84-199).
+#include "model.h"
+
+#include <cstring>
+#include <memory>
+
+#include "common.cuh"
+
+namespace mgb {
+
+thread_local int64_t g_launch_counter = 0;
+static thread_local std::string g_error;
+void set_error(const std::string & msg) { g_error = msg; }
+const std::string & get_error() { return g_error; }
+
+namespace {
+
+struct Uploader {
+    std::vector<void *> & allocs;
+    bool ok = true;
+    void * raw(const void * host, size_t bytes) {
+        void * d = nullptr;
+        if (cudaMalloc(&d, bytes ? bytes : 16) != cudaSuccess) { ok = false; set_error("cudaMalloc failed"); return nullptr; }
+        allocs.push_back(d);
+        if (bytes && cudaMemcpy(d, host, bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
+            ok = false; set_error("cudaMemcpy H2D failed"); return nullptr;
+        }
+        return d;
+    }
+    float * f32(const std::vector<float> & v) { return (float *)raw(v.data(), v.size() * 4); }
+    // weight matrix in the model dtype
+    void * weights(const std::vector<float> & v, int precision) {
+        if (precision == MGB_PREC_F32) return raw(v.data(), v.size() * 4);
+        std::vector<__nv_bfloat16> h(v.size());
+        for (size_t i = 0; i < v.size(); i++) h[i] = __float2bfloat16_rn(v[i]);
+        return raw(h.data(), h.size() * 2);
+    }
+};
+
+bool to_f32(const GgufTensor & t, std::vector<float> & out) {
+    out.resize((size_t)t.nelements());
+    if (!gguf_to_f32(t, out.data())) { set_error("tensor '" + t.name + "': unsupported ggml type " + std::to_string(t.type)); return false; }
+    return true;
+}
+
+int parse_idx(const char * name, const char * prefix) {
+    const char * p = strstr(name, prefix);
+    return p ? atoi(p + strlen(prefix)) : -1;
+}
+
+// Linear (out,in) or conv (out,in,k): ggml ne = [in,out] / [k,in,out].  k>1 is re-laid out
+// tap-major [k][out][in] so every tap is a contiguous row-major matrix.
+bool make_mat(Uploader & up, const GgufTensor & t, int precision, DevMat & m) {
+    std::vector<float> v;
+    if (!to_f32(t, v)) return false;
+    if (t.n_dims == 3 && t.ne[0] > 1) {
+        int k = (int)t.ne[0], in = (int)t.ne[1], out = (int)t.ne[2];
+        std::vector<float> r(v.size());
+        for (int o = 0; o < out; o++)
+            for (int i = 0; i < in; i++)
+                for (int kk = 0; kk < k; kk++)
+                    r[((size_t)kk * out + o) * in + i] = v[((size_t)o * in + i) * k + kk];
+        m.N = out; m.K = in; m.taps = k;
+        m.w = up.weights(r, precision);
+    } else if (t.n_dims == 3) {
+        m.N = (int)t.ne[2]; m.K = (int)t.ne[1]; m.taps = 1;
+        m.w = up.weights(v, precision);
+    } else {
+        m.N = (int)t.ne[1]; m.K = (int)t.ne[0]; m.taps = 1;
+        m.w = up.weights(v, precision);
+    }
+    if (m.K % 8 != 0) { set_error("tensor '" + t.name + "': inner dim must be a multiple of 8"); return false; }
+    return up.ok;
+}
+
+bool make_vec(Uploader & up, const GgufTensor & t, float *& dst, int * rows = nullptr) {
+    std::vector<float> v;
+    if (!to_f32(t, v)) return false;
+    dst = up.f32(v);
+    if (rows) *rows = (int)(t.n_dims >= 2 ? t.ne[1] : 1);
+    return up.ok;
+}
+
+}  // namespace
+
+Model::~Model() {
+    cudaSetDevice(device);
+    for (void * p : allocations) cudaFree(p);
+}
+
+Model * load_model(const char * path, int device, int precision) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        set_error("no CUDA device available (this build has no CPU fallback)");
+        return nullptr;
+    }
+    if (device < 0 || device >= ndev) { set_error("invalid device index"); return nullptr; }
+    if (precision != MGB_PREC_F32 && precision != MGB_PREC_BF16) { set_error("invalid precision"); return nullptr; }
+    if (cudaSetDevice(device) != cudaSuccess) { set_error("cudaSetDevice failed"); return nullptr; }
+
+    GgufFile f;
+    std::string err;
+    if (!f.open(path, err)) { set_error(std::string("magpie_init: ") + err); return nullptr; }
+
+    std::unique_ptr<Model> M(new Model());
+    M->device = device; M->precision = precision; M->wsize = precision == MGB_PREC_F32 ? 4 : 2;
+    mgb_hparams & hp = M->hp;
+    // defaults = reference struct initialisers (magpie.h:35-80); keys as read at magpie.cpp:85-120
+#define HP(field, def) hp.field = f.get_u32("magpie." #field, def)
+    HP(d_model, 768); HP(d_ffn, 3072); HP(d_head, 64);
+    HP(enc_layers, 6); HP(enc_heads, 12); HP(enc_kernel, 3);
+    HP(dec_layers, 12); HP(dec_sa_heads, 12); HP(dec_xa_heads, 1); HP(dec_xa_d_head, 128); HP(dec_kernel, 1);
+    HP(lt_dim, 256); HP(lt_ffn_dim, 1024); HP(lt_layers, 1); HP(lt_heads, 1);
+    HP(text_vocab_size, 2380); HP(num_codebooks, 8); HP(codebook_size, 2016); HP(vocab_per_cb, 2024);
+    HP(num_speakers, 5); HP(context_frames, 110);
+    HP(text_bos_id, 2378); HP(text_eos_id, 2379); HP(audio_bos_id, 2016); HP(audio_eos_id, 2017);
+    HP(max_dec_steps, 500); HP(sample_rate, 22050);
+#undef HP
+    hp.eps = f.get_f32("magpie.eps", 1e-5f);
+    if (hp.num_codebooks != 8 || hp.lt_layers != 1 || hp.lt_heads != 1 || hp.dec_kernel != 1 ||
+        hp.enc_kernel > 3 || hp.d_model % 8 || hp.d_model > 1024 || hp.lt_dim > 256 || hp.lt_dim % 8 ||
+        hp.dec_xa_heads != 1 || hp.dec_xa_d_head != 128 || hp.d_model / hp.dec_sa_heads != 64 ||
+        hp.d_model / hp.enc_heads != 64 || hp.lt_ffn_dim > 1024 || hp.vocab_per_cb > 2048) {
+        set_error("magpie_init: unsupported architecture hyper-parameters for the sm_100a kernels");
+        return nullptr;
+    }
+    for (const char * k : {"magpie.tokenizer.vocab", "magpie.tokenizer.dict"})
+        if (const std::string * s = f.get_str(k)) M->meta_str[k] = *s;
+    for (const char * k : {"magpie.tokenizer.pad", "magpie.tokenizer.oov", "magpie.tokenizer.space"})
+        if (f.find(k)) M->meta_u32[k] = f.get_u32(k, -1);
+
+    M->enc.resize(hp.enc_layers);
+    M->dec.resize(hp.dec_layers);
+    Uploader up{M->allocations};
+    for (const GgufTensor & t : f.tensors()) {
+        const char * name = t.name.c_str();
+        bool ok = true;
+        if (!strcmp(name, "text_embedding.weight")) ok = make_vec(up, t, M->text_emb);
+        else if (strstr(name, "audio_embeddings.")) {
+            int cb = parse_idx(name, "audio_embeddings.");
+            if (cb >= 0 && cb < 8) ok = make_vec(up, t, M->audio_emb[cb]);
+        } else if (!strcmp(name, "baked_context_embedding.weight")) ok = make_vec(up, t, M->baked_ctx);
+        else if (!strcmp(name, "encoder.position_embeddings.weight")) ok = make_vec(up, t, M->enc_pos, &M->enc_pos_rows);
+        else if (strstr(name, "encoder.layers.")) {     // NB: matched before decoder.layers, as the reference
+            int l = parse_idx(name, "encoder.layers.");
+            if (l >= 0 && l < hp.enc_layers) {
+                EncLayer & L = M->enc[l];
+                if (strstr(name, "norm_self.weight")) ok = make_vec(up, t, L.norm_self);
+                else if (strstr(name, "self_attention.qkv_net.weight")) ok = make_mat(up, t, precision, L.qkv);
+                else if (strstr(name, "self_attention.o_net.weight")) ok = make_mat(up, t, precision, L.o);
+                else if (strstr(name, "norm_pos_ff.weight")) ok = make_vec(up, t, L.norm_ff);
+                else if (strstr(name, "pos_ff.proj.conv.weight")) ok = make_mat(up, t, precision, L.ff1);
+                else if (strstr(name, "pos_ff.o_net.conv.weight")) ok = make_mat(up, t, precision, L.ff2);
+            }
+        } else if (!strcmp(name, "encoder.norm_out.weight")) ok = make_vec(up, t, M->enc_norm_out);
+        else if (!strcmp(name, "decoder.position_embeddings.weight")) ok = make_vec(up, t, M->dec_pos, &M->dec_pos_rows);
+        else if (strstr(name, "decoder.layers.")) {
+            int l = parse_idx(name, "decoder.layers.");
+            if (l >= 0 && l < hp.dec_layers) {
+                DecLayer & L = M->dec[l];
+                if (strstr(name, "norm_self.weight")) ok = make_vec(up, t, L.norm_self);
+                else if (strstr(name, "self_attention.qkv_net.weight")) ok = make_mat(up, t, precision, L.qkv);
+                else if (strstr(name, "self_attention.o_net.weight")) ok = make_mat(up, t, precision, L.o);
+                else if (strstr(name, "norm_xattn_query.weight")) ok = make_vec(up, t, L.norm_xa_q);
+                else if (strstr(name, "cross_attention.q_net.weight")) ok = make_mat(up, t, precision, L.xq);
+                else if (strstr(name, "cross_attention.kv_net.weight")) ok = make_mat(up, t, precision, L.xkv);
+                else if (strstr(name, "cross_attention.o_net.weight")) ok = make_mat(up, t, precision, L.xo);
+                else if (strstr(name, "norm_xattn_memory.weight")) ok = make_vec(up, t, L.norm_xa_mem);
+                else if (strstr(name, "norm_pos_ff.weight")) ok = make_vec(up, t, L.norm_ff);
+                else if (strstr(name, "pos_ff.proj.conv.weight")) ok = make_mat(up, t, precision, L.ff1);
+                else if (strstr(name, "pos_ff.o_net.conv.weight")) ok = make_mat(up, t, precision, L.ff2);
+            }
+        } else if (!strcmp(name, "decoder.norm_out.weight")) ok = make_vec(up, t, M->dec_norm_out);
+        else if (!strcmp(name, "final_proj.weight")) ok = make_mat(up, t, precision, M->final_w);
+        else if (!strcmp(name, "final_proj.bias")) ok = make_vec(up, t, M->final_b);
+        else if (strstr(name, "local_transformer_in_projection.weight")) ok = make_mat(up, t, precision, M->lt_in_w);
+        else if (strstr(name, "local_transformer_in_projection.bias")) ok = make_vec(up, t, M->lt_in_b);
+        else if (!strcmp(name, "local_transformer.position_embeddings.weight")) ok = make_vec(up, t, M->lt_pos, &M->lt_pos_rows);
+        else if (strstr(name, "local_transformer.layers.0.norm_self.weight")) ok = make_vec(up, t, M->lt_norm_self);
+        else if (strstr(name, "local_transformer.layers.0.self_attention.qkv_net.weight")) ok = make_mat(up, t, precision, M->lt_qkv);
+        else if (strstr(name, "local_transformer.layers.0.self_attention.o_net.weight")) ok = make_mat(up, t, precision, M->lt_o);
+        else if (strstr(name, "local_transformer.layers.0.norm_pos_ff.weight")) ok = make_vec(up, t, M->lt_norm_ff);
+        else if (strstr(name, "local_transformer.layers.0.pos_ff.proj.conv.weight")) ok = make_mat(up, t, precision, M->lt_ff1);
+        else if (strstr(name, "local_transformer.layers.0.pos_ff.o_net.conv.weight")) ok = make_mat(up, t, precision, M->lt_ff2);
+        else if (strstr(name, "local_transformer_out_projections.")) {
+            int cb = parse_idx(name, "local_transformer_out_projections.");
+            if (cb >= 0 && cb < 8) {
+                if (strstr(name, ".weight")) ok = make_mat(up, t, precision, M->lt_out_w[cb]);
+                else if (strstr(name, ".bias")) ok = make_vec(up, t, M->lt_out_b[cb]);
+            }
+        }
+        // anything else (context_encoder.* etc.) is loaded-but-unused in the reference: skipped here
+        if (!ok || !up.ok) return nullptr;
+    }
+
+    // completeness check: every slot the hot path touches must be present
+    bool complete = M->text_emb && M->baked_ctx && M->enc_pos && M->dec_pos && M->lt_pos && M->enc_norm_out &&
+                    M->dec_norm_out && M->lt_in_w.w && M->lt_in_b && M->lt_norm_self && M->lt_norm_ff &&
+                    M->lt_qkv.w && M->lt_o.w && M->lt_ff1.w && M->lt_ff2.w;
+    for (int cb = 0; cb < 8; cb++) complete = complete && M->audio_emb[cb] && M->lt_out_w[cb].w && M->lt_out_b[cb];
+    for (auto & L : M->enc) complete = complete && L.norm_self && L.norm_ff && L.qkv.w && L.o.w && L.ff1.w && L.ff2.w;
+    for (auto & L : M->dec)
+        complete = complete && L.norm_self && L.norm_xa_q && L.norm_xa_mem && L.norm_ff && L.qkv.w && L.o.w &&
+                   L.xq.w && L.xkv.w && L.xo.w && L.ff1.w && L.ff2.w;
+    if (!complete) { set_error("magpie_init: model file is missing tensors of the synthesis path"); return nullptr; }
+    if (M->dec_pos_rows < hp.context_frames + 2) { set_error("magpie_init: decoder position table too short"); return nullptr; }
+
+    // unique weight bytes one generated frame reads: decoder matrices + LT matrices
+    int64_t el = 0, f32b = 0;
+    for (auto & L : M->dec) {
+        for (const DevMat * m : {&L.qkv, &L.o, &L.xq, &L.xo, &L.ff1, &L.ff2}) el += (int64_t)m->N * m->K * m->taps;
+        f32b += 3 * hp.d_model * 4;
+    }
+    f32b += hp.d_model * 4;
+    for (const DevMat * m : {&M->lt_in_w, &M->lt_qkv, &M->lt_o, &M->lt_ff1, &M->lt_ff2}) el += (int64_t)m->N * m->K;
+    for (int cb = 0; cb < 8; cb++) { el += (int64_t)M->lt_out_w[cb].N * M->lt_out_w[cb].K; f32b += M->lt_out_w[cb].N * 4; }
+    f32b += (hp.lt_dim * 3 + 8 * hp.lt_dim) * 4 + 8 * hp.d_model * 4;
+    M->step_weight_bytes = el * (int64_t)M->wsize + f32b;
+    return M.release();
+}
+
+// ---------------------------------------------------------------------------------------------
+// nano-codec
+// ---------------------------------------------------------------------------------------------
+Codec::~Codec() {
+    cudaSetDevice(device);
+    for (void * p : allocations) cudaFree(p);
+    for (auto & b : buf) if (b) cudaFree(b);
+    if (d_codes) cudaFree(d_codes);
+    if (d_pcm) cudaFree(d_pcm);
+    if (ev0) cudaEventDestroy((cudaEvent_t)ev0);
+    if (ev1) cudaEventDestroy((cudaEvent_t)ev1);
+    if (stream) cudaStreamDestroy((cudaStream_t)stream);
+}
+
+Codec * load_codec(const char * path, int device) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        set_error("no CUDA device available (this build has no CPU fallback)");
+        return nullptr;
+    }
+    if (device < 0 || device >= ndev) { set_error("invalid device index"); return nullptr; }
+    if (cudaSetDevice(device) != cudaSuccess) { set_error("cudaSetDevice failed"); return nullptr; }
+    GgufFile f;
+    std::string err;
+    if (!f.open(path, err)) { set_error(std::string("magpie_codec_init: ") + err); return nullptr; }
+    std::unique_ptr<Codec> C(new Codec());
+    C->device = device;
+    C->hp.sample_rate = f.get_u32("codec.sample_rate", 22050);        // nano-codec.cpp:77-81
+    C->hp.num_codebooks = f.get_u32("codec.num_codebooks", 8);
+    C->hp.codebook_size = f.get_u32("codec.codebook_size", 2016);
+    C->hp.hop_length = f.get_u32("codec.hop_length", 1024);
+    C->hp.latent_dim = f.get_u32("codec.latent_dim", 32);
+    if (C->hp.num_codebooks != 8 || C->hp.latent_dim != 32 || C->hp.hop_length != 1024) {
+        set_error("magpie_codec_init: unsupported codec hyper-parameters");
+        return nullptr;
+    }
+    Uploader up{C->allocations};
+    auto vec = [&](const GgufTensor & t, float *& dst, int * n = nullptr) {
+        std::vector<float> v;
+        if (!to_f32(t, v)) return false;
+        dst = up.f32(v);
+        if (n) *n = (int)v.size();
+        return up.ok;
+    };
+    for (const GgufTensor & t : f.tensors()) {
+        const char * name = t.name.c_str();
+        bool ok = true;
+        if (strstr(name, "dec.pre.weight")) { ok = vec(t, C->pre_w); C->pre_k = (int)t.ne[0]; C->latent = (int)t.ne[1]; C->base_ch = (int)t.ne[2]; }
+        else if (strstr(name, "dec.pre.bias")) ok = vec(t, C->pre_b);
+        else if (strstr(name, "dec.post.weight")) { ok = vec(t, C->post_w); C->post_k = (int)t.ne[0]; }
+        else if (strstr(name, "dec.post.bias")) ok = vec(t, C->post_b);
+        else if (strstr(name, "dec.post_act.alpha")) ok = vec(t, C->post_alpha, &C->n_alpha_post);
+        else if (strstr(name, "dec.up.")) {
+            int i = parse_idx(name, "dec.up.");
+            if (i >= 0 && i < 5) {
+                if (strstr(name, ".weight")) ok = vec(t, C->up_w[i]);
+                else if (strstr(name, ".bias")) ok = vec(t, C->up_b[i]);
+            }
+        } else if (strstr(name, "dec.act.") && strstr(name, "alpha")) {
+            int i = parse_idx(name, "dec.act.");
+            if (i >= 0 && i < 5) ok = vec(t, C->act_alpha[i], &C->n_alpha_act[i]);
+        } else if (strstr(name, "dec.rl.")) {
+            const char * p = strstr(name, "dec.rl.") + 7; int i = atoi(p);
+            const char * p2 = strstr(p, ".rb."); if (!p2) continue; p2 += 4; int j = atoi(p2);
+            const char * p3 = strstr(p2, ".rb."); if (!p3) continue; p3 += 4; int k = atoi(p3);
+            if (i < 0 || i >= 5 || j < 0 || j >= 3 || k < 0 || k >= 3) continue;
+            CodecResBlock & b = C->rb[i][j][k];
+            if (strstr(name, ".in_act.alpha")) ok = vec(t, b.in_alpha, &C->n_alpha_rb[i]);
+            else if (strstr(name, ".in_conv.weight")) ok = vec(t, b.in_w);
+            else if (strstr(name, ".in_conv.bias")) ok = vec(t, b.in_b);
+            else if (strstr(name, ".sk_act.alpha")) ok = vec(t, b.sk_alpha);
+            else if (strstr(name, ".sk_conv.weight")) ok = vec(t, b.sk_w);
+            else if (strstr(name, ".sk_conv.bias")) ok = vec(t, b.sk_b);
+        }
+        if (!ok || !up.ok) return nullptr;
+    }
+    bool complete = C->pre_w && C->pre_b && C->post_w && C->post_b && C->post_alpha;
+    for (int i = 0; i < 5; i++) {
+        complete = complete && C->act_alpha[i] && C->up_w[i] && C->up_b[i];
+        for (int j = 0; j < 3; j++)
+            for (int k = 0; k < 3; k++) {
+                const CodecResBlock & b = C->rb[i][j][k];
+                complete = complete && b.in_alpha && b.in_w && b.in_b && b.sk_alpha && b.sk_w && b.sk_b;
+            }
+    }
+    if (!complete) { set_error("magpie_codec_init: codec file is missing decoder tensors"); return nullptr; }
+    cudaStream_t st; cudaEvent_t e0, e1;
+    if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) {
+        set_error("magpie_codec_init: stream/event creation failed");
+        return nullptr;
+    }
+    C->stream = st; C->ev0 = e0; C->ev1 = e1;
+    return C.release();
+}
+
+}  // namespace mgb

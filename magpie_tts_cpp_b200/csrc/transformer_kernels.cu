@@ -1,0 +1,375 @@
+// Transformer building blocks of the synthesis path (text encoder, context prefill, decoder step):
+// fused LayerNorm -> skinny GEMV/GEMM -> bias/GELU/residual/KV-store epilogue, chunked online-softmax
+// attention over the resident KV cache, and the embedding gathers.
+//
+// Reference semantics restated (paths in the reference repo):
+//   LayerNorm           src/magpie.cpp:2237-2259      self-attention   src/magpie.cpp:1477-1575, 3395-3480
+//   cross-attention     src/magpie.cpp:1663-1767      conv-FFN         src/magpie.cpp:1769-1918
+//   embeddings          src/magpie.cpp:1319-1465, 2746-2787
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace mgb {
+
+namespace {
+
+constexpr int kLinThreads = 256;
+constexpr int kLinWarps = kLinThreads / 32;
+
+struct LinParams {
+    const void * W; int N, K, taps;
+    const float * X; int ldx;
+    const float * ln_w; float eps;
+    const float * bias;
+    const float * res; int ldr;
+    float * Y; int ldy;
+    int act, gelu_f16;
+    const int32_t * tok_pos;
+    int n_q, dkv;
+    void * kdst; void * vdst;
+    const int32_t * tok_slot;
+    int M;
+};
+
+// One CTA: MB input rows (staged in smem, LayerNorm applied) x (8 warps * RW) weight rows.
+// Each weight row is streamed exactly once per M-tile with 16-byte loads; fp32 accumulation.
+template <typename T, int MB, int RW>
+__global__ void __launch_bounds__(kLinThreads) linear_kernel(const LinParams p) {
+    extern __shared__ __align__(16) float xs[];       // [MB][K]
+    __shared__ float red[32];
+    constexpr int VEC = WT<T>::VEC;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m0 = blockIdx.y * MB;
+    const int row0 = (blockIdx.x * kLinWarps + warp) * RW;
+    const int K = p.K, N = p.N;
+
+    float acc[RW][MB];
+#pragma unroll
+    for (int r = 0; r < RW; r++)
+#pragma unroll
+        for (int m = 0; m < MB; m++) acc[r][m] = 0.0f;
+
+    for (int tap = 0; tap < p.taps; tap++) {
+        const int shift = p.taps - 1 - tap;
+        if (tap > 0) __syncthreads();
+        for (int m = 0; m < MB; m++) {
+            const int t = m0 + m;
+            const bool valid = t < p.M && (shift == 0 || p.tok_pos[t] >= shift);
+            const float * xr = p.X + (size_t)(valid ? t - shift : 0) * p.ldx;
+            float * xm = xs + m * K;
+            if (p.ln_w) {
+                float s = 0.0f;
+                for (int k = tid; k < K; k += kLinThreads) { float v = valid ? xr[k] : 0.0f; xm[k] = v; s += v; }
+                const float mean = block_sum(s, red) / (float)K;
+                float s2 = 0.0f;
+                for (int k = tid; k < K; k += kLinThreads) { float v = xm[k] - mean; xm[k] = v; s2 += v * v; }
+                const float var = block_sum(s2, red) / (float)K;
+                const float scale = 1.0f / sqrtf(var + p.eps);
+                for (int k = tid; k < K; k += kLinThreads) xm[k] = valid ? (xm[k] * scale) * p.ln_w[k] : 0.0f;
+            } else {
+                for (int k = tid; k < K; k += kLinThreads) xm[k] = valid ? xr[k] : 0.0f;
+            }
+        }
+        __syncthreads();
+        if (row0 < N) {
+            const T * wbase = (const T *)p.W + ((size_t)tap * N + row0) * K;
+            for (int k = lane * VEC; k < K; k += 32 * VEC) {
+                float w[RW][VEC];
+#pragma unroll
+                for (int r = 0; r < RW; r++) {
+                    if (row0 + r < N) WT<T>::load(wbase + (size_t)r * K + k, w[r]);
+                    else {
+#pragma unroll
+                        for (int v = 0; v < VEC; v++) w[r][v] = 0.0f;
+                    }
+                }
+#pragma unroll
+                for (int m = 0; m < MB; m++) {
+                    float x[VEC];
+#pragma unroll
+                    for (int v4 = 0; v4 < VEC; v4 += 4) {
+                        float4 xv = *reinterpret_cast<const float4 *>(xs + m * K + k + v4);
+                        x[v4] = xv.x; x[v4 + 1] = xv.y; x[v4 + 2] = xv.z; x[v4 + 3] = xv.w;
+                    }
+#pragma unroll
+                    for (int r = 0; r < RW; r++)
+#pragma unroll
+                        for (int v = 0; v < VEC; v++) acc[r][m] = fmaf(w[r][v], x[v], acc[r][m]);
+                }
+            }
+        }
+    }
+
+    float outv = 0.0f;
+#pragma unroll
+    for (int r = 0; r < RW; r++)
+#pragma unroll
+        for (int m = 0; m < MB; m++) {
+            float v = warp_sum(acc[r][m]);
+            if (lane == r * MB + m) outv = v;
+        }
+    if (lane < RW * MB) {
+        const int r = lane / MB, m = lane % MB;
+        const int n = row0 + r, t = m0 + m;
+        if (n < N && t < p.M) {
+            float v = outv;
+            if (p.bias) v += p.bias[n];
+            if (p.act == ACT_GELU) v = gelu_ggml(v, p.gelu_f16);
+            if (p.res) v += p.res[(size_t)t * p.ldr + n];
+            if (p.n_q < 0 || n < p.n_q) p.Y[(size_t)t * p.ldy + n] = v;
+            else {
+                const size_t slot = (size_t)p.tok_slot[t] * p.dkv;
+                const int c = n - p.n_q;
+                if (c < p.dkv) WT<T>::put((T *)p.kdst + slot + c, v);
+                else WT<T>::put((T *)p.vdst + slot + (c - p.dkv), v);
+            }
+        }
+    }
+}
+
+template <typename T, int MB, int RW>
+bool launch_linear_t(const LinParams & p, cudaStream_t stream) {
+    const size_t smem = (size_t)MB * p.K * sizeof(float);
+    static uint64_t attr_done = 0;                     // per-device bit (function attributes are per device)
+    int dev = 0;
+    MGB_CUDA_TRY(cudaGetDevice(&dev));
+    if (!(attr_done >> dev & 1)) {
+        MGB_CUDA_TRY(cudaFuncSetAttribute(linear_kernel<T, MB, RW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_done |= 1ull << dev;
+    }
+    if (smem > 200 * 1024) { set_error("linear: K too large for the staged input tile"); return false; }
+    dim3 grid((p.N + kLinWarps * RW - 1) / (kLinWarps * RW), (p.M + MB - 1) / MB);
+    linear_kernel<T, MB, RW><<<grid, kLinThreads, smem, stream>>>(p);
+    MGB_LAUNCH_CHECK();
+    return true;
+}
+
+template <typename T>
+bool launch_linear_p(const LinParams & p, cudaStream_t stream) {
+    // rows per warp: keep >= ~2 waves of CTAs for the small matrices
+    const int M = p.M;
+    if (M == 1) {
+        if (p.N >= 2048) return launch_linear_t<T, 1, 2>(p, stream);
+        return launch_linear_t<T, 1, 1>(p, stream);
+    }
+    if (M == 2) return launch_linear_t<T, 2, 2>(p, stream);
+    if (M <= 4) return launch_linear_t<T, 4, 2>(p, stream);
+    if (p.K > 4096) return launch_linear_t<T, 4, 4>(p, stream);      // smem budget for very wide inputs
+    return launch_linear_t<T, 8, 4>(p, stream);
+}
+
+// ---- attention ------------------------------------------------------------------------------------
+struct AttnParams {
+    const float * q; int ldq;
+    const void * K; const void * V;
+    int rows_per_utt, H, causal;
+    const int32_t * n_ctx;
+    const int32_t * utt; const int32_t * pos;
+    float * out; int ldo;
+};
+
+constexpr int kAttnWarps = 4;
+
+// grid (H, M), 128 threads.  Keys are processed in chunks of 32: lane j owns key j of the chunk for
+// the q.k dot (reads its whole row with 16-byte loads), then lanes own output dims for P.V with the
+// probabilities broadcast by shuffle.  Online softmax per warp, merged across the 4 warps at the end.
+template <typename T, int DH>
+__global__ void __launch_bounds__(kAttnWarps * 32) attention_kernel(const AttnParams p) {
+    constexpr int VEC = WT<T>::VEC;
+    constexpr int EPL = DH / 32;
+    __shared__ __align__(16) float sq[DH];
+    __shared__ float s_m[kAttnWarps], s_l[kAttnWarps];
+    __shared__ float s_acc[kAttnWarps][DH];
+    const int t = blockIdx.y, h = blockIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int utt = p.utt[t];
+    const int nk = p.causal ? p.pos[t] + 1 : p.n_ctx[utt];
+    const float scale = 1.0f / sqrtf((float)DH);
+    const int ld = p.H * DH;
+    if (tid < DH) sq[tid] = p.q[(size_t)t * p.ldq + h * DH + tid];
+    __syncthreads();
+    const T * Kb = (const T *)p.K + (size_t)utt * p.rows_per_utt * ld + h * DH;
+    const T * Vb = (const T *)p.V + (size_t)utt * p.rows_per_utt * ld + h * DH;
+
+    float mx = -INFINITY, l = 0.0f, acc[EPL];
+#pragma unroll
+    for (int e = 0; e < EPL; e++) acc[e] = 0.0f;
+
+    for (int c0 = warp * 32; c0 < nk; c0 += kAttnWarps * 32) {
+        const int j = c0 + lane;
+        float s = -INFINITY;
+        if (j < nk) {
+            const T * kr = Kb + (size_t)j * ld;
+            float d = 0.0f;
+#pragma unroll
+            for (int c = 0; c < DH; c += VEC) {
+                float kv[VEC];
+                uint4 u = *reinterpret_cast<const uint4 *>(kr + c);
+                if constexpr (VEC == 8) {
+                    kv[0] = bf16lo(u.x); kv[1] = bf16hi(u.x); kv[2] = bf16lo(u.y); kv[3] = bf16hi(u.y);
+                    kv[4] = bf16lo(u.z); kv[5] = bf16hi(u.z); kv[6] = bf16lo(u.w); kv[7] = bf16hi(u.w);
+                } else {
+                    kv[0] = __uint_as_float(u.x); kv[1] = __uint_as_float(u.y);
+                    kv[2] = __uint_as_float(u.z); kv[3] = __uint_as_float(u.w);
+                }
+#pragma unroll
+                for (int v = 0; v < VEC; v++) d = fmaf(kv[v], sq[c + v], d);
+            }
+            s = d * scale;
+        }
+        const float cm = warp_max(s);
+        const float mnew = fmaxf(mx, cm);
+        const float corr = expf(mx - mnew);            // mx = -inf -> 0
+        const float pj = (j < nk) ? expf(s - mnew) : 0.0f;
+        l = l * corr + warp_sum(pj);
+#pragma unroll
+        for (int e = 0; e < EPL; e++) acc[e] *= corr;
+        const int cnt = min(32, nk - c0);
+        for (int jj = 0; jj < cnt; jj++) {
+            const float pb = __shfl_sync(0xffffffffu, pj, jj);
+            const T * vr = Vb + (size_t)(c0 + jj) * ld + lane * EPL;
+#pragma unroll
+            for (int e = 0; e < EPL; e++) acc[e] = fmaf(pb, WT<T>::get(vr + e), acc[e]);
+        }
+        mx = mnew;
+    }
+    if (lane == 0) { s_m[warp] = mx; s_l[warp] = l; }
+#pragma unroll
+    for (int e = 0; e < EPL; e++) s_acc[warp][lane * EPL + e] = acc[e];
+    __syncthreads();
+    if (tid < DH) {
+        float M = s_m[0];
+#pragma unroll
+        for (int w = 1; w < kAttnWarps; w++) M = fmaxf(M, s_m[w]);
+        float L = 0.0f, o = 0.0f;
+#pragma unroll
+        for (int w = 0; w < kAttnWarps; w++) {
+            const float f = expf(s_m[w] - M);
+            L += f * s_l[w];
+            o += f * s_acc[w][tid];
+        }
+        p.out[(size_t)t * p.ldo + h * DH + tid] = o * (1.0f / L);
+    }
+}
+
+// ---- embeddings / LayerNorm -----------------------------------------------------------------------
+struct AudioEmbParams { const float * emb[8]; const float * pos; const int32_t * codes; const int32_t * p; float * x; int d; };
+
+__global__ void audio_embed_kernel(const AudioEmbParams a) {
+    const int b = blockIdx.x;
+    const int32_t * c = a.codes + b * 8;
+    const float * pr = a.pos + (size_t)a.p[b] * a.d;
+    for (int i = threadIdx.x; i < a.d; i += blockDim.x) {
+        float s = a.emb[0][(size_t)c[0] * a.d + i];
+#pragma unroll
+        for (int cb = 1; cb < 8; cb++) s = s + a.emb[cb][(size_t)c[cb] * a.d + i];
+        a.x[(size_t)b * a.d + i] = s * 0.125f + pr[i];
+    }
+}
+
+__global__ void context_embed_kernel(const float * ctx, const float * pos, const int32_t * speakers, const int32_t * utt,
+                                     const int32_t * tpos, float * x, int d, int C) {
+    const int t = blockIdx.x;
+    const int c = tpos[t];
+    const float * src = ctx + ((size_t)speakers[utt[t]] * C + c) * d;
+    const float * pr = pos + (size_t)c * d;
+    for (int i = threadIdx.x; i < d; i += blockDim.x) x[(size_t)t * d + i] = src[i] + pr[i];
+}
+
+__global__ void text_embed_kernel(const float * emb, const float * pos, const int32_t * tokens, const int32_t * tpos,
+                                  float * x, int d) {
+    const int t = blockIdx.x;
+    const float * src = emb + (size_t)tokens[t] * d;
+    const float * pr = pos + (size_t)tpos[t] * d;
+    for (int i = threadIdx.x; i < d; i += blockDim.x) x[(size_t)t * d + i] = src[i] + pr[i];
+}
+
+__global__ void __launch_bounds__(256) layer_norm_kernel(const float * x, const float * w, float eps, int d, float * y) {
+    __shared__ float red[32];
+    __shared__ float xs[1024];
+    const int t = blockIdx.x, tid = threadIdx.x;
+    const float * xr = x + (size_t)t * d;
+    float s = 0.0f;
+    for (int k = tid; k < d; k += 256) { float v = xr[k]; xs[k] = v; s += v; }
+    const float mean = block_sum(s, red) / (float)d;
+    float s2 = 0.0f;
+    for (int k = tid; k < d; k += 256) { float v = xs[k] - mean; xs[k] = v; s2 += v * v; }
+    const float var = block_sum(s2, red) / (float)d;
+    const float scale = 1.0f / sqrtf(var + eps);
+    for (int k = tid; k < d; k += 256) y[(size_t)t * d + k] = (xs[k] * scale) * w[k];
+}
+
+__global__ void add_one_kernel(int32_t * v, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] += 1;
+}
+
+}  // namespace
+
+bool launch_linear(const LinearArgs & a, cudaStream_t stream) {
+    if (a.M <= 0) return true;
+    LinParams p;
+    p.W = a.W.w; p.N = a.W.N; p.K = a.W.K; p.taps = a.W.taps;
+    p.X = a.X; p.ldx = a.ldx; p.ln_w = a.ln_w; p.eps = a.eps; p.bias = a.bias;
+    p.res = a.res; p.ldr = a.ldr; p.Y = a.Y; p.ldy = a.ldy; p.act = a.act; p.gelu_f16 = a.gelu_f16;
+    p.tok_pos = a.tok_pos; p.n_q = a.n_q; p.dkv = a.dkv; p.kdst = a.kdst; p.vdst = a.vdst;
+    p.tok_slot = a.tok_slot; p.M = a.M;
+    if (p.taps > 1 && !p.tok_pos) { set_error("linear: conv taps need token positions"); return false; }
+    if (a.precision == MGB_PREC_F32) return launch_linear_p<float>(p, stream);
+    return launch_linear_p<__nv_bfloat16>(p, stream);
+}
+
+bool launch_attention(const AttnArgs & a, cudaStream_t stream) {
+    if (a.tok.M <= 0) return true;
+    AttnParams p;
+    p.q = a.q; p.ldq = a.ldq; p.K = a.K; p.V = a.V; p.rows_per_utt = a.rows_per_utt; p.H = a.H;
+    p.causal = a.causal; p.n_ctx = a.n_ctx; p.utt = a.tok.utt; p.pos = a.tok.pos; p.out = a.out; p.ldo = a.ldo;
+    dim3 grid(a.H, a.tok.M);
+    const bool f32 = a.precision == MGB_PREC_F32;
+    if (a.dh == 64) {
+        if (f32) attention_kernel<float, 64><<<grid, kAttnWarps * 32, 0, stream>>>(p);
+        else attention_kernel<__nv_bfloat16, 64><<<grid, kAttnWarps * 32, 0, stream>>>(p);
+    } else if (a.dh == 128) {
+        if (f32) attention_kernel<float, 128><<<grid, kAttnWarps * 32, 0, stream>>>(p);
+        else attention_kernel<__nv_bfloat16, 128><<<grid, kAttnWarps * 32, 0, stream>>>(p);
+    } else { set_error("attention: unsupported head dim"); return false; }
+    MGB_LAUNCH_CHECK();
+    return true;
+}
+
+bool launch_audio_embed(const Model & m, const int32_t * codes, const int32_t * pos, int B, float * x, cudaStream_t stream) {
+    AudioEmbParams a;
+    for (int cb = 0; cb < 8; cb++) a.emb[cb] = m.audio_emb[cb];
+    a.pos = m.dec_pos; a.codes = codes; a.p = pos; a.x = x; a.d = m.hp.d_model;
+    audio_embed_kernel<<<B, 256, 0, stream>>>(a);
+    MGB_LAUNCH_CHECK();
+    return true;
+}
+
+bool launch_context_embed(const Model & m, const int32_t * speakers, Tokens tok, float * x, cudaStream_t stream) {
+    context_embed_kernel<<<tok.M, 256, 0, stream>>>(m.baked_ctx, m.dec_pos, speakers, tok.utt, tok.pos, x, m.hp.d_model,
+                                                    m.hp.context_frames);
+    MGB_LAUNCH_CHECK();
+    return true;
+}
+
+bool launch_text_embed(const Model & m, const int32_t * tokens, Tokens tok, float * x, cudaStream_t stream) {
+    text_embed_kernel<<<tok.M, 256, 0, stream>>>(m.text_emb, m.enc_pos, tokens, tok.pos, x, m.hp.d_model);
+    MGB_LAUNCH_CHECK();
+    return true;
+}
+
+bool launch_layer_norm(const float * x, const float * w, float eps, int M, int d, float * y, cudaStream_t stream) {
+    if (d > 1024) { set_error("layer_norm: d > 1024"); return false; }
+    layer_norm_kernel<<<M, 256, 0, stream>>>(x, w, eps, d, y);
+    MGB_LAUNCH_CHECK();
+    return true;
+}
+
+bool launch_add_one(int32_t * v, int n, cudaStream_t stream) {
+    add_one_kernel<<<(n + 127) / 128, 128, 0, stream>>>(v, n);
+    MGB_LAUNCH_CHECK();
+    return true;
+}
+
+}  // namespace mgb

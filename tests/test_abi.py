@@ -1,0 +1,64 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds, loads and exports every symbol
+include/magpie_b200.h declares, and refuses to run without a CUDA device (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def binding():
+    from magpie_tts_cpp_b200 import binding as b
+    if not os.path.exists(b.LIB_PATH):
+        b.build()
+    return b
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "magpie_b200.h")).read()
+    return sorted(set(re.findall(r"MGB_API[^;(]*?\b(mgb_\w+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(binding):
+    L = C.CDLL(binding.LIB_PATH)
+    declared = _header_symbols()
+    assert len(declared) >= 30
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in magpie_b200.h but not exported"
+    assert sorted(binding.SYMBOLS) == declared      # the python mirror binds exactly the header
+
+
+def test_header_cites_reference_interfaces():
+    src = open(os.path.join(ROOT, "include", "magpie_b200.h")).read()
+    for cite in ("magpie.cpp:777", "magpie.cpp:2284", "magpie.cpp:1113", "nano-codec.cpp:758", "nano-codec.cpp:721"):
+        assert cite in src
+
+
+def test_no_cpu_fallback(binding, tiny_model_path, codec_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by the gpu tests")
+    L = binding.lib()
+    assert L.mgb_device_count() == 0
+    with pytest.raises(binding.MagpieError, match="no CUDA device"):
+        binding.Model(tiny_model_path)
+    with pytest.raises(binding.MagpieError, match="no CUDA device"):
+        binding.Codec(codec_path)
+
+
+def test_product_never_imports_oracle():
+    """The oracle is test infrastructure: nothing under the package or include/ may reference it."""
+    bad = []
+    for base in ("magpie_tts_cpp_b200", "include"):
+        for dp, _, fns in os.walk(os.path.join(ROOT, base)):
+            if "build" in dp.split(os.sep):
+                continue
+            for fn in fns:
+                if fn.endswith((".py", ".cu", ".cuh", ".cpp", ".h", "Makefile")):
+                    txt = open(os.path.join(dp, fn), errors="replace").read()
+                    if re.search(r"\boracle\b|magpie_oracle|libmagpie_oracle", txt):
+                        bad.append(os.path.join(dp, fn))
+    assert not bad, bad
