@@ -32,7 +32,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 HELLO = [2378, 7, 4, 11, 11, 14, 32, 26, 22, 14, 17, 11, 3, 32, 28, 2379]   # "Hello, world!" (synthetic vocab)
-FRAMES = 500
+FRAMES = int(os.environ.get("MGB_BENCH_FRAMES", "500"))   # override only for profiling runs (not a bench value)
 METRIC = "decoder_frames_per_s"
 UNIT = "frames/s"
 
