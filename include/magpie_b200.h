@@ -153,6 +153,9 @@ MGB_API int mgb_teacher_forced(mgb_session * s, const int32_t * codes_in, int T,
  * on the session's stream, and the number of kernel launches it issued */
 MGB_API float   mgb_session_last_loop_ms(const mgb_session * s);
 MGB_API int64_t mgb_session_last_loop_launches(const mgb_session * s);
+/* profiling aid (sessions created with MGB_MEGA_DBG=1): clock64() stamps CTA 0 of the batch-1 decoder
+ * megakernel took around every grid barrier of the last step (16 per layer + 2) */
+MGB_API int mgb_session_debug_stamps(mgb_session * s, uint64_t * out, int n);
 
 /* ---- nano-codec ----------------------------------------------------------------------------
  * magpie_codec_init / _free (src/nano-codec.cpp:339-374, 205-333) and magpie_codec_decode

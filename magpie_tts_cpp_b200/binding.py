@@ -41,6 +41,7 @@ SYMBOLS = [
     "mgb_session_new", "mgb_session_free", "mgb_session_batch", "mgb_session_max_seq", "mgb_session_positions",
     "mgb_encode_text", "mgb_prefill", "mgb_decoder_step", "mgb_final_proj", "mgb_lt_sample",
     "mgb_generate", "mgb_teacher_forced", "mgb_session_last_loop_ms", "mgb_session_last_loop_launches",
+    "mgb_session_debug_stamps",
     "mgb_codec_load", "mgb_codec_free", "mgb_codec_get_hparams", "mgb_codec_decode",
     "mgb_codec_fsq_dequantize", "mgb_codec_last_ms", "mgb_codec_last_launches",
 ]
@@ -102,6 +103,7 @@ def lib():
     L.mgb_session_last_loop_ms.argtypes = [vp]
     L.mgb_session_last_loop_launches.restype = C.c_int64
     L.mgb_session_last_loop_launches.argtypes = [vp]
+    L.mgb_session_debug_stamps.argtypes = [vp, vp, C.c_int]
     L.mgb_codec_load.restype = vp
     L.mgb_codec_load.argtypes = [cp, C.c_int]
     L.mgb_codec_free.argtypes = [vp]
@@ -295,6 +297,11 @@ class Session:
         gr = np.zeros((self.B, T, 8), np.int32) if want_greedy else None
         _chk(lib().mgb_teacher_forced(self._h, _p(c), int(T), _p(hid), _p(lg), _p(gr)), "mgb_teacher_forced")
         return hid, lg, gr
+
+    def debug_stamps(self, n: int) -> np.ndarray:
+        out = np.zeros(n, np.uint64)
+        _chk(lib().mgb_session_debug_stamps(self._h, _p(out), n), "debug_stamps")
+        return out
 
     @property
     def last_loop_ms(self) -> float:

@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include "kernels.cuh"
 #include "model.h"
+#include "mega.h"
 
 namespace mgb {
 const std::string & get_error();
@@ -51,6 +52,9 @@ struct Session {
     float * l_logits = nullptr, * l_hidden = nullptr;
     size_t l_cap_forced = 0, l_cap_sampled = 0, l_cap_argmax = 0, l_cap_uni = 0, l_cap_logits = 0, l_cap_hidden = 0;
     float last_ms = 0.0f; int64_t last_launches = 0;
+    // batch-1 megakernel state
+    int mega_grid = 0; float * attn_part = nullptr; unsigned * d_barrier = nullptr; int n_split = 1;
+    unsigned long long * d_dbg = nullptr;
 
     ~Session() {
         if (m) cudaSetDevice(m->device);
@@ -130,14 +134,41 @@ __global__ void advance_kernel(int32_t * pos, int32_t * slot, int B, int32_t * s
     if (i == 0 && step) *step += 1;
 }
 
+__global__ void step_inc_kernel(int32_t * step) { *step += 1; }
+
 static bool launch_advance(Session & s, bool with_step) {
+    if (s.mega_grid > 0) {           // the megakernel advances pos/slot itself
+        if (with_step) { step_inc_kernel<<<1, 1, 0, s.stream>>>(s.d_step); MGB_LAUNCH_CHECK(); }
+        return true;
+    }
     advance_kernel<<<(s.B + 127) / 128, 128, 0, s.stream>>>(s.dec_pos, s.dec_slot, s.B, with_step ? s.d_step : nullptr);
     MGB_LAUNCH_CHECK();
     return true;
 }
 
+// batch 1: the whole step (embedding, 12 layers, final LayerNorm, position advance) is one cooperative kernel
+static bool decoder_step_mega(Session & s) {
+    Model & m = *s.m; const mgb_hparams & hp = m.hp;
+    MegaParams p = {};
+    for (int l = 0; l < hp.dec_layers; l++) {
+        const DecLayer & L = m.dec[l];
+        p.layer[l] = MegaLayer{L.qkv.w, L.o.w, L.xq.w, L.xo.w, L.ff1.w, L.ff2.w, L.norm_self, L.norm_xa_q, L.norm_ff};
+    }
+    p.L = hp.dec_layers; p.d = hp.d_model; p.f = hp.d_ffn; p.dxa = hp.dec_xa_heads * hp.dec_xa_d_head; p.H = hp.dec_sa_heads;
+    p.n_split = s.n_split; p.eps = hp.eps; p.gelu_f16 = m.gelu_f16;
+    for (int cb = 0; cb < 8; cb++) p.audio_emb[cb] = m.audio_emb[cb];
+    p.dec_pos = m.dec_pos; p.norm_out = m.dec_norm_out; p.codes = s.d_codes;
+    p.pos = s.dec_pos; p.pos_rw = s.dec_pos; p.slot_rw = s.dec_slot;
+    p.kcache = s.kc; p.vcache = s.vc; p.kv_layer_stride = (size_t)s.B * s.max_seq * hp.d_model;
+    p.xk = s.xk; p.xv = s.xv; p.xkv_layer_stride = (size_t)s.B * s.max_text * p.dxa; p.n_ctx = s.d_ntext;
+    p.x = s.x; p.q = s.qbuf; p.attn_part = s.attn_part; p.xq = s.xq; p.ffh = s.ffh; p.hidden = s.hidden;
+    p.barrier = s.d_barrier; p.dbg = s.d_dbg;
+    return launch_decoder_mega(p, m.precision, s.mega_grid, s.stream);
+}
+
 // one decoder step on the codes in s.d_codes; leaves hidden in s.hidden
 static bool decoder_step_device(Session & s) {
+    if (s.mega_grid > 0) return decoder_step_mega(s);
     if (!launch_audio_embed(*s.m, s.d_codes, s.dec_pos, s.B, s.x, s.stream)) return false;
     Tokens tok; tok.M = s.B; tok.utt = s.dec_utt; tok.pos = s.dec_pos; tok.slot = s.dec_slot;
     return decoder_layers(s, tok, true);
@@ -232,6 +263,17 @@ mgb_session * mgb_session_new(mgb_model * mm, int batch, int max_text, int max_s
          s->alloc(s->d_done, batch) && s->alloc(s->d_forbid, batch) && s->alloc(s->d_forced, (size_t)batch * 8) &&
          s->alloc(s->d_uniforms, (size_t)batch * 8) && s->alloc(s->d_logits1, (size_t)batch * 8 * V);
     if (!ok) return nullptr;
+    // batch 1: persistent cooperative megakernel (MGB_NO_MEGA=1 keeps the per-op kernels, e.g. for A/B tests)
+    if (batch == 1 && getenv("MGB_NO_MEGA") == nullptr && hp.dec_layers <= kMegaMaxLayers && hp.d_model <= 1024 &&
+        hp.d_ffn <= 11 * 1024 && max_text <= 4096) {
+        const int g = mega_max_grid(m->precision);
+        if (g > 0) {
+            s->n_split = std::max(1, std::min(16, g / hp.dec_sa_heads));
+            if (s->alloc(s->attn_part, (size_t)hp.dec_sa_heads * s->n_split * 66) && s->alloc(s->d_barrier, 1) &&
+                (getenv("MGB_MEGA_DBG") == nullptr || s->alloc(s->d_dbg, 1024 + 160 * 100))) s->mega_grid = g;
+            else return nullptr;
+        }
+    }
     std::vector<int32_t> ids(batch);
     for (int b = 0; b < batch; b++) ids[b] = b;
     if (cudaMemcpy(s->dec_utt, ids.data(), batch * 4, cudaMemcpyHostToDevice) != cudaSuccess) { set_error("H2D failed"); return nullptr; }
@@ -245,6 +287,13 @@ int mgb_session_positions(const mgb_session * ss, int32_t * pos_out) {
     const Session * s = reinterpret_cast<const Session *>(ss);
     if (!s || !pos_out) return MGB_EINVAL;
     for (int b = 0; b < s->B; b++) pos_out[b] = s->pos;
+    return MGB_OK;
+}
+int mgb_session_debug_stamps(mgb_session * ss, uint64_t * out, int n) {
+    Session * s = reinterpret_cast<Session *>(ss);
+    if (!s || !out || n <= 0 || n > 1024 + 160 * 100 || !s->d_dbg) return MGB_EINVAL;
+    if (cudaSetDevice(s->m->device) != cudaSuccess || cudaStreamSynchronize(s->stream) != cudaSuccess ||
+        cudaMemcpy(out, s->d_dbg, (size_t)n * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return MGB_ECUDA;
     return MGB_OK;
 }
 float mgb_session_last_loop_ms(const mgb_session * s) { return s ? reinterpret_cast<const Session *>(s)->last_ms : 0.0f; }

@@ -12,41 +12,20 @@
 // the top-k sampler are cheap and run redundantly (bit-identically) in every CTA, so no gather is
 // needed.  Weights stream from L2/HBM with 16-byte loads, 4 rows in flight per warp.
 #include <cooperative_groups.h>
+#include <cstdlib>
 
-#include "common.cuh"
-#include "kernels.cuh"
+#include "lt_common.cuh"
 
 namespace cg = cooperative_groups;
 
 namespace mgb {
 
+bool lt_resident_supported(const Model & m, int B);
+bool launch_lt_resident(const lt::LtParams & p, cudaStream_t stream);
+
 namespace {
 
-constexpr int kLtThreads = 512;
-constexpr int kLtWarps = kLtThreads / 32;
-constexpr int kL = 256;        // lt_dim (max)
-constexpr int kF = 1024;       // lt_ffn_dim (max)
-constexpr int kD = 1024;       // d_model (max)
-constexpr int kV = 2048;       // vocab_per_cb (max)
-
-struct LtParams {
-    int B, d, L, F, V;
-    float eps; int gelu_f16;
-    const float * hidden;
-    const void * in_w; const float * in_b;
-    const float * pos;
-    const float * norm_self; const float * norm_ff;
-    const void * qkv_w; const void * o_w; const void * ff1_w; const void * ff2_w;
-    const void * out_w[8]; const float * out_b[8];
-    const float * audio_emb[8];
-    float temperature; int top_k;
-    const uint8_t * forbid_eos; int forbid_eos_all;
-    const int32_t * forced; const float * uniforms;
-    uint64_t seed; uint32_t step;
-    int bos_id, eos_id;
-    int32_t * sampled; int32_t * argmax; int32_t * next_codes; float * logits; int32_t * eos_flag;
-    const int32_t * d_step; int T_total, min_frames; int32_t * done_step; float * hidden_hist;
-};
+using namespace lt;
 
 struct LtSmem {
     float hid[kD];
@@ -69,35 +48,18 @@ struct LtSmem {
     int   misc[8];
 };
 
-__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
-                                              uint32_t (&out)[4]) {
-#pragma unroll
-    for (int i = 0; i < 10; i++) {
-        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-        const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
-        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
-        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-    }
-    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
-}
-
-__device__ __forceinline__ unsigned order_key(float f) {      // larger float -> larger key
-    unsigned u = __float_as_uint(f);
-    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-
 template <int CS>
 __device__ __forceinline__ void cluster_barrier(cg::cluster_group & cluster) {
     if constexpr (CS > 1) cluster.sync(); else __syncthreads();
 }
 
 // dst[n] (in every CTA of the cluster) = epi(n, sum_k W[n][k] x[k]) for the rows of this CTA's slice.
+// 8 rows per warp pass: 8 independent 16-byte loads in flight per lane (the loop is L2-latency bound).
 template <typename T, int CS, typename Epi>
 __device__ __forceinline__ void gemv_bcast(cg::cluster_group & cluster, const T * __restrict__ W, int N, int K,
                                            const float * x, float * dst, int rank, Epi epi) {
     constexpr int VEC = WT<T>::VEC;
-    constexpr int RW = (CS >= 8) ? 32 / CS : 4;
+    constexpr int RW = 8;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int gw = rank * kLtWarps + warp;
     for (int n0 = gw * RW; n0 < N; n0 += CS * kLtWarps * RW) {
@@ -108,11 +70,8 @@ __device__ __forceinline__ void gemv_bcast(cg::cluster_group & cluster, const T 
             float w[RW][VEC];
 #pragma unroll
             for (int r = 0; r < RW; r++) {
-                if (n0 + r < N) WT<T>::load(W + (size_t)(n0 + r) * K + k, w[r]);
-                else {
-#pragma unroll
-                    for (int v = 0; v < VEC; v++) w[r][v] = 0.0f;
-                }
+                const int n = min(n0 + r, N - 1);                 // clamp: rows past N are computed and discarded
+                WT<T>::load(W + (size_t)n * K + k, w[r]);
             }
             float xv[VEC];
 #pragma unroll
@@ -125,126 +84,23 @@ __device__ __forceinline__ void gemv_bcast(cg::cluster_group & cluster, const T 
 #pragma unroll
                 for (int v = 0; v < VEC; v++) acc[r] = fmaf(w[r][v], xv[v], acc[r]);
         }
-        float mine = 0.0f;
 #pragma unroll
-        for (int r = 0; r < RW; r++) {
-            float v = warp_sum(acc[r]);
-            if (lane / CS == r) mine = v;
-        }
-        const int r = lane / CS, dr = lane % CS;
-        if (r < RW && n0 + r < N) {
-            const float v = epi(n0 + r, mine);
-            if constexpr (CS > 1) cluster.map_shared_rank(dst, dr)[n0 + r] = v;
-            else dst[n0 + r] = v;
-        }
-    }
-}
-
-__device__ __forceinline__ void block_layer_norm(const float * x, const float * w, float * y, int n, float eps, float * red) {
-    const int tid = threadIdx.x;
-    float v = tid < n ? x[tid] : 0.0f;
-    const float mean = block_sum(v, red) / (float)n;
-    const float c = tid < n ? v - mean : 0.0f;
-    const float var = block_sum(c * c, red) / (float)n;
-    const float scale = 1.0f / sqrtf(var + eps);
-    if (tid < n) y[tid] = (c * scale) * w[tid];
-    __syncthreads();
-}
-
-// argmax with "first max wins" (strict >, lowest index on ties)  -- magpie.cpp:1250-1259
-__device__ __forceinline__ int block_argmax(const float * v, int n, float * red, int * redi) {
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    float bv = -INFINITY; int bi = 0x7fffffff;
-    for (int i = tid; i < n; i += kLtThreads) { float f = v[i]; if (f > bv || (f == bv && i < bi)) { bv = f; bi = i; } }
-    // NB: all -inf rows never happen (only 8 ids are masked)
+        for (int r = 0; r < RW; r++) acc[r] = warp_sum(acc[r]);
+        // RW x CS (row, destination CTA) stores spread over the lanes
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        float ov = __shfl_xor_sync(0xffffffffu, bv, o); int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-    }
-    __syncthreads();
-    if (lane == 0) { red[wid] = bv; redi[wid] = bi; }
-    __syncthreads();
-    if (wid == 0) {
-        bv = lane < kLtWarps ? red[lane] : -INFINITY; bi = lane < kLtWarps ? redi[lane] : 0x7fffffff;
+        for (int i = 0; i < (RW * CS + 31) / 32; i++) {
+            const int idx = lane + 32 * i;
+            const int r = idx / CS, dr = idx % CS;
+            float mine = 0.0f;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            float ov = __shfl_xor_sync(0xffffffffu, bv, o); int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-        }
-        if (lane == 0) redi[0] = bi;
-    }
-    __syncthreads();
-    const int r = redi[0];
-    __syncthreads();
-    return r;
-}
-
-// sample_top_k (magpie.cpp:1072-1109): k largest (value desc, index asc), softmax((l - max)/T) with
-// sequential float accumulation, inverse CDF with draw u; fallback = last of the k.
-__device__ int block_sample_top_k(LtSmem & S, int V, float temperature, int top_k, float u) {
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    int k = top_k < V ? top_k : V;
-    if (k < 1) k = 1;                              // top_k = 0 is UB in the reference: clamp
-    // ---- radix select: key of the k-th largest element ----
-    unsigned prefix = 0, pmask = 0; int want = k;
-    for (int pass = 0; pass < 4; pass++) {
-        const int shift = 24 - 8 * pass;
-        if (tid < 256) S.hist[tid] = 0;
-        __syncthreads();
-        for (int i = tid; i < V; i += kLtThreads) {
-            const unsigned key = order_key(S.logits[i]);
-            if ((key & pmask) == prefix) atomicAdd(&S.hist[(key >> shift) & 255u], 1u);
-        }
-        __syncthreads();
-        if (tid == 0) {
-            int acc = 0, b = 255;
-            for (; b > 0; b--) { if (acc + (int)S.hist[b] >= want) break; acc += (int)S.hist[b]; }
-            S.misc[0] = b; S.misc[1] = want - acc;
-        }
-        __syncthreads();
-        prefix |= (unsigned)S.misc[0] << shift; pmask |= 255u << shift; want = S.misc[1];
-        __syncthreads();
-    }
-    const unsigned thr = prefix;                   // k-th largest key; `want` ties to take (lowest indices)
-    // ---- compaction in index order by warp 0 ----
-    if (wid == 0) {
-        int cnt = 0, eq_taken = 0;
-        for (int i0 = 0; i0 < V; i0 += 32) {
-            const int i = i0 + lane;
-            const unsigned key = i < V ? order_key(S.logits[i]) : 0u;
-            const bool gt = i < V && key > thr, eq = i < V && key == thr;
-            const unsigned eqm = __ballot_sync(0xffffffffu, eq);
-            const int eq_rank = eq_taken + __popc(eqm & ((1u << lane) - 1u));
-            const bool take = gt || (eq && eq_rank < want);
-            const unsigned tm = __ballot_sync(0xffffffffu, take);
-            if (take) { const int ppos = cnt + __popc(tm & ((1u << lane) - 1u)); S.sel_v[ppos] = S.logits[i]; S.sel_i[ppos] = i; }
-            cnt += __popc(tm); eq_taken += __popc(eqm);
+            for (int rr = 0; rr < RW; rr++) if (rr == r) mine = acc[rr];
+            if (r < RW && n0 + r < N) {
+                const float v = epi(n0 + r, mine);
+                if constexpr (CS > 1) cluster.map_shared_rank(dst, dr)[n0 + r] = v;
+                else dst[n0 + r] = v;
+            }
         }
     }
-    __syncthreads();
-    // ---- rank by counting -> sorted (value desc, index asc) ----
-    for (int a = tid; a < k; a += kLtThreads) {
-        const float va = S.sel_v[a]; const int ia = S.sel_i[a];
-        int r = 0;
-        for (int b = 0; b < k; b++) { const float vb = S.sel_v[b]; r += (vb > va || (vb == va && S.sel_i[b] < ia)) ? 1 : 0; }
-        S.srt_v[r] = va; S.srt_i[r] = ia;
-    }
-    __syncthreads();
-    const float mx = S.srt_v[0];
-    for (int a = tid; a < k; a += kLtThreads) S.sel_v[a] = expf((S.srt_v[a] - mx) / temperature);
-    __syncthreads();
-    if (tid == 0) {
-        float sum = 0.0f;
-        for (int a = 0; a < k; a++) sum += S.sel_v[a];
-        float cum = 0.0f; int pick = S.srt_i[k - 1];
-        for (int a = 0; a < k; a++) { cum += S.sel_v[a] / sum; if (u < cum) { pick = S.srt_i[a]; break; } }
-        S.misc[2] = pick;
-    }
-    __syncthreads();
-    const int r = S.misc[2];
-    __syncthreads();
-    return r;
 }
 
 template <typename T, int CS>
@@ -289,8 +145,6 @@ __global__ void __launch_bounds__(kLtThreads, 1) lt_kernel(const LtParams p) {
         // q | k | v rows of qkv_net (magpie.cpp:1501-1503)
         {
             float * kdst = S.kc[cb], * vdst = S.vc[cb];
-            constexpr int RWQ = (CS >= 8) ? 32 / CS : 4;
-            (void)RWQ;
             // three slices so that each lands in its own buffer
             gemv_bcast<T, CS>(cluster, (const T *)p.qkv_w, L, L, S.nrm, S.q, rank, [](int, float v) { return v; });
             gemv_bcast<T, CS>(cluster, (const T *)p.qkv_w + (size_t)L * L, L, L, S.nrm, kdst, rank, [](int, float v) { return v; });
@@ -416,8 +270,33 @@ bool launch_local_transformer(const Model & m, const LtArgs & a, cudaStream_t st
     p.bos_id = m.hp.audio_bos_id; p.eos_id = m.hp.audio_eos_id;
     p.sampled = a.sampled; p.argmax = a.argmax; p.next_codes = a.next_codes; p.logits = a.logits; p.eos_flag = a.eos_flag;
     p.d_step = a.d_step; p.T_total = a.T_total; p.min_frames = a.min_frames; p.done_step = a.done_step; p.hidden_hist = a.hidden_hist;
-    if (m.precision == MGB_PREC_F32) return launch_lt_t<float, 8>(p, stream);
-    return launch_lt_t<__nv_bfloat16, 8>(p, stream);
+    for (int cb = 0; cb < 8; cb++) p.in_table[cb] = m.lt_in_table[cb];
+    // small batches, bf16: weights resident in shared memory (lt_resident.cu)
+    if (lt_resident_supported(m, a.B)) return launch_lt_resident(p, stream);
+    // 16-CTA (non-portable) clusters when the device can schedule them, else the portable 8
+    static int cs16[64] = {};
+    int dev = 0;
+    MGB_CUDA_TRY(cudaGetDevice(&dev));
+    if (cs16[dev & 63] == 0) {
+        cs16[dev & 63] = -1;
+        if (getenv("MGB_LT_CLUSTER8") == nullptr) {
+            int ncl = 0;
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(16); cfg.blockDim = dim3(kLtThreads); cfg.dynamicSmemBytes = sizeof(LtSmem);
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 16; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            bool ok = cudaFuncSetAttribute(lt_kernel<__nv_bfloat16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LtSmem)) == cudaSuccess &&
+                      cudaFuncSetAttribute(lt_kernel<__nv_bfloat16, 16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+                      cudaOccupancyMaxActiveClusters(&ncl, lt_kernel<__nv_bfloat16, 16>, &cfg) == cudaSuccess && ncl >= 1;
+            cudaGetLastError();
+            if (ok) cs16[dev & 63] = 1;
+        }
+    }
+    const bool big = cs16[dev & 63] == 1 && a.B <= 8;      // many utterances already fill the GPU with 8-CTA clusters
+    if (m.precision == MGB_PREC_F32) return big ? launch_lt_t<float, 16>(p, stream) : launch_lt_t<float, 8>(p, stream);
+    return big ? launch_lt_t<__nv_bfloat16, 16>(p, stream) : launch_lt_t<__nv_bfloat16, 8>(p, stream);
 }
 
 }  // namespace mgb

@@ -6,6 +6,7 @@
 #include <memory>
 
 #include "common.cuh"
+#include "kernels.cuh"
 
 namespace mgb {
 
@@ -205,6 +206,20 @@ Model * load_model(const char * path, int device, int precision) {
                    L.xq.w && L.xkv.w && L.xo.w && L.ff1.w && L.ff2.w;
     if (!complete) { set_error("magpie_init: model file is missing tensors of the synthesis path"); return nullptr; }
     if (M->dec_pos_rows < hp.context_frames + 2) { set_error("magpie_init: decoder position table too short"); return nullptr; }
+
+    // feedback table of the local transformer: P_cb[code] = in_proj . E_cb[code] + b (magpie.cpp:1274-1313),
+    // computed once on the device so that the per-codebook feedback is a row gather
+    for (int cb = 0; cb < 8; cb++) {
+        void * t = nullptr;
+        if (cudaMalloc(&t, (size_t)hp.vocab_per_cb * hp.lt_dim * sizeof(float)) != cudaSuccess) { set_error("cudaMalloc failed"); return nullptr; }
+        M->allocations.push_back(t);
+        M->lt_in_table[cb] = (float *)t;
+        LinearArgs a;
+        a.precision = precision; a.M = hp.vocab_per_cb; a.W = M->lt_in_w; a.X = M->audio_emb[cb]; a.ldx = hp.d_model;
+        a.bias = M->lt_in_b; a.Y = M->lt_in_table[cb]; a.ldy = hp.lt_dim;
+        if (!launch_linear(a, nullptr)) return nullptr;
+    }
+    if (cudaDeviceSynchronize() != cudaSuccess) { set_error("magpie_init: building the LT feedback table failed"); return nullptr; }
 
     // unique weight bytes one generated frame reads: decoder matrices + LT matrices
     int64_t el = 0, f32b = 0;

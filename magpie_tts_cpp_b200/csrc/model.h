@@ -47,6 +47,7 @@ struct Model {
     float * lt_norm_self = nullptr, * lt_norm_ff = nullptr;
     DevMat lt_qkv, lt_o, lt_ff1, lt_ff2;
     DevMat lt_out_w[8]; float * lt_out_b[8] = {};
+    float * lt_in_table[8] = {};            // P_cb = E_cb . Win^T + b  [V][lt_dim] f32 (built on the device at load)
 
     std::map<std::string, std::string> meta_str;    // tokenizer strings etc.
     std::map<std::string, int32_t>     meta_u32;

@@ -35,9 +35,25 @@ def B():
     return binding
 
 
+# The reference's CPU path evaluates GELU through ggml's f16 lookup table: a
+# discontinuous function.  A 1e-6 relative perturbation of its input flips table entries and moves the
+# 12-layer decoder output by ~5e-4 (tests/test_oracle_cpu.py::test_gelu_f16_table_amplifies_rounding_noise),
+# so the f32 bar of 1e-4 is checked with the table OFF on both sides (pure f32 arithmetic, where the oracle
+# agrees with float64 to ~1e-6), and the table-ON mode (bit-for-bit the reference's semantics, the product
+# default) is checked at TABLE_TOL, the reference path's own noise floor.
+TABLE_TOL = 3e-3
+
+
+def set_table(m, o, on):
+    m.set_gelu_f16(on)
+    o.set_gelu_table(on)
+
+
 @pytest.fixture(scope="module")
 def tiny_pair(B, oracle_mod, tiny_model_path):
-    return B.Model(tiny_model_path, 0, B.PREC_F32), oracle_mod.OracleModel(tiny_model_path)
+    m, o = B.Model(tiny_model_path, 0, B.PREC_F32), oracle_mod.OracleModel(tiny_model_path)
+    set_table(m, o, False)
+    return m, o
 
 
 # ---- tiny architecture, f32: every stage against the oracle ------------------------------------------
@@ -110,8 +126,10 @@ def test_top_k_sampler_matches_oracle_given_uniforms(tiny_pair):
     assert agree >= 0.97 * total       # expf ulp differences may flip a draw that lands on a CDF edge
 
 
-def test_generate_greedy_f32_matches_oracle(tiny_pair):
+@pytest.mark.parametrize("table", [False, True])
+def test_generate_greedy_f32_matches_oracle(tiny_pair, table):
     m, o = tiny_pair
+    set_table(m, o, table)
     s = m.session(batch=2, max_text=32, max_seq=10 + 24 + 16)
     toks = [HELLO, HELLO[:7] + [2379]]
     s.encode_text(toks, want_output=False)
@@ -121,9 +139,8 @@ def test_generate_greedy_f32_matches_oracle(tiny_pair):
         ref, rh = o.synthesize(toks[b], speaker=[0, 1][b], temperature=0.0, max_steps=24, want_hidden=True)
         assert len(out[b]) == len(ref)
         assert np.mean(np.all(out[b] == ref, axis=1)) >= 0.99
-        # free-running: 1-ulp differences can flip an f16 GELU-table rounding (a discontinuous function the
-        # reference's CPU path applies) and then propagate through the KV cache
-        close(hid[b, :len(ref)], rh[:len(ref)], 5e-4)
+        close(hid[b, :len(ref)], rh[:len(ref)], TABLE_TOL if table else 1e-4)
+    set_table(m, o, False)
 
 
 def test_teacher_forced_equals_stepwise(tiny_pair):
@@ -162,9 +179,9 @@ def test_error_paths(tiny_pair, B):
 
 # ---- full Magpie-357M architecture --------------------------------------------------------------------
 
-@pytest.fixture(scope="module")
-def full_oracle(oracle_mod, full_model_path):
+def _full_oracle(oracle_mod, full_model_path, table):
     o = oracle_mod.OracleModel(full_model_path)
+    o.set_gelu_table(table)
     enc = o.encode_text(HELLO)
     rng = np.random.default_rng(42)
     codes = rng.integers(0, 2016, (12, 8)).astype(np.int32)     # config 2 stream, first frames
@@ -179,18 +196,44 @@ def full_oracle(oracle_mod, full_model_path):
     return dict(o=o, enc=enc, codes=codes, hid=np.stack(hid), lg=np.stack(lgs), gr=np.stack(grs))
 
 
-def test_full_model_teacher_forced_f32(B, full_model_path, full_oracle):
+@pytest.fixture(scope="module")
+def full_oracle(oracle_mod, full_model_path):
+    return _full_oracle(oracle_mod, full_model_path, True)
+
+
+@pytest.fixture(scope="module")
+def full_oracle_notable(oracle_mod, full_model_path):
+    return _full_oracle(oracle_mod, full_model_path, False)
+
+
+@pytest.mark.parametrize("batch", [1, 3])       # batch 1 = megakernel path, batch 3 = per-op kernels
+def test_full_model_teacher_forced_f32(B, full_model_path, full_oracle_notable, batch):
+    fo = full_oracle_notable
     m = B.Model(full_model_path, 0, B.PREC_F32)
+    m.set_gelu_f16(False)
+    s = m.session(batch=batch, max_text=32)
+    enc = s.encode_text([HELLO] * batch)
+    close(enc[0], fo["enc"], 1e-4)
+    s.prefill([0] * batch)
+    hid, lg, gr = s.teacher_forced(np.repeat(fo["codes"][None], batch, axis=0))
+    for b in range(batch):
+        close(hid[b], fo["hid"], 1e-4)
+        close(lg[b], fo["lg"], 1e-4)
+        assert np.mean(np.all(gr[b] == fo["gr"], axis=1)) >= 0.99
+    fp = s.final_proj()
+    close(fp[0], fo["o"].final_proj(fo["hid"][-1]), 1e-4)
+
+
+def test_full_model_teacher_forced_f32_reference_gelu_table(B, full_model_path, full_oracle):
+    m = B.Model(full_model_path, 0, B.PREC_F32)        # product default: ggml-CPU f16 GELU table semantics
     s = m.session(batch=1, max_text=32)
     enc = s.encode_text([HELLO])
-    close(enc[0], full_oracle["enc"], 1e-4)
+    close(enc[0], full_oracle["enc"], TABLE_TOL)
     s.prefill([0])
     hid, lg, gr = s.teacher_forced(full_oracle["codes"][None])
-    close(hid[0], full_oracle["hid"], 1e-4)
-    close(lg[0], full_oracle["lg"], 1e-4)
-    assert np.mean(np.all(gr[0] == full_oracle["gr"], axis=1)) >= 0.99
-    fp = s.final_proj()
-    close(fp[0], full_oracle["o"].final_proj(full_oracle["hid"][-1]), 1e-4)
+    close(hid[0], full_oracle["hid"], TABLE_TOL)
+    close(lg[0], full_oracle["lg"], TABLE_TOL)
+    assert np.mean(gr[0] == full_oracle["gr"]) >= 0.95
 
 
 def test_full_model_teacher_forced_bf16(B, full_model_path, full_oracle):
@@ -209,6 +252,30 @@ def test_full_model_teacher_forced_bf16(B, full_model_path, full_oracle):
     # often below bf16 resolution, so the bf16 bar here is on logits (above), and codes are reported
     agree = np.mean(gr[0] == full_oracle["gr"])
     print(f"bf16 greedy code agreement vs f32 oracle: {agree:.3f}")
+
+
+def test_bf16_fast_paths_match_per_op_kernels(B, full_model_path, full_oracle, monkeypatch):
+    """batch-1 bf16: megakernel + smem-resident LT (the benchmarked path) against the per-op kernels + streaming LT."""
+    m = B.Model(full_model_path, 0, B.PREC_BF16)
+    codes = full_oracle["codes"][None]
+
+    def run():
+        s = m.session(batch=1, max_text=32)
+        s.encode_text([HELLO], want_output=False)
+        s.prefill([0])
+        out = s.teacher_forced(codes)
+        s.close()
+        return out
+
+    hid_f, lg_f, gr_f = run()
+    monkeypatch.setenv("MGB_NO_MEGA", "1")
+    monkeypatch.setenv("MGB_LT_STREAM", "1")
+    hid_s, lg_s, gr_s = run()
+    close(hid_f[0], hid_s[0], 2e-3)
+    close(lg_f[0], lg_s[0], 2e-3)
+    assert np.mean(gr_f == gr_s) >= 0.97
+    close(hid_f[0], full_oracle["hid"], 2e-2)
+    close(lg_f[0], full_oracle["lg"], 2e-2)
 
 
 # ---- nano-codec ---------------------------------------------------------------------------------------
