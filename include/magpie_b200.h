@@ -72,6 +72,9 @@ typedef struct mgb_codec   mgb_codec;
 MGB_API const char * mgb_last_error(void);
 MGB_API int          mgb_device_count(void);                 /* 0 if no CUDA device */
 MGB_API const char * mgb_version(void);
+/* Utterance -> device assignment of the multi-GPU path: independent utterances, weights
+ * replicated per device, utterance i runs on device i mod n_devices; no collective on the data path. */
+MGB_API int          mgb_shard_device(int64_t utterance_index, int n_devices);
 
 /* ---- model -------------------------------------------------------------------------------
  * Replaces magpie_init / magpie_init_with_backend / magpie_free (src/magpie.cpp:777-915):

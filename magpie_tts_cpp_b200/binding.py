@@ -34,7 +34,7 @@ class CodecHParams(C.Structure):
 
 # every symbol include/magpie_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
-    "mgb_last_error", "mgb_device_count", "mgb_version",
+    "mgb_last_error", "mgb_device_count", "mgb_version", "mgb_shard_device",
     "mgb_model_load", "mgb_model_free", "mgb_model_get_hparams", "mgb_model_set_max_dec_steps",
     "mgb_model_set_gelu_f16", "mgb_model_precision", "mgb_model_device", "mgb_model_step_weight_bytes",
     "mgb_model_meta_str", "mgb_model_meta_u32",
@@ -72,6 +72,7 @@ def lib():
     L.mgb_last_error.restype = cp
     L.mgb_version.restype = cp
     L.mgb_device_count.restype = C.c_int
+    L.mgb_shard_device.argtypes = [C.c_int64, C.c_int]
     L.mgb_model_load.restype = vp
     L.mgb_model_load.argtypes = [cp, C.c_int, C.c_int]
     L.mgb_model_free.argtypes = [vp]

@@ -189,6 +189,10 @@ extern "C" {
 
 const char * mgb_last_error(void) { return get_error().c_str(); }
 const char * mgb_version(void) { return "magpie-b200 0.1 (sm_100a)"; }
+int mgb_shard_device(int64_t utterance_index, int n_devices) {
+    if (n_devices <= 0 || utterance_index < 0) return MGB_EINVAL;
+    return (int)(utterance_index % n_devices);
+}
 
 int mgb_device_count(void) {
     int n = 0;
