@@ -12,6 +12,7 @@
 #include "kernels.cuh"
 #include "model.h"
 #include "mega.h"
+#include "frame_loop.h"
 
 namespace mgb {
 const std::string & get_error();
@@ -55,6 +56,10 @@ struct Session {
     // batch-1 megakernel state
     int mega_grid = 0; float * attn_part = nullptr; unsigned * d_barrier = nullptr; int n_split = 1;
     unsigned long long * d_dbg = nullptr;
+    // batch-1 bf16 persistent frame-loop kernel (frame_loop.cu)
+    int loop_grid = 0; uint4 * d_xbuf = nullptr; int xoff[X_COUNT + 1] = {}; unsigned * d_seq = nullptr;
+    int32_t * d_result = nullptr; float * d_xm = nullptr, * d_xn = nullptr; int loop_E = 0; bool loop_tables = false;
+    unsigned long long * d_loop_dbg = nullptr;
 
     ~Session() {
         if (m) cudaSetDevice(m->device);
@@ -278,6 +283,25 @@ mgb_session * mgb_session_new(mgb_model * mm, int batch, int max_text, int max_s
             else return nullptr;
         }
     }
+    // batch 1, bf16, Magpie-357M shapes: the whole frame loop is one persistent kernel (MGB_NO_LOOPK=1 disables it)
+    if (batch == 1 && m->precision == MGB_PREC_BF16 && getenv("MGB_NO_LOOPK") == nullptr &&
+        frame_loop_shape_ok(hp.d_model, hp.d_ffn, hp.dec_sa_heads, hp.lt_dim, hp.lt_ffn_dim, hp.vocab_per_cb, hp.dec_layers) &&
+        dxa == 128 && m->lt_in_table[0]) {
+        const int g = frame_loop_max_grid();
+        if (g > 0) {
+            frame_loop_xchg_layout(hp.vocab_per_cb, s->xoff);
+            const size_t xb = frame_loop_xchg_bytes(s->xoff);
+            char * xp = nullptr;
+            const size_t tab = (size_t)L * kLoopMaxCtx * d;
+            if (!s->alloc(xp, xb) || !s->alloc(s->d_seq, 1) || !s->alloc(s->d_result, 16) || !s->alloc(s->d_xm, tab) || !s->alloc(s->d_xn, tab) ||
+                (getenv("MGB_LOOP_DBG") != nullptr && !s->alloc(s->d_loop_dbg, kLoopDbgStamps))) return nullptr;
+            s->d_xbuf = (uint4 *)xp;
+            const unsigned one = 1;
+            if (cudaMemset(xp, 0, xb) != cudaSuccess || cudaMemcpy(s->d_seq, &one, 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+                (s->d_loop_dbg && cudaMemset(s->d_loop_dbg, 0, kLoopDbgStamps * 8) != cudaSuccess)) { set_error("loop kernel state init failed"); return nullptr; }
+            s->loop_grid = g;
+        }
+    }
     std::vector<int32_t> ids(batch);
     for (int b = 0; b < batch; b++) ids[b] = b;
     if (cudaMemcpy(s->dec_utt, ids.data(), batch * 4, cudaMemcpyHostToDevice) != cudaSuccess) { set_error("H2D failed"); return nullptr; }
@@ -295,9 +319,11 @@ int mgb_session_positions(const mgb_session * ss, int32_t * pos_out) {
 }
 int mgb_session_debug_stamps(mgb_session * ss, uint64_t * out, int n) {
     Session * s = reinterpret_cast<Session *>(ss);
-    if (!s || !out || n <= 0 || n > 1024 + 160 * 100 || !s->d_dbg) return MGB_EINVAL;
+    if (!s || !out || n <= 0) return MGB_EINVAL;
+    const unsigned long long * src = s->d_loop_dbg ? s->d_loop_dbg : s->d_dbg;      // MGB_LOOP_DBG takes precedence
+    if (!src || n > (s->d_loop_dbg ? kLoopDbgStamps : 1024 + 160 * 100)) return MGB_EINVAL;
     if (cudaSetDevice(s->m->device) != cudaSuccess || cudaStreamSynchronize(s->stream) != cudaSuccess ||
-        cudaMemcpy(out, s->d_dbg, (size_t)n * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return MGB_ECUDA;
+        cudaMemcpy(out, src, (size_t)n * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return MGB_ECUDA;
     return MGB_OK;
 }
 float mgb_session_last_loop_ms(const mgb_session * s) { return s ? reinterpret_cast<const Session *>(s)->last_ms : 0.0f; }
@@ -390,6 +416,17 @@ int mgb_prefill(mgb_session * ss, const int32_t * speakers) {
         a.n_q = 0; a.dkv = dxa; a.kdst = (char *)s->xk + l * xkv_layer; a.vdst = (char *)s->xv + l * xkv_layer; a.tok_slot = s->tok_slot;
         a.Y = s->qbuf; a.ldy = d;
         if (!launch_linear(a, st)) return MGB_ECUDA;
+    }
+    // persistent loop kernel: fold q_net / o_net into per-token tables (frame_loop.cu)
+    s->loop_tables = false;
+    if (s->loop_grid > 0 && s->h_ntext[0] <= kLoopMaxCtx) {
+        s->loop_E = s->h_ntext[0];
+        for (int l = 0; l < hp.dec_layers; l++) {
+            const DecLayer & L = m.dec[l];
+            if (!launch_xattn_fold((char *)s->xk + l * xkv_layer, (char *)s->xv + l * xkv_layer, L.xq.w, L.xo.w, s->loop_E, d, dxa,
+                                   1.0f / sqrtf((float)dxa), s->d_xm + (size_t)l * kLoopMaxCtx * d, s->d_xn + (size_t)l * kLoopMaxCtx * d, st)) return MGB_ECUDA;
+        }
+        s->loop_tables = true;
     }
     // context prefill: B*C tokens, one batched causal pass (magpie.cpp:4170-4238)
     const int M = s->B * C;
@@ -510,10 +547,63 @@ static bool enqueue_iteration(Session & s, const LoopCfg & c) {
     return launch_advance(s, true);
 }
 
+// batch 1 / bf16: decoder step + local transformer + sampling + EOS for all frames in ONE persistent kernel
+static int run_loop_persistent(Session & s, const LoopCfg & c, int * steps_run) {
+    Model & m = *s.m; const mgb_hparams & hp = m.hp;
+    cudaStream_t st = s.stream;
+    FrameLoopParams p = {};
+    const size_t tab = (size_t)kLoopMaxCtx * hp.d_model;
+    for (int l = 0; l < hp.dec_layers; l++) {
+        const DecLayer & L = m.dec[l];
+        p.layer[l] = LoopLayer{L.qkv.w, L.o.w, L.ff1.w, L.ff2.w, L.norm_self, L.norm_xa_q, L.norm_ff, s.d_xm + l * tab, s.d_xn + l * tab};
+    }
+    p.L = hp.dec_layers; p.E = s.loop_E; p.eps = hp.eps; p.gelu_f16 = m.gelu_f16;
+    for (int cb = 0; cb < 8; cb++) {
+        p.audio_emb[cb] = m.audio_emb[cb]; p.lt_out_w[cb] = m.lt_out_w[cb].w; p.lt_out_b[cb] = m.lt_out_b[cb]; p.lt_in_table[cb] = m.lt_in_table[cb];
+    }
+    p.dec_pos = m.dec_pos; p.norm_out = m.dec_norm_out;
+    p.kcache = s.kc; p.vcache = s.vc; p.kv_layer_stride = (size_t)s.B * s.max_seq * hp.d_model;
+    p.V = hp.vocab_per_cb;
+    p.lt_in_w = m.lt_in_w.w; p.lt_in_b = m.lt_in_b; p.lt_pos = m.lt_pos; p.lt_norm_self = m.lt_norm_self; p.lt_norm_ff = m.lt_norm_ff;
+    p.lt_qkv = m.lt_qkv.w; p.lt_o = m.lt_o.w; p.lt_ff1 = m.lt_ff1.w; p.lt_ff2 = m.lt_ff2.w;
+    p.n_steps = c.T; p.pos0 = s.pos; p.step0 = 0; p.row0 = 0; p.min_frames = c.teacher ? 0 : 4;       // magpie.cpp:4267, 4325
+    p.teacher = c.teacher ? 1 : 0; p.ignore_eos = c.ignore_eos ? 1 : 0;
+    p.temperature = c.temperature; p.top_k = c.top_k; p.seed = c.seed;
+    p.uniforms = c.have_uniforms ? s.l_uniforms : nullptr;
+    p.forced = c.teacher ? s.l_forced : nullptr;
+    p.codes_io = s.d_codes; p.bos_id = hp.audio_bos_id; p.eos_id = hp.audio_eos_id;
+    p.sampled = s.l_sampled; p.argmax = s.l_argmax; p.logits = c.want_logits ? s.l_logits : nullptr;
+    p.hidden_hist = c.want_hidden ? s.l_hidden : nullptr; p.hidden_last = s.hidden;
+    p.result = s.d_result; p.xbuf = s.d_xbuf; memcpy(p.xoff, s.xoff, sizeof(p.xoff)); p.seq = s.d_seq; p.dbg = s.d_loop_dbg;
+    p.dbg_flags = getenv("MGB_LOOP_FLAGS") ? atoi(getenv("MGB_LOOP_FLAGS")) : 0;
+    const int64_t l0 = g_launch_counter;
+    cudaEventRecord(s.ev0, st);
+    if (!launch_frame_loop(p, s.loop_grid, st)) return MGB_ECUDA;
+    cudaEventRecord(s.ev1, st);
+    int32_t res[10] = {};
+    if (cudaMemcpyAsync(res, s.d_result, sizeof(res), cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) {
+        set_error(std::string("generation loop (persistent kernel): ") + cudaGetErrorString(cudaGetLastError())); return MGB_ECUDA;
+    }
+    cudaEventElapsedTime(&s.last_ms, s.ev0, s.ev1);
+    s.last_launches = g_launch_counter - l0;
+    const int t = res[0];
+    s.pos += t;
+    // keep the per-op step path (mgb_decoder_step) usable afterwards: position, slot, next codes, EOS record
+    const int32_t pos = s.pos, slot = s.pos;
+    if (cudaMemcpyAsync(s.dec_pos, &pos, 4, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+        cudaMemcpyAsync(s.dec_slot, &slot, 4, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+        cudaMemcpyAsync(s.d_codes, res + 2, 32, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+        cudaMemcpyAsync(s.d_done, res + 1, 4, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess) { set_error("generation loop: state write-back failed"); return MGB_ECUDA; }
+    *steps_run = t;
+    return MGB_OK;
+}
+
 static int run_loop(Session & s, const LoopCfg & c, int * steps_run) {
     cudaStream_t st = s.stream;
     const int B = s.B;
     if (s.pos + c.T > s.max_seq) { set_error("generation loop: KV cache too small for the requested steps"); return MGB_ERANGE; }
+    if (s.loop_grid > 0 && s.loop_tables) return run_loop_persistent(s, c, steps_run);
     std::vector<int32_t> neg(B, -1);
     if (cudaMemsetAsync(s.d_step, 0, 4, st) != cudaSuccess ||
         cudaMemcpyAsync(s.d_done, neg.data(), B * 4, cudaMemcpyHostToDevice, st) != cudaSuccess) { set_error("loop init failed"); return MGB_ECUDA; }
