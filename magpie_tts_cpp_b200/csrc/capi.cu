@@ -603,7 +603,8 @@ static int run_loop(Session & s, const LoopCfg & c, int * steps_run) {
     cudaStream_t st = s.stream;
     const int B = s.B;
     if (s.pos + c.T > s.max_seq) { set_error("generation loop: KV cache too small for the requested steps"); return MGB_ERANGE; }
-    if (s.loop_grid > 0 && s.loop_tables) return run_loop_persistent(s, c, steps_run);
+    // (the persistent kernel scans at most 6 key splits x 480 cached keys per attention item)
+    if (s.loop_grid > 0 && s.loop_tables && s.pos + c.T <= 2880) return run_loop_persistent(s, c, steps_run);
     std::vector<int32_t> neg(B, -1);
     if (cudaMemsetAsync(s.d_step, 0, 4, st) != cudaSuccess ||
         cudaMemcpyAsync(s.d_done, neg.data(), B * 4, cudaMemcpyHostToDevice, st) != cudaSuccess) { set_error("loop init failed"); return MGB_ECUDA; }

@@ -98,20 +98,6 @@ __device__ __forceinline__ void st_pkt(uint4 * p, float a, float b, float c, uns
                  ::"l"(p), "r"(__float_as_uint(a)), "r"(__float_as_uint(b)), "r"(__float_as_uint(c)), "r"(flag) : "memory");
 }
 
-enum { EPI_NONE = 0, EPI_RES = 1, EPI_GELU = 2, EPI_BIAS = 3 };
-enum { PH_QKV = 0, PH_O, PH_FF1, PH_FF2, PH_LT_IN, PH_LT_QKV, PH_LT_O, PH_LT_FF1, PH_LT_FF2, NUM_PHASE_DESC };
-
-// static description of a generic phase: poll inputs -> LayerNorm -> GEMV -> epilogue -> emit
-struct PhaseDesc {
-    int xin, npk; float * dst; int nfl;          // input exchange to poll -> dst[0, nfl)
-    const float * ln_src; int nch;               // LayerNorm(ln_src) -> S.vec when the call passes ln weights
-    const float * gin;                           // GEMV input vector (smem)
-    const bf * w;                                // resident weights (smem) or nullptr = next ring slice
-    int N, rpc, nseg;                            // rows of the matrix, rows per CTA, K / 256
-    int epi; const float * res; const float * bias;
-    int xout;
-};
-
 // ---- shared-memory state --------------------------------------------------------------------------
 struct alignas(128) LoopSmem {
     unsigned char ring[kRingBytes];
@@ -122,25 +108,18 @@ struct alignas(128) LoopSmem {
     alignas(16) float av[D];        // combined attention output; final hidden
     alignas(16) float part[24 * kPartStride];   // GEMV partial sums [row][k segment]
     alignas(16) float am[16], al[16], aacc[kCW * 64], aout[68];
-    alignas(16) float qh[DH];
+    alignas(16) float qh[DH], knew[DH], vnew[DH];
     alignas(16) float lx[LD], lx1[LD], latt[LD], lhout[LD];
     alignas(16) float lqkv[8][3 * LD];   // local transformer: [q | k | v] of every position of the frame
     alignas(16) float ltpos[8 * LD];
     alignas(16) float sc[32];
     alignas(16) float outv[24];
-    alignas(16) float red[32]; int redi[32];
+    alignas(16) float red[32], red2[32]; int redi[32];
     alignas(16) float sel_v[2048]; uint16_t sel_i[2048], srt_i[2048], rank[2048];
     unsigned hist[256]; int misc[8];
     uint64_t full_bar[kQD], empty_bar[kQD], res_bar;
     int q_off[kQD];
     volatile int stop;
-    int dbg_on, dbg_i;
-    // launch constants the non-inlined helpers need (kernel parameters must not be passed by reference: that would
-    // copy the 2 KB parameter block into every thread's local memory)
-    uint4 * xbuf; size_t rstride; int xoff[X_COUNT + 1];
-    float eps; int gelu_f16, E;
-    unsigned long long * dbg;
-    PhaseDesc desc[NUM_PHASE_DESC];
 };
 
 static_assert(sizeof(LoopSmem) + 128 <= 227 * 1024, "LoopSmem exceeds the 227 KB shared-memory limit");
@@ -236,43 +215,57 @@ __device__ void prefetch_lane(LoopSmem & S, const FrameLoopParams & p, int b) {
 }
 
 // ---- compute-side helpers ---------------------------------------------------------------------------
-// The frame is a chain of ~115 short dependent phases, so the kernel is latency bound, and instruction-cache
-// misses are latency too: a first version with every phase inlined (190 KB of SASS) ran each phase 3-5x slower
-// than the same code in a loop that fits the instruction cache.  Hence the structure below: ONE generic,
-// non-inlined `phase` (poll inputs -> LayerNorm -> GEMV -> epilogue -> emit) driven by a small descriptor,
-// plus three custom pieces (self-attention, partial combine, folded cross-attention).
-#define LOOP_STAMP() do { if (S.dbg_on && threadIdx.x == 0 && S.dbg_i < kLoopDbgStamps) S.dbg[S.dbg_i++] = gtime(); } while (0)
+// A frame is a chain of ~115 short dependent phases, so everything below is written for LATENCY, not throughput:
+// what costs time is the number of dependent instructions, shared-memory wavefronts and shuffles on the critical
+// path of a phase (measured: 100 dependent instructions ~ 0.25 us).  Hence: one packet per thread with the
+// LayerNorm statistics taken from registers, GEMV warps that load their x segment once and reuse it for several
+// rows with a transposed shuffle reduction, and an epilogue spread over the lanes of one warp.
+struct Ctx {
+    int b, ctid, cw, lane;
+    int kc;                     // consumed non-empty ring slices
+    unsigned seq;               // sequence number (flag) of the NEXT exchange
+    size_t rstride;
+    const uint4 * xin;          // the replica this CTA polls
+    bool dbg_on; int dbg_i;
+};
 
-__device__ __forceinline__ const uint4 * xin_of(const LoopSmem & S, int xb) { return S.xbuf + (size_t)(blockIdx.x % kR) * S.rstride + S.xoff[xb]; }
-__device__ __forceinline__ uint4 * xout_of(const LoopSmem & S, int xb, int replica) { return S.xbuf + (size_t)replica * S.rstride + S.xoff[xb]; }
-
-__device__ __forceinline__ const bf * ring_wait(LoopSmem & S, int kc) {
-    const int slot = kc % kQD;
-    mbar_wait(&S.full_bar[slot], (uint32_t)(kc / kQD) & 1u);
-    return reinterpret_cast<const bf *>(S.ring + S.q_off[slot]);
-}
-__device__ __forceinline__ void ring_release(LoopSmem & S, int kc, int lane) {
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&S.empty_bar[kc % kQD]);
-}
+#define LOOP_STAMP() do { if (c.dbg_on && c.ctid == 0 && c.dbg_i < kLoopDbgPerCta) p.dbg[(size_t)c.b * kLoopDbgPerCta + c.dbg_i++] = gtime(); } while (0)
 
 // profiling aids (MGB_LOOP_FLAGS): bit 0 = the prefetcher re-reads layer 0's slices (L2 hits instead of HBM),
 // bit 1 = polls do not wait (c_poll_mask = 0).  Timing experiments only: the results are garbage.
 __constant__ unsigned c_poll_mask = 0xffffffffu;
 
-// poll packets [0, n) of one exchange into dst[0, nfl) (packet i carries floats 3i .. 3i+2)
-__device__ __noinline__ void poll_vec(const uint4 * src, int n, unsigned flag, float * dst, int nfl) {
-    const int ctid = threadIdx.x;
+__device__ __forceinline__ const bf * ring_wait(LoopSmem & S, const Ctx & c) {
+    const int slot = c.kc % kQD;
+    mbar_wait(&S.full_bar[slot], (uint32_t)(c.kc / kQD) & 1u);
+    return reinterpret_cast<const bf *>(S.ring + S.q_off[slot]);
+}
+__device__ __forceinline__ void ring_release(LoopSmem & S, Ctx & c) {
+    __syncwarp();
+    if (c.lane == 0) mbar_arrive(&S.empty_bar[c.kc % kQD]);
+    c.kc++;
+}
+
+__device__ __forceinline__ uint4 poll_pkt(const uint4 * q, unsigned flag) {
+    uint4 r = ld_pkt(q);
+    while ((r.w ^ flag) & c_poll_mask) r = ld_pkt(q);
+    return r;
+}
+
+// poll packets [0, n) of one exchange into dst[0, nfl) (packet i carries floats 3i .. 3i+2); up to 3 packets per thread
+__device__ __forceinline__ void poll_vec(const uint4 * src, int n, unsigned flag, float * dst, int nfl, int ctid) {
     const unsigned mask = c_poll_mask;
     for (int i = ctid; i < n; i += 3 * kCT) {
         const int i1 = i + kCT, i2 = i + 2 * kCT;
         const uint4 * q0 = src + i, * q1 = src + i1, * q2 = src + i2;
-        uint4 v0 = ld_pkt(q0), v1 = make_uint4(0, 0, 0, flag), v2 = make_uint4(0, 0, 0, flag);
-        if (i1 < n) v1 = ld_pkt(q1);
-        if (i2 < n) v2 = ld_pkt(q2);
-        while ((v0.w ^ flag) & mask) v0 = ld_pkt(q0);
-        while ((v1.w ^ flag) & mask) v1 = ld_pkt(q1);
-        while ((v2.w ^ flag) & mask) v2 = ld_pkt(q2);
+        uint4 v0 = make_uint4(0, 0, 0, ~flag), v1 = make_uint4(0, 0, 0, i1 < n ? ~flag : flag), v2 = make_uint4(0, 0, 0, i2 < n ? ~flag : flag);
+        bool p0 = true, p1 = i1 < n, p2 = i2 < n;
+        do {                                    // all pending packets are re-polled together: one round trip per round
+            if (p0) v0 = ld_pkt(q0);
+            if (p1) v1 = ld_pkt(q1);
+            if (p2) v2 = ld_pkt(q2);
+            p0 = ((v0.w ^ flag) & mask) != 0; p1 = ((v1.w ^ flag) & mask) != 0; p2 = ((v2.w ^ flag) & mask) != 0;
+        } while (p0 || p1 || p2);
         int g = 3 * i;
         if (g < nfl) dst[g] = __uint_as_float(v0.x);
         if (g + 1 < nfl) dst[g + 1] = __uint_as_float(v0.y);
@@ -292,125 +285,128 @@ __device__ __noinline__ void poll_vec(const uint4 * src, int n, unsigned flag, f
     }
 }
 
-// partial dot products: item = (row, 256-wide k segment); part[row*kPartStride + seg].  Three items per warp pass.
-__device__ __noinline__ void gemv_part(const bf * w, int nr, int nseg, const float * x, float * part) {
-    const int cw = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int K = nseg * 256;
-    const int nitems = nr * nseg;
-    for (int it = cw; it < nitems; it += kCW * 3) {
-        float acc[3];
-        int idx[3];
+// ---- full-vector input of a phase: thread i < ceil(N/3) owns floats 3i .. 3i+2 -------------------------------------------
+template <int N> __device__ __forceinline__ void ln_weights3(const float * w, int i, float (&w3)[3]) {
 #pragma unroll
-        for (int u = 0; u < 3; u++) {
-            const int i = it + u * kCW;
-            acc[u] = 0.0f; idx[u] = -1;
-            if (i < nitems) {
-                const int row = i / nseg, seg = i - row * nseg;
-                idx[u] = row * kPartStride + seg;
-                const uint4 wv = *reinterpret_cast<const uint4 *>(w + (size_t)row * K + seg * 256 + lane * 8);
-                const float4 xa = *reinterpret_cast<const float4 *>(x + seg * 256 + lane * 8);
-                const float4 xb = *reinterpret_cast<const float4 *>(x + seg * 256 + lane * 8 + 4);
-                float a = bf16lo(wv.x) * xa.x;
-                a = fmaf(bf16hi(wv.x), xa.y, a); a = fmaf(bf16lo(wv.y), xa.z, a); a = fmaf(bf16hi(wv.y), xa.w, a);
-                a = fmaf(bf16lo(wv.z), xb.x, a); a = fmaf(bf16hi(wv.z), xb.y, a); a = fmaf(bf16lo(wv.w), xb.z, a);
-                a = fmaf(bf16hi(wv.w), xb.w, a);
-                acc[u] = a;
-            }
-        }
+    for (int q = 0; q < 3; q++) w3[q] = (i < (N + 2) / 3 && 3 * i + q < N) ? __ldg(w + 3 * i + q) : 0.0f;
+}
+// poll this thread's packet, keep the raw values in `xs` (smem, for residual adds) and in registers
+template <int N> __device__ __forceinline__ void load3_poll(const uint4 * src, unsigned flag, float * xs, int i, float (&v)[3]) {
+    v[0] = v[1] = v[2] = 0.0f;
+    if (i < (N + 2) / 3) {
+        const uint4 r = poll_pkt(src + i, flag);
+        const float t[3] = {__uint_as_float(r.x), __uint_as_float(r.y), __uint_as_float(r.z)};
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-            for (int u = 0; u < 3; u++) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
-        }
-        if (lane == 0) {
-#pragma unroll
-            for (int u = 0; u < 3; u++) if (idx[u] >= 0) part[idx[u]] = acc[u];
-        }
+        for (int q = 0; q < 3; q++) if (3 * i + q < N) { v[q] = t[q]; xs[3 * i + q] = t[q]; }
     }
 }
-
-// LayerNorm without bias (magpie.cpp:2237-2259): warps 0..nch-1 each compute the statistics of src[0, nch*128)
-// and write chunk `cw` of dst = ((src - mean) * rsqrt(var + eps)) * w; wreg = this lane's 4 weights of chunk cw.
-__device__ __noinline__ void layer_norm(const float * src, float4 wreg, float * dst, int nch, float eps) {
-    const int cw = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (cw < nch) {
-        float4 v[6];
-        float s = 0.0f;
+template <int N> __device__ __forceinline__ void load3_smem(const float * xs, int i, float (&v)[3]) {
 #pragma unroll
-        for (int j = 0; j < 6; j++) {
-            v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (j < nch) { v[j] = *reinterpret_cast<const float4 *>(src + j * 128 + lane * 4); s += (v[j].x + v[j].y) + (v[j].z + v[j].w); }
-        }
-        const float inv_n = 1.0f / (float)(nch * 128);
-        const float mean = warp_sum(s) * inv_n;
-        float q = 0.0f;
-#pragma unroll
-        for (int j = 0; j < 6; j++)
-            if (j < nch) {
-                const float a = v[j].x - mean, b2 = v[j].y - mean, c2 = v[j].z - mean, d2 = v[j].w - mean;
-                q += (a * a + b2 * b2) + (c2 * c2 + d2 * d2);
-            }
-        const float var = warp_sum(q) * inv_n;
-        const float scale = 1.0f / sqrtf(var + eps);
-        float4 m = v[0];
-#pragma unroll
-        for (int j = 1; j < 6; j++) if (j == cw) m = v[j];
-        float4 o;
-        o.x = ((m.x - mean) * scale) * wreg.x; o.y = ((m.y - mean) * scale) * wreg.y;
-        o.z = ((m.z - mean) * scale) * wreg.z; o.w = ((m.w - mean) * scale) * wreg.w;
-        *reinterpret_cast<float4 *>(dst + cw * 128 + lane * 4) = o;
-    }
+    for (int q = 0; q < 3; q++) v[q] = (i < (N + 2) / 3 && 3 * i + q < N) ? xs[3 * i + q] : 0.0f;
 }
-__device__ __forceinline__ float4 ln_weight(const float * w, int nch) {
-    const int cw = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    return cw < nch ? __ldg(reinterpret_cast<const float4 *>(w + cw * 128 + lane * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-}
-
-// one generic phase (descriptor pi); returns true if a ring slice was consumed
-__device__ __noinline__ bool phase(LoopSmem & S, int pi, const float * ln_w, bool do_poll, int kc, unsigned seq) {
-    const PhaseDesc & a = S.desc[pi];
-    const int ctid = threadIdx.x, lane = ctid & 31;
-    float4 wr = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (ln_w) wr = ln_weight(ln_w, a.nch);
-    if (do_poll) {
-        poll_vec(xin_of(S, a.xin), a.npk, seq - 1, a.dst, a.nfl);
-        cbar();
-    }
-    LOOP_STAMP();
-    if (ln_w) {
-        layer_norm(a.ln_src, wr, S.vec, a.nch, S.eps);
-        cbar();
-    }
-    const int rpc = a.rpc, nseg = a.nseg;
-    const int r0 = blockIdx.x * rpc, nr = max(0, min(rpc, a.N - r0));
-    bool used_ring = false;
-    if (nr > 0) {
-        const bf * w = a.w;
-        if (!w) { w = ring_wait(S, kc); used_ring = true; }
-        gemv_part(w, nr, nseg, a.gin, S.part);
-        if (used_ring) ring_release(S, kc, lane);
+// LayerNorm without bias (magpie.cpp:2237-2259) of the vector held 3-per-thread in registers -> out (smem).
+// Statistics in one pass (sum, sum of squares): two warp reductions + one barrier.  Ends with a barrier.
+template <int N>
+__device__ __forceinline__ void ln3(LoopSmem & S, const float (&v)[3], const float (&w3)[3], float * out, float eps, const Ctx & c) {
+    float s = (v[0] + v[1]) + v[2], ss = fmaf(v[0], v[0], fmaf(v[1], v[1], v[2] * v[2]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); ss += __shfl_xor_sync(0xffffffffu, ss, o); }
+    if (c.lane == 0) { S.red[c.cw] = s; S.red2[c.cw] = ss; }
+    cbar();
+    const float4 a0 = *reinterpret_cast<const float4 *>(S.red), a1 = *reinterpret_cast<const float4 *>(S.red + 4),
+                 a2 = *reinterpret_cast<const float4 *>(S.red + 8), a3 = *reinterpret_cast<const float4 *>(S.red + 12);
+    const float4 b0 = *reinterpret_cast<const float4 *>(S.red2), b1 = *reinterpret_cast<const float4 *>(S.red2 + 4),
+                 b2 = *reinterpret_cast<const float4 *>(S.red2 + 8), b3 = *reinterpret_cast<const float4 *>(S.red2 + 12);
+    const float ts = (((a0.x + a0.y) + (a0.z + a0.w)) + ((a1.x + a1.y) + (a1.z + a1.w))) + (((a2.x + a2.y) + (a2.z + a2.w)) + ((a3.x + a3.y) + a3.z));
+    const float tss = (((b0.x + b0.y) + (b0.z + b0.w)) + ((b1.x + b1.y) + (b1.z + b1.w))) + (((b2.x + b2.y) + (b2.z + b2.w)) + ((b3.x + b3.y) + b3.z));
+    const float mean = ts * (1.0f / N);
+    const float var = fmaxf(tss * (1.0f / N) - mean * mean, 0.0f);
+    const float scale = 1.0f / sqrtf(var + eps);
+    const int i = c.ctid;
+    if (i < (N + 2) / 3) {
+#pragma unroll
+        for (int q = 0; q < 3; q++) if (3 * i + q < N) out[3 * i + q] = ((v[q] - mean) * scale) * w3[q];
     }
     cbar();
-    const int npk = (nr + 2) / 3;
-    if (ctid < npk * kR) {
-        const int pk = ctid % npk, r = ctid / npk;
-        const int epi = a.epi;
-        float v[3];
+}
+
+// ---- GEMV over this CTA's nr rows: warp -> (256-wide k segment, row group); x segment loaded once per warp ---------------
+// Row sums of up to P rows are reduced together ("transposed" butterfly: 9 shuffles for 8 rows instead of 40).
+template <int P> __device__ __forceinline__ float reduce_rows(float (&a)[P], int lane, int & r) {
+    r = 0;
+    if constexpr (P >= 8) {
+        const bool up = lane & 16;
 #pragma unroll
-        for (int q = 0; q < 3; q++) {
-            const int row = 3 * pk + q;
-            float s = 0.0f;
-            if (row < nr) {
-                for (int g = 0; g < nseg; g++) s += S.part[row * kPartStride + g];
-                if (epi == EPI_RES) s += a.res[r0 + row];
-                else if (epi == EPI_GELU) s = gelu_ggml(s, S.gelu_f16);
-                else if (epi == EPI_BIAS) s += __ldg(a.bias + r0 + row);
-            }
-            v[q] = s;
-        }
-        st_pkt(xout_of(S, a.xout, r) + r0 / 3 + pk, v[0], v[1], v[2], seq);
+        for (int j = 0; j < 4; j++) { const float send = up ? a[j] : a[j + 4], keep = up ? a[j + 4] : a[j]; a[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16); }
+        r += up ? 4 : 0;
     }
-    return used_ring;
+    if constexpr (P >= 4) {
+        constexpr int lv = P >= 8 ? 8 : 16;
+        const bool up = lane & lv;
+#pragma unroll
+        for (int j = 0; j < 2; j++) { const float send = up ? a[j] : a[j + 2], keep = up ? a[j + 2] : a[j]; a[j] = keep + __shfl_xor_sync(0xffffffffu, send, lv); }
+        r += up ? 2 : 0;
+    }
+    if constexpr (P >= 2) {
+        constexpr int lv = P >= 8 ? 4 : (P >= 4 ? 8 : 16);
+        const bool up = lane & lv;
+        const float send = up ? a[0] : a[1], keep = up ? a[1] : a[0];
+        a[0] = keep + __shfl_xor_sync(0xffffffffu, send, lv);
+        r += up ? 1 : 0;
+    }
+    constexpr int rest = P >= 8 ? 2 : (P >= 4 ? 4 : (P >= 2 ? 8 : 16));
+#pragma unroll
+    for (int o = rest; o > 0; o >>= 1) a[0] += __shfl_xor_sync(0xffffffffu, a[0], o);
+    return a[0];
+}
+
+template <int NSEG, int P>      // P = rows per warp, padded to a power of two (1, 2, 4, 8)
+__device__ __forceinline__ void gemv_rows(const bf * w, int nr, const float * x, float * part, const Ctx & c) {
+    constexpr int K = NSEG * 256, WPS = kCW / NSEG;
+    const int seg = c.cw / WPS, g = c.cw - seg * WPS;
+    if (seg >= NSEG || g >= nr) return;
+    const float4 xa = *reinterpret_cast<const float4 *>(x + seg * 256 + c.lane * 8);
+    const float4 xb = *reinterpret_cast<const float4 *>(x + seg * 256 + c.lane * 8 + 4);
+    float acc[P];
+#pragma unroll
+    for (int r = 0; r < P; r++) {
+        const int row = g + r * WPS;
+        acc[r] = 0.0f;
+        if (row < nr) {
+            const uint4 wv = *reinterpret_cast<const uint4 *>(w + (size_t)row * K + seg * 256 + c.lane * 8);
+            float a = bf16lo(wv.x) * xa.x;
+            a = fmaf(bf16hi(wv.x), xa.y, a); a = fmaf(bf16lo(wv.y), xa.z, a); a = fmaf(bf16hi(wv.y), xa.w, a);
+            a = fmaf(bf16lo(wv.z), xb.x, a); a = fmaf(bf16hi(wv.z), xb.y, a); a = fmaf(bf16lo(wv.w), xb.z, a);
+            a = fmaf(bf16hi(wv.w), xb.w, a);
+            acc[r] = a;
+        }
+    }
+    int r;
+    const float sum = reduce_rows<P>(acc, c.lane, r);
+    const int row = g + r * WPS;
+    if ((c.lane & (32 / P - 1)) == 0 && row < nr) part[row * kPartStride + seg] = sum;
+}
+
+enum { EPI_NONE = 0, EPI_RES = 1, EPI_GELU = 2, EPI_BIAS = 3 };
+
+// epilogue + emit by warp 0: lane r finishes row r (nr <= 21), packets are assembled with shuffles
+template <int NSEG, int EPI>
+__device__ __forceinline__ void emit_rows(const LoopSmem & S, const FrameLoopParams & p, const Ctx & c, int xb, int r0, int nr,
+                                          const float * res, const float * bias, const float * add2) {
+    if (c.cw != 0 || nr <= 0) return;
+    float s = 0.0f;
+    if (c.lane < nr) {
+        s = S.part[c.lane * kPartStride];
+#pragma unroll
+        for (int g = 1; g < NSEG; g++) s += S.part[c.lane * kPartStride + g];
+        if (EPI == EPI_RES) s += res[r0 + c.lane];
+        else if (EPI == EPI_GELU) s = gelu_ggml(s, p.gelu_f16);
+        else if (EPI == EPI_BIAS) s += __ldg(bias + r0 + c.lane) + add2[r0 + c.lane];
+    }
+    const int npk = (nr + 2) / 3;
+    const int pk = c.lane % npk, rep = c.lane / npk;
+    const float v0 = __shfl_sync(0xffffffffu, s, 3 * pk), v1 = __shfl_sync(0xffffffffu, s, 3 * pk + 1), v2 = __shfl_sync(0xffffffffu, s, 3 * pk + 2);
+    if (c.lane < npk * kR) st_pkt(p.xbuf + (size_t)rep * c.rstride + p.xoff[xb] + r0 / 3 + pk, v0, v1, v2, c.seq);
 }
 
 __device__ __forceinline__ bool better(float v, int i, float bv, int bi) { return v > bv || (v == bv && i < bi); }
@@ -430,6 +426,7 @@ __device__ __noinline__ int cta_argmax(LoopSmem & S, const float * v, int n) {
     cbar();
     bv = S.red[0]; bi = S.redi[0];
     for (int w = 1; w < kCW; w++) if (better(S.red[w], S.redi[w], bv, bi)) { bv = S.red[w]; bi = S.redi[w]; }
+    cbar();
     return bi;
 }
 
@@ -477,7 +474,7 @@ __device__ __noinline__ int cta_sample_top_k(LoopSmem & S, float * logits, int V
     }
     cbar();
     float * srt_v = logits;
-    // rank by counting -> sorted (value desc, index asc); ranks are kept in srt_i's slot until everybody is done reading
+    // rank by counting -> sorted (value desc, index asc)
     for (int a = tid; a < k; a += kCT) {
         const float va = S.sel_v[a]; const int ia = S.sel_i[a];
         int r = 0;
@@ -488,7 +485,10 @@ __device__ __noinline__ int cta_sample_top_k(LoopSmem & S, float * logits, int V
     for (int a = tid; a < k; a += kCT) { const int r = S.rank[a]; srt_v[r] = S.sel_v[a]; S.srt_i[r] = S.sel_i[a]; }
     cbar();
     const float mx = srt_v[0];
-    for (int a = tid; a < k; a += kCT) S.sel_v[a] = expf((srt_v[a] - mx) / temperature);
+    float ex[5];
+    { int n = 0; for (int a = tid; a < k; a += kCT, n++) ex[n] = expf((srt_v[a] - mx) / temperature); }
+    cbar();
+    { int n = 0; for (int a = tid; a < k; a += kCT, n++) S.sel_v[a] = ex[n]; }
     cbar();
     if (tid == 0) {
         float sum = 0.0f;
@@ -504,19 +504,40 @@ __device__ __noinline__ int cta_sample_top_k(LoopSmem & S, float * logits, int V
 }
 
 // ---- self-attention partial of item (head h, key split sp): keys [k0, k1) --------------------------------------------
-__device__ __noinline__ void attention_item(LoopSmem & S, bf * kcl, bf * vcl, int h, int k0, int k1, int pos, unsigned seq) {
-    const int ctid = threadIdx.x, cw = ctid >> 5, lane = ctid & 31;
-    const unsigned flag = seq - 1;
+// Latency structure: the K / V rows of the OLD keys do not depend on this step, so their loads are issued before the
+// wait for q; the new key (position pos, last split only) is taken from the exchange, not from the cache, and its
+// cache rows are written off the critical path.
+__device__ __forceinline__ void attention_item(LoopSmem & S, const FrameLoopParams & p, Ctx & c, bf * kcl, bf * vcl,
+                                               int h, int k0, int k1, int pos) {
+    const int cw = c.cw, lane = c.lane, ctid = c.ctid;
+    const unsigned flag = c.seq - 1;
     const bool has_new = pos >= k0 && pos < k1;
-    // q_h -> smem; for the split that holds the new key, k_h / v_h of this step go straight into the cache (bf16).
-    // bar.sync orders these global writes before the loads below (same CTA).
+    const int ke = has_new ? k1 - 1 : k1;                       // old keys [k0, ke); pos == k1 - 1 when has_new
+    const int nw = min(kCW, (ke - k0 + 31) / 32);                // warps holding a chunk (one chunk per warp: per <= 480)
+    // 1. old keys: this warp's chunk of 32 keys; loads in flight while q is awaited
+    const int c0 = k0 + cw * 32, j = c0 + lane;
+    const int cnt = max(0, min(32, ke - c0));
+    uint4 kv[8];
+    uint32_t vraw[32];
+    if (j < ke) {
+        const bf * kr = kcl + (size_t)j * D + h * DH;
+#pragma unroll
+        for (int q = 0; q < 8; q++) kv[q] = __ldcg(reinterpret_cast<const uint4 *>(kr) + q);
+    } else {
+#pragma unroll
+        for (int q = 0; q < 8; q++) kv[q] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    {
+        const bf * vbase = vcl + (size_t)c0 * D + h * DH + lane * 2;
+#pragma unroll
+        for (int jj = 0; jj < 32; jj++) vraw[jj] = jj < cnt ? __ldcg(reinterpret_cast<const uint32_t *>(vbase + (size_t)jj * D)) : 0u;
+    }
+    // 2. q_h (all items) and k_h / v_h of this step (last split): warps 0..2 poll <= 23 packets each
     if (cw < 3 && (cw == 0 || has_new)) {
         const int f0 = cw * D + h * DH;
         const int p0 = f0 / 3, p1 = (f0 + DH - 1) / 3;
         if (lane <= p1 - p0) {
-            const uint4 * q = xin_of(S, X_QKV) + p0 + lane;
-            uint4 v = ld_pkt(q);
-            while ((v.w ^ flag) & c_poll_mask) v = ld_pkt(q);
+            const uint4 v = poll_pkt(c.xin + p.xoff[X_QKV] + p0 + lane, flag);
             const int g = 3 * (p0 + lane) - f0;
             const float vv[3] = {__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z)};
 #pragma unroll
@@ -524,7 +545,11 @@ __device__ __noinline__ void attention_item(LoopSmem & S, bf * kcl, bf * vcl, in
                 const int gi = g + q3;
                 if (gi >= 0 && gi < DH) {
                     if (cw == 0) S.qh[gi] = vv[q3];
-                    else (cw == 1 ? kcl : vcl)[(size_t)pos * D + h * DH + gi] = __float2bfloat16_rn(vv[q3]);
+                    else {          // the cache holds bf16: use the rounded value now, as later steps will
+                        const bf r = __float2bfloat16_rn(vv[q3]);
+                        (cw == 1 ? S.knew : S.vnew)[gi] = __bfloat162float(r);
+                        (cw == 1 ? kcl : vcl)[(size_t)pos * D + h * DH + gi] = r;
+                    }
                 }
             }
         }
@@ -532,51 +557,52 @@ __device__ __noinline__ void attention_item(LoopSmem & S, bf * kcl, bf * vcl, in
     cbar();
     LOOP_STAMP();
     float mx = -INFINITY, lsum = 0.0f, acc0 = 0.0f, acc1 = 0.0f;       // lane owns dims 2*lane, 2*lane+1
-    for (int c0 = k0 + cw * 32; c0 < k1; c0 += kCW * 32) {
-        const int j = c0 + lane;
-        const int cnt = min(32, k1 - c0);
-        // issue the value loads of the whole chunk first: they do not depend on the scores
-        const bf * vbase = vcl + (size_t)c0 * D + h * DH + lane * 2;
-        uint32_t vraw[32];
-#pragma unroll
-        for (int jj = 0; jj < 32; jj++) vraw[jj] = jj < cnt ? __ldcg(reinterpret_cast<const uint32_t *>(vbase + (size_t)jj * D)) : 0u;
+    if (cw < nw) {
         float s = -INFINITY;
-        if (j < k1) {
-            const bf * kr = kcl + (size_t)j * D + h * DH;
-            uint4 kv[8];
-#pragma unroll
-            for (int q = 0; q < 8; q++) kv[q] = __ldcg(reinterpret_cast<const uint4 *>(kr) + q);
-            float dsum = 0.0f;
+        if (j < ke) {
+            float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f, d3 = 0.0f;
 #pragma unroll
             for (int q = 0; q < 8; q++) {
                 const float4 qa = *reinterpret_cast<const float4 *>(S.qh + q * 8), qb = *reinterpret_cast<const float4 *>(S.qh + q * 8 + 4);
-                dsum = fmaf(bf16lo(kv[q].x), qa.x, dsum); dsum = fmaf(bf16hi(kv[q].x), qa.y, dsum);
-                dsum = fmaf(bf16lo(kv[q].y), qa.z, dsum); dsum = fmaf(bf16hi(kv[q].y), qa.w, dsum);
-                dsum = fmaf(bf16lo(kv[q].z), qb.x, dsum); dsum = fmaf(bf16hi(kv[q].z), qb.y, dsum);
-                dsum = fmaf(bf16lo(kv[q].w), qb.z, dsum); dsum = fmaf(bf16hi(kv[q].w), qb.w, dsum);
+                d0 = fmaf(bf16lo(kv[q].x), qa.x, d0); d1 = fmaf(bf16hi(kv[q].x), qa.y, d1);
+                d2 = fmaf(bf16lo(kv[q].y), qa.z, d2); d3 = fmaf(bf16hi(kv[q].y), qa.w, d3);
+                d0 = fmaf(bf16lo(kv[q].z), qb.x, d0); d1 = fmaf(bf16hi(kv[q].z), qb.y, d1);
+                d2 = fmaf(bf16lo(kv[q].w), qb.z, d2); d3 = fmaf(bf16hi(kv[q].w), qb.w, d3);
             }
-            s = dsum * 0.125f;                                        // 1/sqrt(64)
+            s = ((d0 + d1) + (d2 + d3)) * 0.125f;                     // 1/sqrt(64)
         }
-        const float mnew = fmaxf(mx, warp_max(s));
-        const float corr = expf(mx - mnew);
-        const float pj = (j < k1) ? expf(s - mnew) : 0.0f;
-        lsum = lsum * corr + warp_sum(pj);
-        acc0 *= corr; acc1 *= corr;
+        mx = warp_max(s);
+        const float pj = (j < ke) ? expf(s - mx) : 0.0f;
+        lsum = warp_sum(pj);
+        float a0 = 0.0f, a1 = 0.0f, b0 = 0.0f, b1 = 0.0f;
 #pragma unroll
-        for (int jj = 0; jj < 32; jj++) {
-            const float pb = __shfl_sync(0xffffffffu, pj, jj);
-            acc0 = fmaf(pb, bf16lo(vraw[jj]), acc0); acc1 = fmaf(pb, bf16hi(vraw[jj]), acc1);
+        for (int jj = 0; jj < 32; jj += 2) {
+            const float pa = __shfl_sync(0xffffffffu, pj, jj), pb = __shfl_sync(0xffffffffu, pj, jj + 1);
+            a0 = fmaf(pa, bf16lo(vraw[jj]), a0); a1 = fmaf(pa, bf16hi(vraw[jj]), a1);
+            b0 = fmaf(pb, bf16lo(vraw[jj + 1]), b0); b1 = fmaf(pb, bf16hi(vraw[jj + 1]), b1);
         }
+        acc0 = a0 + b0; acc1 = a1 + b1;
+    }
+    if (has_new && cw == nw % kCW) {          // the new key: one more online-softmax update on a warp of its own if there is one
+        const float s = warp_sum(fmaf(S.knew[lane], S.qh[lane], S.knew[lane + 32] * S.qh[lane + 32])) * 0.125f;
+        const float mnew = fmaxf(mx, s);
+        const float corr = (mx == -INFINITY) ? 0.0f : expf(mx - mnew);
+        const float pn = expf(s - mnew);
+        lsum = lsum * corr + pn;
+        acc0 = fmaf(pn, S.vnew[lane * 2], acc0 * corr); acc1 = fmaf(pn, S.vnew[lane * 2 + 1], acc1 * corr);
         mx = mnew;
     }
-    if (lane == 0) { S.am[cw] = mx; S.al[cw] = lsum; }
-    S.aacc[cw * 64 + lane * 2] = acc0; S.aacc[cw * 64 + lane * 2 + 1] = acc1;
+    const int nm = has_new ? max(nw, nw % kCW + 1) : nw;        // warps that hold a partial
+    if (cw < nm) {
+        if (lane == 0) { S.am[cw] = mx; S.al[cw] = lsum; }
+        S.aacc[cw * 64 + lane * 2] = acc0; S.aacc[cw * 64 + lane * 2 + 1] = acc1;
+    }
     cbar();
     if (ctid < 64) {
         float M = S.am[0];
-        for (int w = 1; w < kCW; w++) M = fmaxf(M, S.am[w]);
+        for (int w = 1; w < nm; w++) M = fmaxf(M, S.am[w]);
         float Ls = 0.0f, o = 0.0f;
-        for (int w = 0; w < kCW; w++) {
+        for (int w = 0; w < nm; w++) {
             const float fct = (S.am[w] == -INFINITY) ? 0.0f : expf(S.am[w] - M);
             Ls += fct * S.al[w]; o += fct * S.aacc[w * 64 + ctid];
         }
@@ -586,16 +612,16 @@ __device__ __noinline__ void attention_item(LoopSmem & S, bf * kcl, bf * vcl, in
     cbar();
     if (ctid < 22 * kR) {
         const int pk = ctid % 22, r = ctid / 22;
-        st_pkt(xout_of(S, X_ATT, r) + blockIdx.x * 22 + pk, S.aout[3 * pk], S.aout[3 * pk + 1], S.aout[3 * pk + 2], seq);
+        st_pkt(p.xbuf + (size_t)r * c.rstride + p.xoff[X_ATT] + c.b * 22 + pk, S.aout[3 * pk], S.aout[3 * pk + 1], S.aout[3 * pk + 2], c.seq);
     }
 }
 
 // ---- combine the attention partials of all (head, split) items -> S.av ------------------------------------------------
-__device__ __noinline__ void attention_combine(LoopSmem & S, int S_split, unsigned seq) {
-    poll_vec(xin_of(S, X_ATT), H * S_split * 22, seq - 1, S.vec, H * S_split * 66);
+__device__ __forceinline__ void attention_combine(LoopSmem & S, const FrameLoopParams & p, Ctx & c, int S_split) {
+    poll_vec(c.xin + p.xoff[X_ATT], H * S_split * 22, c.seq - 1, S.vec, H * S_split * 66, c.ctid);
     cbar();
     LOOP_STAMP();
-    for (int i = threadIdx.x; i < D; i += kCT) {
+    for (int i = c.ctid; i < D; i += kCT) {
         const int hh = i / DH, dd = i % DH;
         const float * ph = S.vec + hh * S_split * 66;
         float M = -INFINITY;
@@ -612,25 +638,24 @@ __device__ __noinline__ void attention_combine(LoopSmem & S, int S_split, unsign
 }
 
 // ---- folded cross-attention: x += softmax(M_l LN(x)) N_l  (rows of this CTA) -----------------------------------------------
-__device__ __noinline__ void cross_attention(LoopSmem & S, const float * xm, const float * xn, const float * n_xq, unsigned seq) {
-    const int ctid = threadIdx.x, cw = ctid >> 5, lane = ctid & 31, E = S.E;
-    const float4 wr = ln_weight(n_xq, D / 128);
-    const int r0 = blockIdx.x * RO, nr = max(0, min(RO, D - r0));
+__device__ __forceinline__ void cross_attention(LoopSmem & S, const FrameLoopParams & p, Ctx & c, const LoopLayer & Ly) {
+    const int cw = c.cw, lane = c.lane, E = p.E;
+    float w3[3], v[3];
+    ln_weights3<D>(Ly.n_xq, c.ctid, w3);
+    const int r0 = c.b * RO, nr = max(0, min(RO, D - r0));
     // the tables are activation independent: fetch this warp's rows before waiting for x
     const int j0 = cw, j1 = cw + kCW;
     float4 m0[6], m1[6];
 #pragma unroll
     for (int q = 0; q < 6; q++) {
-        m0[q] = j0 < E ? __ldg(reinterpret_cast<const float4 *>(xm + (size_t)j0 * D + q * 128 + lane * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        m1[q] = j1 < E ? __ldg(reinterpret_cast<const float4 *>(xm + (size_t)j1 * D + q * 128 + lane * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        m0[q] = j0 < E ? __ldg(reinterpret_cast<const float4 *>(Ly.xm + (size_t)j0 * D + q * 128 + lane * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        m1[q] = j1 < E ? __ldg(reinterpret_cast<const float4 *>(Ly.xm + (size_t)j1 * D + q * 128 + lane * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     float nval = 0.0f;
-    if (cw < nr && lane < E) nval = __ldg(xn + (size_t)lane * D + r0 + cw);
-    poll_vec(xin_of(S, X_XA), D / 3, seq - 1, S.xs, D);
-    cbar();
+    if (cw < nr && lane < E) nval = __ldg(Ly.xn + (size_t)lane * D + r0 + cw);
+    load3_poll<D>(c.xin + p.xoff[X_XA], c.seq - 1, S.xs, c.ctid, v);
     LOOP_STAMP();
-    layer_norm(S.xs, wr, S.vec, D / 128, S.eps);
-    cbar();
+    ln3<D>(S, v, w3, S.vec, p.eps, c);
     float d0 = 0.0f, d1 = 0.0f;
 #pragma unroll
     for (int q = 0; q < 6; q++) {
@@ -638,22 +663,25 @@ __device__ __noinline__ void cross_attention(LoopSmem & S, const float * xm, con
         d0 = fmaf(m0[q].x, xv.x, d0); d0 = fmaf(m0[q].y, xv.y, d0); d0 = fmaf(m0[q].z, xv.z, d0); d0 = fmaf(m0[q].w, xv.w, d0);
         d1 = fmaf(m1[q].x, xv.x, d1); d1 = fmaf(m1[q].y, xv.y, d1); d1 = fmaf(m1[q].z, xv.z, d1); d1 = fmaf(m1[q].w, xv.w, d1);
     }
-    d0 = warp_sum(d0); d1 = warp_sum(d1);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { d0 += __shfl_xor_sync(0xffffffffu, d0, o); d1 += __shfl_xor_sync(0xffffffffu, d1, o); }
     if (lane == 0) { if (j0 < E) S.sc[j0] = d0; if (j1 < E) S.sc[j1] = d1; }
     cbar();
+    // softmax over the E tokens and this CTA's output rows: warp r < nr computes row r, warp 0 emits
     if (cw < nr) {
         const float sj = lane < E ? S.sc[lane] : -INFINITY;
         const float mxs = warp_max(sj);
         const float e = lane < E ? expf(sj - mxs) : 0.0f;
-        const float sum = warp_sum(e);
-        const float o = warp_sum(e * nval);
+        float sum = e, o = e * nval;
+#pragma unroll
+        for (int of = 16; of > 0; of >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, of); o += __shfl_xor_sync(0xffffffffu, o, of); }
         if (lane == 0) S.outv[cw] = o * (1.0f / sum) + S.xs[r0 + cw];
     }
     cbar();
     const int npk = (nr + 2) / 3;
-    if (ctid < npk * kR) {
-        const int pk = ctid % npk, r = ctid / npk;
-        st_pkt(xout_of(S, X_XB, r) + r0 / 3 + pk, S.outv[3 * pk], S.outv[3 * pk + 1], S.outv[3 * pk + 2], seq);
+    if (c.ctid < npk * kR) {
+        const int pk = c.ctid % npk, r = c.ctid / npk;
+        st_pkt(p.xbuf + (size_t)r * c.rstride + p.xoff[X_XB] + r0 / 3 + pk, S.outv[3 * pk], S.outv[3 * pk + 1], S.outv[3 * pk + 2], c.seq);
     }
 }
 
@@ -666,59 +694,56 @@ __global__ void __launch_bounds__(kThreads, 1) frame_loop_kernel(const FrameLoop
     if (tid == 0) {
         for (int i = 0; i < kQD; i++) { mbar_init(&S.full_bar[i], 1); mbar_init(&S.empty_bar[i], kCW); S.q_off[i] = 0; }
         mbar_init(&S.res_bar, 1);
-        S.stop = 0; S.dbg_on = 0; S.dbg_i = 0;
-        S.xbuf = p.xbuf; S.rstride = (size_t)p.xoff[X_COUNT];
-        for (int i = 0; i <= X_COUNT; i++) S.xoff[i] = p.xoff[i];
-        S.eps = p.eps; S.gelu_f16 = p.gelu_f16; S.E = p.E; S.dbg = p.dbg;
-        //                     xin     npk           dst     nfl  ln_src  nch       gin     w         N       rpc   nseg      epi       res    bias       xout
-        S.desc[PH_QKV]    = {X_XC,   D / 3,        S.xs,   D,   S.xs,   D / 128,  S.vec,  nullptr,  3 * D,  RQ,   D / 256,  EPI_NONE, nullptr, nullptr,  X_QKV};
-        S.desc[PH_O]      = {-1,     0,            nullptr, 0,  nullptr, 0,       S.av,   nullptr,  D,      RO,   D / 256,  EPI_RES,  S.xs,  nullptr,    X_XA};
-        S.desc[PH_FF1]    = {X_XB,   D / 3,        S.xs,   D,   S.xs,   D / 128,  S.vec,  nullptr,  F,      RF1,  D / 256,  EPI_GELU, nullptr, nullptr,  X_H};
-        S.desc[PH_FF2]    = {X_H,    F / 3,        S.vec,  F,   nullptr, 0,       S.vec,  nullptr,  D,      RF2,  F / 256,  EPI_RES,  S.xs,  nullptr,    X_XC};
-        S.desc[PH_LT_IN]  = {-1,     0,            nullptr, 0,  nullptr, 0,       S.av,   S.w_in,   LD,     RIN,  D / 256,  EPI_BIAS, nullptr, p.lt_in_b, T_SEQ0};
-        S.desc[PH_LT_QKV] = {-1,     0,            nullptr, 0,  S.lx,   LD / 128, S.vec,  S.w_qkv,  3 * LD, RLQ,  1,        EPI_NONE, nullptr, nullptr,  T_QKV};
-        S.desc[PH_LT_O]   = {-1,     0,            nullptr, 0,  nullptr, 0,       S.latt, S.w_o,    LD,     RLO,  1,        EPI_RES,  S.lx,  nullptr,    T_X1};
-        S.desc[PH_LT_FF1] = {T_X1,   (LD + 2) / 3, S.lx1,  LD,  S.lx1,  LD / 128, S.vec,  S.w_ff1,  LF,     RLF1, 1,        EPI_GELU, nullptr, nullptr,  T_H};
-        S.desc[PH_LT_FF2] = {T_H,    (LF + 2) / 3, S.vec,  LF,  nullptr, 0,       S.vec,  S.w_ff2,  LD,     RLF2, LF / 256, EPI_RES,  S.lx1, nullptr,    T_HOUT};
+        S.stop = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (tid < 32) { S.red[tid] = 0.0f; S.red2[tid] = 0.0f; }
     __syncthreads();
     if (warp == kCW) {
         if (lane == 0) prefetch_lane(S, p, b);
         return;
     }
 
-    const int ctid = tid, cw = warp;
-    int kc = 0;                              // consumed non-empty ring slices
-    unsigned seq = *p.seq;                   // sequence number (flag) of the NEXT exchange
+    Ctx c;
+    c.b = b; c.ctid = tid; c.cw = warp; c.lane = lane; c.kc = 0;
+    c.seq = *p.seq; c.rstride = (size_t)p.xoff[X_COUNT];
+    c.xin = p.xbuf + (size_t)(b % kR) * c.rstride;
+    c.dbg_on = false; c.dbg_i = 0;
     const int V = p.V, L = p.L;
+    const int ctid = c.ctid, cw = c.cw;
     const float lt_scale = 1.0f / sqrtf((float)LD);
 
     for (int i = ctid; i < 8 * LD; i += kCT) S.ltpos[i] = p.lt_pos[i];
 
-    // decoder-input embedding accumulators: x0 = (sum_cb E_cb[code_cb]) / 8 + pos_emb   (magpie.cpp:2746-2787)
-    const int e0 = ctid, e1 = ctid + kCT;
-    float emb0 = 0.0f, emb1 = 0.0f;
-    for (int cb = 0; cb < 8; cb++) {
-        const int code = p.codes_io[cb];
-        const float a = p.audio_emb[cb][(size_t)code * D + e0];
-        const float a1 = e1 < D ? p.audio_emb[cb][(size_t)code * D + e1] : 0.0f;
-        emb0 = cb == 0 ? a : emb0 + a; emb1 = cb == 0 ? a1 : emb1 + a1;
+    // decoder-input embedding accumulators: x0 = (sum_cb E_cb[code_cb]) / 8 + pos_emb   (magpie.cpp:2746-2787);
+    // thread i < 256 owns elements 3i .. 3i+2 (the same mapping as the exchange packets)
+    const bool own3 = ctid < D / 3;
+    float emb[3] = {0.0f, 0.0f, 0.0f}, pe[3] = {0.0f, 0.0f, 0.0f};
+    if (own3) {
+        for (int cb = 0; cb < 8; cb++) {
+            const int code = p.codes_io[cb];
+#pragma unroll
+            for (int q = 0; q < 3; q++) { const float a = p.audio_emb[cb][(size_t)code * D + 3 * ctid + q]; emb[q] = cb == 0 ? a : emb[q] + a; }
+        }
+#pragma unroll
+        for (int q = 0; q < 3; q++) pe[q] = p.dec_pos[(size_t)p.pos0 * D + 3 * ctid + q];
     }
-    float pe0 = p.dec_pos[(size_t)p.pos0 * D + e0], pe1 = e1 < D ? p.dec_pos[(size_t)p.pos0 * D + e1] : 0.0f;
+    const bool own3l = ctid < (LD + 2) / 3;
     int eos_step = -1, frames = 0;
+    cbar();
 
     for (int t = 0; t < p.n_steps; t++) {
         const int pos = p.pos0 + t, nk = pos + 1;
         const size_t row = (size_t)p.row0 + t;
-        if (ctid == 0) S.dbg_on = (p.dbg != nullptr && b == 0 && t == p.n_steps - 1) ? 1 : 0;
-        S.xs[e0] = emb0 * 0.125f + pe0;
-        if (e1 < D) S.xs[e1] = emb1 * 0.125f + pe1;
-        cbar();
+        c.dbg_on = p.dbg != nullptr && t == p.n_steps - 1;
         LOOP_STAMP();
-        if (t + 1 < p.n_steps) {            // next frame's position row: fetched a whole frame ahead
-            pe0 = __ldg(p.dec_pos + (size_t)(pos + 1) * D + e0);
-            if (e1 < D) pe1 = __ldg(p.dec_pos + (size_t)(pos + 1) * D + e1);
+        float xv[3];
+#pragma unroll
+        for (int q = 0; q < 3; q++) xv[q] = emb[q] * 0.125f + pe[q];
+        if (own3) { S.xs[3 * ctid] = xv[0]; S.xs[3 * ctid + 1] = xv[1]; S.xs[3 * ctid + 2] = xv[2]; }
+        if (own3 && t + 1 < p.n_steps) {      // next frame's position row: fetched a whole frame ahead
+#pragma unroll
+            for (int q = 0; q < 3; q++) pe[q] = __ldg(p.dec_pos + (size_t)(pos + 1) * D + 3 * ctid + q);
         }
 
         const int S_split = min(kMaxSplit, max(1, (nk + 127) / 128));
@@ -726,45 +751,93 @@ __global__ void __launch_bounds__(kThreads, 1) frame_loop_kernel(const FrameLoop
         for (int l = 0; l < L; l++) {
             const LoopLayer & Ly = p.layer[l];
             // ---- P1: LN -> QKV ---------------------------------------------------------------------------
-            if (phase(S, PH_QKV, Ly.n_self, l > 0, kc, seq)) kc++;
-            seq++;
+            {
+                float w3[3];
+                ln_weights3<D>(Ly.n_self, ctid, w3);
+                if (l > 0) load3_poll<D>(c.xin + p.xoff[X_XC], c.seq - 1, S.xs, ctid, xv);
+                LOOP_STAMP();
+                ln3<D>(S, xv, w3, S.vec, p.eps, c);
+                const int r0 = b * RQ, nr = max(0, min(RQ, 3 * D - r0));
+                if (nr > 0) {
+                    const bf * w = ring_wait(S, c);
+                    gemv_rows<D / 256, 4>(w, nr, S.vec, S.part, c);
+                    ring_release(S, c);
+                }
+                cbar();
+                emit_rows<D / 256, EPI_NONE>(S, p, c, X_QKV, r0, nr, nullptr, nullptr, nullptr);
+                c.seq++;
+            }
             LOOP_STAMP();
             // ---- P2: attention partials, item (head, key split) --------------------------------------------
             if (b < H * S_split) {
                 const int h = b / S_split, sp = b % S_split;
                 const int per = (nk + S_split - 1) / S_split;
-                attention_item(S, (bf *)p.kcache + (size_t)l * p.kv_layer_stride, (bf *)p.vcache + (size_t)l * p.kv_layer_stride,
-                               h, sp * per, min(nk, sp * per + per), pos, seq);
+                attention_item(S, p, c, (bf *)p.kcache + (size_t)l * p.kv_layer_stride, (bf *)p.vcache + (size_t)l * p.kv_layer_stride,
+                               h, sp * per, min(nk, sp * per + per), pos);
             }
-            seq++;
+            c.seq++;
             LOOP_STAMP();
             // ---- P3: combine partials -> attention output; O projection + residual -------------------------
-            attention_combine(S, S_split, seq);
-            if (phase(S, PH_O, nullptr, false, kc, seq)) kc++;
-            seq++;
+            {
+                attention_combine(S, p, c, S_split);
+                const int r0 = b * RO, nr = max(0, min(RO, D - r0));
+                if (nr > 0) {
+                    const bf * w = ring_wait(S, c);
+                    gemv_rows<D / 256, 2>(w, nr, S.av, S.part, c);
+                    ring_release(S, c);
+                }
+                cbar();
+                emit_rows<D / 256, EPI_RES>(S, p, c, X_XA, r0, nr, S.xs, nullptr, nullptr);
+                c.seq++;
+            }
             LOOP_STAMP();
             // ---- P4: LN -> folded cross-attention + residual ---------------------------------------------------
-            cross_attention(S, Ly.xm, Ly.xn, Ly.n_xq, seq);
-            seq++;
+            cross_attention(S, p, c, Ly);
+            c.seq++;
             LOOP_STAMP();
             // ---- P5: LN -> FFN1 -> GELU ------------------------------------------------------------------------
-            if (phase(S, PH_FF1, Ly.n_ff, true, kc, seq)) kc++;
-            seq++;
+            {
+                float w3[3];
+                ln_weights3<D>(Ly.n_ff, ctid, w3);
+                load3_poll<D>(c.xin + p.xoff[X_XB], c.seq - 1, S.xs, ctid, xv);
+                LOOP_STAMP();
+                ln3<D>(S, xv, w3, S.vec, p.eps, c);
+                const int r0 = b * RF1, nr = max(0, min(RF1, F - r0));
+                if (nr > 0) {
+                    const bf * w = ring_wait(S, c);
+                    gemv_rows<D / 256, 8>(w, nr, S.vec, S.part, c);
+                    ring_release(S, c);
+                }
+                cbar();
+                emit_rows<D / 256, EPI_GELU>(S, p, c, X_H, r0, nr, nullptr, nullptr, nullptr);
+                c.seq++;
+            }
             LOOP_STAMP();
             // ---- P6: FFN2 + residual ---------------------------------------------------------------------------
-            if (phase(S, PH_FF2, nullptr, true, kc, seq)) kc++;
-            seq++;
+            {
+                poll_vec(c.xin + p.xoff[X_H], F / 3, c.seq - 1, S.vec, F, ctid);
+                cbar();
+                LOOP_STAMP();
+                const int r0 = b * RF2, nr = max(0, min(RF2, D - r0));
+                if (nr > 0) {
+                    const bf * w = ring_wait(S, c);
+                    gemv_rows<F / 256, 8>(w, nr, S.vec, S.part, c);
+                    ring_release(S, c);
+                }
+                cbar();
+                emit_rows<F / 256, EPI_RES>(S, p, c, X_XC, r0, nr, S.xs, nullptr, nullptr);
+                c.seq++;
+            }
             LOOP_STAMP();
         }
 
         // ---- final LayerNorm -> hidden (every CTA holds it) ------------------------------------------------------
         {
-            const float4 wr = ln_weight(p.norm_out, D / 128);
-            poll_vec(xin_of(S, X_XC), D / 3, seq - 1, S.xs, D);
-            cbar();
+            float w3[3];
+            ln_weights3<D>(p.norm_out, ctid, w3);
+            load3_poll<D>(c.xin + p.xoff[X_XC], c.seq - 1, S.xs, ctid, xv);
             LOOP_STAMP();
-            layer_norm(S.xs, wr, S.av, D / 128, S.eps);
-            cbar();
+            ln3<D>(S, xv, w3, S.av, p.eps, c);
             if (b == 0) {
                 for (int i = ctid; i < D; i += kCT) {
                     const float hv = S.av[i];
@@ -780,87 +853,130 @@ __global__ void __launch_bounds__(kThreads, 1) frame_loop_kernel(const FrameLoop
         const bool forbid_eos = (p.step0 + t) < p.min_frames;
         const bool sampling = p.temperature >= 0.01f;
         bool hit_eos = false;
-        phase(S, PH_LT_IN, nullptr, false, kc, seq);          // seq[0] = in_proj . hidden + b
-        seq++;
-        float seq_next = 0.0f;              // feedback row element `ctid` (ctid < LD) for the next codebook
+        // x_0 = in_proj . hidden + b + pos_lt[0]   (the position row is added by the producer)
+        {
+            const int r0 = b * RIN, nr = max(0, min(RIN, LD - r0));
+            gemv_rows<D / 256, 1>(S.w_in, nr, S.av, S.part, c);
+            cbar();
+            emit_rows<D / 256, EPI_BIAS>(S, p, c, T_SEQ0, r0, nr, nullptr, p.lt_in_b, S.ltpos);
+            c.seq++;
+        }
+        float fb[3] = {0.0f, 0.0f, 0.0f};     // feedback row elements 3i .. 3i+2 for the next codebook
 #pragma unroll 1
         for (int cb = 0; cb < 8; cb++) {
-            float * qkv = S.lqkv[cb];       // [q | k | v] of position cb
+            float * qkv = S.lqkv[cb];         // [q | k | v] of position cb
             // ---- A: x = seq + pos; LN -> QKV --------------------------------------------------------------------
-            if (cb == 0) {
-                poll_vec(xin_of(S, T_SEQ0), (LD + 2) / 3, seq - 1, S.lx, LD);
+            {
+                float w3[3], lv[3];
+                ln_weights3<LD>(p.lt_norm_self, ctid, w3);
+                if (cb == 0) load3_poll<LD>(c.xin + p.xoff[T_SEQ0], c.seq - 1, S.lx, ctid, lv);
+                else {
+#pragma unroll
+                    for (int q = 0; q < 3; q++) {
+                        lv[q] = 0.0f;
+                        if (own3l && 3 * ctid + q < LD) { lv[q] = fb[q] + S.ltpos[cb * LD + 3 * ctid + q]; S.lx[3 * ctid + q] = lv[q]; }
+                    }
+                }
+                LOOP_STAMP();
+                ln3<LD>(S, lv, w3, S.vec, p.eps, c);
+                const int r0 = b * RLQ, nr = max(0, min(RLQ, 3 * LD - r0));
+                gemv_rows<1, 1>(S.w_qkv, nr, S.vec, S.part, c);
                 cbar();
-                if (ctid < LD) S.lx[ctid] += S.ltpos[ctid];
-            } else if (ctid < LD) S.lx[ctid] = seq_next + S.ltpos[cb * LD + ctid];
-            cbar();
-            phase(S, PH_LT_QKV, p.lt_norm_self, false, kc, seq);
-            seq++;
+                emit_rows<1, EPI_NONE>(S, p, c, T_QKV, r0, nr, nullptr, nullptr, nullptr);
+                c.seq++;
+            }
             LOOP_STAMP();
             // ---- B: attention over the <= 8 positions (redundant per CTA); O + residual ------------------------
-            poll_vec(xin_of(S, T_QKV), LD, seq - 1, qkv, 3 * LD);
-            cbar();
-            if (cw <= cb) {
-                float s = 0.0f;
+            {
+                poll_vec(c.xin + p.xoff[T_QKV], LD, c.seq - 1, qkv, 3 * LD, ctid);
+                cbar();
+                LOOP_STAMP();
+                if (cw <= cb) {
+                    float s = 0.0f;
 #pragma unroll
-                for (int q = 0; q < 8; q++) s = fmaf(S.lqkv[cw][LD + lane + 32 * q], qkv[lane + 32 * q], s);
-                s = warp_sum(s);
-                if (lane == 0) S.sc[cw] = s * lt_scale;
+                    for (int q = 0; q < 8; q++) s = fmaf(S.lqkv[cw][LD + lane + 32 * q], qkv[lane + 32 * q], s);
+                    s = warp_sum(s);
+                    if (lane == 0) S.sc[cw] = s * lt_scale;
+                }
+                cbar();
+                if (ctid < LD) {
+                    float mxs = S.sc[0];
+                    for (int j = 1; j <= cb; j++) mxs = fmaxf(mxs, S.sc[j]);
+                    float sum = 0.0f, o = 0.0f;
+                    for (int j = 0; j <= cb; j++) { const float e = expf(S.sc[j] - mxs); sum += e; o = fmaf(e, S.lqkv[j][2 * LD + ctid], o); }
+                    S.latt[ctid] = o * (1.0f / sum);
+                }
+                cbar();
+                const int r0 = b * RLO, nr = max(0, min(RLO, LD - r0));
+                gemv_rows<1, 1>(S.w_o, nr, S.latt, S.part, c);
+                cbar();
+                emit_rows<1, EPI_RES>(S, p, c, T_X1, r0, nr, S.lx, nullptr, nullptr);
+                c.seq++;
             }
-            cbar();
-            if (ctid < LD) {
-                float mxs = S.sc[0];
-                for (int j = 1; j <= cb; j++) mxs = fmaxf(mxs, S.sc[j]);
-                float sum = 0.0f, o = 0.0f;
-                for (int j = 0; j <= cb; j++) { const float e = expf(S.sc[j] - mxs); sum += e; o = fmaf(e, S.lqkv[j][2 * LD + ctid], o); }
-                S.latt[ctid] = o * (1.0f / sum);
-            }
-            cbar();
-            phase(S, PH_LT_O, nullptr, false, kc, seq);
-            seq++;
             LOOP_STAMP();
             // ---- C: LN -> FFN1 -> GELU -----------------------------------------------------------------------------
-            phase(S, PH_LT_FF1, p.lt_norm_ff, true, kc, seq);
-            seq++;
+            {
+                float w3[3], lv[3];
+                ln_weights3<LD>(p.lt_norm_ff, ctid, w3);
+                load3_poll<LD>(c.xin + p.xoff[T_X1], c.seq - 1, S.lx1, ctid, lv);
+                LOOP_STAMP();
+                ln3<LD>(S, lv, w3, S.vec, p.eps, c);
+                const int r0 = b * RLF1, nr = max(0, min(RLF1, LF - r0));
+                gemv_rows<1, 1>(S.w_ff1, nr, S.vec, S.part, c);
+                cbar();
+                emit_rows<1, EPI_GELU>(S, p, c, T_H, r0, nr, nullptr, nullptr, nullptr);
+                c.seq++;
+            }
             LOOP_STAMP();
             // ---- D: FFN2 + residual ---------------------------------------------------------------------------------
-            phase(S, PH_LT_FF2, nullptr, true, kc, seq);
-            seq++;
+            {
+                poll_vec(c.xin + p.xoff[T_H], (LF + 2) / 3, c.seq - 1, S.vec, LF, ctid);
+                cbar();
+                LOOP_STAMP();
+                const int r0 = b * RLF2, nr = max(0, min(RLF2, LD - r0));
+                gemv_rows<LF / 256, 1>(S.w_ff2, nr, S.vec, S.part, c);
+                cbar();
+                emit_rows<LF / 256, EPI_RES>(S, p, c, T_HOUT, r0, nr, S.lx1, nullptr, nullptr);
+                c.seq++;
+            }
             LOOP_STAMP();
             // ---- E: output projection of codebook cb (+bias, forbidden-token mask); local argmax ---------------------
             {
-                poll_vec(xin_of(S, T_HOUT), (LD + 2) / 3, seq - 1, S.lhout, LD);
+                poll_vec(c.xin + p.xoff[T_HOUT], (LD + 2) / 3, c.seq - 1, S.lhout, LD, ctid);
                 cbar();
                 LOOP_STAMP();
                 const int r0 = b * ROUT, nr = max(0, min(ROUT, V - r0));
                 if (nr > 0) {
-                    const bf * w = ring_wait(S, kc);
-                    gemv_part(w, nr, 1, S.lhout, S.part);
-                    ring_release(S, kc, lane);
-                    kc++;
+                    const bf * w = ring_wait(S, c);
+                    gemv_rows<1, 1>(w, nr, S.lhout, S.part, c);
+                    ring_release(S, c);
                 }
                 cbar();
-                if (ctid < nr) {
-                    const int n = r0 + ctid;
-                    float v = S.part[ctid * kPartStride] + __ldg(p.lt_out_b[cb] + n);
-                    const bool masked = n == p.bos_id || (n >= p.bos_id + 2 && n <= p.bos_id + 7) || (forbid_eos && n == p.eos_id);
-                    if (masked) v = -INFINITY;                                    // magpie.cpp:1131-1145, 1243-1248
-                    S.outv[ctid] = v;
-                    if (p.logits) p.logits[(row * 8 + cb) * V + n] = v;
-                }
-                cbar();
-                if (sampling) {
-                    const int npk = (nr + 2) / 3;
-                    if (ctid < npk * kR) {
-                        const int pk = ctid % npk, r = ctid / npk;
-                        const float v0 = S.outv[3 * pk], v1 = 3 * pk + 1 < nr ? S.outv[3 * pk + 1] : 0.0f, v2 = 3 * pk + 2 < nr ? S.outv[3 * pk + 2] : 0.0f;
-                        st_pkt(xout_of(S, T_LOGITS, r) + r0 / 3 + pk, v0, v1, v2, seq);
+                if (cw == 0 && nr > 0) {
+                    float v = -INFINITY;
+                    if (lane < nr) {
+                        const int n = r0 + lane;
+                        v = S.part[lane * kPartStride] + __ldg(p.lt_out_b[cb] + n);
+                        const bool masked = n == p.bos_id || (n >= p.bos_id + 2 && n <= p.bos_id + 7) || (forbid_eos && n == p.eos_id);
+                        if (masked) v = -INFINITY;                                // magpie.cpp:1131-1145, 1243-1248
+                        if (p.logits) p.logits[(row * 8 + cb) * V + n] = v;
                     }
-                } else if (nr > 0 && ctid < kR) {
-                    float bv = S.outv[0]; int bi = 0;
-                    for (int r = 1; r < nr; r++) if (S.outv[r] > bv) { bv = S.outv[r]; bi = r; }
-                    st_pkt(xout_of(S, T_AMAX, ctid) + b, bv, __int_as_float(r0 + bi), 0.0f, seq);
+                    if (sampling) {
+                        const int npk = (nr + 2) / 3;
+                        const int pk = lane % npk, rep = lane / npk;
+                        const float v0 = __shfl_sync(0xffffffffu, v, 3 * pk), v1 = __shfl_sync(0xffffffffu, v, 3 * pk + 1), v2 = __shfl_sync(0xffffffffu, v, 3 * pk + 2);
+                        if (lane < npk * kR) st_pkt(p.xbuf + (size_t)rep * c.rstride + p.xoff[T_LOGITS] + r0 / 3 + pk, v0, v1, v2, c.seq);
+                    } else {
+                        float bv = v; int bi = lane < nr ? r0 + lane : 0x7fffffff;
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            const float ov = __shfl_xor_sync(0xffffffffu, bv, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                            if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+                        }
+                        if (lane < kR) st_pkt(p.xbuf + (size_t)lane * c.rstride + p.xoff[T_AMAX] + b, bv, __int_as_float(bi), 0.0f, c.seq);
+                    }
                 }
-                seq++;
+                c.seq++;
             }
             LOOP_STAMP();
             // ---- F: global argmax / top-k sample; feedback ---------------------------------------------------------------
@@ -869,9 +985,7 @@ __global__ void __launch_bounds__(kThreads, 1) frame_loop_kernel(const FrameLoop
                 const int nprod = (V + ROUT - 1) / ROUT;
                 float bv = -INFINITY; int bi = 0x7fffffff;
                 if (ctid < nprod) {
-                    const uint4 * q = xin_of(S, T_AMAX) + ctid;
-                    uint4 v = ld_pkt(q);
-                    while ((v.w ^ (seq - 1)) & c_poll_mask) v = ld_pkt(q);
+                    const uint4 v = poll_pkt(c.xin + p.xoff[T_AMAX] + ctid, c.seq - 1);
                     bv = __uint_as_float(v.x); bi = (int)v.y;
                     if (c_poll_mask == 0u) bi = min(max(bi, 0), V - 1);
                 }
@@ -888,7 +1002,7 @@ __global__ void __launch_bounds__(kThreads, 1) frame_loop_kernel(const FrameLoop
                 cbar();
                 am = bi; pick = bi;
             } else {
-                poll_vec(xin_of(S, T_LOGITS), (V + 2) / 3, seq - 1, S.vec, V);
+                poll_vec(c.xin + p.xoff[T_LOGITS], (V + 2) / 3, c.seq - 1, S.vec, V, ctid);
                 cbar();
                 LOOP_STAMP();
                 am = cta_argmax(S, S.vec, V);
@@ -905,11 +1019,13 @@ __global__ void __launch_bounds__(kThreads, 1) frame_loop_kernel(const FrameLoop
             const int fed = p.forced ? p.forced[row * 8 + cb] : pick;
             if (b == 0 && ctid == 0) { p.argmax[row * 8 + cb] = am; p.sampled[row * 8 + cb] = pick; p.result[2 + cb] = fed; }
             // feedback: seq[cb+1] = row `fed` of P_cb (no 1/8 scale, magpie.cpp:1285-1291); next frame's embedding
-            if (cb < 7 && ctid < LD) seq_next = __ldg(p.lt_in_table[cb] + (size_t)fed * LD + ctid);
-            {
-                const float a = __ldg(p.audio_emb[cb] + (size_t)fed * D + e0);
-                const float a1 = e1 < D ? __ldg(p.audio_emb[cb] + (size_t)fed * D + e1) : 0.0f;
-                emb0 = cb == 0 ? a : emb0 + a; emb1 = cb == 0 ? a1 : emb1 + a1;
+            if (cb < 7 && own3l) {
+#pragma unroll
+                for (int q = 0; q < 3; q++) if (3 * ctid + q < LD) fb[q] = __ldg(p.lt_in_table[cb] + (size_t)fed * LD + 3 * ctid + q);
+            }
+            if (own3) {
+#pragma unroll
+                for (int q = 0; q < 3; q++) { const float a = __ldg(p.audio_emb[cb] + (size_t)fed * D + 3 * ctid + q); emb[q] = cb == 0 ? a : emb[q] + a; }
             }
             LOOP_STAMP();
         }
@@ -922,7 +1038,7 @@ __global__ void __launch_bounds__(kThreads, 1) frame_loop_kernel(const FrameLoop
     if (ctid == 0) S.stop = 1;
     if (b == 0 && ctid == 0) {
         p.result[0] = frames; p.result[1] = eos_step;
-        *p.seq = seq;
+        *p.seq = c.seq;
     }
 }
 

@@ -8,7 +8,8 @@ namespace mgb {
 
 constexpr int kLoopMaxLayers = 16;
 constexpr int kLoopMaxCtx = 30;          // text tokens the folded cross-attention path handles
-constexpr int kLoopDbgStamps = 1024;
+constexpr int kLoopDbgPerCta = 256;      // globaltimer stamps per CTA (last frame of a launch)
+constexpr int kLoopDbgStamps = 160 * kLoopDbgPerCta;
 
 // exchange buffers (16-byte flag packets, see frame_loop.cu)
 enum LoopXchg { X_QKV = 0, X_ATT, X_XA, X_XB, X_H, X_XC, T_SEQ0, T_QKV, T_X1, T_H, T_HOUT, T_AMAX, T_LOGITS, X_COUNT };
