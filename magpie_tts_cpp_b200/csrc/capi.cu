@@ -60,6 +60,7 @@ struct Session {
     int loop_grid = 0; uint4 * d_xbuf = nullptr; int xoff[X_COUNT + 1] = {}; unsigned * d_seq = nullptr;
     int32_t * d_result = nullptr; float * d_xm = nullptr, * d_xn = nullptr; int loop_E = 0; bool loop_tables = false;
     unsigned long long * d_loop_dbg = nullptr;
+    void * tc_scratch = nullptr; size_t tc_scratch_bytes = 0;     // tensor-core path: activation tile images
 
     ~Session() {
         if (m) cudaSetDevice(m->device);
@@ -96,6 +97,7 @@ static bool decoder_layers(Session & s, Tokens tok, bool want_hidden) {
         const DecLayer & L = m.dec[l];
         char * kl = (char *)s.kc + l * kv_layer, * vl = (char *)s.vc + l * kv_layer;
         LinearArgs a;
+        a.tc_scratch = s.tc_scratch; a.tc_scratch_bytes = s.tc_scratch_bytes;
         a.precision = m.precision; a.eps = hp.eps; a.gelu_f16 = m.gelu_f16; a.M = M;
         // self-attention: LN -> QKV (K,V written straight into the cache) -> attention -> O + residual
         a.W = L.qkv; a.X = s.x; a.ldx = d; a.ln_w = L.norm_self; a.Y = s.qbuf; a.ldy = d;
@@ -106,10 +108,12 @@ static bool decoder_layers(Session & s, Tokens tok, bool want_hidden) {
         at.H = hp.dec_sa_heads; at.dh = d / hp.dec_sa_heads; at.causal = 1; at.tok = tok; at.out = s.attn; at.ldo = d;
         if (!launch_attention(at, s.stream)) return false;
         LinearArgs o;
+        o.tc_scratch = s.tc_scratch; o.tc_scratch_bytes = s.tc_scratch_bytes;
         o.precision = m.precision; o.M = M; o.W = L.o; o.X = s.attn; o.ldx = d; o.res = s.x; o.ldr = d; o.Y = s.x; o.ldy = d;
         if (!launch_linear(o, s.stream)) return false;
         // cross-attention over the cached encoder K/V (no mask)
         LinearArgs q;
+        q.tc_scratch = s.tc_scratch; q.tc_scratch_bytes = s.tc_scratch_bytes;
         q.precision = m.precision; q.eps = hp.eps; q.M = M; q.W = L.xq; q.X = s.x; q.ldx = d; q.ln_w = L.norm_xa_q; q.Y = s.xq; q.ldy = dxa;
         if (!launch_linear(q, s.stream)) return false;
         AttnArgs xt;
@@ -118,14 +122,17 @@ static bool decoder_layers(Session & s, Tokens tok, bool want_hidden) {
         xt.tok = tok; xt.out = s.xatt; xt.ldo = dxa;
         if (!launch_attention(xt, s.stream)) return false;
         LinearArgs xo;
+        xo.tc_scratch = s.tc_scratch; xo.tc_scratch_bytes = s.tc_scratch_bytes;
         xo.precision = m.precision; xo.M = M; xo.W = L.xo; xo.X = s.xatt; xo.ldx = dxa; xo.res = s.x; xo.ldr = d; xo.Y = s.x; xo.ldy = d;
         if (!launch_linear(xo, s.stream)) return false;
         // conv-FFN (kernel 1): LN -> W1 -> GELU -> W2 + residual
         LinearArgs f1;
+        f1.tc_scratch = s.tc_scratch; f1.tc_scratch_bytes = s.tc_scratch_bytes;
         f1.precision = m.precision; f1.eps = hp.eps; f1.gelu_f16 = m.gelu_f16; f1.M = M; f1.W = L.ff1; f1.X = s.x; f1.ldx = d;
         f1.ln_w = L.norm_ff; f1.act = ACT_GELU; f1.Y = s.ffh; f1.ldy = hp.d_ffn;
         if (!launch_linear(f1, s.stream)) return false;
         LinearArgs f2;
+        f2.tc_scratch = s.tc_scratch; f2.tc_scratch_bytes = s.tc_scratch_bytes;
         f2.precision = m.precision; f2.M = M; f2.W = L.ff2; f2.X = s.ffh; f2.ldx = hp.d_ffn; f2.res = s.x; f2.ldr = d; f2.Y = s.x; f2.ldy = d;
         if (!launch_linear(f2, s.stream)) return false;
     }
@@ -272,6 +279,12 @@ mgb_session * mgb_session_new(mgb_model * mm, int batch, int max_text, int max_s
          s->alloc(s->d_done, batch) && s->alloc(s->d_forbid, batch) && s->alloc(s->d_forced, (size_t)batch * 8) &&
          s->alloc(s->d_uniforms, (size_t)batch * 8) && s->alloc(s->d_logits1, (size_t)batch * 8 * V);
     if (!ok) return nullptr;
+    if (m->precision == MGB_PREC_BF16 && s->Mcap >= 16 && m->dec.size() && m->dec[0].qkv.tiles) {
+        const size_t tb = tc_scratch_bytes(s->Mcap, std::max(hp.d_ffn, hp.d_model));
+        char * tp = nullptr;
+        if (!s->alloc(tp, tb)) return nullptr;
+        s->tc_scratch = tp; s->tc_scratch_bytes = tb;
+    }
     // batch 1: persistent cooperative megakernel (MGB_NO_MEGA=1 keeps the per-op kernels, e.g. for A/B tests)
     if (batch == 1 && getenv("MGB_NO_MEGA") == nullptr && hp.dec_layers <= kMegaMaxLayers && hp.d_model <= 1024 &&
         hp.d_ffn <= 11 * 1024 && max_text <= 4096) {
@@ -361,6 +374,7 @@ int mgb_encode_text(mgb_session * ss, const int32_t * tokens, const int32_t * n_
     for (int l = 0; l < hp.enc_layers; l++) {
         const EncLayer & L = m.enc[l];
         LinearArgs a;
+        a.tc_scratch = s->tc_scratch; a.tc_scratch_bytes = s->tc_scratch_bytes;
         a.precision = m.precision; a.eps = hp.eps; a.M = M; a.W = L.qkv; a.X = s->x; a.ldx = d; a.ln_w = L.norm_self;
         a.Y = s->qbuf; a.ldy = d; a.n_q = d; a.dkv = d; a.kdst = s->ek; a.vdst = s->ev; a.tok_slot = T.slot;
         if (!launch_linear(a, st)) return MGB_ECUDA;
@@ -369,13 +383,16 @@ int mgb_encode_text(mgb_session * ss, const int32_t * tokens, const int32_t * n_
         at.H = hp.enc_heads; at.dh = d / hp.enc_heads; at.causal = 1; at.tok = T; at.out = s->attn; at.ldo = d;
         if (!launch_attention(at, st)) return MGB_ECUDA;
         LinearArgs o;
+        o.tc_scratch = s->tc_scratch; o.tc_scratch_bytes = s->tc_scratch_bytes;
         o.precision = m.precision; o.M = M; o.W = L.o; o.X = s->attn; o.ldx = d; o.res = s->x; o.ldr = d; o.Y = s->x; o.ldy = d;
         if (!launch_linear(o, st)) return MGB_ECUDA;
         LinearArgs f1;   // causal conv k=3 as 3 shifted taps (magpie.cpp:1825-1914)
+        f1.tc_scratch = s->tc_scratch; f1.tc_scratch_bytes = s->tc_scratch_bytes;
         f1.precision = m.precision; f1.eps = hp.eps; f1.gelu_f16 = m.gelu_f16; f1.M = M; f1.W = L.ff1; f1.X = s->x; f1.ldx = d;
         f1.ln_w = L.norm_ff; f1.act = ACT_GELU; f1.Y = s->ffh; f1.ldy = hp.d_ffn; f1.tok_pos = T.pos;
         if (!launch_linear(f1, st)) return MGB_ECUDA;
         LinearArgs f2;
+        f2.tc_scratch = s->tc_scratch; f2.tc_scratch_bytes = s->tc_scratch_bytes;
         f2.precision = m.precision; f2.M = M; f2.W = L.ff2; f2.X = s->ffh; f2.ldx = hp.d_ffn; f2.res = s->x; f2.ldr = d;
         f2.Y = s->x; f2.ldy = d; f2.tok_pos = T.pos;
         if (!launch_linear(f2, st)) return MGB_ECUDA;
@@ -412,6 +429,7 @@ int mgb_prefill(mgb_session * ss, const int32_t * speakers) {
     for (int l = 0; l < hp.dec_layers; l++) {
         const DecLayer & L = m.dec[l];
         LinearArgs a;
+        a.tc_scratch = s->tc_scratch; a.tc_scratch_bytes = s->tc_scratch_bytes;
         a.precision = m.precision; a.eps = hp.eps; a.M = s->M_enc; a.W = L.xkv; a.X = s->enc_out; a.ldx = d; a.ln_w = L.norm_xa_mem;
         a.n_q = 0; a.dkv = dxa; a.kdst = (char *)s->xk + l * xkv_layer; a.vdst = (char *)s->xv + l * xkv_layer; a.tok_slot = s->tok_slot;
         a.Y = s->qbuf; a.ldy = d;
@@ -483,6 +501,7 @@ int mgb_final_proj(mgb_session * ss, const float * hidden, float * logits_out) {
     // output [B][N] does not fit the step buffers: use the loop logits buffer
     if (!grow((void **)&s->l_logits, &s->l_cap_logits, (size_t)s->B * N * 4)) return MGB_ECUDA;
     LinearArgs a;
+    a.tc_scratch = s->tc_scratch; a.tc_scratch_bytes = s->tc_scratch_bytes;
     a.precision = m.precision; a.M = s->B; a.W = m.final_w; a.X = hsrc; a.ldx = d; a.bias = m.final_b; a.Y = s->l_logits; a.ldy = N;
     if (!launch_linear(a, st)) return MGB_ECUDA;
     if (cudaMemcpyAsync(logits_out, s->l_logits, (size_t)s->B * N * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess ||

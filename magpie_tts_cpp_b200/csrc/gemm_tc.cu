@@ -1,0 +1,169 @@
+// Batched linear layers on the 5th-generation tensor cores: LayerNorm / bf16 hi-lo packing of the activations into
+// shared-memory tile images, tcgen05.mma mainloop (gemm_tc.cuh), fused bias / GELU / residual / KV-cache epilogue.
+// Replaces linear_kernel (transformer_kernels.cu) for bf16 models when a launch carries >= 16 tokens: batched
+// decoder steps, the 110-frame context prefill and the cross-attention K/V precompute
+// (reference: ggml_mul_mat call sites src/magpie.cpp:3415, 3464-3479, 1733, 1764, 1796, 1805).
+#include "common.cuh"
+#include "gemm_tc.cuh"
+#include "kernels.cuh"
+
+namespace mgb {
+
+namespace {
+
+using bf = __nv_bfloat16;
+
+// row-major bf16 [N][K] -> [ceil(N/128)][K/64] tiles of 128 x 64 in the SWIZZLE_128B K-major image; one thread per 16 bytes
+__global__ void pack_w_kernel(const bf * W, int N, int K, bf * Wt) {
+    const int KT = K / 64, NT = (N + tc::BM - 1) / tc::BM;
+    const size_t total = (size_t)NT * tc::BM * (K / 8);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / (K / 8)), kc = (int)(i % (K / 8));
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (r < N) v = *reinterpret_cast<const uint4 *>(W + (size_t)r * K + kc * 8);
+        const size_t tile = (size_t)(r / tc::BM) * KT + kc / 8;
+        unsigned char * dst = reinterpret_cast<unsigned char *>(Wt) + tile * (tc::BM * 128) + tc::swz_offset(r % tc::BM, (kc % 8) * 8);
+        *reinterpret_cast<uint4 *>(dst) = v;
+    }
+}
+
+// activations f32 [M][ldx] (optionally LayerNorm'd, magpie.cpp:2237-2259) -> hi / lo bf16 tile images [ceil(M/MT)][K/64][MT x 64].
+// One CTA per row of the padded token range; rows >= M are written as zeros.
+__global__ void __launch_bounds__(256) pack_x_kernel(const float * X, int ldx, int M, int K, const float * ln_w, float eps, int MT,
+                                                     bf * hi, bf * lo) {
+    __shared__ float red[32];
+    const int m = blockIdx.x, tid = threadIdx.x;
+    const int KT = K / 64;
+    const bool valid = m < M;
+    const float * xr = X + (size_t)(valid ? m : 0) * ldx;
+    float mean = 0.0f, scale = 1.0f;
+    if (ln_w) {
+        float s = 0.0f;
+        for (int k = tid; k < K; k += 256) s += valid ? xr[k] : 0.0f;
+        mean = block_sum(s, red) / (float)K;
+        float s2 = 0.0f;
+        for (int k = tid; k < K; k += 256) { const float v = (valid ? xr[k] : 0.0f) - mean; s2 += v * v; }
+        const float var = block_sum(s2, red) / (float)K;
+        scale = 1.0f / sqrtf(var + eps);
+    }
+    const size_t tile_row = (size_t)(m / MT) * KT;
+    for (int kc = tid; kc < K / 8; kc += 256) {
+        float v[8];
+        if (valid) {
+            const float4 a = *reinterpret_cast<const float4 *>(xr + kc * 8), b = *reinterpret_cast<const float4 *>(xr + kc * 8 + 4);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+            if (ln_w) {
+#pragma unroll
+                for (int q = 0; q < 8; q++) v[q] = ((v[q] - mean) * scale) * ln_w[kc * 8 + q];
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 8; q++) v[q] = 0.0f;
+        }
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const bf h0 = __float2bfloat16_rn(v[2 * q]), h1 = __float2bfloat16_rn(v[2 * q + 1]);
+            const bf l0 = __float2bfloat16_rn(v[2 * q] - __bfloat162float(h0)), l1 = __float2bfloat16_rn(v[2 * q + 1] - __bfloat162float(h1));
+            h[q] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+            l[q] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+        }
+        const size_t off = (tile_row + kc / 8) * ((size_t)MT * 128) + tc::swz_offset(m % MT, (kc % 8) * 8);
+        *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(hi) + off) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(lo) + off) = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+}
+
+struct TcEpi {
+    int N, M;
+    const float * bias;
+    const float * res; int ldr;
+    float * Y; int ldy;
+    int act, gelu_f16;
+    int n_q, dkv; bf * kdst; bf * vdst; const int32_t * tok_slot;
+};
+
+template <int MT>
+__global__ void __launch_bounds__(tc::kThreads, 1) tc_linear_kernel(const bf * Wt, const bf * Xhi, const bf * Xlo, int KT, const TcEpi e) {
+    extern __shared__ unsigned char tc_smem[];
+    const int nt = blockIdx.x, mt = blockIdx.y;
+    const uint32_t tmem = tc::mainloop<MT>(tc_smem, Wt, Xhi, Xlo, KT, nt, mt);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp >= 2) {
+        const int q = warp & 3;                      // TMEM lane quarter this warp may access
+        const int n = nt * tc::BM + q * 32 + lane;
+        const float bias = (e.bias && n < e.N) ? e.bias[n] : 0.0f;
+        for (int c = 0; c < MT; c += 32) {
+            if (mt * MT + c >= e.M) break;           // warp-uniform
+            uint32_t v[32];
+            tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + c, v);
+            if (n < e.N) {
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    const int m = mt * MT + c + j;
+                    if (m < e.M) {
+                        float y = __uint_as_float(v[j]) + bias;
+                        if (e.act == ACT_GELU) y = gelu_ggml(y, e.gelu_f16);
+                        if (e.res) y += e.res[(size_t)m * e.ldr + n];
+                        if (e.n_q < 0 || n < e.n_q) e.Y[(size_t)m * e.ldy + n] = y;
+                        else {
+                            const size_t slot = (size_t)e.tok_slot[m] * e.dkv;
+                            const int cc = n - e.n_q;
+                            if (cc < e.dkv) e.kdst[slot + cc] = __float2bfloat16_rn(y);
+                            else e.vdst[slot + (cc - e.dkv)] = __float2bfloat16_rn(y);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc::finish<MT>(tmem);
+}
+
+template <int MT> bool launch_tc(const bf * Wt, const bf * hi, const bf * lo, int KT, const TcEpi & e, cudaStream_t stream) {
+    static uint64_t attr_done = 0;
+    int dev = 0;
+    MGB_CUDA_TRY(cudaGetDevice(&dev));
+    if (!(attr_done >> dev & 1)) {
+        MGB_CUDA_TRY(cudaFuncSetAttribute(tc_linear_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Smem<MT>::kBytes));
+        attr_done |= 1ull << dev;
+    }
+    dim3 grid((e.N + tc::BM - 1) / tc::BM, (e.M + MT - 1) / MT);
+    tc_linear_kernel<MT><<<grid, tc::kThreads, tc::Smem<MT>::kBytes, stream>>>(Wt, hi, lo, KT, e);
+    MGB_LAUNCH_CHECK();
+    return true;
+}
+
+}  // namespace
+
+size_t tc_weight_tile_bytes(int N, int K) { return (size_t)((N + tc::BM - 1) / tc::BM) * tc::BM * K * sizeof(bf); }
+
+bool tc_pack_weights(const void * W, int N, int K, void * Wt, cudaStream_t stream) {
+    pack_w_kernel<<<592, 256, 0, stream>>>((const bf *)W, N, K, (bf *)Wt);
+    MGB_LAUNCH_CHECK();
+    return true;
+}
+
+size_t tc_scratch_bytes(int M, int K) { return 2 * (size_t)((M + 127) / 128) * 128 * K * sizeof(bf); }
+
+bool tc_linear_supported(const LinearArgs & a) {
+    return a.precision == MGB_PREC_BF16 && a.W.tiles != nullptr && a.W.taps == 1 && a.M >= 16 && a.W.K % 64 == 0 && a.tc_scratch != nullptr &&
+           tc_scratch_bytes(a.M, a.W.K) <= a.tc_scratch_bytes && (a.ldx % 4) == 0;
+}
+
+bool launch_linear_tc(const LinearArgs & a, cudaStream_t stream) {
+    const int K = a.W.K, M = a.M;
+    const int MT = M <= 64 ? 64 : 128;
+    const int Mpad = (M + MT - 1) / MT * MT;
+    bf * hi = (bf *)a.tc_scratch;
+    bf * lo = hi + (size_t)Mpad * K;
+    pack_x_kernel<<<Mpad, 256, 0, stream>>>(a.X, a.ldx, M, K, a.ln_w, a.eps, MT, hi, lo);
+    MGB_LAUNCH_CHECK();
+    TcEpi e;
+    e.N = a.W.N; e.M = M; e.bias = a.bias; e.res = a.res; e.ldr = a.ldr; e.Y = a.Y; e.ldy = a.ldy; e.act = a.act; e.gelu_f16 = a.gelu_f16;
+    e.n_q = a.n_q; e.dkv = a.dkv; e.kdst = (bf *)a.kdst; e.vdst = (bf *)a.vdst; e.tok_slot = a.tok_slot;
+    if (MT == 64) return launch_tc<64>((const bf *)a.W.tiles, hi, lo, K / 64, e, stream);
+    return launch_tc<128>((const bf *)a.W.tiles, hi, lo, K / 64, e, stream);
+}
+
+}  // namespace mgb

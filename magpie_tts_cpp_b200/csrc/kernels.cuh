@@ -36,8 +36,15 @@ struct LinearArgs {
     void * kdst = nullptr; void * vdst = nullptr;
     const int32_t * tok_slot = nullptr;
     int M = 0;
+    void * tc_scratch = nullptr; size_t tc_scratch_bytes = 0;     // activation tile images of the tensor-core path (gemm_tc.cu)
 };
 bool launch_linear(const LinearArgs & a, cudaStream_t stream);
+// tcgen05 path (bf16, >= 16 tokens): gemm_tc.cu
+size_t tc_weight_tile_bytes(int N, int K);
+bool   tc_pack_weights(const void * W, int N, int K, void * Wt, cudaStream_t stream);
+size_t tc_scratch_bytes(int M, int K);
+bool   tc_linear_supported(const LinearArgs & a);
+bool   launch_linear_tc(const LinearArgs & a, cudaStream_t stream);
 
 struct AttnArgs {
     int precision = 0;

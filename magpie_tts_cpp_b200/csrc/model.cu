@@ -2,6 +2,7 @@
 // (src/magpie.cpp:501-562, 607-667 and src/nano-codec.cpp:84-199).
 #include "model.h"
 
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 
@@ -220,6 +221,24 @@ Model * load_model(const char * path, int device, int precision) {
         if (!launch_linear(a, nullptr)) return nullptr;
     }
     if (cudaDeviceSynchronize() != cudaSuccess) { set_error("magpie_init: building the LT feedback table failed"); return nullptr; }
+
+    // bf16 models: tensor-core tile images of the matrices the batched paths multiply with (gemm_tc.cu);
+    // MGB_NO_TC=1 keeps the CUDA-core kernels (A/B tests)
+    if (precision == MGB_PREC_BF16 && getenv("MGB_NO_TC") == nullptr) {
+        std::vector<DevMat *> mats;
+        for (auto & L : M->dec) for (DevMat * m : {&L.qkv, &L.o, &L.xq, &L.xkv, &L.xo, &L.ff1, &L.ff2}) mats.push_back(m);
+        for (auto & L : M->enc) for (DevMat * m : {&L.qkv, &L.o}) mats.push_back(m);
+        mats.push_back(&M->final_w);
+        for (DevMat * m : mats) {
+            if (m->taps != 1 || m->K % 64 != 0) continue;
+            void * t = nullptr;
+            if (cudaMalloc(&t, tc_weight_tile_bytes(m->N, m->K)) != cudaSuccess) { set_error("cudaMalloc failed (weight tiles)"); return nullptr; }
+            M->allocations.push_back(t);
+            if (!tc_pack_weights(m->w, m->N, m->K, t, nullptr)) return nullptr;
+            m->tiles = t;
+        }
+        if (cudaDeviceSynchronize() != cudaSuccess) { set_error("magpie_init: packing the weight tiles failed"); return nullptr; }
+    }
 
     // unique weight bytes one generated frame reads: decoder matrices + LT matrices
     int64_t el = 0, f32b = 0;

@@ -18,6 +18,7 @@ namespace mgb {
 struct DevMat {
     void * w = nullptr;
     int    N = 0, K = 0, taps = 1;
+    void * tiles = nullptr;      // bf16 models: [ceil(N/128)][K/64] tiles of 128 x 64 in the tcgen05 shared-memory image (gemm_tc.cuh)
 };
 
 struct EncLayer { float * norm_self = nullptr, * norm_ff = nullptr; DevMat qkv, o, ff1, ff2; };

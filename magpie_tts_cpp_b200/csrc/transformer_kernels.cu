@@ -308,6 +308,7 @@ __global__ void add_one_kernel(int32_t * v, int n) {
 
 bool launch_linear(const LinearArgs & a, cudaStream_t stream) {
     if (a.M <= 0) return true;
+    if (tc_linear_supported(a)) return launch_linear_tc(a, stream);
     LinParams p;
     p.W = a.W.w; p.N = a.W.N; p.K = a.W.K; p.taps = a.W.taps;
     p.X = a.X; p.ldx = a.ldx; p.ln_w = a.ln_w; p.eps = a.eps; p.bias = a.bias;

@@ -348,6 +348,38 @@ def test_loop_kernel_is_deterministic_and_chunkable(B, full_model_path, full_ora
     s.close()
 
 
+def test_tensor_core_linear_matches_cuda_core_kernels(B, full_model_path, full_oracle, monkeypatch):
+    """bf16, 24 utterances: the tcgen05 GEMM path (encoder, 110-frame prefill, batched decoder steps) against the
+    CUDA-core linear kernels (MGB_NO_TC=1 at model load) and against the oracle."""
+    codes = np.repeat(full_oracle["codes"][None, :6], 24, axis=0)
+
+    def run(no_tc):
+        if no_tc:
+            monkeypatch.setenv("MGB_NO_TC", "1")
+        else:
+            monkeypatch.delenv("MGB_NO_TC", raising=False)
+        m = B.Model(full_model_path, 0, B.PREC_BF16)
+        monkeypatch.delenv("MGB_NO_TC", raising=False)
+        s = m.session(batch=24, max_text=32)
+        enc = s.encode_text([HELLO] * 24)
+        s.prefill([0] * 24)
+        hid, lg, gr = s.teacher_forced(codes)
+        n = s.last_loop_launches
+        s.close(); m.close()
+        return enc, hid, lg, gr, n
+
+    enc_t, hid_t, lg_t, gr_t, n_t = run(False)
+    enc_c, hid_c, lg_c, gr_c, n_c = run(True)
+    assert n_t > n_c                       # the tensor-core path adds one packing kernel per linear layer
+    close(enc_t[0], enc_c[0], 2e-3)
+    for b in (0, 7, 23):
+        close(hid_t[b], hid_c[b], 4e-3)
+        close(lg_t[b], lg_c[b], 4e-3)
+        close(hid_t[b], full_oracle["hid"][:6], 2e-2)
+        close(lg_t[b], full_oracle["lg"][:6], 2e-2)
+    np.testing.assert_array_equal(gr_t[0], gr_t[23])     # batch rows are independent and deterministic
+
+
 # ---- nano-codec ---------------------------------------------------------------------------------------
 
 def test_fsq_bit_exact(B, oracle_mod, codec_path):
