@@ -11,7 +11,10 @@
 // Activations are [B][C][T] f32, time fastest (the reference's layout, nano-codec.cpp:744-748).
 #include <vector>
 
+#include <cstdlib>
+
 #include "common.cuh"
+#include "codec_tc.h"
 #include "kernels.cuh"
 
 namespace mgb {
@@ -193,6 +196,7 @@ __global__ void post_kernel(const PostParams p) {
     p.pcm[i] = tanhf(acc + p.bias[0]);
 }
 
+
 bool ensure_consts() {
     static uint64_t done = 0;
     int dev = 0;
@@ -244,6 +248,18 @@ __global__ void repack_conv_w_kernel(const float * w, __half * out, int Cout, in
     out[i] = co < Cout ? __float2half_rn(w[((size_t)co * Cin + ci) * K + k]) : __float2half_rn(0.0f);
 }
 
+static bool repack_tiles(Codec & c, const float * w, int C, int K, void ** out, cudaStream_t stream) {
+    if (*out) return true;
+    const ctc::Geom g = ctc::geom_for(C);
+    if (!g.ok) return true;          // this stage stays on the CUDA-core conv
+    void * d = nullptr;
+    MGB_CUDA_TRY(cudaMalloc(&d, ctc::weight_image_bytes(g, K)));
+    c.allocations.push_back(d);
+    if (!ctc::pack_weights(w, g, K, d, stream)) return false;
+    *out = d;
+    return true;
+}
+
 static bool repack(Codec & c, const float * w, int Cout, int Cin, int K, void ** out, cudaStream_t stream) {
     if (*out) return true;
     const int CoPad = pad64(Cout);
@@ -260,6 +276,9 @@ static bool repack(Codec & c, const float * w, int Cout, int Cin, int K, void **
 // Decode B utterances of T frames each: codes [B][8][T] (device) -> pcm [B][T*1024] (device).
 bool codec_decode_device(Codec & c, const int32_t * d_codes, int B, int T, float * d_pcm, cudaStream_t stream) {
     if (!ensure_consts()) return false;
+    // residual-block convs (99.9 % of the MACs) run on the tensor cores (codec_conv_tc.cu) unless MGB_CODEC_NO_TC=1;
+    // the 32->864 pre-conv, the grouped transposed convs and the 27->1 post conv stay on the CUDA cores
+    const bool use_tc = getenv("MGB_CODEC_NO_TC") == nullptr;
     // one-time f16 weight repack (ggml_conv_1d converts the kernel to f16)
     if (!c.pre_w16) {
         if (!repack(c, c.pre_w, c.base_ch, c.latent, c.pre_k, &c.pre_w16, stream)) return false;
@@ -274,12 +293,30 @@ bool codec_decode_device(Codec & c, const int32_t * d_codes, int B, int T, float
                 }
         }
     }
-    // scratch: 6 buffers of the largest stage tensor (C*T is maximal, and equal, for stages 2-4)
-    size_t need = 0;
+    if (use_tc && !c.tc_packed) {
+        int C = c.base_ch;
+        for (int i = 0; i < 5; i++) {
+            C /= 2;
+            for (int j = 0; j < 3; j++)
+                for (int k = 0; k < 3; k++) {
+                    CodecResBlock & b = c.rb[i][j][k];
+                    if (!repack_tiles(c, b.in_w, C, c.res_k[j], &b.in_wt, stream) ||
+                        !repack_tiles(c, b.sk_w, C, c.res_k[j], &b.sk_wt, stream)) return false;
+                }
+        }
+        c.tc_packed = true;
+    }
+    // scratch: 6 f32 buffers of the largest stage tensor (C*T is maximal, and equal, for stages 2-4) and two f16
+    // time-major activation images (tensor-core path)
+    size_t need = 0, need_img = 0;
     {
         int C = c.base_ch, Tc = T;
         need = (size_t)C * Tc;
-        for (int i = 0; i < 5; i++) { C /= 2; Tc *= c.up_rates[i]; need = std::max(need, (size_t)C * Tc); }
+        for (int i = 0; i < 5; i++) {
+            C /= 2; Tc *= c.up_rates[i];
+            need = std::max(need, (size_t)C * Tc);
+            need_img = std::max(need_img, ctc::act_bytes(B, C, Tc));
+        }
         need *= (size_t)B;
     }
     if (need > c.buf_elems) {
@@ -287,6 +324,12 @@ bool codec_decode_device(Codec & c, const int32_t * d_codes, int B, int T, float
         c.buf_elems = 0;
         for (auto & b : c.buf) MGB_CUDA_TRY(cudaMalloc((void **)&b, need * sizeof(float)));
         c.buf_elems = need;
+    }
+    if (use_tc && need_img > c.img_bytes) {
+        for (auto & b : c.img) { if (b) cudaFree(b); b = nullptr; }
+        c.img_bytes = 0;
+        for (auto & b : c.img) MGB_CUDA_TRY(cudaMalloc(&b, need_img));
+        c.img_bytes = need_img;
     }
     float * cur = c.buf[0], * up = c.buf[1], * o = c.buf[2], * act = c.buf[3], * act2 = c.buf[4], * sum = c.buf[5];
 
@@ -309,8 +352,42 @@ bool codec_decode_device(Codec & c, const int32_t * d_codes, int B, int T, float
             MGB_LAUNCH_CHECK();
         }
         const size_t total = (size_t)B * Co * To;
+        const ctc::Geom g = ctc::geom_for(Co);
+        const bool tc_stage = use_tc && g.ok && c.rb[i][0][0].in_wt != nullptr;
+        if (tc_stage) {
+            // zero causal history rows of both images for this stage's geometry
+            const size_t pitch = ctc::act_rows(To) * 128;
+            for (auto & im : c.img) MGB_CUDA_TRY(cudaMemset2DAsync(im, pitch, 0, (size_t)ctc::kHP * 128, (size_t)B * g.nchunk, stream));
+        }
         for (int j = 0; j < 3; j++) {
             const float * oin = up;
+            if (tc_stage) {
+                __half * imA = (__half *)c.img[0], * imB = (__half *)c.img[1];
+                ctc::SnakeArgs sa;
+                sa.x = up; sa.out[0] = imA; sa.alpha[0] = c.rb[i][j][0].in_alpha; sa.n_alpha = c.n_alpha_rb[i]; sa.n_out = 1;
+                sa.B = B; sa.C = Co; sa.T = To;
+                if (!ctc::launch_snake_images(g, sa, stream)) return false;
+                for (int k = 0; k < 3; k++) {
+                    const CodecResBlock & rb = c.rb[i][j][k];
+                    ctc::ConvArgs a1;
+                    a1.xa = imA; a1.w = (const __half *)rb.in_wt; a1.bias = rb.in_b;
+                    a1.ya = imB; a1.alpha2 = rb.sk_alpha; a1.n_alpha2 = c.n_alpha_rb[i];
+                    a1.B = B; a1.T = To; a1.K = c.res_k[j]; a1.dil = c.res_dil[k];
+                    if (!ctc::launch_conv(g, a1, stream)) return false;
+                    ctc::ConvArgs a2;
+                    a2.xa = imB; a2.w = (const __half *)rb.sk_wt; a2.bias = rb.sk_b; a2.res = oin;
+                    a2.B = B; a2.T = To; a2.K = c.res_k[j]; a2.dil = 1;
+                    if (k < 2) {
+                        a2.y = o;      // for k = 1 res and y alias: each element is read then written by the same thread
+                        a2.ya = imA; a2.alpha2 = c.rb[i][j][k + 1].in_alpha; a2.n_alpha2 = c.n_alpha_rb[i];
+                    } else {
+                        a2.sum_in = sum; a2.sum_out = sum; a2.sum_mode = j == 0 ? 1 : (j == 1 ? 2 : 3);
+                    }
+                    if (!ctc::launch_conv(g, a2, stream)) return false;
+                    oin = o;
+                }
+                continue;
+            }
             {   // activated input of the first block of this branch
                 SnakeParams sp = {};
                 sp.x = up; sp.y[0] = act; sp.alpha[0] = c.rb[i][j][0].in_alpha; sp.n_alpha = c.n_alpha_rb[i]; sp.n_out = 1;

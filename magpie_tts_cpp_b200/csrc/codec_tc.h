@@ -1,0 +1,55 @@
+// Tensor-core (tcgen05 / TMEM) implicit-GEMM causal conv of the nano-codec residual blocks (reference
+// src/nano-codec.cpp:429-466, 568-641).  See codec_conv_tc.cu for the design.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace mgb {
+namespace ctc {
+
+constexpr int kHP = 56;            // zero rows in front of every time-major activation image: causal history of the largest conv ((11-1)*5 = 50 -> 56)
+constexpr int kTile = 128;         // time steps per accumulator tile (MMA M)
+
+// How a C -> C conv is mapped: output channels in `nsplit` groups of `nper` (padded to npad MMA columns), input
+// channels in `nchunk` chunks of 64 (one 128-byte swizzle row each).
+struct Geom {
+    int C = 0, nsplit = 1, nper = 0, npad = 0, nchunk = 0;
+    bool ok = false;
+};
+Geom geom_for(int C);
+
+// Time-major f16 activation image: [B][nchunk][kHP + Tpad][64 ch] with the 16-byte channel groups of row r XOR-swizzled
+// by (r & 7) (SWIZZLE_128B), so that any 8-row-aligned window is a ready-made shared-memory operand image.
+inline size_t act_rows(int T) { return (size_t)kHP + (size_t)(T + kTile - 1) / kTile * kTile; }
+inline size_t act_bytes(int B, int C, int T) { return (size_t)B * ((C + 63) / 64) * act_rows(T) * 128; }
+
+size_t weight_image_bytes(const Geom & g, int K);
+// f32 (Cout = C, Cin = C, K) PyTorch layout on the device -> f16 tile images [nsplit][nchunk][K][npad x 64]
+bool pack_weights(const float * w, const Geom & g, int K, void * img, cudaStream_t stream);
+
+struct ConvArgs {
+    const __half * xa = nullptr;     // activated input image (time-major)
+    const __half * w = nullptr;      // weight tile images
+    const float * bias = nullptr;    // [C]
+    const float * res = nullptr;     // optional residual, f32 [B][C][T]
+    float * y = nullptr;             // optional raw output conv + bias (+ res), f32 [B][C][T]
+    __half * ya = nullptr;           // optional activated output image f16(half_snake(y; alpha2))
+    const float * alpha2 = nullptr; int n_alpha2 = 0;
+    const float * sum_in = nullptr; float * sum_out = nullptr; int sum_mode = 0;   // 0 none, 1 init, 2 add, 3 add and * 1/3
+    int B = 0, T = 0, K = 0, dil = 1;
+};
+bool launch_conv(const Geom & g, const ConvArgs & a, cudaStream_t stream);
+
+// x f32 [B][C][T] -> up to three activated images f16(half_snake(x; alpha[j]))
+struct SnakeArgs {
+    const float * x = nullptr;
+    __half * out[3] = {};
+    const float * alpha[3] = {};
+    int n_alpha = 0, n_out = 0;
+    int B = 0, C = 0, T = 0;
+};
+bool launch_snake_images(const Geom & g, const SnakeArgs & a, cudaStream_t stream);
+
+}  // namespace ctc
+}  // namespace mgb

@@ -56,6 +56,10 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// same with f16 operands (format 0)
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                  "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
@@ -75,8 +79,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-template <int MT> struct Smem {
-    static constexpr int kStageBytes = BM * 128 + 2 * MT * 128;
+template <int MT, int NB = 2> struct Smem {
+    static constexpr int kStageBytes = BM * 128 + NB * MT * 128;
     static constexpr int kStages = (200 * 1024) / kStageBytes < 8 ? (200 * 1024) / kStageBytes : 8;
     static constexpr int kBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
@@ -84,10 +88,11 @@ template <int MT> struct Smem {
 // Mainloop: accumulates D[128 x MT] (TMEM, fp32) for weight tile `nt`, token tile `mt`; returns the TMEM base address.
 // Wt: [NT][KT] tiles of 16 KB; Xhi/Xlo: [MTiles][KT] tiles of MT*128 bytes.  Must be called by all 192 threads.
 // After the call, epilogue warps (warp >= 2) own TMEM lanes 32*(warp%4) .. +31; call tc::finish() when done.
-template <int MT>
-__device__ __forceinline__ uint32_t mainloop(unsigned char * smem_raw, const __nv_bfloat16 * Wt, const __nv_bfloat16 * Xhi,
-                                             const __nv_bfloat16 * Xlo, int KT, int nt, int mt) {
-    constexpr int S = Smem<MT>::kStages, SB = Smem<MT>::kStageBytes;
+// NB = 2: activations as hi + lo tiles (bf16, two MMAs per k slice); NB = 1: one tile (Xlo unused).  F16: operands are f16.
+template <int MT, int NB = 2, bool F16 = false>
+__device__ __forceinline__ uint32_t mainloop(unsigned char * smem_raw, const void * Wt, const void * Xhi,
+                                             const void * Xlo, int KT, int nt, int mt) {
+    constexpr int S = Smem<MT, NB>::kStages, SB = Smem<MT, NB>::kStageBytes;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char * tiles = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t * bars = reinterpret_cast<uint64_t *>(tiles + S * SB);
@@ -118,10 +123,10 @@ __device__ __forceinline__ uint32_t mainloop(unsigned char * smem_raw, const __n
             unsigned char * st = tiles + s * SB;
             bulk_g2s(st, wsrc + (size_t)kt * (BM * 128), BM * 128, &full[s]);
             bulk_g2s(st + BM * 128, hsrc + (size_t)kt * (MT * 128), MT * 128, &full[s]);
-            bulk_g2s(st + BM * 128 + MT * 128, lsrc + (size_t)kt * (MT * 128), MT * 128, &full[s]);
+            if (NB == 2) bulk_g2s(st + BM * 128 + MT * 128, lsrc + (size_t)kt * (MT * 128), MT * 128, &full[s]);
         }
     } else if (warp == 1 && lane == 0) {
-        constexpr uint32_t idesc = umma_idesc_bf16(BM, MT);
+        constexpr uint32_t idesc = F16 ? umma_idesc_f16(BM, MT) : umma_idesc_bf16(BM, MT);
         for (int kt = 0; kt < KT; kt++) {
             const int s = kt % S;
             mbar_wait(&full[s], (kt / S) & 1);
@@ -130,7 +135,7 @@ __device__ __forceinline__ uint32_t mainloop(unsigned char * smem_raw, const __n
 #pragma unroll
             for (int j = 0; j < BK / 16; j++) {      // 16 k-elements = 32 bytes inside the swizzle row
                 umma_bf16(tmem_base, umma_desc_sw128(a0 + j * 32), umma_desc_sw128(h0 + j * 32), idesc, (kt | j) != 0);
-                umma_bf16(tmem_base, umma_desc_sw128(a0 + j * 32), umma_desc_sw128(l0 + j * 32), idesc, 1u);
+                if (NB == 2) umma_bf16(tmem_base, umma_desc_sw128(a0 + j * 32), umma_desc_sw128(l0 + j * 32), idesc, 1u);
             }
             umma_commit(&empty[s]);                  // frees the stage when the MMAs above have read it
         }

@@ -261,6 +261,7 @@ Codec::~Codec() {
     cudaSetDevice(device);
     for (void * p : allocations) cudaFree(p);
     for (auto & b : buf) if (b) cudaFree(b);
+    for (auto & b : img) if (b) cudaFree(b);
     if (d_codes) cudaFree(d_codes);
     if (d_pcm) cudaFree(d_pcm);
     if (ev0) cudaEventDestroy((cudaEvent_t)ev0);

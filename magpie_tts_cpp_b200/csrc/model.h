@@ -65,7 +65,8 @@ Model * load_model(const char * path, int device, int precision);
 struct CodecResBlock {
     float * in_alpha = nullptr, * in_w = nullptr, * in_b = nullptr;
     float * sk_alpha = nullptr, * sk_w = nullptr, * sk_b = nullptr;
-    void * in_w16 = nullptr, * sk_w16 = nullptr;       // tap-major padded f16 copies (tensor-core path)
+    void * in_w16 = nullptr, * sk_w16 = nullptr;       // tap-major padded f16 copies (CUDA-core direct conv)
+    void * in_wt = nullptr, * sk_wt = nullptr;         // f16 tile images [split][chunk][tap][npad x 64] (tcgen05 path, codec_tc.h)
 };
 struct Codec {
     mgb_codec_hparams hp{};
@@ -82,6 +83,8 @@ struct Codec {
     // scratch, grown on demand
     float * buf[6] = {}; size_t buf_elems = 0;
     void * pre_w16 = nullptr;
+    void * img[2] = {}; size_t img_bytes = 0;   // tcgen05 path: time-major f16 activation images (codec_tc.h)
+    bool tc_packed = false;
     int32_t * d_codes = nullptr; size_t codes_cap = 0;
     float * d_pcm = nullptr; size_t pcm_cap = 0;
     void * stream = nullptr;     // cudaStream_t
