@@ -29,14 +29,17 @@ namespace ctc {
 
 namespace {
 
-constexpr int kThreads = 320;
+constexpr int kEpiWarps = 16;
+constexpr int kThreads = 64 + 32 * kEpiWarps;
+constexpr int kMaxC = 448;
 constexpr int kABytes = (kTile + kHP) * 128;      // one staged activation window (23 KB)
 constexpr int kMaxNA = 4, kMaxNW = 8;
-constexpr int kSmemBudget = 220 * 1024;
+constexpr int kDynSmemMax = 218 * 1024;                 // + 7 KB static epilogue table
+constexpr int kSmemBudget = 214 * 1024;
 
 struct KParams {
     ConvArgs a;
-    int C, nsplit, nper, npad, nchunk;
+    int C, nsplit, nper, npad, nchunk, cs;
     int hp;                 // staged history rows, (K-1)*dil rounded up to 8
     int tps, ngroups;       // taps per weight stage, stages per chunk
     int NA, NW;             // ring depths
@@ -48,33 +51,34 @@ struct KParams {
 
 __device__ __forceinline__ float f16r(float x) { return __half2float(__float2half_rn(x)); }
 
-// x + sin^2(alpha x)/alpha for c < n_alpha, LeakyReLU(0.01) otherwise (nano-codec.cpp:386-417)
-__device__ __forceinline__ float half_snake(float x, int c, const float * alpha, int n_alpha) {
-    if (c < n_alpha) {
-        const float a = __ldg(alpha + c);
-        const float sn = sinf(x * a);
-        return x + (sn * sn) / a;
-    }
-    return x > 0.0f ? x : 0.01f * x;
-}
-
 __device__ __forceinline__ void mbar_arrive(uint64_t * bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-                   "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                 : "r"(taddr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(taddr) : "memory");
+}
+// x + sin^2(alpha x)/alpha with an explicit two-constant reduction to [-pi, pi] and the SFU sine (abs error ~5e-7, far
+// below the f16 rounding applied to the result)
+__device__ __forceinline__ float snake_fast(float x, float a, float inv_a) {
+    const float z = x * a;
+    const float n = rintf(z * 0.15915494309189535f);
+    float r = fmaf(n, -6.2831854820251465f, z);
+    r = fmaf(n, 1.7484556000744883e-7f, r);
+    const float sn = __sinf(r);
+    return fmaf(sn * sn, inv_a, x);
 }
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     const __half2 h = __floats2half2_rn(a, b);
     return *reinterpret_cast<const uint32_t *>(&h);
 }
 
+// MODE 0: activated image only (first conv of a block); 1: + residual, f32 output and activated image (second conv);
+// 2: + residual, accumulated into the 3-branch mean (last block of a branch), no image
+template <int MODE>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const KParams p) {
     extern __shared__ unsigned char smem_raw[];
+    __shared__ float4 ep_tab[kMaxC];      // per output channel {bias, alpha2 (0 = LeakyReLU), 1/alpha2, -}
     unsigned char * base = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     unsigned char * abuf = base;
     unsigned char * wbuf = base + p.NA * kABytes;
@@ -84,6 +88,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const KParams p) {
     uint32_t * tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+    for (int c = threadIdx.x; c < p.cs; c += kThreads) {
+        const float al = (MODE != 2 && c < p.a.n_alpha2) ? p.a.alpha2[c] : 0.0f;
+        ep_tab[c] = c < p.C ? make_float4(p.a.bias[c], al, al != 0.0f ? 1.0f / al : 0.0f, 0.0f) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     if (threadIdx.x == 0) {
         for (int i = 0; i < p.NA; i++) { tc::mbar_init(&a_full[i], 1); tc::mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < p.NW; i++) { tc::mbar_init(&w_full[i], 1); tc::mbar_init(&w_empty[i], 1); }
@@ -170,9 +178,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const KParams p) {
         }
     } else {
         const int q = warp & 3;                        // TMEM lane quarter this warp may access
-        const int half = (warp - 2) >> 2;              // column half
-        const int ngrp = p.npad >> 4;                  // 16-column groups
-        const int g_lo = half == 0 ? 0 : (ngrp + 1) / 2, g_hi = half == 0 ? (ngrp + 1) / 2 : ngrp;
+        const int part = (warp - 2) >> 2;              // which share of the columns (kEpiWarps / 4 shares)
+        const int n8 = p.npad >> 3;                    // 8-column groups
+        const int g_lo = n8 * part / (kEpiWarps / 4), g_hi = n8 * (part + 1) / (kEpiWarps / 4);
+        constexpr int NB8 = MODE == 1 ? 4 : 2;         // 8-column groups per batch
         const long long hrow_bytes = p.rows * 128;
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, it++) {
@@ -181,47 +190,76 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const KParams p) {
             const int h = hb % p.nsplit, b = hb / p.nsplit;
             const int t = tb * kTile + q * 32 + lane;
             const bool tv = t < T;
-            tc::mbar_wait(&acc_full[buf], (it >> 1) & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.npad);
             const int r_img = kHP + t;
-            for (int g = g_lo; g < g_hi; g++) {
-                uint32_t v[16];
-                tmem_ld16(trow + g * 16, v);
+            const int cbase = h * p.nper;
+            // f32 streams are time-major rows [b][t][cs]: this thread's 8-channel groups are 32 contiguous bytes each
+            const size_t row_off = ((size_t)b * T + (tv ? t : 0)) * p.cs + cbase;
+            unsigned char * ya_row = reinterpret_cast<unsigned char *>(p.a.ya) + (long long)b * p.nchunk * hrow_bytes + (long long)r_img * 128;
+            bool waited = false;
+            for (int g = g_lo; g < g_hi; g += NB8) {
+                // residual (and running-sum) values of this batch are fetched before the accumulator is waited for
+                float4 rr[MODE != 0 ? NB8 : 1][2], ss[MODE == 2 ? NB8 : 1][2];
+                if (MODE != 0) {
 #pragma unroll
-                for (int s = 0; s < 2; s++) {
-                    const int n0 = g * 16 + s * 8;
-                    const int co0 = h * p.nper + n0;
-                    float act[8];
+                    for (int j = 0; j < NB8; j++) {
+                        const bool ok = g + j < g_hi && tv;
+                        const float4 * rp = reinterpret_cast<const float4 *>(p.a.res + row_off + (g + j) * 8);
+                        rr[j][0] = ok ? rp[0] : make_float4(0.f, 0.f, 0.f, 0.f);
+                        rr[j][1] = ok ? rp[1] : make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (MODE == 2) {
+                            const bool oks = ok && p.a.sum_mode >= 2;
+                            const float4 * sp = reinterpret_cast<const float4 *>(p.a.sum_in + row_off + (g + j) * 8);
+                            ss[j][0] = oks ? sp[0] : make_float4(0.f, 0.f, 0.f, 0.f);
+                            ss[j][1] = oks ? sp[1] : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                    }
+                }
+                if (!waited) {
+                    tc::mbar_wait(&acc_full[buf], (it >> 1) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    waited = true;
+                }
+                uint32_t v[NB8][8];
+#pragma unroll
+                for (int j = 0; j < NB8; j++)
+                    if (g + j < g_hi) tmem_ld8_nowait(trow + (g + j) * 8, v[j]);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < NB8; j++) {
+                    if (g + j >= g_hi) break;
+                    const int n0 = (g + j) * 8;
+                    if (p.nsplit > 1 && n0 >= p.nper) break;         // column padding of a split belongs to the next split
+                    const int co0 = cbase + n0;
+                    float y[8], act[8];
 #pragma unroll
                     for (int e = 0; e < 8; e++) {
-                        const int co = co0 + e;
-                        const bool cv = (n0 + e) < p.nper;
-                        float y = 0.0f;
-                        if (cv) {
-                            y = __uint_as_float(v[s * 8 + e]) + __ldg(p.a.bias + co);
-                            if (tv) {
-                                const size_t o = ((size_t)b * p.C + co) * T + t;
-                                if (p.a.res) y = p.a.res[o] + y;
-                                if (p.a.y) p.a.y[o] = y;
-                                if (p.a.sum_mode == 1) p.a.sum_out[o] = y;
-                                else if (p.a.sum_mode == 2) p.a.sum_out[o] = p.a.sum_in[o] + y;
-                                else if (p.a.sum_mode == 3) p.a.sum_out[o] = (p.a.sum_in[o] + y) * (1.0f / 3.0f);
-                            }
-                        }
-                        act[e] = (cv && p.a.ya) ? half_snake(y, co, p.a.alpha2, p.a.n_alpha2) : 0.0f;
+                        const float4 ep = ep_tab[co0 + e];            // {bias, alpha, 1/alpha, -}; zeros for padding channels
+                        y[e] = __uint_as_float(v[j][e]) + ep.x;
+                        if (MODE != 0) y[e] += reinterpret_cast<const float *>(&rr[j][0])[e];
+                        if (MODE != 2) act[e] = ep.y != 0.0f ? snake_fast(y[e], ep.y, ep.z) : fmaxf(y[e], 0.01f * y[e]);
                     }
-                    const bool store_grp = p.nsplit == 1 ? true : n0 < p.nper;
-                    if (p.a.ya && tv && store_grp) {
-                        uint4 pk;
-                        pk.x = pack_h2(act[0], act[1]); pk.y = pack_h2(act[2], act[3]);
-                        pk.z = pack_h2(act[4], act[5]); pk.w = pack_h2(act[6], act[7]);
-                        unsigned char * dst = reinterpret_cast<unsigned char *>(p.a.ya) + ((long long)b * p.nchunk + (co0 >> 6)) * hrow_bytes +
-                                              (long long)r_img * 128 + ((((co0 & 63) >> 3) ^ (r_img & 7)) << 4);
-                        *reinterpret_cast<uint4 *>(dst) = pk;
+                    if (MODE == 2) {
+                        const float sc = p.a.sum_mode == 3 ? (1.0f / 3.0f) : 1.0f;
+#pragma unroll
+                        for (int e = 0; e < 8; e++) y[e] = (reinterpret_cast<const float *>(&ss[j][0])[e] + y[e]) * sc;
+                    }
+                    if (tv) {
+                        if (MODE != 0) {
+                            float4 * yp = reinterpret_cast<float4 *>((MODE == 1 ? p.a.y : p.a.sum_out) + row_off + n0);
+                            yp[0] = make_float4(y[0], y[1], y[2], y[3]);
+                            yp[1] = make_float4(y[4], y[5], y[6], y[7]);
+                        }
+                        if (MODE != 2) {
+                            uint4 pk;
+                            pk.x = pack_h2(act[0], act[1]); pk.y = pack_h2(act[2], act[3]);
+                            pk.z = pack_h2(act[4], act[5]); pk.w = pack_h2(act[6], act[7]);
+                            *reinterpret_cast<uint4 *>(ya_row + (long long)(co0 >> 6) * hrow_bytes + ((((co0 & 63) >> 3) ^ (r_img & 7)) << 4)) = pk;
+                        }
                     }
                 }
             }
+            if (!waited) { tc::mbar_wait(&acc_full[buf], (it >> 1) & 1); }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(&acc_empty[buf]);
         }
@@ -252,27 +290,89 @@ __global__ void pack_w_kernel(const float * w, int C, int K, int nsplit, int npe
     }
 }
 
-struct SnakeKParams { SnakeArgs a; int nchunk; long long rows; };
-// grid (time blocks of 128, 8-channel groups, B); thread = one time step
-__global__ void __launch_bounds__(128) snake_images_kernel(const SnakeKParams p) {
-    const int t = blockIdx.x * 128 + threadIdx.x;
-    if (t >= p.a.T) return;
-    const int g8 = blockIdx.y, b = blockIdx.z;
-    const int c0 = g8 * 8;
-    float x[8];
+// HalfSnake -> grouped ConvTranspose1d (groups = Cout, 2 inputs per group, K = 2*stride, first T*stride samples kept;
+// nano-codec.cpp:481-565) on time-major rows, producing the stage input `up` AND the activated images of the three
+// residual branches (their first HalfSnake) in one pass.  grid (time blocks of 128, 8-channel groups, B).
+struct UpKParams { UpArgs a; int cs_in, cs_out, nchunk; long long rows; };
+__device__ __forceinline__ float half_snake_fast(float x, int c, const float * alpha, int n_alpha) {
+    if (c < n_alpha) {
+        const float a = __ldg(alpha + c);
+        return snake_fast(x, a, 1.0f / a);
+    }
+    return fmaxf(x, 0.01f * x);
+}
+__global__ void __launch_bounds__(128) up_tm_kernel(const UpKParams p) {
+    const int to = blockIdx.x * 128 + threadIdx.x;
+    const int To = p.a.T * p.a.s;
+    if (to >= To) return;
+    const int g0 = blockIdx.y * 8, b = blockIdx.z;
+    const int Cout = p.a.Cin / 2, s = p.a.s, K = 2 * s;
+    const int ti = to / s, r = to - ti * s;
+    float v[8];
 #pragma unroll
-    for (int e = 0; e < 8; e++) x[e] = (c0 + e) < p.a.C ? p.a.x[((size_t)b * p.a.C + c0 + e) * p.a.T + t] : 0.0f;
-    const int r_img = kHP + t;
-    const long long off = ((long long)b * p.nchunk + (c0 >> 6)) * p.rows * 128 + (long long)r_img * 128 + ((((c0 & 63) >> 3) ^ (r_img & 7)) << 4);
-    for (int j = 0; j < p.a.n_out; j++) {
+    for (int e = 0; e < 8; e++) v[e] = 0.0f;
+    if (g0 < Cout) {
+#pragma unroll
+        for (int back = 0; back < 2; back++) {
+            if (back == 1 && ti == 0) break;
+            const float * xr = p.a.x + ((size_t)b * p.a.T + (ti - back)) * p.cs_in + 2 * g0;
+            float xin[16];
+#pragma unroll
+            for (int q4 = 0; q4 < 4; q4++) {
+                float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (2 * g0 + 4 * q4 < p.cs_in) f = *reinterpret_cast<const float4 *>(xr + 4 * q4);
+                xin[4 * q4] = f.x; xin[4 * q4 + 1] = f.y; xin[4 * q4 + 2] = f.z; xin[4 * q4 + 3] = f.w;
+            }
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                const int g = g0 + e;
+                if (g < Cout) {
+                    const float a0 = half_snake_fast(xin[2 * e], 2 * g, p.a.alpha, p.a.n_alpha);
+                    const float a1 = half_snake_fast(xin[2 * e + 1], 2 * g + 1, p.a.alpha, p.a.n_alpha);
+                    const float * w0 = p.a.w + (size_t)(2 * g) * K + r + back * s;
+                    v[e] += __ldg(w0) * a0 + __ldg(w0 + K) * a1;
+                }
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 8; e++) if (g0 + e < Cout) v[e] += __ldg(p.a.bias + g0 + e);
+    }
+    float4 * up = reinterpret_cast<float4 *>(p.a.up + ((size_t)b * To + to) * p.cs_out + g0);
+    up[0] = make_float4(v[0], v[1], v[2], v[3]);
+    up[1] = make_float4(v[4], v[5], v[6], v[7]);
+    const int r_img = kHP + to;
+    const long long off = ((long long)b * p.nchunk + (g0 >> 6)) * p.rows * 128 + (long long)r_img * 128 + ((((g0 & 63) >> 3) ^ (r_img & 7)) << 4);
+    for (int j = 0; j < 3; j++) {
         float act[8];
 #pragma unroll
-        for (int e = 0; e < 8; e++) act[e] = (c0 + e) < p.a.C ? half_snake(x[e], c0 + e, p.a.alpha[j], p.a.n_alpha) : 0.0f;
+        for (int e = 0; e < 8; e++) act[e] = (g0 + e) < Cout ? half_snake_fast(v[e], g0 + e, p.a.br_alpha[j], p.a.n_br_alpha) : 0.0f;
         uint4 pk;
         pk.x = pack_h2(act[0], act[1]); pk.y = pack_h2(act[2], act[3]);
         pk.z = pack_h2(act[4], act[5]); pk.w = pack_h2(act[6], act[7]);
-        *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(p.a.out[j]) + off) = pk;
+        *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(p.a.img[j]) + off) = pk;
     }
+}
+
+// HalfSnake -> causal conv (C -> 1, K taps, operands rounded to f16 as ggml_conv_1d does) -> tanh  (nano-codec.cpp:703-712)
+struct PostKParams { PostArgs a; int cs; };
+__global__ void __launch_bounds__(256) post_tm_kernel(const PostKParams p) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)p.a.B * p.a.T) return;
+    const int t = (int)(i % p.a.T);
+    float acc = 0.0f;
+    for (int k = 0; k < p.a.K; k++) {
+        const int tt = t - (p.a.K - 1 - k);
+        if (tt < 0) continue;
+        const float * xr = p.a.x + (i - (size_t)(t - tt)) * p.cs;
+        for (int c0 = 0; c0 < p.a.C; c0 += 4) {
+            const float4 f = *reinterpret_cast<const float4 *>(xr + c0);
+            const float xv[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+            for (int e = 0; e < 4; e++)
+                if (c0 + e < p.a.C) acc = fmaf(f16r(__ldg(p.a.w + (c0 + e) * p.a.K + k)), f16r(half_snake_fast(xv[e], c0 + e, p.a.alpha, p.a.n_alpha)), acc);
+        }
+    }
+    p.a.pcm[i] = tanhf(acc + __ldg(p.a.bias));
 }
 
 }  // namespace
@@ -307,7 +407,7 @@ bool launch_conv(const Geom & g, const ConvArgs & a, cudaStream_t stream) {
     if (!n_sm[dev]) MGB_CUDA_TRY(cudaDeviceGetAttribute(&n_sm[dev], cudaDevAttrMultiProcessorCount, dev));
     KParams p = {};
     p.a = a;
-    p.C = g.C; p.nsplit = g.nsplit; p.nper = g.nper; p.npad = g.npad; p.nchunk = g.nchunk;
+    p.C = g.C; p.nsplit = g.nsplit; p.nper = g.nper; p.npad = g.npad; p.nchunk = g.nchunk; p.cs = row_stride(g.C);
     const int halo = (a.K - 1) * a.dil;
     if (!g.ok || halo > kHP) { set_error("codec: conv shape not supported by the tensor-core path"); return false; }
     p.hp = (halo + 7) / 8 * 8;
@@ -324,20 +424,38 @@ bool launch_conv(const Geom & g, const ConvArgs & a, cudaStream_t stream) {
     p.rows = (long long)act_rows(a.T);
     const size_t smem = 1024 + (size_t)p.NA * kABytes + (size_t)p.NW * p.wstage_bytes + 512;
     if (!(attr_done >> dev & 1)) {
-        MGB_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        MGB_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmemMax));
+        MGB_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmemMax));
+        MGB_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmemMax));
         attr_done |= 1ull << dev;
     }
+    if (g.C > kMaxC) { set_error("codec: too many channels for the tensor-core path"); return false; }
     const int grid = std::min(p.n_tiles, n_sm[dev]);
-    conv_tc_kernel<<<grid, kThreads, smem, stream>>>(p);
+    const int mode = a.sum_mode ? 2 : (a.res ? 1 : 0);
+    if (mode == 0 && !a.ya) { set_error("codec: conv without an output"); return false; }
+    if (mode == 1 && (!a.y || !a.ya)) { set_error("codec: residual conv needs y and ya"); return false; }
+    if (mode == 2 && (!a.res || !a.sum_out)) { set_error("codec: sum conv needs res and sum_out"); return false; }
+    if (mode == 0) conv_tc_kernel<0><<<grid, kThreads, smem, stream>>>(p);
+    else if (mode == 1) conv_tc_kernel<1><<<grid, kThreads, smem, stream>>>(p);
+    else conv_tc_kernel<2><<<grid, kThreads, smem, stream>>>(p);
     MGB_LAUNCH_CHECK();
     return true;
 }
 
-bool launch_snake_images(const Geom & g, const SnakeArgs & a, cudaStream_t stream) {
-    SnakeKParams p = {};
-    p.a = a; p.nchunk = g.nchunk; p.rows = (long long)act_rows(a.T);
-    dim3 grid((a.T + 127) / 128, g.nchunk * 8, a.B);
-    snake_images_kernel<<<grid, 128, 0, stream>>>(p);
+bool launch_up(const Geom & g, const UpArgs & a, cudaStream_t stream) {
+    UpKParams p = {};
+    p.a = a; p.cs_in = row_stride(a.Cin); p.cs_out = row_stride(a.Cin / 2); p.nchunk = g.nchunk; p.rows = (long long)act_rows(a.T * a.s);
+    dim3 grid((a.T * a.s + 127) / 128, p.cs_out / 8, a.B);
+    up_tm_kernel<<<grid, 128, 0, stream>>>(p);
+    MGB_LAUNCH_CHECK();
+    return true;
+}
+
+bool launch_post(const PostArgs & a, cudaStream_t stream) {
+    PostKParams p = {};
+    p.a = a; p.cs = row_stride(a.C);
+    const size_t total = (size_t)a.B * a.T;
+    post_tm_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(p);
     MGB_LAUNCH_CHECK();
     return true;
 }

@@ -65,6 +65,7 @@ struct ConvParams {
     const float * alpha2; int n_alpha2;
     const float * sum_in; float * sum_out; int sum_mode;   // 0 none, 1 init, 2 add, 3 add and * 1/3
     int round_in;            // apply f16 rounding when staging the input (input not pre-rounded)
+    int tm_stride;           // > 0: y is written as time-major rows [B][T][tm_stride] (tensor-core pipeline, codec_tc.h)
     int Cin, Cout, CoPad, K, dil, T;
 };
 
@@ -136,7 +137,7 @@ __global__ void __launch_bounds__(256) conv1d_kernel(const ConvParams p) {
             const size_t o = ((size_t)b * p.Cout + co) * p.T + t;
             float v = acc[r][j] + bv;
             if (p.res) v = p.res[o] + v;
-            if (p.y) p.y[o] = v;
+            if (p.y) p.y[p.tm_stride > 0 ? ((size_t)b * p.T + t) * p.tm_stride + co : o] = v;
             if (p.ya) p.ya[o] = f16r(half_snake(v, co, p.alpha2, p.n_alpha2));
             if (p.sum_mode == 1) p.sum_out[o] = v;
             else if (p.sum_mode == 2) p.sum_out[o] = p.sum_in[o] + v;
@@ -273,12 +274,109 @@ static bool repack(Codec & c, const float * w, int Cout, int Cin, int K, void **
     return true;
 }
 
+// Tensor-core pipeline (codec_conv_tc.cu): f32 streams as time-major rows, f16 activation images, 3 launches per
+// residual block pair -> 1 (up + 3 images) + 18 convs per stage.
+static bool codec_decode_tc(Codec & c, const int32_t * d_codes, int B, int T, float * d_pcm, cudaStream_t stream) {
+    if (!c.tc_packed) {
+        int C = c.base_ch;
+        for (int i = 0; i < 5; i++) {
+            C /= 2;
+            for (int j = 0; j < 3; j++)
+                for (int k = 0; k < 3; k++) {
+                    CodecResBlock & b = c.rb[i][j][k];
+                    if (!repack_tiles(c, b.in_w, C, c.res_k[j], &b.in_wt, stream) ||
+                        !repack_tiles(c, b.sk_w, C, c.res_k[j], &b.sk_wt, stream)) return false;
+                }
+        }
+        c.tc_packed = true;
+    }
+    // scratch: 4 f32 row buffers (cur / sum, up, o) + the latent, 4 activation images (3 branch inputs + 1 intermediate)
+    size_t need = (size_t)std::max(ctc::row_stride(c.base_ch), 32) * T, need_img = 0;
+    {
+        int C = c.base_ch, Tc = T;
+        for (int i = 0; i < 5; i++) {
+            C /= 2; Tc *= c.up_rates[i];
+            need = std::max(need, (size_t)ctc::row_stride(C) * Tc);
+            need_img = std::max(need_img, ctc::act_bytes(B, C, Tc));
+        }
+        need *= (size_t)B;
+    }
+    if (need > c.buf_elems) {
+        for (auto & b : c.buf) { if (b) cudaFree(b); b = nullptr; }
+        c.buf_elems = 0;
+        for (auto & b : c.buf) MGB_CUDA_TRY(cudaMalloc((void **)&b, need * sizeof(float)));
+        c.buf_elems = need;
+    }
+    if (need_img > c.img_bytes) {
+        for (auto & b : c.img) { if (b) cudaFree(b); b = nullptr; }
+        c.img_bytes = 0;
+        for (auto & b : c.img) MGB_CUDA_TRY(cudaMalloc(&b, need_img));
+        c.img_bytes = need_img;
+    }
+    float * cur = c.buf[0], * up = c.buf[1], * o = c.buf[2], * lat = c.buf[3], * sum = c.buf[5];
+
+    if (!codec_fsq_device(d_codes, B, T, lat, stream)) return false;
+    {   // pre-conv 32 -> 864 on the CUDA cores, written as time-major rows
+        ConvParams p = {};
+        p.xa = lat; p.w = (const __half *)c.pre_w16; p.bias = c.pre_b; p.y = cur; p.round_in = 1; p.tm_stride = ctc::row_stride(c.base_ch);
+        p.Cin = c.latent; p.Cout = c.base_ch; p.CoPad = pad64(c.base_ch); p.K = c.pre_k; p.dil = 1; p.T = T;
+        if (!launch_conv(p, B, stream)) return false;
+    }
+    int C = c.base_ch, Tc = T;
+    for (int i = 0; i < 5; i++) {
+        const int s = c.up_rates[i], Co = C / 2, To = Tc * s;
+        const ctc::Geom g = ctc::geom_for(Co);
+        // zero causal-history rows of the images for this stage's geometry
+        const size_t pitch = ctc::act_rows(To) * 128;
+        for (auto & im : c.img) MGB_CUDA_TRY(cudaMemset2DAsync(im, pitch, 0, (size_t)ctc::kHP * 128, (size_t)B * g.nchunk, stream));
+        {
+            ctc::UpArgs u;
+            u.x = cur; u.alpha = c.act_alpha[i]; u.n_alpha = c.n_alpha_act[i]; u.w = c.up_w[i]; u.bias = c.up_b[i]; u.up = up;
+            for (int j = 0; j < 3; j++) { u.img[j] = (__half *)c.img[j]; u.br_alpha[j] = c.rb[i][j][0].in_alpha; }
+            u.n_br_alpha = c.n_alpha_rb[i];
+            u.B = B; u.Cin = C; u.T = Tc; u.s = s;
+            if (!ctc::launch_up(g, u, stream)) return false;
+        }
+        __half * imB = (__half *)c.img[3];
+        for (int j = 0; j < 3; j++) {
+            __half * imA = (__half *)c.img[j];
+            const float * oin = up;
+            for (int k = 0; k < 3; k++) {
+                const CodecResBlock & rb = c.rb[i][j][k];
+                ctc::ConvArgs a1;
+                a1.xa = imA; a1.w = (const __half *)rb.in_wt; a1.bias = rb.in_b;
+                a1.ya = imB; a1.alpha2 = rb.sk_alpha; a1.n_alpha2 = c.n_alpha_rb[i];
+                a1.B = B; a1.T = To; a1.K = c.res_k[j]; a1.dil = c.res_dil[k];
+                if (!ctc::launch_conv(g, a1, stream)) return false;
+                ctc::ConvArgs a2;
+                a2.xa = imB; a2.w = (const __half *)rb.sk_wt; a2.bias = rb.sk_b; a2.res = oin;
+                a2.B = B; a2.T = To; a2.K = c.res_k[j]; a2.dil = 1;
+                if (k < 2) {
+                    a2.y = o;      // for k = 1 res and y alias: each element is read then written by the same thread
+                    a2.ya = imA; a2.alpha2 = c.rb[i][j][k + 1].in_alpha; a2.n_alpha2 = c.n_alpha_rb[i];
+                } else {
+                    a2.sum_in = sum; a2.sum_out = sum; a2.sum_mode = j == 0 ? 1 : (j == 1 ? 2 : 3);
+                }
+                if (!ctc::launch_conv(g, a2, stream)) return false;
+                oin = o;
+            }
+        }
+        std::swap(cur, sum);      // cur = mean of the three branches
+        C = Co; Tc = To;
+    }
+    {
+        ctc::PostArgs pp;
+        pp.x = cur; pp.alpha = c.post_alpha; pp.n_alpha = c.n_alpha_post; pp.w = c.post_w; pp.bias = c.post_b;
+        pp.pcm = d_pcm; pp.B = B; pp.C = C; pp.K = c.post_k; pp.T = Tc;
+        if (!ctc::launch_post(pp, stream)) return false;
+    }
+    c.buf[0] = cur; c.buf[5] = sum;
+    return true;
+}
+
 // Decode B utterances of T frames each: codes [B][8][T] (device) -> pcm [B][T*1024] (device).
 bool codec_decode_device(Codec & c, const int32_t * d_codes, int B, int T, float * d_pcm, cudaStream_t stream) {
     if (!ensure_consts()) return false;
-    // residual-block convs (99.9 % of the MACs) run on the tensor cores (codec_conv_tc.cu) unless MGB_CODEC_NO_TC=1;
-    // the 32->864 pre-conv, the grouped transposed convs and the 27->1 post conv stay on the CUDA cores
-    const bool use_tc = getenv("MGB_CODEC_NO_TC") == nullptr;
     // one-time f16 weight repack (ggml_conv_1d converts the kernel to f16)
     if (!c.pre_w16) {
         if (!repack(c, c.pre_w, c.base_ch, c.latent, c.pre_k, &c.pre_w16, stream)) return false;
@@ -293,30 +391,27 @@ bool codec_decode_device(Codec & c, const int32_t * d_codes, int B, int T, float
                 }
         }
     }
-    if (use_tc && !c.tc_packed) {
-        int C = c.base_ch;
-        for (int i = 0; i < 5; i++) {
-            C /= 2;
-            for (int j = 0; j < 3; j++)
-                for (int k = 0; k < 3; k++) {
-                    CodecResBlock & b = c.rb[i][j][k];
-                    if (!repack_tiles(c, b.in_w, C, c.res_k[j], &b.in_wt, stream) ||
-                        !repack_tiles(c, b.sk_w, C, c.res_k[j], &b.sk_wt, stream)) return false;
-                }
+    // The residual-block convs (99.9 % of the MACs) run on the tensor cores (codec_conv_tc.cu); the 32->864 pre-conv,
+    // the grouped transposed convs and the 27->1 post conv are CUDA-core kernels.  MGB_CODEC_NO_TC=1 selects the
+    // all-CUDA-core pipeline below (kept as an independent implementation for the parity tests).
+    bool use_tc = getenv("MGB_CODEC_NO_TC") == nullptr;
+    {
+        int C = c.base_ch, Tc = T;
+        for (int i = 0; i < 5 && use_tc; i++) {
+            C /= 2; Tc *= c.up_rates[i];
+            const ctc::Geom g = ctc::geom_for(C);
+            const int halo = (c.res_k[2] - 1) * c.res_dil[2];
+            if (!g.ok || halo > ctc::kHP || (C * 2) % 2 != 0) use_tc = false;
         }
-        c.tc_packed = true;
     }
-    // scratch: 6 f32 buffers of the largest stage tensor (C*T is maximal, and equal, for stages 2-4) and two f16
-    // time-major activation images (tensor-core path)
-    size_t need = 0, need_img = 0;
+    if (use_tc) return codec_decode_tc(c, d_codes, B, T, d_pcm, stream);
+
+    // scratch: 6 buffers of the largest stage tensor (C*T is maximal, and equal, for stages 2-4)
+    size_t need = 0;
     {
         int C = c.base_ch, Tc = T;
         need = (size_t)C * Tc;
-        for (int i = 0; i < 5; i++) {
-            C /= 2; Tc *= c.up_rates[i];
-            need = std::max(need, (size_t)C * Tc);
-            need_img = std::max(need_img, ctc::act_bytes(B, C, Tc));
-        }
+        for (int i = 0; i < 5; i++) { C /= 2; Tc *= c.up_rates[i]; need = std::max(need, (size_t)C * Tc); }
         need *= (size_t)B;
     }
     if (need > c.buf_elems) {
@@ -324,12 +419,6 @@ bool codec_decode_device(Codec & c, const int32_t * d_codes, int B, int T, float
         c.buf_elems = 0;
         for (auto & b : c.buf) MGB_CUDA_TRY(cudaMalloc((void **)&b, need * sizeof(float)));
         c.buf_elems = need;
-    }
-    if (use_tc && need_img > c.img_bytes) {
-        for (auto & b : c.img) { if (b) cudaFree(b); b = nullptr; }
-        c.img_bytes = 0;
-        for (auto & b : c.img) MGB_CUDA_TRY(cudaMalloc(&b, need_img));
-        c.img_bytes = need_img;
     }
     float * cur = c.buf[0], * up = c.buf[1], * o = c.buf[2], * act = c.buf[3], * act2 = c.buf[4], * sum = c.buf[5];
 
@@ -352,42 +441,8 @@ bool codec_decode_device(Codec & c, const int32_t * d_codes, int B, int T, float
             MGB_LAUNCH_CHECK();
         }
         const size_t total = (size_t)B * Co * To;
-        const ctc::Geom g = ctc::geom_for(Co);
-        const bool tc_stage = use_tc && g.ok && c.rb[i][0][0].in_wt != nullptr;
-        if (tc_stage) {
-            // zero causal history rows of both images for this stage's geometry
-            const size_t pitch = ctc::act_rows(To) * 128;
-            for (auto & im : c.img) MGB_CUDA_TRY(cudaMemset2DAsync(im, pitch, 0, (size_t)ctc::kHP * 128, (size_t)B * g.nchunk, stream));
-        }
         for (int j = 0; j < 3; j++) {
             const float * oin = up;
-            if (tc_stage) {
-                __half * imA = (__half *)c.img[0], * imB = (__half *)c.img[1];
-                ctc::SnakeArgs sa;
-                sa.x = up; sa.out[0] = imA; sa.alpha[0] = c.rb[i][j][0].in_alpha; sa.n_alpha = c.n_alpha_rb[i]; sa.n_out = 1;
-                sa.B = B; sa.C = Co; sa.T = To;
-                if (!ctc::launch_snake_images(g, sa, stream)) return false;
-                for (int k = 0; k < 3; k++) {
-                    const CodecResBlock & rb = c.rb[i][j][k];
-                    ctc::ConvArgs a1;
-                    a1.xa = imA; a1.w = (const __half *)rb.in_wt; a1.bias = rb.in_b;
-                    a1.ya = imB; a1.alpha2 = rb.sk_alpha; a1.n_alpha2 = c.n_alpha_rb[i];
-                    a1.B = B; a1.T = To; a1.K = c.res_k[j]; a1.dil = c.res_dil[k];
-                    if (!ctc::launch_conv(g, a1, stream)) return false;
-                    ctc::ConvArgs a2;
-                    a2.xa = imB; a2.w = (const __half *)rb.sk_wt; a2.bias = rb.sk_b; a2.res = oin;
-                    a2.B = B; a2.T = To; a2.K = c.res_k[j]; a2.dil = 1;
-                    if (k < 2) {
-                        a2.y = o;      // for k = 1 res and y alias: each element is read then written by the same thread
-                        a2.ya = imA; a2.alpha2 = c.rb[i][j][k + 1].in_alpha; a2.n_alpha2 = c.n_alpha_rb[i];
-                    } else {
-                        a2.sum_in = sum; a2.sum_out = sum; a2.sum_mode = j == 0 ? 1 : (j == 1 ? 2 : 3);
-                    }
-                    if (!ctc::launch_conv(g, a2, stream)) return false;
-                    oin = o;
-                }
-                continue;
-            }
             {   // activated input of the first block of this branch
                 SnakeParams sp = {};
                 sp.x = up; sp.y[0] = act; sp.alpha[0] = c.rb[i][j][0].in_alpha; sp.n_alpha = c.n_alpha_rb[i]; sp.n_out = 1;

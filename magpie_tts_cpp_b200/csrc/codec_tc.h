@@ -21,6 +21,8 @@ Geom geom_for(int C);
 
 // Time-major f16 activation image: [B][nchunk][kHP + Tpad][64 ch] with the 16-byte channel groups of row r XOR-swizzled
 // by (r & 7) (SWIZZLE_128B), so that any 8-row-aligned window is a ready-made shared-memory operand image.
+// f32 tensors of the tensor-core pipeline are TIME-MAJOR rows [B][T][row_stride(C)] (padding channels stay zero)
+inline int row_stride(int C) { return (C + 15) / 16 * 16; }
 inline size_t act_rows(int T) { return (size_t)kHP + (size_t)(T + kTile - 1) / kTile * kTile; }
 inline size_t act_bytes(int B, int C, int T) { return (size_t)B * ((C + 63) / 64) * act_rows(T) * 128; }
 
@@ -32,8 +34,8 @@ struct ConvArgs {
     const __half * xa = nullptr;     // activated input image (time-major)
     const __half * w = nullptr;      // weight tile images
     const float * bias = nullptr;    // [C]
-    const float * res = nullptr;     // optional residual, f32 [B][C][T]
-    float * y = nullptr;             // optional raw output conv + bias (+ res), f32 [B][C][T]
+    const float * res = nullptr;     // optional residual, f32 rows [B][T][row_stride(C)]
+    float * y = nullptr;             // optional raw output conv + bias (+ res), f32 rows
     __half * ya = nullptr;           // optional activated output image f16(half_snake(y; alpha2))
     const float * alpha2 = nullptr; int n_alpha2 = 0;
     const float * sum_in = nullptr; float * sum_out = nullptr; int sum_mode = 0;   // 0 none, 1 init, 2 add, 3 add and * 1/3
@@ -41,15 +43,27 @@ struct ConvArgs {
 };
 bool launch_conv(const Geom & g, const ConvArgs & a, cudaStream_t stream);
 
-// x f32 [B][C][T] -> up to three activated images f16(half_snake(x; alpha[j]))
-struct SnakeArgs {
-    const float * x = nullptr;
-    __half * out[3] = {};
-    const float * alpha[3] = {};
-    int n_alpha = 0, n_out = 0;
-    int B = 0, C = 0, T = 0;
+// HalfSnake -> grouped transposed conv (stride s) of the previous stage's output, writing the stage input `up` (f32 rows)
+// and the three residual branches' first activated images.
+struct UpArgs {
+    const float * x = nullptr;          // [B][T][row_stride(Cin)]
+    const float * alpha = nullptr; int n_alpha = 0;     // HalfSnake in front of the transposed conv
+    const float * w = nullptr;          // [Cin][1][2s]
+    const float * bias = nullptr;       // [Cin/2]
+    float * up = nullptr;               // [B][T*s][row_stride(Cin/2)]
+    __half * img[3] = {};
+    const float * br_alpha[3] = {}; int n_br_alpha = 0;
+    int B = 0, Cin = 0, T = 0, s = 1;
 };
-bool launch_snake_images(const Geom & g, const SnakeArgs & a, cudaStream_t stream);
+bool launch_up(const Geom & g_out, const UpArgs & a, cudaStream_t stream);
+
+// HalfSnake -> conv (C -> 1) -> tanh on f32 rows -> pcm [B][T]
+struct PostArgs {
+    const float * x = nullptr; const float * alpha = nullptr; int n_alpha = 0;
+    const float * w = nullptr; const float * bias = nullptr; float * pcm = nullptr;
+    int B = 0, C = 0, K = 0, T = 0;
+};
+bool launch_post(const PostArgs & a, cudaStream_t stream);
 
 }  // namespace ctc
 }  // namespace mgb

@@ -83,7 +83,7 @@ struct Codec {
     // scratch, grown on demand
     float * buf[6] = {}; size_t buf_elems = 0;
     void * pre_w16 = nullptr;
-    void * img[2] = {}; size_t img_bytes = 0;   // tcgen05 path: time-major f16 activation images (codec_tc.h)
+    void * img[4] = {}; size_t img_bytes = 0;   // tcgen05 path: time-major f16 activation images (codec_tc.h)
     bool tc_packed = false;
     int32_t * d_codes = nullptr; size_t codes_cap = 0;
     float * d_pcm = nullptr; size_t pcm_cap = 0;
