@@ -51,8 +51,43 @@ struct KParams {
 
 __device__ __forceinline__ float f16r(float x) { return __half2float(__float2half_rn(x)); }
 
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+// low word of a K-major SWIZZLE_128B shared-memory matrix descriptor (start address >> 4, LBO = 1); the high word is
+// constant: SBO = 1024 B >> 4 (bits 32-45), version 1 (bit 46), layout SWIZZLE_128B = 2 (bits 61-63)
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
+constexpr uint32_t kDescHi = 64u | (1u << 14) | (2u << 29);
+__device__ __forceinline__ void umma_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
+                 ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHi) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t * bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                   "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// 256-bit global accesses (one full 32-byte sector per thread)
+__device__ __forceinline__ void ldg256(const float * p, float * v) {
+    asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void stg256f(float * p, const float * v) {
+    asm volatile("st.global.v8.f32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};"
+                 ::"f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "l"(p) : "memory");
+}
+__device__ __forceinline__ void stg256(void * p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f, uint32_t g, uint32_t h) {
+    asm volatile("st.global.v8.b32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};"
+                 ::"r"(a), "r"(b), "r"(c), "r"(d), "r"(e), "r"(f), "r"(g), "r"(h), "l"(p) : "memory");
 }
 __device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&v)[8]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -78,7 +113,9 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const KParams p) {
     extern __shared__ unsigned char smem_raw[];
-    __shared__ float4 ep_tab[kMaxC];      // per output channel {bias, alpha2 (0 = LeakyReLU), 1/alpha2, -}
+    // per output channel: bias, alpha2 (0 = LeakyReLU) and 1/alpha2; per 8-channel group: 0 = all LeakyReLU, 1 = all snake, 2 = mixed
+    __shared__ __align__(16) float s_bias[kMaxC], s_alpha[kMaxC], s_inv[kMaxC];
+    __shared__ int s_kind[kMaxC / 8];
     unsigned char * base = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     unsigned char * abuf = base;
     unsigned char * wbuf = base + p.NA * kABytes;
@@ -89,8 +126,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const KParams p) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     for (int c = threadIdx.x; c < p.cs; c += kThreads) {
-        const float al = (MODE != 2 && c < p.a.n_alpha2) ? p.a.alpha2[c] : 0.0f;
-        ep_tab[c] = c < p.C ? make_float4(p.a.bias[c], al, al != 0.0f ? 1.0f / al : 0.0f, 0.0f) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float al = (MODE != 2 && c < p.a.n_alpha2 && c < p.C) ? p.a.alpha2[c] : 0.0f;
+        s_bias[c] = c < p.C ? p.a.bias[c] : 0.0f;
+        s_alpha[c] = al;
+        s_inv[c] = al != 0.0f ? 1.0f / al : 0.0f;
+    }
+    for (int g8 = threadIdx.x; g8 < p.cs / 8; g8 += kThreads) {
+        int n_snake = 0;
+        for (int e = 0; e < 8; e++) {
+            const int c = g8 * 8 + e;
+            n_snake += (MODE != 2 && c < p.a.n_alpha2 && c < p.C && p.a.alpha2[c] != 0.0f) ? 1 : 0;
+        }
+        s_kind[g8] = n_snake == 0 ? 0 : (n_snake == 8 ? 1 : 2);
     }
     if (threadIdx.x == 0) {
         for (int i = 0; i < p.NA; i++) { tc::mbar_init(&a_full[i], 1); tc::mbar_init(&a_empty[i], 1); }
@@ -109,159 +156,198 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const KParams p) {
     const int K = p.a.K, T = p.a.T;
     const int tile_bytes = p.npad * 128;
 
+    // Producer and MMA roles run their loops warp-uniformly (all lanes poll the barriers; one elected lane issues), so
+    // that addresses and descriptors live in uniform registers and the per-MMA issue cost stays a few instructions.
     if (warp == 0) {
-        if (lane == 0) {
-            const uint32_t abytes = (uint32_t)(kTile + p.hp) * 128;
-            uint32_t ia = 0, iw = 0;
-            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-                const int tb = tile % p.tiles_per_b, hb = tile / p.tiles_per_b;
-                const int h = hb % p.nsplit, b = hb / p.nsplit;
-                const long long row0 = (long long)kHP + (long long)tb * kTile - p.hp;
-                for (int c = 0; c < p.nchunk; c++) {
-                    const int sa = ia % p.NA;
-                    tc::mbar_wait(&a_empty[sa], ((ia / p.NA) & 1) ^ 1);
+        const uint32_t abytes = (uint32_t)(kTile + p.hp) * 128;
+        const bool leader = elect_one();
+        uint32_t ia = 0, iw = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            const int tb = tile % p.tiles_per_b, hb = tile / p.tiles_per_b;
+            const int h = hb % p.nsplit, b = hb / p.nsplit;
+            const long long row0 = (long long)kHP + (long long)tb * kTile - p.hp;
+            for (int c = 0; c < p.nchunk; c++) {
+                const int sa = ia % p.NA;
+                tc::mbar_wait(&a_empty[sa], ((ia / p.NA) & 1) ^ 1);
+                if (leader) {
                     tc::mbar_expect_tx(&a_full[sa], abytes);
                     tc::bulk_g2s(abuf + sa * kABytes,
                                  reinterpret_cast<const unsigned char *>(p.a.xa) + (((long long)b * p.nchunk + c) * p.rows + row0) * 128,
                                  abytes, &a_full[sa]);
-                    ia++;
-                    const unsigned char * wsrc = reinterpret_cast<const unsigned char *>(p.a.w) + ((size_t)(h * p.nchunk + c) * K) * tile_bytes;
-                    for (int g = 0; g < p.ngroups; g++) {
-                        const int sw = iw % p.NW;
-                        const int nt = min(p.tps, K - g * p.tps);
-                        tc::mbar_wait(&w_empty[sw], ((iw / p.NW) & 1) ^ 1);
+                }
+                ia++;
+                const unsigned char * wsrc = reinterpret_cast<const unsigned char *>(p.a.w) + ((size_t)(h * p.nchunk + c) * K) * tile_bytes;
+                for (int g = 0; g < p.ngroups; g++) {
+                    const int sw = iw % p.NW;
+                    const int nt = min(p.tps, K - g * p.tps);
+                    tc::mbar_wait(&w_empty[sw], ((iw / p.NW) & 1) ^ 1);
+                    if (leader) {
                         tc::mbar_expect_tx(&w_full[sw], (uint32_t)(nt * tile_bytes));
                         tc::bulk_g2s(wbuf + (size_t)sw * p.wstage_bytes, wsrc + (size_t)g * p.tps * tile_bytes, (uint32_t)(nt * tile_bytes), &w_full[sw]);
-                        iw++;
                     }
+                    iw++;
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = tc::umma_idesc_f16(kTile, p.npad);
-            uint32_t ia = 0, iw = 0, it = 0;
-            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, it++) {
-                const int buf = it & 1;
-                tc::mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t dcol = tmem_base + (uint32_t)(buf * p.npad);
-                uint32_t first = 1;
-                for (int c = 0; c < p.nchunk; c++) {
-                    const int sa = ia % p.NA;
-                    tc::mbar_wait(&a_full[sa], (ia / p.NA) & 1);
-                    const uint32_t a0 = tc::smem_u32(abuf + sa * kABytes);
-                    const int nk16 = min(4, (p.C - c * 64 + 15) >> 4);
-                    for (int g = 0; g < p.ngroups; g++) {
-                        const int sw = iw % p.NW;
-                        const int nt = min(p.tps, K - g * p.tps);
-                        tc::mbar_wait(&w_full[sw], (iw / p.NW) & 1);
-                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        const uint32_t w0 = tc::smem_u32(wbuf + (size_t)sw * p.wstage_bytes);
-                        for (int q = 0; q < nt; q++) {
-                            const int k = g * p.tps + q;
-                            const uint32_t ak = a0 + (uint32_t)(p.hp - (K - 1 - k) * p.a.dil) * 128;
-                            const uint32_t wk = w0 + (uint32_t)(q * tile_bytes);
-                            for (int j = 0; j < nk16; j++) {
-                                tc::umma_bf16(dcol, tc::umma_desc_sw128(ak + j * 32), tc::umma_desc_sw128(wk + j * 32), idesc, first ^ 1u);
-                                first = 0;
-                            }
-                        }
-                        tc::umma_commit(&w_empty[sw]);
-                        iw++;
-                    }
-                    tc::umma_commit(&a_empty[sa]);
-                    ia++;
-                }
-                tc::umma_commit(&acc_full[buf]);
-            }
-        }
-    } else {
-        const int q = warp & 3;                        // TMEM lane quarter this warp may access
-        const int part = (warp - 2) >> 2;              // which share of the columns (kEpiWarps / 4 shares)
-        const int n8 = p.npad >> 3;                    // 8-column groups
-        const int g_lo = n8 * part / (kEpiWarps / 4), g_hi = n8 * (part + 1) / (kEpiWarps / 4);
-        constexpr int NB8 = MODE == 1 ? 4 : 2;         // 8-column groups per batch
-        const long long hrow_bytes = p.rows * 128;
-        uint32_t it = 0;
+        const uint32_t idesc = tc::umma_idesc_f16(kTile, p.npad);
+        const bool leader = elect_one();
+        const uint32_t tile_d = (uint32_t)tile_bytes >> 4;             // descriptor address units are 16 bytes
+        const uint32_t dil_d = (uint32_t)p.a.dil * 8;                   // one row = 128 bytes = 8 units
+        uint32_t ia = 0, iw = 0, it = 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, it++) {
             const int buf = it & 1;
+            tc::mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t dcol = tmem_base + (uint32_t)(buf * p.npad);
+            uint32_t accum = 0;
+            for (int c = 0; c < p.nchunk; c++) {
+                const int sa = ia % p.NA;
+                tc::mbar_wait(&a_full[sa], (ia / p.NA) & 1);
+                // tap 0 reads rows hp - (K-1)*dil ..., every further tap dil rows later
+                const uint32_t a_lo0 = desc_lo(tc::smem_u32(abuf + sa * kABytes) + (uint32_t)(p.hp - (K - 1) * p.a.dil) * 128);
+                const int nk16 = min(4, (p.C - c * 64 + 15) >> 4);
+                for (int g = 0; g < p.ngroups; g++) {
+                    const int sw = iw % p.NW;
+                    const int nt = min(p.tps, K - g * p.tps);
+                    tc::mbar_wait(&w_full[sw], (iw / p.NW) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    uint32_t a_lo = a_lo0 + (uint32_t)(g * p.tps) * dil_d;
+                    uint32_t w_lo = desc_lo(tc::smem_u32(wbuf + (size_t)sw * p.wstage_bytes));
+                    if (leader) {
+                        for (int q = 0; q < nt; q++) {
+                            umma_lo(dcol, a_lo, w_lo, idesc, accum);
+                            accum = 1;
+                            if (nk16 > 1) umma_lo(dcol, a_lo + 2, w_lo + 2, idesc, 1u);
+                            if (nk16 > 2) umma_lo(dcol, a_lo + 4, w_lo + 4, idesc, 1u);
+                            if (nk16 > 3) umma_lo(dcol, a_lo + 6, w_lo + 6, idesc, 1u);
+                            a_lo += dil_d; w_lo += tile_d;
+                        }
+                        tc::umma_commit(&w_empty[sw]);
+                    }
+                    accum = 1;
+                    iw++;
+                }
+                if (leader) tc::umma_commit(&a_empty[sa]);
+                ia++;
+            }
+            if (leader) tc::umma_commit(&acc_full[buf]);
+        }
+    } else {
+        // Epilogue: thread = one time step (TMEM lane), warp = 32 steps x a share of the 16-channel column units.  The
+        // residual values of the NEXT unit (possibly of the next tile) are fetched while the current one is processed.
+        const int q = warp & 3;                        // TMEM lane quarter this warp may access
+        const int part = (warp - 2) >> 2;              // which share of the columns (kEpiWarps / 4 shares)
+        const int n16 = p.npad >> 4;
+        const int u_lo = n16 * part / (kEpiWarps / 4), u_hi = n16 * (part + 1) / (kEpiWarps / 4);
+        const long long hrow_bytes = p.rows * 128;
+        struct TileInfo { bool tv; int r_img, cbase, b; size_t row_off; };
+        auto decode = [&](int tile) {
+            TileInfo ti;
             const int tb = tile % p.tiles_per_b, hb = tile / p.tiles_per_b;
-            const int h = hb % p.nsplit, b = hb / p.nsplit;
+            const int h = hb % p.nsplit;
+            ti.b = hb / p.nsplit;
             const int t = tb * kTile + q * 32 + lane;
-            const bool tv = t < T;
+            ti.tv = tile < p.n_tiles && t < T;
+            ti.r_img = kHP + t;
+            ti.cbase = h * p.nper;
+            ti.row_off = ((size_t)ti.b * T + (ti.tv ? t : 0)) * p.cs + ti.cbase;
+            return ti;
+        };
+        uint32_t it = 0;
+        TileInfo cur = decode(blockIdx.x);
+        float rn[16];
+#pragma unroll
+        for (int e = 0; e < 16; e++) rn[e] = 0.0f;
+        if (MODE != 0 && u_lo < u_hi && cur.tv) { ldg256(p.a.res + cur.row_off + u_lo * 16, rn); ldg256(p.a.res + cur.row_off + u_lo * 16 + 8, rn + 8); }
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, it++) {
+            const int buf = it & 1;
+            const TileInfo nxt = decode(tile + gridDim.x);
+            tc::mbar_wait(&acc_full[buf], (it >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.npad);
-            const int r_img = kHP + t;
-            const int cbase = h * p.nper;
-            // f32 streams are time-major rows [b][t][cs]: this thread's 8-channel groups are 32 contiguous bytes each
-            const size_t row_off = ((size_t)b * T + (tv ? t : 0)) * p.cs + cbase;
-            unsigned char * ya_row = reinterpret_cast<unsigned char *>(p.a.ya) + (long long)b * p.nchunk * hrow_bytes + (long long)r_img * 128;
-            bool waited = false;
-            for (int g = g_lo; g < g_hi; g += NB8) {
-                // residual (and running-sum) values of this batch are fetched before the accumulator is waited for
-                float4 rr[MODE != 0 ? NB8 : 1][2], ss[MODE == 2 ? NB8 : 1][2];
+            unsigned char * ya_row = reinterpret_cast<unsigned char *>(p.a.ya) + (long long)cur.b * p.nchunk * hrow_bytes + (long long)cur.r_img * 128;
+            for (int u = u_lo; u < u_hi; u++) {
+                float rr[16];
                 if (MODE != 0) {
 #pragma unroll
-                    for (int j = 0; j < NB8; j++) {
-                        const bool ok = g + j < g_hi && tv;
-                        const float4 * rp = reinterpret_cast<const float4 *>(p.a.res + row_off + (g + j) * 8);
-                        rr[j][0] = ok ? rp[0] : make_float4(0.f, 0.f, 0.f, 0.f);
-                        rr[j][1] = ok ? rp[1] : make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (MODE == 2) {
-                            const bool oks = ok && p.a.sum_mode >= 2;
-                            const float4 * sp = reinterpret_cast<const float4 *>(p.a.sum_in + row_off + (g + j) * 8);
-                            ss[j][0] = oks ? sp[0] : make_float4(0.f, 0.f, 0.f, 0.f);
-                            ss[j][1] = oks ? sp[1] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int e = 0; e < 16; e++) rr[e] = rn[e];
+                    // prefetch the residual of the next unit
+                    const bool in_tile = u + 1 < u_hi;
+                    const TileInfo & nt = in_tile ? cur : nxt;
+                    const int un = in_tile ? u + 1 : u_lo;
+                    if (nt.tv) { ldg256(p.a.res + nt.row_off + un * 16, rn); ldg256(p.a.res + nt.row_off + un * 16 + 8, rn + 8); }
+                }
+                float ss[MODE == 2 ? 16 : 1];
+                if (MODE == 2) {
+#pragma unroll
+                    for (int e = 0; e < 16; e++) ss[e] = 0.0f;
+                    if (p.a.sum_mode >= 2 && cur.tv) { ldg256(p.a.sum_in + cur.row_off + u * 16, ss); ldg256(p.a.sum_in + cur.row_off + u * 16 + 8, ss + 8); }
+                }
+                uint32_t v[16];
+                tmem_ld16(trow + u * 16, v);
+                const int co0 = cur.cbase + u * 16;
+                float y[16];
+                {
+                    const float4 * bp = reinterpret_cast<const float4 *>(s_bias + co0);
+#pragma unroll
+                    for (int e4 = 0; e4 < 4; e4++) {
+                        const float4 bv = bp[e4];
+                        y[4 * e4] = __uint_as_float(v[4 * e4]) + bv.x; y[4 * e4 + 1] = __uint_as_float(v[4 * e4 + 1]) + bv.y;
+                        y[4 * e4 + 2] = __uint_as_float(v[4 * e4 + 2]) + bv.z; y[4 * e4 + 3] = __uint_as_float(v[4 * e4 + 3]) + bv.w;
+                    }
+                    if (MODE != 0) {
+#pragma unroll
+                        for (int e = 0; e < 16; e++) y[e] += rr[e];
+                    }
+                }
+                if (MODE != 2) {
+                    uint32_t pk[8];
+#pragma unroll
+                    for (int hh = 0; hh < 2; hh++) {
+                        float act[8];
+                        const int kind = s_kind[(co0 >> 3) + hh];         // warp-uniform
+                        if (kind == 0) {
+#pragma unroll
+                            for (int e = 0; e < 8; e++) act[e] = fmaxf(y[hh * 8 + e], 0.01f * y[hh * 8 + e]);
+                        } else {
+                            const float4 * ap = reinterpret_cast<const float4 *>(s_alpha + co0 + hh * 8);
+                            const float4 * ip = reinterpret_cast<const float4 *>(s_inv + co0 + hh * 8);
+                            const float4 a0 = ap[0], a1 = ap[1], i0 = ip[0], i1 = ip[1];
+                            const float al[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                            const float iv[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
+#pragma unroll
+                            for (int e = 0; e < 8; e++) act[e] = snake_fast(y[hh * 8 + e], al[e], iv[e]);     // branch-free: independent chains
+                            if (kind == 2) {
+#pragma unroll
+                                for (int e = 0; e < 8; e++) act[e] = al[e] != 0.0f ? act[e] : fmaxf(y[hh * 8 + e], 0.01f * y[hh * 8 + e]);
+                            }
                         }
+#pragma unroll
+                        for (int e2 = 0; e2 < 4; e2++) pk[hh * 4 + e2] = pack_h2(act[2 * e2], act[2 * e2 + 1]);
+                    }
+                    if (cur.tv) {
+                        // the unit's two 16-byte groups share one 32-byte sector of the swizzled row; odd rows swap them
+                        const int sw = cur.r_img & 7;
+                        unsigned char * dst = ya_row + (long long)(co0 >> 6) * hrow_bytes + (((((co0 & 63) >> 3) ^ sw) & 6) << 4);
+                        const bool swap = sw & 1;
+                        stg256(dst, swap ? pk[4] : pk[0], swap ? pk[5] : pk[1], swap ? pk[6] : pk[2], swap ? pk[7] : pk[3],
+                                    swap ? pk[0] : pk[4], swap ? pk[1] : pk[5], swap ? pk[2] : pk[6], swap ? pk[3] : pk[7]);
                     }
                 }
-                if (!waited) {
-                    tc::mbar_wait(&acc_full[buf], (it >> 1) & 1);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    waited = true;
-                }
-                uint32_t v[NB8][8];
-#pragma unroll
-                for (int j = 0; j < NB8; j++)
-                    if (g + j < g_hi) tmem_ld8_nowait(trow + (g + j) * 8, v[j]);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                for (int j = 0; j < NB8; j++) {
-                    if (g + j >= g_hi) break;
-                    const int n0 = (g + j) * 8;
-                    if (p.nsplit > 1 && n0 >= p.nper) break;         // column padding of a split belongs to the next split
-                    const int co0 = cbase + n0;
-                    float y[8], act[8];
-#pragma unroll
-                    for (int e = 0; e < 8; e++) {
-                        const float4 ep = ep_tab[co0 + e];            // {bias, alpha, 1/alpha, -}; zeros for padding channels
-                        y[e] = __uint_as_float(v[j][e]) + ep.x;
-                        if (MODE != 0) y[e] += reinterpret_cast<const float *>(&rr[j][0])[e];
-                        if (MODE != 2) act[e] = ep.y != 0.0f ? snake_fast(y[e], ep.y, ep.z) : fmaxf(y[e], 0.01f * y[e]);
-                    }
+                if (MODE != 0 && cur.tv) {
                     if (MODE == 2) {
                         const float sc = p.a.sum_mode == 3 ? (1.0f / 3.0f) : 1.0f;
 #pragma unroll
-                        for (int e = 0; e < 8; e++) y[e] = (reinterpret_cast<const float *>(&ss[j][0])[e] + y[e]) * sc;
+                        for (int e = 0; e < 16; e++) y[e] = (ss[e] + y[e]) * sc;
                     }
-                    if (tv) {
-                        if (MODE != 0) {
-                            float4 * yp = reinterpret_cast<float4 *>((MODE == 1 ? p.a.y : p.a.sum_out) + row_off + n0);
-                            yp[0] = make_float4(y[0], y[1], y[2], y[3]);
-                            yp[1] = make_float4(y[4], y[5], y[6], y[7]);
-                        }
-                        if (MODE != 2) {
-                            uint4 pk;
-                            pk.x = pack_h2(act[0], act[1]); pk.y = pack_h2(act[2], act[3]);
-                            pk.z = pack_h2(act[4], act[5]); pk.w = pack_h2(act[6], act[7]);
-                            *reinterpret_cast<uint4 *>(ya_row + (long long)(co0 >> 6) * hrow_bytes + ((((co0 & 63) >> 3) ^ (r_img & 7)) << 4)) = pk;
-                        }
-                    }
+                    float * yp = (MODE == 1 ? p.a.y : p.a.sum_out) + cur.row_off + u * 16;
+                    stg256f(yp, y); stg256f(yp + 8, y + 8);
                 }
             }
-            if (!waited) { tc::mbar_wait(&acc_full[buf], (it >> 1) & 1); }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(&acc_empty[buf]);
+            cur = nxt;
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -380,12 +466,18 @@ __global__ void __launch_bounds__(256) post_tm_kernel(const PostKParams p) {
 Geom geom_for(int C) {
     Geom g;
     g.C = C;
-    g.nsplit = (C + 223) / 224;
-    if (C <= 0 || C % g.nsplit != 0) return g;
-    g.nper = C / g.nsplit;
-    if (g.nsplit > 1 && (g.nper % 8 != 0 || C % 16 != 0)) return g;
+    if (C <= 0) return g;
+    // output channels in `nsplit` equal groups of at most 224; a split group must be a whole number of 16-channel units
+    for (g.nsplit = 1; g.nsplit <= 8; g.nsplit++) {
+        if (C % g.nsplit != 0) continue;
+        const int nper = C / g.nsplit;
+        if (nper > 224) continue;
+        if (g.nsplit > 1 && nper % 16 != 0) continue;
+        g.nper = nper;
+        break;
+    }
+    if (!g.nper) return g;
     g.npad = (g.nper + 15) / 16 * 16;
-    if (g.npad < 16 || g.npad > 256) return g;
     g.nchunk = (C + 63) / 64;
     g.ok = true;
     return g;
