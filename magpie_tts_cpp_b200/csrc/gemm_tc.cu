@@ -98,13 +98,23 @@ __global__ void __launch_bounds__(tc::kThreads, 1) tc_linear_kernel(const bf * W
             uint32_t v[32];
             tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + c, v);
             if (n < e.N) {
+                // residual values first (Y may alias res for the in-place x += W h updates, which would otherwise
+                // serialise 32 dependent load -> store round trips)
+                float r[32];
+                if (e.res) {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        const int m = mt * MT + c + j;
+                        r[j] = m < e.M ? e.res[(size_t)m * e.ldr + n] : 0.0f;
+                    }
+                }
 #pragma unroll
                 for (int j = 0; j < 32; j++) {
                     const int m = mt * MT + c + j;
                     if (m < e.M) {
                         float y = __uint_as_float(v[j]) + bias;
                         if (e.act == ACT_GELU) y = gelu_ggml(y, e.gelu_f16);
-                        if (e.res) y += e.res[(size_t)m * e.ldr + n];
+                        if (e.res) y += r[j];
                         if (e.n_q < 0 || n < e.n_q) e.Y[(size_t)m * e.ldy + n] = y;
                         else {
                             const size_t slot = (size_t)e.tok_slot[m] * e.dkv;

@@ -220,12 +220,19 @@ __global__ void __launch_bounds__(kLtThreads, 1) lt_kernel(const LtParams p) {
         if (cb < 7) {
             // seq[cb+1] = in_proj . E_cb[code] + b, embedding NOT scaled by 1/8 (magpie.cpp:1274-1313)
             const int fed = forced ? forced[cb] : pick;
-            const float * er = p.audio_emb[cb] + (size_t)fed * d;
-            for (int i = tid; i < d; i += kLtThreads) S.hid[i] = er[i];
-            __syncthreads();
-            gemv_bcast<T, CS>(cluster, (const T *)p.in_w, L, d, S.hid, S.seq, rank,
-                              [&](int n, float v) { return v + p.in_b[n]; });
-            cluster_barrier<CS>(cluster);
+            if (p.in_table[cb] && p.stream_feedback == 0) {
+                // P_cb = E_cb . Win^T + b was folded at load: the feedback in-projection is a row gather, done
+                // redundantly by every CTA (no exchange, no cluster barrier)
+                if (tid < L) S.seq[tid] = p.in_table[cb][(size_t)fed * L + tid];
+                __syncthreads();
+            } else {
+                const float * er = p.audio_emb[cb] + (size_t)fed * d;
+                for (int i = tid; i < d; i += kLtThreads) S.hid[i] = er[i];
+                __syncthreads();
+                gemv_bcast<T, CS>(cluster, (const T *)p.in_w, L, d, S.hid, S.seq, rank,
+                                  [&](int n, float v) { return v + p.in_b[n]; });
+                cluster_barrier<CS>(cluster);
+            }
         }
     }
     // p.next_codes = what the next decoder step consumes (the forced codes under teacher forcing)
@@ -271,6 +278,8 @@ bool launch_local_transformer(const Model & m, const LtArgs & a, cudaStream_t st
     p.sampled = a.sampled; p.argmax = a.argmax; p.next_codes = a.next_codes; p.logits = a.logits; p.eos_flag = a.eos_flag;
     p.d_step = a.d_step; p.T_total = a.T_total; p.min_frames = a.min_frames; p.done_step = a.done_step; p.hidden_hist = a.hidden_hist;
     for (int cb = 0; cb < 8; cb++) p.in_table[cb] = m.lt_in_table[cb];
+    // MGB_LT_STREAM keeps the independent (GEMV) formulation alive for the parity tests; f32 models always use it
+    p.stream_feedback = (getenv("MGB_LT_STREAM") != nullptr || m.precision == MGB_PREC_F32) ? 1 : 0;
     // small batches, bf16: weights resident in shared memory (lt_resident.cu)
     if (lt_resident_supported(m, a.B)) return launch_lt_resident(p, stream);
     // 16-CTA (non-portable) clusters when the device can schedule them, else the portable 8

@@ -170,72 +170,98 @@ struct AttnParams {
 
 constexpr int kAttnWarps = 4;
 
-// grid (H, M), 128 threads.  Keys are processed in chunks of 32: lane j owns key j of the chunk for
-// the q.k dot (reads its whole row with 16-byte loads), then lanes own output dims for P.V with the
-// probabilities broadcast by shuffle.  Online softmax per warp, merged across the 4 warps at the end.
+// grid (H, M), 128 threads.  A key/value row of one head (DH elements) is read by LPK = DH / VEC adjacent lanes with one
+// 16-byte load each (fully used sectors), so a warp instruction covers 32 / LPK keys; each lane group keeps its own online
+// softmax state (m, l, acc over the lane's VEC output dims) for the keys it owns, 4 key slots are in flight per lane, and
+// the groups / warps are merged at the end.
 template <typename T, int DH>
 __global__ void __launch_bounds__(kAttnWarps * 32) attention_kernel(const AttnParams p) {
     constexpr int VEC = WT<T>::VEC;
-    constexpr int EPL = DH / 32;
-    __shared__ __align__(16) float sq[DH];
+    constexpr int LPK = DH / VEC;            // lanes per key row
+    constexpr int KPI = 32 / LPK;            // keys per warp instruction
+    constexpr int U = 4;                     // key slots in flight per lane
+    static_assert(LPK >= 1 && LPK <= 32 && (LPK & (LPK - 1)) == 0, "head dim / vector width must be a power of two <= 32");
     __shared__ float s_m[kAttnWarps], s_l[kAttnWarps];
     __shared__ float s_acc[kAttnWarps][DH];
     const int t = blockIdx.y, h = blockIdx.x;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int sub = lane % LPK, grp = lane / LPK;
     const int utt = p.utt[t];
     const int nk = p.causal ? p.pos[t] + 1 : p.n_ctx[utt];
     const float scale = 1.0f / sqrtf((float)DH);
     const int ld = p.H * DH;
-    if (tid < DH) sq[tid] = p.q[(size_t)t * p.ldq + h * DH + tid];
-    __syncthreads();
-    const T * Kb = (const T *)p.K + (size_t)utt * p.rows_per_utt * ld + h * DH;
-    const T * Vb = (const T *)p.V + (size_t)utt * p.rows_per_utt * ld + h * DH;
-
-    float mx = -INFINITY, l = 0.0f, acc[EPL];
+    float qv[VEC];
+    {
+        const float * qp = p.q + (size_t)t * p.ldq + h * DH + sub * VEC;
 #pragma unroll
-    for (int e = 0; e < EPL; e++) acc[e] = 0.0f;
+        for (int v = 0; v < VEC; v++) qv[v] = qp[v] * scale;
+    }
+    const T * Kb = (const T *)p.K + (size_t)utt * p.rows_per_utt * ld + h * DH + sub * VEC;
+    const T * Vb = (const T *)p.V + (size_t)utt * p.rows_per_utt * ld + h * DH + sub * VEC;
 
-    for (int c0 = warp * 32; c0 < nk; c0 += kAttnWarps * 32) {
-        const int j = c0 + lane;
-        float s = -INFINITY;
-        if (j < nk) {
-            const T * kr = Kb + (size_t)j * ld;
+    float mx = -INFINITY, l = 0.0f, acc[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; v++) acc[v] = 0.0f;
+
+    for (int base = warp * (KPI * U); base < nk; base += kAttnWarps * KPI * U) {
+        float kk[U][VEC], vv[U][VEC], sc[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int j = base + u * KPI + grp;
+            if (j < nk) {
+                WT<T>::load(Kb + (size_t)j * ld, kk[u]);
+                WT<T>::load(Vb + (size_t)j * ld, vv[u]);
+            } else {
+#pragma unroll
+                for (int v = 0; v < VEC; v++) { kk[u][v] = 0.0f; vv[u][v] = 0.0f; }
+            }
+        }
+        float mnew = mx;
+#pragma unroll
+        for (int u = 0; u < U; u++) {
             float d = 0.0f;
 #pragma unroll
-            for (int c = 0; c < DH; c += VEC) {
-                float kv[VEC];
-                uint4 u = *reinterpret_cast<const uint4 *>(kr + c);
-                if constexpr (VEC == 8) {
-                    kv[0] = bf16lo(u.x); kv[1] = bf16hi(u.x); kv[2] = bf16lo(u.y); kv[3] = bf16hi(u.y);
-                    kv[4] = bf16lo(u.z); kv[5] = bf16hi(u.z); kv[6] = bf16lo(u.w); kv[7] = bf16hi(u.w);
-                } else {
-                    kv[0] = __uint_as_float(u.x); kv[1] = __uint_as_float(u.y);
-                    kv[2] = __uint_as_float(u.z); kv[3] = __uint_as_float(u.w);
-                }
+            for (int v = 0; v < VEC; v++) d = fmaf(kk[u][v], qv[v], d);
 #pragma unroll
-                for (int v = 0; v < VEC; v++) d = fmaf(kv[v], sq[c + v], d);
+            for (int o = LPK / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+            sc[u] = (base + u * KPI + grp < nk) ? d : -INFINITY;
+            mnew = fmaxf(mnew, sc[u]);
+        }
+        if (mnew != -INFINITY) {
+            const float corr = expf(mx - mnew);            // mx = -inf -> 0
+            float ps = 0.0f;
+#pragma unroll
+            for (int v = 0; v < VEC; v++) acc[v] *= corr;
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const float pj = expf(sc[u] - mnew);       // -inf -> 0
+                ps += pj;
+#pragma unroll
+                for (int v = 0; v < VEC; v++) acc[v] = fmaf(pj, vv[u][v], acc[v]);
             }
-            s = d * scale;
+            l = l * corr + ps;
+            mx = mnew;
         }
-        const float cm = warp_max(s);
-        const float mnew = fmaxf(mx, cm);
-        const float corr = expf(mx - mnew);            // mx = -inf -> 0
-        const float pj = (j < nk) ? expf(s - mnew) : 0.0f;
-        l = l * corr + warp_sum(pj);
+    }
+    // merge the key groups of the warp
 #pragma unroll
-        for (int e = 0; e < EPL; e++) acc[e] *= corr;
-        const int cnt = min(32, nk - c0);
-        for (int jj = 0; jj < cnt; jj++) {
-            const float pb = __shfl_sync(0xffffffffu, pj, jj);
-            const T * vr = Vb + (size_t)(c0 + jj) * ld + lane * EPL;
+    for (int o = LPK; o < 32; o <<= 1) {
+        const float om = __shfl_xor_sync(0xffffffffu, mx, o), ol = __shfl_xor_sync(0xffffffffu, l, o);
+        const float mn = fmaxf(mx, om);
+        const float fa = mx == -INFINITY ? 0.0f : expf(mx - mn), fb = om == -INFINITY ? 0.0f : expf(om - mn);
+        l = l * fa + ol * fb;
 #pragma unroll
-            for (int e = 0; e < EPL; e++) acc[e] = fmaf(pb, WT<T>::get(vr + e), acc[e]);
+        for (int v = 0; v < VEC; v++) {
+            const float oa = __shfl_xor_sync(0xffffffffu, acc[v], o);
+            acc[v] = acc[v] * fa + oa * fb;
         }
-        mx = mnew;
+        mx = mn;
     }
     if (lane == 0) { s_m[warp] = mx; s_l[warp] = l; }
+    if (grp == 0) {
 #pragma unroll
-    for (int e = 0; e < EPL; e++) s_acc[warp][lane * EPL + e] = acc[e];
+        for (int v = 0; v < VEC; v++) s_acc[warp][sub * VEC + v] = acc[v];
+    }
     __syncthreads();
     if (tid < DH) {
         float M = s_m[0];
@@ -244,7 +270,7 @@ __global__ void __launch_bounds__(kAttnWarps * 32) attention_kernel(const AttnPa
         float L = 0.0f, o = 0.0f;
 #pragma unroll
         for (int w = 0; w < kAttnWarps; w++) {
-            const float f = expf(s_m[w] - M);
+            const float f = s_m[w] == -INFINITY ? 0.0f : expf(s_m[w] - M);
             L += f * s_l[w];
             o += f * s_acc[w][tid];
         }
