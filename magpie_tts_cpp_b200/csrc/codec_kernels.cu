@@ -394,7 +394,8 @@ bool codec_decode_device(Codec & c, const int32_t * d_codes, int B, int T, float
     // The residual-block convs (99.9 % of the MACs) run on the tensor cores (codec_conv_tc.cu); the 32->864 pre-conv,
     // the grouped transposed convs and the 27->1 post conv are CUDA-core kernels.  MGB_CODEC_NO_TC=1 selects the
     // all-CUDA-core pipeline below (kept as an independent implementation for the parity tests).
-    bool use_tc = getenv("MGB_CODEC_NO_TC") == nullptr;
+    if (c.tc_mode < 0) c.tc_mode = getenv("MGB_CODEC_NO_TC") == nullptr ? 1 : 0;      // fixed at the first decode of this codec
+    bool use_tc = c.tc_mode == 1;
     {
         int C = c.base_ch, Tc = T;
         for (int i = 0; i < 5 && use_tc; i++) {

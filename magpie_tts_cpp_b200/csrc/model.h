@@ -85,6 +85,7 @@ struct Codec {
     void * pre_w16 = nullptr;
     void * img[4] = {}; size_t img_bytes = 0;   // tcgen05 path: time-major f16 activation images (codec_tc.h)
     bool tc_packed = false;
+    int tc_mode = -1;            // 1 tensor-core pipeline, 0 CUDA-core pipeline (MGB_CODEC_NO_TC=1), -1 undecided
     int32_t * d_codes = nullptr; size_t codes_cap = 0;
     float * d_pcm = nullptr; size_t pcm_cap = 0;
     void * stream = nullptr;     // cudaStream_t
