@@ -32,7 +32,6 @@ namespace {
 constexpr int kEpiWarps = 16;
 constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kMaxC = 448;
-constexpr int kABytes = (kTile + kHP) * 128;      // one staged activation window (23 KB)
 constexpr int kMaxNA = 4, kMaxNW = 8;
 constexpr int kDynSmemMax = 218 * 1024;                 // + 7 KB static epilogue table
 constexpr int kSmemBudget = 214 * 1024;
@@ -44,7 +43,9 @@ struct KParams {
     int tps, ngroups;       // taps per weight stage, stages per chunk
     int NA, NW;             // ring depths
     int wstage_bytes;       // bytes of a full weight stage
-    int tiles_per_b, n_tiles;
+    int R;                  // 128-step accumulator tiles per work item (R * npad * 2 TMEM columns)
+    int abuf_bytes;         // bytes of one staged activation window: (R * 128 + kHP) rows
+    int tiles_per_b, n_tiles;   // work items per utterance / in total
     int tmem_cols;
     long long rows;         // rows per (utterance, chunk) of the activation images
 };
@@ -118,7 +119,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const KParams p) {
     __shared__ int s_kind[kMaxC / 8];
     unsigned char * base = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     unsigned char * abuf = base;
-    unsigned char * wbuf = base + p.NA * kABytes;
+    unsigned char * wbuf = base + p.NA * p.abuf_bytes;
     uint64_t * bars = reinterpret_cast<uint64_t *>(wbuf + (size_t)p.NW * p.wstage_bytes);
     uint64_t * a_full = bars, * a_empty = bars + kMaxNA, * w_full = bars + 2 * kMaxNA, * w_empty = w_full + kMaxNW;
     uint64_t * acc_full = w_empty + kMaxNW, * acc_empty = acc_full + 2;
@@ -159,19 +160,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const KParams p) {
     // Producer and MMA roles run their loops warp-uniformly (all lanes poll the barriers; one elected lane issues), so
     // that addresses and descriptors live in uniform registers and the per-MMA issue cost stays a few instructions.
     if (warp == 0) {
-        const uint32_t abytes = (uint32_t)(kTile + p.hp) * 128;
+        const uint32_t abytes = (uint32_t)(p.R * kTile + p.hp) * 128;
         const bool leader = elect_one();
         uint32_t ia = 0, iw = 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
             const int tb = tile % p.tiles_per_b, hb = tile / p.tiles_per_b;
             const int h = hb % p.nsplit, b = hb / p.nsplit;
-            const long long row0 = (long long)kHP + (long long)tb * kTile - p.hp;
+            const long long row0 = (long long)kHP + (long long)tb * (p.R * kTile) - p.hp;
             for (int c = 0; c < p.nchunk; c++) {
                 const int sa = ia % p.NA;
                 tc::mbar_wait(&a_empty[sa], ((ia / p.NA) & 1) ^ 1);
                 if (leader) {
                     tc::mbar_expect_tx(&a_full[sa], abytes);
-                    tc::bulk_g2s(abuf + sa * kABytes,
+                    tc::bulk_g2s(abuf + (size_t)sa * p.abuf_bytes,
                                  reinterpret_cast<const unsigned char *>(p.a.xa) + (((long long)b * p.nchunk + c) * p.rows + row0) * 128,
                                  abytes, &a_full[sa]);
                 }
@@ -199,13 +200,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const KParams p) {
             const int buf = it & 1;
             tc::mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t dcol = tmem_base + (uint32_t)(buf * p.npad);
+            const uint32_t dcol = tmem_base + (uint32_t)(buf * p.R * p.npad);
+            // accumulator tiles of this item that hold valid time steps (the last item of an utterance may be partial)
+            const int tb = tile % p.tiles_per_b;
+            const int rt = min(p.R, (T - tb * (p.R * kTile) + kTile - 1) / kTile);
             uint32_t accum = 0;
             for (int c = 0; c < p.nchunk; c++) {
                 const int sa = ia % p.NA;
                 tc::mbar_wait(&a_full[sa], (ia / p.NA) & 1);
                 // tap 0 reads rows hp - (K-1)*dil ..., every further tap dil rows later
-                const uint32_t a_lo0 = desc_lo(tc::smem_u32(abuf + sa * kABytes) + (uint32_t)(p.hp - (K - 1) * p.a.dil) * 128);
+                const uint32_t a_lo0 = desc_lo(tc::smem_u32(abuf + (size_t)sa * p.abuf_bytes) + (uint32_t)(p.hp - (K - 1) * p.a.dil) * 128);
                 const int nk16 = min(4, (p.C - c * 64 + 15) >> 4);
                 for (int g = 0; g < p.ngroups; g++) {
                     const int sw = iw % p.NW;
@@ -216,11 +220,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const KParams p) {
                     uint32_t w_lo = desc_lo(tc::smem_u32(wbuf + (size_t)sw * p.wstage_bytes));
                     if (leader) {
                         for (int q = 0; q < nt; q++) {
-                            umma_lo(dcol, a_lo, w_lo, idesc, accum);
+                            for (int r = 0; r < rt; r++) {
+                                const uint32_t ar = a_lo + (uint32_t)r * (kTile * 8), dr = dcol + (uint32_t)(r * p.npad);
+                                umma_lo(dr, ar, w_lo, idesc, accum);
+                                if (nk16 > 1) umma_lo(dr, ar + 2, w_lo + 2, idesc, 1u);
+                                if (nk16 > 2) umma_lo(dr, ar + 4, w_lo + 4, idesc, 1u);
+                                if (nk16 > 3) umma_lo(dr, ar + 6, w_lo + 6, idesc, 1u);
+                            }
                             accum = 1;
-                            if (nk16 > 1) umma_lo(dcol, a_lo + 2, w_lo + 2, idesc, 1u);
-                            if (nk16 > 2) umma_lo(dcol, a_lo + 4, w_lo + 4, idesc, 1u);
-                            if (nk16 > 3) umma_lo(dcol, a_lo + 6, w_lo + 6, idesc, 1u);
                             a_lo += dil_d; w_lo += tile_d;
                         }
                         tc::umma_commit(&w_empty[sw]);
@@ -239,53 +246,65 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const KParams p) {
         const int q = warp & 3;                        // TMEM lane quarter this warp may access
         const int part = (warp - 2) >> 2;              // which share of the columns (kEpiWarps / 4 shares)
         const int n16 = p.npad >> 4;
-        const int u_lo = n16 * part / (kEpiWarps / 4), u_hi = n16 * (part + 1) / (kEpiWarps / 4);
+        const int n_units = p.R * n16;                 // (accumulator tile r, 16-column unit u) pairs: w = r * n16 + u
+        const int w_lo = n_units * part / (kEpiWarps / 4), w_hi = n_units * (part + 1) / (kEpiWarps / 4);
         const long long hrow_bytes = p.rows * 128;
-        struct TileInfo { bool tv; int r_img, cbase, b; size_t row_off; };
+        const size_t tile_stride = (size_t)kTile * p.cs;          // f32 elements between accumulator tiles of an item
+        struct TileInfo { int t0, r_img0, cbase, b, rt; size_t row_off; };     // r = 0 row of this thread
         auto decode = [&](int tile) {
             TileInfo ti;
             const int tb = tile % p.tiles_per_b, hb = tile / p.tiles_per_b;
             const int h = hb % p.nsplit;
             ti.b = hb / p.nsplit;
-            const int t = tb * kTile + q * 32 + lane;
-            ti.tv = tile < p.n_tiles && t < T;
-            ti.r_img = kHP + t;
+            ti.t0 = tb * (p.R * kTile) + q * 32 + lane;
+            ti.rt = tile < p.n_tiles ? min(p.R, (T - tb * (p.R * kTile) + kTile - 1) / kTile) : 0;
+            ti.r_img0 = kHP + ti.t0;
             ti.cbase = h * p.nper;
-            ti.row_off = ((size_t)ti.b * T + (ti.tv ? t : 0)) * p.cs + ti.cbase;
+            ti.row_off = ((size_t)ti.b * T + ti.t0) * p.cs + ti.cbase;
             return ti;
         };
         uint32_t it = 0;
         TileInfo cur = decode(blockIdx.x);
         float rn[16];
+        int pf_tile = -1, pf_w = -1;                  // which (item, unit) the prefetched residual in rn belongs to
 #pragma unroll
         for (int e = 0; e < 16; e++) rn[e] = 0.0f;
-        if (MODE != 0 && u_lo < u_hi && cur.tv) { ldg256(p.a.res + cur.row_off + u_lo * 16, rn); ldg256(p.a.res + cur.row_off + u_lo * 16 + 8, rn + 8); }
+        auto res_fetch = [&](const TileInfo & ti, int tile, int w) {
+            const int r = w / n16, u = w - r * n16;
+            pf_tile = tile; pf_w = w;
+            if (ti.t0 + r * kTile < T) {
+                const float * src = p.a.res + ti.row_off + r * tile_stride + u * 16;
+                ldg256(src, rn); ldg256(src + 8, rn + 8);
+            }
+        };
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, it++) {
             const int buf = it & 1;
             const TileInfo nxt = decode(tile + gridDim.x);
+            const int w_end = min(w_hi, cur.rt * n16);            // units of valid accumulator tiles only
+            if (MODE != 0 && w_lo < w_end && !(pf_tile == tile && pf_w == w_lo)) res_fetch(cur, tile, w_lo);
             tc::mbar_wait(&acc_full[buf], (it >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.npad);
-            unsigned char * ya_row = reinterpret_cast<unsigned char *>(p.a.ya) + (long long)cur.b * p.nchunk * hrow_bytes + (long long)cur.r_img * 128;
-            for (int u = u_lo; u < u_hi; u++) {
-                float rr[16];
+            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.R * p.npad);
+            for (int w = w_lo; w < w_end; w++) {
+                const int r = w / n16, u = w - r * n16;
+                const bool tv = cur.t0 + r * kTile < T;
+                const int r_img = cur.r_img0 + r * kTile;
+                const size_t row_off = cur.row_off + r * tile_stride;
+                float rr[16], ss[MODE == 2 ? 16 : 1];
                 if (MODE != 0) {
 #pragma unroll
                     for (int e = 0; e < 16; e++) rr[e] = rn[e];
-                    // prefetch the residual of the next unit
-                    const bool in_tile = u + 1 < u_hi;
-                    const TileInfo & nt = in_tile ? cur : nxt;
-                    const int un = in_tile ? u + 1 : u_lo;
-                    if (nt.tv) { ldg256(p.a.res + nt.row_off + un * 16, rn); ldg256(p.a.res + nt.row_off + un * 16 + 8, rn + 8); }
-                }
-                float ss[MODE == 2 ? 16 : 1];
-                if (MODE == 2) {
+                    if (MODE == 2) {
 #pragma unroll
-                    for (int e = 0; e < 16; e++) ss[e] = 0.0f;
-                    if (p.a.sum_mode >= 2 && cur.tv) { ldg256(p.a.sum_in + cur.row_off + u * 16, ss); ldg256(p.a.sum_in + cur.row_off + u * 16 + 8, ss + 8); }
+                        for (int e = 0; e < 16; e++) ss[e] = 0.0f;
+                        if (p.a.sum_mode >= 2 && tv) { ldg256(p.a.sum_in + row_off + u * 16, ss); ldg256(p.a.sum_in + row_off + u * 16 + 8, ss + 8); }
+                    }
+                    // prefetch the residual of the next unit (of this item, else the first one of the next item)
+                    if (w + 1 < w_end) res_fetch(cur, tile, w + 1);
+                    else if (w_lo < min(w_hi, nxt.rt * n16)) res_fetch(nxt, tile + gridDim.x, w_lo);
                 }
                 uint32_t v[16];
-                tmem_ld16(trow + u * 16, v);
+                tmem_ld16(trow + r * p.npad + u * 16, v);
                 const int co0 = cur.cbase + u * 16;
                 float y[16];
                 {
@@ -326,22 +345,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const KParams p) {
 #pragma unroll
                         for (int e2 = 0; e2 < 4; e2++) pk[hh * 4 + e2] = pack_h2(act[2 * e2], act[2 * e2 + 1]);
                     }
-                    if (cur.tv) {
+                    if (tv) {
                         // the unit's two 16-byte groups share one 32-byte sector of the swizzled row; odd rows swap them
-                        const int sw = cur.r_img & 7;
-                        unsigned char * dst = ya_row + (long long)(co0 >> 6) * hrow_bytes + (((((co0 & 63) >> 3) ^ sw) & 6) << 4);
+                        const int sw = r_img & 7;
+                        unsigned char * dst = reinterpret_cast<unsigned char *>(p.a.ya) + ((long long)cur.b * p.nchunk + (co0 >> 6)) * hrow_bytes +
+                                              (long long)r_img * 128 + (((((co0 & 63) >> 3) ^ sw) & 6) << 4);
                         const bool swap = sw & 1;
                         stg256(dst, swap ? pk[4] : pk[0], swap ? pk[5] : pk[1], swap ? pk[6] : pk[2], swap ? pk[7] : pk[3],
                                     swap ? pk[0] : pk[4], swap ? pk[1] : pk[5], swap ? pk[2] : pk[6], swap ? pk[3] : pk[7]);
                     }
                 }
-                if (MODE != 0 && cur.tv) {
+                if (MODE != 0 && tv) {
                     if (MODE == 2) {
                         const float sc = p.a.sum_mode == 3 ? (1.0f / 3.0f) : 1.0f;
 #pragma unroll
                         for (int e = 0; e < 16; e++) y[e] = (ss[e] + y[e]) * sc;
                     }
-                    float * yp = (MODE == 1 ? p.a.y : p.a.sum_out) + cur.row_off + u * 16;
+                    float * yp = (MODE == 1 ? p.a.y : p.a.sum_out) + row_off + u * 16;
                     stg256f(yp, y); stg256f(yp + 8, y + 8);
                 }
             }
@@ -387,55 +407,79 @@ __device__ __forceinline__ float half_snake_fast(float x, int c, const float * a
     }
     return fmaxf(x, 0.01f * x);
 }
+// thread = one INPUT time step of one 8-output-channel group: the 2 x 16 activated inputs (this step and the previous
+// one, taken from the neighbouring lane) are computed once and reused for all s output steps; the per-channel constants
+// of the CTA's channel group live in shared memory.
 __global__ void __launch_bounds__(128) up_tm_kernel(const UpKParams p) {
-    const int to = blockIdx.x * 128 + threadIdx.x;
-    const int To = p.a.T * p.a.s;
-    if (to >= To) return;
+    __shared__ float s_ia[16], s_iinv[16], s_w[16 * 16], s_b[8], s_ba[3][8], s_binv[3][8];
     const int g0 = blockIdx.y * 8, b = blockIdx.z;
     const int Cout = p.a.Cin / 2, s = p.a.s, K = 2 * s;
-    const int ti = to / s, r = to - ti * s;
-    float v[8];
+    const int tid = threadIdx.x;
+    if (tid < 16) {
+        const int ci = 2 * g0 + tid;
+        const float al = (ci < p.a.n_alpha && ci < p.a.Cin) ? p.a.alpha[ci] : 0.0f;
+        s_ia[tid] = al; s_iinv[tid] = al != 0.0f ? 1.0f / al : 0.0f;
+    }
+    for (int i = tid; i < 16 * K; i += 128) {
+        const int ci = 2 * g0 + i / K;
+        s_w[i] = ci < p.a.Cin ? p.a.w[(size_t)ci * K + i % K] : 0.0f;
+    }
+    if (tid < 8) s_b[tid] = g0 + tid < Cout ? p.a.bias[g0 + tid] : 0.0f;
+    if (tid >= 32 && tid < 56) {
+        const int j = (tid - 32) / 8, e = (tid - 32) % 8, c = g0 + e;
+        const float al = (c < p.a.n_br_alpha && c < Cout) ? p.a.br_alpha[j][c] : 0.0f;
+        s_ba[j][e] = al; s_binv[j][e] = al != 0.0f ? 1.0f / al : 0.0f;
+    }
+    __syncthreads();
+    const int ti = blockIdx.x * 128 + tid;
+    const bool tv = ti < p.a.T;
+    // activated inputs of this step; the previous step's come from lane - 1 (lane 0 computes them itself)
+    float a_cur[16], a_prev[16];
+    auto load_act = [&](int t, float * out) {
+        const bool ok = t >= 0 && t < p.a.T && g0 < Cout;
+        const float * xr = p.a.x + ((size_t)b * p.a.T + (ok ? t : 0)) * p.cs_in + 2 * g0;
 #pragma unroll
-    for (int e = 0; e < 8; e++) v[e] = 0.0f;
-    if (g0 < Cout) {
-#pragma unroll
-        for (int back = 0; back < 2; back++) {
-            if (back == 1 && ti == 0) break;
-            const float * xr = p.a.x + ((size_t)b * p.a.T + (ti - back)) * p.cs_in + 2 * g0;
-            float xin[16];
-#pragma unroll
-            for (int q4 = 0; q4 < 4; q4++) {
-                float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (2 * g0 + 4 * q4 < p.cs_in) f = *reinterpret_cast<const float4 *>(xr + 4 * q4);
-                xin[4 * q4] = f.x; xin[4 * q4 + 1] = f.y; xin[4 * q4 + 2] = f.z; xin[4 * q4 + 3] = f.w;
-            }
-#pragma unroll
-            for (int e = 0; e < 8; e++) {
-                const int g = g0 + e;
-                if (g < Cout) {
-                    const float a0 = half_snake_fast(xin[2 * e], 2 * g, p.a.alpha, p.a.n_alpha);
-                    const float a1 = half_snake_fast(xin[2 * e + 1], 2 * g + 1, p.a.alpha, p.a.n_alpha);
-                    const float * w0 = p.a.w + (size_t)(2 * g) * K + r + back * s;
-                    v[e] += __ldg(w0) * a0 + __ldg(w0 + K) * a1;
-                }
-            }
+        for (int q4 = 0; q4 < 4; q4++) {
+            float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok && 2 * g0 + 4 * q4 < p.cs_in) f = *reinterpret_cast<const float4 *>(xr + 4 * q4);
+            out[4 * q4] = f.x; out[4 * q4 + 1] = f.y; out[4 * q4 + 2] = f.z; out[4 * q4 + 3] = f.w;
         }
 #pragma unroll
-        for (int e = 0; e < 8; e++) if (g0 + e < Cout) v[e] += __ldg(p.a.bias + g0 + e);
-    }
-    float4 * up = reinterpret_cast<float4 *>(p.a.up + ((size_t)b * To + to) * p.cs_out + g0);
-    up[0] = make_float4(v[0], v[1], v[2], v[3]);
-    up[1] = make_float4(v[4], v[5], v[6], v[7]);
-    const int r_img = kHP + to;
-    const long long off = ((long long)b * p.nchunk + (g0 >> 6)) * p.rows * 128 + (long long)r_img * 128 + ((((g0 & 63) >> 3) ^ (r_img & 7)) << 4);
-    for (int j = 0; j < 3; j++) {
-        float act[8];
+        for (int i = 0; i < 16; i++) {
+            const float al = s_ia[i];                      // warp-uniform
+            out[i] = al != 0.0f ? snake_fast(out[i], al, s_iinv[i]) : fmaxf(out[i], 0.01f * out[i]);
+        }
+    };
+    load_act(ti, a_cur);
 #pragma unroll
-        for (int e = 0; e < 8; e++) act[e] = (g0 + e) < Cout ? half_snake_fast(v[e], g0 + e, p.a.br_alpha[j], p.a.n_br_alpha) : 0.0f;
-        uint4 pk;
-        pk.x = pack_h2(act[0], act[1]); pk.y = pack_h2(act[2], act[3]);
-        pk.z = pack_h2(act[4], act[5]); pk.w = pack_h2(act[6], act[7]);
-        *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(p.a.img[j]) + off) = pk;
+    for (int i = 0; i < 16; i++) a_prev[i] = __shfl_up_sync(0xffffffffu, a_cur[i], 1);
+    if ((tid & 31) == 0) load_act(ti - 1, a_prev);        // zero history for ti == 0 (ok == false -> act(0) = 0)
+    if (!tv) return;
+    const int To = p.a.T * s;
+    for (int r = 0; r < s; r++) {
+        const int to = ti * s + r;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            const float * w0 = s_w + (2 * e) * K + r, * w1 = w0 + K;
+            v[e] = s_b[e] + w0[0] * a_cur[2 * e] + w1[0] * a_cur[2 * e + 1] + w0[s] * a_prev[2 * e] + w1[s] * a_prev[2 * e + 1];
+        }
+        stg256f(p.a.up + ((size_t)b * To + to) * p.cs_out + g0, v);
+        const int r_img = kHP + to;
+        const long long off = ((long long)b * p.nchunk + (g0 >> 6)) * p.rows * 128 + (long long)r_img * 128 + ((((g0 & 63) >> 3) ^ (r_img & 7)) << 4);
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            float act[8];
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                const float al = s_ba[j][e];               // warp-uniform
+                act[e] = al != 0.0f ? snake_fast(v[e], al, s_binv[j][e]) : fmaxf(v[e], 0.01f * v[e]);
+            }
+            uint4 pk;
+            pk.x = pack_h2(act[0], act[1]); pk.y = pack_h2(act[2], act[3]);
+            pk.z = pack_h2(act[4], act[5]); pk.w = pack_h2(act[6], act[7]);
+            *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(p.a.img[j]) + off) = pk;
+        }
     }
 }
 
@@ -507,14 +551,20 @@ bool launch_conv(const Geom & g, const ConvArgs & a, cudaStream_t stream) {
     p.tps = std::max(1, std::min(a.K, (32 * 1024) / tile_bytes));
     p.ngroups = (a.K + p.tps - 1) / p.tps;
     p.wstage_bytes = p.tps * tile_bytes;
-    p.NA = 3;
-    p.NW = std::max(2, std::min(kMaxNW, (kSmemBudget - p.NA * kABytes) / p.wstage_bytes));
-    p.tiles_per_b = (a.T + kTile - 1) / kTile;
+    // accumulator tiles per work item: as many as TMEM (2 buffers x R x npad <= 512 columns) and shared memory allow;
+    // small channel counts amortise the per-item pipeline hand-offs and the weight stream over up to 512 time steps
+    p.R = std::max(1, std::min(4, 256 / g.npad));
+    if (p.R == 3) p.R = 2;
+    p.abuf_bytes = (p.R * kTile + kHP) * 128;
+    p.NA = p.R >= 4 ? 2 : 3;
+    p.NW = std::max(2, std::min(kMaxNW, (kSmemBudget - p.NA * p.abuf_bytes) / p.wstage_bytes));
+    p.tiles_per_b = (a.T + p.R * kTile - 1) / (p.R * kTile);
     p.n_tiles = g.nsplit * a.B * p.tiles_per_b;
     p.tmem_cols = 32;
-    while (p.tmem_cols < 2 * g.npad) p.tmem_cols *= 2;
+    while (p.tmem_cols < 2 * p.R * g.npad) p.tmem_cols *= 2;
     p.rows = (long long)act_rows(a.T);
-    const size_t smem = 1024 + (size_t)p.NA * kABytes + (size_t)p.NW * p.wstage_bytes + 512;
+    const size_t smem = 1024 + (size_t)p.NA * p.abuf_bytes + (size_t)p.NW * p.wstage_bytes + 512;
+    if (smem > (size_t)kDynSmemMax) { set_error("codec: conv tile configuration exceeds shared memory"); return false; }
     if (!(attr_done >> dev & 1)) {
         MGB_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmemMax));
         MGB_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmemMax));
@@ -537,7 +587,8 @@ bool launch_conv(const Geom & g, const ConvArgs & a, cudaStream_t stream) {
 bool launch_up(const Geom & g, const UpArgs & a, cudaStream_t stream) {
     UpKParams p = {};
     p.a = a; p.cs_in = row_stride(a.Cin); p.cs_out = row_stride(a.Cin / 2); p.nchunk = g.nchunk; p.rows = (long long)act_rows(a.T * a.s);
-    dim3 grid((a.T * a.s + 127) / 128, p.cs_out / 8, a.B);
+    if (a.s > 8) { set_error("codec: up-sampling stride > 8"); return false; }
+    dim3 grid((a.T + 127) / 128, p.cs_out / 8, a.B);
     up_tm_kernel<<<grid, 128, 0, stream>>>(p);
     MGB_LAUNCH_CHECK();
     return true;

@@ -23,7 +23,7 @@ Geom geom_for(int C);
 // by (r & 7) (SWIZZLE_128B), so that any 8-row-aligned window is a ready-made shared-memory operand image.
 // f32 tensors of the tensor-core pipeline are TIME-MAJOR rows [B][T][row_stride(C)] (padding channels stay zero)
 inline int row_stride(int C) { return (C + 15) / 16 * 16; }
-inline size_t act_rows(int T) { return (size_t)kHP + (size_t)(T + kTile - 1) / kTile * kTile; }
+inline size_t act_rows(int T) { return (size_t)kHP + (size_t)(T + 4 * kTile - 1) / (4 * kTile) * (4 * kTile); }   // a work item spans up to 4 tiles
 inline size_t act_bytes(int B, int C, int T) { return (size_t)B * ((C + 63) / 64) * act_rows(T) * 128; }
 
 size_t weight_image_bytes(const Geom & g, int K);
