@@ -32,6 +32,7 @@ __global__ void pack_w_kernel(const bf * W, int N, int K, bf * Wt) {
 __global__ void __launch_bounds__(256) pack_x_kernel(const float * X, int ldx, int M, int K, const float * ln_w, float eps, int MT,
                                                      bf * hi, bf * lo) {
     __shared__ float red[32];
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");     // let the GEMM's CTAs start prefetching weights
     const int m = blockIdx.x, tid = threadIdx.x;
     const int KT = K / 64;
     const bool valid = m < M;
@@ -87,7 +88,7 @@ template <int MT>
 __global__ void __launch_bounds__(tc::kThreads, 1) tc_linear_kernel(const bf * Wt, const bf * Xhi, const bf * Xlo, int KT, const TcEpi e) {
     extern __shared__ unsigned char tc_smem[];
     const int nt = blockIdx.x, mt = blockIdx.y;
-    const uint32_t tmem = tc::mainloop<MT>(tc_smem, Wt, Xhi, Xlo, KT, nt, mt);
+    const uint32_t tmem = tc::mainloop<MT, 2, false, true>(tc_smem, Wt, Xhi, Xlo, KT, nt, mt);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp >= 2) {
         const int q = warp & 3;                      // TMEM lane quarter this warp may access
@@ -138,8 +139,16 @@ template <int MT> bool launch_tc(const bf * Wt, const bf * hi, const bf * lo, in
         MGB_CUDA_TRY(cudaFuncSetAttribute(tc_linear_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Smem<MT>::kBytes));
         attr_done |= 1ull << dev;
     }
-    dim3 grid((e.N + tc::BM - 1) / tc::BM, (e.M + MT - 1) / MT);
-    tc_linear_kernel<MT><<<grid, tc::kThreads, tc::Smem<MT>::kBytes, stream>>>(Wt, hi, lo, KT, e);
+    // launched as a programmatic dependent of the activation-packing kernel: CTAs start (and prefetch weight tiles)
+    // while pack_x_kernel is still running, and wait for it with griddepcontrol.wait before touching its output
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((e.N + tc::BM - 1) / tc::BM, (e.M + MT - 1) / MT); cfg.blockDim = dim3(tc::kThreads);
+    cfg.dynamicSmemBytes = tc::Smem<MT>::kBytes; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    MGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc_linear_kernel<MT>, Wt, hi, lo, KT, e));
     MGB_LAUNCH_CHECK();
     return true;
 }

@@ -89,7 +89,7 @@ template <int MT, int NB = 2> struct Smem {
 // Wt: [NT][KT] tiles of 16 KB; Xhi/Xlo: [MTiles][KT] tiles of MT*128 bytes.  Must be called by all 192 threads.
 // After the call, epilogue warps (warp >= 2) own TMEM lanes 32*(warp%4) .. +31; call tc::finish() when done.
 // NB = 2: activations as hi + lo tiles (bf16, two MMAs per k slice); NB = 1: one tile (Xlo unused).  F16: operands are f16.
-template <int MT, int NB = 2, bool F16 = false>
+template <int MT, int NB = 2, bool F16 = false, bool PDL = false>
 __device__ __forceinline__ uint32_t mainloop(unsigned char * smem_raw, const void * Wt, const void * Xhi,
                                              const void * Xlo, int KT, int nt, int mt) {
     constexpr int S = Smem<MT, NB>::kStages, SB = Smem<MT, NB>::kStageBytes;
@@ -116,12 +116,22 @@ __device__ __forceinline__ uint32_t mainloop(unsigned char * smem_raw, const voi
         const unsigned char * wsrc = reinterpret_cast<const unsigned char *>(Wt) + (size_t)nt * KT * (BM * 128);
         const unsigned char * hsrc = reinterpret_cast<const unsigned char *>(Xhi) + (size_t)mt * KT * (MT * 128);
         const unsigned char * lsrc = reinterpret_cast<const unsigned char *>(Xlo) + (size_t)mt * KT * (MT * 128);
+        // Programmatic dependent launch: the weight tiles do not depend on the preceding kernel (which packs the
+        // activations), so the first ring-full of them is requested BEFORE waiting for that kernel to complete.
+        const int npre = PDL ? (KT < S ? KT : S) : 0;
+        for (int kt = 0; kt < npre; kt++) {
+            mbar_expect_tx(&full[kt], SB);
+            bulk_g2s(tiles + kt * SB, wsrc + (size_t)kt * (BM * 128), BM * 128, &full[kt]);
+        }
+        if (PDL) asm volatile("griddepcontrol.wait;" ::: "memory");
         for (int kt = 0; kt < KT; kt++) {
             const int s = kt % S;
-            mbar_wait(&empty[s], ((kt / S) & 1) ^ 1);
-            mbar_expect_tx(&full[s], SB);
             unsigned char * st = tiles + s * SB;
-            bulk_g2s(st, wsrc + (size_t)kt * (BM * 128), BM * 128, &full[s]);
+            if (kt >= npre) {
+                mbar_wait(&empty[s], ((kt / S) & 1) ^ 1);
+                mbar_expect_tx(&full[s], SB);
+                bulk_g2s(st, wsrc + (size_t)kt * (BM * 128), BM * 128, &full[s]);
+            }
             bulk_g2s(st + BM * 128, hsrc + (size_t)kt * (MT * 128), MT * 128, &full[s]);
             if (NB == 2) bulk_g2s(st + BM * 128 + MT * 128, lsrc + (size_t)kt * (MT * 128), MT * 128, &full[s]);
         }
@@ -142,6 +152,7 @@ __device__ __forceinline__ uint32_t mainloop(unsigned char * smem_raw, const voi
         umma_commit(acc_full);                       // accumulator complete
     }
     if (warp >= 2) {
+        if (PDL) asm volatile("griddepcontrol.wait;" ::: "memory");
         mbar_wait(acc_full, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
