@@ -61,6 +61,7 @@ struct Session {
     int32_t * d_result = nullptr; float * d_xm = nullptr, * d_xn = nullptr; int loop_E = 0; bool loop_tables = false;
     unsigned long long * d_loop_dbg = nullptr;
     void * tc_scratch = nullptr; size_t tc_scratch_bytes = 0;     // tensor-core path: activation tile images
+    void * lt_scratch = nullptr; size_t lt_scratch_bytes = 0;     // batched local transformer: activation scratch
 
     ~Session() {
         if (m) cudaSetDevice(m->device);
@@ -284,6 +285,12 @@ mgb_session * mgb_session_new(mgb_model * mm, int batch, int max_text, int max_s
         char * tp = nullptr;
         if (!s->alloc(tp, tb)) return nullptr;
         s->tc_scratch = tp; s->tc_scratch_bytes = tb;
+    }
+    if (m->precision == MGB_PREC_BF16 && batch >= 16) {
+        const size_t lb = lt_batch_scratch_bytes(*m, batch);
+        char * lp = nullptr;
+        if (!s->alloc(lp, lb)) return nullptr;
+        s->lt_scratch = lp; s->lt_scratch_bytes = lb;
     }
     // batch 1: persistent cooperative megakernel (MGB_NO_MEGA=1 keeps the per-op kernels, e.g. for A/B tests)
     if (batch == 1 && getenv("MGB_NO_MEGA") == nullptr && hp.dec_layers <= kMegaMaxLayers && hp.d_model <= 1024 &&
@@ -530,6 +537,7 @@ int mgb_lt_sample(mgb_session * ss, const float * hidden, float temperature, int
     if (uniforms) { ok = ok && cudaMemcpyAsync(s->d_uniforms, uniforms, (size_t)B * 8 * 4, cudaMemcpyHostToDevice, st) == cudaSuccess; a.uniforms = s->d_uniforms; }
     if (!ok) { set_error("mgb_lt_sample: H2D failed"); return MGB_ECUDA; }
     a.sampled = s->d_sampled; a.argmax = s->d_argmax; a.next_codes = s->d_codes; a.logits = logits_out ? s->d_logits1 : nullptr;
+    a.lt_scratch = s->lt_scratch; a.lt_scratch_bytes = s->lt_scratch_bytes;
     if (!launch_local_transformer(m, a, st)) return MGB_ECUDA;
     if (sampled) ok = ok && cudaMemcpyAsync(sampled, s->d_sampled, (size_t)B * 8 * 4, cudaMemcpyDeviceToHost, st) == cudaSuccess;
     if (argmax) ok = ok && cudaMemcpyAsync(argmax, s->d_argmax, (size_t)B * 8 * 4, cudaMemcpyDeviceToHost, st) == cudaSuccess;
@@ -562,6 +570,7 @@ static bool enqueue_iteration(Session & s, const LoopCfg & c) {
     a.logits = c.want_logits ? s.l_logits : nullptr;
     a.d_step = s.d_step; a.T_total = c.T; a.min_frames = c.teacher ? 0 : 4;      // magpie.cpp:4267, 4325
     a.done_step = s.d_done; a.hidden_hist = c.want_hidden ? s.l_hidden : nullptr;
+    a.lt_scratch = s.lt_scratch; a.lt_scratch_bytes = s.lt_scratch_bytes;
     if (!launch_local_transformer(*s.m, a, s.stream)) return false;
     return launch_advance(s, true);
 }

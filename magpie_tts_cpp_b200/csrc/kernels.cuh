@@ -93,7 +93,9 @@ struct LtArgs {
     int T_total = 0, min_frames = 0;
     int32_t * done_step = nullptr;
     float * hidden_hist = nullptr;
+    void * lt_scratch = nullptr; size_t lt_scratch_bytes = 0;     // activation scratch of the batched kernel (lt_batch.cu)
 };
+size_t lt_batch_scratch_bytes(const Model & m, int B);
 bool launch_local_transformer(const Model & m, const LtArgs & a, cudaStream_t stream);
 
 // ---- nano-codec ---------------------------------------------------------------------------------

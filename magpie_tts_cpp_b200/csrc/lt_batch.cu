@@ -1,0 +1,325 @@
+// Local transformer + sampler for MANY utterances at once: one persistent cooperative kernel, weight-stationary.
+//
+// Same arithmetic as lt_kernel.cu (reference src/magpie.cpp:946-1048 LT layer, 1072-1109 sample_top_k, 1113-1317
+// magpie_local_transformer_sample_all), different parallelisation.  lt_kernel runs one cluster per utterance and
+// re-streams the 10 MB of LT weights from L2 for every utterance (64 utterances: 0.66 GB per step, 764 us).  Here every
+// CTA keeps a fixed slice of the rows of EVERY LT matrix in shared memory for the whole launch (10.3 MB bf16 / 148 CTAs
+// = 70 KB), and each phase computes those rows for ALL utterances from an activation tile staged through shared memory:
+// each weight element is read from HBM/L2 once per step, the 8 x 7 dependent phases are separated by grid barriers.
+//
+//   per codebook:  QKV (LN prologue) | attention (utterance-owner CTAs) | O + residual | FF1 (LN prologue, GELU) |
+//                  FF2 + residual | out-projection + bias | mask / argmax / top-k sample / feedback gather (owner CTAs)
+#include <cooperative_groups.h>
+#include <cstdlib>
+
+#include "lt_common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace mgb {
+
+namespace {
+
+using namespace lt;
+using bf = __nv_bfloat16;
+
+constexpr int kTileFloats = 64 * 260;          // activation tile staged per pass (65 KB): 64 utterances x 256 columns, padded rows
+
+struct BParams {
+    LtParams p;
+    float * seq, * q, * kc, * vc, * att, * x1, * ffh, * hout, * logits;     // [B][..] f32 scratch
+};
+
+struct Slice { int n0, n1; };
+__device__ __forceinline__ Slice slice_of(int N, int c, int G) { return {(int)((long long)c * N / G), (int)((long long)(c + 1) * N / G)}; }
+
+// sampler scratch, aliased onto the activation tile
+struct SampSmem {
+    float logits[kV];
+    float sel_v[kV]; int sel_i[kV];
+    float srt_v[kV]; int srt_i[kV];
+    float red[32]; int redi[32];
+    unsigned hist[256];
+    int misc[8];
+};
+static_assert(sizeof(SampSmem) <= kTileFloats * 4, "sampler scratch must fit the activation tile");
+
+// rows [n0, n1) of W (bf16 [N][K], row-major) -> shared memory, 16-byte copies
+__device__ __forceinline__ void load_rows(bf * dst, const void * W, int K, Slice s) {
+    const uint4 * src = reinterpret_cast<const uint4 *>(reinterpret_cast<const bf *>(W) + (size_t)s.n0 * K);
+    const int n16 = (s.n1 - s.n0) * K / 8;
+    for (int i = threadIdx.x; i < n16; i += kLtThreads) reinterpret_cast<uint4 *>(dst)[i] = src[i];
+}
+
+// One GEMV phase: for every utterance u and every row n of this CTA's slice, epi(u, n, sum_k W[n][k] * X[u][k]).
+// 64 utterances x 256 input columns are staged per pass (row stride 260 floats: conflict-free 16-byte reads with one
+// utterance per lane); warp w owns utterance group (w & 1) and the slice rows (w >> 1), (w >> 1) + 8: no shuffles, the
+// weights are shared-memory broadcasts.  `prep(u, row)` may transform a staged row in place (position add / LayerNorm;
+// K == 256 only) and is executed by one warp per row.
+constexpr int kKC = 256, kKS = kKC + 4, kUB = 64;
+static_assert(kUB * kKS <= kTileFloats, "stage tile");
+template <bool PREP, typename Prep, typename Epi>
+__device__ __forceinline__ void gemv_phase(const bf * Ws, Slice s, int K, const float * X, int ldx, int B, float * tile, Prep prep, Epi epi) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ug = warp & 1, rw = warp >> 1;
+    const int R = s.n1 - s.n0;
+    for (int ub = 0; ub < B; ub += kUB) {
+        const int nu = min(kUB, B - ub);
+        float acc[2] = {0.0f, 0.0f};
+        for (int kc = 0; kc < K; kc += kKC) {
+            __syncthreads();
+            for (int i = threadIdx.x; i < nu * (kKC / 4); i += kLtThreads) {
+                const int u = i / (kKC / 4), k = (i % (kKC / 4)) * 4;
+                *reinterpret_cast<float4 *>(tile + u * kKS + k) = *reinterpret_cast<const float4 *>(X + (size_t)(ub + u) * ldx + kc + k);
+            }
+            __syncthreads();
+            if (PREP) {
+                for (int u = warp; u < nu; u += kLtWarps) prep(ub + u, tile + u * kKS);
+                __syncthreads();
+            }
+            if (rw < R && ug * 32 < nu) {
+                const float * xr = tile + (ug * 32 + min(lane, nu - ug * 32 - 1)) * kKS;      // lanes past the batch repeat the last row
+                const bf * w0 = Ws + (size_t)rw * K + kc;
+                const bool two = rw + 8 < R;
+                const bf * w1 = two ? w0 + (size_t)8 * K : w0;
+#pragma unroll 4
+                for (int k = 0; k < kKC; k += 4) {
+                    const float4 x = *reinterpret_cast<const float4 *>(xr + k);
+                    const uint2 a = *reinterpret_cast<const uint2 *>(w0 + k), b = *reinterpret_cast<const uint2 *>(w1 + k);
+                    acc[0] = fmaf(bf16lo(a.x), x.x, acc[0]); acc[0] = fmaf(bf16hi(a.x), x.y, acc[0]);
+                    acc[0] = fmaf(bf16lo(a.y), x.z, acc[0]); acc[0] = fmaf(bf16hi(a.y), x.w, acc[0]);
+                    acc[1] = fmaf(bf16lo(b.x), x.x, acc[1]); acc[1] = fmaf(bf16hi(b.x), x.y, acc[1]);
+                    acc[1] = fmaf(bf16lo(b.y), x.z, acc[1]); acc[1] = fmaf(bf16hi(b.y), x.w, acc[1]);
+                }
+            }
+        }
+        const int u = ub + ug * 32 + lane;
+        if (rw < R && u < B) {
+            epi(u, s.n0 + rw, acc[0]);
+            if (rw + 8 < R) epi(u, s.n0 + rw + 8, acc[1]);
+        }
+    }
+}
+
+// in-place LayerNorm of one staged row by one warp (magpie.cpp:2237-2259: mean, centred variance, * weight)
+__device__ __forceinline__ void warp_layer_norm(float * row, int n, const float * w, float eps) {
+    const int lane = threadIdx.x & 31;
+    float s = 0.0f;
+    for (int i = lane; i < n; i += 32) s += row[i];
+    const float mean = warp_sum(s) / (float)n;
+    float s2 = 0.0f;
+    for (int i = lane; i < n; i += 32) { const float c = row[i] - mean; s2 += c * c; }
+    const float scale = 1.0f / sqrtf(warp_sum(s2) / (float)n + eps);
+    for (int i = lane; i < n; i += 32) row[i] = ((row[i] - mean) * scale) * w[i];
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(kLtThreads, 1) lt_batch_kernel(const BParams bp) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const LtParams & p = bp.p;
+    cg::grid_group grid = cg::this_grid();
+    const int G = gridDim.x, c = blockIdx.x, tid = threadIdx.x;
+    const int B = p.B, d = p.d, L = p.L, F = p.F, V = p.V;
+    float * tile = reinterpret_cast<float *>(smem_raw);
+    SampSmem & S = *reinterpret_cast<SampSmem *>(smem_raw);
+    bf * wbase = reinterpret_cast<bf *>(smem_raw + (size_t)kTileFloats * 4);
+
+    // ---- this CTA's row slices of every matrix, resident for the whole launch ----
+    const Slice s_in = slice_of(L, c, G), s_qkv = slice_of(3 * L, c, G), s_o = slice_of(L, c, G), s_f1 = slice_of(F, c, G),
+                s_f2 = slice_of(L, c, G), s_out = slice_of(V, c, G);
+    bf * w_in = wbase;
+    bf * w_qkv = w_in + (size_t)(s_in.n1 - s_in.n0) * d;
+    bf * w_o = w_qkv + (size_t)(s_qkv.n1 - s_qkv.n0) * L;
+    bf * w_f1 = w_o + (size_t)(s_o.n1 - s_o.n0) * L;
+    bf * w_f2 = w_f1 + (size_t)(s_f1.n1 - s_f1.n0) * L;
+    bf * w_out0 = w_f2 + (size_t)(s_f2.n1 - s_f2.n0) * F;
+    const size_t out_elems = (size_t)(s_out.n1 - s_out.n0) * L;
+    load_rows(w_in, p.in_w, d, s_in);
+    load_rows(w_qkv, p.qkv_w, L, s_qkv);
+    load_rows(w_o, p.o_w, L, s_o);
+    load_rows(w_f1, p.ff1_w, L, s_f1);
+    load_rows(w_f2, p.ff2_w, F, s_f2);
+    for (int cb = 0; cb < 8; cb++) load_rows(w_out0 + cb * out_elems, p.out_w[cb], L, s_out);
+
+    const bool loop = p.d_step != nullptr;
+    const int step = loop ? *p.d_step : (int)p.step;
+    const float att_scale = 1.0f / sqrtf((float)L);
+    auto no_prep = [](int, float *) {};
+
+    // seq[0] = in_proj . hidden + b   (magpie.cpp:1153-1185)
+    gemv_phase<false>(w_in, s_in, d, p.hidden, d, B, tile, no_prep, [&](int u, int n, float v) { bp.seq[(size_t)u * L + n] = v + p.in_b[n]; });
+    if (p.hidden_hist)
+        for (size_t i = (size_t)c * kLtThreads + tid; i < (size_t)B * d; i += (size_t)G * kLtThreads) {
+            const size_t u = i / d, k = i % d;
+            p.hidden_hist[((loop ? u * p.T_total + step : u)) * d + k] = p.hidden[i];
+        }
+    grid.sync();
+
+    bool hit_eos[8];                       // per owned utterance (utterances c, c + G, ...), thread-uniform
+#pragma unroll
+    for (int i = 0; i < 8; i++) hit_eos[i] = false;
+
+    for (int cb = 0; cb < 8; cb++) {
+        const float * pos = p.pos + cb * L;
+        // q | k | v = qkv_net . LN(seq + pos)   (magpie.cpp:1026-1030, 1501-1503)
+        gemv_phase<true>(w_qkv, s_qkv, L, bp.seq, L, B, tile,
+                   [&](int, float * row) {
+                       const int lane = threadIdx.x & 31;
+                       for (int i = lane; i < L; i += 32) row[i] += pos[i];
+                       __syncwarp();
+                       warp_layer_norm(row, L, p.norm_self, p.eps);
+                   },
+                   [&](int u, int n, float v) {
+                       if (n < L) bp.q[(size_t)u * L + n] = v;
+                       else if (n < 2 * L) bp.kc[((size_t)u * 8 + cb) * L + (n - L)] = v;
+                       else bp.vc[((size_t)u * 8 + cb) * L + (n - 2 * L)] = v;
+                   });
+        grid.sync();
+        // single-head causal attention over positions 0..cb, one owner CTA per utterance (magpie.cpp:946-1013)
+        for (int u = c; u < B; u += G) {
+            __syncthreads();
+            float * sc = tile;             // scores[8]
+            const int warp = tid >> 5, lane = tid & 31;
+            if (warp <= cb) {
+                float s = 0.0f;
+                for (int i = lane; i < L; i += 32) s = fmaf(bp.kc[((size_t)u * 8 + warp) * L + i], bp.q[(size_t)u * L + i], s);
+                s = warp_sum(s);
+                if (lane == 0) sc[warp] = s * att_scale;
+            }
+            __syncthreads();
+            if (tid < L) {
+                float mxs = sc[0];
+                for (int j = 1; j <= cb; j++) mxs = fmaxf(mxs, sc[j]);
+                float e[8], sum = 0.0f;
+#pragma unroll
+                for (int j = 0; j < 8; j++) { e[j] = (j <= cb) ? expf(sc[j] - mxs) : 0.0f; sum += e[j]; }
+                const float inv = 1.0f / sum;
+                float o = 0.0f;
+#pragma unroll
+                for (int j = 0; j < 8; j++) if (j <= cb) o = fmaf(e[j] * inv, bp.vc[((size_t)u * 8 + j) * L + tid], o);
+                bp.att[(size_t)u * L + tid] = o;
+            }
+        }
+        grid.sync();
+        // x1 = (seq + pos) + o_net . att
+        gemv_phase<false>(w_o, s_o, L, bp.att, L, B, tile, no_prep,
+                   [&](int u, int n, float v) { bp.x1[(size_t)u * L + n] = v + (bp.seq[(size_t)u * L + n] + pos[n]); });
+        grid.sync();
+        // ffh = gelu(ff1 . LN(x1))
+        gemv_phase<true>(w_f1, s_f1, L, bp.x1, L, B, tile,
+                   [&](int, float * row) { warp_layer_norm(row, L, p.norm_ff, p.eps); },
+                   [&](int u, int n, float v) { bp.ffh[(size_t)u * F + n] = gelu_ggml(v, p.gelu_f16); });
+        grid.sync();
+        // hout = x1 + ff2 . ffh
+        gemv_phase<false>(w_f2, s_f2, F, bp.ffh, F, B, tile, no_prep,
+                   [&](int u, int n, float v) { bp.hout[(size_t)u * L + n] = v + bp.x1[(size_t)u * L + n]; });
+        grid.sync();
+        // logits = out_proj[cb] . hout + b   (magpie.cpp:1037-1048)
+        {
+            const float * ob = p.out_b[cb];
+            gemv_phase<false>(w_out0 + cb * out_elems, s_out, L, bp.hout, L, B, tile, no_prep,
+                       [&](int u, int n, float v) { bp.logits[(size_t)u * V + n] = v + ob[n]; });
+        }
+        grid.sync();
+        // masking, argmax, top-k sampling, feedback embedding: owner CTA per utterance
+        int oi = 0;
+        for (int u = c; u < B; u += G, oi++) {
+            __syncthreads();
+            const size_t row = loop ? (size_t)u * p.T_total + step : (size_t)u;
+            const int32_t * forced = p.forced ? p.forced + row * 8 : nullptr;
+            const bool forbid_eos = p.forbid_eos_all || (p.forbid_eos && p.forbid_eos[u]) || (loop && step < p.min_frames);
+            for (int i = tid; i < V; i += kLtThreads) S.logits[i] = bp.logits[(size_t)u * V + i];
+            __syncthreads();
+            // forbidden ids: BOS, BOS+2..BOS+7, and EOS while forbid_eos (magpie.cpp:1131-1145, 1243-1248)
+            if (tid < 8) {
+                const int id = tid == 0 ? p.bos_id : (tid < 7 ? p.bos_id + 1 + tid : (forbid_eos ? p.eos_id : -1));
+                if (id >= 0 && id < V) S.logits[id] = -INFINITY;
+            }
+            __syncthreads();
+            if (p.logits)
+                for (int i = tid; i < V; i += kLtThreads) p.logits[(row * 8 + cb) * V + i] = S.logits[i];
+            const int am = block_argmax(S.logits, V, S.red, S.redi);
+            int pick = am;
+            if (p.temperature >= 0.01f) {
+                float uu;
+                if (p.uniforms) uu = p.uniforms[row * 8 + cb];
+                else {
+                    uint32_t r[4];
+                    philox4x32_10((uint32_t)step, (uint32_t)u, (uint32_t)cb, 0u, (uint32_t)p.seed, (uint32_t)(p.seed >> 32), r);
+                    uu = (float)(r[0] >> 8) * (1.0f / 16777216.0f);
+                }
+                pick = block_sample_top_k(S, V, p.temperature, p.top_k, uu);
+            }
+            if (oi < 8) hit_eos[oi] = hit_eos[oi] || pick == p.eos_id || am == p.eos_id;
+            if (tid == 0) {
+                p.argmax[row * 8 + cb] = am;
+                p.sampled[row * 8 + cb] = pick;
+                if (p.next_codes) p.next_codes[u * 8 + cb] = forced ? forced[cb] : pick;
+                if (cb == 7) {
+                    const bool he = oi < 8 ? hit_eos[oi] : false;
+                    if (p.eos_flag) p.eos_flag[u] = he ? 1 : 0;
+                    if (p.done_step && he && p.done_step[u] < 0) p.done_step[u] = step;
+                }
+            }
+            if (cb < 7) {
+                // seq[cb+1] = in_proj . E_cb[code] + b, folded at load into a table (model.cu)
+                const int fed = forced ? forced[cb] : pick;
+                if (tid < L) bp.seq[(size_t)u * L + tid] = p.in_table[cb][(size_t)fed * L + tid];
+            }
+        }
+        if (cb < 7) grid.sync();
+    }
+}
+
+size_t slice_smem_bytes(const Model & m, int G) {
+    const mgb_hparams & hp = m.hp;
+    auto rows = [&](int N) { return (size_t)((N + G - 1) / G + 1); };     // upper bound of a balanced slice
+    const int L = hp.lt_dim, F = hp.lt_ffn_dim, d = hp.d_model, V = hp.vocab_per_cb;
+    size_t e = rows(L) * d + rows(3 * L) * L + rows(L) * L + rows(F) * L + rows(L) * F + 8 * rows(V) * L;
+    return e * sizeof(bf);
+}
+
+}  // namespace
+
+size_t lt_batch_scratch_bytes(const Model & m, int B) {
+    const mgb_hparams & hp = m.hp;
+    const size_t L = hp.lt_dim, F = hp.lt_ffn_dim, V = hp.vocab_per_cb;
+    return (size_t)B * (L * 5 + 2 * 8 * L + F + V) * sizeof(float);
+}
+
+// bf16 models with the folded feedback table, >= 16 utterances, at most 8 utterances per owner CTA
+bool lt_batch_supported(const Model & m, int B) {
+    if (getenv("MGB_NO_LT_BATCH") != nullptr) return false;
+    const mgb_hparams & hp = m.hp;
+    if (m.precision != MGB_PREC_BF16 || !m.lt_in_table[0] || B < 16) return false;
+    if (hp.lt_dim != 256 || hp.lt_ffn_dim > kF || hp.lt_ffn_dim % 256 != 0 || hp.d_model % 256 != 0 || hp.d_model > kD || hp.vocab_per_cb > kV) return false;
+    return B <= 8 * 132;
+}
+
+bool launch_lt_batch(const Model & m, const LtParams & p, void * scratch, size_t scratch_bytes, cudaStream_t stream) {
+    static int n_sm[64] = {};
+    static uint64_t attr_done = 0;
+    int dev = 0;
+    MGB_CUDA_TRY(cudaGetDevice(&dev));
+    if (!n_sm[dev & 63]) MGB_CUDA_TRY(cudaDeviceGetAttribute(&n_sm[dev & 63], cudaDevAttrMultiProcessorCount, dev));
+    const int G = n_sm[dev & 63];
+    const size_t smem = (size_t)kTileFloats * 4 + slice_smem_bytes(m, G);
+    if (smem > 227 * 1024) { set_error("lt_batch: weight slices do not fit shared memory"); return false; }
+    if (scratch_bytes < lt_batch_scratch_bytes(m, p.B) || !scratch) { set_error("lt_batch: scratch too small"); return false; }
+    if (!(attr_done >> (dev & 63) & 1)) {
+        MGB_CUDA_TRY(cudaFuncSetAttribute(lt_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_done |= 1ull << (dev & 63);
+    }
+    BParams bp;
+    bp.p = p;
+    const size_t B = p.B, L = p.L, F = p.F, V = p.V;
+    float * f = (float *)scratch;
+    bp.seq = f; f += B * L; bp.q = f; f += B * L; bp.kc = f; f += B * 8 * L; bp.vc = f; f += B * 8 * L;
+    bp.att = f; f += B * L; bp.x1 = f; f += B * L; bp.ffh = f; f += B * F; bp.hout = f; f += B * L; bp.logits = f;
+    void * args[] = {&bp};
+    MGB_CUDA_TRY(cudaLaunchCooperativeKernel((void *)lt_batch_kernel, dim3(G), dim3(kLtThreads), args, smem, stream));
+    MGB_LAUNCH_CHECK();
+    return true;
+}
+
+}  // namespace mgb

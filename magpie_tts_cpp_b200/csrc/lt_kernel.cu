@@ -22,6 +22,8 @@ namespace mgb {
 
 bool lt_resident_supported(const Model & m, int B);
 bool launch_lt_resident(const lt::LtParams & p, cudaStream_t stream);
+bool lt_batch_supported(const Model & m, int B);
+bool launch_lt_batch(const Model & m, const lt::LtParams & p, void * scratch, size_t scratch_bytes, cudaStream_t stream);
 
 namespace {
 
@@ -280,6 +282,9 @@ bool launch_local_transformer(const Model & m, const LtArgs & a, cudaStream_t st
     for (int cb = 0; cb < 8; cb++) p.in_table[cb] = m.lt_in_table[cb];
     // MGB_LT_STREAM keeps the independent (GEMV) formulation alive for the parity tests; f32 models always use it
     p.stream_feedback = (getenv("MGB_LT_STREAM") != nullptr || m.precision == MGB_PREC_F32) ? 1 : 0;
+    // many utterances, bf16: weight-stationary persistent kernel over all utterances (lt_batch.cu)
+    if (a.lt_scratch && lt_batch_supported(m, a.B) && getenv("MGB_LT_STREAM") == nullptr)
+        return launch_lt_batch(m, p, a.lt_scratch, a.lt_scratch_bytes, stream);
     // small batches, bf16: weights resident in shared memory (lt_resident.cu)
     if (lt_resident_supported(m, a.B)) return launch_lt_resident(p, stream);
     // 16-CTA (non-portable) clusters when the device can schedule them, else the portable 8

@@ -412,6 +412,49 @@ def test_tensor_core_linear_matches_cuda_core_kernels(B, full_model_path, full_o
     np.testing.assert_array_equal(gr_t[0], gr_t[23])     # batch rows are independent and deterministic
 
 
+def test_batched_local_transformer_matches_per_utterance_kernel(B, full_model_path, full_oracle, monkeypatch):
+    """bf16, 20 utterances: the weight-stationary persistent LT (lt_batch.cu, default for >= 16 utterances) against the
+    one-cluster-per-utterance kernel (MGB_NO_LT_BATCH=1) and the oracle; same bf16 weights and f32 arithmetic, so the two
+    kernels differ by summation order only."""
+    nb = 20
+    m = B.Model(full_model_path, 0, B.PREC_BF16)
+    s = m.session(batch=nb, max_text=32)
+    rng = np.random.default_rng(11)
+    hid = np.stack([full_oracle["hid"][b % len(full_oracle["hid"])] for b in range(nb)]).astype(np.float32)
+    hid[nb // 2:] += 0.05 * rng.standard_normal(hid[nb // 2:].shape).astype(np.float32)
+    forced = rng.integers(0, 2016, (nb, 8)).astype(np.int32)
+    u = rng.random((nb, 8)).astype(np.float32)
+
+    def run(no_batch, **kw):
+        if no_batch:
+            monkeypatch.setenv("MGB_NO_LT_BATCH", "1")
+        else:
+            monkeypatch.delenv("MGB_NO_LT_BATCH", raising=False)
+        out = s.lt_sample(hid, **kw)
+        monkeypatch.delenv("MGB_NO_LT_BATCH", raising=False)
+        return out
+
+    # teacher-forced: logits of all 8 codebooks
+    sa, aa, la = run(False, temperature=0.0, forced_codes=forced)
+    sb, ab, lb = run(True, temperature=0.0, forced_codes=forced)
+    close(la, lb, 1e-4)
+    assert np.mean(aa == ab) >= 0.99
+    # against the oracle for the rows that carry the oracle's own hidden states and forced codes
+    o = full_oracle["o"]
+    for b in (0, 3):
+        _, a_ref, lg_ref = o.lt_sample(hid[b], 0.0, 80, forced_codes=forced[b])
+        close(la[b], lg_ref, 2e-2)
+    # free-running greedy and top-k sampling from given uniforms (forbid EOS on half of the rows)
+    fe = (np.arange(nb) % 2).astype(np.uint8)
+    sa, aa, _ = run(False, temperature=0.0, forbid_eos=fe, want_logits=False)
+    sb, ab, _ = run(True, temperature=0.0, forbid_eos=fe, want_logits=False)
+    assert np.mean(np.all(sa == sb, axis=1)) >= 0.9 and np.array_equal(sa, aa)
+    sa, aa, _ = run(False, temperature=0.7, top_k=80, uniforms=u, want_logits=False)
+    sb, ab, _ = run(True, temperature=0.7, top_k=80, uniforms=u, want_logits=False)
+    assert np.mean(sa[:, 0] == sb[:, 0]) >= 0.9          # later picks follow the first differing draw
+    s.close(); m.close()
+
+
 # ---- nano-codec ---------------------------------------------------------------------------------------
 
 def test_fsq_bit_exact(B, oracle_mod, codec_path):
