@@ -11,8 +11,10 @@
  * therefore restates (a) the reference's graph builders op for op and (b) upstream ggml's CPU
  * rounding points from its published algorithm (f64 LayerNorm/softmax sums, f16 GELU table,
  * f16 im2col for conv_1d, f16 / Q8_0 activation rounding in mul_mat).  What *is* pinned:
- * the FSQ formula and constants (nano-codec.cpp:729-742, tests/test_codec_fsq.cpp:42-74),
- * forbidden-token ids and the EOS rule (magpie.cpp:1131-1145, 4341-4348), the 1/8 audio
+ * orc_fsq_dequantize and orc_sample_top_k against the REFERENCE'S OWN fsq_dequantize_cpu / sample_top_k
+ * (compiled from /root/reference by oracle/build_ref_pieces.py, golden vectors in tests/golden/ref_pieces.json,
+ * tests/test_golden.py: bit-exact / identical picks), the FSQ formula and constants (nano-codec.cpp:729-742,
+ * tests/test_codec_fsq.cpp:42-74), forbidden-token ids and the EOS rule (magpie.cpp:1131-1145, 4341-4348), the 1/8 audio
  * embedding scale (magpie.cpp:2769-2770); tests/ additionally cross-checks every function here
  * against an independent float64 torch restatement.
  *

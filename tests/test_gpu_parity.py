@@ -5,6 +5,8 @@ Tolerances (BASELINE.json north_star): f32 logits/hidden within 1e-4, bf16 withi
 |a-b| <= tol*|b| + tol*rms(b) (pure rtol is undefined at zero crossings); greedy codes
 identical for >= 99 % of frames; FSQ bit-exact; codec waveform >= 40 dB SNR.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -470,6 +472,18 @@ def test_fsq_bit_exact(B, oracle_mod, codec_path):
     lat3 = c.fsq_dequantize(codes3)
     for b in range(3):
         np.testing.assert_array_equal(lat3[b].view(np.uint32), oracle_mod.fsq_dequantize(codes3[b]).view(np.uint32))
+
+
+def test_fsq_matches_reference_golden(B, codec_path):
+    """GPU FSQ against tests/golden/ref_pieces.json, produced by running the reference's own fsq_dequantize_cpu
+    (nano-codec.cpp:721-752) incl. out-of-range and negative indices: bit-exact."""
+    import json
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_pieces.json"), encoding="utf-8"))
+    idx = np.array(g["fsq"]["indices"], np.int32)
+    codes = np.stack([np.roll(idx, g["fsq"]["roll_per_codebook"] * cb) for cb in range(8)]).astype(np.int32)
+    bits = B.Codec(codec_path).fsq_dequantize(codes).view(np.uint32)
+    np.testing.assert_array_equal(bits[:4], np.array(g["fsq"]["latent_bits_cb0"], np.uint32))
+    assert int(np.bitwise_xor.reduce(bits.ravel() * np.arange(1, bits.size + 1, dtype=np.uint32))) == g["fsq"]["latent_bits_checksum"]
 
 
 def test_codec_decode_snr(B, oracle_mod, codec_path):
