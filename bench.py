@@ -240,19 +240,39 @@ def extra_measurements(binding, fixtures, m, args):
     """Secondary numbers of the BASELINE metric string: batched decoder frames/s and codec audio-s/s."""
     out = {}
     try:
+        # BASELINE configs[3]: 64 utterances per GPU, 10 s (215 frames) each, distinct random texts of 20..80 tokens,
+        # speakers 0..4, EOS disabled (teacher-forced fixed length)
         B = 64
-        frames = 215                                  # 10 s utterances (config 4)
-        s = m.session(batch=B, max_text=32, max_seq=m.hp["context_frames"] + frames + 16)
-        s.encode_text([HELLO] * B, want_output=False)
-        s.prefill([b % 5 for b in range(B)])
+        frames = 215
+        rng = np.random.default_rng(7)
+        texts = [[2378] + rng.integers(0, 90, int(rng.integers(18, 79))).tolist() + [2379] for _ in range(B)]
+        s = m.session(batch=B, max_text=96, max_seq=m.hp["context_frames"] + frames + 16)
         codes = np.repeat(forced_codes(frames), B, axis=0)
-        s.teacher_forced(codes, want_hidden=False, want_logits=False)
-        s.encode_text([HELLO] * B, want_output=False); s.prefill([b % 5 for b in range(B)])
-        s.teacher_forced(codes, want_hidden=False, want_logits=False)
+        for _ in range(2):
+            s.encode_text(texts, want_output=False)
+            s.prefill([b % 5 for b in range(B)])
+            s.teacher_forced(codes, want_hidden=False, want_logits=False)
         out["decoder_b64_frames_per_s"] = B * frames / (s.last_loop_ms * 1e-3)
+        out["decoder_b64_sample"] = "config 4: 64 utterances x 215 frames, random texts of 20..80 tokens, speakers 0..4"
+        out["decoder_b64_launches_per_step"] = s.last_loop_launches / frames
         s.close()
     except Exception as e:  # noqa: BLE001
         out["decoder_b64_error"] = str(e)
+    try:
+        # BASELINE configs[4] (per-GPU share): Q8_0 GGUF, 32 utterances, 2600-frame utterances (KV length 110 -> 2710)
+        mq = binding.Model(fixtures.ensure_fixture("model-long-q8"), m.device if hasattr(m, "device") else 0, binding.PREC_BF16)
+        B, frames = 32, 2600
+        s = mq.session(batch=B, max_text=32, max_seq=mq.hp["context_frames"] + frames + 16)
+        codes = np.repeat(forced_codes(frames), B, axis=0)
+        s.encode_text([HELLO] * B, want_output=False); s.prefill([b % 5 for b in range(B)])
+        s.teacher_forced(codes[:, :64], want_hidden=False, want_logits=False)
+        s.encode_text([HELLO] * B, want_output=False); s.prefill([b % 5 for b in range(B)])
+        s.teacher_forced(codes, want_hidden=False, want_logits=False)
+        out["decoder_q8_long_b32_frames_per_s"] = B * frames / (s.last_loop_ms * 1e-3)
+        out["decoder_q8_long_sample"] = "config 5 per-GPU share: Q8_0 GGUF (dequantised to bf16 at load), 32 utterances x 2600 frames"
+        s.close(); mq.close()
+    except Exception as e:  # noqa: BLE001
+        out["decoder_q8_long_error"] = str(e)
     try:
         # BASELINE configs[2]: nano-codec decode only, 60 s of 21.5 fps codes (1291 frames), batch 32, one call
         c = binding.Codec(fixtures.ensure_fixture("codec-f32"), 0)
