@@ -62,6 +62,7 @@ struct Session {
     unsigned long long * d_loop_dbg = nullptr;
     void * tc_scratch = nullptr; size_t tc_scratch_bytes = 0;     // tensor-core path: activation tile images
     void * lt_scratch = nullptr; size_t lt_scratch_bytes = 0;     // batched local transformer: activation scratch
+    float * fold_xm = nullptr, * fold_xn = nullptr; bool fold_ready = false;     // batched decode: folded cross-attention tables [L][B][max_text][d]
 
     ~Session() {
         if (m) cudaSetDevice(m->device);
@@ -112,7 +113,12 @@ static bool decoder_layers(Session & s, Tokens tok, bool want_hidden) {
         o.tc_scratch = s.tc_scratch; o.tc_scratch_bytes = s.tc_scratch_bytes;
         o.precision = m.precision; o.M = M; o.W = L.o; o.X = s.attn; o.ldx = d; o.res = s.x; o.ldr = d; o.Y = s.x; o.ldy = d;
         if (!launch_linear(o, s.stream)) return false;
-        // cross-attention over the cached encoder K/V (no mask)
+        // cross-attention over the cached encoder K/V (no mask); a batched decoder step (one token per utterance) uses
+        // the folded tables: one launch instead of LN+pack, q GEMM, attention, pack, o GEMM
+        if (s.fold_ready && M == s.B && tok.utt == s.dec_utt) {
+            const size_t tab = (size_t)s.B * s.max_text * d;
+            if (!launch_xattn_folded(s.x, L.norm_xa_q, hp.eps, s.fold_xm + l * tab, s.fold_xn + l * tab, s.d_ntext, s.B, d, s.max_text, s.stream)) return false;
+        } else {
         LinearArgs q;
         q.tc_scratch = s.tc_scratch; q.tc_scratch_bytes = s.tc_scratch_bytes;
         q.precision = m.precision; q.eps = hp.eps; q.M = M; q.W = L.xq; q.X = s.x; q.ldx = d; q.ln_w = L.norm_xa_q; q.Y = s.xq; q.ldy = dxa;
@@ -126,6 +132,7 @@ static bool decoder_layers(Session & s, Tokens tok, bool want_hidden) {
         xo.tc_scratch = s.tc_scratch; xo.tc_scratch_bytes = s.tc_scratch_bytes;
         xo.precision = m.precision; xo.M = M; xo.W = L.xo; xo.X = s.xatt; xo.ldx = dxa; xo.res = s.x; xo.ldr = d; xo.Y = s.x; xo.ldy = d;
         if (!launch_linear(xo, s.stream)) return false;
+        }
         // conv-FFN (kernel 1): LN -> W1 -> GELU -> W2 + residual
         LinearArgs f1;
         f1.tc_scratch = s.tc_scratch; f1.tc_scratch_bytes = s.tc_scratch_bytes;
@@ -286,6 +293,11 @@ mgb_session * mgb_session_new(mgb_model * mm, int batch, int max_text, int max_s
         if (!s->alloc(tp, tb)) return nullptr;
         s->tc_scratch = tp; s->tc_scratch_bytes = tb;
     }
+    if (m->precision == MGB_PREC_BF16 && batch >= 2 && dxa == 128 && getenv("MGB_NO_XFOLD") == nullptr &&
+        (size_t)L * batch * max_text * d * 8 <= ((size_t)8 << 30)) {
+        const size_t tab = (size_t)L * batch * max_text * d;
+        if (!s->alloc(s->fold_xm, tab) || !s->alloc(s->fold_xn, tab)) return nullptr;
+    }
     if (m->precision == MGB_PREC_BF16 && batch >= 16) {
         const size_t lb = lt_batch_scratch_bytes(*m, batch);
         char * lp = nullptr;
@@ -414,7 +426,7 @@ int mgb_encode_text(mgb_session * ss, const int32_t * tokens, const int32_t * n_
             }
     }
     if (cudaStreamSynchronize(st) != cudaSuccess) { set_error(std::string("magpie_encode_text: ") + cudaGetErrorString(cudaGetLastError())); return MGB_ECUDA; }
-    s->encoded = true; s->prefilled = false;
+    s->encoded = true; s->prefilled = false; s->fold_ready = false;
     return MGB_OK;
 }
 
@@ -452,6 +464,17 @@ int mgb_prefill(mgb_session * ss, const int32_t * speakers) {
                                    1.0f / sqrtf((float)dxa), s->d_xm + (size_t)l * kLoopMaxCtx * d, s->d_xn + (size_t)l * kLoopMaxCtx * d, st)) return MGB_ECUDA;
         }
         s->loop_tables = true;
+    }
+    // batched decode: the same fold for every (utterance, text position) row of the cross K/V
+    s->fold_ready = false;
+    if (s->fold_xm) {
+        const size_t tab = (size_t)s->B * s->max_text * d;
+        for (int l = 0; l < hp.dec_layers; l++) {
+            const DecLayer & L = m.dec[l];
+            if (!launch_xattn_fold((char *)s->xk + l * xkv_layer, (char *)s->xv + l * xkv_layer, L.xq.w, L.xo.w, s->B * s->max_text, d, dxa,
+                                   1.0f / sqrtf((float)dxa), s->fold_xm + l * tab, s->fold_xn + l * tab, st)) return MGB_ECUDA;
+        }
+        s->fold_ready = true;
     }
     // context prefill: B*C tokens, one batched causal pass (magpie.cpp:4170-4238)
     const int M = s->B * C;

@@ -29,6 +29,14 @@ __constant__ int c_fsq_levels[4];
 
 __device__ __forceinline__ float f16r(float x) { return __half2float(__float2half_rn(x)); }
 
+// one FSQ level (nano-codec.cpp:736-741): integer div/mod, value from the LUT built with the reference's C expression
+__device__ __forceinline__ float fsq_level(int index, int d) {
+    const int nonneg = (index / c_fsq_base[d]) % c_fsq_levels[d];     // C semantics incl. negatives
+    if (nonneg >= 0) return c_fsq_lut[d][nonneg];
+    const int half = c_fsq_levels[d] / 2;
+    return (float)(nonneg - half) / (float)half;
+}
+
 // x + sin^2(alpha x)/alpha for c < n_alpha, LeakyReLU(0.01) otherwise (nano-codec.cpp:386-417)
 __device__ __forceinline__ float half_snake(float x, int c, const float * alpha, int n_alpha) {
     if (c < n_alpha) {
@@ -46,17 +54,12 @@ __global__ void fsq_kernel(const int32_t * codes, float * latent, int T, size_t 
     const size_t bc = i / T; const int t = (int)(i % T);
     const int index = codes[i];
 #pragma unroll
-    for (int d = 0; d < 4; d++) {
-        const int nonneg = (index / c_fsq_base[d]) % c_fsq_levels[d];     // C semantics incl. negatives
-        float v;
-        if (nonneg >= 0) v = c_fsq_lut[d][nonneg];
-        else { const int half = c_fsq_levels[d] / 2; v = (float)(nonneg - half) / (float)half; }
-        latent[(bc * 4 + d) * T + t] = v;
-    }
+    for (int d = 0; d < 4; d++) latent[(bc * 4 + d) * T + t] = fsq_level(index, d);
 }
 
 struct ConvParams {
     const float * xa;        // activated, f16-representable input [B][Cin][T]
+    const int32_t * codes;   // non-null: the input is the FSQ latent of codes [B][Cin/4][T], dequantised while staging (xa unused)
     const __half * w;        // [Cin][K][CoPad]
     const float * bias;      // [Cout]
     const float * res;       // optional residual [B][Cout][T]
@@ -97,7 +100,11 @@ __global__ void __launch_bounds__(256) conv1d_kernel(const ConvParams p) {
         for (int i = tid; i < nci * xw; i += 256) {
             const int ci = i / xw, tt = i % xw;
             const int t = t0 - halo + tt;
-            float v = (t >= 0 && t < p.T) ? xb[(size_t)(ci0 + ci) * p.T + t] : 0.0f;
+            float v = 0.0f;
+            if (t >= 0 && t < p.T) {
+                const int c = ci0 + ci;
+                v = p.codes ? fsq_level(p.codes[((size_t)b * (p.Cin / 4) + (c >> 2)) * p.T + t], c & 3) : xb[(size_t)c * p.T + t];
+            }
             xs[ci * xw + tt] = p.round_in ? f16r(v) : v;
         }
         for (int i = tid; i < nci * p.K * (CO_T / 8); i += 256) {      // 16-byte chunks of 8 halves
@@ -315,10 +322,9 @@ static bool codec_decode_tc(Codec & c, const int32_t * d_codes, int B, int T, fl
     }
     float * cur = c.buf[0], * up = c.buf[1], * o = c.buf[2], * lat = c.buf[3], * sum = c.buf[5];
 
-    if (!codec_fsq_device(d_codes, B, T, lat, stream)) return false;
-    {   // pre-conv 32 -> 864 on the CUDA cores, written as time-major rows
+    {   // FSQ dequantisation fused into the staging of the pre-conv 32 -> 864 (CUDA cores), output as time-major rows
         ConvParams p = {};
-        p.xa = lat; p.w = (const __half *)c.pre_w16; p.bias = c.pre_b; p.y = cur; p.round_in = 1; p.tm_stride = ctc::row_stride(c.base_ch);
+        p.xa = lat; p.codes = d_codes; p.w = (const __half *)c.pre_w16; p.bias = c.pre_b; p.y = cur; p.round_in = 1; p.tm_stride = ctc::row_stride(c.base_ch);
         p.Cin = c.latent; p.Cout = c.base_ch; p.CoPad = pad64(c.base_ch); p.K = c.pre_k; p.dil = 1; p.T = T;
         if (!launch_conv(p, B, stream)) return false;
     }

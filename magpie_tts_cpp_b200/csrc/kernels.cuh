@@ -58,6 +58,9 @@ struct AttnArgs {
     float * out = nullptr; int ldo = 0;
 };
 bool launch_attention(const AttnArgs & a, cudaStream_t stream);
+// batched decoder step: folded cross-attention x += softmax(M LN(x)) N (tables from launch_xattn_fold, frame_loop.cu)
+bool launch_xattn_folded(float * x, const float * ln_w, float eps, const float * xm, const float * xn, const int32_t * n_ctx, int B, int d,
+                         int max_text, cudaStream_t stream);
 
 // x[t] = (sum_cb E_cb[codes[utt][cb]]) * 1/8 + dec_pos[pos]        (magpie.cpp:2746-2787, 4376-4379)
 bool launch_audio_embed(const Model & m, const int32_t * codes /*[B][8] device*/, const int32_t * pos /*[B]*/,

@@ -364,6 +364,60 @@ bool launch_attention(const AttnArgs & a, cudaStream_t stream) {
     return true;
 }
 
+// ---- folded cross-attention for a batched decoder step -----------------------------------------------------------------
+// x_u += softmax(M_u LN(x_u; w)) N_u with the per-utterance tables M = scale K Wq (E x d) and N = V Wo^T (E x d) built at
+// prefill (frame_loop.cu xattn_fold_kernel): the reference's q_net GEMV, 1-head attention over E text tokens and o_net GEMV
+// (magpie.cpp:1713-1767, 3513) in ONE launch instead of five.  One CTA per utterance, 512 threads.
+struct XFoldParams { float * x; const float * ln_w; float eps; const float * xm; const float * xn; const int32_t * n_ctx; int d, max_text; };
+__global__ void __launch_bounds__(512) xattn_folded_kernel(const XFoldParams p) {
+    __shared__ float xl[1024];
+    __shared__ float sc[512];
+    __shared__ float red[32];
+    const int u = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int d = p.d, E = p.n_ctx[u];
+    float * xr = p.x + (size_t)u * d;
+    // LayerNorm (no bias), magpie.cpp:2237-2259
+    float s = 0.0f;
+    for (int i = tid; i < d; i += 512) s += xr[i];
+    const float mean = block_sum(s, red) / (float)d;
+    float s2 = 0.0f;
+    for (int i = tid; i < d; i += 512) { const float c = xr[i] - mean; s2 += c * c; }
+    const float scale = 1.0f / sqrtf(block_sum(s2, red) / (float)d + p.eps);
+    for (int i = tid; i < d; i += 512) xl[i] = ((xr[i] - mean) * scale) * p.ln_w[i];
+    __syncthreads();
+    const float * xm = p.xm + (size_t)u * p.max_text * d, * xn = p.xn + (size_t)u * p.max_text * d;
+    for (int j = warp; j < E; j += 16) {
+        const float * mr = xm + (size_t)j * d;
+        float a = 0.0f;
+        for (int i = lane * 4; i < d; i += 128) {
+            const float4 m4 = *reinterpret_cast<const float4 *>(mr + i);
+            a = fmaf(m4.x, xl[i], a); a = fmaf(m4.y, xl[i + 1], a); a = fmaf(m4.z, xl[i + 2], a); a = fmaf(m4.w, xl[i + 3], a);
+        }
+        a = warp_sum(a);
+        if (lane == 0) sc[j] = a;
+    }
+    __syncthreads();
+    float mx = -INFINITY;
+    for (int j = 0; j < E; j++) mx = fmaxf(mx, sc[j]);
+    float sum = 0.0f;
+    for (int j = 0; j < E; j++) sum += expf(sc[j] - mx);
+    const float inv = 1.0f / sum;
+    for (int i = tid; i < d; i += 512) {
+        float o = 0.0f;
+        for (int j = 0; j < E; j++) o = fmaf(expf(sc[j] - mx) * inv, xn[(size_t)j * d + i], o);
+        xr[i] += o;
+    }
+}
+
+bool launch_xattn_folded(float * x, const float * ln_w, float eps, const float * xm, const float * xn, const int32_t * n_ctx, int B, int d,
+                         int max_text, cudaStream_t stream) {
+    if (d > 1024 || max_text > 512) { set_error("xattn_folded: shape not supported"); return false; }
+    XFoldParams p{x, ln_w, eps, xm, xn, n_ctx, d, max_text};
+    xattn_folded_kernel<<<B, 512, 0, stream>>>(p);
+    MGB_LAUNCH_CHECK();
+    return true;
+}
+
 bool launch_audio_embed(const Model & m, const int32_t * codes, const int32_t * pos, int B, float * x, cudaStream_t stream) {
     AudioEmbParams a;
     for (int cb = 0; cb < 8; cb++) a.emb[cb] = m.audio_emb[cb];

@@ -414,6 +414,36 @@ def test_tensor_core_linear_matches_cuda_core_kernels(B, full_model_path, full_o
     np.testing.assert_array_equal(gr_t[0], gr_t[23])     # batch rows are independent and deterministic
 
 
+def test_folded_cross_attention_matches_unfolded_kernels(B, full_model_path, full_oracle, monkeypatch):
+    """bf16, 5 utterances with different texts: batched decoder steps with the folded cross-attention tables (one launch per
+    layer) against the q_net GEMM + attention + o_net GEMM kernels (MGB_NO_XFOLD=1 at session creation) and the oracle."""
+    texts = [HELLO, HELLO[:9] + [2379], HELLO, [2378, 5, 6, 2379], HELLO]
+    codes = np.repeat(full_oracle["codes"][None, :6], 5, axis=0)
+    m = B.Model(full_model_path, 0, B.PREC_BF16)
+
+    def run(no_fold):
+        if no_fold:
+            monkeypatch.setenv("MGB_NO_XFOLD", "1")
+        s = m.session(batch=5, max_text=32)
+        monkeypatch.delenv("MGB_NO_XFOLD", raising=False)
+        s.encode_text(texts, want_output=False)
+        s.prefill([0, 1, 0, 2, 0])
+        hid, lg, gr = s.teacher_forced(codes)
+        n = s.last_loop_launches
+        s.close()
+        return hid, lg, gr, n
+
+    hid_f, lg_f, gr_f, n_f = run(False)
+    hid_u, lg_u, gr_u, n_u = run(True)
+    assert n_f < n_u                                   # 4 launches fewer per layer and step
+    for b in range(5):
+        close(hid_f[b], hid_u[b], 2e-3)
+        close(lg_f[b], lg_u[b], 2e-3)
+    for b in (0, 2, 4):                                # the oracle's text and speaker
+        close(hid_f[b], full_oracle["hid"][:6], 2e-2)
+    m.close()
+
+
 def test_batched_local_transformer_matches_per_utterance_kernel(B, full_model_path, full_oracle, monkeypatch):
     """bf16, 20 utterances: the weight-stationary persistent LT (lt_batch.cu, default for >= 16 utterances) against the
     one-cluster-per-utterance kernel (MGB_NO_LT_BATCH=1) and the oracle; same bf16 weights and f32 arithmetic, so the two
