@@ -3,6 +3,8 @@
 // Replaces linear_kernel (transformer_kernels.cu) for bf16 models when a launch carries >= 16 tokens: batched
 // decoder steps, the 110-frame context prefill and the cross-attention K/V precompute
 // (reference: ggml_mul_mat call sites src/magpie.cpp:3415, 3464-3479, 1733, 1764, 1796, 1805).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "gemm_tc.cuh"
 #include "kernels.cuh"
@@ -84,13 +86,41 @@ struct TcEpi {
     int n_q, dkv; bf * kdst; bf * vdst; const int32_t * tok_slot;
 };
 
-template <int MT>
+// SPLIT > 1: split-K over a thread-block cluster of SPLIT CTAs (cluster dims 1 x 1 x SPLIT, rank = blockIdx.z).  Every CTA
+// accumulates its share of the k tiles in its own TMEM; ranks > 0 then push their accumulator into rank 0's shared memory
+// through DSMEM, and rank 0 adds them in rank order (deterministic) and runs the epilogue.  At M <= 64 a GEMM launch is
+// bound by how fast ONE SM can ingest its CTA's weight + activation tiles, so the split shortens the critical path.
+template <int SPLIT> struct StageCap { static constexpr int value = SPLIT == 1 ? 8 : (SPLIT == 2 ? 5 : 3); };
+
+template <int MT, int SPLIT>
 __global__ void __launch_bounds__(tc::kThreads, 1) tc_linear_kernel(const bf * Wt, const bf * Xhi, const bf * Xlo, int KT, const TcEpi e) {
     extern __shared__ unsigned char tc_smem[];
+    constexpr int SCAP = StageCap<SPLIT>::value;
     const int nt = blockIdx.x, mt = blockIdx.y;
-    const uint32_t tmem = tc::mainloop<MT, 2, false, true>(tc_smem, Wt, Xhi, Xlo, KT, nt, mt);
+    const int rank = SPLIT > 1 ? (int)blockIdx.z : 0;
+    const int kt0 = rank * KT / SPLIT, kt1 = (rank + 1) * KT / SPLIT;
+    const uint32_t tmem = tc::mainloop<MT, 2, false, true, SCAP>(tc_smem, Wt, Xhi, Xlo, KT, nt, mt, kt0, kt1 - kt0);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (warp >= 2) {
+    // exchange buffer of rank 0: [SPLIT-1][MT columns][128 rows] f32, behind the stage ring and the barriers
+    unsigned char * tiles = reinterpret_cast<unsigned char *>(((uintptr_t)tc_smem + 1023) & ~(uintptr_t)1023);
+    float * xbuf = reinterpret_cast<float *>(tiles + tc::Smem<MT, 2, SCAP>::kStages * tc::Smem<MT, 2, SCAP>::kStageBytes + 256);
+    if (SPLIT > 1) {
+        if (rank > 0 && warp >= 2) {
+            const int q = warp & 3;
+            for (int c = 0; c < MT; c += 32) {
+                uint32_t v[32];
+                tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + c, v);
+                const uint32_t local = tc::smem_u32(xbuf + ((size_t)(rank - 1) * MT + c) * 128 + q * 32 + lane);
+                uint32_t remote;
+                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(0));
+#pragma unroll
+                for (int j = 0; j < 32; j++) asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(remote + j * 128 * 4), "r"(v[j]) : "memory");
+            }
+        }
+        __syncwarp();
+        asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    }
+    if (warp >= 2 && rank == 0) {
         const int q = warp & 3;                      // TMEM lane quarter this warp may access
         const int n = nt * tc::BM + q * 32 + lane;
         const float bias = (e.bias && n < e.N) ? e.bias[n] : 0.0f;
@@ -98,6 +128,13 @@ __global__ void __launch_bounds__(tc::kThreads, 1) tc_linear_kernel(const bf * W
             if (mt * MT + c >= e.M) break;           // warp-uniform
             uint32_t v[32];
             tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + c, v);
+            if (SPLIT > 1) {
+#pragma unroll
+                for (int r = 1; r < SPLIT; r++)
+#pragma unroll
+                    for (int j = 0; j < 32; j++)
+                        v[j] = __float_as_uint(__uint_as_float(v[j]) + xbuf[((size_t)(r - 1) * MT + c + j) * 128 + q * 32 + lane]);
+            }
             if (n < e.N) {
                 // residual values first (Y may alias res for the in-place x += W h updates, which would otherwise
                 // serialise 32 dependent load -> store round trips)
@@ -131,24 +168,29 @@ __global__ void __launch_bounds__(tc::kThreads, 1) tc_linear_kernel(const bf * W
     tc::finish<MT>(tmem);
 }
 
-template <int MT> bool launch_tc(const bf * Wt, const bf * hi, const bf * lo, int KT, const TcEpi & e, cudaStream_t stream) {
+template <int MT, int SPLIT> bool launch_tc(const bf * Wt, const bf * hi, const bf * lo, int KT, const TcEpi & e, cudaStream_t stream) {
     static uint64_t attr_done = 0;
     int dev = 0;
     MGB_CUDA_TRY(cudaGetDevice(&dev));
+    constexpr int SCAP = StageCap<SPLIT>::value;
+    constexpr int smem = tc::Smem<MT, 2, SCAP>::kBytes + (SPLIT - 1) * MT * 128 * 4;
+    static_assert(smem <= 227 * 1024, "tc_linear shared memory");
     if (!(attr_done >> dev & 1)) {
-        MGB_CUDA_TRY(cudaFuncSetAttribute(tc_linear_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Smem<MT>::kBytes));
+        MGB_CUDA_TRY(cudaFuncSetAttribute(tc_linear_kernel<MT, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_done |= 1ull << dev;
     }
     // launched as a programmatic dependent of the activation-packing kernel: CTAs start (and prefetch weight tiles)
     // while pack_x_kernel is still running, and wait for it with griddepcontrol.wait before touching its output
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((e.N + tc::BM - 1) / tc::BM, (e.M + MT - 1) / MT); cfg.blockDim = dim3(tc::kThreads);
-    cfg.dynamicSmemBytes = tc::Smem<MT>::kBytes; cfg.stream = stream;
-    cudaLaunchAttribute at[1];
+    cfg.gridDim = dim3((e.N + tc::BM - 1) / tc::BM, (e.M + MT - 1) / MT, SPLIT); cfg.blockDim = dim3(tc::kThreads);
+    cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    MGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc_linear_kernel<MT>, Wt, hi, lo, KT, e));
+    at[1].id = cudaLaunchAttributeClusterDimension;
+    at[1].val.clusterDim.x = 1; at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = SPLIT;
+    cfg.attrs = at; cfg.numAttrs = SPLIT > 1 ? 2 : 1;
+    MGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc_linear_kernel<MT, SPLIT>, Wt, hi, lo, KT, e));
     MGB_LAUNCH_CHECK();
     return true;
 }
@@ -181,8 +223,16 @@ bool launch_linear_tc(const LinearArgs & a, cudaStream_t stream) {
     TcEpi e;
     e.N = a.W.N; e.M = M; e.bias = a.bias; e.res = a.res; e.ldr = a.ldr; e.Y = a.Y; e.ldy = a.ldy; e.act = a.act; e.gelu_f16 = a.gelu_f16;
     e.n_q = a.n_q; e.dkv = a.dkv; e.kdst = (bf *)a.kdst; e.vdst = (bf *)a.vdst; e.tok_slot = a.tok_slot;
-    if (MT == 64) return launch_tc<64>((const bf *)a.W.tiles, hi, lo, K / 64, e, stream);
-    return launch_tc<128>((const bf *)a.W.tiles, hi, lo, K / 64, e, stream);
+    if (MT == 64) {
+        // one token tile: split K over a cluster (deterministic DSMEM reduction) to shorten the per-SM ingest chain
+        const int KT = K / 64;
+        static const bool no_split = getenv("MGB_NO_SPLITK") != nullptr;
+        static const bool all4 = getenv("MGB_SPLITK4") != nullptr;
+        if (!no_split && (KT >= 32 || (all4 && KT >= 8))) return launch_tc<64, 4>((const bf *)a.W.tiles, hi, lo, KT, e, stream);
+        if (!no_split && KT >= 8) return launch_tc<64, 2>((const bf *)a.W.tiles, hi, lo, KT, e, stream);
+        return launch_tc<64, 1>((const bf *)a.W.tiles, hi, lo, KT, e, stream);
+    }
+    return launch_tc<128, 1>((const bf *)a.W.tiles, hi, lo, K / 64, e, stream);
 }
 
 }  // namespace mgb

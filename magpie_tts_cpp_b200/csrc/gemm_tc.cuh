@@ -79,9 +79,9 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-template <int MT, int NB = 2> struct Smem {
+template <int MT, int NB = 2, int SCAP = 8> struct Smem {
     static constexpr int kStageBytes = BM * 128 + NB * MT * 128;
-    static constexpr int kStages = (200 * 1024) / kStageBytes < 8 ? (200 * 1024) / kStageBytes : 8;
+    static constexpr int kStages = (200 * 1024) / kStageBytes < SCAP ? (200 * 1024) / kStageBytes : SCAP;
     static constexpr int kBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
@@ -89,10 +89,12 @@ template <int MT, int NB = 2> struct Smem {
 // Wt: [NT][KT] tiles of 16 KB; Xhi/Xlo: [MTiles][KT] tiles of MT*128 bytes.  Must be called by all 192 threads.
 // After the call, epilogue warps (warp >= 2) own TMEM lanes 32*(warp%4) .. +31; call tc::finish() when done.
 // NB = 2: activations as hi + lo tiles (bf16, two MMAs per k slice); NB = 1: one tile (Xlo unused).  F16: operands are f16.
-template <int MT, int NB = 2, bool F16 = false, bool PDL = false>
+// Only the k tiles [kt_begin, kt_begin + kt_count) are accumulated (split-K over a cluster; default: all KT).
+template <int MT, int NB = 2, bool F16 = false, bool PDL = false, int SCAP = 8>
 __device__ __forceinline__ uint32_t mainloop(unsigned char * smem_raw, const void * Wt, const void * Xhi,
-                                             const void * Xlo, int KT, int nt, int mt) {
-    constexpr int S = Smem<MT, NB>::kStages, SB = Smem<MT, NB>::kStageBytes;
+                                             const void * Xlo, int KT, int nt, int mt, int kt_begin = 0, int kt_count = -1) {
+    constexpr int S = Smem<MT, NB, SCAP>::kStages, SB = Smem<MT, NB, SCAP>::kStageBytes;
+    const int NK = kt_count < 0 ? KT : kt_count;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char * tiles = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t * bars = reinterpret_cast<uint64_t *>(tiles + S * SB);
@@ -113,18 +115,18 @@ __device__ __forceinline__ uint32_t mainloop(unsigned char * smem_raw, const voi
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0 && lane == 0) {
-        const unsigned char * wsrc = reinterpret_cast<const unsigned char *>(Wt) + (size_t)nt * KT * (BM * 128);
-        const unsigned char * hsrc = reinterpret_cast<const unsigned char *>(Xhi) + (size_t)mt * KT * (MT * 128);
-        const unsigned char * lsrc = reinterpret_cast<const unsigned char *>(Xlo) + (size_t)mt * KT * (MT * 128);
+        const unsigned char * wsrc = reinterpret_cast<const unsigned char *>(Wt) + ((size_t)nt * KT + kt_begin) * (BM * 128);
+        const unsigned char * hsrc = reinterpret_cast<const unsigned char *>(Xhi) + ((size_t)mt * KT + kt_begin) * (MT * 128);
+        const unsigned char * lsrc = reinterpret_cast<const unsigned char *>(Xlo) + ((size_t)mt * KT + kt_begin) * (MT * 128);
         // Programmatic dependent launch: the weight tiles do not depend on the preceding kernel (which packs the
         // activations), so the first ring-full of them is requested BEFORE waiting for that kernel to complete.
-        const int npre = PDL ? (KT < S ? KT : S) : 0;
+        const int npre = PDL ? (NK < S ? NK : S) : 0;
         for (int kt = 0; kt < npre; kt++) {
             mbar_expect_tx(&full[kt], SB);
             bulk_g2s(tiles + kt * SB, wsrc + (size_t)kt * (BM * 128), BM * 128, &full[kt]);
         }
         if (PDL) asm volatile("griddepcontrol.wait;" ::: "memory");
-        for (int kt = 0; kt < KT; kt++) {
+        for (int kt = 0; kt < NK; kt++) {
             const int s = kt % S;
             unsigned char * st = tiles + s * SB;
             if (kt >= npre) {
@@ -137,7 +139,7 @@ __device__ __forceinline__ uint32_t mainloop(unsigned char * smem_raw, const voi
         }
     } else if (warp == 1 && lane == 0) {
         constexpr uint32_t idesc = F16 ? umma_idesc_f16(BM, MT) : umma_idesc_bf16(BM, MT);
-        for (int kt = 0; kt < KT; kt++) {
+        for (int kt = 0; kt < NK; kt++) {
             const int s = kt % S;
             mbar_wait(&full[s], (kt / S) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
