@@ -61,6 +61,7 @@ struct Session {
     int32_t * d_result = nullptr; float * d_xm = nullptr, * d_xn = nullptr; int loop_E = 0; bool loop_tables = false;
     unsigned long long * d_loop_dbg = nullptr;
     void * tc_scratch = nullptr; size_t tc_scratch_bytes = 0;     // tensor-core path: activation tile images
+    void * tc_scratch2 = nullptr;                                  // second image buffer (FF1 epilogue -> FF2 input)
     void * lt_scratch = nullptr; size_t lt_scratch_bytes = 0;     // batched local transformer: activation scratch
     float * fold_xm = nullptr, * fold_xn = nullptr; bool fold_ready = false;     // batched decode: folded cross-attention tables [L][B][max_text][d]
 
@@ -105,19 +106,38 @@ static bool decoder_layers(Session & s, Tokens tok, bool want_hidden) {
         a.W = L.qkv; a.X = s.x; a.ldx = d; a.ln_w = L.norm_self; a.Y = s.qbuf; a.ldy = d;
         a.n_q = d; a.dkv = d; a.kdst = kl; a.vdst = vl; a.tok_slot = tok.slot;
         if (!launch_linear(a, s.stream)) return false;
-        AttnArgs at;
-        at.precision = m.precision; at.q = s.qbuf; at.ldq = d; at.K = kl; at.V = vl; at.rows_per_utt = s.max_seq;
-        at.H = hp.dec_sa_heads; at.dh = d / hp.dec_sa_heads; at.causal = 1; at.tok = tok; at.out = s.attn; at.ldo = d;
-        if (!launch_attention(at, s.stream)) return false;
         LinearArgs o;
         o.tc_scratch = s.tc_scratch; o.tc_scratch_bytes = s.tc_scratch_bytes;
         o.precision = m.precision; o.M = M; o.W = L.o; o.X = s.attn; o.ldx = d; o.res = s.x; o.ldr = d; o.Y = s.x; o.ldy = d;
+        AttnArgs at;
+        at.precision = m.precision; at.q = s.qbuf; at.ldq = d; at.K = kl; at.V = vl; at.rows_per_utt = s.max_seq;
+        at.H = hp.dec_sa_heads; at.dh = d / hp.dec_sa_heads; at.causal = 1; at.tok = tok; at.out = s.attn; at.ldo = d;
+        // batched decoder step on the tensor-core path: the attention kernel writes the O-projection's packed input itself
+        if (M == s.B && tok.utt == s.dec_utt && M <= 64 && at.dh == 64 && tc_linear_supported(o) && getenv("MGB_NO_CHAIN") == nullptr) {
+            at.pack_out = s.tc_scratch; o.x_prepacked = true;
+        }
+        if (!launch_attention(at, s.stream)) return false;
         if (!launch_linear(o, s.stream)) return false;
         // cross-attention over the cached encoder K/V (no mask); a batched decoder step (one token per utterance) uses
         // the folded tables: one launch instead of LN+pack, q GEMM, attention, pack, o GEMM
-        if (s.fold_ready && M == s.B && tok.utt == s.dec_utt) {
+        // a batched decoder step on the tensor-core path chains the packed activations through the kernels: the folded
+        // cross-attention emits LN(x) for FF1, FF1's epilogue emits GELU(h) for FF2 (no separate packing kernels)
+        LinearArgs f1;
+        f1.tc_scratch = s.tc_scratch; f1.tc_scratch_bytes = s.tc_scratch_bytes;
+        f1.precision = m.precision; f1.eps = hp.eps; f1.gelu_f16 = m.gelu_f16; f1.M = M; f1.W = L.ff1; f1.X = s.x; f1.ldx = d;
+        f1.ln_w = L.norm_ff; f1.act = ACT_GELU; f1.Y = s.ffh; f1.ldy = hp.d_ffn;
+        LinearArgs f2;
+        f2.tc_scratch = s.tc_scratch; f2.tc_scratch_bytes = s.tc_scratch_bytes;
+        f2.precision = m.precision; f2.M = M; f2.W = L.ff2; f2.X = s.ffh; f2.ldx = hp.d_ffn; f2.res = s.x; f2.ldr = d; f2.Y = s.x; f2.ldy = d;
+        const bool step = M == s.B && tok.utt == s.dec_utt;
+        const bool chain = step && M <= 64 && s.tc_scratch2 && tc_linear_supported(f1) && tc_linear_supported(f2) && hp.d_ffn % 64 == 0 &&
+                           getenv("MGB_NO_CHAIN") == nullptr;
+        if (s.fold_ready && step) {
             const size_t tab = (size_t)s.B * s.max_text * d;
-            if (!launch_xattn_folded(s.x, L.norm_xa_q, hp.eps, s.fold_xm + l * tab, s.fold_xn + l * tab, s.d_ntext, s.B, d, s.max_text, s.stream)) return false;
+            const bool pk = chain;
+            if (!launch_xattn_folded(s.x, L.norm_xa_q, hp.eps, s.fold_xm + l * tab, s.fold_xn + l * tab, s.d_ntext, s.B, d, s.max_text,
+                                     pk ? L.norm_ff : nullptr, pk ? s.tc_scratch : nullptr, s.stream)) return false;
+            if (pk) f1.x_prepacked = true;
         } else {
         LinearArgs q;
         q.tc_scratch = s.tc_scratch; q.tc_scratch_bytes = s.tc_scratch_bytes;
@@ -134,14 +154,8 @@ static bool decoder_layers(Session & s, Tokens tok, bool want_hidden) {
         if (!launch_linear(xo, s.stream)) return false;
         }
         // conv-FFN (kernel 1): LN -> W1 -> GELU -> W2 + residual
-        LinearArgs f1;
-        f1.tc_scratch = s.tc_scratch; f1.tc_scratch_bytes = s.tc_scratch_bytes;
-        f1.precision = m.precision; f1.eps = hp.eps; f1.gelu_f16 = m.gelu_f16; f1.M = M; f1.W = L.ff1; f1.X = s.x; f1.ldx = d;
-        f1.ln_w = L.norm_ff; f1.act = ACT_GELU; f1.Y = s.ffh; f1.ldy = hp.d_ffn;
+        if (chain) { f1.pack_out = s.tc_scratch2; f1.Y = nullptr; f2.tc_scratch = s.tc_scratch2; f2.x_prepacked = true; }
         if (!launch_linear(f1, s.stream)) return false;
-        LinearArgs f2;
-        f2.tc_scratch = s.tc_scratch; f2.tc_scratch_bytes = s.tc_scratch_bytes;
-        f2.precision = m.precision; f2.M = M; f2.W = L.ff2; f2.X = s.ffh; f2.ldx = hp.d_ffn; f2.res = s.x; f2.ldr = d; f2.Y = s.x; f2.ldy = d;
         if (!launch_linear(f2, s.stream)) return false;
     }
     if (want_hidden) return launch_layer_norm(s.x, m.dec_norm_out, hp.eps, M, d, s.hidden, s.stream);
@@ -292,6 +306,9 @@ mgb_session * mgb_session_new(mgb_model * mm, int batch, int max_text, int max_s
         char * tp = nullptr;
         if (!s->alloc(tp, tb)) return nullptr;
         s->tc_scratch = tp; s->tc_scratch_bytes = tb;
+        char * tp2 = nullptr;
+        if (!s->alloc(tp2, tb)) return nullptr;
+        s->tc_scratch2 = tp2;
     }
     if (m->precision == MGB_PREC_BF16 && batch >= 2 && dxa == 128 && getenv("MGB_NO_XFOLD") == nullptr &&
         (size_t)L * batch * max_text * d * 8 <= ((size_t)8 << 30)) {

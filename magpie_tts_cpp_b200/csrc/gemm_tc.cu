@@ -84,6 +84,7 @@ struct TcEpi {
     float * Y; int ldy;
     int act, gelu_f16;
     int n_q, dkv; bf * kdst; bf * vdst; const int32_t * tok_slot;
+    bf * pk_hi; bf * pk_lo;          // optional: the output as hi / lo tile images [N/64][64 x 64] for a following GEMM over K' = N (M <= 64)
 };
 
 // SPLIT > 1: split-K over a thread-block cluster of SPLIT CTAs (cluster dims 1 x 1 x SPLIT, rank = blockIdx.z).  Every CTA
@@ -92,8 +93,18 @@ struct TcEpi {
 // bound by how fast ONE SM can ingest its CTA's weight + activation tiles, so the split shortens the critical path.
 template <int SPLIT> struct StageCap { static constexpr int value = SPLIT == 1 ? 8 : (SPLIT == 2 ? 5 : 3); };
 
-template <int MT, int SPLIT>
+// EPI specialises the epilogue so that a decoder-step GEMM carries only the code it runs (these launches are latency
+// bound and start with cold instruction caches: code size is time): 0 = generic, 1 = q | K | V split store (no
+// activation / residual), 2 = residual add into an f32 row, 3 = GELU + packed hi | lo output for the next GEMM.
+enum { EPI_GENERIC = 0, EPI_QKV = 1, EPI_RES = 2, EPI_GELU_PACK = 3 };
+
+template <int MT, int SPLIT, int EPI>
 __global__ void __launch_bounds__(tc::kThreads, 1) tc_linear_kernel(const bf * Wt, const bf * Xhi, const bf * Xlo, int KT, const TcEpi e) {
+    constexpr bool kRes = EPI == EPI_GENERIC || EPI == EPI_RES;
+    constexpr bool kAct = EPI == EPI_GENERIC || EPI == EPI_GELU_PACK;
+    constexpr bool kPack = EPI == EPI_GENERIC || EPI == EPI_GELU_PACK;
+    constexpr bool kSplitStore = EPI == EPI_GENERIC || EPI == EPI_QKV;
+    constexpr bool kPlainStore = EPI != EPI_GELU_PACK;
     extern __shared__ unsigned char tc_smem[];
     constexpr int SCAP = StageCap<SPLIT>::value;
     const int nt = blockIdx.x, mt = blockIdx.y;
@@ -138,8 +149,8 @@ __global__ void __launch_bounds__(tc::kThreads, 1) tc_linear_kernel(const bf * W
             if (n < e.N) {
                 // residual values first (Y may alias res for the in-place x += W h updates, which would otherwise
                 // serialise 32 dependent load -> store round trips)
-                float r[32];
-                if (e.res) {
+                float r[kRes ? 32 : 1];
+                if (kRes && e.res) {
 #pragma unroll
                     for (int j = 0; j < 32; j++) {
                         const int m = mt * MT + c + j;
@@ -151,9 +162,16 @@ __global__ void __launch_bounds__(tc::kThreads, 1) tc_linear_kernel(const bf * W
                     const int m = mt * MT + c + j;
                     if (m < e.M) {
                         float y = __uint_as_float(v[j]) + bias;
-                        if (e.act == ACT_GELU) y = gelu_ggml(y, e.gelu_f16);
-                        if (e.res) y += r[j];
-                        if (e.n_q < 0 || n < e.n_q) e.Y[(size_t)m * e.ldy + n] = y;
+                        if (kAct && (EPI == EPI_GELU_PACK || e.act == ACT_GELU)) y = gelu_ggml(y, e.gelu_f16);
+                        if (kRes && e.res) y += r[j];
+                        if (kPack && (EPI == EPI_GELU_PACK || e.pk_hi)) {
+                            const bf h = __float2bfloat16_rn(y);
+                            const size_t off = (size_t)(n >> 6) * (64 * 128) + tc::swz_offset(m, n & 63);
+                            *reinterpret_cast<bf *>(reinterpret_cast<unsigned char *>(e.pk_hi) + off) = h;
+                            *reinterpret_cast<bf *>(reinterpret_cast<unsigned char *>(e.pk_lo) + off) = __float2bfloat16_rn(y - __bfloat162float(h));
+                        }
+                        if (!kPlainStore || !e.Y) continue;
+                        if (!kSplitStore || e.n_q < 0 || n < e.n_q) e.Y[(size_t)m * e.ldy + n] = y;
                         else {
                             const size_t slot = (size_t)e.tok_slot[m] * e.dkv;
                             const int cc = n - e.n_q;
@@ -168,7 +186,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) tc_linear_kernel(const bf * W
     tc::finish<MT>(tmem);
 }
 
-template <int MT, int SPLIT> bool launch_tc(const bf * Wt, const bf * hi, const bf * lo, int KT, const TcEpi & e, cudaStream_t stream) {
+template <int MT, int SPLIT, int EPI> bool launch_tc(const bf * Wt, const bf * hi, const bf * lo, int KT, const TcEpi & e, cudaStream_t stream) {
     static uint64_t attr_done = 0;
     int dev = 0;
     MGB_CUDA_TRY(cudaGetDevice(&dev));
@@ -176,7 +194,7 @@ template <int MT, int SPLIT> bool launch_tc(const bf * Wt, const bf * hi, const 
     constexpr int smem = tc::Smem<MT, 2, SCAP>::kBytes + (SPLIT - 1) * MT * 128 * 4;
     static_assert(smem <= 227 * 1024, "tc_linear shared memory");
     if (!(attr_done >> dev & 1)) {
-        MGB_CUDA_TRY(cudaFuncSetAttribute(tc_linear_kernel<MT, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        MGB_CUDA_TRY(cudaFuncSetAttribute(tc_linear_kernel<MT, SPLIT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_done |= 1ull << dev;
     }
     // launched as a programmatic dependent of the activation-packing kernel: CTAs start (and prefetch weight tiles)
@@ -190,7 +208,7 @@ template <int MT, int SPLIT> bool launch_tc(const bf * Wt, const bf * hi, const 
     at[1].id = cudaLaunchAttributeClusterDimension;
     at[1].val.clusterDim.x = 1; at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = SPLIT;
     cfg.attrs = at; cfg.numAttrs = SPLIT > 1 ? 2 : 1;
-    MGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc_linear_kernel<MT, SPLIT>, Wt, hi, lo, KT, e));
+    MGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc_linear_kernel<MT, SPLIT, EPI>, Wt, hi, lo, KT, e));
     MGB_LAUNCH_CHECK();
     return true;
 }
@@ -218,21 +236,39 @@ bool launch_linear_tc(const LinearArgs & a, cudaStream_t stream) {
     const int Mpad = (M + MT - 1) / MT * MT;
     bf * hi = (bf *)a.tc_scratch;
     bf * lo = hi + (size_t)Mpad * K;
-    pack_x_kernel<<<Mpad, 256, 0, stream>>>(a.X, a.ldx, M, K, a.ln_w, a.eps, MT, hi, lo);
-    MGB_LAUNCH_CHECK();
+    if (!a.x_prepacked) {
+        pack_x_kernel<<<Mpad, 256, 0, stream>>>(a.X, a.ldx, M, K, a.ln_w, a.eps, MT, hi, lo);
+        MGB_LAUNCH_CHECK();
+    }
     TcEpi e;
+    e.pk_hi = nullptr; e.pk_lo = nullptr;
+    if (a.pack_out) {
+        if (M > 64 || a.W.N % 64 != 0 || a.n_q >= 0) { set_error("linear: packed output needs one token tile and N % 64 == 0"); return false; }
+        e.pk_hi = (bf *)a.pack_out; e.pk_lo = e.pk_hi + (size_t)64 * a.W.N;
+    }
     e.N = a.W.N; e.M = M; e.bias = a.bias; e.res = a.res; e.ldr = a.ldr; e.Y = a.Y; e.ldy = a.ldy; e.act = a.act; e.gelu_f16 = a.gelu_f16;
     e.n_q = a.n_q; e.dkv = a.dkv; e.kdst = (bf *)a.kdst; e.vdst = (bf *)a.vdst; e.tok_slot = a.tok_slot;
     if (MT == 64) {
         // one token tile: split K over a cluster (deterministic DSMEM reduction) to shorten the per-SM ingest chain
         const int KT = K / 64;
         static const bool no_split = getenv("MGB_NO_SPLITK") != nullptr;
-        static const bool all4 = getenv("MGB_SPLITK4") != nullptr;
-        if (!no_split && (KT >= 32 || (all4 && KT >= 8))) return launch_tc<64, 4>((const bf *)a.W.tiles, hi, lo, KT, e, stream);
-        if (!no_split && KT >= 8) return launch_tc<64, 2>((const bf *)a.W.tiles, hi, lo, KT, e, stream);
-        return launch_tc<64, 1>((const bf *)a.W.tiles, hi, lo, KT, e, stream);
+        const bf * W = (const bf *)a.W.tiles;
+        const bool qkv = a.n_q >= 0 && !a.res && a.act == ACT_NONE && !a.pack_out;
+        const bool resid = a.n_q < 0 && a.res && a.act == ACT_NONE && !a.pack_out && a.Y;
+        const bool gpack = a.n_q < 0 && !a.res && a.act == ACT_GELU && a.pack_out && !a.Y;
+        if (!no_split && KT >= 32) {
+            if (resid) return launch_tc<64, 4, EPI_RES>(W, hi, lo, KT, e, stream);
+            return launch_tc<64, 4, EPI_GENERIC>(W, hi, lo, KT, e, stream);
+        }
+        if (!no_split && KT >= 8) {
+            if (qkv) return launch_tc<64, 2, EPI_QKV>(W, hi, lo, KT, e, stream);
+            if (resid) return launch_tc<64, 2, EPI_RES>(W, hi, lo, KT, e, stream);
+            if (gpack) return launch_tc<64, 2, EPI_GELU_PACK>(W, hi, lo, KT, e, stream);
+            return launch_tc<64, 2, EPI_GENERIC>(W, hi, lo, KT, e, stream);
+        }
+        return launch_tc<64, 1, EPI_GENERIC>(W, hi, lo, KT, e, stream);
     }
-    return launch_tc<128, 1>((const bf *)a.W.tiles, hi, lo, K / 64, e, stream);
+    return launch_tc<128, 1, EPI_GENERIC>((const bf *)a.W.tiles, hi, lo, K / 64, e, stream);
 }
 
 }  // namespace mgb

@@ -37,6 +37,8 @@ struct LinearArgs {
     const int32_t * tok_slot = nullptr;
     int M = 0;
     void * tc_scratch = nullptr; size_t tc_scratch_bytes = 0;     // activation tile images of the tensor-core path (gemm_tc.cu)
+    bool x_prepacked = false;        // tc_scratch already holds the hi | lo tile images of X (written by the producing kernel)
+    void * pack_out = nullptr;       // tensor-core path, M <= 64: write the output as hi | lo tile images here (Y may be null)
 };
 bool launch_linear(const LinearArgs & a, cudaStream_t stream);
 // tcgen05 path (bf16, >= 16 tokens): gemm_tc.cu
@@ -56,11 +58,13 @@ struct AttnArgs {
     const int32_t * n_ctx = nullptr;
     Tokens tok;
     float * out = nullptr; int ldo = 0;
+    void * pack_out = nullptr;                   // dh == 64, <= 64 tokens: write hi | lo tile images for the next GEMM instead of `out`
 };
 bool launch_attention(const AttnArgs & a, cudaStream_t stream);
 // batched decoder step: folded cross-attention x += softmax(M LN(x)) N (tables from launch_xattn_fold, frame_loop.cu)
+// pack_ln_w / pack_out (optional, B <= 64): additionally emit LN(x_new; pack_ln_w) as hi | lo tile images for the next GEMM
 bool launch_xattn_folded(float * x, const float * ln_w, float eps, const float * xm, const float * xn, const int32_t * n_ctx, int B, int d,
-                         int max_text, cudaStream_t stream);
+                         int max_text, const float * pack_ln_w, void * pack_out, cudaStream_t stream);
 
 // x[t] = (sum_cb E_cb[codes[utt][cb]]) * 1/8 + dec_pos[pos]        (magpie.cpp:2746-2787, 4376-4379)
 bool launch_audio_embed(const Model & m, const int32_t * codes /*[B][8] device*/, const int32_t * pos /*[B]*/,

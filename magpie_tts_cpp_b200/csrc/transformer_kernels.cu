@@ -166,9 +166,10 @@ struct AttnParams {
     const int32_t * n_ctx;
     const int32_t * utt; const int32_t * pos;
     float * out; int ldo;
+    __nv_bfloat16 * pk_hi; __nv_bfloat16 * pk_lo;      // optional (DH == 64, <= 64 tokens): output as hi | lo tile images for the next GEMM
 };
 
-constexpr int kAttnWarps = 4;
+constexpr int kAttnWarps = 8;
 
 // grid (H, M), 128 threads.  A key/value row of one head (DH elements) is read by LPK = DH / VEC adjacent lanes with one
 // 16-byte load each (fully used sectors), so a warp instruction covers 32 / LPK keys; each lane group keeps its own online
@@ -274,7 +275,16 @@ __global__ void __launch_bounds__(kAttnWarps * 32) attention_kernel(const AttnPa
             L += f * s_l[w];
             o += f * s_acc[w][tid];
         }
-        p.out[(size_t)t * p.ldo + h * DH + tid] = o * (1.0f / L);
+        const float y = o * (1.0f / L);
+        if (p.pk_hi) {
+            // head h is exactly k tile h of the following GEMM (64 columns = one 128-byte swizzle row): gemm_tc.cu layout
+            const __nv_bfloat16 hv = __float2bfloat16_rn(y);
+            const size_t off = (size_t)h * (64 * 128) + (size_t)t * 128 + (((((tid >> 3) ^ (t & 7)) & 7) << 4) + ((tid & 7) << 1));
+            *reinterpret_cast<__nv_bfloat16 *>(reinterpret_cast<unsigned char *>(p.pk_hi) + off) = hv;
+            *reinterpret_cast<__nv_bfloat16 *>(reinterpret_cast<unsigned char *>(p.pk_lo) + off) = __float2bfloat16_rn(y - __bfloat162float(hv));
+        } else {
+            p.out[(size_t)t * p.ldo + h * DH + tid] = y;
+        }
     }
 }
 
@@ -351,6 +361,11 @@ bool launch_attention(const AttnArgs & a, cudaStream_t stream) {
     AttnParams p;
     p.q = a.q; p.ldq = a.ldq; p.K = a.K; p.V = a.V; p.rows_per_utt = a.rows_per_utt; p.H = a.H;
     p.causal = a.causal; p.n_ctx = a.n_ctx; p.utt = a.tok.utt; p.pos = a.tok.pos; p.out = a.out; p.ldo = a.ldo;
+    p.pk_hi = nullptr; p.pk_lo = nullptr;
+    if (a.pack_out) {
+        if (a.dh != 64 || a.tok.M > 64) { set_error("attention: packed output needs head dim 64 and one token tile"); return false; }
+        p.pk_hi = (__nv_bfloat16 *)a.pack_out; p.pk_lo = p.pk_hi + (size_t)64 * a.H * a.dh;
+    }
     dim3 grid(a.H, a.tok.M);
     const bool f32 = a.precision == MGB_PREC_F32;
     if (a.dh == 64) {
@@ -368,7 +383,8 @@ bool launch_attention(const AttnArgs & a, cudaStream_t stream) {
 // x_u += softmax(M_u LN(x_u; w)) N_u with the per-utterance tables M = scale K Wq (E x d) and N = V Wo^T (E x d) built at
 // prefill (frame_loop.cu xattn_fold_kernel): the reference's q_net GEMV, 1-head attention over E text tokens and o_net GEMV
 // (magpie.cpp:1713-1767, 3513) in ONE launch instead of five.  One CTA per utterance, 512 threads.
-struct XFoldParams { float * x; const float * ln_w; float eps; const float * xm; const float * xn; const int32_t * n_ctx; int d, max_text; };
+struct XFoldParams { float * x; const float * ln_w; float eps; const float * xm; const float * xn; const int32_t * n_ctx; int d, max_text;
+                     const float * pack_ln_w; __nv_bfloat16 * pk_hi; __nv_bfloat16 * pk_lo; };
 __global__ void __launch_bounds__(512) xattn_folded_kernel(const XFoldParams p) {
     __shared__ float xl[1024];
     __shared__ float sc[512];
@@ -402,17 +418,44 @@ __global__ void __launch_bounds__(512) xattn_folded_kernel(const XFoldParams p) 
     float sum = 0.0f;
     for (int j = 0; j < E; j++) sum += expf(sc[j] - mx);
     const float inv = 1.0f / sum;
+    float s3 = 0.0f;
     for (int i = tid; i < d; i += 512) {
         float o = 0.0f;
         for (int j = 0; j < E; j++) o = fmaf(expf(sc[j] - mx) * inv, xn[(size_t)j * d + i], o);
-        xr[i] += o;
+        const float v = xr[i] + o;
+        xr[i] = v;
+        if (p.pk_hi) { xl[i] = v; s3 += v; }       // xl is free: its last readers (the score dots) finished before the barrier above
+    }
+    if (!p.pk_hi) return;
+    // LayerNorm of the updated row with the NEXT sub-block's weight, emitted as bf16 hi | lo tile images (gemm_tc.cu layout,
+    // 64-token tile): replaces the separate packing kernel in front of the FFN's first GEMM
+    const float mean2 = block_sum(s3, red) / (float)d;
+    float s4 = 0.0f;
+    for (int i = tid; i < d; i += 512) { const float c = xl[i] - mean2; s4 += c * c; }
+    const float scale2 = 1.0f / sqrtf(block_sum(s4, red) / (float)d + p.eps);
+    for (int kc = tid; kc < d / 8; kc += 512) {
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int i0 = kc * 8 + 2 * q;
+            const float v0 = ((xl[i0] - mean2) * scale2) * p.pack_ln_w[i0], v1 = ((xl[i0 + 1] - mean2) * scale2) * p.pack_ln_w[i0 + 1];
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+            const __nv_bfloat16 l0 = __float2bfloat16_rn(v0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(v1 - __bfloat162float(h1));
+            h[q] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+            l[q] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+        }
+        const size_t off = (size_t)(kc / 8) * (64 * 128) + (size_t)u * 128 + ((((kc % 8) ^ (u & 7)) & 7) << 4);
+        *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(p.pk_hi) + off) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(p.pk_lo) + off) = make_uint4(l[0], l[1], l[2], l[3]);
     }
 }
 
 bool launch_xattn_folded(float * x, const float * ln_w, float eps, const float * xm, const float * xn, const int32_t * n_ctx, int B, int d,
-                         int max_text, cudaStream_t stream) {
-    if (d > 1024 || max_text > 512) { set_error("xattn_folded: shape not supported"); return false; }
-    XFoldParams p{x, ln_w, eps, xm, xn, n_ctx, d, max_text};
+                         int max_text, const float * pack_ln_w, void * pack_out, cudaStream_t stream) {
+    if (d > 1024 || max_text > 512 || d % 64 != 0) { set_error("xattn_folded: shape not supported"); return false; }
+    if (pack_out && B > 64) { set_error("xattn_folded: packed output needs one token tile"); return false; }
+    XFoldParams p{x, ln_w, eps, xm, xn, n_ctx, d, max_text, pack_ln_w, (__nv_bfloat16 *)pack_out,
+                  pack_out ? (__nv_bfloat16 *)pack_out + (size_t)64 * d : nullptr};
     xattn_folded_kernel<<<B, 512, 0, stream>>>(p);
     MGB_LAUNCH_CHECK();
     return true;
