@@ -3,8 +3,8 @@
 // Same arithmetic as lt_kernel.cu (reference src/magpie.cpp:946-1048 LT layer, 1072-1109 sample_top_k, 1113-1317
 // magpie_local_transformer_sample_all), different parallelisation.  lt_kernel runs one cluster per utterance and
 // re-streams the 10 MB of LT weights from L2 for every utterance (64 utterances: 0.66 GB per step, 764 us).  Here every
-// CTA keeps a fixed slice of the rows of EVERY LT matrix in shared memory for the whole launch (10.3 MB bf16 / 148 CTAs
-// = 70 KB), and each phase computes those rows for ALL utterances from an activation tile staged through shared memory:
+// CTA keeps a fixed slice of the rows of EVERY LT matrix in shared memory for the whole launch (10.3 MB bf16 / 148 CTAs,
+// kept as f32: 141 KB), and each phase computes those rows for ALL utterances from an activation tile staged through shared memory:
 // each weight element is read from HBM/L2 once per step, the 8 x 7 dependent phases are separated by grid barriers.
 //
 //   per codebook:  QKV (LN prologue) | attention (utterance-owner CTAs) | O + residual | FF1 (LN prologue, GELU) |
@@ -28,6 +28,7 @@ constexpr int kTileFloats = 64 * 260;          // activation tile staged per pas
 struct BParams {
     LtParams p;
     float * seq, * q, * kc, * vc, * att, * x1, * ffh, * hout, * logits;     // [B][..] f32 scratch
+    unsigned long long * dbg;        // MGB_LT_DBG: globaltimer stamps of CTA 0 at every phase boundary
 };
 
 struct Slice { int n0, n1; };
@@ -44,11 +45,16 @@ struct SampSmem {
 };
 static_assert(sizeof(SampSmem) <= kTileFloats * 4, "sampler scratch must fit the activation tile");
 
-// rows [n0, n1) of W (bf16 [N][K], row-major) -> shared memory, 16-byte copies
-__device__ __forceinline__ void load_rows(bf * dst, const void * W, int K, Slice s) {
+// rows [n0, n1) of W (bf16 [N][K], row-major) -> shared memory as f32 (converted once per launch: the inner loops then
+// issue one 16-byte broadcast load per 4 weights and no conversions)
+__device__ __forceinline__ void load_rows(float * dst, const void * W, int K, Slice s) {
     const uint4 * src = reinterpret_cast<const uint4 *>(reinterpret_cast<const bf *>(W) + (size_t)s.n0 * K);
     const int n16 = (s.n1 - s.n0) * K / 8;
-    for (int i = threadIdx.x; i < n16; i += kLtThreads) reinterpret_cast<uint4 *>(dst)[i] = src[i];
+    for (int i = threadIdx.x; i < n16; i += kLtThreads) {
+        const uint4 v = src[i];
+        reinterpret_cast<float4 *>(dst)[2 * i] = make_float4(bf16lo(v.x), bf16hi(v.x), bf16lo(v.y), bf16hi(v.y));
+        reinterpret_cast<float4 *>(dst)[2 * i + 1] = make_float4(bf16lo(v.z), bf16hi(v.z), bf16lo(v.w), bf16hi(v.w));
+    }
 }
 
 // One GEMV phase: for every utterance u and every row n of this CTA's slice, epi(u, n, sum_k W[n][k] * X[u][k]).
@@ -59,7 +65,7 @@ __device__ __forceinline__ void load_rows(bf * dst, const void * W, int K, Slice
 constexpr int kKC = 256, kKS = kKC + 4, kUB = 64;
 static_assert(kUB * kKS <= kTileFloats, "stage tile");
 template <bool PREP, typename Prep, typename Epi>
-__device__ __forceinline__ void gemv_phase(const bf * Ws, Slice s, int K, const float * X, int ldx, int B, float * tile, Prep prep, Epi epi) {
+__device__ __forceinline__ void gemv_phase(const float * Ws, Slice s, int K, const float * X, int ldx, int B, float * tile, Prep prep, Epi epi) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ug = warp & 1, rw = warp >> 1;
     const int R = s.n1 - s.n0;
@@ -79,17 +85,17 @@ __device__ __forceinline__ void gemv_phase(const bf * Ws, Slice s, int K, const 
             }
             if (rw < R && ug * 32 < nu) {
                 const float * xr = tile + (ug * 32 + min(lane, nu - ug * 32 - 1)) * kKS;      // lanes past the batch repeat the last row
-                const bf * w0 = Ws + (size_t)rw * K + kc;
+                const float * w0 = Ws + (size_t)rw * K + kc;
                 const bool two = rw + 8 < R;
-                const bf * w1 = two ? w0 + (size_t)8 * K : w0;
+                const float * w1 = two ? w0 + (size_t)8 * K : w0;
 #pragma unroll 4
                 for (int k = 0; k < kKC; k += 4) {
                     const float4 x = *reinterpret_cast<const float4 *>(xr + k);
-                    const uint2 a = *reinterpret_cast<const uint2 *>(w0 + k), b = *reinterpret_cast<const uint2 *>(w1 + k);
-                    acc[0] = fmaf(bf16lo(a.x), x.x, acc[0]); acc[0] = fmaf(bf16hi(a.x), x.y, acc[0]);
-                    acc[0] = fmaf(bf16lo(a.y), x.z, acc[0]); acc[0] = fmaf(bf16hi(a.y), x.w, acc[0]);
-                    acc[1] = fmaf(bf16lo(b.x), x.x, acc[1]); acc[1] = fmaf(bf16hi(b.x), x.y, acc[1]);
-                    acc[1] = fmaf(bf16lo(b.y), x.z, acc[1]); acc[1] = fmaf(bf16hi(b.y), x.w, acc[1]);
+                    const float4 a = *reinterpret_cast<const float4 *>(w0 + k), b = *reinterpret_cast<const float4 *>(w1 + k);
+                    acc[0] = fmaf(a.x, x.x, acc[0]); acc[0] = fmaf(a.y, x.y, acc[0]);
+                    acc[0] = fmaf(a.z, x.z, acc[0]); acc[0] = fmaf(a.w, x.w, acc[0]);
+                    acc[1] = fmaf(b.x, x.x, acc[1]); acc[1] = fmaf(b.y, x.y, acc[1]);
+                    acc[1] = fmaf(b.z, x.z, acc[1]); acc[1] = fmaf(b.w, x.w, acc[1]);
                 }
             }
         }
@@ -101,16 +107,21 @@ __device__ __forceinline__ void gemv_phase(const bf * Ws, Slice s, int K, const 
     }
 }
 
-// in-place LayerNorm of one staged row by one warp (magpie.cpp:2237-2259: mean, centred variance, * weight)
-__device__ __forceinline__ void warp_layer_norm(float * row, int n, const float * w, float eps) {
+// in-place LayerNorm of one staged row of kKC = 256 values by one warp (magpie.cpp:2237-2259: mean, centred variance,
+// * weight).  Lane l owns elements l, l + 32, ...; `add` (position embedding or zeros) and the weights `w` are the lane's
+// 8 values, fetched ONCE per phase by the caller so that no global load sits on the per-row dependency chain.
+__device__ __forceinline__ void warp_layer_norm(float * row, const float (&add)[8], const float (&w)[8], float eps) {
     const int lane = threadIdx.x & 31;
-    float s = 0.0f;
-    for (int i = lane; i < n; i += 32) s += row[i];
-    const float mean = warp_sum(s) / (float)n;
+    float v[8], s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 8; k++) { v[k] = row[lane + 32 * k] + add[k]; s += v[k]; }
+    const float mean = warp_sum(s) * (1.0f / 256.0f);
     float s2 = 0.0f;
-    for (int i = lane; i < n; i += 32) { const float c = row[i] - mean; s2 += c * c; }
-    const float scale = 1.0f / sqrtf(warp_sum(s2) / (float)n + eps);
-    for (int i = lane; i < n; i += 32) row[i] = ((row[i] - mean) * scale) * w[i];
+#pragma unroll
+    for (int k = 0; k < 8; k++) { v[k] -= mean; s2 += v[k] * v[k]; }
+    const float scale = 1.0f / sqrtf(warp_sum(s2) * (1.0f / 256.0f) + eps);
+#pragma unroll
+    for (int k = 0; k < 8; k++) row[lane + 32 * k] = (v[k] * scale) * w[k];
     __syncwarp();
 }
 
@@ -122,17 +133,17 @@ __global__ void __launch_bounds__(kLtThreads, 1) lt_batch_kernel(const BParams b
     const int B = p.B, d = p.d, L = p.L, F = p.F, V = p.V;
     float * tile = reinterpret_cast<float *>(smem_raw);
     SampSmem & S = *reinterpret_cast<SampSmem *>(smem_raw);
-    bf * wbase = reinterpret_cast<bf *>(smem_raw + (size_t)kTileFloats * 4);
+    float * wbase = reinterpret_cast<float *>(smem_raw + (size_t)kTileFloats * 4);
 
     // ---- this CTA's row slices of every matrix, resident for the whole launch ----
     const Slice s_in = slice_of(L, c, G), s_qkv = slice_of(3 * L, c, G), s_o = slice_of(L, c, G), s_f1 = slice_of(F, c, G),
                 s_f2 = slice_of(L, c, G), s_out = slice_of(V, c, G);
-    bf * w_in = wbase;
-    bf * w_qkv = w_in + (size_t)(s_in.n1 - s_in.n0) * d;
-    bf * w_o = w_qkv + (size_t)(s_qkv.n1 - s_qkv.n0) * L;
-    bf * w_f1 = w_o + (size_t)(s_o.n1 - s_o.n0) * L;
-    bf * w_f2 = w_f1 + (size_t)(s_f1.n1 - s_f1.n0) * L;
-    bf * w_out0 = w_f2 + (size_t)(s_f2.n1 - s_f2.n0) * F;
+    float * w_in = wbase;
+    float * w_qkv = w_in + (size_t)(s_in.n1 - s_in.n0) * d;
+    float * w_o = w_qkv + (size_t)(s_qkv.n1 - s_qkv.n0) * L;
+    float * w_f1 = w_o + (size_t)(s_o.n1 - s_o.n0) * L;
+    float * w_f2 = w_f1 + (size_t)(s_f1.n1 - s_f1.n0) * L;
+    float * w_out0 = w_f2 + (size_t)(s_f2.n1 - s_f2.n0) * F;
     const size_t out_elems = (size_t)(s_out.n1 - s_out.n0) * L;
     load_rows(w_in, p.in_w, d, s_in);
     load_rows(w_qkv, p.qkv_w, L, s_qkv);
@@ -141,6 +152,12 @@ __global__ void __launch_bounds__(kLtThreads, 1) lt_batch_kernel(const BParams b
     load_rows(w_f2, p.ff2_w, F, s_f2);
     for (int cb = 0; cb < 8; cb++) load_rows(w_out0 + cb * out_elems, p.out_w[cb], L, s_out);
 
+    int n_stamp = 0;
+    auto stamp = [&]() {
+        if (bp.dbg && c == 0 && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); bp.dbg[n_stamp] = t; }
+        n_stamp++;
+    };
+    stamp();
     const bool loop = p.d_step != nullptr;
     const int step = loop ? *p.d_step : (int)p.step;
     const float att_scale = 1.0f / sqrtf((float)L);
@@ -153,7 +170,7 @@ __global__ void __launch_bounds__(kLtThreads, 1) lt_batch_kernel(const BParams b
             const size_t u = i / d, k = i % d;
             p.hidden_hist[((loop ? u * p.T_total + step : u)) * d + k] = p.hidden[i];
         }
-    grid.sync();
+    stamp(); grid.sync(); stamp();
 
     bool hit_eos[8];                       // per owned utterance (utterances c, c + G, ...), thread-uniform
 #pragma unroll
@@ -162,19 +179,17 @@ __global__ void __launch_bounds__(kLtThreads, 1) lt_batch_kernel(const BParams b
     for (int cb = 0; cb < 8; cb++) {
         const float * pos = p.pos + cb * L;
         // q | k | v = qkv_net . LN(seq + pos)   (magpie.cpp:1026-1030, 1501-1503)
+        float ln_add[8], ln_w[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) { ln_add[k] = pos[(tid & 31) + 32 * k]; ln_w[k] = p.norm_self[(tid & 31) + 32 * k]; }
         gemv_phase<true>(w_qkv, s_qkv, L, bp.seq, L, B, tile,
-                   [&](int, float * row) {
-                       const int lane = threadIdx.x & 31;
-                       for (int i = lane; i < L; i += 32) row[i] += pos[i];
-                       __syncwarp();
-                       warp_layer_norm(row, L, p.norm_self, p.eps);
-                   },
+                   [&](int, float * row) { warp_layer_norm(row, ln_add, ln_w, p.eps); },
                    [&](int u, int n, float v) {
                        if (n < L) bp.q[(size_t)u * L + n] = v;
                        else if (n < 2 * L) bp.kc[((size_t)u * 8 + cb) * L + (n - L)] = v;
                        else bp.vc[((size_t)u * 8 + cb) * L + (n - 2 * L)] = v;
                    });
-        grid.sync();
+        stamp(); grid.sync(); stamp();
         // single-head causal attention over positions 0..cb, one owner CTA per utterance (magpie.cpp:946-1013)
         for (int u = c; u < B; u += G) {
             __syncthreads();
@@ -200,27 +215,29 @@ __global__ void __launch_bounds__(kLtThreads, 1) lt_batch_kernel(const BParams b
                 bp.att[(size_t)u * L + tid] = o;
             }
         }
-        grid.sync();
+        stamp(); grid.sync(); stamp();
         // x1 = (seq + pos) + o_net . att
         gemv_phase<false>(w_o, s_o, L, bp.att, L, B, tile, no_prep,
                    [&](int u, int n, float v) { bp.x1[(size_t)u * L + n] = v + (bp.seq[(size_t)u * L + n] + pos[n]); });
-        grid.sync();
+        stamp(); grid.sync(); stamp();
         // ffh = gelu(ff1 . LN(x1))
+#pragma unroll
+        for (int k = 0; k < 8; k++) { ln_add[k] = 0.0f; ln_w[k] = p.norm_ff[(tid & 31) + 32 * k]; }
         gemv_phase<true>(w_f1, s_f1, L, bp.x1, L, B, tile,
-                   [&](int, float * row) { warp_layer_norm(row, L, p.norm_ff, p.eps); },
+                   [&](int, float * row) { warp_layer_norm(row, ln_add, ln_w, p.eps); },
                    [&](int u, int n, float v) { bp.ffh[(size_t)u * F + n] = gelu_ggml(v, p.gelu_f16); });
-        grid.sync();
+        stamp(); grid.sync(); stamp();
         // hout = x1 + ff2 . ffh
         gemv_phase<false>(w_f2, s_f2, F, bp.ffh, F, B, tile, no_prep,
                    [&](int u, int n, float v) { bp.hout[(size_t)u * L + n] = v + bp.x1[(size_t)u * L + n]; });
-        grid.sync();
+        stamp(); grid.sync(); stamp();
         // logits = out_proj[cb] . hout + b   (magpie.cpp:1037-1048)
         {
             const float * ob = p.out_b[cb];
             gemv_phase<false>(w_out0 + cb * out_elems, s_out, L, bp.hout, L, B, tile, no_prep,
                        [&](int u, int n, float v) { bp.logits[(size_t)u * V + n] = v + ob[n]; });
         }
-        grid.sync();
+        stamp(); grid.sync(); stamp();
         // masking, argmax, top-k sampling, feedback embedding: owner CTA per utterance
         int oi = 0;
         for (int u = c; u < B; u += G, oi++) {
@@ -267,16 +284,16 @@ __global__ void __launch_bounds__(kLtThreads, 1) lt_batch_kernel(const BParams b
                 if (tid < L) bp.seq[(size_t)u * L + tid] = p.in_table[cb][(size_t)fed * L + tid];
             }
         }
-        if (cb < 7) grid.sync();
+        if (cb < 7) { stamp(); grid.sync(); stamp(); }
     }
 }
 
 size_t slice_smem_bytes(const Model & m, int G) {
     const mgb_hparams & hp = m.hp;
-    auto rows = [&](int N) { return (size_t)((N + G - 1) / G + 1); };     // upper bound of a balanced slice
+    auto rows = [&](int N) { return (size_t)((N + G - 1) / G); };         // largest balanced slice
     const int L = hp.lt_dim, F = hp.lt_ffn_dim, d = hp.d_model, V = hp.vocab_per_cb;
     size_t e = rows(L) * d + rows(3 * L) * L + rows(L) * L + rows(F) * L + rows(L) * F + 8 * rows(V) * L;
-    return e * sizeof(bf);
+    return e * sizeof(float);
 }
 
 }  // namespace
@@ -315,7 +332,16 @@ bool launch_lt_batch(const Model & m, const LtParams & p, void * scratch, size_t
     const size_t B = p.B, L = p.L, F = p.F, V = p.V;
     float * f = (float *)scratch;
     bp.seq = f; f += B * L; bp.q = f; f += B * L; bp.kc = f; f += B * 8 * L; bp.vc = f; f += B * 8 * L;
-    bp.att = f; f += B * L; bp.x1 = f; f += B * L; bp.ffh = f; f += B * F; bp.hout = f; f += B * L; bp.logits = f;
+    bp.att = f; f += B * L; bp.x1 = f; f += B * L; bp.ffh = f; f += B * F; bp.hout = f; f += B * L; bp.logits = f; f += B * V;
+    static unsigned long long * dbg = nullptr;
+    if (getenv("MGB_LT_DBG") && !dbg) { MGB_CUDA_TRY(cudaMalloc((void **)&dbg, 256 * 8)); MGB_CUDA_TRY(cudaMemset(dbg, 0, 256 * 8)); }
+    bp.dbg = dbg;
+    if (dbg && getenv("MGB_LT_DBG_DUMP")) {
+        unsigned long long h[256];
+        cudaDeviceSynchronize();
+        cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
+        for (int i = 1; i < 256 && h[i]; i++) fprintf(stderr, "lt_batch stamp %3d  +%6llu ns  (%s)\n", i, h[i] - h[i - 1], (i & 1) ? "work" : "sync");
+    }
     void * args[] = {&bp};
     MGB_CUDA_TRY(cudaLaunchCooperativeKernel((void *)lt_batch_kernel, dim3(G), dim3(kLtThreads), args, smem, stream));
     MGB_LAUNCH_CHECK();
