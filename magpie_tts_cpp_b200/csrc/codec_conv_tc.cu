@@ -110,7 +110,7 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 }
 
 // MODE 0: activated image only (first conv of a block); 1: + residual, f32 output and activated image (second conv);
-// 2: + residual, accumulated into the 3-branch mean (last block of a branch), no image
+// 2: + residual, f32 output only (last block of a branch: the 3-branch mean is taken by the consumer, up_tm / post_tm)
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const KParams p) {
     extern __shared__ unsigned char smem_raw[];
@@ -290,15 +290,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const KParams p) {
                 const bool tv = cur.t0 + r * kTile < T;
                 const int r_img = cur.r_img0 + r * kTile;
                 const size_t row_off = cur.row_off + r * tile_stride;
-                float rr[16], ss[MODE == 2 ? 16 : 1];
+                float rr[16];
                 if (MODE != 0) {
 #pragma unroll
                     for (int e = 0; e < 16; e++) rr[e] = rn[e];
-                    if (MODE == 2) {
-#pragma unroll
-                        for (int e = 0; e < 16; e++) ss[e] = 0.0f;
-                        if (p.a.sum_mode >= 2 && tv) { ldg256(p.a.sum_in + row_off + u * 16, ss); ldg256(p.a.sum_in + row_off + u * 16 + 8, ss + 8); }
-                    }
                     // prefetch the residual of the next unit (of this item, else the first one of the next item)
                     if (w + 1 < w_end) res_fetch(cur, tile, w + 1);
                     else if (w_lo < min(w_hi, nxt.rt * n16)) res_fetch(nxt, tile + gridDim.x, w_lo);
@@ -356,12 +351,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const KParams p) {
                     }
                 }
                 if (MODE != 0 && tv) {
-                    if (MODE == 2) {
-                        const float sc = p.a.sum_mode == 3 ? (1.0f / 3.0f) : 1.0f;
-#pragma unroll
-                        for (int e = 0; e < 16; e++) y[e] = (ss[e] + y[e]) * sc;
-                    }
-                    float * yp = (MODE == 1 ? p.a.y : p.a.sum_out) + row_off + u * 16;
+                    float * yp = p.a.y + row_off + u * 16;
                     stg256f(yp, y); stg256f(yp + 8, y + 8);
                 }
             }
@@ -437,11 +427,18 @@ __global__ void __launch_bounds__(128) up_tm_kernel(const UpKParams p) {
     float a_cur[16], a_prev[16];
     auto load_act = [&](int t, float * out) {
         const bool ok = t >= 0 && t < p.a.T && g0 < Cout;
-        const float * xr = p.a.x + ((size_t)b * p.a.T + (ok ? t : 0)) * p.cs_in + 2 * g0;
+        const size_t xo = ((size_t)b * p.a.T + (ok ? t : 0)) * p.cs_in + 2 * g0;
 #pragma unroll
         for (int q4 = 0; q4 < 4; q4++) {
             float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ok && 2 * g0 + 4 * q4 < p.cs_in) f = *reinterpret_cast<const float4 *>(xr + 4 * q4);
+            if (ok && 2 * g0 + 4 * q4 < p.cs_in) {
+                f = *reinterpret_cast<const float4 *>(p.a.x[0] + xo + 4 * q4);
+                if (p.a.n_x == 3) {        // input = mean of the previous stage's three residual branches (nano-codec.cpp:601-641)
+                    const float4 g = *reinterpret_cast<const float4 *>(p.a.x[1] + xo + 4 * q4), h = *reinterpret_cast<const float4 *>(p.a.x[2] + xo + 4 * q4);
+                    f.x = ((f.x + g.x) + h.x) * (1.0f / 3.0f); f.y = ((f.y + g.y) + h.y) * (1.0f / 3.0f);
+                    f.z = ((f.z + g.z) + h.z) * (1.0f / 3.0f); f.w = ((f.w + g.w) + h.w) * (1.0f / 3.0f);
+                }
+            }
             out[4 * q4] = f.x; out[4 * q4 + 1] = f.y; out[4 * q4 + 2] = f.z; out[4 * q4 + 3] = f.w;
         }
 #pragma unroll
@@ -485,24 +482,42 @@ __global__ void __launch_bounds__(128) up_tm_kernel(const UpKParams p) {
 
 // HalfSnake -> causal conv (C -> 1, K taps, operands rounded to f16 as ggml_conv_1d does) -> tanh  (nano-codec.cpp:703-712)
 struct PostKParams { PostArgs a; int cs; };
+// block = 256 consecutive time steps of one utterance (+ K-1 history rows): every thread activates ITS row once
+// (3-branch mean -> HalfSnake -> f16 rounding) into shared memory, then takes the K-tap dot product from there.
+constexpr int kPostCS = 32;               // channels per row (27 used)
 __global__ void __launch_bounds__(256) post_tm_kernel(const PostKParams p) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (size_t)p.a.B * p.a.T) return;
-    const int t = (int)(i % p.a.T);
-    float acc = 0.0f;
-    for (int k = 0; k < p.a.K; k++) {
-        const int tt = t - (p.a.K - 1 - k);
-        if (tt < 0) continue;
-        const float * xr = p.a.x + (i - (size_t)(t - tt)) * p.cs;
+    __shared__ float sa[(256 + 8) * (kPostCS + 1)];
+    __shared__ float sw[kPostCS * 8];
+    const int b = blockIdx.y, t0 = blockIdx.x * 256, tid = threadIdx.x;
+    const int H = p.a.K - 1;              // history rows
+    for (int i = tid; i < p.a.C * p.a.K; i += 256) sw[i] = f16r(p.a.w[i]);
+    for (int r = tid; r < 256 + H; r += 256) {
+        const int t = t0 - H + r;
+        float * dst = sa + r * (kPostCS + 1);
+        if (t < 0 || t >= p.a.T) {
+            for (int c = 0; c < p.a.C; c++) dst[c] = 0.0f;
+            continue;
+        }
+        const size_t xo = ((size_t)b * p.a.T + t) * p.cs;
         for (int c0 = 0; c0 < p.a.C; c0 += 4) {
-            const float4 f = *reinterpret_cast<const float4 *>(xr + c0);
-            const float xv[4] = {f.x, f.y, f.z, f.w};
+            const float4 f = *reinterpret_cast<const float4 *>(p.a.x[0] + xo + c0), g = *reinterpret_cast<const float4 *>(p.a.x[1] + xo + c0),
+                         h = *reinterpret_cast<const float4 *>(p.a.x[2] + xo + c0);
+            const float xv[4] = {((f.x + g.x) + h.x) * (1.0f / 3.0f), ((f.y + g.y) + h.y) * (1.0f / 3.0f),
+                                 ((f.z + g.z) + h.z) * (1.0f / 3.0f), ((f.w + g.w) + h.w) * (1.0f / 3.0f)};
 #pragma unroll
             for (int e = 0; e < 4; e++)
-                if (c0 + e < p.a.C) acc = fmaf(f16r(__ldg(p.a.w + (c0 + e) * p.a.K + k)), f16r(half_snake_fast(xv[e], c0 + e, p.a.alpha, p.a.n_alpha)), acc);
+                if (c0 + e < p.a.C) dst[c0 + e] = f16r(half_snake_fast(xv[e], c0 + e, p.a.alpha, p.a.n_alpha));
         }
     }
-    p.a.pcm[i] = tanhf(acc + __ldg(p.a.bias));
+    __syncthreads();
+    const int t = t0 + tid;
+    if (t >= p.a.T) return;
+    float acc = 0.0f;
+    for (int k = 0; k < p.a.K; k++) {
+        const float * row = sa + (tid + k) * (kPostCS + 1);       // input step t - (K-1-k)
+        for (int c = 0; c < p.a.C; c++) acc = fmaf(sw[c * p.a.K + k], row[c], acc);
+    }
+    p.a.pcm[(size_t)b * p.a.T + t] = tanhf(acc + __ldg(p.a.bias));
 }
 
 }  // namespace
@@ -573,10 +588,10 @@ bool launch_conv(const Geom & g, const ConvArgs & a, cudaStream_t stream) {
     }
     if (g.C > kMaxC) { set_error("codec: too many channels for the tensor-core path"); return false; }
     const int grid = std::min(p.n_tiles, n_sm[dev]);
-    const int mode = a.sum_mode ? 2 : (a.res ? 1 : 0);
+    const int mode = a.res ? (a.ya ? 1 : 2) : 0;
     if (mode == 0 && !a.ya) { set_error("codec: conv without an output"); return false; }
     if (mode == 1 && (!a.y || !a.ya)) { set_error("codec: residual conv needs y and ya"); return false; }
-    if (mode == 2 && (!a.res || !a.sum_out)) { set_error("codec: sum conv needs res and sum_out"); return false; }
+    if (mode == 2 && !a.y) { set_error("codec: residual conv needs y"); return false; }
     if (mode == 0) conv_tc_kernel<0><<<grid, kThreads, smem, stream>>>(p);
     else if (mode == 1) conv_tc_kernel<1><<<grid, kThreads, smem, stream>>>(p);
     else conv_tc_kernel<2><<<grid, kThreads, smem, stream>>>(p);
@@ -597,8 +612,9 @@ bool launch_up(const Geom & g, const UpArgs & a, cudaStream_t stream) {
 bool launch_post(const PostArgs & a, cudaStream_t stream) {
     PostKParams p = {};
     p.a = a; p.cs = row_stride(a.C);
-    const size_t total = (size_t)a.B * a.T;
-    post_tm_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(p);
+    if (a.C > kPostCS || a.K > 8) { set_error("codec: post conv shape not supported"); return false; }
+    dim3 grid((a.T + 255) / 256, a.B);
+    post_tm_kernel<<<grid, 256, 0, stream>>>(p);
     MGB_LAUNCH_CHECK();
     return true;
 }

@@ -320,11 +320,13 @@ static bool codec_decode_tc(Codec & c, const int32_t * d_codes, int B, int T, fl
         for (auto & b : c.img) MGB_CUDA_TRY(cudaMalloc(&b, need_img));
         c.img_bytes = need_img;
     }
-    float * cur = c.buf[0], * up = c.buf[1], * o = c.buf[2], * lat = c.buf[3], * sum = c.buf[5];
+    float * pre = c.buf[0], * up = c.buf[1], * o = c.buf[2];
+    float * br[3] = {c.buf[3], c.buf[4], c.buf[5]};      // outputs of the three residual branches of a stage
 
     {   // FSQ dequantisation fused into the staging of the pre-conv 32 -> 864 (CUDA cores), output as time-major rows
         ConvParams p = {};
-        p.xa = lat; p.codes = d_codes; p.w = (const __half *)c.pre_w16; p.bias = c.pre_b; p.y = cur; p.round_in = 1; p.tm_stride = ctc::row_stride(c.base_ch);
+        p.codes = d_codes;
+        p.w = (const __half *)c.pre_w16; p.bias = c.pre_b; p.y = pre; p.round_in = 1; p.tm_stride = ctc::row_stride(c.base_ch);
         p.Cin = c.latent; p.Cout = c.base_ch; p.CoPad = pad64(c.base_ch); p.K = c.pre_k; p.dil = 1; p.T = T;
         if (!launch_conv(p, B, stream)) return false;
     }
@@ -337,7 +339,9 @@ static bool codec_decode_tc(Codec & c, const int32_t * d_codes, int B, int T, fl
         for (auto & im : c.img) MGB_CUDA_TRY(cudaMemset2DAsync(im, pitch, 0, (size_t)ctc::kHP * 128, (size_t)B * g.nchunk, stream));
         {
             ctc::UpArgs u;
-            u.x = cur; u.alpha = c.act_alpha[i]; u.n_alpha = c.n_alpha_act[i]; u.w = c.up_w[i]; u.bias = c.up_b[i]; u.up = up;
+            if (i == 0) { u.x[0] = pre; u.n_x = 1; }
+            else { u.x[0] = br[0]; u.x[1] = br[1]; u.x[2] = br[2]; u.n_x = 3; }      // mean of the previous stage's branches
+            u.alpha = c.act_alpha[i]; u.n_alpha = c.n_alpha_act[i]; u.w = c.up_w[i]; u.bias = c.up_b[i]; u.up = up;
             for (int j = 0; j < 3; j++) { u.img[j] = (__half *)c.img[j]; u.br_alpha[j] = c.rb[i][j][0].in_alpha; }
             u.n_br_alpha = c.n_alpha_rb[i];
             u.B = B; u.Cin = C; u.T = Tc; u.s = s;
@@ -361,22 +365,21 @@ static bool codec_decode_tc(Codec & c, const int32_t * d_codes, int B, int T, fl
                     a2.y = o;      // for k = 1 res and y alias: each element is read then written by the same thread
                     a2.ya = imA; a2.alpha2 = c.rb[i][j][k + 1].in_alpha; a2.n_alpha2 = c.n_alpha_rb[i];
                 } else {
-                    a2.sum_in = sum; a2.sum_out = sum; a2.sum_mode = j == 0 ? 1 : (j == 1 ? 2 : 3);
+                    a2.y = br[j];  // branch output; the consumer (next stage's up kernel / post kernel) takes the mean of the three
                 }
                 if (!ctc::launch_conv(g, a2, stream)) return false;
                 oin = o;
             }
         }
-        std::swap(cur, sum);      // cur = mean of the three branches
         C = Co; Tc = To;
     }
     {
         ctc::PostArgs pp;
-        pp.x = cur; pp.alpha = c.post_alpha; pp.n_alpha = c.n_alpha_post; pp.w = c.post_w; pp.bias = c.post_b;
+        pp.x[0] = br[0]; pp.x[1] = br[1]; pp.x[2] = br[2];
+        pp.alpha = c.post_alpha; pp.n_alpha = c.n_alpha_post; pp.w = c.post_w; pp.bias = c.post_b;
         pp.pcm = d_pcm; pp.B = B; pp.C = C; pp.K = c.post_k; pp.T = Tc;
         if (!ctc::launch_post(pp, stream)) return false;
     }
-    c.buf[0] = cur; c.buf[5] = sum;
     return true;
 }
 

@@ -38,7 +38,6 @@ struct ConvArgs {
     float * y = nullptr;             // optional raw output conv + bias (+ res), f32 rows
     __half * ya = nullptr;           // optional activated output image f16(half_snake(y; alpha2))
     const float * alpha2 = nullptr; int n_alpha2 = 0;
-    const float * sum_in = nullptr; float * sum_out = nullptr; int sum_mode = 0;   // 0 none, 1 init, 2 add, 3 add and * 1/3
     int B = 0, T = 0, K = 0, dil = 1;
 };
 bool launch_conv(const Geom & g, const ConvArgs & a, cudaStream_t stream);
@@ -46,7 +45,7 @@ bool launch_conv(const Geom & g, const ConvArgs & a, cudaStream_t stream);
 // HalfSnake -> grouped transposed conv (stride s) of the previous stage's output, writing the stage input `up` (f32 rows)
 // and the three residual branches' first activated images.
 struct UpArgs {
-    const float * x = nullptr;          // [B][T][row_stride(Cin)]
+    const float * x[3] = {}; int n_x = 1;   // [B][T][row_stride(Cin)]; n_x == 3: the input is the mean of three branch outputs
     const float * alpha = nullptr; int n_alpha = 0;     // HalfSnake in front of the transposed conv
     const float * w = nullptr;          // [Cin][1][2s]
     const float * bias = nullptr;       // [Cin/2]
@@ -59,7 +58,8 @@ bool launch_up(const Geom & g_out, const UpArgs & a, cudaStream_t stream);
 
 // HalfSnake -> conv (C -> 1) -> tanh on f32 rows -> pcm [B][T]
 struct PostArgs {
-    const float * x = nullptr; const float * alpha = nullptr; int n_alpha = 0;
+    const float * x[3] = {};            // the three branch outputs of the last stage (their mean is the input)
+    const float * alpha = nullptr; int n_alpha = 0;
     const float * w = nullptr; const float * bias = nullptr; float * pcm = nullptr;
     int B = 0, C = 0, K = 0, T = 0;
 };
