@@ -39,6 +39,8 @@ constexpr int kSmemBudget = 214 * 1024;
 struct KParams {
     ConvArgs a;
     int C, nsplit, nper, npad, nchunk, cs;
+    int rb;                 // bytes per image / weight-tile row: 128 (64 channels, SWIZZLE_128B) or 64 (32 channels, SWIZZLE_64B)
+    uint32_t desc_hi;       // constant high word of the shared-memory matrix descriptors for this row size
     int hp;                 // staged history rows, (K-1)*dil rounded up to 8
     int tps, ngroups;       // taps per weight stage, stages per chunk
     int NA, NW;             // ring depths
@@ -52,6 +54,9 @@ struct KParams {
 
 __device__ __forceinline__ float f16r(float x) { return __half2float(__float2half_rn(x)); }
 
+// XOR applied to the 16-byte group index of image row r: SWIZZLE_128B (8 groups per 128-byte row) or SWIZZLE_64B (4 groups per
+// 64-byte row, address bits [4,5] ^= bits [7,8])
+__host__ __device__ __forceinline__ int img_swz(int r, int rb) { return rb == 128 ? (r & 7) : ((r >> 1) & 3); }
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
@@ -60,12 +65,13 @@ __device__ __forceinline__ bool elect_one() {
 // low word of a K-major SWIZZLE_128B shared-memory matrix descriptor (start address >> 4, LBO = 1); the high word is
 // constant: SBO = 1024 B >> 4 (bits 32-45), version 1 (bit 46), layout SWIZZLE_128B = 2 (bits 61-63)
 __device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
-constexpr uint32_t kDescHi = 64u | (1u << 14) | (2u << 29);
-__device__ __forceinline__ void umma_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+// (SWIZZLE_64B rows of 64 bytes: SBO = 512 B >> 4 = 32, layout 4)
+__host__ __device__ constexpr uint32_t desc_hi_for(int rb) { return rb == 128 ? (64u | (1u << 14) | (2u << 29)) : (32u | (1u << 14) | (4u << 29)); }
+__device__ __forceinline__ void umma_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate, uint32_t desc_hi) {
     asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                  "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
                  "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
-                 ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHi) : "memory");
+                 ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(desc_hi) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t * bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
@@ -155,12 +161,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const KParams p) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
     const int K = p.a.K, T = p.a.T;
-    const int tile_bytes = p.npad * 128;
+    const int tile_bytes = p.npad * p.rb;
+    const int cpr = p.rb >> 1;           // channels per row
 
     // Producer and MMA roles run their loops warp-uniformly (all lanes poll the barriers; one elected lane issues), so
     // that addresses and descriptors live in uniform registers and the per-MMA issue cost stays a few instructions.
     if (warp == 0) {
-        const uint32_t abytes = (uint32_t)(p.R * kTile + p.hp) * 128;
+        const uint32_t abytes = (uint32_t)(p.R * kTile + p.hp) * p.rb;
         const bool leader = elect_one();
         uint32_t ia = 0, iw = 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
@@ -173,7 +180,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const KParams p) {
                 if (leader) {
                     tc::mbar_expect_tx(&a_full[sa], abytes);
                     tc::bulk_g2s(abuf + (size_t)sa * p.abuf_bytes,
-                                 reinterpret_cast<const unsigned char *>(p.a.xa) + (((long long)b * p.nchunk + c) * p.rows + row0) * 128,
+                                 reinterpret_cast<const unsigned char *>(p.a.xa) + (((long long)b * p.nchunk + c) * p.rows + row0) * p.rb,
                                  abytes, &a_full[sa]);
                 }
                 ia++;
@@ -194,7 +201,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const KParams p) {
         const uint32_t idesc = tc::umma_idesc_f16(kTile, p.npad);
         const bool leader = elect_one();
         const uint32_t tile_d = (uint32_t)tile_bytes >> 4;             // descriptor address units are 16 bytes
-        const uint32_t dil_d = (uint32_t)p.a.dil * 8;                   // one row = 128 bytes = 8 units
+        const uint32_t dil_d = (uint32_t)p.a.dil * (p.rb >> 4);         // one row = rb bytes = rb / 16 units
+        const uint32_t tile_rows_d = (uint32_t)kTile * (p.rb >> 4);
         uint32_t ia = 0, iw = 0, it = 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, it++) {
             const int buf = it & 1;
@@ -209,8 +217,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const KParams p) {
                 const int sa = ia % p.NA;
                 tc::mbar_wait(&a_full[sa], (ia / p.NA) & 1);
                 // tap 0 reads rows hp - (K-1)*dil ..., every further tap dil rows later
-                const uint32_t a_lo0 = desc_lo(tc::smem_u32(abuf + (size_t)sa * p.abuf_bytes) + (uint32_t)(p.hp - (K - 1) * p.a.dil) * 128);
-                const int nk16 = min(4, (p.C - c * 64 + 15) >> 4);
+                const uint32_t a_lo0 = desc_lo(tc::smem_u32(abuf + (size_t)sa * p.abuf_bytes) + (uint32_t)(p.hp - (K - 1) * p.a.dil) * p.rb);
+                const int nk16 = min(cpr >> 4, (p.C - c * cpr + 15) >> 4);
                 for (int g = 0; g < p.ngroups; g++) {
                     const int sw = iw % p.NW;
                     const int nt = min(p.tps, K - g * p.tps);
@@ -221,11 +229,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const KParams p) {
                     if (leader) {
                         for (int q = 0; q < nt; q++) {
                             for (int r = 0; r < rt; r++) {
-                                const uint32_t ar = a_lo + (uint32_t)r * (kTile * 8), dr = dcol + (uint32_t)(r * p.npad);
-                                umma_lo(dr, ar, w_lo, idesc, accum);
-                                if (nk16 > 1) umma_lo(dr, ar + 2, w_lo + 2, idesc, 1u);
-                                if (nk16 > 2) umma_lo(dr, ar + 4, w_lo + 4, idesc, 1u);
-                                if (nk16 > 3) umma_lo(dr, ar + 6, w_lo + 6, idesc, 1u);
+                                const uint32_t ar = a_lo + (uint32_t)r * tile_rows_d, dr = dcol + (uint32_t)(r * p.npad);
+                                umma_lo(dr, ar, w_lo, idesc, accum, p.desc_hi);
+                                if (nk16 > 1) umma_lo(dr, ar + 2, w_lo + 2, idesc, 1u, p.desc_hi);
+                                if (nk16 > 2) umma_lo(dr, ar + 4, w_lo + 4, idesc, 1u, p.desc_hi);
+                                if (nk16 > 3) umma_lo(dr, ar + 6, w_lo + 6, idesc, 1u, p.desc_hi);
                             }
                             accum = 1;
                             a_lo += dil_d; w_lo += tile_d;
@@ -248,7 +256,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const KParams p) {
         const int n16 = p.npad >> 4;
         const int n_units = p.R * n16;                 // (accumulator tile r, 16-column unit u) pairs: w = r * n16 + u
         const int w_lo = n_units * part / (kEpiWarps / 4), w_hi = n_units * (part + 1) / (kEpiWarps / 4);
-        const long long hrow_bytes = p.rows * 128;
+        const long long hrow_bytes = p.rows * p.rb;
         const size_t tile_stride = (size_t)kTile * p.cs;          // f32 elements between accumulator tiles of an item
         struct TileInfo { int t0, r_img0, cbase, b, rt; size_t row_off; };     // r = 0 row of this thread
         auto decode = [&](int tile) {
@@ -342,9 +350,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const KParams p) {
                     }
                     if (tv) {
                         // the unit's two 16-byte groups share one 32-byte sector of the swizzled row; odd rows swap them
-                        const int sw = r_img & 7;
-                        unsigned char * dst = reinterpret_cast<unsigned char *>(p.a.ya) + ((long long)cur.b * p.nchunk + (co0 >> 6)) * hrow_bytes +
-                                              (long long)r_img * 128 + (((((co0 & 63) >> 3) ^ sw) & 6) << 4);
+                        const int sw = img_swz(r_img, p.rb);
+                        unsigned char * dst = reinterpret_cast<unsigned char *>(p.a.ya) + ((long long)cur.b * p.nchunk + co0 / cpr) * hrow_bytes +
+                                              (long long)r_img * p.rb + (((((co0 % cpr) >> 3) ^ sw) & 6) << 4);
                         const bool swap = sw & 1;
                         stg256(dst, swap ? pk[4] : pk[0], swap ? pk[5] : pk[1], swap ? pk[6] : pk[2], swap ? pk[7] : pk[3],
                                     swap ? pk[0] : pk[4], swap ? pk[1] : pk[5], swap ? pk[2] : pk[6], swap ? pk[3] : pk[7]);
@@ -366,11 +374,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const KParams p) {
 }
 
 // f32 (C, C, K) -> f16 tile images [nsplit][nchunk][K][npad x 64]; one thread per 16-byte group of 8 input channels
-__global__ void pack_w_kernel(const float * w, int C, int K, int nsplit, int nper, int npad, int nchunk, __half * out) {
-    const size_t total = (size_t)nsplit * nchunk * K * npad * 8;
+__global__ void pack_w_kernel(const float * w, int C, int K, int nsplit, int nper, int npad, int nchunk, int rb, __half * out) {
+    const int gpr = rb >> 4, cpr = rb >> 1;             // 16-byte groups / channels per row
+    const size_t total = (size_t)nsplit * nchunk * K * npad * gpr;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int kc = (int)(i % 8);
-        size_t r = i / 8;
+        const int kc = (int)(i % gpr);
+        size_t r = i / gpr;
         const int n = (int)(r % npad); r /= npad;
         const int k = (int)(r % K); r /= K;
         const int c = (int)(r % nchunk); const int h = (int)(r / nchunk);
@@ -378,10 +387,11 @@ __global__ void pack_w_kernel(const float * w, int C, int K, int nsplit, int npe
         __half hv[8];
 #pragma unroll
         for (int e = 0; e < 8; e++) {
-            const int ci = c * 64 + kc * 8 + e;
+            const int ci = c * cpr + kc * 8 + e;
             hv[e] = __float2half_rn((n < nper && ci < C) ? w[((size_t)co * C + ci) * K + k] : 0.0f);
         }
-        unsigned char * dst = reinterpret_cast<unsigned char *>(out) + (((size_t)(h * nchunk + c) * K + k) * npad) * 128 + tc::swz_offset(n, kc * 8);
+        unsigned char * dst = reinterpret_cast<unsigned char *>(out) + (((size_t)(h * nchunk + c) * K + k) * npad) * rb + (size_t)n * rb +
+                              ((kc ^ img_swz(n, rb)) << 4);
         *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(hv);
     }
 }
@@ -389,7 +399,7 @@ __global__ void pack_w_kernel(const float * w, int C, int K, int nsplit, int npe
 // HalfSnake -> grouped ConvTranspose1d (groups = Cout, 2 inputs per group, K = 2*stride, first T*stride samples kept;
 // nano-codec.cpp:481-565) on time-major rows, producing the stage input `up` AND the activated images of the three
 // residual branches (their first HalfSnake) in one pass.  grid (time blocks of 128, 8-channel groups, B).
-struct UpKParams { UpArgs a; int cs_in, cs_out, nchunk; long long rows; };
+struct UpKParams { UpArgs a; int cs_in, cs_out, nchunk, rb; long long rows; };
 __device__ __forceinline__ float half_snake_fast(float x, int c, const float * alpha, int n_alpha) {
     if (c < n_alpha) {
         const float a = __ldg(alpha + c);
@@ -463,7 +473,8 @@ __global__ void __launch_bounds__(128) up_tm_kernel(const UpKParams p) {
         }
         stg256f(p.a.up + ((size_t)b * To + to) * p.cs_out + g0, v);
         const int r_img = kHP + to;
-        const long long off = ((long long)b * p.nchunk + (g0 >> 6)) * p.rows * 128 + (long long)r_img * 128 + ((((g0 & 63) >> 3) ^ (r_img & 7)) << 4);
+        const int cpr = p.rb >> 1;
+        const long long off = (((long long)b * p.nchunk + g0 / cpr) * p.rows + r_img) * p.rb + ((((g0 % cpr) >> 3) ^ img_swz(r_img, p.rb)) << 4);
 #pragma unroll
         for (int j = 0; j < 3; j++) {
             float act[8];
@@ -537,15 +548,17 @@ Geom geom_for(int C) {
     }
     if (!g.nper) return g;
     g.npad = (g.nper + 15) / 16 * 16;
-    g.nchunk = (C + 63) / 64;
+    // 64-byte rows (32 channels) for narrow stages: the 27-channel stage would otherwise move 128-byte rows with 54 useful bytes
+    g.rb = g.npad <= 32 ? 64 : 128;
+    g.nchunk = (C + g.rb / 2 - 1) / (g.rb / 2);
     g.ok = true;
     return g;
 }
 
-size_t weight_image_bytes(const Geom & g, int K) { return (size_t)g.nsplit * g.nchunk * K * g.npad * 128; }
+size_t weight_image_bytes(const Geom & g, int K) { return (size_t)g.nsplit * g.nchunk * K * g.npad * g.rb; }
 
 bool pack_weights(const float * w, const Geom & g, int K, void * img, cudaStream_t stream) {
-    pack_w_kernel<<<296, 256, 0, stream>>>(w, g.C, K, g.nsplit, g.nper, g.npad, g.nchunk, (__half *)img);
+    pack_w_kernel<<<296, 256, 0, stream>>>(w, g.C, K, g.nsplit, g.nper, g.npad, g.nchunk, g.rb, (__half *)img);
     MGB_LAUNCH_CHECK();
     return true;
 }
@@ -562,7 +575,8 @@ bool launch_conv(const Geom & g, const ConvArgs & a, cudaStream_t stream) {
     const int halo = (a.K - 1) * a.dil;
     if (!g.ok || halo > kHP) { set_error("codec: conv shape not supported by the tensor-core path"); return false; }
     p.hp = (halo + 7) / 8 * 8;
-    const int tile_bytes = g.npad * 128;
+    const int tile_bytes = g.npad * g.rb;
+    p.rb = g.rb; p.desc_hi = desc_hi_for(g.rb);
     p.tps = std::max(1, std::min(a.K, (32 * 1024) / tile_bytes));
     p.ngroups = (a.K + p.tps - 1) / p.tps;
     p.wstage_bytes = p.tps * tile_bytes;
@@ -570,7 +584,7 @@ bool launch_conv(const Geom & g, const ConvArgs & a, cudaStream_t stream) {
     // small channel counts amortise the per-item pipeline hand-offs and the weight stream over up to 512 time steps
     p.R = std::max(1, std::min(4, 256 / g.npad));
     if (p.R == 3) p.R = 2;
-    p.abuf_bytes = (p.R * kTile + kHP) * 128;
+    p.abuf_bytes = ((p.R * kTile + kHP) * g.rb + 1023) / 1024 * 1024;
     p.NA = p.R >= 4 ? 2 : 3;
     p.NW = std::max(2, std::min(kMaxNW, (kSmemBudget - p.NA * p.abuf_bytes) / p.wstage_bytes));
     p.tiles_per_b = (a.T + p.R * kTile - 1) / (p.R * kTile);
@@ -601,7 +615,7 @@ bool launch_conv(const Geom & g, const ConvArgs & a, cudaStream_t stream) {
 
 bool launch_up(const Geom & g, const UpArgs & a, cudaStream_t stream) {
     UpKParams p = {};
-    p.a = a; p.cs_in = row_stride(a.Cin); p.cs_out = row_stride(a.Cin / 2); p.nchunk = g.nchunk; p.rows = (long long)act_rows(a.T * a.s);
+    p.a = a; p.cs_in = row_stride(a.Cin); p.cs_out = row_stride(a.Cin / 2); p.nchunk = g.nchunk; p.rb = g.rb; p.rows = (long long)act_rows(a.T * a.s);
     if (a.s > 8) { set_error("codec: up-sampling stride > 8"); return false; }
     dim3 grid((a.T + 127) / 128, p.cs_out / 8, a.B);
     up_tm_kernel<<<grid, 128, 0, stream>>>(p);

@@ -304,7 +304,7 @@ static bool codec_decode_tc(Codec & c, const int32_t * d_codes, int B, int T, fl
         for (int i = 0; i < 5; i++) {
             C /= 2; Tc *= c.up_rates[i];
             need = std::max(need, (size_t)ctc::row_stride(C) * Tc);
-            need_img = std::max(need_img, ctc::act_bytes(B, C, Tc));
+            need_img = std::max(need_img, ctc::act_bytes(B, ctc::geom_for(C), Tc));
         }
         need *= (size_t)B;
     }
@@ -335,8 +335,8 @@ static bool codec_decode_tc(Codec & c, const int32_t * d_codes, int B, int T, fl
         const int s = c.up_rates[i], Co = C / 2, To = Tc * s;
         const ctc::Geom g = ctc::geom_for(Co);
         // zero causal-history rows of the images for this stage's geometry
-        const size_t pitch = ctc::act_rows(To) * 128;
-        for (auto & im : c.img) MGB_CUDA_TRY(cudaMemset2DAsync(im, pitch, 0, (size_t)ctc::kHP * 128, (size_t)B * g.nchunk, stream));
+        const size_t pitch = ctc::act_rows(To) * g.rb;
+        for (auto & im : c.img) MGB_CUDA_TRY(cudaMemset2DAsync(im, pitch, 0, (size_t)ctc::kHP * g.rb, (size_t)B * g.nchunk, stream));
         {
             ctc::UpArgs u;
             if (i == 0) { u.x[0] = pre; u.n_x = 1; }

@@ -15,6 +15,7 @@ constexpr int kTile = 128;         // time steps per accumulator tile (MMA M)
 // channels in `nchunk` chunks of 64 (one 128-byte swizzle row each).
 struct Geom {
     int C = 0, nsplit = 1, nper = 0, npad = 0, nchunk = 0;
+    int rb = 128;           // bytes per image row: 128 (64 channels per chunk) or 64 (32 channels, stages with <= 32 channels)
     bool ok = false;
 };
 Geom geom_for(int C);
@@ -24,7 +25,7 @@ Geom geom_for(int C);
 // f32 tensors of the tensor-core pipeline are TIME-MAJOR rows [B][T][row_stride(C)] (padding channels stay zero)
 inline int row_stride(int C) { return (C + 15) / 16 * 16; }
 inline size_t act_rows(int T) { return (size_t)kHP + (size_t)(T + 4 * kTile - 1) / (4 * kTile) * (4 * kTile); }   // a work item spans up to 4 tiles
-inline size_t act_bytes(int B, int C, int T) { return (size_t)B * ((C + 63) / 64) * act_rows(T) * 128; }
+inline size_t act_bytes(int B, const Geom & g, int T) { return (size_t)B * g.nchunk * act_rows(T) * g.rb; }
 
 size_t weight_image_bytes(const Geom & g, int K);
 // f32 (Cout = C, Cin = C, K) PyTorch layout on the device -> f16 tile images [nsplit][nchunk][K][npad x 64]
