@@ -484,7 +484,12 @@ int mgb_prefill(mgb_session * ss, const int32_t * speakers) {
     }
     // batched decode: the same fold for every (utterance, text position) row of the cross K/V
     s->fold_ready = false;
-    if (s->fold_xm) {
+    // (the folded kernel streams 2 x E x d f32 table rows per utterance and layer, a quarter per CTA of a 4-CTA cluster:
+    //  measured faster than the q GEMM + attention + o GEMM launches up to the 80-token texts of config 4; very long texts
+    //  keep the unfolded kernels)
+    long long sum_e = 0;
+    for (int b = 0; b < s->B; b++) sum_e += s->h_ntext[b];
+    if (s->fold_xm && (sum_e <= (long long)(getenv("MGB_XFOLD_MAXE") ? atoi(getenv("MGB_XFOLD_MAXE")) : 128) * s->B)) {
         const size_t tab = (size_t)s->B * s->max_text * d;
         for (int l = 0; l < hp.dec_layers; l++) {
             const DecLayer & L = m.dec[l];

@@ -385,66 +385,102 @@ bool launch_attention(const AttnArgs & a, cudaStream_t stream) {
 // (magpie.cpp:1713-1767, 3513) in ONE launch instead of five.  One CTA per utterance, 512 threads.
 struct XFoldParams { float * x; const float * ln_w; float eps; const float * xm; const float * xn; const int32_t * n_ctx; int d, max_text;
                      const float * pack_ln_w; __nv_bfloat16 * pk_hi; __nv_bfloat16 * pk_lo; };
-__global__ void __launch_bounds__(512) xattn_folded_kernel(const XFoldParams p) {
-    __shared__ float xl[1024];
-    __shared__ float sc[512];
+// One CLUSTER of kXC CTAs per utterance; CTA rank r owns the d / kXC columns [r * dc, (r + 1) * dc) of the row, i.e. a
+// quarter of both tables: partial scores and the LayerNorm statistics of the updated row are exchanged through DSMEM.
+constexpr int kXC = 4, kXT = 256;
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void dsmem_store(float * local, int rank, float v) {
+    uint32_t la = (uint32_t)__cvta_generic_to_shared(local), ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(rank));
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(v) : "memory");
+}
+__global__ void __launch_bounds__(kXT) xattn_folded_kernel(const XFoldParams p) {
+    __shared__ float xl[256];                 // this CTA's columns: LN(x), later the updated row
+    __shared__ float part[kXC][512];          // partial scores of every rank (written through DSMEM)
+    __shared__ float prob[512];
+    __shared__ float stat[2][kXC];            // partial sums for the second LayerNorm
     __shared__ float red[32];
-    const int u = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int d = p.d, E = p.n_ctx[u];
+    const int u = blockIdx.x / kXC, rank = blockIdx.x % kXC;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int d = p.d, dc = d / kXC, c0 = rank * dc, E = p.n_ctx[u];
     float * xr = p.x + (size_t)u * d;
-    // LayerNorm (no bias), magpie.cpp:2237-2259
+    // LayerNorm statistics over the whole row, redundantly in every CTA (magpie.cpp:2237-2259)
     float s = 0.0f;
-    for (int i = tid; i < d; i += 512) s += xr[i];
+    for (int i = tid; i < d; i += kXT) s += xr[i];
     const float mean = block_sum(s, red) / (float)d;
     float s2 = 0.0f;
-    for (int i = tid; i < d; i += 512) { const float c = xr[i] - mean; s2 += c * c; }
+    for (int i = tid; i < d; i += kXT) { const float c = xr[i] - mean; s2 += c * c; }
     const float scale = 1.0f / sqrtf(block_sum(s2, red) / (float)d + p.eps);
-    for (int i = tid; i < d; i += 512) xl[i] = ((xr[i] - mean) * scale) * p.ln_w[i];
+    const float xraw = tid < dc ? xr[c0 + tid] : 0.0f;
+    if (tid < dc) xl[tid] = ((xraw - mean) * scale) * p.ln_w[c0 + tid];
     __syncthreads();
-    const float * xm = p.xm + (size_t)u * p.max_text * d, * xn = p.xn + (size_t)u * p.max_text * d;
-    for (int j = warp; j < E; j += 16) {
+    const float * xm = p.xm + (size_t)u * p.max_text * d + c0, * xn = p.xn + (size_t)u * p.max_text * d + c0;
+    // partial scores over this CTA's columns, broadcast to the cluster
+    for (int j = warp; j < E; j += kXT / 32) {
         const float * mr = xm + (size_t)j * d;
         float a = 0.0f;
-        for (int i = lane * 4; i < d; i += 128) {
-            const float4 m4 = *reinterpret_cast<const float4 *>(mr + i);
-            a = fmaf(m4.x, xl[i], a); a = fmaf(m4.y, xl[i + 1], a); a = fmaf(m4.z, xl[i + 2], a); a = fmaf(m4.w, xl[i + 3], a);
+        for (int i = lane * 2; i < dc; i += 64) {
+            const float2 m2 = *reinterpret_cast<const float2 *>(mr + i);
+            a = fmaf(m2.x, xl[i], a); a = fmaf(m2.y, xl[i + 1], a);
         }
         a = warp_sum(a);
-        if (lane == 0) sc[j] = a;
+        if (lane < kXC) dsmem_store(&part[rank][j], lane, a);
     }
-    __syncthreads();
+    cluster_sync_all();
     float mx = -INFINITY;
-    for (int j = 0; j < E; j++) mx = fmaxf(mx, sc[j]);
-    float sum = 0.0f;
-    for (int j = 0; j < E; j++) sum += expf(sc[j] - mx);
-    const float inv = 1.0f / sum;
-    float s3 = 0.0f;
-    for (int i = tid; i < d; i += 512) {
-        float o = 0.0f;
-        for (int j = 0; j < E; j++) o = fmaf(expf(sc[j] - mx) * inv, xn[(size_t)j * d + i], o);
-        const float v = xr[i] + o;
-        xr[i] = v;
-        if (p.pk_hi) { xl[i] = v; s3 += v; }       // xl is free: its last readers (the score dots) finished before the barrier above
+    for (int j = tid; j < E; j += kXT) {
+        float sc = 0.0f;
+#pragma unroll
+        for (int r = 0; r < kXC; r++) sc += part[r][j];
+        prob[j] = sc;
+        mx = fmaxf(mx, sc);
     }
-    if (!p.pk_hi) return;
-    // LayerNorm of the updated row with the NEXT sub-block's weight, emitted as bf16 hi | lo tile images (gemm_tc.cu layout,
-    // 64-token tile): replaces the separate packing kernel in front of the FFN's first GEMM
-    const float mean2 = block_sum(s3, red) / (float)d;
-    float s4 = 0.0f;
-    for (int i = tid; i < d; i += 512) { const float c = xl[i] - mean2; s4 += c * c; }
-    const float scale2 = 1.0f / sqrtf(block_sum(s4, red) / (float)d + p.eps);
-    for (int kc = tid; kc < d / 8; kc += 512) {
+    // block max / sum of exp (E <= 512: at most two entries per thread)
+    mx = warp_max(mx);
+    __syncthreads();
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    mx = red[0];
+    for (int w = 1; w < kXT / 32; w++) mx = fmaxf(mx, red[w]);
+    float se = 0.0f;
+    for (int j = tid; j < E; j += kXT) { const float e = expf(prob[j] - mx); prob[j] = e; se += e; }
+    const float inv = 1.0f / block_sum(se, red);
+    __syncthreads();
+    float v = 0.0f;
+    if (tid < dc) {
+        float o = 0.0f;
+        for (int j = 0; j < E; j++) o = fmaf(prob[j] * inv, xn[(size_t)j * d + tid], o);
+        v = xraw + o;
+        xr[c0 + tid] = v;
+    }
+    if (!p.pk_hi) { cluster_sync_all(); return; }         // (no CTA may exit while a peer can still write into its shared memory)
+    // LayerNorm of the updated row with the NEXT sub-block's weight -> bf16 hi | lo tile images (gemm_tc.cu layout, one
+    // 64-token tile): the packing kernel in front of the FFN's first GEMM is not needed
+    const float ps = block_sum(tid < dc ? v : 0.0f, red);
+    if (tid < kXC) dsmem_store(&stat[0][rank], tid, ps);
+    cluster_sync_all();
+    const float mean2 = (stat[0][0] + stat[0][1] + stat[0][2] + stat[0][3]) / (float)d;
+    const float cv = tid < dc ? v - mean2 : 0.0f;
+    const float pq = block_sum(cv * cv, red);
+    if (tid < kXC) dsmem_store(&stat[1][rank], tid, pq);
+    cluster_sync_all();
+    const float scale2 = 1.0f / sqrtf((stat[1][0] + stat[1][1] + stat[1][2] + stat[1][3]) / (float)d + p.eps);
+    if (tid < dc) xl[tid] = (cv * scale2) * p.pack_ln_w[c0 + tid];
+    __syncthreads();
+    for (int kc = tid; kc < dc / 8; kc += kXT) {
         uint32_t h[4], l[4];
 #pragma unroll
         for (int q = 0; q < 4; q++) {
-            const int i0 = kc * 8 + 2 * q;
-            const float v0 = ((xl[i0] - mean2) * scale2) * p.pack_ln_w[i0], v1 = ((xl[i0 + 1] - mean2) * scale2) * p.pack_ln_w[i0 + 1];
+            const float v0 = xl[kc * 8 + 2 * q], v1 = xl[kc * 8 + 2 * q + 1];
             const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
             const __nv_bfloat16 l0 = __float2bfloat16_rn(v0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(v1 - __bfloat162float(h1));
             h[q] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
             l[q] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
         }
-        const size_t off = (size_t)(kc / 8) * (64 * 128) + (size_t)u * 128 + ((((kc % 8) ^ (u & 7)) & 7) << 4);
+        const int kg = (c0 >> 3) + kc;                       // 8-column group index in the row
+        const size_t off = (size_t)(kg / 8) * (64 * 128) + (size_t)u * 128 + ((((kg % 8) ^ (u & 7)) & 7) << 4);
         *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(p.pk_hi) + off) = make_uint4(h[0], h[1], h[2], h[3]);
         *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(p.pk_lo) + off) = make_uint4(l[0], l[1], l[2], l[3]);
     }
@@ -452,11 +488,17 @@ __global__ void __launch_bounds__(512) xattn_folded_kernel(const XFoldParams p) 
 
 bool launch_xattn_folded(float * x, const float * ln_w, float eps, const float * xm, const float * xn, const int32_t * n_ctx, int B, int d,
                          int max_text, const float * pack_ln_w, void * pack_out, cudaStream_t stream) {
-    if (d > 1024 || max_text > 512 || d % 64 != 0) { set_error("xattn_folded: shape not supported"); return false; }
+    if (d > 1024 || max_text > 512 || d % (kXC * 8) != 0) { set_error("xattn_folded: shape not supported"); return false; }
     if (pack_out && B > 64) { set_error("xattn_folded: packed output needs one token tile"); return false; }
     XFoldParams p{x, ln_w, eps, xm, xn, n_ctx, d, max_text, pack_ln_w, (__nv_bfloat16 *)pack_out,
                   pack_out ? (__nv_bfloat16 *)pack_out + (size_t)64 * d : nullptr};
-    xattn_folded_kernel<<<B, 512, 0, stream>>>(p);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(B * kXC); cfg.blockDim = dim3(kXT); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = kXC; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    MGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, xattn_folded_kernel, p));
     MGB_LAUNCH_CHECK();
     return true;
 }
