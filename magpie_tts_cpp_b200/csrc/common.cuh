@@ -105,4 +105,19 @@ __device__ __forceinline__ float gelu_ggml(float x, int f16_table) {
     return __half2float(__float2half_rn(gelu_tanh(xh)));
 }
 
+// Same function with tanh evaluated as 1 - 2 / (1 + e^{2z}) on the SFU (abs error ~1e-6, well below the f16 rounding of the
+// table emulation): used by the latency-bound tensor-core epilogues, where libdevice's tanhf is most of the code size.
+__device__ __forceinline__ float gelu_ggml_fast(float x, int f16_table) {
+    const float a = 0.044715f, s = 0.79788456080286535587989211986876f;
+    if (f16_table) {
+        if (x <= -10.0f) return 0.0f;
+        if (x >= 10.0f) return x;
+        x = __half2float(__float2half_rn(x));
+    }
+    const float z = s * x * (1.0f + a * x * x);
+    const float t = 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * z));
+    const float y = 0.5f * x * (1.0f + t);
+    return f16_table ? __half2float(__float2half_rn(y)) : y;
+}
+
 }  // namespace mgb

@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) tc_linear_kernel(const bf * W
                     const int m = mt * MT + c + j;
                     if (m < e.M) {
                         float y = __uint_as_float(v[j]) + bias;
-                        if (kAct && (EPI == EPI_GELU_PACK || e.act == ACT_GELU)) y = gelu_ggml(y, e.gelu_f16);
+                        if (kAct && (EPI == EPI_GELU_PACK || e.act == ACT_GELU)) y = EPI == EPI_GELU_PACK ? gelu_ggml_fast(y, e.gelu_f16) : gelu_ggml(y, e.gelu_f16);
                         if (kRes && e.res) y += r[j];
                         if (kPack && (EPI == EPI_GELU_PACK || e.pk_hi)) {
                             const bf h = __float2bfloat16_rn(y);
