@@ -221,7 +221,11 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "one frame = decoder-step kernels + local-transformer kernel",
                      "achieved": achieved, "peak": hbm, "peak_source": which, "unit": "GB/s", "frac": achieved / hbm,
-                     "traffic": None, "algorithmic_bytes_per_launch": bytes_per_iter, "launch_us": iter_s * 1e6},
+                     # DRAM bytes per frame of the frame-loop kernel from the committed ncu --set full capture (7.054 GB over a
+                     # 40-frame launch, profiles/r1_frame_loop_kernel_ncu_full.txt); batch 1 / bf16 only
+                     "traffic": 176.4e6 if (B == 1 and prec == binding.PREC_BF16) else None,
+                     "traffic_source": "profiles/r1_frame_loop_kernel_ncu_full.txt (dram read+write of one 40-frame launch / 40)",
+                     "algorithmic_bytes_per_launch": bytes_per_iter, "launch_us": iter_s * 1e6},
         "clocks": clk.summary(),
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
