@@ -107,6 +107,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) tc_linear_kernel(const bf * W
     constexpr bool kPlainStore = EPI != EPI_GELU_PACK;
     extern __shared__ unsigned char tc_smem[];
     constexpr int SCAP = StageCap<SPLIT>::value;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");      // let a dependent kernel start its own prefetching
     const int nt = blockIdx.x, mt = blockIdx.y;
     const int rank = SPLIT > 1 ? (int)blockIdx.z : 0;
     const int kt0 = rank * KT / SPLIT, kt1 = (rank + 1) * KT / SPLIT;

@@ -167,6 +167,7 @@ struct AttnParams {
     const int32_t * utt; const int32_t * pos;
     float * out; int ldo;
     __nv_bfloat16 * pk_hi; __nv_bfloat16 * pk_lo;      // optional (DH == 64, <= 64 tokens): output as hi | lo tile images for the next GEMM
+    int pdl;                                           // launched with programmatic stream serialization (see kernel)
 };
 
 constexpr int kAttnWarps = 8;
@@ -191,6 +192,17 @@ __global__ void __launch_bounds__(kAttnWarps * 32) attention_kernel(const AttnPa
     const int nk = p.causal ? p.pos[t] + 1 : p.n_ctx[utt];
     const float scale = 1.0f / sqrtf((float)DH);
     const int ld = p.H * DH;
+    if (p.pdl) {
+        // launched as a programmatic dependent of the QKV GEMM: the old keys' K / V rows do not depend on it, so they are
+        // pulled into L2 while that kernel is still running; q and the new key's row are read after the wait
+        const char * Kp = (const char *)p.K + ((size_t)utt * p.rows_per_utt * ld + h * DH) * sizeof(T);
+        const char * Vp = (const char *)p.V + ((size_t)utt * p.rows_per_utt * ld + h * DH) * sizeof(T);
+        for (int j = tid; j < nk - 1; j += kAttnWarps * 32) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(Kp + (size_t)j * ld * sizeof(T)));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(Vp + (size_t)j * ld * sizeof(T)));
+        }
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+    }
     float qv[VEC];
     {
         const float * qp = p.q + (size_t)t * p.ldq + h * DH + sub * VEC;
@@ -368,6 +380,18 @@ bool launch_attention(const AttnArgs & a, cudaStream_t stream) {
     }
     dim3 grid(a.H, a.tok.M);
     const bool f32 = a.precision == MGB_PREC_F32;
+    p.pdl = (a.pack_out && !f32 && a.dh == 64) ? 1 : 0;       // decoder-step chain only
+    if (p.pdl) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid; cfg.blockDim = dim3(kAttnWarps * 32); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        MGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, attention_kernel<__nv_bfloat16, 64>, p));
+        MGB_LAUNCH_CHECK();
+        return true;
+    }
     if (a.dh == 64) {
         if (f32) attention_kernel<float, 64><<<grid, kAttnWarps * 32, 0, stream>>>(p);
         else attention_kernel<__nv_bfloat16, 64><<<grid, kAttnWarps * 32, 0, stream>>>(p);
@@ -406,6 +430,18 @@ __global__ void __launch_bounds__(kXT) xattn_folded_kernel(const XFoldParams p) 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int d = p.d, dc = d / kXC, c0 = rank * dc, E = p.n_ctx[u];
     float * xr = p.x + (size_t)u * d;
+    {
+        // programmatic dependent of the O-projection GEMM: this CTA's quarter of the (static) tables is pulled into L2 while
+        // that kernel is still running
+        const char * m0 = (const char *)(p.xm + (size_t)u * p.max_text * d + c0), * n0 = (const char *)(p.xn + (size_t)u * p.max_text * d + c0);
+        const int lines = dc * 4 / 128;                 // 128-byte lines per table row quarter
+        for (int i = tid; i < E * lines; i += kXT) {
+            const size_t off = (size_t)(i / lines) * d * 4 + (size_t)(i % lines) * 128;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(m0 + off));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(n0 + off));
+        }
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+    }
     // LayerNorm statistics over the whole row, redundantly in every CTA (magpie.cpp:2237-2259)
     float s = 0.0f;
     for (int i = tid; i < d; i += kXT) s += xr[i];
@@ -494,10 +530,12 @@ bool launch_xattn_folded(float * x, const float * ln_w, float eps, const float *
                   pack_out ? (__nv_bfloat16 *)pack_out + (size_t)64 * d : nullptr};
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(B * kXC); cfg.blockDim = dim3(kXT); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = kXC; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 2;
     MGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, xattn_folded_kernel, p));
     MGB_LAUNCH_CHECK();
     return true;
