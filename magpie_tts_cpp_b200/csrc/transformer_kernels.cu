@@ -192,6 +192,7 @@ __global__ void __launch_bounds__(kAttnWarps * 32) attention_kernel(const AttnPa
     const int nk = p.causal ? p.pos[t] + 1 : p.n_ctx[utt];
     const float scale = 1.0f / sqrtf((float)DH);
     const int ld = p.H * DH;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");      // the following GEMM may start prefetching its weights
     if (p.pdl) {
         // launched as a programmatic dependent of the QKV GEMM: the old keys' K / V rows do not depend on it, so they are
         // pulled into L2 while that kernel is still running; q and the new key's row are read after the wait
@@ -430,6 +431,7 @@ __global__ void __launch_bounds__(kXT) xattn_folded_kernel(const XFoldParams p) 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int d = p.d, dc = d / kXC, c0 = rank * dc, E = p.n_ctx[u];
     float * xr = p.x + (size_t)u * d;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");      // the following GEMM may start prefetching its weights
     {
         // programmatic dependent of the O-projection GEMM: this CTA's quarter of the (static) tables is pulled into L2 while
         // that kernel is still running
