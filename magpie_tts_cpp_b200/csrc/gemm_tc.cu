@@ -35,6 +35,7 @@ __global__ void __launch_bounds__(256) pack_x_kernel(const float * X, int ldx, i
                                                      bf * hi, bf * lo) {
     __shared__ float red[32];
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");     // let the GEMM's CTAs start prefetching weights
+    asm volatile("griddepcontrol.wait;" ::: "memory");                  // (itself launched as a programmatic dependent of the previous kernel)
     const int m = blockIdx.x, tid = threadIdx.x;
     const int KT = K / 64;
     const bool valid = m < M;
@@ -238,7 +239,13 @@ bool launch_linear_tc(const LinearArgs & a, cudaStream_t stream) {
     bf * hi = (bf *)a.tc_scratch;
     bf * lo = hi + (size_t)Mpad * K;
     if (!a.x_prepacked) {
-        pack_x_kernel<<<Mpad, 256, 0, stream>>>(a.X, a.ldx, M, K, a.ln_w, a.eps, MT, hi, lo);
+        cudaLaunchConfig_t pc = {};
+        pc.gridDim = dim3(Mpad); pc.blockDim = dim3(256); pc.dynamicSmemBytes = 0; pc.stream = stream;
+        cudaLaunchAttribute pa[1];
+        pa[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        pa[0].val.programmaticStreamSerializationAllowed = 1;
+        pc.attrs = pa; pc.numAttrs = 1;
+        MGB_CUDA_TRY(cudaLaunchKernelEx(&pc, pack_x_kernel, a.X, a.ldx, M, K, a.ln_w, a.eps, MT, hi, lo));
         MGB_LAUNCH_CHECK();
     }
     TcEpi e;
