@@ -444,6 +444,23 @@ def test_folded_cross_attention_matches_unfolded_kernels(B, full_model_path, ful
     m.close()
 
 
+@pytest.mark.parametrize("nb", [70, 130])
+def test_large_batches_take_the_multi_tile_paths(B, full_model_path, full_oracle, nb):
+    """More than 64 utterances: two 64-token tiles (70) / 128-token GEMM tiles and > 1 owned utterance per CTA in the batched
+    local transformer (130).  Every row must reproduce the oracle (bf16 bar) and equal rows must give equal results."""
+    m = B.Model(full_model_path, 0, B.PREC_BF16)
+    s = m.session(batch=nb, max_text=32)
+    s.encode_text([HELLO] * nb, want_output=False)
+    s.prefill([0] * nb)
+    codes = np.repeat(full_oracle["codes"][None, :4], nb, axis=0)
+    hid, lg, gr = s.teacher_forced(codes)
+    for b in (0, 63, 64, nb - 1):
+        close(hid[b], full_oracle["hid"][:4], 2e-2)
+        close(lg[b], full_oracle["lg"][:4], 2e-2)
+    np.testing.assert_array_equal(gr[0], gr[nb - 1])
+    s.close(); m.close()
+
+
 def test_batched_local_transformer_matches_per_utterance_kernel(B, full_model_path, full_oracle, monkeypatch):
     """bf16, 20 utterances: the weight-stationary persistent LT (lt_batch.cu, default for >= 16 utterances) against the
     one-cluster-per-utterance kernel (MGB_NO_LT_BATCH=1) and the oracle; same bf16 weights and f32 arithmetic, so the two
