@@ -827,18 +827,33 @@ int mgb_codec_decode(mgb_codec * cc, const int32_t * codes, int batch, int n_fra
     if (rc != MGB_OK) return rc;
     const size_t ns = (size_t)batch * n_frames * c->hp.hop_length;
     if (!grow((void **)&c->d_pcm, &c->pcm_cap, ns * 4)) return MGB_ECUDA;
-    // bound scratch memory: decode utterances in groups of <= ~8K frames
+    // bound scratch memory: decode utterances in groups of <= ~8K frames.  All groups are enqueued first; the PCM of
+    // group g is then copied back while the kernels of the later groups are still running (events per group).
     const int per = std::max(1, 8192 / n_frames);
+    const int n_groups = (batch + per - 1) / per;
+    while ((int)c->group_events.size() < n_groups) {
+        cudaEvent_t e = nullptr;
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { set_error("codec: event creation failed"); return MGB_ECUDA; }
+        c->group_events.push_back(e);
+    }
     const int64_t l0 = g_launch_counter;
     cudaEventRecord((cudaEvent_t)c->ev0, st);
-    for (int b0 = 0; b0 < batch; b0 += per) {
-        const int nb = std::min(per, batch - b0);
+    for (int g = 0; g < n_groups; g++) {
+        const int b0 = g * per, nb = std::min(per, batch - b0);
         if (!codec_decode_device(*c, c->d_codes + (size_t)b0 * 8 * n_frames, nb, n_frames,
                                  c->d_pcm + (size_t)b0 * n_frames * c->hp.hop_length, st)) return MGB_ECUDA;
+        cudaEventRecord((cudaEvent_t)c->group_events[g], st);
     }
     cudaEventRecord((cudaEvent_t)c->ev1, st);
-    if (cudaMemcpyAsync(pcm_out, c->d_pcm, ns * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
-        cudaStreamSynchronize(st) != cudaSuccess) {
+    for (int g = 0; g < n_groups; g++) {
+        const int b0 = g * per, nb = std::min(per, batch - b0);
+        const size_t off = (size_t)b0 * n_frames * c->hp.hop_length, cnt = (size_t)nb * n_frames * c->hp.hop_length;
+        if (cudaEventSynchronize((cudaEvent_t)c->group_events[g]) != cudaSuccess ||
+            cudaMemcpy(pcm_out + off, c->d_pcm + off, cnt * 4, cudaMemcpyDeviceToHost) != cudaSuccess) {
+            set_error(std::string("magpie_codec_decode: ") + cudaGetErrorString(cudaGetLastError())); return MGB_ECUDA;
+        }
+    }
+    if (cudaStreamSynchronize(st) != cudaSuccess) {
         set_error(std::string("magpie_codec_decode: ") + cudaGetErrorString(cudaGetLastError())); return MGB_ECUDA;
     }
     cudaEventElapsedTime(&c->last_ms, (cudaEvent_t)c->ev0, (cudaEvent_t)c->ev1);

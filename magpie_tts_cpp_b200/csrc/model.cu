@@ -266,6 +266,7 @@ Codec::~Codec() {
     if (d_pcm) cudaFree(d_pcm);
     if (ev0) cudaEventDestroy((cudaEvent_t)ev0);
     if (ev1) cudaEventDestroy((cudaEvent_t)ev1);
+    for (void * e : group_events) cudaEventDestroy((cudaEvent_t)e);
     if (stream) cudaStreamDestroy((cudaStream_t)stream);
 }
 

@@ -90,6 +90,7 @@ struct Codec {
     float * d_pcm = nullptr; size_t pcm_cap = 0;
     void * stream = nullptr;     // cudaStream_t
     void * ev0 = nullptr, * ev1 = nullptr;
+    std::vector<void *> group_events;     // one per utterance group of a decode call (D2H of a group overlaps later groups)
     float last_ms = 0.0f; int64_t last_launches = 0;
     ~Codec();
 };
