@@ -42,7 +42,8 @@ constexpr int kRingBytes = 112 * 1024;
 constexpr int D = 768, F = 3072, H = 12, DH = 64, LD = 256, LF = 1024;
 constexpr int kMaxSplit = 6;
 // rows per CTA (multiples of 3 = one packet)
-constexpr int RQ = 18, RO = 6, RF1 = 21, RF2 = 6, RIN = 3, RLQ = 6, RLO = 3, RLF1 = 9, RLF2 = 3, ROUT = 15;
+constexpr int RQ = 18, RO = 6, RF1 = 21, RF2 = 6, RIN = 3, RLQ = 9, RLF1 = 9, RLF2 = 3, ROUT = 15;
+constexpr int LQ = 4 * LD;           // local transformer: q | k | hi(Wo Wv n) | lo(Wo Wv n) rows
 constexpr int kSlicesPerFrameLayer = 4;
 constexpr int kVecFloats = 4800;                             // >= max(F, H*kMaxSplit*66, 2025 + 2048)
 constexpr int kPartStride = 12;
@@ -102,15 +103,15 @@ __device__ __forceinline__ void st_pkt(uint4 * p, float a, float b, float c, uns
 struct alignas(128) LoopSmem {
     unsigned char ring[kRingBytes];
     // local-transformer layer slices, resident for the whole launch
-    bf w_in[RIN * D]; bf w_qkv[RLQ * LD]; bf w_o[RLO * LD]; bf w_ff1[RLF1 * LD]; bf w_ff2[RLF2 * LF];
+    bf w_in[RIN * D]; bf w_qkv[RLQ * LD]; bf w_ff1[RLF1 * LD]; bf w_ff2[RLF2 * LF];
     alignas(16) float xs[D];        // residual stream (full vector, refreshed by every x exchange)
     alignas(16) float vec[kVecFloats];   // staged GEMV input / attention partials / gathered logits
     alignas(16) float av[D];        // combined attention output; final hidden
     alignas(16) float part[24 * kPartStride];   // GEMV partial sums [row][k segment]
     alignas(16) float am[16], al[16], aacc[kCW * 64], aout[68];
     alignas(16) float qh[DH], knew[DH], vnew[DH];
-    alignas(16) float lx[LD], lx1[LD], latt[LD], lhout[LD];
-    alignas(16) float lqkv[8][3 * LD];   // local transformer: [q | k | v] of every position of the frame
+    alignas(16) float lx[LD], lx1[LD], lhout[LD];
+    alignas(16) float lqkv[8][3 * LD];   // local transformer: [q | k | vo] of every position of the frame (vo = Wo Wv n = hi + lo rows)
     alignas(16) float ltpos[8 * LD];
     alignas(16) float sc[32];
     alignas(16) float outv[24];
@@ -154,13 +155,11 @@ __device__ __forceinline__ Slice frame_slice(const FrameLoopParams & p, int j, i
 __device__ void prefetch_lane(LoopSmem & S, const FrameLoopParams & p, int b) {
     // resident local-transformer slices
     {
-        const Slice a = make_slice(p.lt_in_w, LD, D, RIN, b), q = make_slice(p.lt_qkv, 3 * LD, LD, RLQ, b),
-                    o = make_slice(p.lt_o, LD, LD, RLO, b), f1 = make_slice(p.lt_ff1, LF, LD, RLF1, b),
-                    f2 = make_slice(p.lt_ff2, LD, LF, RLF2, b);
-        mbar_expect_tx(&S.res_bar, a.bytes + q.bytes + o.bytes + f1.bytes + f2.bytes);
+        const Slice a = make_slice(p.lt_in_w, LD, D, RIN, b), q = make_slice(p.lt_qkvo, LQ, LD, RLQ, b),
+                    f1 = make_slice(p.lt_ff1, LF, LD, RLF1, b), f2 = make_slice(p.lt_ff2, LD, LF, RLF2, b);
+        mbar_expect_tx(&S.res_bar, a.bytes + q.bytes + f1.bytes + f2.bytes);
         if (a.bytes) bulk_g2s(S.w_in, a.src, a.bytes, &S.res_bar);
         if (q.bytes) bulk_g2s(S.w_qkv, q.src, q.bytes, &S.res_bar);
-        if (o.bytes) bulk_g2s(S.w_o, o.src, o.bytes, &S.res_bar);
         if (f1.bytes) bulk_g2s(S.w_ff1, f1.src, f1.bytes, &S.res_bar);
         if (f2.bytes) bulk_g2s(S.w_ff2, f2.src, f2.bytes, &S.res_bar);
     }
@@ -879,16 +878,22 @@ __global__ void __launch_bounds__(kThreads, 1) frame_loop_kernel(const FrameLoop
                 }
                 LOOP_STAMP();
                 ln3<LD>(S, lv, w3, S.vec, p.eps, c);
-                const int r0 = b * RLQ, nr = max(0, min(RLQ, 3 * LD - r0));
+                const int r0 = b * RLQ, nr = max(0, min(RLQ, LQ - r0));
                 gemv_rows<1, 1>(S.w_qkv, nr, S.vec, S.part, c);
                 cbar();
                 emit_rows<1, EPI_NONE>(S, p, c, T_QKV, r0, nr, nullptr, nullptr, nullptr);
                 c.seq++;
             }
             LOOP_STAMP();
-            // ---- B: attention over the <= 8 positions (redundant per CTA); O + residual ------------------------
+            // ---- B: attention over the <= 8 positions, redundantly in every CTA.  The O-projection is folded into the value
+            //      rows (vo_j = Wo Wv n_j, hi + lo), so x1 = x + sum_j p_j vo_j needs no GEMV and NO exchange of its own ----
             {
-                poll_vec(c.xin + p.xoff[T_QKV], LD, c.seq - 1, qkv, 3 * LD, ctid);
+                poll_vec(c.xin + p.xoff[T_QKV], (LQ + 2) / 3, c.seq - 1, S.vec, LQ, ctid);
+                cbar();
+                if (ctid < LD) {
+                    qkv[ctid] = S.vec[ctid]; qkv[LD + ctid] = S.vec[LD + ctid];
+                    qkv[2 * LD + ctid] = S.vec[2 * LD + ctid] + S.vec[3 * LD + ctid];
+                }
                 cbar();
                 LOOP_STAMP();
                 if (cw <= cb) {
@@ -903,22 +908,22 @@ __global__ void __launch_bounds__(kThreads, 1) frame_loop_kernel(const FrameLoop
                     float mxs = S.sc[0];
                     for (int j = 1; j <= cb; j++) mxs = fmaxf(mxs, S.sc[j]);
                     float sum = 0.0f, o = 0.0f;
-                    for (int j = 0; j <= cb; j++) { const float e = expf(S.sc[j] - mxs); sum += e; o = fmaf(e, S.lqkv[j][2 * LD + ctid], o); }
-                    S.latt[ctid] = o * (1.0f / sum);
+                    for (int j = 0; j <= cb; j++) {
+                        const float e = expf(S.sc[j] - mxs);
+                        sum += e;
+                        o = fmaf(e, S.lqkv[j][2 * LD + ctid], o);
+                    }
+                    S.lx1[ctid] = S.lx[ctid] + o * (1.0f / sum);
                 }
                 cbar();
-                const int r0 = b * RLO, nr = max(0, min(RLO, LD - r0));
-                gemv_rows<1, 1>(S.w_o, nr, S.latt, S.part, c);
-                cbar();
-                emit_rows<1, EPI_RES>(S, p, c, T_X1, r0, nr, S.lx, nullptr, nullptr);
-                c.seq++;
             }
             LOOP_STAMP();
             // ---- C: LN -> FFN1 -> GELU -----------------------------------------------------------------------------
             {
                 float w3[3], lv[3];
                 ln_weights3<LD>(p.lt_norm_ff, ctid, w3);
-                load3_poll<LD>(c.xin + p.xoff[T_X1], c.seq - 1, S.lx1, ctid, lv);
+#pragma unroll
+                for (int q = 0; q < 3; q++) lv[q] = (own3l && 3 * ctid + q < LD) ? S.lx1[3 * ctid + q] : 0.0f;
                 LOOP_STAMP();
                 ln3<LD>(S, lv, w3, S.vec, p.eps, c);
                 const int r0 = b * RLF1, nr = max(0, min(RLF1, LF - r0));
@@ -1070,7 +1075,7 @@ bool frame_loop_shape_ok(int d, int f, int h, int ld, int lf, int V, int L) {
 }
 
 void frame_loop_xchg_layout(int V, int * xoff) {
-    const int n[X_COUNT] = {3 * D / 3, H * kMaxSplit * 22, D / 3, D / 3, F / 3, D / 3, (LD + 2) / 3, LD, (LD + 2) / 3, (LF + 2) / 3,
+    const int n[X_COUNT] = {3 * D / 3, H * kMaxSplit * 22, D / 3, D / 3, F / 3, D / 3, (LD + 2) / 3, (LQ + 2) / 3, (LD + 2) / 3, (LF + 2) / 3,
                             (LD + 2) / 3, 160, (V + 2) / 3 + 8};
     int o = 0;
     for (int i = 0; i < X_COUNT; i++) { xoff[i] = o; o += (n[i] + 7) & ~7; }     // 128-byte aligned starts

@@ -29,7 +29,8 @@ struct FrameLoopParams {
     // local transformer
     int V;
     const void * lt_in_w; const float * lt_in_b; const float * lt_pos; const float * lt_norm_self; const float * lt_norm_ff;
-    const void * lt_qkv, * lt_o, * lt_ff1, * lt_ff2; const void * lt_out_w[8]; const float * lt_out_b[8];
+    const void * lt_qkvo;            // [4*LD][LD] bf16: [Wq; Wk; hi(Wo Wv); lo(Wo Wv)] (model.cu)
+    const void * lt_ff1, * lt_ff2; const void * lt_out_w[8]; const float * lt_out_b[8];
     const float * lt_in_table[8];
     // loop control
     int n_steps, pos0, step0, row0, min_frames, teacher, ignore_eos;

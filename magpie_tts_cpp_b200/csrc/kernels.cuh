@@ -76,6 +76,8 @@ bool launch_text_embed(const Model & m, const int32_t * tokens /*[M] compact*/, 
 // y[t] = LN(x[t]) * w                                              (magpie.cpp:2237-2259)
 bool launch_layer_norm(const float * x, const float * w, float eps, int M, int d, float * y, cudaStream_t stream);
 bool launch_add_one(int32_t * v, int n, cudaStream_t stream);
+// bf16 qkv [3L][L], o [L][L] -> bf16 [4L][L] = [Wq; Wk; hi(Wo Wv); lo(Wo Wv)]
+bool launch_lt_fold_ov(const void * qkv, const void * o, int L, void * out, cudaStream_t stream);
 
 // ---- local transformer + sampler (magpie.cpp:946-1048, 1072-1317) ------------------------------
 struct LtArgs {

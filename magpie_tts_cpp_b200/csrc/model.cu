@@ -221,6 +221,18 @@ Model * load_model(const char * path, int device, int precision) {
         if (!launch_linear(a, nullptr)) return nullptr;
     }
     if (cudaDeviceSynchronize() != cudaSuccess) { set_error("magpie_init: building the LT feedback table failed"); return nullptr; }
+    // local transformer, bf16: [Wq; Wk; hi(Wo Wv); lo(Wo Wv)] -- with the O-projection folded into the value rows the attention
+    // output needs no GEMV of its own (o . sum_j p_j v_j = sum_j p_j (Wo Wv) n_j); the product is kept as a bf16 hi + lo pair
+    if (precision == MGB_PREC_BF16) {
+        const int L = hp.lt_dim;
+        void * t = nullptr;
+        if (cudaMalloc(&t, (size_t)4 * L * L * 2) != cudaSuccess) { set_error("cudaMalloc failed"); return nullptr; }
+        M->allocations.push_back(t);
+        M->lt_qkvo = t;
+        if (!launch_lt_fold_ov(M->lt_qkv.w, M->lt_o.w, L, t, nullptr) || cudaDeviceSynchronize() != cudaSuccess) {
+            set_error("magpie_init: folding the LT output projection failed"); return nullptr;
+        }
+    }
 
     // bf16 models: tensor-core tile images of the matrices the batched paths multiply with (gemm_tc.cu);
     // MGB_NO_TC=1 keeps the CUDA-core kernels (A/B tests)

@@ -572,6 +572,24 @@ bool launch_layer_norm(const float * x, const float * w, float eps, int M, int d
     return true;
 }
 
+__global__ void lt_fold_ov_kernel(const __nv_bfloat16 * qkv, const __nv_bfloat16 * o, int L, __nv_bfloat16 * out) {
+    const int i = blockIdx.x, k = threadIdx.x;           // output row i, column k
+    if (k >= L) return;
+    out[(size_t)i * L + k] = qkv[(size_t)i * L + k];                              // Wq
+    out[(size_t)(L + i) * L + k] = qkv[(size_t)(L + i) * L + k];                  // Wk
+    float acc = 0.0f;
+    for (int j = 0; j < L; j++) acc = fmaf(__bfloat162float(o[(size_t)i * L + j]), __bfloat162float(qkv[(size_t)(2 * L + j) * L + k]), acc);
+    const __nv_bfloat16 h = __float2bfloat16_rn(acc);
+    out[(size_t)(2 * L + i) * L + k] = h;
+    out[(size_t)(3 * L + i) * L + k] = __float2bfloat16_rn(acc - __bfloat162float(h));
+}
+bool launch_lt_fold_ov(const void * qkv, const void * o, int L, void * out, cudaStream_t stream) {
+    if (L > 1024) { set_error("lt_fold_ov: lt_dim too large"); return false; }
+    lt_fold_ov_kernel<<<L, L, 0, stream>>>((const __nv_bfloat16 *)qkv, (const __nv_bfloat16 *)o, L, (__nv_bfloat16 *)out);
+    MGB_LAUNCH_CHECK();
+    return true;
+}
+
 bool launch_add_one(int32_t * v, int n, cudaStream_t stream) {
     add_one_kernel<<<(n + 127) / 128, 128, 0, stream>>>(v, n);
     MGB_LAUNCH_CHECK();
