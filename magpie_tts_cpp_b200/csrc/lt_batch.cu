@@ -7,7 +7,7 @@
 // kept as f32: 141 KB), and each phase computes those rows for ALL utterances from an activation tile staged through shared memory:
 // each weight element is read from HBM/L2 once per step, the 8 x 7 dependent phases are separated by grid barriers.
 //
-//   per codebook:  QKV (LN prologue) | attention (utterance-owner CTAs) | O + residual | FF1 (LN prologue, GELU) |
+//   per codebook:  QKV (LN prologue) | attention + folded O-projection + residual (utterance-owner CTAs) | FF1 (LN prologue, GELU) |
 //                  FF2 + residual | out-projection + bias | mask / argmax / top-k sample / feedback gather (owner CTAs)
 #include <cooperative_groups.h>
 #include <cstdlib>
@@ -28,6 +28,7 @@ constexpr int kTileFloats = 64 * 260;          // activation tile staged per pas
 struct BParams {
     LtParams p;
     float * seq, * q, * kc, * vc, * att, * x1, * ffh, * hout, * logits;     // [B][..] f32 scratch
+    const void * qkvo;               // [4L][L] bf16: [Wq; Wk; hi(Wo Wv); lo(Wo Wv)]
     unsigned long long * dbg;        // MGB_LT_DBG: globaltimer stamps of CTA 0 at every phase boundary
 };
 
@@ -136,18 +137,23 @@ __global__ void __launch_bounds__(kLtThreads, 1) lt_batch_kernel(const BParams b
     float * wbase = reinterpret_cast<float *>(smem_raw + (size_t)kTileFloats * 4);
 
     // ---- this CTA's row slices of every matrix, resident for the whole launch ----
-    const Slice s_in = slice_of(L, c, G), s_qkv = slice_of(3 * L, c, G), s_o = slice_of(L, c, G), s_f1 = slice_of(F, c, G),
+    const Slice s_in = slice_of(L, c, G), s_qkv = slice_of(3 * L, c, G), s_f1 = slice_of(F, c, G),
                 s_f2 = slice_of(L, c, G), s_out = slice_of(V, c, G);
     float * w_in = wbase;
     float * w_qkv = w_in + (size_t)(s_in.n1 - s_in.n0) * d;
-    float * w_o = w_qkv + (size_t)(s_qkv.n1 - s_qkv.n0) * L;
-    float * w_f1 = w_o + (size_t)(s_o.n1 - s_o.n0) * L;
+    float * w_f1 = w_qkv + (size_t)(s_qkv.n1 - s_qkv.n0) * L;
     float * w_f2 = w_f1 + (size_t)(s_f1.n1 - s_f1.n0) * L;
     float * w_out0 = w_f2 + (size_t)(s_f2.n1 - s_f2.n0) * F;
     const size_t out_elems = (size_t)(s_out.n1 - s_out.n0) * L;
     load_rows(w_in, p.in_w, d, s_in);
-    load_rows(w_qkv, p.qkv_w, L, s_qkv);
-    load_rows(w_o, p.o_w, L, s_o);
+    // q and k rows as they are; value rows carry the folded output projection vo = (Wo Wv) n, stored as a bf16 hi + lo pair
+    // (model.cu): rows [2L, 3L) = hi, [3L, 4L) = lo, summed here into one f32 row
+    for (int r = s_qkv.n0; r < s_qkv.n1; r++) {
+        const bf * src = reinterpret_cast<const bf *>(bp.qkvo) + (size_t)r * L;
+        float * dst = w_qkv + (size_t)(r - s_qkv.n0) * L;
+        for (int k = tid; k < L; k += kLtThreads)
+            dst[k] = r < 2 * L ? __bfloat162float(src[k]) : __bfloat162float(src[k]) + __bfloat162float(src[(size_t)L * L + k]);
+    }
     load_rows(w_f1, p.ff1_w, L, s_f1);
     load_rows(w_f2, p.ff2_w, F, s_f2);
     for (int cb = 0; cb < 8; cb++) load_rows(w_out0 + cb * out_elems, p.out_w[cb], L, s_out);
@@ -190,7 +196,8 @@ __global__ void __launch_bounds__(kLtThreads, 1) lt_batch_kernel(const BParams b
                        else bp.vc[((size_t)u * 8 + cb) * L + (n - 2 * L)] = v;
                    });
         stamp(); grid.sync(); stamp();
-        // single-head causal attention over positions 0..cb, one owner CTA per utterance (magpie.cpp:946-1013)
+        // single-head causal attention over positions 0..cb, one owner CTA per utterance (magpie.cpp:946-1013); with the
+        // output projection folded into the value rows, x1 = (seq + pos) + sum_j p_j vo_j comes out of the same phase
         for (int u = c; u < B; u += G) {
             __syncthreads();
             float * sc = tile;             // scores[8]
@@ -212,13 +219,9 @@ __global__ void __launch_bounds__(kLtThreads, 1) lt_batch_kernel(const BParams b
                 float o = 0.0f;
 #pragma unroll
                 for (int j = 0; j < 8; j++) if (j <= cb) o = fmaf(e[j] * inv, bp.vc[((size_t)u * 8 + j) * L + tid], o);
-                bp.att[(size_t)u * L + tid] = o;
+                bp.x1[(size_t)u * L + tid] = (bp.seq[(size_t)u * L + tid] + pos[tid]) + o;
             }
         }
-        stamp(); grid.sync(); stamp();
-        // x1 = (seq + pos) + o_net . att
-        gemv_phase<false>(w_o, s_o, L, bp.att, L, B, tile, no_prep,
-                   [&](int u, int n, float v) { bp.x1[(size_t)u * L + n] = v + (bp.seq[(size_t)u * L + n] + pos[n]); });
         stamp(); grid.sync(); stamp();
         // ffh = gelu(ff1 . LN(x1))
 #pragma unroll
@@ -292,7 +295,7 @@ size_t slice_smem_bytes(const Model & m, int G) {
     const mgb_hparams & hp = m.hp;
     auto rows = [&](int N) { return (size_t)((N + G - 1) / G); };         // largest balanced slice
     const int L = hp.lt_dim, F = hp.lt_ffn_dim, d = hp.d_model, V = hp.vocab_per_cb;
-    size_t e = rows(L) * d + rows(3 * L) * L + rows(L) * L + rows(F) * L + rows(L) * F + 8 * rows(V) * L;
+    size_t e = rows(L) * d + rows(3 * L) * L + rows(F) * L + rows(L) * F + 8 * rows(V) * L;
     return e * sizeof(float);
 }
 
@@ -308,7 +311,7 @@ size_t lt_batch_scratch_bytes(const Model & m, int B) {
 bool lt_batch_supported(const Model & m, int B) {
     if (getenv("MGB_NO_LT_BATCH") != nullptr) return false;
     const mgb_hparams & hp = m.hp;
-    if (m.precision != MGB_PREC_BF16 || !m.lt_in_table[0] || B < 16) return false;
+    if (m.precision != MGB_PREC_BF16 || !m.lt_in_table[0] || !m.lt_qkvo || B < 16) return false;
     if (hp.lt_dim != 256 || hp.lt_ffn_dim > kF || hp.lt_ffn_dim % 256 != 0 || hp.d_model % 256 != 0 || hp.d_model > kD || hp.vocab_per_cb > kV) return false;
     return B <= 8 * 132;
 }
@@ -329,6 +332,7 @@ bool launch_lt_batch(const Model & m, const LtParams & p, void * scratch, size_t
     }
     BParams bp;
     bp.p = p;
+    bp.qkvo = m.lt_qkvo;
     const size_t B = p.B, L = p.L, F = p.F, V = p.V;
     float * f = (float *)scratch;
     bp.seq = f; f += B * L; bp.q = f; f += B * L; bp.kc = f; f += B * 8 * L; bp.vc = f; f += B * 8 * L;
