@@ -335,7 +335,7 @@ mgb_session * mgb_session_new(mgb_model * mm, int batch, int max_text, int max_s
     // batch 1, bf16, Magpie-357M shapes: the whole frame loop is one persistent kernel (MGB_NO_LOOPK=1 disables it)
     if (batch == 1 && m->precision == MGB_PREC_BF16 && getenv("MGB_NO_LOOPK") == nullptr &&
         frame_loop_shape_ok(hp.d_model, hp.d_ffn, hp.dec_sa_heads, hp.lt_dim, hp.lt_ffn_dim, hp.vocab_per_cb, hp.dec_layers) &&
-        dxa == 128 && m->lt_in_table[0] && m->lt_qkvo) {
+        dxa == 128 && m->lt_in_table[0] && m->lt_qkvo && m->lt_qkv_tab) {
         const int g = frame_loop_max_grid();
         if (g > 0) {
             frame_loop_xchg_layout(hp.vocab_per_cb, s->xoff);
@@ -638,7 +638,7 @@ static int run_loop_persistent(Session & s, const LoopCfg & c, int * steps_run) 
     p.kcache = s.kc; p.vcache = s.vc; p.kv_layer_stride = (size_t)s.B * s.max_seq * hp.d_model;
     p.V = hp.vocab_per_cb;
     p.lt_in_w = m.lt_in_w.w; p.lt_in_b = m.lt_in_b; p.lt_pos = m.lt_pos; p.lt_norm_self = m.lt_norm_self; p.lt_norm_ff = m.lt_norm_ff;
-    p.lt_qkvo = m.lt_qkvo; p.lt_ff1 = m.lt_ff1.w; p.lt_ff2 = m.lt_ff2.w;
+    p.lt_qkvo = m.lt_qkvo; p.lt_qkv_tab = m.lt_qkv_tab; p.lt_ff1 = m.lt_ff1.w; p.lt_ff2 = m.lt_ff2.w;
     p.n_steps = c.T; p.pos0 = s.pos; p.step0 = 0; p.row0 = 0; p.min_frames = c.teacher ? 0 : 4;       // magpie.cpp:4267, 4325
     p.teacher = c.teacher ? 1 : 0; p.ignore_eos = c.ignore_eos ? 1 : 0;
     p.temperature = c.temperature; p.top_k = c.top_k; p.seed = c.seed;

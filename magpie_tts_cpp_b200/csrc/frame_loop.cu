@@ -861,21 +861,17 @@ __global__ void __launch_bounds__(kThreads, 1) frame_loop_kernel(const FrameLoop
             c.seq++;
         }
         float fb[3] = {0.0f, 0.0f, 0.0f};     // feedback row elements 3i .. 3i+2 for the next codebook
+        int fed_prev = 0;                      // code fed back by the previous codebook
 #pragma unroll 1
         for (int cb = 0; cb < 8; cb++) {
             float * qkv = S.lqkv[cb];         // [q | k | v] of position cb
-            // ---- A: x = seq + pos; LN -> QKV --------------------------------------------------------------------
-            {
+            // ---- A (position 0 only): x = seq + pos; LN -> QKV.  Positions 1..7 see x = P_cb[fed] + pos[cb], a function of
+            //      (codebook, fed code) alone: their [q | k | vo] row is GATHERED from a table built at load (model.cu),
+            //      which removes the LayerNorm, the GEMV and the exchange of its result ------------------------------
+            if (cb == 0) {
                 float w3[3], lv[3];
                 ln_weights3<LD>(p.lt_norm_self, ctid, w3);
-                if (cb == 0) load3_poll<LD>(c.xin + p.xoff[T_SEQ0], c.seq - 1, S.lx, ctid, lv);
-                else {
-#pragma unroll
-                    for (int q = 0; q < 3; q++) {
-                        lv[q] = 0.0f;
-                        if (own3l && 3 * ctid + q < LD) { lv[q] = fb[q] + S.ltpos[cb * LD + 3 * ctid + q]; S.lx[3 * ctid + q] = lv[q]; }
-                    }
-                }
+                load3_poll<LD>(c.xin + p.xoff[T_SEQ0], c.seq - 1, S.lx, ctid, lv);
                 LOOP_STAMP();
                 ln3<LD>(S, lv, w3, S.vec, p.eps, c);
                 const int r0 = b * RLQ, nr = max(0, min(RLQ, LQ - r0));
@@ -883,13 +879,29 @@ __global__ void __launch_bounds__(kThreads, 1) frame_loop_kernel(const FrameLoop
                 cbar();
                 emit_rows<1, EPI_NONE>(S, p, c, T_QKV, r0, nr, nullptr, nullptr, nullptr);
                 c.seq++;
+            } else {
+                if (own3l) {
+#pragma unroll
+                    for (int q = 0; q < 3; q++) if (3 * ctid + q < LD) S.lx[3 * ctid + q] = fb[q] + S.ltpos[cb * LD + 3 * ctid + q];
+                }
+                LOOP_STAMP();
             }
             LOOP_STAMP();
             // ---- B: attention over the <= 8 positions, redundantly in every CTA.  The O-projection is folded into the value
             //      rows (vo_j = Wo Wv n_j, hi + lo), so x1 = x + sum_j p_j vo_j needs no GEMV and NO exchange of its own ----
             {
-                poll_vec(c.xin + p.xoff[T_QKV], (LQ + 2) / 3, c.seq - 1, S.vec, LQ, ctid);
-                cbar();
+                if (cb == 0) {
+                    poll_vec(c.xin + p.xoff[T_QKV], (LQ + 2) / 3, c.seq - 1, S.vec, LQ, ctid);
+                    cbar();
+                } else {
+                    const float4 * row = reinterpret_cast<const float4 *>(p.lt_qkv_tab + ((size_t)(cb - 1) * V + fed_prev) * (3 * LD));
+                    if (ctid < 3 * LD / 4) {
+                        const float4 f = __ldg(row + ctid);
+                        S.vec[4 * ctid] = f.x; S.vec[4 * ctid + 1] = f.y; S.vec[4 * ctid + 2] = f.z; S.vec[4 * ctid + 3] = f.w;
+                    }
+                    if (ctid < LD) S.vec[3 * LD + ctid] = 0.0f;       // no separate lo part: the table holds hi + lo
+                    cbar();
+                }
                 if (ctid < LD) {
                     qkv[ctid] = S.vec[ctid]; qkv[LD + ctid] = S.vec[LD + ctid];
                     qkv[2 * LD + ctid] = S.vec[2 * LD + ctid] + S.vec[3 * LD + ctid];
@@ -1023,6 +1035,7 @@ __global__ void __launch_bounds__(kThreads, 1) frame_loop_kernel(const FrameLoop
             hit_eos = hit_eos || pick == p.eos_id || am == p.eos_id;
             const int fed = p.forced ? p.forced[row * 8 + cb] : pick;
             if (b == 0 && ctid == 0) { p.argmax[row * 8 + cb] = am; p.sampled[row * 8 + cb] = pick; p.result[2 + cb] = fed; }
+            fed_prev = fed;
             // feedback: seq[cb+1] = row `fed` of P_cb (no 1/8 scale, magpie.cpp:1285-1291); next frame's embedding
             if (cb < 7 && own3l) {
 #pragma unroll

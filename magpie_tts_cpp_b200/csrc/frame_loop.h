@@ -32,6 +32,7 @@ struct FrameLoopParams {
     const void * lt_qkvo;            // [4*LD][LD] bf16: [Wq; Wk; hi(Wo Wv); lo(Wo Wv)] (model.cu)
     const void * lt_ff1, * lt_ff2; const void * lt_out_w[8]; const float * lt_out_b[8];
     const float * lt_in_table[8];
+    const float * lt_qkv_tab;        // [7][V][3*LD] f32: [q | k | vo] of LT position cb+1 for every fed code of codebook cb
     // loop control
     int n_steps, pos0, step0, row0, min_frames, teacher, ignore_eos;
     float temperature; int top_k; unsigned long long seed;

@@ -77,6 +77,9 @@ bool launch_text_embed(const Model & m, const int32_t * tokens /*[M] compact*/, 
 bool launch_layer_norm(const float * x, const float * w, float eps, int M, int d, float * y, cudaStream_t stream);
 bool launch_add_one(int32_t * v, int n, cudaStream_t stream);
 // bf16 qkv [3L][L], o [L][L] -> bf16 [4L][L] = [Wq; Wk; hi(Wo Wv); lo(Wo Wv)]
+// out[code] = [q | k | vo](LN(in_table[code] + pos; ln_w)) with the folded matrix qkvo ([Wq; Wk; hi; lo], bf16 [4L][L])
+bool launch_lt_qkv_table(const float * in_table, const float * pos, const float * ln_w, float eps, const void * qkvo, int V, int L,
+                         float * out, cudaStream_t stream);
 bool launch_lt_fold_ov(const void * qkv, const void * o, int L, void * out, cudaStream_t stream);
 
 // ---- local transformer + sampler (magpie.cpp:946-1048, 1072-1317) ------------------------------

@@ -232,6 +232,16 @@ Model * load_model(const char * path, int device, int precision) {
         if (!launch_lt_fold_ov(M->lt_qkv.w, M->lt_o.w, L, t, nullptr) || cudaDeviceSynchronize() != cudaSuccess) {
             set_error("magpie_init: folding the LT output projection failed"); return nullptr;
         }
+        // LT positions 1..7 see x = P_cb[code] + pos[cb+1], a function of (cb, code) only: their [q | k | vo] rows are tabulated
+        // (7 x V x 3L f32 = 43.5 MB), so those positions need neither LayerNorm + QKV GEMV nor the exchange of its result
+        void * tb = nullptr;
+        if (cudaMalloc(&tb, (size_t)7 * hp.vocab_per_cb * 3 * L * sizeof(float)) != cudaSuccess) { set_error("cudaMalloc failed"); return nullptr; }
+        M->allocations.push_back(tb);
+        M->lt_qkv_tab = (float *)tb;
+        for (int cb = 0; cb < 7; cb++)
+            if (!launch_lt_qkv_table(M->lt_in_table[cb], M->lt_pos + (size_t)(cb + 1) * L, M->lt_norm_self, hp.eps, t, hp.vocab_per_cb, L,
+                                     M->lt_qkv_tab + (size_t)cb * hp.vocab_per_cb * 3 * L, nullptr)) return nullptr;
+        if (cudaDeviceSynchronize() != cudaSuccess) { set_error("magpie_init: building the LT QKV table failed"); return nullptr; }
     }
 
     // bf16 models: tensor-core tile images of the matrices the batched paths multiply with (gemm_tc.cu);

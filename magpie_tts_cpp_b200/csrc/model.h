@@ -48,6 +48,7 @@ struct Model {
     float * lt_norm_self = nullptr, * lt_norm_ff = nullptr;
     DevMat lt_qkv, lt_o, lt_ff1, lt_ff2;
     DevMat lt_out_w[8]; float * lt_out_b[8] = {};
+    float * lt_qkv_tab = nullptr;           // f32 [7][V][3*lt_dim]: [q | k | Wo Wv n] of LT position cb+1 for every fed code of codebook cb (row gather instead of LN + QKV GEMV)
     void * lt_qkvo = nullptr;               // bf16 [4*lt_dim][lt_dim]: [Wq; Wk; hi(Wo Wv); lo(Wo Wv)] (frame_loop.cu: the O-projection folded into V)
     float * lt_in_table[8] = {};            // P_cb = E_cb . Win^T + b  [V][lt_dim] f32 (built on the device at load)
 

@@ -590,6 +590,47 @@ bool launch_lt_fold_ov(const void * qkv, const void * o, int L, void * out, cuda
     return true;
 }
 
+__global__ void __launch_bounds__(256) lt_qkv_table_kernel(const float * in_table, const float * pos, const float * ln_w, float eps,
+                                                           const __nv_bfloat16 * qkvo, int L, float * out) {
+    __shared__ float xn[1024];
+    __shared__ float red[32];
+    const int code = blockIdx.x, tid = threadIdx.x;
+    float v = 0.0f;
+    for (int i = tid; i < L; i += 256) v += in_table[(size_t)code * L + i] + pos[i];
+    const float mean = block_sum(v, red) / (float)L;
+    float s2 = 0.0f;
+    for (int i = tid; i < L; i += 256) { const float c = in_table[(size_t)code * L + i] + pos[i] - mean; s2 += c * c; }
+    const float scale = 1.0f / sqrtf(block_sum(s2, red) / (float)L + eps);
+    for (int i = tid; i < L; i += 256) xn[i] = ((in_table[(size_t)code * L + i] + pos[i] - mean) * scale) * ln_w[i];
+    __syncthreads();
+    // one warp per output row: coalesced 16-byte weight loads; rows [0, 2L) = q, k; rows [2L, 3L) = hi + lo of Wo Wv
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int r = warp; r < 3 * L; r += 8) {
+        float acc = 0.0f;
+        for (int k = lane * 8; k < L; k += 256) {
+            float w[8];
+            WT<__nv_bfloat16>::load(qkvo + (size_t)r * L + k, w);
+            if (r >= 2 * L) {
+                float w2[8];
+                WT<__nv_bfloat16>::load(qkvo + (size_t)(r + L) * L + k, w2);
+#pragma unroll
+                for (int q = 0; q < 8; q++) w[q] += w2[q];
+            }
+#pragma unroll
+            for (int q = 0; q < 8; q++) acc = fmaf(w[q], xn[k + q], acc);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) out[(size_t)code * 3 * L + r] = acc;
+    }
+}
+bool launch_lt_qkv_table(const float * in_table, const float * pos, const float * ln_w, float eps, const void * qkvo, int V, int L,
+                         float * out, cudaStream_t stream) {
+    if (L > 1024 || L % 8 != 0) { set_error("lt_qkv_table: lt_dim not supported"); return false; }
+    lt_qkv_table_kernel<<<V, 256, 0, stream>>>(in_table, pos, ln_w, eps, (const __nv_bfloat16 *)qkvo, L, out);
+    MGB_LAUNCH_CHECK();
+    return true;
+}
+
 bool launch_add_one(int32_t * v, int n, cudaStream_t stream) {
     add_one_kernel<<<(n + 127) / 128, 128, 0, stream>>>(v, n);
     MGB_LAUNCH_CHECK();
