@@ -28,6 +28,7 @@ constexpr int kTileFloats = 64 * 260;          // activation tile staged per pas
 struct BParams {
     LtParams p;
     float * seq, * q, * kc, * vc, * att, * x1, * ffh, * hout, * logits;     // [B][..] f32 scratch
+    const float * qkv_tab;           // [7][V][3L] f32: [q | k | vo] of position cb+1 per fed code of codebook cb (model.cu)
     const void * qkvo;               // [4L][L] bf16: [Wq; Wk; hi(Wo Wv); lo(Wo Wv)]
     unsigned long long * dbg;        // MGB_LT_DBG: globaltimer stamps of CTA 0 at every phase boundary
 };
@@ -182,47 +183,54 @@ __global__ void __launch_bounds__(kLtThreads, 1) lt_batch_kernel(const BParams b
 #pragma unroll
     for (int i = 0; i < 8; i++) hit_eos[i] = false;
 
-    for (int cb = 0; cb < 8; cb++) {
-        const float * pos = p.pos + cb * L;
-        // q | k | v = qkv_net . LN(seq + pos)   (magpie.cpp:1026-1030, 1501-1503)
-        float ln_add[8], ln_w[8];
-#pragma unroll
-        for (int k = 0; k < 8; k++) { ln_add[k] = pos[(tid & 31) + 32 * k]; ln_w[k] = p.norm_self[(tid & 31) + 32 * k]; }
-        gemv_phase<true>(w_qkv, s_qkv, L, bp.seq, L, B, tile,
-                   [&](int, float * row) { warp_layer_norm(row, ln_add, ln_w, p.eps); },
-                   [&](int u, int n, float v) {
-                       if (n < L) bp.q[(size_t)u * L + n] = v;
-                       else if (n < 2 * L) bp.kc[((size_t)u * 8 + cb) * L + (n - L)] = v;
-                       else bp.vc[((size_t)u * 8 + cb) * L + (n - 2 * L)] = v;
-                   });
-        stamp(); grid.sync(); stamp();
-        // single-head causal attention over positions 0..cb, one owner CTA per utterance (magpie.cpp:946-1013); with the
-        // output projection folded into the value rows, x1 = (seq + pos) + sum_j p_j vo_j comes out of the same phase
-        for (int u = c; u < B; u += G) {
-            __syncthreads();
-            float * sc = tile;             // scores[8]
-            const int warp = tid >> 5, lane = tid & 31;
-            if (warp <= cb) {
-                float s = 0.0f;
-                for (int i = lane; i < L; i += 32) s = fmaf(bp.kc[((size_t)u * 8 + warp) * L + i], bp.q[(size_t)u * L + i], s);
-                s = warp_sum(s);
-                if (lane == 0) sc[warp] = s * att_scale;
-            }
-            __syncthreads();
-            if (tid < L) {
-                float mxs = sc[0];
-                for (int j = 1; j <= cb; j++) mxs = fmaxf(mxs, sc[j]);
-                float e[8], sum = 0.0f;
-#pragma unroll
-                for (int j = 0; j < 8; j++) { e[j] = (j <= cb) ? expf(sc[j] - mxs) : 0.0f; sum += e[j]; }
-                const float inv = 1.0f / sum;
-                float o = 0.0f;
-#pragma unroll
-                for (int j = 0; j < 8; j++) if (j <= cb) o = fmaf(e[j] * inv, bp.vc[((size_t)u * 8 + j) * L + tid], o);
-                bp.x1[(size_t)u * L + tid] = (bp.seq[(size_t)u * L + tid] + pos[tid]) + o;
-            }
+    // attention of LT position `cbq` of utterance u by its owner CTA (magpie.cpp:946-1013): q from bp.q, keys / folded values of
+    // positions 0..cbq from bp.kc / bp.vc; with the output projection folded into the value rows,
+    // x1 = (seq + pos[cbq]) + sum_j p_j vo_j comes out directly.  `sc` = 8 floats of shared scratch.
+    auto attend = [&](int u, int cbq, float * sc) {
+        const int warp = tid >> 5, lane = tid & 31;
+        const float * posq = p.pos + cbq * L;
+        if (warp <= cbq) {
+            float s = 0.0f;
+            for (int i = lane; i < L; i += 32) s = fmaf(bp.kc[((size_t)u * 8 + warp) * L + i], bp.q[(size_t)u * L + i], s);
+            s = warp_sum(s);
+            if (lane == 0) sc[warp] = s * att_scale;
         }
-        stamp(); grid.sync(); stamp();
+        __syncthreads();
+        if (tid < L) {
+            float mxs = sc[0];
+            for (int j = 1; j <= cbq; j++) mxs = fmaxf(mxs, sc[j]);
+            float e[8], sum = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 8; j++) { e[j] = (j <= cbq) ? expf(sc[j] - mxs) : 0.0f; sum += e[j]; }
+            const float inv = 1.0f / sum;
+            float o = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 8; j++) if (j <= cbq) o = fmaf(e[j] * inv, bp.vc[((size_t)u * 8 + j) * L + tid], o);
+            bp.x1[(size_t)u * L + tid] = (bp.seq[(size_t)u * L + tid] + posq[tid]) + o;
+        }
+        __syncthreads();
+    };
+
+    for (int cb = 0; cb < 8; cb++) {
+        if (cb == 0) {
+            // position 0: q | k | vo = [Wq; Wk; Wo Wv] . LN(seq + pos[0])   (magpie.cpp:1026-1030, 1501-1503).  Positions 1..7 take
+            // their rows from the (codebook, fed code) table in the sampling phase below: no QKV phase, no attention phase.
+            const float * pos = p.pos;
+            float ln_add[8], ln_w[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) { ln_add[k] = pos[(tid & 31) + 32 * k]; ln_w[k] = p.norm_self[(tid & 31) + 32 * k]; }
+            gemv_phase<true>(w_qkv, s_qkv, L, bp.seq, L, B, tile,
+                       [&](int, float * row) { warp_layer_norm(row, ln_add, ln_w, p.eps); },
+                       [&](int u, int n, float v) {
+                           if (n < L) bp.q[(size_t)u * L + n] = v;
+                           else if (n < 2 * L) bp.kc[((size_t)u * 8) * L + (n - L)] = v;
+                           else bp.vc[((size_t)u * 8) * L + (n - 2 * L)] = v;
+                       });
+            stamp(); grid.sync(); stamp();
+            for (int u = c; u < B; u += G) { __syncthreads(); attend(u, 0, tile); }
+            stamp(); grid.sync(); stamp();
+        }
+        float ln_add[8], ln_w[8];
         // ffh = gelu(ff1 . LN(x1))
 #pragma unroll
         for (int k = 0; k < 8; k++) { ln_add[k] = 0.0f; ln_w[k] = p.norm_ff[(tid & 31) + 32 * k]; }
@@ -282,9 +290,18 @@ __global__ void __launch_bounds__(kLtThreads, 1) lt_batch_kernel(const BParams b
                 }
             }
             if (cb < 7) {
-                // seq[cb+1] = in_proj . E_cb[code] + b, folded at load into a table (model.cu)
+                // seq[cb+1] = in_proj . E_cb[code] + b and its [q | k | vo] row, both tabulated at load (model.cu); the owner CTA
+                // then runs the attention of position cb+1 right here
                 const int fed = forced ? forced[cb] : pick;
-                if (tid < L) bp.seq[(size_t)u * L + tid] = p.in_table[cb][(size_t)fed * L + tid];
+                if (tid < L) {
+                    const float * row = bp.qkv_tab + ((size_t)cb * V + fed) * (3 * L);
+                    bp.seq[(size_t)u * L + tid] = p.in_table[cb][(size_t)fed * L + tid];
+                    bp.q[(size_t)u * L + tid] = row[tid];
+                    bp.kc[((size_t)u * 8 + cb + 1) * L + tid] = row[L + tid];
+                    bp.vc[((size_t)u * 8 + cb + 1) * L + tid] = row[2 * L + tid];
+                }
+                __syncthreads();
+                attend(u, cb + 1, reinterpret_cast<float *>(S.hist));      // (the sampler's histogram is free again)
             }
         }
         if (cb < 7) { stamp(); grid.sync(); stamp(); }
@@ -311,7 +328,7 @@ size_t lt_batch_scratch_bytes(const Model & m, int B) {
 bool lt_batch_supported(const Model & m, int B) {
     if (getenv("MGB_NO_LT_BATCH") != nullptr) return false;
     const mgb_hparams & hp = m.hp;
-    if (m.precision != MGB_PREC_BF16 || !m.lt_in_table[0] || !m.lt_qkvo || B < 16) return false;
+    if (m.precision != MGB_PREC_BF16 || !m.lt_in_table[0] || !m.lt_qkvo || !m.lt_qkv_tab || B < 16) return false;
     if (hp.lt_dim != 256 || hp.lt_ffn_dim > kF || hp.lt_ffn_dim % 256 != 0 || hp.d_model % 256 != 0 || hp.d_model > kD || hp.vocab_per_cb > kV) return false;
     return B <= 8 * 132;
 }
@@ -332,7 +349,7 @@ bool launch_lt_batch(const Model & m, const LtParams & p, void * scratch, size_t
     }
     BParams bp;
     bp.p = p;
-    bp.qkvo = m.lt_qkvo;
+    bp.qkvo = m.lt_qkvo; bp.qkv_tab = m.lt_qkv_tab;
     const size_t B = p.B, L = p.L, F = p.F, V = p.V;
     float * f = (float *)scratch;
     bp.seq = f; f += B * L; bp.q = f; f += B * L; bp.kc = f; f += B * 8 * L; bp.vc = f; f += B * 8 * L;
