@@ -63,6 +63,7 @@ struct Session {
     void * tc_scratch = nullptr; size_t tc_scratch_bytes = 0;     // tensor-core path: activation tile images
     void * tc_scratch2 = nullptr;                                  // second image buffer (FF1 epilogue -> FF2 input)
     void * lt_scratch = nullptr; size_t lt_scratch_bytes = 0;     // batched local transformer: activation scratch
+    int prefill_len = 0;                                            // > 0 while mgb_prefill runs decoder_layers on the context frames
     float * fold_xm = nullptr, * fold_xn = nullptr; bool fold_ready = false;     // batched decode: folded cross-attention tables [L][B][max_text][d]
 
     ~Session() {
@@ -112,6 +113,7 @@ static bool decoder_layers(Session & s, Tokens tok, bool want_hidden) {
         AttnArgs at;
         at.precision = m.precision; at.q = s.qbuf; at.ldq = d; at.K = kl; at.V = vl; at.rows_per_utt = s.max_seq;
         at.H = hp.dec_sa_heads; at.dh = d / hp.dec_sa_heads; at.causal = 1; at.tok = tok; at.out = s.attn; at.ldo = d;
+        at.prefill_len = s.prefill_len;
         // batched decoder step on the tensor-core path: the attention kernel writes the O-projection's packed input itself
         if (M == s.B && tok.utt == s.dec_utt && M <= 64 && at.dh == 64 && tc_linear_supported(o) && getenv("MGB_NO_CHAIN") == nullptr) {
             at.pack_out = s.tc_scratch; o.x_prepacked = true;
@@ -494,7 +496,7 @@ int mgb_prefill(mgb_session * ss, const int32_t * speakers) {
         for (int l = 0; l < hp.dec_layers; l++) {
             const DecLayer & L = m.dec[l];
             if (!launch_xattn_fold((char *)s->xk + l * xkv_layer, (char *)s->xv + l * xkv_layer, L.xq.w, L.xo.w, s->B * s->max_text, d, dxa,
-                                   1.0f / sqrtf((float)dxa), s->fold_xm + l * tab, s->fold_xn + l * tab, st)) return MGB_ECUDA;
+                                   1.0f / sqrtf((float)dxa), s->fold_xm + l * tab, s->fold_xn + l * tab, st, s->d_ntext, s->max_text)) return MGB_ECUDA;
         }
         s->fold_ready = true;
     }
@@ -509,7 +511,10 @@ int mgb_prefill(mgb_session * ss, const int32_t * speakers) {
         cudaMemcpyAsync(s->tok_slot, slot.data(), M * 4, cudaMemcpyHostToDevice, st) != cudaSuccess) { set_error("H2D failed"); return MGB_ECUDA; }
     Tokens T; T.M = M; T.utt = s->tok_utt; T.pos = s->tok_pos; T.slot = s->tok_slot;
     if (!launch_context_embed(m, s->d_speakers, T, s->x, st)) return MGB_ECUDA;
-    if (!decoder_layers(*s, T, false)) return MGB_ECUDA;
+    s->prefill_len = C;
+    const bool pf_ok = decoder_layers(*s, T, false);
+    s->prefill_len = 0;
+    if (!pf_ok) return MGB_ECUDA;
     std::vector<int32_t> p0(s->B, C), s0(s->B);
     for (int b = 0; b < s->B; b++) s0[b] = b * s->max_seq + C;
     if (cudaMemcpyAsync(s->dec_pos, p0.data(), s->B * 4, cudaMemcpyHostToDevice, st) != cudaSuccess ||

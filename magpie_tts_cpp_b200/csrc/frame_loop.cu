@@ -1062,8 +1062,9 @@ __global__ void __launch_bounds__(kThreads, 1) frame_loop_kernel(const FrameLoop
 
 // ---- folded cross-attention tables -----------------------------------------------------------------------------------
 __global__ void xattn_fold_kernel(const bf * xk, const bf * xv, const bf * wq, const bf * wo, int d, int dxa, float scale,
-                                  float * xm, float * xn) {
-    const int j = blockIdx.x;                 // text token
+                                  float * xm, float * xn, const int32_t * n_ctx, int rows_per_utt) {
+    const int j = blockIdx.x;                 // row of the cross K/V storage: (utterance, text token)
+    if (n_ctx && (j % rows_per_utt) >= n_ctx[j / rows_per_utt]) return;       // rows past the text are never read
     extern __shared__ float kv[];             // [2][dxa]
     for (int i = threadIdx.x; i < dxa; i += blockDim.x) {
         kv[i] = __bfloat162float(xk[(size_t)j * dxa + i]);
@@ -1072,9 +1073,14 @@ __global__ void xattn_fold_kernel(const bf * xk, const bf * xv, const bf * wq, c
     __syncthreads();
     for (int i = threadIdx.x; i < d; i += blockDim.x) {
         float m = 0.0f, n = 0.0f;
-        for (int cc = 0; cc < dxa; cc++) {
-            m = fmaf(kv[cc], __bfloat162float(wq[(size_t)cc * d + i]), m);
-            n = fmaf(kv[dxa + cc], __bfloat162float(wo[(size_t)i * dxa + cc]), n);
+        // M row: column i of Wq (coalesced across the threads); N row: row i of Wo, contiguous per thread (16-byte loads)
+        for (int cc = 0; cc < dxa; cc++) m = fmaf(kv[cc], __bfloat162float(wq[(size_t)cc * d + i]), m);
+        const uint4 * wr = reinterpret_cast<const uint4 *>(wo + (size_t)i * dxa);
+        for (int c8 = 0; c8 < dxa / 8; c8++) {
+            const uint4 u = wr[c8];
+            const float * v = kv + dxa + c8 * 8;
+            n = fmaf(bf16lo(u.x), v[0], n); n = fmaf(bf16hi(u.x), v[1], n); n = fmaf(bf16lo(u.y), v[2], n); n = fmaf(bf16hi(u.y), v[3], n);
+            n = fmaf(bf16lo(u.z), v[4], n); n = fmaf(bf16hi(u.z), v[5], n); n = fmaf(bf16lo(u.w), v[6], n); n = fmaf(bf16hi(u.w), v[7], n);
         }
         xm[(size_t)j * d + i] = m * scale;
         xn[(size_t)j * d + i] = n;
@@ -1120,9 +1126,10 @@ bool launch_frame_loop(const FrameLoopParams & p, int grid, cudaStream_t stream)
 }
 
 bool launch_xattn_fold(const void * xk, const void * xv, const void * wq, const void * wo, int E, int d, int dxa, float scale,
-                       float * xm, float * xn, cudaStream_t stream) {
+                       float * xm, float * xn, cudaStream_t stream, const int32_t * n_ctx, int rows_per_utt) {
+    if (dxa % 8 != 0) { set_error("xattn_fold: cross-attention width must be a multiple of 8"); return false; }
     xattn_fold_kernel<<<E, 256, 2 * dxa * sizeof(float), stream>>>((const bf *)xk, (const bf *)xv, (const bf *)wq, (const bf *)wo, d, dxa,
-                                                                   scale, xm, xn);
+                                                                   scale, xm, xn, n_ctx, rows_per_utt);
     MGB_LAUNCH_CHECK();
     return true;
 }

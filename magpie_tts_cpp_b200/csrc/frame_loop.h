@@ -60,6 +60,6 @@ bool   launch_frame_loop(const FrameLoopParams & p, int grid, cudaStream_t strea
 
 // M_l[j][i] = scale * sum_c K_l[j][c] Wq_l[c][i],  N_l[j][n] = sum_c V_l[j][c] Wo_l[n][c]   (bf16 inputs, f32 out)
 bool   launch_xattn_fold(const void * xk, const void * xv, const void * wq, const void * wo, int E, int d, int dxa,
-                         float scale, float * xm, float * xn, cudaStream_t stream);
+                         float scale, float * xm, float * xn, cudaStream_t stream, const int32_t * n_ctx = nullptr, int rows_per_utt = 1);
 
 }  // namespace mgb

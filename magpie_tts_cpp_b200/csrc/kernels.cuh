@@ -59,6 +59,7 @@ struct AttnArgs {
     Tokens tok;
     float * out = nullptr; int ldo = 0;
     void * pack_out = nullptr;                   // dh == 64, <= 64 tokens: write hi | lo tile images for the next GEMM instead of `out`
+    int prefill_len = 0;                         // > 0: tokens are utterance-major runs of positions 0..prefill_len-1 (context prefill)
 };
 bool launch_attention(const AttnArgs & a, cudaStream_t stream);
 // batched decoder step: folded cross-attention x += softmax(M LN(x)) N (tables from launch_xattn_fold, frame_loop.cu)

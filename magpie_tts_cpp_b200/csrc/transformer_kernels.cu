@@ -369,6 +369,71 @@ bool launch_linear(const LinearArgs & a, cudaStream_t stream) {
     return launch_linear_p<__nv_bfloat16>(p, stream);
 }
 
+// ---- context prefill: causal self-attention of C consecutive positions 0..C-1 of one utterance (magpie.cpp:3911-3988) -------
+// grid (H, B), 256 threads: the head's K / V rows of the utterance are staged ONCE in shared memory (f32, K rows padded to
+// 65 floats) and shared by all C queries; warp w handles queries w, w + 8, ...: lane-per-key dot products, warp softmax,
+// lane-per-dimension P.V.  (The token-parallel attention_kernel re-reads the K / V rows for every query.)
+template <typename T>
+__global__ void __launch_bounds__(256) prefill_attention_kernel(const AttnParams p, int C) {
+    constexpr int DH = 64, KS = DH + 1;
+    extern __shared__ float pa_smem[];
+    float * Ks = pa_smem;                    // [C][65]
+    float * Vs = Ks + (size_t)C * KS;        // [C][64]
+    float * sq = Vs + (size_t)C * DH;        // [8][64]
+    float * sp = sq + 8 * DH;                // [8][128]
+    const int h = blockIdx.x, u = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ld = p.H * DH;
+    const T * Kb = (const T *)p.K + (size_t)u * p.rows_per_utt * ld + h * DH;
+    const T * Vb = (const T *)p.V + (size_t)u * p.rows_per_utt * ld + h * DH;
+    for (int i = tid; i < C * DH; i += 256) {
+        const int j = i / DH, dd = i % DH;
+        Ks[j * KS + dd] = WT<T>::get(Kb + (size_t)j * ld + dd);
+        Vs[j * DH + dd] = WT<T>::get(Vb + (size_t)j * ld + dd);
+    }
+    __syncthreads();
+    const float scale = 0.125f;              // 1 / sqrt(64)
+    for (int t = warp; t < C; t += 8) {
+        const size_t row = (size_t)u * C + t;
+        sq[warp * DH + lane] = p.q[row * p.ldq + h * DH + lane] * scale;
+        sq[warp * DH + lane + 32] = p.q[row * p.ldq + h * DH + lane + 32] * scale;
+        __syncwarp();
+        float sc[4], mx = -INFINITY;
+#pragma unroll
+        for (int k4 = 0; k4 < 4; k4++) {
+            const int j = lane + 32 * k4;
+            float dsum = -INFINITY;
+            if (j <= t) {
+                dsum = 0.0f;
+                const float * kr = Ks + j * KS, * qr = sq + warp * DH;
+#pragma unroll 16
+                for (int dd = 0; dd < DH; dd++) dsum = fmaf(kr[dd], qr[dd], dsum);
+            }
+            sc[k4] = dsum;
+            mx = fmaxf(mx, dsum);
+        }
+        mx = warp_max(mx);
+        float sum = 0.0f;
+#pragma unroll
+        for (int k4 = 0; k4 < 4; k4++) {
+            const float e = sc[k4] == -INFINITY ? 0.0f : expf(sc[k4] - mx);
+            sp[warp * 128 + lane + 32 * k4] = e;
+            sum += e;
+        }
+        sum = warp_sum(sum);
+        __syncwarp();
+        float o0 = 0.0f, o1 = 0.0f;
+        for (int j = 0; j <= t; j++) {
+            const float pj = sp[warp * 128 + j];
+            o0 = fmaf(pj, Vs[j * DH + lane], o0);
+            o1 = fmaf(pj, Vs[j * DH + lane + 32], o1);
+        }
+        const float inv = 1.0f / sum;
+        p.out[row * p.ldo + h * DH + lane] = o0 * inv;
+        p.out[row * p.ldo + h * DH + lane + 32] = o1 * inv;
+        __syncwarp();
+    }
+}
+
 bool launch_attention(const AttnArgs & a, cudaStream_t stream) {
     if (a.tok.M <= 0) return true;
     AttnParams p;
@@ -379,8 +444,27 @@ bool launch_attention(const AttnArgs & a, cudaStream_t stream) {
         if (a.dh != 64 || a.tok.M > 64) { set_error("attention: packed output needs head dim 64 and one token tile"); return false; }
         p.pk_hi = (__nv_bfloat16 *)a.pack_out; p.pk_lo = p.pk_hi + (size_t)64 * a.H * a.dh;
     }
-    dim3 grid(a.H, a.tok.M);
     const bool f32 = a.precision == MGB_PREC_F32;
+    if (a.prefill_len > 0 && a.causal && a.dh == 64 && a.prefill_len <= 128 && a.tok.M % a.prefill_len == 0 && !a.pack_out) {
+        // tokens are (utterance-major, positions 0..C-1): one CTA per (head, utterance) with the K / V rows staged once
+        const int C = a.prefill_len;
+        const size_t smem = ((size_t)C * 65 + (size_t)C * 64 + 8 * 64 + 8 * 128) * sizeof(float);
+        static uint64_t attr_done = 0;
+        int dev = 0;
+        MGB_CUDA_TRY(cudaGetDevice(&dev));
+        if (!(attr_done >> dev & 1)) {
+            MGB_CUDA_TRY(cudaFuncSetAttribute(prefill_attention_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+            MGB_CUDA_TRY(cudaFuncSetAttribute(prefill_attention_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+            attr_done |= 1ull << dev;
+        }
+        p.pdl = 0;
+        dim3 pg(a.H, a.tok.M / C);
+        if (f32) prefill_attention_kernel<float><<<pg, 256, smem, stream>>>(p, C);
+        else prefill_attention_kernel<__nv_bfloat16><<<pg, 256, smem, stream>>>(p, C);
+        MGB_LAUNCH_CHECK();
+        return true;
+    }
+    dim3 grid(a.H, a.tok.M);
     p.pdl = (a.pack_out && !f32 && a.dh == 64) ? 1 : 0;       // decoder-step chain only
     if (p.pdl) {
         cudaLaunchConfig_t cfg = {};
