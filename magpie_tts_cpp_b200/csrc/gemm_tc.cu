@@ -16,13 +16,16 @@ namespace {
 using bf = __nv_bfloat16;
 
 // row-major bf16 [N][K] -> [ceil(N/128)][K/64] tiles of 128 x 64 in the SWIZZLE_128B K-major image; one thread per 16 bytes
-__global__ void pack_w_kernel(const bf * W, int N, int K, bf * Wt) {
+// taps > 1 (causal conv weights stored tap-major [taps][N][K]): the taps are concatenated along k, k' = tap * K + k
+__global__ void pack_w_kernel(const bf * W, int N, int Ktap, int taps, bf * Wt) {
+    const int K = Ktap * taps;
     const int KT = K / 64, NT = (N + tc::BM - 1) / tc::BM;
     const size_t total = (size_t)NT * tc::BM * (K / 8);
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int r = (int)(i / (K / 8)), kc = (int)(i % (K / 8));
         uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (r < N) v = *reinterpret_cast<const uint4 *>(W + (size_t)r * K + kc * 8);
+        const int tap = (kc * 8) / Ktap, kk = kc * 8 - tap * Ktap;
+        if (r < N) v = *reinterpret_cast<const uint4 *>(W + ((size_t)tap * N + r) * Ktap + kk);
         const size_t tile = (size_t)(r / tc::BM) * KT + kc / 8;
         unsigned char * dst = reinterpret_cast<unsigned char *>(Wt) + tile * (tc::BM * 128) + tc::swz_offset(r % tc::BM, (kc % 8) * 8);
         *reinterpret_cast<uint4 *>(dst) = v;
@@ -31,50 +34,56 @@ __global__ void pack_w_kernel(const bf * W, int N, int K, bf * Wt) {
 
 // activations f32 [M][ldx] (optionally LayerNorm'd, magpie.cpp:2237-2259) -> hi / lo bf16 tile images [ceil(M/MT)][K/64][MT x 64].
 // One CTA per row of the padded token range; rows >= M are written as zeros.
+// taps > 1: row m of the packed operand is [x(m - (taps-1)) | ... | x(m)] (each LayerNorm'd on its own), a shifted row being
+// zero when it would cross the start of the utterance (tok_pos[m] < shift): the k = 3 causal conv as ONE GEMM over 3 K.
 __global__ void __launch_bounds__(256) pack_x_kernel(const float * X, int ldx, int M, int K, const float * ln_w, float eps, int MT,
-                                                     bf * hi, bf * lo) {
+                                                     bf * hi, bf * lo, int taps, const int32_t * tok_pos) {
     __shared__ float red[32];
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");     // let the GEMM's CTAs start prefetching weights
     asm volatile("griddepcontrol.wait;" ::: "memory");                  // (itself launched as a programmatic dependent of the previous kernel)
     const int m = blockIdx.x, tid = threadIdx.x;
-    const int KT = K / 64;
-    const bool valid = m < M;
-    const float * xr = X + (size_t)(valid ? m : 0) * ldx;
-    float mean = 0.0f, scale = 1.0f;
-    if (ln_w) {
-        float s = 0.0f;
-        for (int k = tid; k < K; k += 256) s += valid ? xr[k] : 0.0f;
-        mean = block_sum(s, red) / (float)K;
-        float s2 = 0.0f;
-        for (int k = tid; k < K; k += 256) { const float v = (valid ? xr[k] : 0.0f) - mean; s2 += v * v; }
-        const float var = block_sum(s2, red) / (float)K;
-        scale = 1.0f / sqrtf(var + eps);
-    }
+    const int KT = K * taps / 64;
     const size_t tile_row = (size_t)(m / MT) * KT;
-    for (int kc = tid; kc < K / 8; kc += 256) {
-        float v[8];
-        if (valid) {
-            const float4 a = *reinterpret_cast<const float4 *>(xr + kc * 8), b = *reinterpret_cast<const float4 *>(xr + kc * 8 + 4);
-            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-            if (ln_w) {
+    for (int tap = 0; tap < taps; tap++) {
+        const int shift = taps - 1 - tap;
+        const bool valid = m < M && (shift == 0 || tok_pos[m] >= shift);
+        const float * xr = X + (size_t)(valid ? m - shift : 0) * ldx;
+        float mean = 0.0f, scale = 1.0f;
+        if (ln_w) {
+            float s = 0.0f;
+            for (int k = tid; k < K; k += 256) s += valid ? xr[k] : 0.0f;
+            mean = block_sum(s, red) / (float)K;
+            float s2 = 0.0f;
+            for (int k = tid; k < K; k += 256) { const float v = (valid ? xr[k] : 0.0f) - mean; s2 += v * v; }
+            const float var = block_sum(s2, red) / (float)K;
+            scale = 1.0f / sqrtf(var + eps);
+        }
+        for (int kc = tid; kc < K / 8; kc += 256) {
+            float v[8];
+            if (valid) {
+                const float4 a = *reinterpret_cast<const float4 *>(xr + kc * 8), b = *reinterpret_cast<const float4 *>(xr + kc * 8 + 4);
+                v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+                if (ln_w) {
 #pragma unroll
-                for (int q = 0; q < 8; q++) v[q] = ((v[q] - mean) * scale) * ln_w[kc * 8 + q];
+                    for (int q = 0; q < 8; q++) v[q] = ((v[q] - mean) * scale) * ln_w[kc * 8 + q];
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 8; q++) v[q] = 0.0f;
             }
-        } else {
+            uint32_t h[4], l[4];
 #pragma unroll
-            for (int q = 0; q < 8; q++) v[q] = 0.0f;
+            for (int q = 0; q < 4; q++) {
+                const bf h0 = __float2bfloat16_rn(v[2 * q]), h1 = __float2bfloat16_rn(v[2 * q + 1]);
+                const bf l0 = __float2bfloat16_rn(v[2 * q] - __bfloat162float(h0)), l1 = __float2bfloat16_rn(v[2 * q + 1] - __bfloat162float(h1));
+                h[q] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                l[q] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+            }
+            const int kg = tap * (K / 8) + kc;                       // 8-column group of the concatenated row
+            const size_t off = (tile_row + kg / 8) * ((size_t)MT * 128) + tc::swz_offset(m % MT, (kg % 8) * 8);
+            *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(hi) + off) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(lo) + off) = make_uint4(l[0], l[1], l[2], l[3]);
         }
-        uint32_t h[4], l[4];
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const bf h0 = __float2bfloat16_rn(v[2 * q]), h1 = __float2bfloat16_rn(v[2 * q + 1]);
-            const bf l0 = __float2bfloat16_rn(v[2 * q] - __bfloat162float(h0)), l1 = __float2bfloat16_rn(v[2 * q + 1] - __bfloat162float(h1));
-            h[q] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-            l[q] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-        }
-        const size_t off = (tile_row + kc / 8) * ((size_t)MT * 128) + tc::swz_offset(m % MT, (kc % 8) * 8);
-        *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(hi) + off) = make_uint4(h[0], h[1], h[2], h[3]);
-        *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(lo) + off) = make_uint4(l[0], l[1], l[2], l[3]);
     }
 }
 
@@ -217,10 +226,10 @@ template <int MT, int SPLIT, int EPI> bool launch_tc(const bf * Wt, const bf * h
 
 }  // namespace
 
-size_t tc_weight_tile_bytes(int N, int K) { return (size_t)((N + tc::BM - 1) / tc::BM) * tc::BM * K * sizeof(bf); }
+size_t tc_weight_tile_bytes(int N, int K) { return (size_t)((N + tc::BM - 1) / tc::BM) * tc::BM * K * sizeof(bf); }      // K = taps * K_tap
 
-bool tc_pack_weights(const void * W, int N, int K, void * Wt, cudaStream_t stream) {
-    pack_w_kernel<<<592, 256, 0, stream>>>((const bf *)W, N, K, (bf *)Wt);
+bool tc_pack_weights(const void * W, int N, int K, void * Wt, cudaStream_t stream, int taps) {
+    pack_w_kernel<<<592, 256, 0, stream>>>((const bf *)W, N, K, taps, (bf *)Wt);
     MGB_LAUNCH_CHECK();
     return true;
 }
@@ -228,12 +237,12 @@ bool tc_pack_weights(const void * W, int N, int K, void * Wt, cudaStream_t strea
 size_t tc_scratch_bytes(int M, int K) { return 2 * (size_t)((M + 127) / 128) * 128 * K * sizeof(bf); }
 
 bool tc_linear_supported(const LinearArgs & a) {
-    return a.precision == MGB_PREC_BF16 && a.W.tiles != nullptr && a.W.taps == 1 && a.M >= 16 && a.W.K % 64 == 0 && a.tc_scratch != nullptr &&
-           tc_scratch_bytes(a.M, a.W.K) <= a.tc_scratch_bytes && (a.ldx % 4) == 0;
+    return a.precision == MGB_PREC_BF16 && a.W.tiles != nullptr && (a.W.taps == 1 || a.tok_pos != nullptr) && a.M >= 16 && a.W.K % 64 == 0 &&
+           a.tc_scratch != nullptr && tc_scratch_bytes(a.M, a.W.K * a.W.taps) <= a.tc_scratch_bytes && (a.ldx % 4) == 0;
 }
 
 bool launch_linear_tc(const LinearArgs & a, cudaStream_t stream) {
-    const int K = a.W.K, M = a.M;
+    const int Ktap = a.W.K, taps = a.W.taps, K = Ktap * taps, M = a.M;       // taps > 1: one GEMM over the concatenated taps
     const int MT = M <= 64 ? 64 : 128;
     const int Mpad = (M + MT - 1) / MT * MT;
     bf * hi = (bf *)a.tc_scratch;
@@ -245,7 +254,7 @@ bool launch_linear_tc(const LinearArgs & a, cudaStream_t stream) {
         pa[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         pa[0].val.programmaticStreamSerializationAllowed = 1;
         pc.attrs = pa; pc.numAttrs = 1;
-        MGB_CUDA_TRY(cudaLaunchKernelEx(&pc, pack_x_kernel, a.X, a.ldx, M, K, a.ln_w, a.eps, MT, hi, lo));
+        MGB_CUDA_TRY(cudaLaunchKernelEx(&pc, pack_x_kernel, a.X, a.ldx, M, Ktap, a.ln_w, a.eps, MT, hi, lo, taps, a.tok_pos));
         MGB_LAUNCH_CHECK();
     }
     TcEpi e;

@@ -43,7 +43,7 @@ struct LinearArgs {
 bool launch_linear(const LinearArgs & a, cudaStream_t stream);
 // tcgen05 path (bf16, >= 16 tokens): gemm_tc.cu
 size_t tc_weight_tile_bytes(int N, int K);
-bool   tc_pack_weights(const void * W, int N, int K, void * Wt, cudaStream_t stream);
+bool   tc_pack_weights(const void * W, int N, int K, void * Wt, cudaStream_t stream, int taps = 1);     // W: [taps][N][K]
 size_t tc_scratch_bytes(int M, int K);
 bool   tc_linear_supported(const LinearArgs & a);
 bool   launch_linear_tc(const LinearArgs & a, cudaStream_t stream);

@@ -249,14 +249,14 @@ Model * load_model(const char * path, int device, int precision) {
     if (precision == MGB_PREC_BF16 && getenv("MGB_NO_TC") == nullptr) {
         std::vector<DevMat *> mats;
         for (auto & L : M->dec) for (DevMat * m : {&L.qkv, &L.o, &L.xq, &L.xkv, &L.xo, &L.ff1, &L.ff2}) mats.push_back(m);
-        for (auto & L : M->enc) for (DevMat * m : {&L.qkv, &L.o}) mats.push_back(m);
+        for (auto & L : M->enc) for (DevMat * m : {&L.qkv, &L.o, &L.ff1, &L.ff2}) mats.push_back(m);      // (ff1 / ff2: k = 3 causal convs, taps concatenated along k)
         mats.push_back(&M->final_w);
         for (DevMat * m : mats) {
-            if (m->taps != 1 || m->K % 64 != 0) continue;
+            if (m->K % 64 != 0) continue;
             void * t = nullptr;
-            if (cudaMalloc(&t, tc_weight_tile_bytes(m->N, m->K)) != cudaSuccess) { set_error("cudaMalloc failed (weight tiles)"); return nullptr; }
+            if (cudaMalloc(&t, tc_weight_tile_bytes(m->N, m->K * m->taps)) != cudaSuccess) { set_error("cudaMalloc failed (weight tiles)"); return nullptr; }
             M->allocations.push_back(t);
-            if (!tc_pack_weights(m->w, m->N, m->K, t, nullptr)) return nullptr;
+            if (!tc_pack_weights(m->w, m->N, m->K, t, nullptr, m->taps)) return nullptr;
             m->tiles = t;
         }
         if (cudaDeviceSynchronize() != cudaSuccess) { set_error("magpie_init: packing the weight tiles failed"); return nullptr; }
