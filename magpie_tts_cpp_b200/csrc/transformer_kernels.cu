@@ -6,6 +6,8 @@
 //   LayerNorm           src/magpie.cpp:2237-2259      self-attention   src/magpie.cpp:1477-1575, 3395-3480
 //   cross-attention     src/magpie.cpp:1663-1767      conv-FFN         src/magpie.cpp:1769-1918
 //   embeddings          src/magpie.cpp:1319-1465, 2746-2787
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -392,7 +394,8 @@ __global__ void __launch_bounds__(256) prefill_attention_kernel(const AttnParams
     }
     __syncthreads();
     const float scale = 0.125f;              // 1 / sqrt(64)
-    for (int t = warp; t < C; t += 8) {
+    // queries are interleaved over gridDim.z CTAs (small batches would otherwise leave most SMs idle)
+    for (int t = warp * gridDim.z + blockIdx.z; t < C; t += 8 * gridDim.z) {
         const size_t row = (size_t)u * C + t;
         sq[warp * DH + lane] = p.q[row * p.ldq + h * DH + lane] * scale;
         sq[warp * DH + lane + 32] = p.q[row * p.ldq + h * DH + lane + 32] * scale;
@@ -458,7 +461,9 @@ bool launch_attention(const AttnArgs & a, cudaStream_t stream) {
             attr_done |= 1ull << dev;
         }
         p.pdl = 0;
-        dim3 pg(a.H, a.tok.M / C);
+        const int nb = a.tok.M / C;
+        const int qs = std::max(1, std::min(8, 296 / std::max(1, a.H * nb)));
+        dim3 pg(a.H, nb, qs);
         if (f32) prefill_attention_kernel<float><<<pg, 256, smem, stream>>>(p, C);
         else prefill_attention_kernel<__nv_bfloat16><<<pg, 256, smem, stream>>>(p, C);
         MGB_LAUNCH_CHECK();
