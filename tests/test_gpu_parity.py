@@ -461,6 +461,40 @@ def test_large_batches_take_the_multi_tile_paths(B, full_model_path, full_oracle
     s.close(); m.close()
 
 
+def test_batched_generation_loop_with_both_local_transformer_kernels(B, full_model_path, monkeypatch):
+    """Free-running generation of 18 utterances (different texts / speakers) in the device loop: the weight-stationary LT kernel
+    (loop mode: device step counter, EOS bookkeeping, min-frames rule, Philox draws) against the per-utterance cluster kernel."""
+    nb = 18
+    rng = np.random.default_rng(5)
+    texts = [[2378] + rng.integers(0, 90, int(rng.integers(3, 20))).tolist() + [2379] for _ in range(nb)]
+    m = B.Model(full_model_path, 0, B.PREC_BF16)
+
+    def run(no_batch, **kw):
+        if no_batch:
+            monkeypatch.setenv("MGB_NO_LT_BATCH", "1")
+        s = m.session(batch=nb, max_text=32)
+        s.encode_text(texts, want_output=False)
+        s.prefill([b % 5 for b in range(nb)])
+        out = s.generate(**kw)
+        monkeypatch.delenv("MGB_NO_LT_BATCH", raising=False)
+        s.close()
+        return out
+
+    a = run(False, max_steps=10, temperature=0.0, ignore_eos=True)
+    b = run(True, max_steps=10, temperature=0.0, ignore_eos=True)
+    assert all(len(x) == 10 for x in a) and all(len(x) == 10 for x in b)
+    same = np.mean([np.array_equal(x[:4], y[:4]) for x, y in zip(a, b)])       # later frames follow the first differing pick
+    assert same >= 0.8, same
+    a = run(False, max_steps=12, temperature=0.0)                              # EOS honoured: lengths may be ragged
+    b = run(True, max_steps=12, temperature=0.0)
+    assert np.mean([len(x) == len(y) for x, y in zip(a, b)]) >= 0.8
+    assert all(len(x) >= 4 for x in a)                                          # EOS is forbidden for the first 4 frames
+    a = run(False, max_steps=6, temperature=0.7, top_k=80, seed=1234, ignore_eos=True)
+    b = run(True, max_steps=6, temperature=0.7, top_k=80, seed=1234, ignore_eos=True)
+    assert np.mean([x[0][0] == y[0][0] for x, y in zip(a, b)]) >= 0.8           # same Philox draw, same first pick
+    m.close()
+
+
 def test_batched_local_transformer_matches_per_utterance_kernel(B, full_model_path, full_oracle, monkeypatch):
     """bf16, 20 utterances: the weight-stationary persistent LT (lt_batch.cu, default for >= 16 utterances) against the
     one-cluster-per-utterance kernel (MGB_NO_LT_BATCH=1) and the oracle; same bf16 weights and f32 arithmetic, so the two
