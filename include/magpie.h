@@ -127,6 +127,11 @@ struct magpie_stream_params {
     magpie_audio_callback    on_audio = nullptr;
     magpie_progress_callback on_progress = nullptr;
     void * user_data = nullptr;
+    // Extension (appended, default = reference behaviour): 0 decodes every chunk with zero causal history, as the reference does
+    // (magpie.cpp:4482-4500, audible seams every chunk); N > 0 decodes each chunk together with the previous N frames of codes and
+    // emits only the new samples.  The codec's receptive field is 24.8 frames, so N >= 25 makes the streamed
+    // audio identical to a whole-utterance decode.
+    int   codec_context_frames = 0;
 };
 
 MAGPIE_API std::vector<std::string> magpie_split_sentences(const char * text);

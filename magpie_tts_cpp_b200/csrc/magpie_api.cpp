@@ -366,7 +366,22 @@ int magpie_synthesize_sentence_streaming(magpie_context * ctx, magpie_codec * co
     if (!s) return -1;
     magpie_model_impl * im = ctx->model.impl;
     const int per_chunk = params.frames_per_chunk > 0 ? params.frames_per_chunk : 4;
-    std::vector<int32_t> bos(8, hp.audio_bos_id), pending;
+    std::vector<int32_t> bos(8, hp.audio_bos_id), pending, history;      // history: last codec_context_frames frames already emitted
+    const int n_ctx = std::max(0, params.codec_context_frames);
+    const int hop = codec->hparams.hop_length;
+    // decode `pending` (np frames); with a context, together with the previous frames, keeping only the new samples
+    auto decode_pending = [&](int np) {
+        if (n_ctx == 0) return decode_chunk(codec, pending, np);                // reference behaviour: zero causal history
+        std::vector<int32_t> both(history);
+        both.insert(both.end(), pending.begin(), pending.begin() + (size_t)np * 8);
+        const int nh = (int)history.size() / 8;
+        std::vector<float> audio = decode_chunk(codec, both, nh + np);
+        if (audio.size() == (size_t)(nh + np) * hop) audio.erase(audio.begin(), audio.begin() + (size_t)nh * hop);
+        else audio.clear();
+        const size_t keep = std::min(both.size(), (size_t)n_ctx * 8);
+        history.assign(both.end() - keep, both.end());
+        return audio;
+    };
     int total = 0, frames = 0;
     bool ok = mgb_decoder_step(s, bos.data(), nullptr) == MGB_OK;
     for (int step = 0; ok && step < hp.max_dec_steps; step++) {
@@ -380,7 +395,7 @@ int magpie_synthesize_sentence_streaming(magpie_context * ctx, magpie_codec * co
         frames++;
         const int np = (int)pending.size() / 8;
         if (np >= per_chunk || eos) {
-            std::vector<float> audio = decode_chunk(codec, pending, np);       // each chunk decoded with zero causal history
+            std::vector<float> audio = decode_pending(np);
             if (!audio.empty() && params.on_audio && !params.on_audio(audio.data(), (int)audio.size(), params.user_data)) eos = true;
             total += (int)audio.size();
             pending.clear();
@@ -390,7 +405,7 @@ int magpie_synthesize_sentence_streaming(magpie_context * ctx, magpie_codec * co
         if (mgb_decoder_step(s, nullptr, nullptr) != MGB_OK) { ok = false; break; }      // consumes the sampled codes left on the device
     }
     if (ok && !pending.empty()) {
-        std::vector<float> audio = decode_chunk(codec, pending, (int)pending.size() / 8);
+        std::vector<float> audio = decode_pending((int)pending.size() / 8);
         if (!audio.empty() && params.on_audio) params.on_audio(audio.data(), (int)audio.size(), params.user_data);
         total += (int)audio.size();
     }

@@ -2,7 +2,7 @@
 //   api_test tokenize <vocab.txt> <dict.tsv> <space_id> <bos> <eos> <text>      (CPU only)
 //   api_test split <text>                                                      (CPU only)
 //   api_test synth <model.gguf> <codec.gguf> <text> <max_steps>                (GPU) greedy codes + LT sample + encode
-//   api_test stream <model.gguf> <codec.gguf> <text> <max_steps> <frames_per_chunk>   (GPU)
+//   api_test stream <model.gguf> <codec.gguf> <text> <max_steps> <frames_per_chunk> [codec_context_frames [dump.f32]]   (GPU)
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -49,7 +49,7 @@ int main(int argc, char ** argv) {
         for (const std::string & s : magpie_split_sentences(argv[2])) printf("[%s]\n", s.c_str());
         return 0;
     }
-    if ((cmd == "synth" && argc == 6) || (cmd == "stream" && argc == 7)) {
+    if ((cmd == "synth" && argc == 6) || (cmd == "stream" && argc >= 7 && argc <= 9)) {
         magpie_context * ctx = magpie_init(argv[2]);
         if (!ctx) return 3;
         if (magpie_init_with_backend(argv[2], MAGPIE_BACKEND_CPU) != nullptr) return 4;      // no CPU fallback
@@ -87,7 +87,10 @@ int main(int argc, char ** argv) {
             magpie_stream_params sp;
             sp.temperature = 0.0f; sp.top_k = 1; sp.speaker_id = 1; sp.frames_per_chunk = atoi(argv[6]);
             sp.on_audio = on_audio; sp.on_progress = on_progress; sp.user_data = &log;
+            if (argc > 7) sp.codec_context_frames = atoi(argv[7]);
+            if (argc > 8) sp.sentence_chunking = false;
             const int total = magpie_synthesize_streaming(ctx, codec, argv[4], sp);
+            if (argc > 8) { FILE * f = fopen(argv[8], "wb"); if (f) { fwrite(log.audio.data(), 4, log.audio.size(), f); fclose(f); } }
             printf("total: %d\nchunks:", total);
             for (int n : log.chunk_samples) printf(" %d", n);
             printf("\nprogress: %d %d\n", log.progress_calls, log.last_frames);

@@ -10,6 +10,11 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "magpie_tts_cpp_b200")
+def snr_db(a, b):
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    return 10 * np.log10(np.sum(b ** 2) / max(np.sum((a - b) ** 2), 1e-300))
+
+
 HELLO = [2378, 7, 4, 11, 11, 14, 32, 26, 22, 14, 17, 11, 3, 32, 28, 2379]
 
 
@@ -130,6 +135,25 @@ def test_streaming_api(api_test, oracle_mod, tiny_model_path, codec_path):
     assert int(lines["total"]) == sum(chunks) and all(c % 1024 == 0 and 0 < c <= 4 * 1024 for c in chunks)
     # two sentences, each at least min 4 frames; chunks are flushed per sentence
     assert sum(chunks) >= 2 * 4 * 1024
+
+
+@pytest.mark.gpu
+def test_streaming_with_codec_context_is_seamless(api_test, oracle_mod, tiny_model_path, codec_path, tmp_path):
+    """codec_context_frames = 25 (>= the codec's 24.8-frame receptive field): the chunks streamed every 4 frames concatenate to
+    the whole-utterance decode of the same codes; with 0 (the reference's zero-history chunks) they do not."""
+    env = dict(os.environ, MAGPIE_PRECISION="f32")
+    o = oracle_mod.OracleModel(tiny_model_path)
+    codes = o.synthesize(HELLO, speaker=1, temperature=0.0, max_steps=12)     # greedy: the streamed codes are the same
+    audio = {}
+    for ctx_frames in (0, 25):
+        f = str(tmp_path / f"stream{ctx_frames}.f32")
+        subprocess.check_output([api_test, "stream", tiny_model_path, codec_path, "Hello, world!", "12", "4", str(ctx_frames), f], text=True, env=env)
+        audio[ctx_frames] = np.fromfile(f, np.float32)
+    n = len(codes) * 1024
+    assert len(audio[0]) == len(audio[25]) >= n
+    whole = oracle_mod.OracleCodec(codec_path).decode(np.ascontiguousarray(codes.T))
+    assert snr_db(audio[25][:n], whole) >= 40.0
+    assert snr_db(audio[0][4 * 1024:n], whole[4 * 1024:]) < 20.0      # zero-history chunks differ from the continuous decode
 
 
 @pytest.mark.gpu
