@@ -491,6 +491,111 @@ __global__ void __launch_bounds__(128) up_tm_kernel(const UpKParams p) {
     }
 }
 
+// Same operation for stages with at most kUpNG 8-channel output groups (every stage but the first): lanes run ACROSS the
+// channel groups of a row, so every warp access is a run of whole rows (f32 rows in, f32 rows + swizzled f16 rows out, no
+// partially written sectors), and a thread walks kUpNT consecutive input steps carrying the previous step's activated
+// inputs in registers (no neighbour exchange; the next step's rows are loaded before the current one is computed).
+constexpr int kUpNG = 28, kUpNT = 8;
+template <int S>
+__global__ void __launch_bounds__(128) up_rows_kernel(const UpKParams p) {
+    constexpr int K = 2 * S, WS = 16 * K + 1;
+    __shared__ float s_w[kUpNG * WS], s_ia[kUpNG * 17], s_iinv[kUpNG * 17], s_b[kUpNG * 9], s_ba[3][kUpNG * 9], s_binv[3][kUpNG * 9];
+    const int ng = p.cs_out >> 3, b = blockIdx.y, tid = threadIdx.x;
+    const int Cout = p.a.Cin / 2;
+    for (int i = tid; i < ng * 16; i += 128) {
+        const float al = (i < p.a.n_alpha && i < p.a.Cin) ? p.a.alpha[i] : 0.0f;
+        s_ia[(i >> 4) * 17 + (i & 15)] = al; s_iinv[(i >> 4) * 17 + (i & 15)] = al != 0.0f ? 1.0f / al : 0.0f;
+    }
+    for (int i = tid; i < ng * 16 * K; i += 128) {
+        const int ci = i / K;
+        s_w[(ci >> 4) * WS + (ci & 15) * K + i % K] = ci < p.a.Cin ? p.a.w[i] : 0.0f;
+    }
+    for (int i = tid; i < ng * 8; i += 128) {
+        const int o = (i >> 3) * 9 + (i & 7);
+        s_b[o] = i < Cout ? p.a.bias[i] : 0.0f;
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            const float al = (i < p.a.n_br_alpha && i < Cout) ? p.a.br_alpha[j][i] : 0.0f;
+            s_ba[j][o] = al; s_binv[j][o] = al != 0.0f ? 1.0f / al : 0.0f;
+        }
+    }
+    __syncthreads();
+    const int cpb = 128 / ng, chunk = tid / ng, gi = tid - chunk * ng;
+    const int t0 = (blockIdx.x * cpb + chunk) * kUpNT;
+    if (chunk >= cpb || t0 >= p.a.T) return;
+    const int g0 = gi * 8;
+    const bool in_ok[4] = {2 * g0 < p.cs_in, 2 * g0 + 4 < p.cs_in, 2 * g0 + 8 < p.cs_in, 2 * g0 + 12 < p.cs_in};
+    auto load_raw = [&](int t, float * out) {          // mean of the branch outputs (nano-codec.cpp:601-641) or the single input
+        const size_t xo = ((size_t)b * p.a.T + t) * p.cs_in + 2 * g0;
+#pragma unroll
+        for (int q4 = 0; q4 < 4; q4++) {
+            float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (in_ok[q4]) {
+                f = *reinterpret_cast<const float4 *>(p.a.x[0] + xo + 4 * q4);
+                if (p.a.n_x == 3) {
+                    const float4 g = *reinterpret_cast<const float4 *>(p.a.x[1] + xo + 4 * q4), h = *reinterpret_cast<const float4 *>(p.a.x[2] + xo + 4 * q4);
+                    f.x = ((f.x + g.x) + h.x) * (1.0f / 3.0f); f.y = ((f.y + g.y) + h.y) * (1.0f / 3.0f);
+                    f.z = ((f.z + g.z) + h.z) * (1.0f / 3.0f); f.w = ((f.w + g.w) + h.w) * (1.0f / 3.0f);
+                }
+            }
+            out[4 * q4] = f.x; out[4 * q4 + 1] = f.y; out[4 * q4 + 2] = f.z; out[4 * q4 + 3] = f.w;
+        }
+    };
+    auto activate = [&](float * v) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            const float al = s_ia[gi * 17 + i];
+            v[i] = al != 0.0f ? snake_fast(v[i], al, s_iinv[gi * 17 + i]) : fmaxf(v[i], 0.01f * v[i]);
+        }
+    };
+    float a_prev[16], a_cur[16], nxt[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) a_prev[i] = 0.0f;        // zero history in front of step 0: act(0) = 0
+    if (t0 > 0) { load_raw(t0 - 1, a_prev); activate(a_prev); }
+    load_raw(t0, nxt);
+    const int To = p.a.T * S;
+    const int cpr = p.rb >> 1;
+    const long long img_base = ((long long)b * p.nchunk + g0 / cpr) * p.rows;
+    const int kc = (g0 % cpr) >> 3;
+    const float * wg = s_w + gi * WS;
+    for (int i = 0; i < kUpNT; i++) {
+        const int ti = t0 + i;
+        if (ti >= p.a.T) break;
+#pragma unroll
+        for (int e = 0; e < 16; e++) a_cur[e] = nxt[e];
+        if (i + 1 < kUpNT && ti + 1 < p.a.T) load_raw(ti + 1, nxt);
+        activate(a_cur);
+#pragma unroll
+        for (int r = 0; r < S; r++) {
+            const int to = ti * S + r;
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                const float * w0 = wg + (2 * e) * K + r, * w1 = w0 + K;
+                v[e] = s_b[gi * 9 + e] + w0[0] * a_cur[2 * e] + w1[0] * a_cur[2 * e + 1] + w0[S] * a_prev[2 * e] + w1[S] * a_prev[2 * e + 1];
+            }
+            stg256f(p.a.up + ((size_t)b * To + to) * p.cs_out + g0, v);
+            const int r_img = kHP + to;
+            const long long off = (img_base + r_img) * p.rb + ((kc ^ img_swz(r_img, p.rb)) << 4);
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                float act[8];
+#pragma unroll
+                for (int e = 0; e < 8; e++) {
+                    const float al = s_ba[j][gi * 9 + e];
+                    act[e] = al != 0.0f ? snake_fast(v[e], al, s_binv[j][gi * 9 + e]) : fmaxf(v[e], 0.01f * v[e]);
+                }
+                uint4 pk;
+                pk.x = pack_h2(act[0], act[1]); pk.y = pack_h2(act[2], act[3]);
+                pk.z = pack_h2(act[4], act[5]); pk.w = pack_h2(act[6], act[7]);
+                *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(p.a.img[j]) + off) = pk;
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 16; e++) a_prev[e] = a_cur[e];
+    }
+}
+
 // HalfSnake -> causal conv (C -> 1, K taps, operands rounded to f16 as ggml_conv_1d does) -> tanh  (nano-codec.cpp:703-712)
 struct PostKParams { PostArgs a; int cs; };
 // block = 256 consecutive time steps of one utterance (+ K-1 history rows): every thread activates ITS row once
@@ -502,23 +607,24 @@ __global__ void __launch_bounds__(256) post_tm_kernel(const PostKParams p) {
     const int b = blockIdx.y, t0 = blockIdx.x * 256, tid = threadIdx.x;
     const int H = p.a.K - 1;              // history rows
     for (int i = tid; i < p.a.C * p.a.K; i += 256) sw[i] = f16r(p.a.w[i]);
-    for (int r = tid; r < 256 + H; r += 256) {
+    // staging: consecutive lanes take consecutive 16-byte pieces of the rows (whole-row runs per warp access)
+    const int q4n = p.cs >> 2;
+    for (int i = tid; i < (256 + H) * q4n; i += 256) {
+        const int r = i / q4n, c0 = (i - r * q4n) * 4;
         const int t = t0 - H + r;
-        float * dst = sa + r * (kPostCS + 1);
-        if (t < 0 || t >= p.a.T) {
-            for (int c = 0; c < p.a.C; c++) dst[c] = 0.0f;
-            continue;
+        float * dst = sa + r * (kPostCS + 1) + c0;
+        float xv[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        const bool ok = t >= 0 && t < p.a.T;
+        if (ok) {
+            const size_t xo = ((size_t)b * p.a.T + t) * p.cs + c0;
+            const float4 f = *reinterpret_cast<const float4 *>(p.a.x[0] + xo), g = *reinterpret_cast<const float4 *>(p.a.x[1] + xo),
+                         h = *reinterpret_cast<const float4 *>(p.a.x[2] + xo);
+            xv[0] = ((f.x + g.x) + h.x) * (1.0f / 3.0f); xv[1] = ((f.y + g.y) + h.y) * (1.0f / 3.0f);
+            xv[2] = ((f.z + g.z) + h.z) * (1.0f / 3.0f); xv[3] = ((f.w + g.w) + h.w) * (1.0f / 3.0f);
         }
-        const size_t xo = ((size_t)b * p.a.T + t) * p.cs;
-        for (int c0 = 0; c0 < p.a.C; c0 += 4) {
-            const float4 f = *reinterpret_cast<const float4 *>(p.a.x[0] + xo + c0), g = *reinterpret_cast<const float4 *>(p.a.x[1] + xo + c0),
-                         h = *reinterpret_cast<const float4 *>(p.a.x[2] + xo + c0);
-            const float xv[4] = {((f.x + g.x) + h.x) * (1.0f / 3.0f), ((f.y + g.y) + h.y) * (1.0f / 3.0f),
-                                 ((f.z + g.z) + h.z) * (1.0f / 3.0f), ((f.w + g.w) + h.w) * (1.0f / 3.0f)};
 #pragma unroll
-            for (int e = 0; e < 4; e++)
-                if (c0 + e < p.a.C) dst[c0 + e] = f16r(half_snake_fast(xv[e], c0 + e, p.a.alpha, p.a.n_alpha));
-        }
+        for (int e = 0; e < 4; e++)
+            if (c0 + e < p.a.C) dst[e] = ok ? f16r(half_snake_fast(xv[e], c0 + e, p.a.alpha, p.a.n_alpha)) : 0.0f;
     }
     __syncthreads();
     const int t = t0 + tid;
@@ -617,8 +723,18 @@ bool launch_up(const Geom & g, const UpArgs & a, cudaStream_t stream) {
     UpKParams p = {};
     p.a = a; p.cs_in = row_stride(a.Cin); p.cs_out = row_stride(a.Cin / 2); p.nchunk = g.nchunk; p.rb = g.rb; p.rows = (long long)act_rows(a.T * a.s);
     if (a.s > 8) { set_error("codec: up-sampling stride > 8"); return false; }
-    dim3 grid((a.T + 127) / 128, p.cs_out / 8, a.B);
-    up_tm_kernel<<<grid, 128, 0, stream>>>(p);
+    static const bool lane_per_step = getenv("MGB_UP_LANE_PER_STEP") != nullptr;      // diagnostic: the first-stage kernel everywhere
+    const int ng = p.cs_out / 8;
+    if (!lane_per_step && ng <= kUpNG && (a.s == 2 || a.s == 4 || a.s == 8)) {
+        const int cpb = 128 / ng;
+        dim3 grid(((a.T + kUpNT - 1) / kUpNT + cpb - 1) / cpb, a.B);
+        if (a.s == 2) up_rows_kernel<2><<<grid, 128, 0, stream>>>(p);
+        else if (a.s == 4) up_rows_kernel<4><<<grid, 128, 0, stream>>>(p);
+        else up_rows_kernel<8><<<grid, 128, 0, stream>>>(p);
+    } else {
+        dim3 grid((a.T + 127) / 128, p.cs_out / 8, a.B);
+        up_tm_kernel<<<grid, 128, 0, stream>>>(p);
+    }
     MGB_LAUNCH_CHECK();
     return true;
 }

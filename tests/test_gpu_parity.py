@@ -614,6 +614,27 @@ def test_codec_tensor_core_path_matches_cuda_core_path_and_oracle(B, oracle_mod,
     assert snr_db(p_small[0], c_cc.decode(small[0])) >= 55.0
 
 
+def test_codec_full_size_properties(B, oracle_mod, codec_path):
+    """BASELINE config 3 at its full size (32 utterances x 1291 frames = 60 s each), checked through properties the causal
+    codec offers: a prefix of the long decode equals the decode of the prefix (zero history, nano-codec.cpp:429-466), batch rows
+    are independent, the head of the long decode matches the oracle, every sample is finite and inside tanh's range."""
+    rng = np.random.default_rng(42)
+    T = 1291
+    codes = rng.integers(0, 2016, (32, 8, T)).astype(np.int32)
+    c = B.Codec(codec_path)
+    pcm = c.decode(codes)
+    assert pcm.shape == (32, T * 1024)
+    assert np.isfinite(pcm).all() and np.abs(pcm).max() <= 1.0
+    for b, n in ((0, 40), (17, 129), (31, 1)):
+        head = c.decode(np.ascontiguousarray(codes[b][:, :n]))
+        np.testing.assert_allclose(head, pcm[b][:n * 1024], rtol=0, atol=1e-5)
+    np.testing.assert_allclose(c.decode(codes[9]), pcm[9], rtol=0, atol=1e-6)
+    ref = oracle_mod.OracleCodec(codec_path, conv_f16=True).decode(np.ascontiguousarray(codes[3][:, :5]))
+    assert snr_db(pcm[3][:5 * 1024], ref) >= 40.0
+    # rows differ (no aliasing of scratch images between utterances)
+    assert np.abs(pcm[0] - pcm[1]).max() > 1e-3
+
+
 def test_codec_ragged_lengths(B, oracle_mod, codec_path):
     c = B.Codec(codec_path)
     o = oracle_mod.OracleCodec(codec_path, conv_f16=True)
