@@ -277,6 +277,12 @@ bool launch_linear_tc(const LinearArgs & a, cudaStream_t stream) {
             if (resid) return launch_tc<64, 4, EPI_RES>(W, hi, lo, KT, e, stream);
             return launch_tc<64, 4, EPI_GENERIC>(W, hi, lo, KT, e, stream);
         }
+        static const bool mid2 = getenv("MGB_SPLIT_MID2") != nullptr;     // diagnostic: 2-way instead of 4-way split for K = 512..1984
+        if (!no_split && !mid2 && KT >= 8 && KT % 4 == 0) {
+            if (qkv) return launch_tc<64, 4, EPI_QKV>(W, hi, lo, KT, e, stream);
+            if (resid) return launch_tc<64, 4, EPI_RES>(W, hi, lo, KT, e, stream);
+            if (gpack) return launch_tc<64, 4, EPI_GELU_PACK>(W, hi, lo, KT, e, stream);
+        }
         if (!no_split && KT >= 8) {
             if (qkv) return launch_tc<64, 2, EPI_QKV>(W, hi, lo, KT, e, stream);
             if (resid) return launch_tc<64, 2, EPI_RES>(W, hi, lo, KT, e, stream);
