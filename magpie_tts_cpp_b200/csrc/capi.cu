@@ -834,7 +834,8 @@ int mgb_codec_decode(mgb_codec * cc, const int32_t * codes, int batch, int n_fra
     if (!grow((void **)&c->d_pcm, &c->pcm_cap, ns * 4)) return MGB_ECUDA;
     // bound scratch memory: decode utterances in groups of <= ~8K frames.  All groups are enqueued first; the PCM of
     // group g is then copied back while the kernels of the later groups are still running (events per group).
-    const int per = std::max(1, 8192 / n_frames);
+    static const int group_frames = [] { const char * e = getenv("MGB_CODEC_GROUP_FRAMES"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 8192; }();
+    const int per = std::max(1, group_frames / n_frames);
     const int n_groups = (batch + per - 1) / per;
     while ((int)c->group_events.size() < n_groups) {
         cudaEvent_t e = nullptr;

@@ -243,7 +243,8 @@ bool tc_linear_supported(const LinearArgs & a) {
 
 bool launch_linear_tc(const LinearArgs & a, cudaStream_t stream) {
     const int Ktap = a.W.K, taps = a.W.taps, K = Ktap * taps, M = a.M;       // taps > 1: one GEMM over the concatenated taps
-    const int MT = M <= 64 ? 64 : 128;
+    static const int mt64_max = [] { const char * e = getenv("MGB_TC_MT64_MAX"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 128; }();
+    const int MT = M <= mt64_max ? 64 : 128;     // up to two 64-token tiles with cluster split-K: shorter per-SM ingest chains than one 128-token tile
     const int Mpad = (M + MT - 1) / MT * MT;
     bf * hi = (bf *)a.tc_scratch;
     bf * lo = hi + (size_t)Mpad * K;
