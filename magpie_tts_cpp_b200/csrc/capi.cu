@@ -47,6 +47,7 @@ struct Session {
     std::vector<int32_t> h_ntext, h_enc_off;
     int M_enc = 0;
     int pos = 0;                       // host mirror of the (uniform) decode position
+    int attn_split = 0;                // batched decoder step: CTAs per (head, utterance) in the self-attention (long KV, few utterances)
     bool encoded = false, prefilled = false;
     // loop buffers (grown on demand)
     int32_t * l_forced = nullptr, * l_sampled = nullptr, * l_argmax = nullptr; float * l_uniforms = nullptr;
@@ -116,7 +117,7 @@ static bool decoder_layers(Session & s, Tokens tok, bool want_hidden) {
         at.prefill_len = s.prefill_len;
         // batched decoder step on the tensor-core path: the attention kernel writes the O-projection's packed input itself
         if (M == s.B && tok.utt == s.dec_utt && M <= 64 && at.dh == 64 && tc_linear_supported(o) && getenv("MGB_NO_CHAIN") == nullptr) {
-            at.pack_out = s.tc_scratch; o.x_prepacked = true;
+            at.pack_out = s.tc_scratch; o.x_prepacked = true; at.kv_split = s.attn_split;
         }
         if (!launch_attention(at, s.stream)) return false;
         if (!launch_linear(o, s.stream)) return false;
@@ -535,6 +536,7 @@ int mgb_decoder_step(mgb_session * ss, const int32_t * codes, float * hidden_out
             if (codes[i] < 0 || codes[i] >= hp.vocab_per_cb) { set_error("mgb_decoder_step: code out of range"); return MGB_EINVAL; }
         if (cudaMemcpyAsync(s->d_codes, codes, (size_t)s->B * 8 * 4, cudaMemcpyHostToDevice, st) != cudaSuccess) { set_error("H2D failed"); return MGB_ECUDA; }
     }
+    s->attn_split = attention_plan_kv_split(s->m->hp.dec_sa_heads * s->B, s->pos + 1);
     if (!decoder_step_device(*s) || !launch_advance(*s, false)) return MGB_ECUDA;
     if (hidden_out && cudaMemcpyAsync(hidden_out, s->hidden, (size_t)s->B * hp.d_model * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) {
         set_error("D2H failed"); return MGB_ECUDA;
@@ -683,6 +685,8 @@ static int run_loop(Session & s, const LoopCfg & c, int * steps_run) {
     if (s.pos + c.T > s.max_seq) { set_error("generation loop: KV cache too small for the requested steps"); return MGB_ERANGE; }
     // (the persistent kernel scans at most 6 key splits x 480 cached keys per attention item)
     if (s.loop_grid > 0 && s.loop_tables && s.pos + c.T <= 2880) return run_loop_persistent(s, c, steps_run);
+    // the iteration is captured once, so the key split of the self-attention is planned for the KV length the loop will reach
+    s.attn_split = attention_plan_kv_split(s.m->hp.dec_sa_heads * B, s.pos + c.T);
     std::vector<int32_t> neg(B, -1);
     if (cudaMemsetAsync(s.d_step, 0, 4, st) != cudaSuccess ||
         cudaMemcpyAsync(s.d_done, neg.data(), B * 4, cudaMemcpyHostToDevice, st) != cudaSuccess) { set_error("loop init failed"); return MGB_ECUDA; }

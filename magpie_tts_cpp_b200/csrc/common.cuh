@@ -77,6 +77,9 @@ template <> struct WT<float> {
         w[0] = __uint_as_float(u.x); w[1] = __uint_as_float(u.y);
         w[2] = __uint_as_float(u.z); w[3] = __uint_as_float(u.w);
     }
+    __device__ static __forceinline__ void unpack(const uint4 & u, float (&w)[4]) {
+        w[0] = __uint_as_float(u.x); w[1] = __uint_as_float(u.y); w[2] = __uint_as_float(u.z); w[3] = __uint_as_float(u.w);
+    }
     __device__ static __forceinline__ float get(const float * p) { return *p; }
     __device__ static __forceinline__ void put(float * p, float v) { *p = v; }
 };
@@ -84,6 +87,10 @@ template <> struct WT<__nv_bfloat16> {
     static constexpr int VEC = 8;
     __device__ static __forceinline__ void load(const __nv_bfloat16 * p, float (&w)[8]) {
         uint4 u = ldg_stream(p);
+        w[0] = bf16lo(u.x); w[1] = bf16hi(u.x); w[2] = bf16lo(u.y); w[3] = bf16hi(u.y);
+        w[4] = bf16lo(u.z); w[5] = bf16hi(u.z); w[6] = bf16lo(u.w); w[7] = bf16hi(u.w);
+    }
+    __device__ static __forceinline__ void unpack(const uint4 & u, float (&w)[8]) {
         w[0] = bf16lo(u.x); w[1] = bf16hi(u.x); w[2] = bf16lo(u.y); w[3] = bf16hi(u.y);
         w[4] = bf16lo(u.z); w[5] = bf16hi(u.z); w[6] = bf16lo(u.w); w[7] = bf16hi(u.w);
     }

@@ -60,8 +60,10 @@ struct AttnArgs {
     float * out = nullptr; int ldo = 0;
     void * pack_out = nullptr;                   // dh == 64, <= 64 tokens: write hi | lo tile images for the next GEMM instead of `out`
     int prefill_len = 0;                         // > 0: tokens are utterance-major runs of positions 0..prefill_len-1 (context prefill)
+    int kv_split = 0;                            // packed-output decoder step only: >= 1 = long-KV kernel, keys of a (head, token) divided over a cluster of this many CTAs
 };
 bool launch_attention(const AttnArgs & a, cudaStream_t stream);
+int attention_plan_kv_split(int items, int max_keys);   // cluster size for a decoder step that will reach max_keys keys
 // batched decoder step: folded cross-attention x += softmax(M LN(x)) N (tables from launch_xattn_fold, frame_loop.cu)
 // pack_ln_w / pack_out (optional, B <= 64): additionally emit LN(x_new; pack_ln_w) as hi | lo tile images for the next GEMM
 bool launch_xattn_folded(float * x, const float * ln_w, float eps, const float * xm, const float * xn, const int32_t * n_ctx, int B, int d,

@@ -170,6 +170,8 @@ struct AttnParams {
     float * out; int ldo;
     __nv_bfloat16 * pk_hi; __nv_bfloat16 * pk_lo;      // optional (DH == 64, <= 64 tokens): output as hi | lo tile images for the next GEMM
     int pdl;                                           // launched with programmatic stream serialization (see kernel)
+    int split_min_keys;                                // SPLIT kernels: a token's keys are divided over the cluster from this many keys per CTA on
+    int pf_keys;                                       // pdl: keys per CTA whose K / V rows are prefetched into L2 ahead of the wait (the launch's share of L2)
 };
 
 constexpr int kAttnWarps = 8;
@@ -178,8 +180,23 @@ constexpr int kAttnWarps = 8;
 // 16-byte load each (fully used sectors), so a warp instruction covers 32 / LPK keys; each lane group keeps its own online
 // softmax state (m, l, acc over the lane's VEC output dims) for the keys it owns, 4 key slots are in flight per lane, and
 // the groups / warps are merged at the end.
-template <typename T, int DH>
-__global__ void __launch_bounds__(kAttnWarps * 32) attention_kernel(const AttnParams p) {
+//
+// SPLIT (long KV, few tokens: BASELINE configs[4]): grid (H, M, S) launched as clusters (1, 1, S).  The S CTAs of a cluster divide
+// the keys of their (head, token) into contiguous 128-aligned ranges (flash-decoding), so H x M x S work items fill the SMs in
+// balanced waves and S times as many loads are in flight per KV row; ranks > 0 hand their (max, sum, unnormalised output) to
+// rank 0 through DSMEM, which merges them in rank order (deterministic) and writes the output.
+__device__ __forceinline__ void attn_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void attn_dsmem_store(float * local, unsigned rank, float v) {
+    uint32_t la = (uint32_t)__cvta_generic_to_shared(local), ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(rank));
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(v) : "memory");
+}
+constexpr int kAttnMaxSplit = 8;
+
+template <typename T, int DH, int SPLIT = 0>      // SPLIT: 0 = one CTA per (head, token); 1 / 2 = cluster key split compiled for 2 / 3 resident CTAs per SM
+__global__ void __launch_bounds__(kAttnWarps * 32, SPLIT == 2 ? 3 : 0) attention_kernel(const AttnParams p) {
     constexpr int VEC = WT<T>::VEC;
     constexpr int LPK = DH / VEC;            // lanes per key row
     constexpr int KPI = 32 / LPK;            // keys per warp instruction
@@ -187,6 +204,7 @@ __global__ void __launch_bounds__(kAttnWarps * 32) attention_kernel(const AttnPa
     static_assert(LPK >= 1 && LPK <= 32 && (LPK & (LPK - 1)) == 0, "head dim / vector width must be a power of two <= 32");
     __shared__ float s_m[kAttnWarps], s_l[kAttnWarps];
     __shared__ float s_acc[kAttnWarps][DH];
+    __shared__ float x_m[SPLIT ? kAttnMaxSplit : 1], x_l[SPLIT ? kAttnMaxSplit : 1], x_o[SPLIT ? kAttnMaxSplit : 1][DH];   // rank 0: the peers' partials
     const int t = blockIdx.y, h = blockIdx.x;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int sub = lane % LPK, grp = lane / LPK;
@@ -194,13 +212,21 @@ __global__ void __launch_bounds__(kAttnWarps * 32) attention_kernel(const AttnPa
     const int nk = p.causal ? p.pos[t] + 1 : p.n_ctx[utt];
     const float scale = 1.0f / sqrtf((float)DH);
     const int ld = p.H * DH;
+    int k0 = 0, k1 = nk;                   // this CTA's key range
+    unsigned crank = 0, csize = 1;
+    if constexpr (SPLIT) {
+        crank = blockIdx.z; csize = gridDim.z;             // cluster (1, 1, S) spans the whole z extent
+        const int se = nk >= p.split_min_keys * (int)csize ? (int)csize : 1;
+        const int chunk = (((nk + se - 1) / se) + 127) & ~127;
+        k0 = min(nk, (int)crank * chunk); k1 = (int)crank < se ? min(nk, k0 + chunk) : k0;
+    }
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");      // the following GEMM may start prefetching its weights
     if (p.pdl) {
         // launched as a programmatic dependent of the QKV GEMM: the old keys' K / V rows do not depend on it, so they are
         // pulled into L2 while that kernel is still running; q and the new key's row are read after the wait
         const char * Kp = (const char *)p.K + ((size_t)utt * p.rows_per_utt * ld + h * DH) * sizeof(T);
         const char * Vp = (const char *)p.V + ((size_t)utt * p.rows_per_utt * ld + h * DH) * sizeof(T);
-        for (int j = tid; j < nk - 1; j += kAttnWarps * 32) {
+        for (int j = k0 + tid; j < min(min(k1, nk - 1), k0 + p.pf_keys); j += kAttnWarps * 32) {
             asm volatile("prefetch.global.L2 [%0];" ::"l"(Kp + (size_t)j * ld * sizeof(T)));
             asm volatile("prefetch.global.L2 [%0];" ::"l"(Vp + (size_t)j * ld * sizeof(T)));
         }
@@ -219,12 +245,66 @@ __global__ void __launch_bounds__(kAttnWarps * 32) attention_kernel(const AttnPa
 #pragma unroll
     for (int v = 0; v < VEC; v++) acc[v] = 0.0f;
 
-    for (int base = warp * (KPI * U); base < nk; base += kAttnWarps * KPI * U) {
+    if constexpr (SPLIT == 1) {
+        // long KV: software-pipelined scan.  The raw 16-byte K / V words of the NEXT 16 keys of the warp are requested before the
+        // current ones are used (twice the bytes in flight per warp, loads overlap the softmax arithmetic); same arithmetic and
+        // order per key as the loop below.
+        constexpr int STEP = kAttnWarps * KPI * U;
+        uint4 kr[U], vr[U];
+        int base = k0 + warp * (KPI * U);
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int j = base + u * KPI + grp;
+            kr[u] = make_uint4(0u, 0u, 0u, 0u); vr[u] = make_uint4(0u, 0u, 0u, 0u);
+            if (j < k1) { kr[u] = ldg_stream(Kb + (size_t)j * ld); vr[u] = ldg_stream(Vb + (size_t)j * ld); }
+        }
+        for (; base < k1; base += STEP) {
+            uint4 kc[U], vc[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) { kc[u] = kr[u]; vc[u] = vr[u]; }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int j = base + STEP + u * KPI + grp;
+                if (j < k1) { kr[u] = ldg_stream(Kb + (size_t)j * ld); vr[u] = ldg_stream(Vb + (size_t)j * ld); }
+            }
+            float sc[U], mnew = mx;
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                float kk[VEC];
+                WT<T>::unpack(kc[u], kk);
+                float d = 0.0f;
+#pragma unroll
+                for (int v = 0; v < VEC; v++) d = fmaf(kk[v], qv[v], d);
+#pragma unroll
+                for (int o = LPK / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+                sc[u] = (base + u * KPI + grp < k1) ? d : -INFINITY;
+                mnew = fmaxf(mnew, sc[u]);
+            }
+            if (mnew != -INFINITY) {
+                const float corr = expf(mx - mnew);
+                float ps = 0.0f;
+#pragma unroll
+                for (int v = 0; v < VEC; v++) acc[v] *= corr;
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    const float pj = expf(sc[u] - mnew);
+                    ps += pj;
+                    float vv[VEC];
+                    WT<T>::unpack(vc[u], vv);
+#pragma unroll
+                    for (int v = 0; v < VEC; v++) acc[v] = fmaf(pj, vv[v], acc[v]);
+                }
+                l = l * corr + ps;
+                mx = mnew;
+            }
+        }
+    } else {
+    for (int base = k0 + warp * (KPI * U); base < k1; base += kAttnWarps * KPI * U) {
         float kk[U][VEC], vv[U][VEC], sc[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const int j = base + u * KPI + grp;
-            if (j < nk) {
+            if (j < k1) {
                 WT<T>::load(Kb + (size_t)j * ld, kk[u]);
                 WT<T>::load(Vb + (size_t)j * ld, vv[u]);
             } else {
@@ -240,7 +320,7 @@ __global__ void __launch_bounds__(kAttnWarps * 32) attention_kernel(const AttnPa
             for (int v = 0; v < VEC; v++) d = fmaf(kk[u][v], qv[v], d);
 #pragma unroll
             for (int o = LPK / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-            sc[u] = (base + u * KPI + grp < nk) ? d : -INFINITY;
+            sc[u] = (base + u * KPI + grp < k1) ? d : -INFINITY;
             mnew = fmaxf(mnew, sc[u]);
         }
         if (mnew != -INFINITY) {
@@ -258,6 +338,7 @@ __global__ void __launch_bounds__(kAttnWarps * 32) attention_kernel(const AttnPa
             l = l * corr + ps;
             mx = mnew;
         }
+    }
     }
     // merge the key groups of the warp
 #pragma unroll
@@ -279,17 +360,38 @@ __global__ void __launch_bounds__(kAttnWarps * 32) attention_kernel(const AttnPa
         for (int v = 0; v < VEC; v++) s_acc[warp][sub * VEC + v] = acc[v];
     }
     __syncthreads();
+    float M = -INFINITY, L = 0.0f, o = 0.0f;
     if (tid < DH) {
-        float M = s_m[0];
+        M = s_m[0];
 #pragma unroll
         for (int w = 1; w < kAttnWarps; w++) M = fmaxf(M, s_m[w]);
-        float L = 0.0f, o = 0.0f;
 #pragma unroll
         for (int w = 0; w < kAttnWarps; w++) {
             const float f = s_m[w] == -INFINITY ? 0.0f : expf(s_m[w] - M);
             L += f * s_l[w];
             o += f * s_acc[w][tid];
         }
+    }
+    if constexpr (SPLIT) {
+        if (crank != 0 && tid < DH) {
+            if (tid == 0) { attn_dsmem_store(&x_m[crank], 0, M); attn_dsmem_store(&x_l[crank], 0, L); }
+            attn_dsmem_store(&x_o[crank][tid], 0, o);
+        }
+        attn_cluster_sync();               // every thread of every CTA of the cluster; rank 0's shared memory is written before it
+        if (crank != 0) return;
+        if (tid < DH) {
+            for (unsigned r = 1; r < csize; r++) {          // fixed rank order: deterministic
+                const float om = x_m[r];
+                if (om == -INFINITY) continue;              // that rank had no keys
+                const float mn = fmaxf(M, om);
+                const float fa = M == -INFINITY ? 0.0f : expf(M - mn), fb = expf(om - mn);
+                L = L * fa + x_l[r] * fb;
+                o = o * fa + x_o[r][tid] * fb;
+                M = mn;
+            }
+        }
+    }
+    if (tid < DH) {
         const float y = o * (1.0f / L);
         if (p.pk_hi) {
             // head h is exactly k tile h of the following GEMM (64 columns = one 128-byte swizzle row): gemm_tc.cu layout
@@ -437,6 +539,31 @@ __global__ void __launch_bounds__(256) prefill_attention_kernel(const AttnParams
     }
 }
 
+// Key split for a decoder step of `items` = heads x tokens (head, token) pairs over up to `max_keys` keys: the S <= 8 that
+// minimises waves(items * S) / S, i.e. the time of the last wave relative to perfectly divisible work (ties: the smaller S).
+int attention_plan_kv_split(int items, int max_keys) {
+    if (items <= 0 || max_keys < 768 || getenv("MGB_NO_ATTN_SPLIT")) return 0;      // 0 = the one-CTA kernel
+    if (getenv("MGB_ATTN_SPLIT")) return std::max(0, std::min(atoi(getenv("MGB_ATTN_SPLIT")), kAttnMaxSplit));
+    static int cap = 0;
+    if (cap == 0) {
+        int dev = 0, sms = 148, per_sm = 2;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const cudaError_t e = getenv("MGB_ATTN_OCC3")
+            ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, attention_kernel<__nv_bfloat16, 64, 2>, kAttnWarps * 32, 0)
+            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, attention_kernel<__nv_bfloat16, 64, 1>, kAttnWarps * 32, 0);
+        if (e != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 2; }
+        cap = sms * per_sm;
+    }
+    int best = 1; double best_cost = 1e30;
+    for (int S = 1; S <= kAttnMaxSplit; S++) {
+        if (S > 1 && max_keys / S < 256) break;
+        const double cost = (double)((items * S + cap - 1) / cap) / S;
+        if (cost < best_cost * 0.97) { best_cost = cost; best = S; }
+    }
+    return best;
+}
+
 bool launch_attention(const AttnArgs & a, cudaStream_t stream) {
     if (a.tok.M <= 0) return true;
     AttnParams p;
@@ -471,14 +598,25 @@ bool launch_attention(const AttnArgs & a, cudaStream_t stream) {
     }
     dim3 grid(a.H, a.tok.M);
     p.pdl = (a.pack_out && !f32 && a.dh == 64) ? 1 : 0;       // decoder-step chain only
+    p.split_min_keys = 256; p.pf_keys = 0;
     if (p.pdl) {
+        const int S = std::max(0, std::min(a.kv_split, kAttnMaxSplit));       // 0: one-CTA kernel; >= 1: long-KV kernels, cluster of S
+        // the prefetch ahead of the dependency wait is capped at about half of the 126 MB L2 for the whole launch: rows prefetched
+        // beyond what L2 holds are evicted before they are used and cross HBM twice (long KV: 247 MB of K / V rows per layer)
+        const double pf_mb = getenv("MGB_ATTN_PF_MB") ? atof(getenv("MGB_ATTN_PF_MB")) : 64.0;
+        p.pf_keys = (int)std::min(1e9, pf_mb * 1048576.0 / ((double)a.H * a.tok.M * std::max(S, 1) * 2.0 * a.dh * sizeof(__nv_bfloat16)));
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = grid; cfg.blockDim = dim3(kAttnWarps * 32); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
-        cudaLaunchAttribute at[1];
+        cfg.gridDim = dim3(a.H, a.tok.M, std::max(S, 1)); cfg.blockDim = dim3(kAttnWarps * 32); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+        cudaLaunchAttribute at[2];
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
-        MGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, attention_kernel<__nv_bfloat16, 64>, p));
+        at[1].id = cudaLaunchAttributeClusterDimension;
+        at[1].val.clusterDim.x = 1; at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = std::max(S, 1);
+        cfg.attrs = at; cfg.numAttrs = S >= 1 ? 2 : 1;
+        const bool occ3 = getenv("MGB_ATTN_OCC3") != nullptr;
+        if (S >= 1 && occ3) MGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, attention_kernel<__nv_bfloat16, 64, 2>, p));
+        else if (S >= 1) MGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, attention_kernel<__nv_bfloat16, 64, 1>, p));
+        else MGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, attention_kernel<__nv_bfloat16, 64>, p));
         MGB_LAUNCH_CHECK();
         return true;
     }

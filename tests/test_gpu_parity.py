@@ -444,6 +444,45 @@ def test_folded_cross_attention_matches_unfolded_kernels(B, full_model_path, ful
     m.close()
 
 
+def test_long_kv_attention_key_split_matches_single_cta_and_oracle(B, oracle_mod, full_model_path, monkeypatch):
+    """Decoder steps that reach >= 768 cached keys with few utterances divide each (head, utterance)'s keys over a CTA cluster
+    (DSMEM merge in rank order) and scan them with a software-pipelined loop.  The long-KV kernels (cluster of 1, 2 and 3 CTAs,
+    both occupancy builds, with and without the L2 prefetch, and the planner's own choice) must reproduce the one-CTA kernel
+    and the oracle's hidden states at the long positions."""
+    nb, T = 16, 700                                   # KV length 111 .. 810
+    codes1 = np.random.default_rng(5).integers(0, 2016, (T, 8)).astype(np.int32)
+    codes = np.repeat(codes1[None], nb, axis=0)
+
+    def run(env):
+        for k in ("MGB_NO_ATTN_SPLIT", "MGB_ATTN_SPLIT", "MGB_ATTN_OCC3", "MGB_ATTN_PF_MB"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        m = B.Model(full_model_path, 0, B.PREC_BF16)
+        s = m.session(batch=nb, max_text=32, max_seq=110 + T + 16)
+        s.encode_text([HELLO] * nb, want_output=False)
+        s.prefill([0] * nb)
+        hid, _, _ = s.teacher_forced(codes, want_logits=False, want_greedy=False)
+        s.close(); m.close()
+        return hid
+
+    base = run({"MGB_NO_ATTN_SPLIT": "1"})
+    for env in ({"MGB_ATTN_SPLIT": "1"}, {"MGB_ATTN_SPLIT": "2"}, {"MGB_ATTN_SPLIT": "3", "MGB_ATTN_PF_MB": "0"},
+                {"MGB_ATTN_SPLIT": "3", "MGB_ATTN_OCC3": "1"}, {}):
+        hid = run(env)
+        close(hid[0, -200:], base[0, -200:], 2e-3)
+        for b in (1, nb - 1):
+            np.testing.assert_array_equal(hid[b], hid[0])        # equal rows, equal results (fixed merge order)
+    o = oracle_mod.OracleModel(full_model_path)
+    st = o.new_state(o.encode_text(HELLO), 0, 110 + T + 16)
+    prev = np.full(8, o.hp["audio_bos_id"], np.int32)
+    ref = []
+    for t in range(T):
+        ref.append(st.step(prev)); prev = codes1[t]
+    close(hid[0, -8:], np.stack(ref[-8:]), 2e-2)
+    close(base[0, -8:], np.stack(ref[-8:]), 2e-2)
+
+
 @pytest.mark.parametrize("nb", [70, 130])
 def test_large_batches_take_the_multi_tile_paths(B, full_model_path, full_oracle, nb):
     """More than 64 utterances: two 64-token tiles (70) / 128-token GEMM tiles and > 1 owned utterance per CTA in the batched
