@@ -195,7 +195,7 @@ __device__ __forceinline__ void attn_dsmem_store(float * local, unsigned rank, f
 }
 constexpr int kAttnMaxSplit = 8;
 
-template <typename T, int DH, int SPLIT = 0>      // SPLIT: 0 = one CTA per (head, token); 1 / 2 = cluster key split compiled for 2 / 3 resident CTAs per SM
+template <typename T, int DH, int SPLIT = 0>      // SPLIT: 0 = one CTA per (head, token); 1 / 2 = pipelined scan + cluster key split compiled for 2 / 3 resident CTAs per SM
 __global__ void __launch_bounds__(kAttnWarps * 32, SPLIT == 2 ? 3 : 0) attention_kernel(const AttnParams p) {
     constexpr int VEC = WT<T>::VEC;
     constexpr int LPK = DH / VEC;            // lanes per key row
@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(kAttnWarps * 32, SPLIT == 2 ? 3 : 0) attention
 #pragma unroll
     for (int v = 0; v < VEC; v++) acc[v] = 0.0f;
 
-    if constexpr (SPLIT == 1) {
+    if constexpr (SPLIT >= 1) {
         // long KV: software-pipelined scan.  The raw 16-byte K / V words of the NEXT 16 keys of the warp are requested before the
         // current ones are used (twice the bytes in flight per warp, loads overlap the softmax arithmetic); same arithmetic and
         // order per key as the loop below.

@@ -1,2 +1,6 @@
-python bench.py --gpus 2 --steps 3 --warmup 3 > gpurun_out/bench_2gpu_b1.log 2>&1; echo "rc=$?" >> gpurun_out/bench_2gpu_b1.log; tail -2 gpurun_out/bench_2gpu_b1.log | cut -c1-200
-python bench.py --gpus 2 --batch 64 --steps 2 --warmup 3 > gpurun_out/bench_2gpu_b64.log 2>&1; echo "rc=$?" >> gpurun_out/bench_2gpu_b64.log; tail -2 gpurun_out/bench_2gpu_b64.log | cut -c1-200
+L=gpurun_out/split_ab3.log; rm -f $L
+for v in "X=1" "MGB_ATTN_OCC3=1"; do echo "== b64 $v" >> $L; env $v timeout 120 python tools/b64_step.py 215 1 >> $L 2>&1; done
+for v in "X=1" "MGB_ATTN_OCC3=1" "MGB_ATTN_OCC3=1 MGB_ATTN_SPLIT=2"; do echo "== long32 $v" >> $L; env $v timeout 120 python tools/long_step.py 2>&1 | grep -v "KV scan" >> $L; done
+for v in "X=1" "MGB_ATTN_OCC3=1" "MGB_ATTN_OCC3=1 MGB_ATTN_SPLIT=3"; do echo "== long16 $v" >> $L; env $v timeout 120 python tools/long_step.py 2400 2 16 2>&1 | grep -v "KV scan" >> $L; done
+cat $L
+timeout 300 python -m pytest tests/test_gpu_parity.py -x -q -k "long_kv" 2>&1 | tail -3
