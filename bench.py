@@ -15,6 +15,9 @@ N > 1: launched under torchrun, one rank per GPU, each rank runs the same per-GP
 own utterance (independent utterances, no collective on the data path -> weak scaling); value is
 all ranks' frames / max-over-ranks time.
 
+extra (N=1): configs[3] (64 utterances x 215 frames) and configs[4]'s per-GPU share (Q8_0 GGUF, 32 x 2600 frames), each with
+its HBM step roofline (weights once + per-utterance mean K/V scan), and the codec on configs[2] with its tensor roofline.
+
 --impl reference: the CPU restatement of the reference (oracle/, all host threads) on a bounded
 sample of the same workload.  The real reference cannot be built here (needs ggml).
 """
@@ -35,6 +38,17 @@ HELLO = [2378, 7, 4, 11, 11, 14, 32, 26, 22, 14, 17, 11, 3, 32, 28, 2379]   # "H
 FRAMES = int(os.environ.get("MGB_BENCH_FRAMES", "500"))   # override only for profiling runs (not a bench value)
 METRIC = "decoder_frames_per_s"
 UNIT = "frames/s"
+
+
+def step_roofline(m, B, ctx, frames, text_len, s_per_step):
+    """HBM roofline of one batched decoder+LT step: weights once + per utterance the mean K/V scan (W + B * KV(P))."""
+    hp, wsz = m.hp, 2
+    pbar = ctx + (frames + 1) / 2.0
+    kv = hp["dec_layers"] * 2 * pbar * hp["d_model"] * wsz + hp["dec_layers"] * 2 * text_len * 128 * wsz
+    by = m.step_weight_bytes + B * kv
+    hbm, _, src = peaks()
+    return {"bound": "hbm", "achieved": by / s_per_step / 1e9, "peak": hbm, "peak_source": src, "unit": "GB/s",
+            "frac": by / s_per_step / 1e9 / hbm, "algorithmic_bytes_per_step": by, "step_us": s_per_step * 1e6}
 
 
 def peaks():
@@ -259,6 +273,7 @@ def extra_measurements(binding, fixtures, m, args):
         out["decoder_b64_frames_per_s"] = B * frames / (s.last_loop_ms * 1e-3)
         out["decoder_b64_sample"] = "config 4: 64 utterances x 215 frames, random texts of 20..80 tokens, speakers 0..4"
         out["decoder_b64_launches_per_step"] = s.last_loop_launches / frames
+        out["decoder_b64_roofline"] = step_roofline(m, B, m.hp["context_frames"], frames, 50, s.last_loop_ms * 1e-3 / frames)
         s.close()
     except Exception as e:  # noqa: BLE001
         out["decoder_b64_error"] = str(e)
@@ -274,6 +289,7 @@ def extra_measurements(binding, fixtures, m, args):
         s.teacher_forced(codes, want_hidden=False, want_logits=False)
         out["decoder_q8_long_b32_frames_per_s"] = B * frames / (s.last_loop_ms * 1e-3)
         out["decoder_q8_long_sample"] = "config 5 per-GPU share: Q8_0 GGUF (dequantised to bf16 at load), 32 utterances x 2600 frames"
+        out["decoder_q8_long_roofline"] = step_roofline(mq, B, mq.hp["context_frames"], frames, len(HELLO), s.last_loop_ms * 1e-3 / frames)
         s.close(); mq.close()
     except Exception as e:  # noqa: BLE001
         out["decoder_q8_long_error"] = str(e)
