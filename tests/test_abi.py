@@ -62,3 +62,17 @@ def test_product_never_imports_oracle():
                     if re.search(r"\boracle\b|magpie_oracle|libmagpie_oracle", txt):
                         bad.append(os.path.join(dp, fn))
     assert not bad, bad
+
+
+def test_every_environment_switch_is_documented():
+    """INTEGRATION.md section 4 lists every getenv() of the product sources (A/B switches must not be hidden behaviour)."""
+    import glob
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    names = set()
+    for f in glob.glob(os.path.join(root, "magpie_tts_cpp_b200", "csrc", "*.c*")):
+        names |= set(re.findall(r'getenv\("([A-Z0-9_]+)"\)', open(f).read()))
+    assert names, "no switches found: the scan is broken"
+    missing = sorted(n for n in names if n not in doc)
+    assert not missing, f"undocumented environment switches: {missing}"
