@@ -66,15 +66,29 @@ struct magpie_model {
     magpie_model_impl * impl = nullptr;
 };
 
+// reference src/magpie.h:237-259 without the ggml tensor members (the device cache is owned by the session behind
+// magpie_model_impl); the public scalars and reset() are kept
 struct magpie_kv_cache {
-    int max_seq = 0;          // context_frames + max_dec_steps + 16 (reference magpie.cpp:4077)
-    int seq_len = 0;
+    int32_t seq_len = 0;      // current sequence length
+    int32_t max_seq = 0;      // context_frames + max_dec_steps + 16 (reference magpie.cpp:4077)
+    int32_t enc_seq_len = 0;  // encoder sequence length (cross-attention)
+    void reset() { seq_len = 0; enc_seq_len = 0; }
 };
 
+// reference src/magpie.h:265-288 without the ggml allocator
 struct magpie_state {
-    std::vector<float> encoder_output;     // [enc_seq][d_model], filled by magpie_encode_text
-    int enc_seq_len = 0;
     magpie_kv_cache kv_cache;
+    std::vector<int32_t> generated_codes;  // [n_frames][num_codebooks] of the last synthesis call
+    int32_t n_generated_frames = 0;
+    std::vector<float> encoder_output;     // [enc_seq][d_model], filled by magpie_encode_text
+    int32_t enc_seq_len = 0;
+    void reset() {
+        kv_cache.reset();
+        generated_codes.clear();
+        n_generated_frames = 0;
+        encoder_output.clear();
+        enc_seq_len = 0;
+    }
 };
 
 struct magpie_codec;
@@ -112,6 +126,8 @@ MAGPIE_API std::vector<int32_t> magpie_synthesize_codes_graph_reuse(magpie_conte
 MAGPIE_API magpie_sample_result magpie_local_transformer_sample_all(magpie_context * ctx, const float * decoder_hidden,
                                                          float temperature, int top_k, bool forbid_eos = false);
 
+// reference signature (src/magpie.h:823, magpie.cpp:3273) and a pointer overload for callers that hold a raw frame
+MAGPIE_API bool magpie_is_eos(const std::vector<int32_t> & frame_codes, int32_t eos_id);
 MAGPIE_API bool magpie_is_eos(const int32_t * codes, int n_codebooks, int eos_id);
 
 // ---- streaming -------------------------------------------------------------------------------------

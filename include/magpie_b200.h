@@ -160,6 +160,27 @@ MGB_API int64_t mgb_session_last_loop_launches(const mgb_session * s);
  * megakernel took around every grid barrier of the last step (16 per layer + 2) */
 MGB_API int mgb_session_debug_stamps(mgb_session * s, uint64_t * out, int n);
 
+/* ---- in-process multi-GPU pool ---------------------------------------------------------------------
+ * The reference is single-device (src/magpie.cpp:14-67 picks ONE backend; magpie_synthesize_codes_graph_reuse,
+ * magpie.cpp:4063-4432, synthesises one utterance).  Independent utterances shard with no collective: a pool
+ * owns one model replica per device and, per call, one session + one submission thread (one stream) per device; utterance i
+ * runs on device mgb_shard_device(i, n_devices).  devices == NULL / n_devices <= 0 = all visible devices.  No NCCL.
+ *   tokens [n_utt][max_text] (padded), n_tokens [n_utt], speakers [n_utt] or NULL (= 0)
+ *   mgb_pool_generate:       codes_out [n_utt][max_steps][8], n_frames_out [n_utt]   (as mgb_generate, per utterance)
+ *   mgb_pool_teacher_forced: codes_in [n_utt][T][8] -> greedy_out [n_utt][T][8] (optional)
+ *   device_ms_out (optional) [n_devices]: device time of each device's loop (CUDA events on its stream) */
+typedef struct mgb_pool mgb_pool;
+MGB_API mgb_pool *  mgb_pool_new(const char * gguf_path, const int * devices, int n_devices, int precision);
+MGB_API void        mgb_pool_free(mgb_pool * p);
+MGB_API int         mgb_pool_n_devices(const mgb_pool * p);
+MGB_API mgb_model * mgb_pool_model(mgb_pool * p, int i);          /* replica i (borrowed) */
+MGB_API int mgb_pool_generate(mgb_pool * p, int n_utt, const int32_t * tokens, const int32_t * n_tokens, int max_text,
+                              const int32_t * speakers, int max_steps, float temperature, int top_k, uint64_t seed, int ignore_eos,
+                              int32_t * codes_out, int32_t * n_frames_out, float * device_ms_out);
+MGB_API int mgb_pool_teacher_forced(mgb_pool * p, int n_utt, const int32_t * tokens, const int32_t * n_tokens, int max_text,
+                                    const int32_t * speakers, const int32_t * codes_in, int T, int32_t * greedy_out,
+                                    float * device_ms_out);
+
 /* ---- nano-codec ----------------------------------------------------------------------------
  * magpie_codec_init / _free (src/nano-codec.cpp:339-374, 205-333) and magpie_codec_decode
  * (nano-codec.cpp:758-845) incl. fsq_dequantize_cpu (nano-codec.cpp:721-752). */

@@ -42,6 +42,7 @@ SYMBOLS = [
     "mgb_encode_text", "mgb_prefill", "mgb_decoder_step", "mgb_final_proj", "mgb_lt_sample",
     "mgb_generate", "mgb_teacher_forced", "mgb_session_last_loop_ms", "mgb_session_last_loop_launches",
     "mgb_session_debug_stamps",
+    "mgb_pool_new", "mgb_pool_free", "mgb_pool_n_devices", "mgb_pool_model", "mgb_pool_generate", "mgb_pool_teacher_forced",
     "mgb_codec_load", "mgb_codec_free", "mgb_codec_get_hparams", "mgb_codec_decode",
     "mgb_codec_fsq_dequantize", "mgb_codec_last_ms", "mgb_codec_last_launches",
 ]
@@ -105,6 +106,14 @@ def lib():
     L.mgb_session_last_loop_launches.restype = C.c_int64
     L.mgb_session_last_loop_launches.argtypes = [vp]
     L.mgb_session_debug_stamps.argtypes = [vp, vp, C.c_int]
+    L.mgb_pool_new.restype = vp
+    L.mgb_pool_new.argtypes = [cp, vp, C.c_int, C.c_int]
+    L.mgb_pool_free.argtypes = [vp]
+    L.mgb_pool_n_devices.argtypes = [vp]
+    L.mgb_pool_model.restype = vp
+    L.mgb_pool_model.argtypes = [vp, C.c_int]
+    L.mgb_pool_generate.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp, C.c_int, C.c_float, C.c_int, C.c_uint64, C.c_int, vp, vp, vp]
+    L.mgb_pool_teacher_forced.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp, vp, C.c_int, vp, vp]
     L.mgb_codec_load.restype = vp
     L.mgb_codec_load.argtypes = [cp, C.c_int]
     L.mgb_codec_free.argtypes = [vp]
@@ -311,6 +320,63 @@ class Session:
     @property
     def last_loop_launches(self) -> int:
         return int(lib().mgb_session_last_loop_launches(self._h))
+
+
+class Pool:
+    """In-process multi-GPU synthesis (mgb_pool_*): one replica + one submission thread per device, utterance i on device
+    i mod G, no collective.  The C++ side owns the threads; this is only the ctypes mirror."""
+
+    def __init__(self, gguf_path: str, devices=None, precision: int = PREC_BF16):
+        dv = _i32(devices) if devices is not None else None
+        self._h = lib().mgb_pool_new(os.fsencode(gguf_path), _p(dv), 0 if dv is None else len(dv), int(precision))
+        if not self._h:
+            raise _err("mgb_pool_new")
+        self.n_devices = int(lib().mgb_pool_n_devices(self._h))
+        hp = HParams()
+        _chk(lib().mgb_model_get_hparams(lib().mgb_pool_model(self._h, 0), C.byref(hp)), "hparams")
+        self.hp = {k: getattr(hp, k) for k in HP_FIELDS}
+        self.last_device_ms = np.zeros(self.n_devices, np.float32)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().mgb_pool_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def _pad(token_lists):
+        mt = max(len(t) for t in token_lists)
+        tok = np.zeros((len(token_lists), mt), np.int32)
+        n = np.zeros(len(token_lists), np.int32)
+        for i, t in enumerate(token_lists):
+            tok[i, :len(t)] = t
+            n[i] = len(t)
+        return tok, n, mt
+
+    def generate(self, token_lists, speakers=None, max_steps=0, temperature=0.0, top_k=80, seed=0, ignore_eos=False):
+        tok, n, mt = self._pad(token_lists)
+        T = max_steps if max_steps > 0 else self.hp["max_dec_steps"]
+        spk = _i32(speakers) if speakers is not None else None
+        codes = np.zeros((len(token_lists), T, 8), np.int32)
+        nf = np.zeros(len(token_lists), np.int32)
+        _chk(lib().mgb_pool_generate(self._h, len(token_lists), _p(tok), _p(n), mt, _p(spk), int(T), float(temperature), int(top_k),
+                                     C.c_uint64(seed), int(ignore_eos), _p(codes), _p(nf), _p(self.last_device_ms)), "mgb_pool_generate")
+        return [codes[i, :nf[i]].copy() for i in range(len(token_lists))]
+
+    def teacher_forced(self, token_lists, codes_in, speakers=None, want_greedy=True):
+        tok, n, mt = self._pad(token_lists)
+        c = _i32(codes_in)
+        assert c.ndim == 3 and c.shape[0] == len(token_lists) and c.shape[2] == 8
+        spk = _i32(speakers) if speakers is not None else None
+        gr = np.zeros_like(c) if want_greedy else None
+        _chk(lib().mgb_pool_teacher_forced(self._h, len(token_lists), _p(tok), _p(n), mt, _p(spk), _p(c), int(c.shape[1]), _p(gr),
+                                           _p(self.last_device_ms)), "mgb_pool_teacher_forced")
+        return gr
 
 
 class Codec:

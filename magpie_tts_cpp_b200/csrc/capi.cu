@@ -4,7 +4,9 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <memory>
+#include <string>
 #include <vector>
 
 #include "../../include/magpie_b200.h"
@@ -59,7 +61,7 @@ struct Session {
     unsigned long long * d_dbg = nullptr;
     // batch-1 bf16 persistent frame-loop kernel (frame_loop.cu)
     int loop_grid = 0; uint4 * d_xbuf = nullptr; int xoff[X_COUNT + 1] = {}; unsigned * d_seq = nullptr;
-    int32_t * d_result = nullptr; float * d_xm = nullptr, * d_xn = nullptr; int loop_E = 0; bool loop_tables = false;
+    int32_t * d_result = nullptr; float * d_xm = nullptr, * d_xn = nullptr; int loop_E = 0, loop_cap = 0; bool loop_tables = false;
     unsigned long long * d_loop_dbg = nullptr;
     void * tc_scratch = nullptr; size_t tc_scratch_bytes = 0;     // tensor-core path: activation tile images
     void * tc_scratch2 = nullptr;                                  // second image buffer (FF1 epilogue -> FF2 input)
@@ -239,7 +241,9 @@ int mgb_device_count(void) {
 
 mgb_model * mgb_model_load(const char * path, int device, int precision) {
     if (!path) { set_error("null path"); return nullptr; }
-    return reinterpret_cast<mgb_model *>(load_model(path, device, precision));
+    try { return reinterpret_cast<mgb_model *>(load_model(path, device, precision)); }      // no exception may cross the C ABI
+    catch (const std::exception & e) { set_error(std::string("magpie_init: ") + e.what()); return nullptr; }
+    catch (...) { set_error("magpie_init: unknown failure"); return nullptr; }
 }
 void mgb_model_free(mgb_model * m) { delete reinterpret_cast<Model *>(m); }
 int mgb_model_get_hparams(const mgb_model * m, mgb_hparams * out) {
@@ -313,7 +317,9 @@ mgb_session * mgb_session_new(mgb_model * mm, int batch, int max_text, int max_s
         if (!s->alloc(tp2, tb)) return nullptr;
         s->tc_scratch2 = tp2;
     }
-    if (m->precision == MGB_PREC_BF16 && batch >= 2 && dxa == 128 && getenv("MGB_NO_XFOLD") == nullptr &&
+    // (launch_xattn_folded holds one score per text position in shared memory: up to 512 positions; longer text capacities keep
+    //  the q GEMM + attention + o GEMM kernels)
+    if (m->precision == MGB_PREC_BF16 && batch >= 2 && dxa == 128 && max_text <= 512 && getenv("MGB_NO_XFOLD") == nullptr &&
         (size_t)L * batch * max_text * d * 8 <= ((size_t)8 << 30)) {
         const size_t tab = (size_t)L * batch * max_text * d;
         if (!s->alloc(s->fold_xm, tab) || !s->alloc(s->fold_xn, tab)) return nullptr;
@@ -344,7 +350,8 @@ mgb_session * mgb_session_new(mgb_model * mm, int batch, int max_text, int max_s
             frame_loop_xchg_layout(hp.vocab_per_cb, s->xoff);
             const size_t xb = frame_loop_xchg_bytes(s->xoff);
             char * xp = nullptr;
-            const size_t tab = (size_t)L * kLoopMaxCtx * d;
+            s->loop_cap = std::min(max_text, kLoopMaxCtx);
+            const size_t tab = (size_t)L * s->loop_cap * d;
             if (!s->alloc(xp, xb) || !s->alloc(s->d_seq, 1) || !s->alloc(s->d_result, 16) || !s->alloc(s->d_xm, tab) || !s->alloc(s->d_xn, tab) ||
                 (getenv("MGB_LOOP_DBG") != nullptr && !s->alloc(s->d_loop_dbg, kLoopDbgStamps))) return nullptr;
             s->d_xbuf = (uint4 *)xp;
@@ -476,12 +483,12 @@ int mgb_prefill(mgb_session * ss, const int32_t * speakers) {
     }
     // persistent loop kernel: fold q_net / o_net into per-token tables (frame_loop.cu)
     s->loop_tables = false;
-    if (s->loop_grid > 0 && s->h_ntext[0] <= kLoopMaxCtx) {
+    if (s->loop_grid > 0 && s->h_ntext[0] <= s->loop_cap) {
         s->loop_E = s->h_ntext[0];
         for (int l = 0; l < hp.dec_layers; l++) {
             const DecLayer & L = m.dec[l];
             if (!launch_xattn_fold((char *)s->xk + l * xkv_layer, (char *)s->xv + l * xkv_layer, L.xq.w, L.xo.w, s->loop_E, d, dxa,
-                                   1.0f / sqrtf((float)dxa), s->d_xm + (size_t)l * kLoopMaxCtx * d, s->d_xn + (size_t)l * kLoopMaxCtx * d, st)) return MGB_ECUDA;
+                                   1.0f / sqrtf((float)dxa), s->d_xm + (size_t)l * s->loop_cap * d, s->d_xn + (size_t)l * s->loop_cap * d, st)) return MGB_ECUDA;
         }
         s->loop_tables = true;
     }
@@ -551,6 +558,7 @@ int mgb_final_proj(mgb_session * ss, const float * hidden, float * logits_out) {
     if (!check_ready(s, false) || !logits_out) return MGB_EINVAL;
     Model & m = *s->m; const mgb_hparams & hp = m.hp;
     const int N = hp.num_codebooks * hp.vocab_per_cb, d = hp.d_model;
+    if (!m.final_w.w || !m.final_b) { set_error("mgb_final_proj: the model file has no final_proj.weight / final_proj.bias"); return MGB_EINVAL; }
     cudaStream_t st = s->stream;
     const float * hsrc = s->hidden;
     if (hidden) {
@@ -632,7 +640,7 @@ static int run_loop_persistent(Session & s, const LoopCfg & c, int * steps_run) 
     Model & m = *s.m; const mgb_hparams & hp = m.hp;
     cudaStream_t st = s.stream;
     FrameLoopParams p = {};
-    const size_t tab = (size_t)kLoopMaxCtx * hp.d_model;
+    const size_t tab = (size_t)s.loop_cap * hp.d_model;
     for (int l = 0; l < hp.dec_layers; l++) {
         const DecLayer & L = m.dec[l];
         p.layer[l] = LoopLayer{L.qkv.w, L.o.w, L.ff1.w, L.ff2.w, L.norm_self, L.norm_xa_q, L.norm_ff, s.d_xm + l * tab, s.d_xn + l * tab};
@@ -656,6 +664,7 @@ static int run_loop_persistent(Session & s, const LoopCfg & c, int * steps_run) 
     p.hidden_hist = c.want_hidden ? s.l_hidden : nullptr; p.hidden_last = s.hidden;
     p.result = s.d_result; p.xbuf = s.d_xbuf; memcpy(p.xoff, s.xoff, sizeof(p.xoff)); p.seq = s.d_seq; p.dbg = s.d_loop_dbg;
     p.dbg_flags = getenv("MGB_LOOP_FLAGS") ? atoi(getenv("MGB_LOOP_FLAGS")) : 0;
+    p.max_split = getenv("MGB_LOOP_MAXSPLIT") ? std::max(1, std::min(6, atoi(getenv("MGB_LOOP_MAXSPLIT")))) : 6;
     const int64_t l0 = g_launch_counter;
     cudaEventRecord(s.ev0, st);
     if (!launch_frame_loop(p, s.loop_grid, st)) return MGB_ECUDA;
@@ -683,8 +692,9 @@ static int run_loop(Session & s, const LoopCfg & c, int * steps_run) {
     cudaStream_t st = s.stream;
     const int B = s.B;
     if (s.pos + c.T > s.max_seq) { set_error("generation loop: KV cache too small for the requested steps"); return MGB_ERANGE; }
-    // (the persistent kernel scans at most 6 key splits x 480 cached keys per attention item)
-    if (s.loop_grid > 0 && s.loop_tables && s.pos + c.T <= 2880) return run_loop_persistent(s, c, steps_run);
+    // (the persistent kernel divides the cached keys over up to 6 CTAs per head; each warp scans 32-key chunks, the first
+    //  480 keys of an item before the wait for q, longer items in further rounds)
+    if (s.loop_grid > 0 && s.loop_tables) return run_loop_persistent(s, c, steps_run);
     // the iteration is captured once, so the key split of the self-attention is planned for the KV length the loop will reach
     s.attn_split = attention_plan_kv_split(s.m->hp.dec_sa_heads * B, s.pos + c.T);
     std::vector<int32_t> neg(B, -1);
@@ -810,7 +820,9 @@ int mgb_teacher_forced(mgb_session * ss, const int32_t * codes_in, int T, float 
 // ---- codec ------------------------------------------------------------------------------------------
 mgb_codec * mgb_codec_load(const char * path, int device) {
     if (!path) { set_error("null path"); return nullptr; }
-    return reinterpret_cast<mgb_codec *>(load_codec(path, device));
+    try { return reinterpret_cast<mgb_codec *>(load_codec(path, device)); }
+    catch (const std::exception & e) { set_error(std::string("magpie_codec_init: ") + e.what()); return nullptr; }
+    catch (...) { set_error("magpie_codec_init: unknown failure"); return nullptr; }
 }
 void mgb_codec_free(mgb_codec * c) { delete reinterpret_cast<Codec *>(c); }
 int mgb_codec_get_hparams(const mgb_codec * c, mgb_codec_hparams * out) {

@@ -670,11 +670,11 @@ bool pack_weights(const float * w, const Geom & g, int K, void * img, cudaStream
 }
 
 bool launch_conv(const Geom & g, const ConvArgs & a, cudaStream_t stream) {
-    static int n_sm[64] = {};
-    static uint64_t attr_done = 0;
+    static std::atomic<int> n_sm[64];
+    static DeviceOnce attr_done;
     int dev = 0;
     MGB_CUDA_TRY(cudaGetDevice(&dev));
-    if (!n_sm[dev]) MGB_CUDA_TRY(cudaDeviceGetAttribute(&n_sm[dev], cudaDevAttrMultiProcessorCount, dev));
+    if (!n_sm[dev & 63]) { int n = 0; MGB_CUDA_TRY(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev)); n_sm[dev & 63] = n; }
     KParams p = {};
     p.a = a;
     p.C = g.C; p.nsplit = g.nsplit; p.nper = g.nper; p.npad = g.npad; p.nchunk = g.nchunk; p.cs = row_stride(g.C);
@@ -700,14 +700,14 @@ bool launch_conv(const Geom & g, const ConvArgs & a, cudaStream_t stream) {
     p.rows = (long long)act_rows(a.T);
     const size_t smem = 1024 + (size_t)p.NA * p.abuf_bytes + (size_t)p.NW * p.wstage_bytes + 512;
     if (smem > (size_t)kDynSmemMax) { set_error("codec: conv tile configuration exceeds shared memory"); return false; }
-    if (!(attr_done >> dev & 1)) {
+    if (!attr_done.done(dev)) {
         MGB_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmemMax));
         MGB_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmemMax));
         MGB_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmemMax));
-        attr_done |= 1ull << dev;
+        attr_done.set(dev);
     }
     if (g.C > kMaxC) { set_error("codec: too many channels for the tensor-core path"); return false; }
-    const int grid = std::min(p.n_tiles, n_sm[dev]);
+    const int grid = std::min(p.n_tiles, n_sm[dev & 63].load());
     const int mode = a.res ? (a.ya ? 1 : 2) : 0;
     if (mode == 0 && !a.ya) { set_error("codec: conv without an output"); return false; }
     if (mode == 1 && (!a.y || !a.ya)) { set_error("codec: residual conv needs y and ya"); return false; }

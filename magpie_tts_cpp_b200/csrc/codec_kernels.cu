@@ -206,10 +206,10 @@ __global__ void post_kernel(const PostParams p) {
 
 
 bool ensure_consts() {
-    static uint64_t done = 0;
+    static DeviceOnce done;
     int dev = 0;
     MGB_CUDA_TRY(cudaGetDevice(&dev));
-    if (done >> dev & 1) return true;
+    if (done.done(dev)) return true;
     float lut[4][8] = {};
     for (int d = 0; d < 4; d++) {
         const int half = h_fsq_levels[d] / 2;
@@ -218,7 +218,10 @@ bool ensure_consts() {
     MGB_CUDA_TRY(cudaMemcpyToSymbol(c_fsq_lut, lut, sizeof(lut)));
     MGB_CUDA_TRY(cudaMemcpyToSymbol(c_fsq_base, h_fsq_base, sizeof(h_fsq_base)));
     MGB_CUDA_TRY(cudaMemcpyToSymbol(c_fsq_levels, h_fsq_levels, sizeof(h_fsq_levels)));
-    done |= 1ull << dev;
+    // the codec kernels run on a non-blocking stream, which the legacy-stream copies above do not order against:
+    // wait until the constants have landed before the first launch may read them
+    MGB_CUDA_TRY(cudaDeviceSynchronize());
+    done.set(dev);
     return true;
 }
 

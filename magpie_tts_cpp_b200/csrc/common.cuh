@@ -3,6 +3,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <string>
@@ -31,6 +32,15 @@ extern thread_local int64_t g_launch_counter;      // kernels launched by this t
             return false;                                                                       \
         }                                                                                       \
     } while (0)
+
+// Per-device "done once" flags for lazily set function attributes / uploaded constants.  Several host threads (one per GPU,
+// sharding.py / mgb_pool) go through the launch wrappers concurrently: the bits are atomic so no device's flag is lost; two
+// threads racing on the same device merely repeat an idempotent call.
+struct DeviceOnce {
+    std::atomic<uint64_t> bits{0};
+    bool done(int dev) const { return (bits.load(std::memory_order_acquire) >> (dev & 63)) & 1u; }
+    void set(int dev) { bits.fetch_or(1ull << (dev & 63), std::memory_order_release); }
+};
 
 constexpr int kWarp = 32;
 

@@ -492,13 +492,13 @@ size_t mega_smem_bytes() { return sizeof(MegaSmem) + 128; }
 bool launch_decoder_mega(const MegaParams & p, int precision, int grid, cudaStream_t stream) {
     const size_t smem = mega_smem_bytes();
     void * kfn = precision == MGB_PREC_F32 ? (void *)decoder_mega_kernel<float> : (void *)decoder_mega_kernel<__nv_bfloat16>;
-    static uint64_t attr_done[2] = {0, 0};
+    static DeviceOnce attr_done[2];
     int dev = 0;
     MGB_CUDA_TRY(cudaGetDevice(&dev));
     const int pi = precision == MGB_PREC_F32 ? 0 : 1;
-    if (!(attr_done[pi] >> dev & 1)) {
+    if (!attr_done[pi].done(dev)) {
         MGB_CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done[pi] |= 1ull << dev;
+        attr_done[pi].set(dev);
     }
     MGB_CUDA_TRY(cudaMemsetAsync(p.barrier, 0, sizeof(unsigned), stream));
     MegaParams pc = p;

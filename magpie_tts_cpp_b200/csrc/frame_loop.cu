@@ -17,7 +17,7 @@
 //     slices); consumers spin on the packets themselves with volatile vector loads.  One L2 round trip per
 //     exchange, no fences, no atomics; buffers are reused only after two later all-to-all exchanges, which
 //     makes the reuse race-free.
-//   * cross-attention (1 head over E <= 30 text tokens) is folded at prefill: M_l = scale K_l Wq_l and
+//   * cross-attention (1 head over E <= kLoopMaxCtx text tokens) is folded at prefill: M_l = scale K_l Wq_l and
 //     N_l = V_l Wo_l^T, so that scores = M_l LN(x) and the output projection = softmax(scores) N_l; this
 //     removes one exchange per layer (the reference's q_net / o_net GEMVs become part of the tables).
 //   * the local transformer runs on all CTAs from shared memory; argmax is a 135-packet exchange, top-k
@@ -512,10 +512,11 @@ __device__ __forceinline__ void attention_item(LoopSmem & S, const FrameLoopPara
     const unsigned flag = c.seq - 1;
     const bool has_new = pos >= k0 && pos < k1;
     const int ke = has_new ? k1 - 1 : k1;                       // old keys [k0, ke); pos == k1 - 1 when has_new
-    const int nw = min(kCW, (ke - k0 + 31) / 32);                // warps holding a chunk (one chunk per warp: per <= 480)
-    // 1. old keys: this warp's chunk of 32 keys; loads in flight while q is awaited
-    const int c0 = k0 + cw * 32, j = c0 + lane;
-    const int cnt = max(0, min(32, ke - c0));
+    const int nch = (ke - k0 + 31) / 32;                         // 32-key chunks of this item; warp cw scans chunks cw, cw + 15, ...
+    const int nw = min(kCW, nch);                                // warps holding a partial
+    // 1. old keys: this warp's FIRST chunk of 32 keys; loads in flight while q is awaited
+    int c0 = k0 + cw * 32, j = c0 + lane;
+    int cnt = max(0, min(32, ke - c0));
     uint4 kv[8];
     uint32_t vraw[32];
     if (j < ke) {
@@ -556,7 +557,18 @@ __device__ __forceinline__ void attention_item(LoopSmem & S, const FrameLoopPara
     cbar();
     LOOP_STAMP();
     float mx = -INFINITY, lsum = 0.0f, acc0 = 0.0f, acc1 = 0.0f;       // lane owns dims 2*lane, 2*lane+1
-    if (cw < nw) {
+    for (int cc = cw; cc < nch; cc += kCW) {
+        if (cc != cw) {                 // items longer than 480 keys (KV beyond 2 880): further chunks, loaded after the wait
+            c0 = k0 + cc * 32; j = c0 + lane; cnt = max(0, min(32, ke - c0));
+            if (j < ke) {
+                const bf * kr = kcl + (size_t)j * D + h * DH;
+#pragma unroll
+                for (int q = 0; q < 8; q++) kv[q] = __ldcg(reinterpret_cast<const uint4 *>(kr) + q);
+            }
+            const bf * vbase = vcl + (size_t)c0 * D + h * DH + lane * 2;
+#pragma unroll
+            for (int jj = 0; jj < 32; jj++) vraw[jj] = jj < cnt ? __ldcg(reinterpret_cast<const uint32_t *>(vbase + (size_t)jj * D)) : 0u;
+        }
         float s = -INFINITY;
         if (j < ke) {
             float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f, d3 = 0.0f;
@@ -570,9 +582,9 @@ __device__ __forceinline__ void attention_item(LoopSmem & S, const FrameLoopPara
             }
             s = ((d0 + d1) + (d2 + d3)) * 0.125f;                     // 1/sqrt(64)
         }
-        mx = warp_max(s);
-        const float pj = (j < ke) ? expf(s - mx) : 0.0f;
-        lsum = warp_sum(pj);
+        const float cmx = warp_max(s);
+        const float pj = (j < ke) ? expf(s - cmx) : 0.0f;
+        const float cl = warp_sum(pj);
         float a0 = 0.0f, a1 = 0.0f, b0 = 0.0f, b1 = 0.0f;
 #pragma unroll
         for (int jj = 0; jj < 32; jj += 2) {
@@ -580,7 +592,14 @@ __device__ __forceinline__ void attention_item(LoopSmem & S, const FrameLoopPara
             a0 = fmaf(pa, bf16lo(vraw[jj]), a0); a1 = fmaf(pa, bf16hi(vraw[jj]), a1);
             b0 = fmaf(pb, bf16lo(vraw[jj + 1]), b0); b1 = fmaf(pb, bf16hi(vraw[jj + 1]), b1);
         }
-        acc0 = a0 + b0; acc1 = a1 + b1;
+        if (cc == cw) { mx = cmx; lsum = cl; acc0 = a0 + b0; acc1 = a1 + b1; }
+        else {                          // online-softmax merge of this chunk into the warp's running partial
+            const float mnew = fmaxf(mx, cmx);
+            const float fo = expf(mx - mnew), fn = expf(cmx - mnew);
+            lsum = lsum * fo + cl * fn;
+            acc0 = acc0 * fo + (a0 + b0) * fn; acc1 = acc1 * fo + (a1 + b1) * fn;
+            mx = mnew;
+        }
     }
     if (has_new && cw == nw % kCW) {          // the new key: one more online-softmax update on a warp of its own if there is one
         const float s = warp_sum(fmaf(S.knew[lane], S.qh[lane], S.knew[lane + 32] * S.qh[lane + 32])) * 0.125f;
@@ -637,41 +656,63 @@ __device__ __forceinline__ void attention_combine(LoopSmem & S, const FrameLoopP
 }
 
 // ---- folded cross-attention: x += softmax(M_l LN(x)) N_l  (rows of this CTA) -----------------------------------------------
+// Text tokens are handled 30 at a time (two table rows per warp).  The first 30 rows are activation independent and are
+// fetched BEFORE the wait for x (all of a "Hello, world!"-sized text); longer texts (up to kLoopMaxCtx tokens) stream the
+// remaining rows from L2 after it, 2 x 3 KB per warp and round.
+constexpr int kScOff = 1024;             // scores live in S.vec[kScOff .. kScOff + kLoopMaxCtx) (LN(x) occupies [0, D))
 __device__ __forceinline__ void cross_attention(LoopSmem & S, const FrameLoopParams & p, Ctx & c, const LoopLayer & Ly) {
     const int cw = c.cw, lane = c.lane, E = p.E;
+    float * sc = S.vec + kScOff;
     float w3[3], v[3];
     ln_weights3<D>(Ly.n_xq, c.ctid, w3);
     const int r0 = c.b * RO, nr = max(0, min(RO, D - r0));
-    // the tables are activation independent: fetch this warp's rows before waiting for x
-    const int j0 = cw, j1 = cw + kCW;
+    // the tables are activation independent: fetch this warp's first rows before waiting for x
     float4 m0[6], m1[6];
+    {
+        const int j0 = cw, j1 = cw + kCW;
 #pragma unroll
-    for (int q = 0; q < 6; q++) {
-        m0[q] = j0 < E ? __ldg(reinterpret_cast<const float4 *>(Ly.xm + (size_t)j0 * D + q * 128 + lane * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        m1[q] = j1 < E ? __ldg(reinterpret_cast<const float4 *>(Ly.xm + (size_t)j1 * D + q * 128 + lane * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int q = 0; q < 6; q++) {
+            m0[q] = j0 < E ? __ldg(reinterpret_cast<const float4 *>(Ly.xm + (size_t)j0 * D + q * 128 + lane * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            m1[q] = j1 < E ? __ldg(reinterpret_cast<const float4 *>(Ly.xm + (size_t)j1 * D + q * 128 + lane * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
     }
     float nval = 0.0f;
     if (cw < nr && lane < E) nval = __ldg(Ly.xn + (size_t)lane * D + r0 + cw);
     load3_poll<D>(c.xin + p.xoff[X_XA], c.seq - 1, S.xs, c.ctid, v);
     LOOP_STAMP();
     ln3<D>(S, v, w3, S.vec, p.eps, c);
-    float d0 = 0.0f, d1 = 0.0f;
+    for (int jb = 0; jb < E; jb += 2 * kCW) {
+        const int j0 = jb + cw, j1 = jb + cw + kCW;
+        if (jb > 0) {
 #pragma unroll
-    for (int q = 0; q < 6; q++) {
-        const float4 xv = *reinterpret_cast<const float4 *>(S.vec + q * 128 + lane * 4);
-        d0 = fmaf(m0[q].x, xv.x, d0); d0 = fmaf(m0[q].y, xv.y, d0); d0 = fmaf(m0[q].z, xv.z, d0); d0 = fmaf(m0[q].w, xv.w, d0);
-        d1 = fmaf(m1[q].x, xv.x, d1); d1 = fmaf(m1[q].y, xv.y, d1); d1 = fmaf(m1[q].z, xv.z, d1); d1 = fmaf(m1[q].w, xv.w, d1);
+            for (int q = 0; q < 6; q++) {
+                m0[q] = j0 < E ? __ldg(reinterpret_cast<const float4 *>(Ly.xm + (size_t)j0 * D + q * 128 + lane * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                m1[q] = j1 < E ? __ldg(reinterpret_cast<const float4 *>(Ly.xm + (size_t)j1 * D + q * 128 + lane * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        float d0 = 0.0f, d1 = 0.0f;
+#pragma unroll
+        for (int q = 0; q < 6; q++) {
+            const float4 xv = *reinterpret_cast<const float4 *>(S.vec + q * 128 + lane * 4);
+            d0 = fmaf(m0[q].x, xv.x, d0); d0 = fmaf(m0[q].y, xv.y, d0); d0 = fmaf(m0[q].z, xv.z, d0); d0 = fmaf(m0[q].w, xv.w, d0);
+            d1 = fmaf(m1[q].x, xv.x, d1); d1 = fmaf(m1[q].y, xv.y, d1); d1 = fmaf(m1[q].z, xv.z, d1); d1 = fmaf(m1[q].w, xv.w, d1);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { d0 += __shfl_xor_sync(0xffffffffu, d0, o); d1 += __shfl_xor_sync(0xffffffffu, d1, o); }
+        if (lane == 0) { if (j0 < E) sc[j0] = d0; if (j1 < E) sc[j1] = d1; }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { d0 += __shfl_xor_sync(0xffffffffu, d0, o); d1 += __shfl_xor_sync(0xffffffffu, d1, o); }
-    if (lane == 0) { if (j0 < E) S.sc[j0] = d0; if (j1 < E) S.sc[j1] = d1; }
     cbar();
     // softmax over the E tokens and this CTA's output rows: warp r < nr computes row r, warp 0 emits
     if (cw < nr) {
-        const float sj = lane < E ? S.sc[lane] : -INFINITY;
-        const float mxs = warp_max(sj);
-        const float e = lane < E ? expf(sj - mxs) : 0.0f;
-        float sum = e, o = e * nval;
+        float mxs = -INFINITY;
+        for (int j = lane; j < E; j += 32) mxs = fmaxf(mxs, sc[j]);
+        mxs = warp_max(mxs);
+        float sum = 0.0f, o = 0.0f;
+        for (int j = lane; j < E; j += 32) {
+            const float e = expf(sc[j] - mxs);
+            const float nv = j < 32 ? nval : __ldg(Ly.xn + (size_t)j * D + r0 + cw);
+            sum += e; o = fmaf(e, nv, o);
+        }
 #pragma unroll
         for (int of = 16; of > 0; of >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, of); o += __shfl_xor_sync(0xffffffffu, o, of); }
         if (lane == 0) S.outv[cw] = o * (1.0f / sum) + S.xs[r0 + cw];
@@ -745,7 +786,7 @@ __global__ void __launch_bounds__(kThreads, 1) frame_loop_kernel(const FrameLoop
             for (int q = 0; q < 3; q++) pe[q] = __ldg(p.dec_pos + (size_t)(pos + 1) * D + 3 * ctid + q);
         }
 
-        const int S_split = min(kMaxSplit, max(1, (nk + 127) / 128));
+        const int S_split = min(p.max_split, max(1, (nk + 127) / 128));
 #pragma unroll 1
         for (int l = 0; l < L; l++) {
             const LoopLayer & Ly = p.layer[l];

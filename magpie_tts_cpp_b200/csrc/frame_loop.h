@@ -7,7 +7,7 @@
 namespace mgb {
 
 constexpr int kLoopMaxLayers = 16;
-constexpr int kLoopMaxCtx = 30;          // text tokens the folded cross-attention path handles
+constexpr int kLoopMaxCtx = 512;         // text tokens the folded cross-attention path handles (the first 30 from registers, the rest streamed)
 constexpr int kLoopDbgPerCta = 256;      // globaltimer stamps per CTA (last frame of a launch)
 constexpr int kLoopDbgStamps = 160 * kLoopDbgPerCta;
 
@@ -50,6 +50,7 @@ struct FrameLoopParams {
     unsigned * seq;                      // persistent exchange sequence number
     unsigned long long * dbg;            // optional: globaltimer stamps of CTA 0 for the last frame
     int dbg_flags;                       // profiling aids, see frame_loop.cu (0 in production)
+    int max_split;                       // key splits per head, 1..6 (6 in production; smaller values exercise the multi-round scan in tests)
 };
 
 bool   frame_loop_shape_ok(int d, int f, int H, int ld, int lf, int V, int L);

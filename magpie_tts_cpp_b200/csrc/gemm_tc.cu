@@ -198,15 +198,15 @@ __global__ void __launch_bounds__(tc::kThreads, 1) tc_linear_kernel(const bf * W
 }
 
 template <int MT, int SPLIT, int EPI> bool launch_tc(const bf * Wt, const bf * hi, const bf * lo, int KT, const TcEpi & e, cudaStream_t stream) {
-    static uint64_t attr_done = 0;
+    static DeviceOnce attr_done;
     int dev = 0;
     MGB_CUDA_TRY(cudaGetDevice(&dev));
     constexpr int SCAP = StageCap<SPLIT>::value;
     constexpr int smem = tc::Smem<MT, 2, SCAP>::kBytes + (SPLIT - 1) * MT * 128 * 4;
     static_assert(smem <= 227 * 1024, "tc_linear shared memory");
-    if (!(attr_done >> dev & 1)) {
+    if (!attr_done.done(dev)) {
         MGB_CUDA_TRY(cudaFuncSetAttribute(tc_linear_kernel<MT, SPLIT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_done |= 1ull << dev;
+        attr_done.set(dev);
     }
     // launched as a programmatic dependent of the activation-packing kernel: CTAs start (and prefetch weight tiles)
     // while pack_x_kernel is still running, and wait for it with griddepcontrol.wait before touching its output

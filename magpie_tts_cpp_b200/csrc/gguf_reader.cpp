@@ -1,6 +1,7 @@
 #include "gguf_reader.h"
 
 #include <cstring>
+#include <exception>
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
@@ -18,12 +19,12 @@ struct Cursor {
     const uint8_t * p; const uint8_t * end; bool ok = true;
     template <typename T> T rd() {
         T v{};
-        if (p + sizeof(T) > end) { ok = false; return v; }
+        if (!ok || (size_t)(end - p) < sizeof(T)) { ok = false; return v; }
         memcpy(&v, p, sizeof(T)); p += sizeof(T); return v;
     }
     std::string str() {
         uint64_t n = rd<uint64_t>();
-        if (!ok || p + n > end) { ok = false; return {}; }
+        if (!ok || n > (uint64_t)(end - p)) { ok = false; return {}; }      // remaining-size comparison: p + n cannot wrap
         std::string s((const char *)p, (size_t)n); p += n; return s;
     }
 };
@@ -59,7 +60,7 @@ bool read_value(Cursor & c, int32_t type, GgufValue & v) {
             if (et == T_STR) { for (uint64_t i = 0; i < n && c.ok; i++) c.str(); }
             else {
                 size_t es = scalar_size(et);
-                if (es == 0 || c.p + es * n > c.end) { c.ok = false; break; }
+                if (es == 0 || !c.ok || n > (uint64_t)(c.end - c.p) / es) { c.ok = false; break; }
                 c.p += es * n;
             }
             break;
@@ -87,6 +88,7 @@ float f16_to_f32(uint16_t h) {
 
 size_t GgufTensor::nbytes() const {
     int64_t n = nelements();
+    if (n < 0) return 0;
     switch (type) {
         case GGML_F32: return (size_t)n * 4;
         case GGML_F16: return (size_t)n * 2;
@@ -113,33 +115,47 @@ bool GgufFile::open(const char * path, std::string & err) {
     uint32_t version = c.rd<uint32_t>();
     if (version < 2 || version > 3) { err = "unsupported GGUF version"; return false; }
     uint64_t n_tensors = c.rd<uint64_t>(), n_kv = c.rd<uint64_t>();
-    uint32_t alignment = 32;
+    // every KV entry takes >= 12 bytes (key length + type), every tensor entry >= 24: counts beyond that are corrupt
+    if (!c.ok || n_kv > map_size_ / 12 || n_tensors > map_size_ / 24) { err = "corrupt GGUF header (entry counts exceed the file size)"; return false; }
+    uint64_t alignment = 32;
     for (uint64_t i = 0; i < n_kv && c.ok; i++) {
         std::string key = c.str();
         int32_t type = c.rd<int32_t>();
         GgufValue v;
         if (!read_value(c, type, v)) break;
-        if (key == "general.alignment" && v.type == T_U32) alignment = (uint32_t)v.u;
+        if (key == "general.alignment" && v.type == T_U32) alignment = v.u;
         kv_[key] = std::move(v);
     }
     if (!c.ok) { err = "truncated GGUF metadata"; return false; }
-    tensors_.resize((size_t)n_tensors);
+    if (alignment == 0 || (alignment & (alignment - 1)) != 0 || alignment > (1u << 20)) { err = "general.alignment must be a power of two"; return false; }
+    try { tensors_.resize((size_t)n_tensors); }
+    catch (const std::exception &) { err = "out of memory reading the tensor table"; return false; }
     for (auto & t : tensors_) {
         t.name = c.str();
         t.n_dims = (int)c.rd<uint32_t>();
         if (!c.ok || t.n_dims < 0 || t.n_dims > 4) { err = "bad tensor info"; return false; }
-        for (int d = 0; d < t.n_dims; d++) t.ne[d] = (int64_t)c.rd<uint64_t>();
+        int64_t total = 1;
+        for (int d = 0; d < t.n_dims; d++) {
+            const uint64_t ne = c.rd<uint64_t>();
+            // dimensions must be positive and the element count must stay far below 2^63 (no overflow in nelements / nbytes)
+            if (!c.ok || ne == 0 || ne > (uint64_t)1 << 40 || (uint64_t)total > ((uint64_t)1 << 44) / ne) { err = "tensor '" + t.name + "': bad dimensions"; return false; }
+            t.ne[d] = (int64_t)ne;
+            total *= (int64_t)ne;
+        }
         t.type = c.rd<int32_t>();
         t.offset = c.rd<uint64_t>();
+        if ((t.type == GGML_Q8_0 || t.type == GGML_Q4_0) && t.ne[0] % 32 != 0) { err = "tensor '" + t.name + "': quantised row length is not a multiple of 32"; return false; }
     }
     if (!c.ok) { err = "truncated GGUF tensor table"; return false; }
-    size_t pos = (size_t)(c.p - (const uint8_t *)map_);
-    size_t data_off = (pos + alignment - 1) / alignment * alignment;
+    const size_t pos = (size_t)(c.p - (const uint8_t *)map_);
+    const size_t data_off = (pos + alignment - 1) / alignment * alignment;
+    if (data_off > map_size_) { err = "GGUF data section starts past the end of the file"; return false; }
+    const size_t data_size = map_size_ - data_off;
     for (size_t i = 0; i < tensors_.size(); i++) {
         auto & t = tensors_[i];
-        size_t nb = t.nbytes();
+        const size_t nb = t.nbytes();
         if (nb == 0 && t.nelements() != 0) { err = "tensor '" + t.name + "': unsupported type"; return false; }
-        if (data_off + t.offset + nb > map_size_) { err = "tensor '" + t.name + "' runs past end of file"; return false; }
+        if (t.offset > data_size || nb > data_size - t.offset) { err = "tensor '" + t.name + "' runs past end of file"; return false; }
         t.data = (const uint8_t *)map_ + data_off + t.offset;
         index_[t.name] = i;
     }

@@ -334,18 +334,18 @@ bool lt_batch_supported(const Model & m, int B) {
 }
 
 bool launch_lt_batch(const Model & m, const LtParams & p, void * scratch, size_t scratch_bytes, cudaStream_t stream) {
-    static int n_sm[64] = {};
-    static uint64_t attr_done = 0;
+    static std::atomic<int> n_sm[64];
+    static DeviceOnce attr_done;
     int dev = 0;
     MGB_CUDA_TRY(cudaGetDevice(&dev));
-    if (!n_sm[dev & 63]) MGB_CUDA_TRY(cudaDeviceGetAttribute(&n_sm[dev & 63], cudaDevAttrMultiProcessorCount, dev));
+    if (!n_sm[dev & 63]) { int n = 0; MGB_CUDA_TRY(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev)); n_sm[dev & 63] = n; }
     const int G = n_sm[dev & 63];
     const size_t smem = (size_t)kTileFloats * 4 + slice_smem_bytes(m, G);
     if (smem > 227 * 1024) { set_error("lt_batch: weight slices do not fit shared memory"); return false; }
     if (scratch_bytes < lt_batch_scratch_bytes(m, p.B) || !scratch) { set_error("lt_batch: scratch too small"); return false; }
-    if (!(attr_done >> (dev & 63) & 1)) {
+    if (!attr_done.done(dev)) {
         MGB_CUDA_TRY(cudaFuncSetAttribute(lt_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_done |= 1ull << (dev & 63);
+        attr_done.set(dev);
     }
     BParams bp;
     bp.p = p;

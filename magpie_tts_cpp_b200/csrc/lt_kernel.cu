@@ -244,13 +244,13 @@ __global__ void __launch_bounds__(kLtThreads, 1) lt_kernel(const LtParams p) {
 template <typename T, int CS>
 bool launch_lt_t(const LtParams & p, cudaStream_t stream) {
     const size_t smem = sizeof(LtSmem);
-    static uint64_t attr_done = 0;
+    static DeviceOnce attr_done;
     int dev = 0;
     MGB_CUDA_TRY(cudaGetDevice(&dev));
-    if (!(attr_done >> dev & 1)) {
+    if (!attr_done.done(dev)) {
         MGB_CUDA_TRY(cudaFuncSetAttribute(lt_kernel<T, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         if (CS > 8) MGB_CUDA_TRY(cudaFuncSetAttribute(lt_kernel<T, CS>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-        attr_done |= 1ull << dev;
+        attr_done.set(dev);
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(p.B * CS); cfg.blockDim = dim3(kLtThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
@@ -288,11 +288,11 @@ bool launch_local_transformer(const Model & m, const LtArgs & a, cudaStream_t st
     // small batches, bf16: weights resident in shared memory (lt_resident.cu)
     if (lt_resident_supported(m, a.B)) return launch_lt_resident(p, stream);
     // 16-CTA (non-portable) clusters when the device can schedule them, else the portable 8
-    static int cs16[64] = {};
+    static std::atomic<int> cs16[64];
     int dev = 0;
     MGB_CUDA_TRY(cudaGetDevice(&dev));
-    if (cs16[dev & 63] == 0) {
-        cs16[dev & 63] = -1;
+    if (cs16[dev & 63] == 0) {          // probed once per device; the result is published only when the probe is complete
+        int verdict = -1;
         if (getenv("MGB_LT_CLUSTER8") == nullptr) {
             int ncl = 0;
             cudaLaunchConfig_t cfg = {};
@@ -305,8 +305,9 @@ bool launch_local_transformer(const Model & m, const LtArgs & a, cudaStream_t st
                       cudaFuncSetAttribute(lt_kernel<__nv_bfloat16, 16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
                       cudaOccupancyMaxActiveClusters(&ncl, lt_kernel<__nv_bfloat16, 16>, &cfg) == cudaSuccess && ncl >= 1;
             cudaGetLastError();
-            if (ok) cs16[dev & 63] = 1;
+            if (ok) verdict = 1;
         }
+        cs16[dev & 63] = verdict;
     }
     const bool big = cs16[dev & 63] == 1 && a.B <= 8;      // many utterances already fill the GPU with 8-CTA clusters
     if (m.precision == MGB_PREC_F32) return big ? launch_lt_t<float, 16>(p, stream) : launch_lt_t<float, 8>(p, stream);

@@ -271,11 +271,10 @@ bool lt_resident_supported(const Model & m, int B) {
     if (hp.lt_dim > kL || hp.lt_dim % 8 || hp.lt_ffn_dim > kF || hp.vocab_per_cb > kV || hp.d_model > kF) return false;
     if ((3 * hp.lt_dim + kCS - 1) / kCS > kQkvRows || (hp.lt_dim + kCS - 1) / kCS > kORows ||
         (hp.lt_ffn_dim + kCS - 1) / kCS > kF1Rows || (hp.vocab_per_cb + kCS - 1) / kCS > kOutRows) return false;
-    static int ok_dev[64] = {};
+    static std::atomic<int> ok_dev[64];
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return false;
-    if (ok_dev[dev & 63] == 0) {
-        ok_dev[dev & 63] = -1;
+    if (ok_dev[dev & 63] == 0) {        // probed once per device; the result is published only when the probe is complete
         int ncl = 0;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(kCS); cfg.blockDim = dim3(kLtThreads); cfg.dynamicSmemBytes = sizeof(LtResSmem);
@@ -287,7 +286,7 @@ bool lt_resident_supported(const Model & m, int B) {
                         cudaFuncSetAttribute(lt_resident_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
                         cudaOccupancyMaxActiveClusters(&ncl, lt_resident_kernel, &cfg) == cudaSuccess && ncl >= 1;
         cudaGetLastError();
-        if (ok) ok_dev[dev & 63] = 1;
+        ok_dev[dev & 63] = ok ? 1 : -1;
     }
     return ok_dev[dev & 63] == 1;
 }

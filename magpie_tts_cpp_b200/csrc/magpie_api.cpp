@@ -154,8 +154,10 @@ void copy_hparams(magpie_hparams & d, const mgb_hparams & s) {
 }
 
 int env_precision() {
-    const char * e = getenv("MAGPIE_PRECISION");        // "f32" (default: parity with the reference) or "bf16"
-    return (e && (!strcmp(e, "bf16") || !strcmp(e, "BF16"))) ? MGB_PREC_BF16 : MGB_PREC_F32;
+    // default bf16: the B200 production path (persistent frame-loop kernel at batch 1, tcgen05 GEMMs when batched);
+    // MAGPIE_PRECISION=f32 selects the f32 parity mode (1e-4 against the reference's f32 CPU arithmetic)
+    const char * e = getenv("MAGPIE_PRECISION");
+    return (e && (!strcmp(e, "f32") || !strcmp(e, "F32") || !strcmp(e, "fp32"))) ? MGB_PREC_F32 : MGB_PREC_BF16;
 }
 int env_device() { const char * e = getenv("MAGPIE_DEVICE"); return e ? atoi(e) : 0; }
 
@@ -176,6 +178,7 @@ mgb_session * start_utterance(magpie_context * ctx, const int32_t * tokens, int 
         return nullptr;
     }
     ctx->state.enc_seq_len = n_tokens;
+    ctx->state.kv_cache.enc_seq_len = n_tokens;
     ctx->state.kv_cache.max_seq = max_seq;
     ctx->state.kv_cache.seq_len = hp.context_frames;
     return s;
@@ -196,6 +199,8 @@ std::vector<int32_t> synthesize(magpie_context * ctx, const int32_t * tokens, in
     mgb_session_free(s);
     if (rc != MGB_OK) { fprintf(stderr, "magpie: %s\n", mgb_last_error()); return out; }
     ctx->state.kv_cache.seq_len = hp.context_frames + 1 + n_frames;
+    ctx->state.n_generated_frames = n_frames;
+    ctx->state.generated_codes.assign(codes.begin(), codes.begin() + (size_t)n_frames * 8);
     if (ms > 0.0f) fprintf(stderr, "magpie: generated %d frames in %.1f ms (%.1f frames/s)\n", n_frames, ms, n_frames * 1e3f / ms);
     out.assign(codes.begin(), codes.begin() + (size_t)n_frames * 8);
     return out;
@@ -265,6 +270,8 @@ magpie_context * magpie_init_with_backend(const char * model_path, magpie_backen
     if (!model_path) { fprintf(stderr, "magpie_init: null model path\n"); return nullptr; }
     mgb_model * m = mgb_model_load(model_path, env_device(), env_precision());
     if (!m) { fprintf(stderr, "magpie_init: %s\n", mgb_last_error()); return nullptr; }
+    // MAGPIE_GELU_TABLE=0: plain f32 tanh-GELU instead of ggml-CPU's f16 lookup table (default on: the reference's CPU semantics)
+    if (const char * e = getenv("MAGPIE_GELU_TABLE")) mgb_model_set_gelu_f16(m, atoi(e) != 0);
     magpie_context * ctx = new magpie_context();
     mgb_hparams hp;
     mgb_model_get_hparams(m, &hp);
@@ -333,6 +340,10 @@ magpie_sample_result magpie_local_transformer_sample_all(magpie_context * ctx, c
     return r;
 }
 
+bool magpie_is_eos(const std::vector<int32_t> & frame_codes, int32_t eos_id) {      // magpie.cpp:3273-3278
+    for (int32_t code : frame_codes) if (code == eos_id) return true;
+    return false;
+}
 bool magpie_is_eos(const int32_t * codes, int n_codebooks, int eos_id) {
     for (int i = 0; i < n_codebooks; i++) if (codes[i] == eos_id) return true;
     return false;

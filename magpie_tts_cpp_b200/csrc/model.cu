@@ -53,7 +53,18 @@ int parse_idx(const char * name, const char * prefix) {
 
 // Linear (out,in) or conv (out,in,k): ggml ne = [in,out] / [k,in,out].  k>1 is re-laid out
 // tap-major [k][out][in] so every tap is a contiguous row-major matrix.
-bool make_mat(Uploader & up, const GgufTensor & t, int precision, DevMat & m) {
+// The kernels index weights by the hyper-parameters, so every tensor's shape is checked against them BEFORE upload (a
+// mismatched or corrupt file must fail here, where the reference's ggml would assert, not read device memory out of bounds).
+bool make_mat(Uploader & up, const GgufTensor & t, int precision, DevMat & m, int64_t want_n, int64_t want_k, int64_t want_taps = 1) {
+    {
+        const int64_t k = t.n_dims == 3 ? t.ne[1] : t.ne[0], n = t.n_dims == 3 ? t.ne[2] : t.ne[1], taps = t.n_dims == 3 ? t.ne[0] : 1;
+        if (t.n_dims < 2 || t.n_dims > 3 || n != want_n || k != want_k || taps != want_taps) {
+            set_error("tensor '" + t.name + "': shape [" + std::to_string(n) + "][" + std::to_string(k) + "] x " + std::to_string(taps) +
+                      " taps does not match the hyper-parameters (expected [" + std::to_string(want_n) + "][" + std::to_string(want_k) +
+                      "] x " + std::to_string(want_taps) + ")");
+            return false;
+        }
+    }
     std::vector<float> v;
     if (!to_f32(t, v)) return false;
     if (t.n_dims == 3 && t.ne[0] > 1) {
@@ -76,11 +87,22 @@ bool make_mat(Uploader & up, const GgufTensor & t, int precision, DevMat & m) {
     return up.ok;
 }
 
-bool make_vec(Uploader & up, const GgufTensor & t, float *& dst, int * rows = nullptr) {
+// want_cols: required ne[0]; want_rows: required number of rows (product of the other dims), 0 = any (>= min_rows)
+bool make_vec(Uploader & up, const GgufTensor & t, float *& dst, int64_t want_cols, int64_t want_rows, int * rows = nullptr, int64_t min_rows = 1) {
+    {
+        const int64_t cols = t.ne[0], r = t.nelements() / (t.ne[0] > 0 ? t.ne[0] : 1);
+        const bool flat_ok = want_rows > 0 && t.nelements() == want_cols * want_rows;     // e.g. baked context stored as (speakers, C*d)
+        if (!flat_ok && (cols != want_cols || (want_rows > 0 ? r != want_rows : r < min_rows))) {
+            set_error("tensor '" + t.name + "': " + std::to_string(r) + " rows of " + std::to_string(cols) +
+                      " do not match the hyper-parameters (expected " + (want_rows > 0 ? std::to_string(want_rows) : ">= " + std::to_string(min_rows)) +
+                      " rows of " + std::to_string(want_cols) + ")");
+            return false;
+        }
+    }
     std::vector<float> v;
     if (!to_f32(t, v)) return false;
     dst = up.f32(v);
-    if (rows) *rows = (int)(t.n_dims >= 2 ? t.ne[1] : 1);
+    if (rows) *rows = (int)(t.nelements() / t.ne[0]);
     return up.ok;
 }
 
@@ -120,6 +142,13 @@ Model * load_model(const char * path, int device, int precision) {
     HP(max_dec_steps, 500); HP(sample_rate, 22050);
 #undef HP
     hp.eps = f.get_f32("magpie.eps", 1e-5f);
+    if (hp.d_model <= 0 || hp.d_ffn <= 0 || hp.d_ffn % 8 || hp.enc_layers <= 0 || hp.enc_layers > 64 || hp.dec_layers <= 0 || hp.dec_layers > 64 ||
+        hp.enc_heads <= 0 || hp.dec_sa_heads <= 0 || hp.enc_kernel <= 0 || hp.lt_dim <= 0 || hp.lt_ffn_dim <= 0 || hp.lt_ffn_dim % 8 ||
+        hp.text_vocab_size <= 0 || hp.vocab_per_cb <= 0 || hp.num_speakers <= 0 || hp.context_frames <= 0 || hp.max_dec_steps <= 0 ||
+        hp.audio_bos_id < 0 || hp.audio_bos_id + 7 >= hp.vocab_per_cb || hp.audio_eos_id < 0 || hp.audio_eos_id >= hp.vocab_per_cb) {
+        set_error("magpie_init: invalid hyper-parameters in the model file");
+        return nullptr;
+    }
     if (hp.num_codebooks != 8 || hp.lt_layers != 1 || hp.lt_heads != 1 || hp.dec_kernel != 1 ||
         hp.enc_kernel > 3 || hp.d_model % 8 || hp.d_model > 1024 || hp.lt_dim > 256 || hp.lt_dim % 8 ||
         hp.dec_xa_heads != 1 || hp.dec_xa_d_head != 128 || hp.d_model / hp.dec_sa_heads != 64 ||
@@ -138,58 +167,58 @@ Model * load_model(const char * path, int device, int precision) {
     for (const GgufTensor & t : f.tensors()) {
         const char * name = t.name.c_str();
         bool ok = true;
-        if (!strcmp(name, "text_embedding.weight")) ok = make_vec(up, t, M->text_emb);
+        if (!strcmp(name, "text_embedding.weight")) ok = make_vec(up, t, M->text_emb, hp.d_model, hp.text_vocab_size);
         else if (strstr(name, "audio_embeddings.")) {
             int cb = parse_idx(name, "audio_embeddings.");
-            if (cb >= 0 && cb < 8) ok = make_vec(up, t, M->audio_emb[cb]);
-        } else if (!strcmp(name, "baked_context_embedding.weight")) ok = make_vec(up, t, M->baked_ctx);
-        else if (!strcmp(name, "encoder.position_embeddings.weight")) ok = make_vec(up, t, M->enc_pos, &M->enc_pos_rows);
+            if (cb >= 0 && cb < 8) ok = make_vec(up, t, M->audio_emb[cb], hp.d_model, hp.vocab_per_cb);
+        } else if (!strcmp(name, "baked_context_embedding.weight")) ok = make_vec(up, t, M->baked_ctx, hp.d_model, (int64_t)hp.num_speakers * hp.context_frames);
+        else if (!strcmp(name, "encoder.position_embeddings.weight")) ok = make_vec(up, t, M->enc_pos, hp.d_model, 0, &M->enc_pos_rows);
         else if (strstr(name, "encoder.layers.")) {     // NB: matched before decoder.layers, as the reference
             int l = parse_idx(name, "encoder.layers.");
             if (l >= 0 && l < hp.enc_layers) {
                 EncLayer & L = M->enc[l];
-                if (strstr(name, "norm_self.weight")) ok = make_vec(up, t, L.norm_self);
-                else if (strstr(name, "self_attention.qkv_net.weight")) ok = make_mat(up, t, precision, L.qkv);
-                else if (strstr(name, "self_attention.o_net.weight")) ok = make_mat(up, t, precision, L.o);
-                else if (strstr(name, "norm_pos_ff.weight")) ok = make_vec(up, t, L.norm_ff);
-                else if (strstr(name, "pos_ff.proj.conv.weight")) ok = make_mat(up, t, precision, L.ff1);
-                else if (strstr(name, "pos_ff.o_net.conv.weight")) ok = make_mat(up, t, precision, L.ff2);
+                if (strstr(name, "norm_self.weight")) ok = make_vec(up, t, L.norm_self, hp.d_model, 1);
+                else if (strstr(name, "self_attention.qkv_net.weight")) ok = make_mat(up, t, precision, L.qkv, 3 * hp.d_model, hp.d_model);
+                else if (strstr(name, "self_attention.o_net.weight")) ok = make_mat(up, t, precision, L.o, hp.d_model, hp.d_model);
+                else if (strstr(name, "norm_pos_ff.weight")) ok = make_vec(up, t, L.norm_ff, hp.d_model, 1);
+                else if (strstr(name, "pos_ff.proj.conv.weight")) ok = make_mat(up, t, precision, L.ff1, hp.d_ffn, hp.d_model, hp.enc_kernel);
+                else if (strstr(name, "pos_ff.o_net.conv.weight")) ok = make_mat(up, t, precision, L.ff2, hp.d_model, hp.d_ffn, hp.enc_kernel);
             }
-        } else if (!strcmp(name, "encoder.norm_out.weight")) ok = make_vec(up, t, M->enc_norm_out);
-        else if (!strcmp(name, "decoder.position_embeddings.weight")) ok = make_vec(up, t, M->dec_pos, &M->dec_pos_rows);
+        } else if (!strcmp(name, "encoder.norm_out.weight")) ok = make_vec(up, t, M->enc_norm_out, hp.d_model, 1);
+        else if (!strcmp(name, "decoder.position_embeddings.weight")) ok = make_vec(up, t, M->dec_pos, hp.d_model, 0, &M->dec_pos_rows, hp.context_frames + 2);
         else if (strstr(name, "decoder.layers.")) {
             int l = parse_idx(name, "decoder.layers.");
             if (l >= 0 && l < hp.dec_layers) {
                 DecLayer & L = M->dec[l];
-                if (strstr(name, "norm_self.weight")) ok = make_vec(up, t, L.norm_self);
-                else if (strstr(name, "self_attention.qkv_net.weight")) ok = make_mat(up, t, precision, L.qkv);
-                else if (strstr(name, "self_attention.o_net.weight")) ok = make_mat(up, t, precision, L.o);
-                else if (strstr(name, "norm_xattn_query.weight")) ok = make_vec(up, t, L.norm_xa_q);
-                else if (strstr(name, "cross_attention.q_net.weight")) ok = make_mat(up, t, precision, L.xq);
-                else if (strstr(name, "cross_attention.kv_net.weight")) ok = make_mat(up, t, precision, L.xkv);
-                else if (strstr(name, "cross_attention.o_net.weight")) ok = make_mat(up, t, precision, L.xo);
-                else if (strstr(name, "norm_xattn_memory.weight")) ok = make_vec(up, t, L.norm_xa_mem);
-                else if (strstr(name, "norm_pos_ff.weight")) ok = make_vec(up, t, L.norm_ff);
-                else if (strstr(name, "pos_ff.proj.conv.weight")) ok = make_mat(up, t, precision, L.ff1);
-                else if (strstr(name, "pos_ff.o_net.conv.weight")) ok = make_mat(up, t, precision, L.ff2);
+                if (strstr(name, "norm_self.weight")) ok = make_vec(up, t, L.norm_self, hp.d_model, 1);
+                else if (strstr(name, "self_attention.qkv_net.weight")) ok = make_mat(up, t, precision, L.qkv, 3 * hp.d_model, hp.d_model);
+                else if (strstr(name, "self_attention.o_net.weight")) ok = make_mat(up, t, precision, L.o, hp.d_model, hp.d_model);
+                else if (strstr(name, "norm_xattn_query.weight")) ok = make_vec(up, t, L.norm_xa_q, hp.d_model, 1);
+                else if (strstr(name, "cross_attention.q_net.weight")) ok = make_mat(up, t, precision, L.xq, 128, hp.d_model);
+                else if (strstr(name, "cross_attention.kv_net.weight")) ok = make_mat(up, t, precision, L.xkv, 256, hp.d_model);
+                else if (strstr(name, "cross_attention.o_net.weight")) ok = make_mat(up, t, precision, L.xo, hp.d_model, 128);
+                else if (strstr(name, "norm_xattn_memory.weight")) ok = make_vec(up, t, L.norm_xa_mem, hp.d_model, 1);
+                else if (strstr(name, "norm_pos_ff.weight")) ok = make_vec(up, t, L.norm_ff, hp.d_model, 1);
+                else if (strstr(name, "pos_ff.proj.conv.weight")) ok = make_mat(up, t, precision, L.ff1, hp.d_ffn, hp.d_model);
+                else if (strstr(name, "pos_ff.o_net.conv.weight")) ok = make_mat(up, t, precision, L.ff2, hp.d_model, hp.d_ffn);
             }
-        } else if (!strcmp(name, "decoder.norm_out.weight")) ok = make_vec(up, t, M->dec_norm_out);
-        else if (!strcmp(name, "final_proj.weight")) ok = make_mat(up, t, precision, M->final_w);
-        else if (!strcmp(name, "final_proj.bias")) ok = make_vec(up, t, M->final_b);
-        else if (strstr(name, "local_transformer_in_projection.weight")) ok = make_mat(up, t, precision, M->lt_in_w);
-        else if (strstr(name, "local_transformer_in_projection.bias")) ok = make_vec(up, t, M->lt_in_b);
-        else if (!strcmp(name, "local_transformer.position_embeddings.weight")) ok = make_vec(up, t, M->lt_pos, &M->lt_pos_rows);
-        else if (strstr(name, "local_transformer.layers.0.norm_self.weight")) ok = make_vec(up, t, M->lt_norm_self);
-        else if (strstr(name, "local_transformer.layers.0.self_attention.qkv_net.weight")) ok = make_mat(up, t, precision, M->lt_qkv);
-        else if (strstr(name, "local_transformer.layers.0.self_attention.o_net.weight")) ok = make_mat(up, t, precision, M->lt_o);
-        else if (strstr(name, "local_transformer.layers.0.norm_pos_ff.weight")) ok = make_vec(up, t, M->lt_norm_ff);
-        else if (strstr(name, "local_transformer.layers.0.pos_ff.proj.conv.weight")) ok = make_mat(up, t, precision, M->lt_ff1);
-        else if (strstr(name, "local_transformer.layers.0.pos_ff.o_net.conv.weight")) ok = make_mat(up, t, precision, M->lt_ff2);
+        } else if (!strcmp(name, "decoder.norm_out.weight")) ok = make_vec(up, t, M->dec_norm_out, hp.d_model, 1);
+        else if (!strcmp(name, "final_proj.weight")) ok = make_mat(up, t, precision, M->final_w, (int64_t)8 * hp.vocab_per_cb, hp.d_model);
+        else if (!strcmp(name, "final_proj.bias")) ok = make_vec(up, t, M->final_b, (int64_t)8 * hp.vocab_per_cb, 1);
+        else if (strstr(name, "local_transformer_in_projection.weight")) ok = make_mat(up, t, precision, M->lt_in_w, hp.lt_dim, hp.d_model);
+        else if (strstr(name, "local_transformer_in_projection.bias")) ok = make_vec(up, t, M->lt_in_b, hp.lt_dim, 1);
+        else if (!strcmp(name, "local_transformer.position_embeddings.weight")) ok = make_vec(up, t, M->lt_pos, hp.lt_dim, 0, &M->lt_pos_rows, 8);
+        else if (strstr(name, "local_transformer.layers.0.norm_self.weight")) ok = make_vec(up, t, M->lt_norm_self, hp.lt_dim, 1);
+        else if (strstr(name, "local_transformer.layers.0.self_attention.qkv_net.weight")) ok = make_mat(up, t, precision, M->lt_qkv, 3 * hp.lt_dim, hp.lt_dim);
+        else if (strstr(name, "local_transformer.layers.0.self_attention.o_net.weight")) ok = make_mat(up, t, precision, M->lt_o, hp.lt_dim, hp.lt_dim);
+        else if (strstr(name, "local_transformer.layers.0.norm_pos_ff.weight")) ok = make_vec(up, t, M->lt_norm_ff, hp.lt_dim, 1);
+        else if (strstr(name, "local_transformer.layers.0.pos_ff.proj.conv.weight")) ok = make_mat(up, t, precision, M->lt_ff1, hp.lt_ffn_dim, hp.lt_dim);
+        else if (strstr(name, "local_transformer.layers.0.pos_ff.o_net.conv.weight")) ok = make_mat(up, t, precision, M->lt_ff2, hp.lt_dim, hp.lt_ffn_dim);
         else if (strstr(name, "local_transformer_out_projections.")) {
             int cb = parse_idx(name, "local_transformer_out_projections.");
             if (cb >= 0 && cb < 8) {
-                if (strstr(name, ".weight")) ok = make_mat(up, t, precision, M->lt_out_w[cb]);
-                else if (strstr(name, ".bias")) ok = make_vec(up, t, M->lt_out_b[cb]);
+                if (strstr(name, ".weight")) ok = make_mat(up, t, precision, M->lt_out_w[cb], hp.vocab_per_cb, hp.lt_dim);
+                else if (strstr(name, ".bias")) ok = make_vec(up, t, M->lt_out_b[cb], hp.vocab_per_cb, 1);
             }
         }
         // anything else (context_encoder.* etc.) is loaded-but-unused in the reference: skipped here
@@ -252,7 +281,7 @@ Model * load_model(const char * path, int device, int precision) {
         for (auto & L : M->enc) for (DevMat * m : {&L.qkv, &L.o, &L.ff1, &L.ff2}) mats.push_back(m);      // (ff1 / ff2: k = 3 causal convs, taps concatenated along k)
         mats.push_back(&M->final_w);
         for (DevMat * m : mats) {
-            if (m->K % 64 != 0) continue;
+            if (m->w == nullptr || m->K % 64 != 0) continue;
             void * t = nullptr;
             if (cudaMalloc(&t, tc_weight_tile_bytes(m->N, m->K * m->taps)) != cudaSuccess) { set_error("cudaMalloc failed (weight tiles)"); return nullptr; }
             M->allocations.push_back(t);
@@ -315,42 +344,51 @@ Codec * load_codec(const char * path, int device) {
         return nullptr;
     }
     Uploader up{C->allocations};
-    auto vec = [&](const GgufTensor & t, float *& dst, int * n = nullptr) {
+    // the decoder architecture is fixed (magpie.h:666-677: 864 -> 432 -> 216 -> 108 -> 54 -> 27 channels, strides 8,8,4,2,2, residual
+    // kernels 3/7/11): every tensor's element count is checked against it before upload, so a mismatched file fails here
+    auto vec = [&](const GgufTensor & t, float *& dst, int64_t want, int * n = nullptr) {
+        if (t.nelements() != want) {
+            set_error("tensor '" + t.name + "': " + std::to_string(t.nelements()) + " elements, expected " + std::to_string(want) +
+                      " for the nano-codec decoder");
+            return false;
+        }
         std::vector<float> v;
         if (!to_f32(t, v)) return false;
         dst = up.f32(v);
         if (n) *n = (int)v.size();
         return up.ok;
     };
+    auto stage_ch = [&](int i) { return (int64_t)(C->base_ch >> (i + 1)); };       // output channels of up-sampling stage i
     for (const GgufTensor & t : f.tensors()) {
         const char * name = t.name.c_str();
         bool ok = true;
-        if (strstr(name, "dec.pre.weight")) { ok = vec(t, C->pre_w); C->pre_k = (int)t.ne[0]; C->latent = (int)t.ne[1]; C->base_ch = (int)t.ne[2]; }
-        else if (strstr(name, "dec.pre.bias")) ok = vec(t, C->pre_b);
-        else if (strstr(name, "dec.post.weight")) { ok = vec(t, C->post_w); C->post_k = (int)t.ne[0]; }
-        else if (strstr(name, "dec.post.bias")) ok = vec(t, C->post_b);
-        else if (strstr(name, "dec.post_act.alpha")) ok = vec(t, C->post_alpha, &C->n_alpha_post);
+        if (strstr(name, "dec.pre.weight")) ok = vec(t, C->pre_w, (int64_t)C->base_ch * C->latent * C->pre_k);
+        else if (strstr(name, "dec.pre.bias")) ok = vec(t, C->pre_b, C->base_ch);
+        else if (strstr(name, "dec.post.weight")) ok = vec(t, C->post_w, stage_ch(4) * C->post_k);
+        else if (strstr(name, "dec.post.bias")) ok = vec(t, C->post_b, 1);
+        else if (strstr(name, "dec.post_act.alpha")) ok = vec(t, C->post_alpha, stage_ch(4) / 2, &C->n_alpha_post);
         else if (strstr(name, "dec.up.")) {
             int i = parse_idx(name, "dec.up.");
             if (i >= 0 && i < 5) {
-                if (strstr(name, ".weight")) ok = vec(t, C->up_w[i]);
-                else if (strstr(name, ".bias")) ok = vec(t, C->up_b[i]);
+                if (strstr(name, ".weight")) ok = vec(t, C->up_w[i], 2 * stage_ch(i) * 2 * C->up_rates[i]);
+                else if (strstr(name, ".bias")) ok = vec(t, C->up_b[i], stage_ch(i));
             }
         } else if (strstr(name, "dec.act.") && strstr(name, "alpha")) {
             int i = parse_idx(name, "dec.act.");
-            if (i >= 0 && i < 5) ok = vec(t, C->act_alpha[i], &C->n_alpha_act[i]);
+            if (i >= 0 && i < 5) ok = vec(t, C->act_alpha[i], stage_ch(i), &C->n_alpha_act[i]);       // half of the 2 x stage_ch(i) input channels
         } else if (strstr(name, "dec.rl.")) {
             const char * p = strstr(name, "dec.rl.") + 7; int i = atoi(p);
             const char * p2 = strstr(p, ".rb."); if (!p2) continue; p2 += 4; int j = atoi(p2);
             const char * p3 = strstr(p2, ".rb."); if (!p3) continue; p3 += 4; int k = atoi(p3);
             if (i < 0 || i >= 5 || j < 0 || j >= 3 || k < 0 || k >= 3) continue;
             CodecResBlock & b = C->rb[i][j][k];
-            if (strstr(name, ".in_act.alpha")) ok = vec(t, b.in_alpha, &C->n_alpha_rb[i]);
-            else if (strstr(name, ".in_conv.weight")) ok = vec(t, b.in_w);
-            else if (strstr(name, ".in_conv.bias")) ok = vec(t, b.in_b);
-            else if (strstr(name, ".sk_act.alpha")) ok = vec(t, b.sk_alpha);
-            else if (strstr(name, ".sk_conv.weight")) ok = vec(t, b.sk_w);
-            else if (strstr(name, ".sk_conv.bias")) ok = vec(t, b.sk_b);
+            const int64_t c = stage_ch(i), wn = c * c * C->res_k[j];
+            if (strstr(name, ".in_act.alpha")) ok = vec(t, b.in_alpha, c / 2, &C->n_alpha_rb[i]);
+            else if (strstr(name, ".in_conv.weight")) ok = vec(t, b.in_w, wn);
+            else if (strstr(name, ".in_conv.bias")) ok = vec(t, b.in_b, c);
+            else if (strstr(name, ".sk_act.alpha")) ok = vec(t, b.sk_alpha, c / 2);
+            else if (strstr(name, ".sk_conv.weight")) ok = vec(t, b.sk_w, wn);
+            else if (strstr(name, ".sk_conv.bias")) ok = vec(t, b.sk_b, c);
         }
         if (!ok || !up.ok) return nullptr;
     }

@@ -132,12 +132,12 @@ __global__ void __launch_bounds__(kLinThreads) linear_kernel(const LinParams p) 
 template <typename T, int MB, int RW>
 bool launch_linear_t(const LinParams & p, cudaStream_t stream) {
     const size_t smem = (size_t)MB * p.K * sizeof(float);
-    static uint64_t attr_done = 0;                     // per-device bit (function attributes are per device)
+    static DeviceOnce attr_done;                     // per-device bit (function attributes are per device)
     int dev = 0;
     MGB_CUDA_TRY(cudaGetDevice(&dev));
-    if (!(attr_done >> dev & 1)) {
+    if (!attr_done.done(dev)) {
         MGB_CUDA_TRY(cudaFuncSetAttribute(linear_kernel<T, MB, RW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_done |= 1ull << dev;
+        attr_done.set(dev);
     }
     if (smem > 200 * 1024) { set_error("linear: K too large for the staged input tile"); return false; }
     dim3 grid((p.N + kLinWarps * RW - 1) / (kLinWarps * RW), (p.M + MB - 1) / MB);
@@ -549,15 +549,18 @@ int attention_plan_kv_split(int items, int max_keys) {
     if (getenv("MGB_ATTN_SPLIT")) return std::max(0, std::min(atoi(getenv("MGB_ATTN_SPLIT")), kAttnMaxSplit));
     const int long_min = getenv("MGB_ATTN_LONG_MIN") ? atoi(getenv("MGB_ATTN_LONG_MIN")) : 0;
     if (max_keys < long_min) return 0;
-    static int cap = 0;
+    static std::atomic<int> cap_dev[64];               // resident CTA slots, per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int cap = cap_dev[dev & 63];
     if (cap == 0) {
-        int dev = 0, sms = 148, per_sm = 2;
-        cudaGetDevice(&dev);
+        int sms = 148, per_sm = 2;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, attention_kernel<__nv_bfloat16, 64, 1>, kAttnWarps * 32, 0) != cudaSuccess || per_sm < 1) {
             cudaGetLastError(); per_sm = 2;
         }
         cap = sms * per_sm;
+        cap_dev[dev & 63] = cap;
     }
     int S = std::max(1, std::min((cap + items / 2) / items, kAttnMaxSplit));      // nearest: 16 utterances -> 2 (1169 -> 1140 us at 2512 keys)
     while (S > 1 && max_keys / S < 256) S--;
@@ -579,13 +582,13 @@ bool launch_attention(const AttnArgs & a, cudaStream_t stream) {
         // tokens are (utterance-major, positions 0..C-1): one CTA per (head, utterance) with the K / V rows staged once
         const int C = a.prefill_len;
         const size_t smem = ((size_t)C * 65 + (size_t)C * 64 + 8 * 64 + 8 * 128) * sizeof(float);
-        static uint64_t attr_done = 0;
+        static DeviceOnce attr_done;
         int dev = 0;
         MGB_CUDA_TRY(cudaGetDevice(&dev));
-        if (!(attr_done >> dev & 1)) {
+        if (!attr_done.done(dev)) {
             MGB_CUDA_TRY(cudaFuncSetAttribute(prefill_attention_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
             MGB_CUDA_TRY(cudaFuncSetAttribute(prefill_attention_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
-            attr_done |= 1ull << dev;
+            attr_done.set(dev);
         }
         p.pdl = 0;
         const int nb = a.tok.M / C;

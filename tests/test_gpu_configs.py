@@ -1,0 +1,370 @@
+"""GPU parity on BASELINE.json's OWN configurations, at their sizes (not on shortened stand-ins):
+
+  config 1  "Hello, world!" greedy through the magpie-tts CLI on the full Magpie-357M f32 GGUF -> WAV vs the oracle's WAV
+  config 2  500-frame teacher-forced run of the benchmarked batch-1 bf16 kernel (frame_loop_kernel) vs the oracle on EVERY
+            frame (KV length 111..610 = key splits 1..5), greedy codes asserted on the margin-qualified picks
+  config 3  one whole 60 s utterance (1291 frames) through the codec vs the oracle, >= 40 dB
+  config 4  64 utterances, texts of 20..80 tokens, max_text 96, speakers 0..4: encoder output, decoder hidden, LT logits
+  config 5  KV length 2 710 (2 600 teacher-forced frames): batch-1 frame loop and the batched long-KV attention vs the oracle
+
+The oracle (oracle/, CPU restatement of the reference) runs on the box's host cores; every case is sized so that it
+finishes in about a minute.  Tolerances: BASELINE.json north_star (bf16 2e-2, f32 1e-4, codec >= 40 dB).
+"""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from test_gpu_parity import HELLO, TABLE_TOL, close, snr_db
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "magpie_tts_cpp_b200")
+
+
+@pytest.fixture(scope="module")
+def B():
+    from magpie_tts_cpp_b200 import binding
+    return binding
+
+
+def config2_codes(frames):
+    return np.random.default_rng(42).integers(0, 2016, (frames, 8)).astype(np.int32)      # bench.py forced_codes()
+
+
+def oracle_teacher_forced(o, tokens, speaker, codes, max_seq, want_logits=True, keep=None):
+    """Teacher-forced oracle run; returns hidden [T][d], logits [T][8][V] (or None), greedy [T][8].  keep: frames to record
+    (default all); the other frames are still run (they build the KV cache)."""
+    enc = o.encode_text(tokens)
+    st = o.new_state(enc, speaker, max_seq)
+    prev = np.full(8, o.hp["audio_bos_id"], np.int32)
+    hid, lgs, grs = [], [], []
+    for t in range(len(codes)):
+        h = st.step(prev)
+        if keep is None or t in keep:
+            _, a, lg = o.lt_sample(h, 0.0, 80, forced_codes=codes[t], want_logits=want_logits)
+            hid.append(h); lgs.append(lg); grs.append(a)
+        prev = codes[t]
+    return enc, np.stack(hid), (np.stack(lgs) if want_logits else None), np.stack(grs)
+
+
+@pytest.fixture(scope="module")
+def config2_oracle(oracle_mod, full_model_path):
+    o = oracle_mod.OracleModel(full_model_path)              # f16 GELU table on: the reference's CPU semantics
+    codes = config2_codes(500)
+    enc, hid, lg, gr = oracle_teacher_forced(o, HELLO, 0, codes, 110 + 500 + 16)
+    return dict(o=o, codes=codes, enc=enc, hid=hid, lg=lg, gr=gr)
+
+
+def margin_qualified(ref_lg, tol):
+    """Picks whose top-2 logit margin exceeds twice the tolerance band |a-b| <= tol |b| + tol rms(b): a kernel inside the band
+    cannot flip them.  ref_lg [..., V] with -inf at masked ids."""
+    fin = np.isfinite(ref_lg)
+    rms = np.sqrt(np.mean(np.where(fin, ref_lg, 0.0).astype(np.float64) ** 2, axis=-1) * ref_lg.shape[-1] / np.maximum(fin.sum(-1), 1))
+    srt = np.sort(np.where(fin, ref_lg, -np.inf), axis=-1)
+    top1, top2 = srt[..., -1].astype(np.float64), srt[..., -2].astype(np.float64)
+    band = tol * np.abs(top1) + tol * rms
+    return (top1 - top2) > 2.0 * band, top1 - top2
+
+
+def test_config2_frame_loop_500_frames_bf16_vs_oracle(B, config2_oracle, full_model_path, monkeypatch):
+    """BASELINE configs[1] as benchmarked: ONE launch of frame_loop_kernel for all 500 frames; every frame's decoder hidden
+    state and 8 LT logit vectors against the oracle at the bf16 bar."""
+    for k in ("MGB_NO_LOOPK", "MGB_NO_MEGA", "MGB_LT_STREAM", "MGB_LOOP_MAXSPLIT"):
+        monkeypatch.delenv(k, raising=False)
+    fo = config2_oracle
+    m = B.Model(full_model_path, 0, B.PREC_BF16)
+    s = m.session(batch=1, max_text=32, max_seq=110 + 500 + 16)
+    enc = s.encode_text([HELLO])
+    close(enc[0], fo["enc"], 2e-2)
+    s.prefill([0])
+    hid, lg, gr = s.teacher_forced(fo["codes"][None])
+    assert s.last_loop_launches == 1, "the 500-frame run must be one launch of the persistent frame-loop kernel"
+    close(hid[0], fo["hid"], 2e-2)
+    close(lg[0], fo["lg"], 2e-2)
+    # per key-split count (the kernel divides the cached keys over min(6, ceil(KV / 128)) CTAs per head): a failure names the split
+    kv = 111 + np.arange(500)
+    splits = np.minimum(6, (kv + 127) // 128)
+    assert set(splits.tolist()) == {1, 2, 3, 4, 5}
+    for S in (1, 2, 3, 4, 5):
+        sel = splits == S
+        close(hid[0][sel], fo["hid"][sel], 2e-2)
+        close(lg[0][sel], fo["lg"][sel], 2e-2)
+    # greedy codes: bf16 noise may flip a pick only where the oracle's own top-2 margin is inside the bf16 band, so the
+    # margin-qualified picks must ALL agree (north_star: greedy codes identical; random-init logits are nearly flat, which is
+    # why the unqualified rest is reported, not asserted)
+    q, margin = margin_qualified(fo["lg"], 2e-2)
+    agree = gr[0] == fo["gr"]
+    print(f"config 2 bf16: {q.mean():.3f} of the 4000 picks are margin-qualified; agreement on them {agree[q].mean():.4f}, "
+          f"overall {agree.mean():.3f}, frames with all 8 codes equal {np.all(agree, axis=1).mean():.3f}")
+    assert q.sum() >= 40, "too few margin-qualified picks for the check to mean anything"
+    assert agree[q].all(), f"{(~agree[q]).sum()} margin-qualified greedy picks differ from the oracle"
+    # a flipped pick must sit on a near-tie of the oracle: the oracle's logit of the kernel's pick is within the band of its top
+    t_idx, cb_idx = np.nonzero(~agree)
+    for t, cb in zip(t_idx, cb_idx):
+        row = fo["lg"][t, cb]
+        fin = row[np.isfinite(row)]
+        band = 2.0 * (2e-2 * abs(float(row[fo["gr"][t, cb]])) + 2e-2 * float(np.sqrt(np.mean(fin.astype(np.float64) ** 2))))
+        assert row[fo["gr"][t, cb]] - row[gr[0, t, cb]] <= band, (t, cb)
+    s.close(); m.close()
+
+
+def test_config2_frame_loop_multi_round_key_scan(B, config2_oracle, full_model_path, monkeypatch):
+    """Attention items longer than 480 keys (KV beyond 2 880 in production) take the multi-round scan of frame_loop_kernel.
+    MGB_LOOP_MAXSPLIT=1 gives every head ONE item of up to 610 keys: same results as the 5-way split, and within the bf16 bar."""
+    fo = config2_oracle
+    m = B.Model(full_model_path, 0, B.PREC_BF16)
+
+    def run(maxsplit):
+        if maxsplit:
+            monkeypatch.setenv("MGB_LOOP_MAXSPLIT", str(maxsplit))
+        else:
+            monkeypatch.delenv("MGB_LOOP_MAXSPLIT", raising=False)
+        s = m.session(batch=1, max_text=32, max_seq=110 + 500 + 16)
+        s.encode_text([HELLO], want_output=False)
+        s.prefill([0])
+        hid, _, gr = s.teacher_forced(fo["codes"][None], want_logits=False)
+        n = s.last_loop_launches
+        s.close()
+        return hid[0], gr[0], n
+
+    h6, g6, n6 = run(0)
+    h1, g1, n1 = run(1)
+    h2, g2, n2 = run(2)
+    monkeypatch.delenv("MGB_LOOP_MAXSPLIT", raising=False)
+    assert n6 == n1 == n2 == 1
+    for h in (h1, h2):
+        close(h, h6, 2e-3)                       # same bf16 weights and cache, different summation order
+        close(h, fo["hid"], 2e-2)
+    assert np.mean(g1 == g6) >= 0.97
+    m.close()
+
+
+@pytest.mark.parametrize("n_text", [70, 256])
+def test_frame_loop_long_texts_vs_oracle(B, oracle_mod, full_model_path, n_text, monkeypatch):
+    """The reference's doc example is 70 tokens; magpie_encode_text takes any length up to the position table.  The batch-1
+    bf16 frame loop keeps its folded cross-attention for texts up to 512 tokens (first 30 table rows from registers, the rest
+    streamed): still one launch, still inside the bf16 bar."""
+    for k in ("MGB_NO_LOOPK", "MGB_NO_MEGA", "MGB_LT_STREAM", "MGB_LOOP_MAXSPLIT"):
+        monkeypatch.delenv(k, raising=False)
+    rng = np.random.default_rng(n_text)
+    text = [2378] + rng.integers(0, 90, n_text - 2).tolist() + [2379]
+    codes = config2_codes(10)
+    o = oracle_mod.OracleModel(full_model_path)
+    enc_ref, hid_ref, lg_ref, gr_ref = oracle_teacher_forced(o, text, 2, codes, 110 + 10 + 16)
+    m = B.Model(full_model_path, 0, B.PREC_BF16)
+    s = m.session(batch=1, max_text=n_text, max_seq=110 + 10 + 16)
+    enc = s.encode_text([text])
+    close(enc[0], enc_ref, 2e-2)
+    s.prefill([2])
+    hid, lg, gr = s.teacher_forced(codes[None])
+    assert s.last_loop_launches == 1
+    close(hid[0], hid_ref, 2e-2)
+    close(lg[0], lg_ref, 2e-2)
+    # and free-running generation takes the same kernel
+    s.encode_text([text], want_output=False)
+    s.prefill([2])
+    out = s.generate(max_steps=6, temperature=0.0, ignore_eos=True)
+    assert s.last_loop_launches == 1 and len(out[0]) == 6
+    s.close(); m.close()
+
+
+def test_config4_shapes_64_utterances_bf16(B, oracle_mod, full_model_path):
+    """BASELINE configs[3] shapes as bench.py runs them: 64 utterances, distinct random texts of 20..80 tokens, max_text 96
+    (encoder / cross-K/V GEMMs over two 64-token tiles per utterance group, folded cross-attention with E > 32), speakers
+    0..4, distinct forced codes per utterance.  Six utterances (shortest / longest text, first, last, two in between) are
+    followed through the oracle: encoder output, 6 decoder steps, LT logits."""
+    nb = 64
+    rng = np.random.default_rng(7)
+    texts = [[2378] + rng.integers(0, 90, int(rng.integers(18, 79))).tolist() + [2379] for _ in range(nb)]
+    speakers = [b % 5 for b in range(nb)]
+    codes = np.random.default_rng(11).integers(0, 2016, (nb, 6, 8)).astype(np.int32)
+    lens = [len(t) for t in texts]
+    assert min(lens) >= 20 and max(lens) <= 80 and max(lens) > 64
+    m = B.Model(full_model_path, 0, B.PREC_BF16)
+    s = m.session(batch=nb, max_text=96, max_seq=110 + 215 + 16)
+    enc = s.encode_text(texts)
+    s.prefill(speakers)
+    hid, lg, gr = s.teacher_forced(codes)
+    o = oracle_mod.OracleModel(full_model_path)
+    picks = sorted({int(np.argmin(lens)), int(np.argmax(lens)), 0, 13, 37, nb - 1})
+    for b in picks:
+        enc_ref, hid_ref, lg_ref, _ = oracle_teacher_forced(o, texts[b], speakers[b], codes[b], 110 + 215 + 16)
+        close(enc[b], enc_ref, 2e-2)
+        close(hid[b], hid_ref, 2e-2)
+        close(lg[b], lg_ref, 2e-2)
+    s.close(); m.close()
+
+
+def test_config4_shapes_f32_long_texts(B, oracle_mod, full_model_path):
+    """The same text shapes in the f32 parity mode (1e-4, GELU table off on both sides): 4 utterances of 80 / 65 / 33 / 20 tokens."""
+    rng = np.random.default_rng(3)
+    texts = [[2378] + rng.integers(0, 90, n - 2).tolist() + [2379] for n in (80, 65, 33, 20)]
+    codes = np.random.default_rng(4).integers(0, 2016, (4, 4, 8)).astype(np.int32)
+    m = B.Model(full_model_path, 0, B.PREC_F32)
+    m.set_gelu_f16(False)
+    o = oracle_mod.OracleModel(full_model_path)
+    o.set_gelu_table(False)
+    s = m.session(batch=4, max_text=96)
+    enc = s.encode_text(texts)
+    s.prefill([4, 3, 2, 1])
+    hid, lg, gr = s.teacher_forced(codes)
+    for b in range(4):
+        enc_ref, hid_ref, lg_ref, gr_ref = oracle_teacher_forced(o, texts[b], [4, 3, 2, 1][b], codes[b], m.hp["context_frames"] + m.hp["max_dec_steps"] + 16)
+        close(enc[b], enc_ref, 1e-4)
+        close(hid[b], hid_ref, 1e-4)
+        close(lg[b], lg_ref, 1e-4)
+        assert np.mean(gr[b] == gr_ref) >= 0.99
+    s.close(); m.close()
+
+
+def test_batched_step_with_text_capacity_beyond_the_folded_kernel(B, oracle_mod, full_model_path):
+    """bf16, 2 utterances in a session sized for 1024 text tokens: beyond the 512 positions the folded cross-attention kernel
+    holds, so the decoder steps must take the unfolded q GEMM + attention + o GEMM kernels (round-1 advisor finding: every
+    step used to fail with 'shape not supported')."""
+    texts = [HELLO, HELLO[:9] + [2379]]
+    codes = np.repeat(config2_codes(5)[None], 2, axis=0)
+    m = B.Model(full_model_path, 0, B.PREC_BF16)
+    s = m.session(batch=2, max_text=1024)
+    s.encode_text(texts, want_output=False)
+    s.prefill([0, 1])
+    hid, lg, gr = s.teacher_forced(codes)
+    o = oracle_mod.OracleModel(full_model_path)
+    for b in range(2):
+        _, hid_ref, lg_ref, _ = oracle_teacher_forced(o, texts[b], [0, 1][b], codes[b], 110 + 500 + 16)
+        close(hid[b], hid_ref, 2e-2)
+        close(lg[b], lg_ref, 2e-2)
+    s.close(); m.close()
+
+
+def test_config5_kv_length_2710_vs_oracle(B, oracle_mod, full_model_path, monkeypatch):
+    """BASELINE configs[4]'s cache length: 2 600 teacher-forced frames (KV 111 -> 2 710).  The batch-1 frame loop (6 key splits
+    of up to 452 keys) and the batched step (16 utterances: cluster key-split self-attention) against the oracle's hidden
+    states at the end, in the middle and at the start of the run."""
+    for k in ("MGB_NO_LOOPK", "MGB_NO_MEGA", "MGB_LT_STREAM", "MGB_LOOP_MAXSPLIT", "MGB_NO_ATTN_SPLIT", "MGB_ATTN_SPLIT"):
+        monkeypatch.delenv(k, raising=False)
+    T = 2600
+    codes = config2_codes(T)
+    keep = set(range(0, 4)) | set(range(1298, 1302)) | set(range(T - 8, T))
+    o = oracle_mod.OracleModel(full_model_path)
+    _, hid_ref, _, _ = oracle_teacher_forced(o, HELLO, 0, codes, 110 + T + 16, want_logits=False, keep=keep)
+    idx = sorted(keep)
+    m = B.Model(full_model_path, 0, B.PREC_BF16)
+    s = m.session(batch=1, max_text=32, max_seq=110 + T + 16)
+    s.encode_text([HELLO], want_output=False)
+    s.prefill([0])
+    hid, _, _ = s.teacher_forced(codes[None], want_logits=False, want_greedy=False)
+    assert s.last_loop_launches == 1
+    close(hid[0][idx], hid_ref, 2e-2)
+    s.close()
+    nb = 16
+    s = m.session(batch=nb, max_text=32, max_seq=110 + T + 16)
+    s.encode_text([HELLO] * nb, want_output=False)
+    s.prefill([0] * nb)
+    hidb, _, _ = s.teacher_forced(np.repeat(codes[None], nb, axis=0), want_logits=False, want_greedy=False)
+    close(hidb[0][idx], hid_ref, 2e-2)
+    np.testing.assert_array_equal(hidb[nb - 1], hidb[0])
+    s.close(); m.close()
+
+
+# ---- config 3: a whole 60 s utterance ---------------------------------------------------------------------------------
+
+def test_config3_whole_60s_utterance_vs_oracle(B, oracle_mod, codec_path):
+    rng = np.random.default_rng(42)
+    T = 1291                                      # 60 s x 22050 / 1024
+    codes = rng.integers(0, 2016, (2, 8, T)).astype(np.int32)
+    c = B.Codec(codec_path)
+    pcm = c.decode(codes)
+    ref = oracle_mod.OracleCodec(codec_path, conv_f16=True).decode(codes[1])
+    assert ref.shape == pcm[1].shape == (T * 1024,)
+    s_all = snr_db(pcm[1], ref)
+    # per 5 s window as well: a localised defect must not hide in the utterance-wide average
+    win = 5 * 22050
+    s_min = min(snr_db(pcm[1][i:i + win], ref[i:i + win]) for i in range(0, len(ref) - win + 1, win))
+    print(f"config 3: whole 60 s utterance SNR {s_all:.1f} dB, worst 5 s window {s_min:.1f} dB")
+    assert s_all >= 40.0 and s_min >= 40.0
+    assert np.abs(pcm[1] - ref).max() < 2e-3
+
+
+# ---- config 1: the CLI on the full model ----------------------------------------------------------------------------------
+
+def read_wav(path):
+    b = open(path, "rb").read()
+    assert b[:4] == b"RIFF" and b[8:16] == b"WAVEfmt " and b[36:40] == b"data"
+    n = struct.unpack("<I", b[40:44])[0]
+    assert len(b) == 44 + n
+    return np.frombuffer(b[44:], dtype="<i2")
+
+
+def test_config1_cli_full_model_f32_wav_vs_oracle(tmp_path, oracle_mod, full_model_path, codec_path):
+    """BASELINE configs[0]: Magpie-357M f32 GGUF + nano-codec, greedy "Hello, world!" through `magpie-tts` -> 22 050 Hz WAV,
+    compared with the oracle's codes and with the oracle's WAV under the CLI's 32-frame chunking (magpie-tts.cpp:183-206).
+    Free-running greedy decoding amplifies a single flipped near-tie into a different trajectory, so the comparison runs in
+    pure f32 (MAGPIE_GELU_TABLE=0 on our side, table off in the oracle: noise ~1e-6) and covers the common prefix of the two
+    trajectories, which must be at least one whole 32-frame chunk (and in practice is the whole utterance)."""
+    cli = os.path.join(PKG, "bin", "magpie-tts")
+    if not os.path.exists(cli):
+        subprocess.check_call(["make", "-C", os.path.join(PKG, "csrc"), "-s", "cli"])
+    wav = str(tmp_path / "hello.wav")
+    r = subprocess.run([cli, "-m", full_model_path, "-c", codec_path, "-t", "Hello, world!", "--temp", "0", "-o", wav],
+                       capture_output=True, text=True, env=dict(os.environ, MAGPIE_PRECISION="f32", MAGPIE_GELU_TABLE="0"))
+    assert r.returncode == 0, r.stderr
+    pcm16 = read_wav(wav)
+    o = oracle_mod.OracleModel(full_model_path)
+    o.set_gelu_table(False)
+    ref_codes = o.synthesize(HELLO, speaker=0, temperature=0.0)              # max_dec_steps of the fixture = 500
+    n_cli = len(pcm16) // 1024
+    assert len(pcm16) == n_cli * 1024 and n_cli >= 4
+    # decode the oracle codes chunk by chunk; compare chunk-wise until the first chunk that differs by more than rounding
+    oc = oracle_mod.OracleCodec(codec_path)
+    n_cmp = min(n_cli, len(ref_codes))
+    same_chunks = 0
+    snrs = []
+    for i in range(0, n_cmp, 32):
+        n = min(32, n_cmp - i)
+        if n < 32 and (n_cli != len(ref_codes)):
+            break                                                            # ragged tails of different lengths are not comparable
+        ref = oc.decode(np.ascontiguousarray(ref_codes[i:i + n].T))
+        ref16 = (np.clip(ref, -1, 1) * np.float32(32767.0)).astype(np.int16)
+        got = pcm16[i * 1024:(i + n) * 1024].astype(np.int32)
+        err = got - ref16.astype(np.int32)
+        snr = 10 * np.log10(np.sum(ref16.astype(np.float64) ** 2) / max(np.sum(err.astype(np.float64) ** 2), 1e-9))
+        if snr < 40.0:
+            break
+        snrs.append(snr)
+        same_chunks += 1
+    total_chunks = (n_cmp + 31) // 32
+    print(f"config 1: CLI {n_cli} frames, oracle {len(ref_codes)} frames; {same_chunks}/{total_chunks} chunks >= 40 dB "
+          f"(min {min(snrs) if snrs else float('nan'):.1f} dB)")
+    assert same_chunks >= 1, "not even the first 32-frame chunk of the CLI's WAV matches the oracle"
+    assert same_chunks >= 0.5 * total_chunks, "the CLI's trajectory left the oracle's in the first half of the utterance"
+
+
+def test_corrupt_gguf_files_fail_cleanly(B, tiny_model_path, tmp_path):
+    """Round-1 advisor finding: the loader trusted the file.  Truncated tables, absurd counts, zero alignment, wrong tensor
+    shapes must all produce an error (never a crash or an out-of-bounds device read)."""
+    raw = bytearray(open(tiny_model_path, "rb").read())
+
+    def attempt(data, name):
+        p = str(tmp_path / name)
+        open(p, "wb").write(bytes(data))
+        with pytest.raises(B.MagpieError):
+            B.Model(p, 0, B.PREC_F32)
+
+    attempt(raw[:1000], "truncated_meta.gguf")
+    attempt(raw[:len(raw) // 2], "truncated_data.gguf")
+    bad = bytearray(raw); bad[8:16] = struct.pack("<Q", 1 << 60); attempt(bad, "huge_tensor_count.gguf")
+    bad = bytearray(raw); bad[16:24] = struct.pack("<Q", 1 << 61); attempt(bad, "huge_kv_count.gguf")
+    # a tensor with a wrong shape: rewrite the file with the hyper-parameter d_ffn changed but the tensors kept
+    from gguf import GGUFReader
+    r = GGUFReader(tiny_model_path)
+    f = r.fields["magpie.d_ffn"]
+    off = int(f.offset) + sum(int(p.nbytes) for p in f.parts[:-1])
+    bad = bytearray(raw)
+    old = struct.unpack("<I", bad[off:off + 4])[0]
+    assert old == int(f.parts[-1][0])
+    bad[off:off + 4] = struct.pack("<I", old * 2)
+    attempt(bad, "wrong_ffn_shape.gguf")

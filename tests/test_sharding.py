@@ -67,3 +67,44 @@ def test_multi_gpu_synthesizer_matches_single_session(tiny_model_path, oracle_mo
     for i, u in enumerate(utts):
         ref = o.synthesize(u, speaker=[0, 1, 0][i], temperature=0.0, max_steps=10)
         assert out[i].shape == ref.shape and np.mean(np.all(out[i] == ref, axis=1)) >= 0.99
+
+
+def test_pool_fails_loudly_without_a_device(tiny_model_path):
+    """The in-process pool has no CPU fallback either."""
+    import torch
+    from magpie_tts_cpp_b200 import binding
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(binding.MagpieError, match="no CUDA device"):
+        binding.Pool(tiny_model_path)
+    with pytest.raises(binding.MagpieError):
+        binding.Pool(tiny_model_path, devices=[0, 1])
+
+
+@pytest.mark.gpu
+def test_inprocess_pool_matches_oracle_and_single_session(tiny_model_path, oracle_mod):
+    """mgb_pool_* (C++: one replica + one submission thread + one stream per device slot, utterance i on slot i mod G).  Two
+    slots on device 0 exercise the sharding, threading and scatter logic on a one-GPU box; results must equal the oracle's and
+    a plain single-session run, in utterance order."""
+    from magpie_tts_cpp_b200 import binding
+    utts = [HELLO, HELLO[:9] + [2379], HELLO[:5] + [2379], [2378, 3, 4, 2379], HELLO[:12] + [2379]]
+    spk = [0, 1, 0, 1, 0]
+    pool = binding.Pool(tiny_model_path, devices=[0, 0], precision=binding.PREC_F32)
+    assert pool.n_devices == 2
+    out = pool.generate(utts, speakers=spk, max_steps=10)
+    o = oracle_mod.OracleModel(tiny_model_path)
+    for i, u in enumerate(utts):
+        ref = o.synthesize(u, speaker=spk[i], temperature=0.0, max_steps=10)
+        assert out[i].shape == ref.shape and np.mean(np.all(out[i] == ref, axis=1)) >= 0.99
+    assert (pool.last_device_ms > 0).all()
+    codes = np.random.default_rng(3).integers(0, 2016, (len(utts), 6, 8)).astype(np.int32)
+    gr = pool.teacher_forced(utts, codes, speakers=spk)
+    m = binding.Model(tiny_model_path, 0, binding.PREC_F32)
+    s = m.session(batch=len(utts), max_text=16)
+    s.encode_text(utts, want_output=False)
+    s.prefill(spk)
+    _, _, gr1 = s.teacher_forced(codes, want_hidden=False, want_logits=False)
+    assert np.mean(gr == gr1) >= 0.99
+    with pytest.raises(binding.MagpieError):
+        pool.generate([list(range(5000))], max_steps=4)          # text longer than the encoder position table
+    pool.close()
