@@ -158,11 +158,18 @@ static void round_activation(const float * x, float * y, int n, int act) {
     }
 }
 
+/* ggml-CPU's mul_mat rounds the ACTIVATION row to the weight's storage type before the dot (f16 / Q8_0 blocks).  The switch
+ * below turns that rounding off (weights still dequantised exactly), which isolates the WEIGHT format from ggml's activation
+ * noise: the product keeps f32 activations, so against this mode it is held to the plain f32 / bf16 bars, while its distance
+ * to the full ggml semantics is reported separately (tests/test_gpu_parity.py::test_quantised_gguf_weights_match_oracle). */
+static int g_activation_rounding = 1;
+ORC_API void orc_set_activation_rounding(int on) { g_activation_rounding = on; }
+
 /* Y[t][n] = sum_k W[n][k] X[t][k] (+bias[n]);  ggml_mul_mat(W, X).  ldx/ldy are row strides. */
 static void linear(const mat_t * W, const float * bias, const float * X, int ldx, float * Y, int ldy,
                    int T, int N, int K) {
     float * Xr = (float *)X; int ldr = ldx; float * tmp = NULL;
-    if (W->act != ACT_F32) {
+    if (W->act != ACT_F32 && g_activation_rounding) {
         tmp = (float *)malloc((size_t)T * K * sizeof(float));
         for (int t = 0; t < T; t++) round_activation(X + (size_t)t * ldx, tmp + (size_t)t * K, K, W->act);
         Xr = tmp; ldr = K;

@@ -94,6 +94,7 @@ def lib():
     L.orc_gelu.restype = C.c_float
     L.orc_gelu.argtypes = [C.c_float, C.c_int]
     L.orc_num_threads.restype = C.c_int
+    L.orc_set_activation_rounding.argtypes = [C.c_int]
     L.orc_set_num_threads.argtypes = [C.c_int]
     _lib = L
     return L
@@ -329,6 +330,11 @@ def layer_norm(x, w, eps=1e-5):
 
 def gelu(x: float, table=True) -> float:
     return float(lib().orc_gelu(float(x), int(table)))
+
+
+def set_activation_rounding(on: bool):
+    """ggml-CPU mul_mat rounds the activation row to the weight's storage type (f16 / Q8_0 blocks); off = weights only."""
+    lib().orc_set_activation_rounding(int(on))
 
 
 def num_threads() -> int:

@@ -256,31 +256,65 @@ def test_full_model_teacher_forced_bf16(B, full_model_path, full_oracle):
     print(f"bf16 greedy code agreement vs f32 oracle: {agree:.3f}")
 
 
-@pytest.mark.parametrize("kind,tol", [("model-f16", 1e-2), ("model-q8", 6e-2)])
-def test_quantised_gguf_weights_match_oracle(B, fx, oracle_mod, kind, tol):
-    """F16 and Q8_0 GGUF files (BASELINE configs[4]): the loader dequantises the blocks exactly; the
-    oracle reproduces ggml-CPU's mul_mat, which additionally rounds the ACTIVATION row to f16 / Q8_0 blocks before each dot
-    (SURVEY.md 8c item 4).  The product keeps f32 activations, so the comparison bar is that rounding noise (f16: 2^-11
-    relative per element; Q8_0: 1/254 of the block maximum, measured 5 % of the logit rms after the LT), not the f32 bar."""
+@pytest.mark.parametrize("kind,ggml_tol", [("model-f16", 1e-2), ("model-q8", 6e-2)])
+def test_quantised_gguf_weights_match_oracle(B, fx, oracle_mod, kind, ggml_tol):
+    """F16 and Q8_0 GGUF files (BASELINE configs[4]).  Two comparisons:
+    (1) WEIGHT FORMAT: the oracle with the same exactly-dequantised weights and f32 activations (activation rounding off) --
+        the product computes precisely that, so it is held to the plain bars: 1e-4 in f32 (GELU table off), 2e-2 in bf16, the
+        latter with the Q8_0 matrices consumed as int8 + f16 scale inside the kernels where the path supports it;
+    (2) ggml-CPU SEMANTICS: ggml's mul_mat additionally rounds the ACTIVATION row to f16 / Q8_0 blocks before each dot
+        (SURVEY.md 8c item 4).  That is noise of the reference's CPU kernels, not of the file format; the distance to it is
+        bounded at the noise level itself (f16: 2^-11 relative per element; Q8_0: 1/254 of the block maximum, ~5 % of the logit
+        rms after the LT) and reported."""
     path = fx.ensure_fixture(kind)
-    fo = _full_oracle(oracle_mod, path, True)
+    oracle_mod.set_activation_rounding(False)
+    try:
+        o = oracle_mod.OracleModel(path)
+        o.set_gelu_table(False)
+        enc_w = o.encode_text(HELLO)
+        rng = np.random.default_rng(42)
+        codes = rng.integers(0, 2016, (12, 8)).astype(np.int32)
+        st = o.new_state(enc_w, 0)
+        prev = np.full(8, o.hp["audio_bos_id"], np.int32)
+        hid_w, lg_w = [], []
+        for t in range(12):
+            h = st.step(prev)
+            _, _, lg = o.lt_sample(h, 0.0, 80, forced_codes=codes[t])
+            hid_w.append(h); lg_w.append(lg); prev = codes[t]
+        hid_w, lg_w = np.stack(hid_w), np.stack(lg_w)
+    finally:
+        oracle_mod.set_activation_rounding(True)
+    fo = _full_oracle(oracle_mod, path, True)                 # full ggml-CPU semantics (activation rounding + GELU table)
     m = B.Model(path, 0, B.PREC_F32)
+    m.set_gelu_f16(False)
     s = m.session(batch=2, max_text=32)
     enc = s.encode_text([HELLO, HELLO])
-    close(enc[0], fo["enc"], tol)
+    close(enc[0], enc_w, 1e-4)
     s.prefill([0, 0])
-    hid, lg, gr = s.teacher_forced(np.stack([fo["codes"], fo["codes"]]))
-    close(hid[0], fo["hid"], tol)
-    close(lg[0], fo["lg"], tol)
+    hid, lg, gr = s.teacher_forced(np.stack([codes, codes]))
+    close(hid[0], hid_w, 1e-4)
+    close(lg[0], lg_w, 1e-4)
     np.testing.assert_array_equal(gr[0], gr[1])
-    # the same file in bf16 compute (weights dequantised, then rounded to bf16)
+    m.set_gelu_f16(True)
+    s.encode_text([HELLO, HELLO], want_output=False)
+    s.prefill([0, 0])
+    hid_t, lg_t, _ = s.teacher_forced(np.stack([fo["codes"], fo["codes"]]))
+    close(hid_t[0], fo["hid"], ggml_tol)
+    close(lg_t[0], fo["lg"], ggml_tol)
+    d = np.abs(lg_t[0][np.isfinite(fo["lg"])] - fo["lg"][np.isfinite(fo["lg"])]).max() / np.sqrt(np.mean(fo["lg"][np.isfinite(fo["lg"])] ** 2))
+    print(f"{kind}: max logit distance to the ggml-CPU semantics (activation rounding on) = {d:.3e} of the logit rms")
+    s.close(); m.close()
+    # the same file in bf16 compute, batch 1 (frame loop) and batched
     mb = B.Model(path, 0, B.PREC_BF16)
-    sb = mb.session(batch=1, max_text=32)
-    sb.encode_text([HELLO], want_output=False)
-    sb.prefill([0])
-    hid_b, lg_b, _ = sb.teacher_forced(fo["codes"][None])
-    close(hid_b[0], fo["hid"], max(tol, 2e-2))
-    close(lg_b[0], fo["lg"], max(tol, 2e-2))
+    for nb in (1, 3):
+        sb = mb.session(batch=nb, max_text=32)
+        sb.encode_text([HELLO] * nb, want_output=False)
+        sb.prefill([0] * nb)
+        hid_b, lg_b, _ = sb.teacher_forced(np.repeat(codes[None], nb, axis=0))
+        close(hid_b[nb - 1], hid_w, 2e-2)
+        close(lg_b[nb - 1], lg_w, 2e-2)
+        sb.close()
+    mb.close()
 
 
 def _bf16_b1_run(m, codes, monkeypatch, env):
