@@ -98,6 +98,13 @@ MGB_API int32_t      mgb_model_meta_u32(const mgb_model * m, const char * key, i
  * max_text: capacity of encoder tokens per utterance; max_seq: KV slots per utterance
  * (reference uses context_frames + max_dec_steps + 16, magpie.cpp:4077; pass 0 for that). */
 MGB_API mgb_session * mgb_session_new(mgb_model * m, int batch, int max_text, int max_seq);
+/* Same, with an explicit page pool for the decoder self-attention cache: the cache is PAGED (pages of 128 positions, one page
+ * table per utterance read by the attention kernels; the reference allocates one contiguous [12][max_seq][768] slab per call,
+ * magpie.cpp:3315-3376).  kv_pages = 0 reserves ceil(max_seq / 128) pages per utterance up front (what mgb_session_new does);
+ * kv_pages > 0 sizes the pool to that many pages shared by all utterances, handed out on demand as utterances grow and returned
+ * when they finish (mgb_generate_queue) -- ragged batches then need memory for the frames they really produce. */
+MGB_API mgb_session * mgb_session_new_paged(mgb_model * m, int batch, int max_text, int max_seq, int kv_pages);
+MGB_API int           mgb_session_kv_pages(const mgb_session * s, int32_t * total, int32_t * in_use);
 MGB_API void          mgb_session_free(mgb_session * s);
 MGB_API int           mgb_session_batch(const mgb_session * s);
 MGB_API int           mgb_session_max_seq(const mgb_session * s);
@@ -145,6 +152,18 @@ MGB_API int mgb_lt_sample(mgb_session * s, const float * hidden, float temperatu
 MGB_API int mgb_generate(mgb_session * s, int max_steps, float temperature, int top_k,
                          const float * uniforms /*[B][max_steps][8] or NULL*/, uint64_t seed,
                          int ignore_eos, int32_t * codes_out, int32_t * n_frames_out, float * hidden_out);
+
+/* Continuous batching (BASELINE configs[3]/[4] with EOS enabled): n_utt utterances (n_utt >= the session's batch B) are streamed
+ * through the B slots of the session.  Every step runs all B slots; a slot whose utterance hit EOS (magpie.cpp:4341-4352) or its
+ * frame limit is retired at the next poll (every 8 steps): its codes are copied out, its cache pages go back to the pool and the
+ * slot is refilled from the queue (text encoder + cross K/V + 110-frame prefill of that slot only), so the batch stays full and
+ * the loop runs about sum(frames) / B steps instead of (n_utt / B) x max(frames).
+ *   tokens [n_utt][max_text] (padded; max_text <= the session's), n_tokens / speakers [n_utt],
+ *   max_steps_per_utt [n_utt] or NULL (= max_steps): per-utterance frame limits (ragged requests),
+ *   codes_out [n_utt][max_steps][8], n_frames_out [n_utt], steps_run_out (optional): decoder steps the loop executed. */
+MGB_API int mgb_generate_queue(mgb_session * s, int n_utt, const int32_t * tokens, const int32_t * n_tokens, int max_text,
+                               const int32_t * speakers, const int32_t * max_steps_per_utt, int max_steps, float temperature,
+                               int top_k, uint64_t seed, int32_t * codes_out, int32_t * n_frames_out, int64_t * steps_run_out);
 
 /* Teacher-forced run (BASELINE config 2): feeds BOS then codes_in [B][T][8]; outputs per step the
  * decoder hidden [B][T][d_model] (optional), the 8 masked LT logit vectors [B][T][8][V] (optional)

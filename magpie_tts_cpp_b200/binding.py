@@ -38,7 +38,7 @@ SYMBOLS = [
     "mgb_model_load", "mgb_model_free", "mgb_model_get_hparams", "mgb_model_set_max_dec_steps",
     "mgb_model_set_gelu_f16", "mgb_model_precision", "mgb_model_device", "mgb_model_step_weight_bytes",
     "mgb_model_meta_str", "mgb_model_meta_u32",
-    "mgb_session_new", "mgb_session_free", "mgb_session_batch", "mgb_session_max_seq", "mgb_session_positions",
+    "mgb_session_new", "mgb_session_new_paged", "mgb_session_kv_pages", "mgb_generate_queue", "mgb_session_free", "mgb_session_batch", "mgb_session_max_seq", "mgb_session_positions",
     "mgb_encode_text", "mgb_prefill", "mgb_decoder_step", "mgb_final_proj", "mgb_lt_sample",
     "mgb_generate", "mgb_teacher_forced", "mgb_session_last_loop_ms", "mgb_session_last_loop_launches",
     "mgb_session_debug_stamps",
@@ -91,6 +91,10 @@ def lib():
     L.mgb_session_new.restype = vp
     L.mgb_session_new.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     L.mgb_session_free.argtypes = [vp]
+    L.mgb_session_new_paged.restype = vp
+    L.mgb_session_new_paged.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.mgb_session_kv_pages.argtypes = [vp, vp, vp]
+    L.mgb_generate_queue.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp, vp, C.c_int, C.c_float, C.c_int, C.c_uint64, vp, vp, vp]
     L.mgb_session_batch.argtypes = [vp]
     L.mgb_session_max_seq.argtypes = [vp]
     L.mgb_session_positions.argtypes = [vp, vp]
@@ -200,16 +204,16 @@ class Model:
     def meta_u32(self, key: str, default: int = -1) -> int:
         return int(lib().mgb_model_meta_u32(self._h, key.encode(), default))
 
-    def session(self, batch: int = 1, max_text: int = 128, max_seq: int = 0) -> "Session":
-        return Session(self, batch, max_text, max_seq)
+    def session(self, batch: int = 1, max_text: int = 128, max_seq: int = 0, kv_pages: int = 0) -> "Session":
+        return Session(self, batch, max_text, max_seq, kv_pages)
 
 
 class Session:
     """Device state of `batch` independent utterances (KV caches, positions)."""
 
-    def __init__(self, model: Model, batch: int, max_text: int, max_seq: int = 0):
+    def __init__(self, model: Model, batch: int, max_text: int, max_seq: int = 0, kv_pages: int = 0):
         self.model = model
-        self._h = lib().mgb_session_new(model._h, int(batch), int(max_text), int(max_seq))
+        self._h = lib().mgb_session_new_paged(model._h, int(batch), int(max_text), int(max_seq), int(kv_pages))
         if not self._h:
             raise _err("mgb_session_new")
         self.B = batch
@@ -296,6 +300,33 @@ class Session:
                                 int(ignore_eos), _p(codes), _p(n), _p(hid)), "magpie_synthesize_codes")
         out = [codes[b, :n[b]].copy() for b in range(self.B)]
         return (out, hid) if want_hidden else out
+
+    @property
+    def kv_pages(self):
+        """(pages in the pool, pages currently assigned to utterances) of the paged self-attention cache."""
+        t, u = C.c_int32(0), C.c_int32(0)
+        _chk(lib().mgb_session_kv_pages(self._h, C.byref(t), C.byref(u)), "kv_pages")
+        return int(t.value), int(u.value)
+
+    def generate_queue(self, token_lists, speakers=None, max_steps=0, max_steps_per_utt=None, temperature=0.0, top_k=80, seed=0):
+        """Continuous batching: len(token_lists) >= B utterances streamed through the B slots.  Returns (codes list, steps run)."""
+        hp = self.model.hp
+        n = len(token_lists)
+        T = max_steps if max_steps > 0 else hp["max_dec_steps"]
+        mt = max(len(t) for t in token_lists)
+        tok = np.zeros((n, mt), np.int32)
+        nt = np.zeros(n, np.int32)
+        for i, t in enumerate(token_lists):
+            tok[i, :len(t)] = t
+            nt[i] = len(t)
+        spk = _i32(speakers) if speakers is not None else None
+        lim = _i32(max_steps_per_utt) if max_steps_per_utt is not None else None
+        codes = np.zeros((n, T, 8), np.int32)
+        nf = np.zeros(n, np.int32)
+        steps = C.c_int64(0)
+        _chk(lib().mgb_generate_queue(self._h, n, _p(tok), _p(nt), mt, _p(spk), _p(lim), int(T), float(temperature), int(top_k),
+                                      C.c_uint64(seed), _p(codes), _p(nf), C.byref(steps)), "mgb_generate_queue")
+        return [codes[i, :nf[i]].copy() for i in range(n)], int(steps.value)
 
     def teacher_forced(self, codes_in, want_hidden=True, want_logits=True, want_greedy=True):
         hp = self.model.hp

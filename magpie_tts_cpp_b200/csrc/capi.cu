@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <exception>
+#include <functional>
 #include <memory>
 #include <string>
 #include <vector>
@@ -47,6 +48,8 @@ struct Session {
     int32_t * d_forced = nullptr; float * d_uniforms = nullptr;              // [B][8] single-shot
     float * d_logits1 = nullptr;       // [B][8][V] single-shot
     std::vector<int32_t> h_ntext, h_enc_off;
+    std::vector<int32_t> h_speakers;
+    std::vector<int> enc_slots;        // slots the resident encoder output belongs to (list order = compact row order)
     int M_enc = 0;
     int pos = 0;                       // host mirror of the (uniform) decode position
     int attn_split = 0;                // batched decoder step: CTAs per (head, utterance) in the self-attention (long KV, few utterances)
@@ -68,6 +71,18 @@ struct Session {
     void * lt_scratch = nullptr; size_t lt_scratch_bytes = 0;     // batched local transformer: activation scratch
     int prefill_len = 0;                                            // > 0 while mgb_prefill runs decoder_layers on the context frames
     float * fold_xm = nullptr, * fold_xn = nullptr; bool fold_ready = false;     // batched decode: folded cross-attention tables [L][B][max_text][d]
+    // paged decoder self-attention cache: per layer a pool of n_pages pages of kKvPageRows rows; utterance b's cache position j
+    // lives in row page_table[b][j / 128] * 128 + j % 128.  Pages are handed out lowest id first (a one-utterance session therefore
+    // always holds pages 0, 1, 2, ... = contiguous rows, which the batch-1 persistent kernels rely on) and returned when an
+    // utterance is retired (mgb_generate_queue).
+    int max_pages = 0, n_pages = 0; size_t kv_rows = 0;
+    int32_t * d_page_table = nullptr;          // [B][max_pages]
+    std::vector<int32_t> h_pt;                 // host mirror
+    std::vector<int> utt_pages;                // pages held by each utterance
+    std::vector<int32_t> free_pages;           // min-heap of free page ids
+    bool pt_dirty = false; bool pages_on_demand = false;
+    // per-utterance loop state (continuous batching): steps emitted so far / 1 while the slot is generating
+    int32_t * d_utt_step = nullptr, * d_active = nullptr;
 
     ~Session() {
         if (m) cudaSetDevice(m->device);
@@ -95,11 +110,51 @@ static bool grow(void ** p, size_t * cap, size_t bytes) {
     return true;
 }
 
+// ---- paged K / V cache -------------------------------------------------------------------------------
+static bool ensure_pages(Session & s, int b, int rows) {          // utterance b must be able to hold cache positions [0, rows)
+    const int need = (rows + kKvPageRows - 1) / kKvPageRows;
+    if (need > s.max_pages) { set_error("KV cache: utterance exceeds the session's max_seq"); return false; }
+    while (s.utt_pages[b] < need) {
+        if (s.free_pages.empty()) { set_error("KV cache: page pool exhausted (create the session with more kv_pages)"); return false; }
+        std::pop_heap(s.free_pages.begin(), s.free_pages.end(), std::greater<int32_t>());
+        const int32_t pg = s.free_pages.back(); s.free_pages.pop_back();
+        s.h_pt[(size_t)b * s.max_pages + s.utt_pages[b]++] = pg;
+        s.pt_dirty = true;
+    }
+    return true;
+}
+static void release_pages(Session & s, int b) {
+    for (int i = 0; i < s.utt_pages[b]; i++) {
+        s.free_pages.push_back(s.h_pt[(size_t)b * s.max_pages + i]);
+        std::push_heap(s.free_pages.begin(), s.free_pages.end(), std::greater<int32_t>());
+        s.h_pt[(size_t)b * s.max_pages + i] = 0;
+    }
+    s.utt_pages[b] = 0; s.pt_dirty = true;
+}
+static bool flush_page_table(Session & s) {
+    if (!s.pt_dirty) return true;
+    MGB_CUDA_TRY(cudaMemcpyAsync(s.d_page_table, s.h_pt.data(), s.h_pt.size() * 4, cudaMemcpyHostToDevice, s.stream));
+    s.pt_dirty = false;
+    return true;
+}
+static bool ensure_pages_all(Session & s, int rows) {
+    for (int b = 0; b < s.B; b++) if (!ensure_pages(s, b, rows)) return false;
+    return flush_page_table(s);
+}
+// the batch-1 persistent kernels address the cache as contiguous rows: true if utterance 0 holds pages 0, 1, 2, ...
+static bool pages_contiguous(const Session & s, int rows) {
+    const int need = (rows + kKvPageRows - 1) / kKvPageRows;
+    if (s.utt_pages[0] < need) return false;
+    for (int i = 0; i < need; i++) if (s.h_pt[i] != i) return false;
+    return true;
+}
+static inline int32_t cache_row(const Session & s, int b, int j) { return s.h_pt[(size_t)b * s.max_pages + j / kKvPageRows] * kKvPageRows + j % kKvPageRows; }
+
 // ---- shared layer drivers -------------------------------------------------------------------------
 static bool decoder_layers(Session & s, Tokens tok, bool want_hidden) {
     Model & m = *s.m; const mgb_hparams & hp = m.hp;
     const int d = hp.d_model, dxa = hp.dec_xa_heads * hp.dec_xa_d_head, M = tok.M;
-    const size_t kv_layer = (size_t)s.B * s.max_seq * d * m.wsize, xkv_layer = (size_t)s.B * s.max_text * dxa * m.wsize;
+    const size_t kv_layer = s.kv_rows * d * m.wsize, xkv_layer = (size_t)s.B * s.max_text * dxa * m.wsize;
     for (int l = 0; l < hp.dec_layers; l++) {
         const DecLayer & L = m.dec[l];
         char * kl = (char *)s.kc + l * kv_layer, * vl = (char *)s.vc + l * kv_layer;
@@ -114,7 +169,8 @@ static bool decoder_layers(Session & s, Tokens tok, bool want_hidden) {
         o.tc_scratch = s.tc_scratch; o.tc_scratch_bytes = s.tc_scratch_bytes;
         o.precision = m.precision; o.M = M; o.W = L.o; o.X = s.attn; o.ldx = d; o.res = s.x; o.ldr = d; o.Y = s.x; o.ldy = d;
         AttnArgs at;
-        at.precision = m.precision; at.q = s.qbuf; at.ldq = d; at.K = kl; at.V = vl; at.rows_per_utt = s.max_seq;
+        at.precision = m.precision; at.q = s.qbuf; at.ldq = d; at.K = kl; at.V = vl; at.rows_per_utt = 0;
+        at.page_table = s.d_page_table; at.max_pages = s.max_pages;
         at.H = hp.dec_sa_heads; at.dh = d / hp.dec_sa_heads; at.causal = 1; at.tok = tok; at.out = s.attn; at.ldo = d;
         at.prefill_len = s.prefill_len;
         // batched decoder step on the tensor-core path: the attention kernel writes the O-projection's packed input itself
@@ -167,20 +223,30 @@ static bool decoder_layers(Session & s, Tokens tok, bool want_hidden) {
     return true;
 }
 
-__global__ void advance_kernel(int32_t * pos, int32_t * slot, int B, int32_t * step) {
+// after a step: position + 1 and the cache row of the NEXT position from the page table; with an `active` mask (continuous
+// batching) retired / finished slots stay where they are (they keep being computed, their rows are rewritten in place)
+__global__ void advance_kernel(int32_t * pos, int32_t * slot, int B, int32_t * step, const int32_t * page_table, int max_pages,
+                               const int32_t * active, int32_t * utt_step) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < B) { pos[i] += 1; slot[i] += 1; }
+    if (i < B && (!active || active[i])) {
+        const int np = pos[i] + 1;
+        pos[i] = np;
+        const int pg = np / kKvPageRows;        // (one past the last position of a full cache: no page, the row is never used)
+        slot[i] = pg < max_pages ? page_table[(size_t)i * max_pages + pg] * kKvPageRows + np % kKvPageRows : 0;
+        if (utt_step) utt_step[i] += 1;
+    }
     if (i == 0 && step) *step += 1;
 }
 
 __global__ void step_inc_kernel(int32_t * step) { *step += 1; }
 
-static bool launch_advance(Session & s, bool with_step) {
+static bool launch_advance(Session & s, bool with_step, bool per_utt = false) {
     if (s.mega_grid > 0) {           // the megakernel advances pos/slot itself
         if (with_step) { step_inc_kernel<<<1, 1, 0, s.stream>>>(s.d_step); MGB_LAUNCH_CHECK(); }
         return true;
     }
-    advance_kernel<<<(s.B + 127) / 128, 128, 0, s.stream>>>(s.dec_pos, s.dec_slot, s.B, with_step ? s.d_step : nullptr);
+    advance_kernel<<<(s.B + 127) / 128, 128, 0, s.stream>>>(s.dec_pos, s.dec_slot, s.B, with_step ? s.d_step : nullptr, s.d_page_table,
+                                                            s.max_pages, per_utt ? s.d_active : nullptr, per_utt ? s.d_utt_step : nullptr);
     MGB_LAUNCH_CHECK();
     return true;
 }
@@ -198,7 +264,7 @@ static bool decoder_step_mega(Session & s) {
     for (int cb = 0; cb < 8; cb++) p.audio_emb[cb] = m.audio_emb[cb];
     p.dec_pos = m.dec_pos; p.norm_out = m.dec_norm_out; p.codes = s.d_codes;
     p.pos = s.dec_pos; p.pos_rw = s.dec_pos; p.slot_rw = s.dec_slot;
-    p.kcache = s.kc; p.vcache = s.vc; p.kv_layer_stride = (size_t)s.B * s.max_seq * hp.d_model;
+    p.kcache = s.kc; p.vcache = s.vc; p.kv_layer_stride = s.kv_rows * hp.d_model;
     p.xk = s.xk; p.xv = s.xv; p.xkv_layer_stride = (size_t)s.B * s.max_text * p.dxa; p.n_ctx = s.d_ntext;
     p.x = s.x; p.q = s.qbuf; p.attn_part = s.attn_part; p.xq = s.xq; p.ffh = s.ffh; p.hidden = s.hidden;
     p.barrier = s.d_barrier; p.dbg = s.d_dbg;
@@ -275,6 +341,10 @@ int32_t mgb_model_meta_u32(const mgb_model * m, const char * key, int32_t def) {
 }
 
 mgb_session * mgb_session_new(mgb_model * mm, int batch, int max_text, int max_seq) {
+    return mgb_session_new_paged(mm, batch, max_text, max_seq, 0);
+}
+
+mgb_session * mgb_session_new_paged(mgb_model * mm, int batch, int max_text, int max_seq, int kv_pages) {
     Model * m = reinterpret_cast<Model *>(mm);
     if (!m || batch <= 0 || max_text <= 0) { set_error("mgb_session_new: invalid arguments"); return nullptr; }
     const mgb_hparams & hp = m->hp;
@@ -296,7 +366,18 @@ mgb_session * mgb_session_new(mgb_model * mm, int batch, int max_text, int max_s
               s->alloc(s->xatt, M * dxa) && s->alloc(s->ffh, M * hp.d_ffn) && s->alloc(s->hidden, (size_t)batch * d) &&
               s->alloc(s->enc_out, (size_t)batch * max_text * d);
     char * p = nullptr;
-    const size_t kvb = (size_t)L * batch * max_seq * d * m->wsize, xkvb = (size_t)L * batch * max_text * dxa * m->wsize;
+    // paged self-attention cache: kv_pages = 0 reserves max_seq rows for every utterance (all pages assigned up front, utterance b
+    // holding the contiguous pages b * max_pages ...); kv_pages > 0 sizes the pool explicitly and pages are assigned on demand
+    s->max_pages = (max_seq + kKvPageRows - 1) / kKvPageRows;
+    s->pages_on_demand = kv_pages > 0;
+    s->n_pages = kv_pages > 0 ? kv_pages : batch * s->max_pages;
+    if (s->n_pages < batch * ((hp.context_frames + 2 + kKvPageRows - 1) / kKvPageRows)) { set_error("mgb_session_new_paged: kv_pages cannot hold the context frames of every utterance"); return nullptr; }
+    s->kv_rows = (size_t)s->n_pages * kKvPageRows;
+    s->h_pt.assign((size_t)batch * s->max_pages, 0);
+    s->utt_pages.assign(batch, 0);
+    for (int pg = 0; pg < s->n_pages; pg++) s->free_pages.push_back(pg);
+    std::make_heap(s->free_pages.begin(), s->free_pages.end(), std::greater<int32_t>());
+    const size_t kvb = (size_t)L * s->kv_rows * d * m->wsize, xkvb = (size_t)L * batch * max_text * dxa * m->wsize;
     const size_t ekb = (size_t)batch * max_text * d * m->wsize;
     ok = ok && s->alloc(p, kvb); s->kc = p; ok = ok && s->alloc(p, kvb); s->vc = p;
     ok = ok && s->alloc(p, xkvb); s->xk = p; ok = ok && s->alloc(p, xkvb); s->xv = p;
@@ -306,8 +387,13 @@ mgb_session * mgb_session_new(mgb_model * mm, int batch, int max_text, int max_s
          s->alloc(s->d_ntext, batch) && s->alloc(s->d_speakers, batch) && s->alloc(s->d_codes, (size_t)batch * 8) &&
          s->alloc(s->d_sampled, (size_t)batch * 8) && s->alloc(s->d_argmax, (size_t)batch * 8) && s->alloc(s->d_step, 1) &&
          s->alloc(s->d_done, batch) && s->alloc(s->d_forbid, batch) && s->alloc(s->d_forced, (size_t)batch * 8) &&
-         s->alloc(s->d_uniforms, (size_t)batch * 8) && s->alloc(s->d_logits1, (size_t)batch * 8 * V);
+         s->alloc(s->d_uniforms, (size_t)batch * 8) && s->alloc(s->d_logits1, (size_t)batch * 8 * V) &&
+         s->alloc(s->d_page_table, (size_t)batch * s->max_pages) && s->alloc(s->d_utt_step, batch) && s->alloc(s->d_active, batch);
     if (!ok) return nullptr;
+    if (!s->pages_on_demand)
+        for (int b = 0; b < batch; b++) if (!ensure_pages(*s, b, max_seq)) return nullptr;
+    s->pt_dirty = true;
+    if (!flush_page_table(*s) || cudaStreamSynchronize(s->stream) != cudaSuccess) { set_error("mgb_session_new: page table upload failed"); return nullptr; }
     if (m->precision == MGB_PREC_BF16 && s->Mcap >= 16 && m->dec.size() && m->dec[0].qkv.tiles) {
         const size_t tb = tc_scratch_bytes(s->Mcap, std::max(hp.d_ffn, hp.d_model));
         char * tp = nullptr;
@@ -368,6 +454,13 @@ mgb_session * mgb_session_new(mgb_model * mm, int batch, int max_text, int max_s
 }
 
 void mgb_session_free(mgb_session * s) { delete reinterpret_cast<Session *>(s); }
+int mgb_session_kv_pages(const mgb_session * ss, int32_t * total, int32_t * in_use) {
+    const Session * s = reinterpret_cast<const Session *>(ss);
+    if (!s) return MGB_EINVAL;
+    if (total) *total = s->n_pages;
+    if (in_use) *in_use = s->n_pages - (int)s->free_pages.size();
+    return MGB_OK;
+}
 int mgb_session_batch(const mgb_session * s) { return s ? reinterpret_cast<const Session *>(s)->B : MGB_EINVAL; }
 int mgb_session_max_seq(const mgb_session * s) { return s ? reinterpret_cast<const Session *>(s)->max_seq : MGB_EINVAL; }
 int mgb_session_positions(const mgb_session * ss, int32_t * pos_out) {
@@ -388,20 +481,27 @@ int mgb_session_debug_stamps(mgb_session * ss, uint64_t * out, int n) {
 float mgb_session_last_loop_ms(const mgb_session * s) { return s ? reinterpret_cast<const Session *>(s)->last_ms : 0.0f; }
 int64_t mgb_session_last_loop_launches(const mgb_session * s) { return s ? reinterpret_cast<const Session *>(s)->last_launches : 0; }
 
-int mgb_encode_text(mgb_session * ss, const int32_t * tokens, const int32_t * n_tokens, float * enc_out) {
-    Session * s = reinterpret_cast<Session *>(ss);
-    if (!check_ready(s, false)) return MGB_EINVAL;
-    if (!tokens || !n_tokens) { set_error("magpie_encode_text: null tokens"); return MGB_EINVAL; }
+}  // extern "C"
+
+namespace mgb {
+
+// Text encoder for the utterances in `slots` (session slot ids, ascending); tokens[i] / n_tokens[i] belong to slots[i].  The
+// compact encoder output rows of exactly these utterances are left in s->enc_out (offsets h_enc_off by list position) and the
+// tok_* maps describe them, for the prefill that follows.  enc_out (optional, host): [len(slots)][max_text][d].
+static int encode_slots(Session * s, const std::vector<int> & slots, const int32_t * const * tokens, const int32_t * n_tokens, float * enc_out) {
     Model & m = *s->m; const mgb_hparams & hp = m.hp; const int d = hp.d_model;
     std::vector<int32_t> utt, pos, slot, tok;
-    s->h_ntext.assign(n_tokens, n_tokens + s->B);
-    s->h_enc_off.assign(s->B + 1, 0);
-    for (int b = 0; b < s->B; b++) {
-        const int n = n_tokens[b];
+    const int ns = (int)slots.size();
+    if ((int)s->h_ntext.size() != s->B) s->h_ntext.assign(s->B, 1);
+    s->h_enc_off.assign(ns + 1, 0);
+    s->enc_slots = slots;
+    for (int i = 0; i < ns; i++) {
+        const int b = slots[i], n = n_tokens[i];
         if (n <= 0 || n > s->max_text) { set_error("magpie_encode_text: token count out of range"); return MGB_EINVAL; }
-        s->h_enc_off[b + 1] = s->h_enc_off[b] + n;
+        s->h_ntext[b] = n;
+        s->h_enc_off[i + 1] = s->h_enc_off[i] + n;
         for (int t = 0; t < n; t++) {
-            const int32_t id = tokens[(size_t)b * s->max_text + t];
+            const int32_t id = tokens[i][t];
             if (id < 0 || id >= hp.text_vocab_size) { set_error("magpie_encode_text: token id out of range"); return MGB_EINVAL; }
             utt.push_back(b); pos.push_back(t); slot.push_back(b * s->max_text + t); tok.push_back(id);
         }
@@ -445,31 +545,54 @@ int mgb_encode_text(mgb_session * ss, const int32_t * tokens, const int32_t * n_
     }
     if (!launch_layer_norm(s->x, m.enc_norm_out, hp.eps, M, d, s->enc_out, st)) return MGB_ECUDA;
     if (enc_out) {
-        memset(enc_out, 0, (size_t)s->B * s->max_text * d * sizeof(float));
-        for (int b = 0; b < s->B; b++)
-            if (cudaMemcpyAsync(enc_out + (size_t)b * s->max_text * d, s->enc_out + (size_t)s->h_enc_off[b] * d,
-                                (size_t)s->h_ntext[b] * d * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) {
+        memset(enc_out, 0, (size_t)ns * s->max_text * d * sizeof(float));
+        for (int i = 0; i < ns; i++)
+            if (cudaMemcpyAsync(enc_out + (size_t)i * s->max_text * d, s->enc_out + (size_t)s->h_enc_off[i] * d,
+                                (size_t)n_tokens[i] * d * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) {
                 set_error("magpie_encode_text: D2H failed"); return MGB_ECUDA;
             }
     }
     if (cudaStreamSynchronize(st) != cudaSuccess) { set_error(std::string("magpie_encode_text: ") + cudaGetErrorString(cudaGetLastError())); return MGB_ECUDA; }
+    return MGB_OK;
+}
+
+}  // namespace mgb
+
+extern "C" {
+
+int mgb_encode_text(mgb_session * ss, const int32_t * tokens, const int32_t * n_tokens, float * enc_out) {
+    Session * s = reinterpret_cast<Session *>(ss);
+    if (!check_ready(s, false)) return MGB_EINVAL;
+    if (!tokens || !n_tokens) { set_error("magpie_encode_text: null tokens"); return MGB_EINVAL; }
+    std::vector<int> slots(s->B);
+    std::vector<const int32_t *> rows(s->B);
+    for (int b = 0; b < s->B; b++) { slots[b] = b; rows[b] = tokens + (size_t)b * s->max_text; }
+    const int rc = encode_slots(s, slots, rows.data(), n_tokens, enc_out);
+    if (rc != MGB_OK) return rc;
     s->encoded = true; s->prefilled = false; s->fold_ready = false;
     return MGB_OK;
 }
 
-int mgb_prefill(mgb_session * ss, const int32_t * speakers) {
-    Session * s = reinterpret_cast<Session *>(ss);
-    if (!check_ready(s, false)) return MGB_EINVAL;
-    if (!s->encoded) { set_error("mgb_prefill: call mgb_encode_text first"); return MGB_EINVAL; }
+}  // extern "C"
+
+namespace mgb {
+
+// Steps 2-5 of magpie_synthesize_codes_graph_reuse for the utterances whose encoder output is resident (s->enc_slots, left by
+// encode_slots): cross-attention K/V, folded tables, fresh cache pages, 110-frame context prefill, decode position = C.  The
+// other slots of the session are not touched (continuous batching refills single slots while the rest keep their state).
+static int prefill_slots(Session * s, const int32_t * speakers /* by list position, or null */, bool whole_session) {
     Model & m = *s->m; const mgb_hparams & hp = m.hp;
     const int d = hp.d_model, dxa = hp.dec_xa_heads * hp.dec_xa_d_head, C = hp.context_frames;
-    std::vector<int32_t> spk(s->B, 0);
-    for (int b = 0; b < s->B; b++) {
-        spk[b] = speakers ? speakers[b] : 0;
-        if (spk[b] < 0 || spk[b] >= hp.num_speakers) { set_error("mgb_prefill: speaker id out of range"); return MGB_EINVAL; }
+    const std::vector<int> & slots = s->enc_slots;
+    const int ns = (int)slots.size();
+    if ((int)s->h_speakers.size() != s->B) s->h_speakers.assign(s->B, 0);
+    for (int i = 0; i < ns; i++) {
+        const int v = speakers ? speakers[i] : 0;
+        if (v < 0 || v >= hp.num_speakers) { set_error("mgb_prefill: speaker id out of range"); return MGB_EINVAL; }
+        s->h_speakers[slots[i]] = v;
     }
     cudaStream_t st = s->stream;
-    if (cudaMemcpyAsync(s->d_speakers, spk.data(), s->B * 4, cudaMemcpyHostToDevice, st) != cudaSuccess) { set_error("H2D failed"); return MGB_ECUDA; }
+    if (cudaMemcpyAsync(s->d_speakers, s->h_speakers.data(), s->B * 4, cudaMemcpyHostToDevice, st) != cudaSuccess) { set_error("H2D failed"); return MGB_ECUDA; }
     // per-layer cross-attention K/V from the (still resident) encoder output; tok_* hold the encoder map
     const size_t xkv_layer = (size_t)s->B * s->max_text * dxa * m.wsize;
     for (int l = 0; l < hp.dec_layers; l++) {
@@ -482,37 +605,55 @@ int mgb_prefill(mgb_session * ss, const int32_t * speakers) {
         if (!launch_linear(a, st)) return MGB_ECUDA;
     }
     // persistent loop kernel: fold q_net / o_net into per-token tables (frame_loop.cu)
-    s->loop_tables = false;
-    if (s->loop_grid > 0 && s->h_ntext[0] <= s->loop_cap) {
-        s->loop_E = s->h_ntext[0];
-        for (int l = 0; l < hp.dec_layers; l++) {
-            const DecLayer & L = m.dec[l];
-            if (!launch_xattn_fold((char *)s->xk + l * xkv_layer, (char *)s->xv + l * xkv_layer, L.xq.w, L.xo.w, s->loop_E, d, dxa,
-                                   1.0f / sqrtf((float)dxa), s->d_xm + (size_t)l * s->loop_cap * d, s->d_xn + (size_t)l * s->loop_cap * d, st)) return MGB_ECUDA;
+    if (whole_session) {
+        s->loop_tables = false;
+        if (s->loop_grid > 0 && s->h_ntext[0] <= s->loop_cap) {
+            s->loop_E = s->h_ntext[0];
+            for (int l = 0; l < hp.dec_layers; l++) {
+                const DecLayer & L = m.dec[l];
+                if (!launch_xattn_fold((char *)s->xk + l * xkv_layer, (char *)s->xv + l * xkv_layer, L.xq.w, L.xo.w, s->loop_E, d, dxa,
+                                       1.0f / sqrtf((float)dxa), s->d_xm + (size_t)l * s->loop_cap * d, s->d_xn + (size_t)l * s->loop_cap * d, st)) return MGB_ECUDA;
+            }
+            s->loop_tables = true;
         }
-        s->loop_tables = true;
     }
     // batched decode: the same fold for every (utterance, text position) row of the cross K/V
-    s->fold_ready = false;
     // (the folded kernel streams 2 x E x d f32 table rows per utterance and layer, a quarter per CTA of a 4-CTA cluster:
     //  measured faster than the q GEMM + attention + o GEMM launches up to the 80-token texts of config 4; very long texts
     //  keep the unfolded kernels)
-    long long sum_e = 0;
-    for (int b = 0; b < s->B; b++) sum_e += s->h_ntext[b];
-    if (s->fold_xm && (sum_e <= (long long)(getenv("MGB_XFOLD_MAXE") ? atoi(getenv("MGB_XFOLD_MAXE")) : 128) * s->B)) {
+    if (whole_session) {
+        s->fold_ready = false;
+        long long sum_e = 0;
+        for (int b = 0; b < s->B; b++) sum_e += s->h_ntext[b];
+        s->fold_ready = s->fold_xm && (sum_e <= (long long)(getenv("MGB_XFOLD_MAXE") ? atoi(getenv("MGB_XFOLD_MAXE")) : 128) * s->B);
+    }
+    if (s->fold_ready) {
         const size_t tab = (size_t)s->B * s->max_text * d;
         for (int l = 0; l < hp.dec_layers; l++) {
             const DecLayer & L = m.dec[l];
-            if (!launch_xattn_fold((char *)s->xk + l * xkv_layer, (char *)s->xv + l * xkv_layer, L.xq.w, L.xo.w, s->B * s->max_text, d, dxa,
-                                   1.0f / sqrtf((float)dxa), s->fold_xm + l * tab, s->fold_xn + l * tab, st, s->d_ntext, s->max_text)) return MGB_ECUDA;
+            if (whole_session) {
+                if (!launch_xattn_fold((char *)s->xk + l * xkv_layer, (char *)s->xv + l * xkv_layer, L.xq.w, L.xo.w, s->B * s->max_text, d, dxa,
+                                       1.0f / sqrtf((float)dxa), s->fold_xm + l * tab, s->fold_xn + l * tab, st, s->d_ntext, s->max_text)) return MGB_ECUDA;
+            } else {
+                for (int b : slots) {          // only the refilled utterances' rows
+                    const size_t ro = (size_t)b * s->max_text;
+                    if (!launch_xattn_fold((char *)s->xk + l * xkv_layer + ro * dxa * m.wsize, (char *)s->xv + l * xkv_layer + ro * dxa * m.wsize,
+                                           L.xq.w, L.xo.w, s->max_text, d, dxa, 1.0f / sqrtf((float)dxa), s->fold_xm + l * tab + ro * d,
+                                           s->fold_xn + l * tab + ro * d, st, s->d_ntext + b, s->max_text)) return MGB_ECUDA;
+                }
+            }
         }
-        s->fold_ready = true;
     }
-    // context prefill: B*C tokens, one batched causal pass (magpie.cpp:4170-4238)
-    const int M = s->B * C;
+    // context prefill: ns*C tokens, one batched causal pass (magpie.cpp:4170-4238)
+    const int M = ns * C;
     std::vector<int32_t> utt(M), pos(M), slot(M);
-    for (int b = 0; b < s->B; b++)
-        for (int c = 0; c < C; c++) { utt[b * C + c] = b; pos[b * C + c] = c; slot[b * C + c] = b * s->max_seq + c; }
+    for (int b : slots) {
+        if (s->pages_on_demand) release_pages(*s, b);      // a new utterance starts with an empty cache
+        if (!ensure_pages(*s, b, C + 1)) return MGB_ERANGE;
+    }
+    if (!flush_page_table(*s)) return MGB_ECUDA;
+    for (int i = 0; i < ns; i++)
+        for (int c = 0; c < C; c++) { utt[i * C + c] = slots[i]; pos[i * C + c] = c; slot[i * C + c] = cache_row(*s, slots[i], c); }
     if (cudaStreamSynchronize(st) != cudaSuccess) { set_error("mgb_prefill: xattn K/V failed"); return MGB_ECUDA; }
     if (cudaMemcpyAsync(s->tok_utt, utt.data(), M * 4, cudaMemcpyHostToDevice, st) != cudaSuccess ||
         cudaMemcpyAsync(s->tok_pos, pos.data(), M * 4, cudaMemcpyHostToDevice, st) != cudaSuccess ||
@@ -523,12 +664,27 @@ int mgb_prefill(mgb_session * ss, const int32_t * speakers) {
     const bool pf_ok = decoder_layers(*s, T, false);
     s->prefill_len = 0;
     if (!pf_ok) return MGB_ECUDA;
-    std::vector<int32_t> p0(s->B, C), s0(s->B);
-    for (int b = 0; b < s->B; b++) s0[b] = b * s->max_seq + C;
-    if (cudaMemcpyAsync(s->dec_pos, p0.data(), s->B * 4, cudaMemcpyHostToDevice, st) != cudaSuccess ||
-        cudaMemcpyAsync(s->dec_slot, s0.data(), s->B * 4, cudaMemcpyHostToDevice, st) != cudaSuccess) { set_error("H2D failed"); return MGB_ECUDA; }
+    for (int b : slots) {
+        const int32_t p0 = C, s0 = cache_row(*s, b, C);
+        if (cudaMemcpyAsync(s->dec_pos + b, &p0, 4, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+            cudaMemcpyAsync(s->dec_slot + b, &s0, 4, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+            cudaStreamSynchronize(st) != cudaSuccess) { set_error("H2D failed"); return MGB_ECUDA; }      // (p0 / s0 are stack values: sync before they go out of scope)
+    }
     if (cudaStreamSynchronize(st) != cudaSuccess) { set_error(std::string("mgb_prefill: ") + cudaGetErrorString(cudaGetLastError())); return MGB_ECUDA; }
-    s->pos = C; s->prefilled = true; s->encoded = false;      // tok_* now hold the prefill map
+    return MGB_OK;
+}
+
+}  // namespace mgb
+
+extern "C" {
+
+int mgb_prefill(mgb_session * ss, const int32_t * speakers) {
+    Session * s = reinterpret_cast<Session *>(ss);
+    if (!check_ready(s, false)) return MGB_EINVAL;
+    if (!s->encoded) { set_error("mgb_prefill: call mgb_encode_text first"); return MGB_EINVAL; }
+    const int rc = prefill_slots(s, speakers, true);
+    if (rc != MGB_OK) return rc;
+    s->pos = s->m->hp.context_frames; s->prefilled = true; s->encoded = false;      // tok_* now hold the prefill map
     return MGB_OK;
 }
 
@@ -544,6 +700,8 @@ int mgb_decoder_step(mgb_session * ss, const int32_t * codes, float * hidden_out
         if (cudaMemcpyAsync(s->d_codes, codes, (size_t)s->B * 8 * 4, cudaMemcpyHostToDevice, st) != cudaSuccess) { set_error("H2D failed"); return MGB_ECUDA; }
     }
     s->attn_split = attention_plan_kv_split(s->m->hp.dec_sa_heads * s->B, s->pos + 1);
+    if (!ensure_pages_all(*s, std::min(s->pos + 2, s->max_seq))) return MGB_ERANGE;       // this position and the next (advance reads its page)
+    if (s->mega_grid > 0 && !pages_contiguous(*s, s->pos + 1)) { set_error("mgb_decoder_step: the batch-1 kernel needs contiguous cache pages"); return MGB_ERANGE; }
     if (!decoder_step_device(*s) || !launch_advance(*s, false)) return MGB_ECUDA;
     if (hidden_out && cudaMemcpyAsync(hidden_out, s->hidden, (size_t)s->B * hp.d_model * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) {
         set_error("D2H failed"); return MGB_ECUDA;
@@ -650,7 +808,7 @@ static int run_loop_persistent(Session & s, const LoopCfg & c, int * steps_run) 
         p.audio_emb[cb] = m.audio_emb[cb]; p.lt_out_w[cb] = m.lt_out_w[cb].w; p.lt_out_b[cb] = m.lt_out_b[cb]; p.lt_in_table[cb] = m.lt_in_table[cb];
     }
     p.dec_pos = m.dec_pos; p.norm_out = m.dec_norm_out;
-    p.kcache = s.kc; p.vcache = s.vc; p.kv_layer_stride = (size_t)s.B * s.max_seq * hp.d_model;
+    p.kcache = s.kc; p.vcache = s.vc; p.kv_layer_stride = s.kv_rows * hp.d_model;
     p.V = hp.vocab_per_cb;
     p.lt_in_w = m.lt_in_w.w; p.lt_in_b = m.lt_in_b; p.lt_pos = m.lt_pos; p.lt_norm_self = m.lt_norm_self; p.lt_norm_ff = m.lt_norm_ff;
     p.lt_qkvo = m.lt_qkvo; p.lt_qkv_tab = m.lt_qkv_tab; p.lt_ff1 = m.lt_ff1.w; p.lt_ff2 = m.lt_ff2.w;
@@ -694,7 +852,14 @@ static int run_loop(Session & s, const LoopCfg & c, int * steps_run) {
     if (s.pos + c.T > s.max_seq) { set_error("generation loop: KV cache too small for the requested steps"); return MGB_ERANGE; }
     // (the persistent kernel divides the cached keys over up to 6 CTAs per head; each warp scans 32-key chunks, the first
     //  480 keys of an item before the wait for q, longer items in further rounds)
-    if (s.loop_grid > 0 && s.loop_tables) return run_loop_persistent(s, c, steps_run);
+    if (s.loop_grid > 0 && s.loop_tables) {
+        if (!ensure_pages_all(s, std::min(s.pos + c.T + 1, s.max_seq))) return MGB_ERANGE;
+        if (!pages_contiguous(s, s.pos + c.T)) { set_error("generation loop: the batch-1 kernel needs contiguous cache pages"); return MGB_ERANGE; }
+        return run_loop_persistent(s, c, steps_run);
+    }
+    if (s.mega_grid > 0 && (!ensure_pages_all(s, std::min(s.pos + c.T + 1, s.max_seq)) || !pages_contiguous(s, s.pos + c.T))) {
+        set_error("generation loop: the batch-1 kernel needs contiguous cache pages"); return MGB_ERANGE;
+    }
     // the iteration is captured once, so the key split of the self-attention is planned for the KV length the loop will reach
     s.attn_split = attention_plan_kv_split(s.m->hp.dec_sa_heads * B, s.pos + c.T);
     std::vector<int32_t> neg(B, -1);
@@ -718,6 +883,8 @@ static int run_loop(Session & s, const LoopCfg & c, int * steps_run) {
     cudaEventRecord(s.ev0, st);
     while (t < c.T) {
         const int n = std::min(check_every, c.T - t);
+        // cache pages for the positions this chunk writes and the one after it (pools sized on demand grow here)
+        if (!ensure_pages_all(s, std::min(s.pos + t + n + 1, s.max_seq))) { rc = MGB_ERANGE; break; }
         for (int i = 0; i < n && rc == MGB_OK; i++) {
             if (use_graph) { if (cudaGraphLaunch(exec, st) != cudaSuccess) { set_error("graph launch failed"); rc = MGB_ECUDA; } }
             else if (!enqueue_iteration(s, c)) rc = MGB_ECUDA;
@@ -814,6 +981,191 @@ int mgb_teacher_forced(mgb_session * ss, const int32_t * codes_in, int T, float 
     if (hidden_out) ok = ok && cudaMemcpyAsync(hidden_out, s->l_hidden, n * hp.d_model * 4, cudaMemcpyDeviceToHost, st) == cudaSuccess;
     if (lt_logits_out) ok = ok && cudaMemcpyAsync(lt_logits_out, s->l_logits, n * 8 * hp.vocab_per_cb * 4, cudaMemcpyDeviceToHost, st) == cudaSuccess;
     if (!ok || cudaStreamSynchronize(st) != cudaSuccess) { set_error("mgb_teacher_forced: D2H failed"); return MGB_ECUDA; }
+    return MGB_OK;
+}
+
+}  // extern "C"
+
+// ---- continuous batching ------------------------------------------------------------------------------
+namespace mgb {
+
+// after a queue-mode step: an active slot whose frame hit EOS (done_step set by the LT kernel) or that reached its frame limit
+// stops; the others move to the next position / cache row and count one more emitted frame
+__global__ void advance_queue_kernel(int32_t * pos, int32_t * slot, int B, const int32_t * page_table, int max_pages, int32_t * active,
+                                     int32_t * utt_step, const int32_t * done_step, const int32_t * limit) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B || !active[i]) return;
+    if (done_step[i] >= 0) { active[i] = 0; return; }                      // EOS frame: not emitted (magpie.cpp:4341-4352)
+    const int np = pos[i] + 1, pg = np / kKvPageRows;
+    pos[i] = np;
+    slot[i] = pg < max_pages ? page_table[(size_t)i * max_pages + pg] * kKvPageRows + np % kKvPageRows : 0;
+    utt_step[i] += 1;
+    if (utt_step[i] >= limit[i]) active[i] = 0;
+}
+
+}  // namespace mgb
+
+extern "C" {
+
+int mgb_generate_queue(mgb_session * ss, int n_utt, const int32_t * tokens, const int32_t * n_tokens, int max_text,
+                       const int32_t * speakers, const int32_t * max_steps_per_utt, int max_steps, float temperature, int top_k,
+                       uint64_t seed, int32_t * codes_out, int32_t * n_frames_out, int64_t * steps_run_out) {
+    Session * s = reinterpret_cast<Session *>(ss);
+    if (!check_ready(s, false)) return MGB_EINVAL;
+    Model & m = *s->m; const mgb_hparams & hp = m.hp;
+    if (n_utt <= 0 || !tokens || !n_tokens || !codes_out || !n_frames_out || max_steps <= 0 || max_text <= 0 || max_text > s->max_text) {
+        set_error("mgb_generate_queue: invalid arguments"); return MGB_EINVAL;
+    }
+    if (temperature >= 0.01f && top_k < 1) { set_error("mgb_generate_queue: top_k must be >= 1 when sampling"); return MGB_EINVAL; }
+    const int B = s->B, C = hp.context_frames;
+    if (C + max_steps + 1 > s->max_seq) { set_error("mgb_generate_queue: max_steps exceeds the session's max_seq"); return MGB_ERANGE; }
+    if (n_utt < B && s->mega_grid == 0) { set_error("mgb_generate_queue: fewer utterances than session slots (use a smaller session)"); return MGB_EINVAL; }
+    for (int q = 0; q < n_utt; q++) {
+        if (n_tokens[q] <= 0 || n_tokens[q] > max_text) { set_error("mgb_generate_queue: token count out of range"); return MGB_EINVAL; }
+        if (max_steps_per_utt && (max_steps_per_utt[q] <= 0 || max_steps_per_utt[q] > max_steps)) { set_error("mgb_generate_queue: per-utterance step limit out of range"); return MGB_EINVAL; }
+    }
+    cudaStream_t st = s->stream;
+    if (s->mega_grid > 0) {
+        // one-slot session: the batch-1 kernels advance their own position; utterances simply run one after the other
+        int64_t steps = 0;
+        cudaEventRecord(s->ev0, st);
+        float ms = 0.0f;
+        for (int q = 0; q < n_utt; q++) {
+            std::vector<int32_t> row((size_t)s->max_text, 0);
+            memcpy(row.data(), tokens + (size_t)q * max_text, (size_t)n_tokens[q] * 4);
+            const int32_t spk = speakers ? speakers[q] : 0, lim = max_steps_per_utt ? max_steps_per_utt[q] : max_steps;
+            int rc = mgb_encode_text(ss, row.data(), n_tokens + q, nullptr);
+            if (rc == MGB_OK) rc = mgb_prefill(ss, &spk);
+            if (rc == MGB_OK) rc = mgb_generate(ss, lim, temperature, top_k, nullptr, seed + (uint64_t)q, 0, codes_out + (size_t)q * max_steps * 8, n_frames_out + q, nullptr);
+            if (rc != MGB_OK) return rc;
+            steps += n_frames_out[q]; ms += s->last_ms;
+        }
+        s->last_ms = ms;
+        if (steps_run_out) *steps_run_out = steps;
+        return MGB_OK;
+    }
+    const int T_total = max_steps + 1;                 // one scratch row per slot: finished slots keep being computed
+    LoopCfg c;
+    c.T = T_total; c.temperature = temperature; c.top_k = top_k; c.seed = seed;
+    if (!prepare_loop_buffers(*s, c)) return MGB_ECUDA;
+    std::vector<int> slot_utt(B, -1), slot_steps(B, 0);          // utterance in each slot; host's upper bound of its emitted frames
+    std::vector<int32_t> h_limit(B, 1), h_active(B, 0), h_done(B, -1), h_ustep(B, 0);
+    int32_t * d_limit = s->d_forced;                   // [B][8] scratch: the first B entries hold the frame limits
+    int next = 0, finished = 0;
+    int64_t steps = 0, launches0 = g_launch_counter;
+    s->attn_split = attention_plan_kv_split(hp.dec_sa_heads * B, C + 1 + max_steps);
+    const bool use_graph = getenv("MGB_NO_GRAPH") == nullptr;
+    cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
+    auto cleanup = [&]() { if (exec) cudaGraphExecDestroy(exec); if (graph) cudaGraphDestroy(graph); };
+    // one iteration: decoder step on d_codes -> LT (+sampling) with per-utterance step counters -> queue advance
+    auto enqueue = [&]() -> bool {
+        if (!launch_audio_embed(m, s->d_codes, s->dec_pos, B, s->x, st)) return false;
+        Tokens tok; tok.M = B; tok.utt = s->dec_utt; tok.pos = s->dec_pos; tok.slot = s->dec_slot;
+        if (!decoder_layers(*s, tok, true)) return false;
+        LtArgs a;
+        a.B = B; a.hidden = s->hidden; a.temperature = temperature; a.top_k = top_k; a.seed = seed;
+        a.sampled = s->l_sampled; a.argmax = s->l_argmax; a.next_codes = s->d_codes;
+        a.utt_step = s->d_utt_step; a.T_total = T_total; a.min_frames = 4; a.done_step = s->d_done;
+        a.lt_scratch = s->lt_scratch; a.lt_scratch_bytes = s->lt_scratch_bytes;
+        if (!launch_local_transformer(m, a, st)) return false;
+        advance_queue_kernel<<<(B + 127) / 128, 128, 0, st>>>(s->dec_pos, s->dec_slot, B, s->d_page_table, s->max_pages, s->d_active,
+                                                              s->d_utt_step, s->d_done, d_limit);
+        MGB_LAUNCH_CHECK();
+        return true;
+    };
+    // (re)fill the free slots from the queue: encoder + cross K/V + context prefill of just those slots
+    auto refill = [&](const std::vector<int> & free_slots) -> int {
+        std::vector<int> slots; std::vector<const int32_t *> rows; std::vector<int32_t> nt, spk;
+        for (int b : free_slots) {
+            if (next >= n_utt) break;
+            slots.push_back(b); rows.push_back(tokens + (size_t)next * max_text); nt.push_back(n_tokens[next]);
+            spk.push_back(speakers ? speakers[next] : 0);
+            slot_utt[b] = next; slot_steps[b] = 0;
+            h_limit[b] = max_steps_per_utt ? max_steps_per_utt[next] : max_steps;
+            next++;
+        }
+        if (slots.empty()) return MGB_OK;
+        int rc = encode_slots(s, slots, rows.data(), nt.data(), nullptr);
+        if (rc == MGB_OK) rc = prefill_slots(s, spk.data(), false);
+        if (rc != MGB_OK) return rc;
+        std::vector<int32_t> bos(8, hp.audio_bos_id);
+        for (int b : slots) {
+            h_active[b] = 1; h_done[b] = -1; h_ustep[b] = 0;
+            if (cudaMemcpyAsync(s->d_codes + (size_t)b * 8, bos.data(), 32, cudaMemcpyHostToDevice, st) != cudaSuccess) { set_error("H2D failed"); return MGB_ECUDA; }
+        }
+        if (cudaMemcpyAsync(s->d_active, h_active.data(), B * 4, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+            cudaMemcpyAsync(s->d_done, h_done.data(), B * 4, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+            cudaMemcpyAsync(s->d_utt_step, h_ustep.data(), B * 4, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+            cudaMemcpyAsync(d_limit, h_limit.data(), B * 4, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+            cudaStreamSynchronize(st) != cudaSuccess) { set_error("mgb_generate_queue: slot state upload failed"); return MGB_ECUDA; }
+        return MGB_OK;
+    };
+    // the folded cross-attention tables serve every slot or none: decided once for the whole queue (texts up to 128 tokens)
+    s->fold_ready = s->fold_xm != nullptr && max_text <= 128;
+    s->loop_tables = false; s->prefilled = false; s->encoded = false;
+    cudaEventRecord(s->ev0, st);
+    std::vector<int> all(B);
+    for (int b = 0; b < B; b++) all[b] = b;
+    int rc = refill(all);
+    if (rc != MGB_OK) return rc;
+    if (use_graph) {
+        if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { set_error("graph capture begin failed"); return MGB_ECUDA; }
+        const bool okq = enqueue();
+        const cudaError_t e = cudaStreamEndCapture(st, &graph);
+        if (!okq || e != cudaSuccess || !graph) { cleanup(); if (okq) set_error("graph capture failed"); return MGB_ECUDA; }
+        if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) { cleanup(); set_error("graph instantiate failed"); return MGB_ECUDA; }
+    }
+    const int check_every = 8;
+    while (finished < n_utt) {
+        // cache pages for the positions the next chunk writes (and the one after): on-demand pools grow here
+        for (int b = 0; b < B; b++)
+            if (h_active[b] && !ensure_pages(*s, b, std::min(C + 1 + slot_steps[b] + check_every + 1, s->max_seq))) { cleanup(); return MGB_ERANGE; }
+        if (!flush_page_table(*s)) { cleanup(); return MGB_ECUDA; }
+        for (int i = 0; i < check_every; i++) {
+            if (use_graph) { if (cudaGraphLaunch(exec, st) != cudaSuccess) { cleanup(); set_error("graph launch failed"); return MGB_ECUDA; } }
+            else if (!enqueue()) { cleanup(); return MGB_ECUDA; }
+        }
+        steps += check_every;
+        for (int b = 0; b < B; b++) if (h_active[b]) slot_steps[b] += check_every;
+        if (cudaMemcpyAsync(h_active.data(), s->d_active, B * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaMemcpyAsync(h_done.data(), s->d_done, B * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaMemcpyAsync(h_ustep.data(), s->d_utt_step, B * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaStreamSynchronize(st) != cudaSuccess) { cleanup(); set_error(std::string("mgb_generate_queue: ") + cudaGetErrorString(cudaGetLastError())); return MGB_ECUDA; }
+        std::vector<int> free_slots;
+        for (int b = 0; b < B; b++) {
+            if (h_active[b] || slot_utt[b] < 0) continue;
+            const int q = slot_utt[b];
+            const int nf = h_done[b] >= 0 ? std::min(h_done[b], h_limit[b]) : h_limit[b];
+            n_frames_out[q] = nf;
+            if (nf > 0 && cudaMemcpyAsync(codes_out + (size_t)q * max_steps * 8, s->l_sampled + (size_t)b * T_total * 8, (size_t)nf * 32,
+                                          cudaMemcpyDeviceToHost, st) != cudaSuccess) { cleanup(); set_error("mgb_generate_queue: D2H failed"); return MGB_ECUDA; }
+            slot_utt[b] = -1; finished++;
+            release_pages(*s, b);
+            free_slots.push_back(b);
+        }
+        if (!free_slots.empty()) {
+            if (cudaStreamSynchronize(st) != cudaSuccess) { cleanup(); set_error("mgb_generate_queue: D2H failed"); return MGB_ECUDA; }
+            rc = refill(free_slots);
+            if (rc != MGB_OK) { cleanup(); return rc; }
+            // slots left without an utterance (the queue is drained) keep being computed: park them on position 0 of a page of
+            // their own, so the row they rewrite every step can never belong to another utterance
+            for (int b : free_slots) {
+                if (slot_utt[b] >= 0) continue;
+                if (!ensure_pages(*s, b, 1) || !flush_page_table(*s)) { cleanup(); return MGB_ERANGE; }
+                const int32_t zero = 0, row = cache_row(*s, b, 0);
+                if (cudaMemcpyAsync(s->dec_pos + b, &zero, 4, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+                    cudaMemcpyAsync(s->dec_slot + b, &row, 4, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+                    cudaStreamSynchronize(st) != cudaSuccess) { cleanup(); set_error("mgb_generate_queue: H2D failed"); return MGB_ECUDA; }
+            }
+        }
+    }
+    cudaEventRecord(s->ev1, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess) { cleanup(); set_error(std::string("mgb_generate_queue: ") + cudaGetErrorString(cudaGetLastError())); return MGB_ECUDA; }
+    cudaEventElapsedTime(&s->last_ms, s->ev0, s->ev1);
+    s->last_launches = g_launch_counter - launches0;
+    cleanup();
+    if (steps_run_out) *steps_run_out = steps;
+    s->prefilled = false;                              // the session's slots hold finished utterances: encode + prefill before reuse
     return MGB_OK;
 }
 

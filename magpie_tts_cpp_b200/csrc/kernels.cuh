@@ -19,6 +19,7 @@ struct Tokens {
 };
 
 enum { ACT_NONE = 0, ACT_GELU = 1 };
+constexpr int kKvPageRows = 128;      // rows (cache positions) per page of the paged decoder self-attention K / V cache
 
 struct LinearArgs {
     DevMat W;                       // [taps][N][K]
@@ -60,6 +61,7 @@ struct AttnArgs {
     float * out = nullptr; int ldo = 0;
     void * pack_out = nullptr;                   // dh == 64, <= 64 tokens: write hi | lo tile images for the next GEMM instead of `out`
     int prefill_len = 0;                         // > 0: tokens are utterance-major runs of positions 0..prefill_len-1 (context prefill)
+    const int32_t * page_table = nullptr; int max_pages = 0;   // paged K / V: [utterances][max_pages] page ids (pages of kKvPageRows rows); null = contiguous
     int kv_split = 0;                            // packed-output decoder step only: >= 1 = long-KV kernel, keys of a (head, token) divided over a cluster of this many CTAs
 };
 bool launch_attention(const AttnArgs & a, cudaStream_t stream);
@@ -105,6 +107,7 @@ struct LtArgs {
     // stays [B][8].  forbid_eos applies while step < min_frames.  done_step[utt] (init -1) records the
     // first step at which EOS was hit; hidden_hist (optional) receives the hidden state [B][T_total][d].
     const int32_t * d_step = nullptr;
+    const int32_t * utt_step = nullptr;  // loop mode with per-utterance step counters [B] (continuous batching); takes precedence over d_step
     int T_total = 0, min_frames = 0;
     int32_t * done_step = nullptr;
     float * hidden_hist = nullptr;

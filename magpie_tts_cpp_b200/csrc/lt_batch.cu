@@ -165,8 +165,9 @@ __global__ void __launch_bounds__(kLtThreads, 1) lt_batch_kernel(const BParams b
         n_stamp++;
     };
     stamp();
-    const bool loop = p.d_step != nullptr;
-    const int step = loop ? *p.d_step : (int)p.step;
+    const bool loop = p.d_step != nullptr || p.utt_step != nullptr;
+    const int step0 = loop && p.d_step ? *p.d_step : (int)p.step;
+    auto step_of = [&](size_t u) { return p.utt_step ? p.utt_step[u] : step0; };
     const float att_scale = 1.0f / sqrtf((float)L);
     auto no_prep = [](int, float *) {};
 
@@ -175,7 +176,7 @@ __global__ void __launch_bounds__(kLtThreads, 1) lt_batch_kernel(const BParams b
     if (p.hidden_hist)
         for (size_t i = (size_t)c * kLtThreads + tid; i < (size_t)B * d; i += (size_t)G * kLtThreads) {
             const size_t u = i / d, k = i % d;
-            p.hidden_hist[((loop ? u * p.T_total + step : u)) * d + k] = p.hidden[i];
+            p.hidden_hist[((loop ? u * p.T_total + step_of(u) : u)) * d + k] = p.hidden[i];
         }
     stamp(); grid.sync(); stamp();
 
@@ -253,6 +254,7 @@ __global__ void __launch_bounds__(kLtThreads, 1) lt_batch_kernel(const BParams b
         int oi = 0;
         for (int u = c; u < B; u += G, oi++) {
             __syncthreads();
+            const int step = step_of(u);
             const size_t row = loop ? (size_t)u * p.T_total + step : (size_t)u;
             const int32_t * forced = p.forced ? p.forced + row * 8 : nullptr;
             const bool forbid_eos = p.forbid_eos_all || (p.forbid_eos && p.forbid_eos[u]) || (loop && step < p.min_frames);

@@ -35,6 +35,7 @@ struct LtParams {
     int bos_id, eos_id;
     int32_t * sampled; int32_t * argmax; int32_t * next_codes; float * logits; int32_t * eos_flag;
     const int32_t * d_step; int T_total, min_frames; int32_t * done_step; float * hidden_hist;
+    const int32_t * utt_step;       // optional [B]: per-utterance step counters instead of *d_step (continuous batching: utterances start at different times)
     int stream_feedback = 0;        // 1: feedback in-projection as a GEMV (lt_kernel); 0: row gather from in_table
     const float * in_table[8];      // P_cb = E_cb . Win^T + b, [V][L] f32 (resident kernel: feedback is a row gather)
 };

@@ -117,8 +117,8 @@ __global__ void __launch_bounds__(kLtThreads, 1) lt_kernel(const LtParams p) {
     const float att_scale = 1.0f / sqrtf((float)L);
 
     // loop mode: per-step arrays are indexed by the device-side step counter (CUDA-graph replayable)
-    const bool loop = p.d_step != nullptr;
-    const int step = loop ? *p.d_step : (int)p.step;
+    const bool loop = p.d_step != nullptr || p.utt_step != nullptr;
+    const int step = p.utt_step ? p.utt_step[utt] : (loop ? *p.d_step : (int)p.step);
     const size_t row = loop ? (size_t)utt * p.T_total + step : (size_t)utt;
     const int32_t * forced = p.forced ? p.forced + row * 8 : nullptr;
     const float * uniforms = p.uniforms ? p.uniforms + row * 8 : nullptr;
@@ -278,7 +278,7 @@ bool launch_local_transformer(const Model & m, const LtArgs & a, cudaStream_t st
     p.forced = a.forced; p.uniforms = a.uniforms; p.seed = a.seed; p.step = a.step;
     p.bos_id = m.hp.audio_bos_id; p.eos_id = m.hp.audio_eos_id;
     p.sampled = a.sampled; p.argmax = a.argmax; p.next_codes = a.next_codes; p.logits = a.logits; p.eos_flag = a.eos_flag;
-    p.d_step = a.d_step; p.T_total = a.T_total; p.min_frames = a.min_frames; p.done_step = a.done_step; p.hidden_hist = a.hidden_hist;
+    p.d_step = a.d_step; p.utt_step = a.utt_step; p.T_total = a.T_total; p.min_frames = a.min_frames; p.done_step = a.done_step; p.hidden_hist = a.hidden_hist;
     for (int cb = 0; cb < 8; cb++) p.in_table[cb] = m.lt_in_table[cb];
     // MGB_LT_STREAM keeps the independent (GEMV) formulation alive for the parity tests; f32 models always use it
     p.stream_feedback = (getenv("MGB_LT_STREAM") != nullptr || m.precision == MGB_PREC_F32) ? 1 : 0;

@@ -150,8 +150,8 @@ __global__ void __cluster_dims__(kCS, 1, 1) __launch_bounds__(kLtThreads, 1) lt_
         if (b_out) bulk_g2s(S.w_out, (const bf *)p.out_w[0] + (size_t)s_out.r0 * L, b_out, &S.mbar[1]);
     }
 
-    const bool loop = p.d_step != nullptr;
-    const int step = loop ? *p.d_step : (int)p.step;
+    const bool loop = p.d_step != nullptr || p.utt_step != nullptr;
+    const int step = p.utt_step ? p.utt_step[utt] : (loop ? *p.d_step : (int)p.step);
     const size_t row = loop ? (size_t)utt * p.T_total + step : (size_t)utt;
     const int32_t * forced = p.forced ? p.forced + row * 8 : nullptr;
     const float * uniforms = p.uniforms ? p.uniforms + row * 8 : nullptr;

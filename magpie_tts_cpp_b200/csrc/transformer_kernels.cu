@@ -172,7 +172,11 @@ struct AttnParams {
     int pdl;                                           // launched with programmatic stream serialization (see kernel)
     int split_min_keys;                                // SPLIT kernels: a token's keys are divided over the cluster from this many keys per CTA on
     int pf_keys;                                       // pdl: keys per CTA whose K / V rows are prefetched into L2 ahead of the wait (the launch's share of L2)
+    // paged K / V (decoder self-attention cache): key j of utterance u lives in row page_table[u * max_pages + j / 128] * 128 + j % 128
+    // of the layer's page pool; null = contiguous rows u * rows_per_utt + j (cross-attention K / V, encoder scratch)
+    const int32_t * page_table; int max_pages;
 };
+constexpr int kPageShift = 7, kPageRows = 1 << kPageShift;     // = kKvPageRows (kernels.cuh)
 
 constexpr int kAttnWarps = 8;
 
@@ -212,6 +216,10 @@ __global__ void __launch_bounds__(kAttnWarps * 32, SPLIT == 2 ? 3 : 0) attention
     const int nk = p.causal ? p.pos[t] + 1 : p.n_ctx[utt];
     const float scale = 1.0f / sqrtf((float)DH);
     const int ld = p.H * DH;
+    const int32_t * pt = p.page_table ? p.page_table + (size_t)utt * p.max_pages : nullptr;
+    auto krow = [&](int j) -> size_t {      // storage row of key j of this token's utterance
+        return pt ? (size_t)__ldg(pt + (j >> kPageShift)) * kPageRows + (size_t)(j & (kPageRows - 1)) : (size_t)utt * p.rows_per_utt + (size_t)j;
+    };
     int k0 = 0, k1 = nk;                   // this CTA's key range
     unsigned crank = 0, csize = 1;
     if constexpr (SPLIT) {
@@ -224,11 +232,11 @@ __global__ void __launch_bounds__(kAttnWarps * 32, SPLIT == 2 ? 3 : 0) attention
     if (p.pdl) {
         // launched as a programmatic dependent of the QKV GEMM: the old keys' K / V rows do not depend on it, so they are
         // pulled into L2 while that kernel is still running; q and the new key's row are read after the wait
-        const char * Kp = (const char *)p.K + ((size_t)utt * p.rows_per_utt * ld + h * DH) * sizeof(T);
-        const char * Vp = (const char *)p.V + ((size_t)utt * p.rows_per_utt * ld + h * DH) * sizeof(T);
+        const char * Kp = (const char *)p.K + (size_t)(h * DH) * sizeof(T);
+        const char * Vp = (const char *)p.V + (size_t)(h * DH) * sizeof(T);
         for (int j = k0 + tid; j < min(min(k1, nk - 1), k0 + p.pf_keys); j += kAttnWarps * 32) {
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(Kp + (size_t)j * ld * sizeof(T)));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(Vp + (size_t)j * ld * sizeof(T)));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(Kp + krow(j) * ld * sizeof(T)));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(Vp + krow(j) * ld * sizeof(T)));
         }
         asm volatile("griddepcontrol.wait;" ::: "memory");
     }
@@ -238,8 +246,8 @@ __global__ void __launch_bounds__(kAttnWarps * 32, SPLIT == 2 ? 3 : 0) attention
 #pragma unroll
         for (int v = 0; v < VEC; v++) qv[v] = qp[v] * scale;
     }
-    const T * Kb = (const T *)p.K + (size_t)utt * p.rows_per_utt * ld + h * DH + sub * VEC;
-    const T * Vb = (const T *)p.V + (size_t)utt * p.rows_per_utt * ld + h * DH + sub * VEC;
+    const T * Kb = (const T *)p.K + h * DH + sub * VEC;
+    const T * Vb = (const T *)p.V + h * DH + sub * VEC;
 
     float mx = -INFINITY, l = 0.0f, acc[VEC];
 #pragma unroll
@@ -256,7 +264,7 @@ __global__ void __launch_bounds__(kAttnWarps * 32, SPLIT == 2 ? 3 : 0) attention
         for (int u = 0; u < U; u++) {
             const int j = base + u * KPI + grp;
             kr[u] = make_uint4(0u, 0u, 0u, 0u); vr[u] = make_uint4(0u, 0u, 0u, 0u);
-            if (j < k1) { kr[u] = ldg_stream(Kb + (size_t)j * ld); vr[u] = ldg_stream(Vb + (size_t)j * ld); }
+            if (j < k1) { kr[u] = ldg_stream(Kb + krow(j) * ld); vr[u] = ldg_stream(Vb + krow(j) * ld); }
         }
         for (; base < k1; base += STEP) {
             uint4 kc[U], vc[U];
@@ -265,7 +273,7 @@ __global__ void __launch_bounds__(kAttnWarps * 32, SPLIT == 2 ? 3 : 0) attention
 #pragma unroll
             for (int u = 0; u < U; u++) {
                 const int j = base + STEP + u * KPI + grp;
-                if (j < k1) { kr[u] = ldg_stream(Kb + (size_t)j * ld); vr[u] = ldg_stream(Vb + (size_t)j * ld); }
+                if (j < k1) { kr[u] = ldg_stream(Kb + krow(j) * ld); vr[u] = ldg_stream(Vb + krow(j) * ld); }
             }
             float sc[U], mnew = mx;
 #pragma unroll
@@ -305,8 +313,8 @@ __global__ void __launch_bounds__(kAttnWarps * 32, SPLIT == 2 ? 3 : 0) attention
         for (int u = 0; u < U; u++) {
             const int j = base + u * KPI + grp;
             if (j < k1) {
-                WT<T>::load(Kb + (size_t)j * ld, kk[u]);
-                WT<T>::load(Vb + (size_t)j * ld, vv[u]);
+                WT<T>::load(Kb + krow(j) * ld, kk[u]);
+                WT<T>::load(Vb + krow(j) * ld, vv[u]);
             } else {
 #pragma unroll
                 for (int v = 0; v < VEC; v++) { kk[u][v] = 0.0f; vv[u][v] = 0.0f; }
@@ -487,8 +495,11 @@ __global__ void __launch_bounds__(256) prefill_attention_kernel(const AttnParams
     float * sp = sq + 8 * DH;                // [8][128]
     const int h = blockIdx.x, u = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ld = p.H * DH;
-    const T * Kb = (const T *)p.K + (size_t)u * p.rows_per_utt * ld + h * DH;
-    const T * Vb = (const T *)p.V + (size_t)u * p.rows_per_utt * ld + h * DH;
+    // (paged cache: the C <= 128 context rows are page 0 of the utterance)
+    const int uu = p.utt[(size_t)u * C];         // utterance (session slot) of this run of C tokens: a prefill may cover a subset of the slots
+    const size_t row0 = p.page_table ? (size_t)p.page_table[(size_t)uu * p.max_pages] * kPageRows : (size_t)uu * p.rows_per_utt;
+    const T * Kb = (const T *)p.K + row0 * ld + h * DH;
+    const T * Vb = (const T *)p.V + row0 * ld + h * DH;
     for (int i = tid; i < C * DH; i += 256) {
         const int j = i / DH, dd = i % DH;
         Ks[j * KS + dd] = WT<T>::get(Kb + (size_t)j * ld + dd);
@@ -573,6 +584,7 @@ bool launch_attention(const AttnArgs & a, cudaStream_t stream) {
     p.q = a.q; p.ldq = a.ldq; p.K = a.K; p.V = a.V; p.rows_per_utt = a.rows_per_utt; p.H = a.H;
     p.causal = a.causal; p.n_ctx = a.n_ctx; p.utt = a.tok.utt; p.pos = a.tok.pos; p.out = a.out; p.ldo = a.ldo;
     p.pk_hi = nullptr; p.pk_lo = nullptr;
+    p.page_table = a.page_table; p.max_pages = a.max_pages;
     if (a.pack_out) {
         if (a.dh != 64 || a.tok.M > 64) { set_error("attention: packed output needs head dim 64 and one token tile"); return false; }
         p.pk_hi = (__nv_bfloat16 *)a.pack_out; p.pk_lo = p.pk_hi + (size_t)64 * a.H * a.dh;
