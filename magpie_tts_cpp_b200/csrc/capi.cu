@@ -153,6 +153,9 @@ static inline int32_t cache_row(const Session & s, int b, int j) { return s.h_pt
 // ---- shared layer drivers -------------------------------------------------------------------------
 static bool decoder_layers(Session & s, Tokens tok, bool want_hidden) {
     Model & m = *s.m; const mgb_hparams & hp = m.hp;
+    // timing experiments only (results are garbage): bit 0 skips the cross-attention launches, bit 1 the self-attention, bit 2 the
+    // QKV GEMM, bit 3 the O GEMM, bit 4 FF1, bit 5 FF2 -- the step-time difference is that kernel's LIVE cost inside the chain
+    static const int skip = getenv("MGB_STEP_SKIP") ? atoi(getenv("MGB_STEP_SKIP")) : 0;
     const int d = hp.d_model, dxa = hp.dec_xa_heads * hp.dec_xa_d_head, M = tok.M;
     const size_t kv_layer = s.kv_rows * d * m.wsize, xkv_layer = (size_t)s.B * s.max_text * dxa * m.wsize;
     for (int l = 0; l < hp.dec_layers; l++) {
@@ -164,7 +167,7 @@ static bool decoder_layers(Session & s, Tokens tok, bool want_hidden) {
         // self-attention: LN -> QKV (K,V written straight into the cache) -> attention -> O + residual
         a.W = L.qkv; a.X = s.x; a.ldx = d; a.ln_w = L.norm_self; a.Y = s.qbuf; a.ldy = d;
         a.n_q = d; a.dkv = d; a.kdst = kl; a.vdst = vl; a.tok_slot = tok.slot;
-        if (!launch_linear(a, s.stream)) return false;
+        if (!(skip & 4) && !launch_linear(a, s.stream)) return false;
         LinearArgs o;
         o.tc_scratch = s.tc_scratch; o.tc_scratch_bytes = s.tc_scratch_bytes;
         o.precision = m.precision; o.M = M; o.W = L.o; o.X = s.attn; o.ldx = d; o.res = s.x; o.ldr = d; o.Y = s.x; o.ldy = d;
@@ -177,8 +180,8 @@ static bool decoder_layers(Session & s, Tokens tok, bool want_hidden) {
         if (M == s.B && tok.utt == s.dec_utt && M <= 64 && at.dh == 64 && tc_linear_supported(o) && getenv("MGB_NO_CHAIN") == nullptr) {
             at.pack_out = s.tc_scratch; o.x_prepacked = true; at.kv_split = s.attn_split;
         }
-        if (!launch_attention(at, s.stream)) return false;
-        if (!launch_linear(o, s.stream)) return false;
+        if (!(skip & 2) && !launch_attention(at, s.stream)) return false;
+        if (!(skip & 8) && !launch_linear(o, s.stream)) return false;
         // cross-attention over the cached encoder K/V (no mask); a batched decoder step (one token per utterance) uses
         // the folded tables: one launch instead of LN+pack, q GEMM, attention, pack, o GEMM
         // a batched decoder step on the tensor-core path chains the packed activations through the kernels: the folded
@@ -196,8 +199,8 @@ static bool decoder_layers(Session & s, Tokens tok, bool want_hidden) {
         if (s.fold_ready && step) {
             const size_t tab = (size_t)s.B * s.max_text * d;
             const bool pk = chain;
-            if (!launch_xattn_folded(s.x, L.norm_xa_q, hp.eps, s.fold_xm + l * tab, s.fold_xn + l * tab, s.d_ntext, s.B, d, s.max_text,
-                                     pk ? L.norm_ff : nullptr, pk ? s.tc_scratch : nullptr, s.stream)) return false;
+            if (!(skip & 1) && !launch_xattn_folded(s.x, L.norm_xa_q, hp.eps, s.fold_xm + l * tab, s.fold_xn + l * tab, s.d_ntext, s.B, d, s.max_text,
+                                                    pk ? L.norm_ff : nullptr, pk ? s.tc_scratch : nullptr, s.stream)) return false;
             if (pk) f1.x_prepacked = true;
         } else {
         LinearArgs q;
@@ -216,8 +219,8 @@ static bool decoder_layers(Session & s, Tokens tok, bool want_hidden) {
         }
         // conv-FFN (kernel 1): LN -> W1 -> GELU -> W2 + residual
         if (chain) { f1.pack_out = s.tc_scratch2; f1.Y = nullptr; f2.tc_scratch = s.tc_scratch2; f2.x_prepacked = true; }
-        if (!launch_linear(f1, s.stream)) return false;
-        if (!launch_linear(f2, s.stream)) return false;
+        if (!(skip & 16) && !launch_linear(f1, s.stream)) return false;
+        if (!(skip & 32) && !launch_linear(f2, s.stream)) return false;
     }
     if (want_hidden) return launch_layer_norm(s.x, m.dec_norm_out, hp.eps, M, d, s.hidden, s.stream);
     return true;

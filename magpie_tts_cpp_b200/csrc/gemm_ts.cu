@@ -1,0 +1,292 @@
+// Token-stationary tcgen05 GEMM for the batched decoder step (<= 64 tokens): Y[t][n] = sum_k X[t][k] W[n][k].
+//
+// gemm_tc.cu makes the weight matrix the MMA "A" operand (128 output features per CTA), which caps a 768-row matrix at 6 CTAs
+// (x a 4-way cluster split-K = 24): at 64 tokens such a launch is bound by how fast ONE SM ingests its tiles, with 120+ SMs
+// idle (round-1 ncu: 117-320 GB/s per launch).  Here the roles are swapped: the <= 64 TOKENS are the MMA M side
+// (tcgen05.mma M = 64: accumulator rows on TMEM lanes 32 (m / 16) + m % 16) and every CTA owns a thin slice of n = 8 / 16 / 32
+// weight rows as the MMA N side, so a GEMM spreads over 96-144 CTAs, each streaming only its n x K weight bytes plus the
+// (L2-resident) activation tiles; no split-K, no cluster, no cross-CTA reduction: results are deterministic by construction.
+// Operands are the same shared-memory images gemm_tc.cu uses (SWIZZLE_128B K-major tiles of 64 k): an 8-row-aligned run of n
+// rows inside a packed 128-row weight tile is itself a valid n-row tile, so no second weight layout is needed.
+// Replaces ggml_mul_mat at src/magpie.cpp:3415, 3472, 1796, 1805 for the batched step.
+#include <cstdlib>
+
+#include "common.cuh"
+#include "gemm_tc.cuh"
+#include "kernels.cuh"
+
+namespace mgb {
+
+namespace {
+
+using bf = __nv_bfloat16;
+
+constexpr int kTsThreads = 192;          // warp 0 producer, warp 1 TMEM + MMA issue, warps 2..5 epilogue
+constexpr int kXTile = 64 * 128;         // one 64-token x 64-k bf16 image
+
+struct TsEpi {
+    int N, M;
+    const float * res; int ldr;
+    float * Y; int ldy;
+    int gelu_f16;
+    int n_q, dkv; bf * kdst; bf * vdst; const int32_t * tok_slot;
+    bf * pk_hi; bf * pk_lo;
+};
+
+enum { TS_QKV = 1, TS_RES = 2, TS_GELU_PACK = 3 };
+
+template <int NC> __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&v)[NC]);
+template <> __device__ __forceinline__ void tmem_ld_cols<8>(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+template <> __device__ __forceinline__ void tmem_ld_cols<16>(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                   "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]) : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+template <> __device__ __forceinline__ void tmem_ld_cols<32>(uint32_t taddr, uint32_t (&v)[32]) { tc::tmem_ld32(taddr, v); }
+template <> __device__ __forceinline__ void tmem_ld_cols<64>(uint32_t taddr, uint32_t (&v)[64]) {
+    uint32_t a[32], b[32];
+    tc::tmem_ld32(taddr, a); tc::tmem_ld32(taddr + 32, b);
+#pragma unroll
+    for (int j = 0; j < 32; j++) { v[j] = a[j]; v[32 + j] = b[j]; }
+}
+
+// NC = weight rows (output features) per CTA.  SPLIT > 1 (wide K: the FFN's second GEMM, K = 3072): a cluster of SPLIT CTAs
+// (grid y) shares one slice of NC rows and divides the k tiles; at 64 tokens a CTA is bound by how fast its SM ingests the
+// activation operand (786 KB for K = 3072), so the split shortens the critical path.  Ranks > 0 push their accumulator into rank
+// 0's shared memory through DSMEM; rank 0 adds them in rank order (deterministic) and runs the epilogue.
+template <int NC, int EPI, int SPLIT, int kTsStages>
+__global__ void __launch_bounds__(kTsThreads, 1) ts_linear_kernel(const bf * Wt, const bf * Xhi, const bf * Xlo, int KT_all, const TsEpi e) {
+    constexpr int kWTile = NC * 128;
+    constexpr int kStage = 2 * kXTile + (kWTile < 1024 ? 1024 : kWTile);
+    extern __shared__ unsigned char ts_smem[];
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");      // let the dependent kernel start its own prefetching
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char * tiles = reinterpret_cast<unsigned char *>(((uintptr_t)ts_smem + 1023) & ~(uintptr_t)1023);
+    uint64_t * bars = reinterpret_cast<uint64_t *>(tiles + kTsStages * kStage);
+    uint64_t * full = bars, * empty = bars + kTsStages, * acc_full = bars + 2 * kTsStages;
+    uint32_t * tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kTsStages + 1);
+    const int n0 = blockIdx.x * NC;                                      // first output feature of this CTA
+    const int rank = SPLIT > 1 ? (int)blockIdx.y : 0;
+    const int kt_lo = rank * KT_all / SPLIT, KT = (rank + 1) * KT_all / SPLIT - kt_lo;      // this CTA's k tiles [kt_lo, kt_lo + KT)
+    float * xbuf = reinterpret_cast<float *>(tiles + kTsStages * kStage + 256);             // rank 0: [SPLIT - 1][64][NC] partial accumulators
+    // every CTA reads the SAME activation tiles: with all of them walking k = 0, 1, 2, ... in lock step the 96-144 SMs would hit
+    // the same few L2 slices at the same time, so CTA c starts its walk at k tile (5 c) mod KT (a fixed order per CTA: deterministic)
+    const int kt_first = (int)((blockIdx.x * 5u) % (unsigned)KT);
+    const int KTW = KT_all;                                              // k tiles per 128-row weight tile row
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kTsStages; s++) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
+        tc::mbar_init(acc_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(tmem_slot)), "n"(NC < 32 ? 32 : NC));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0 && lane == 0) {
+        // weight rows n0 .. n0 + NC - 1 of k tile kt: an 8-row-aligned run inside the packed 128-row tile (n0 / 128, kt)
+        const unsigned char * wsrc = reinterpret_cast<const unsigned char *>(Wt) + ((size_t)(n0 / tc::BM) * KTW + kt_lo) * (tc::BM * 128) + (size_t)(n0 % tc::BM) * 128;
+        const unsigned char * hsrc = reinterpret_cast<const unsigned char *>(Xhi) + (size_t)kt_lo * kXTile, * lsrc = reinterpret_cast<const unsigned char *>(Xlo) + (size_t)kt_lo * kXTile;
+        // programmatic dependent launch: the weights do not depend on the preceding kernel (which produces the activations)
+        const int npre = KT < kTsStages ? KT : kTsStages;
+        for (int kt = 0; kt < npre; kt++) {
+            int kk = kt + kt_first; kk = kk >= KT ? kk - KT : kk;
+            tc::mbar_expect_tx(&full[kt], 2 * kXTile + kWTile);
+            tc::bulk_g2s(tiles + kt * kStage + 2 * kXTile, wsrc + (size_t)kk * (tc::BM * 128), kWTile, &full[kt]);
+        }
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        for (int kt = 0; kt < KT; kt++) {
+            const int s = kt % kTsStages;
+            int kk = kt + kt_first; kk = kk >= KT ? kk - KT : kk;
+            unsigned char * st = tiles + s * kStage;
+            if (kt >= npre) {
+                tc::mbar_wait(&empty[s], ((kt / kTsStages) & 1) ^ 1);
+                tc::mbar_expect_tx(&full[s], 2 * kXTile + kWTile);
+                tc::bulk_g2s(st + 2 * kXTile, wsrc + (size_t)kk * (tc::BM * 128), kWTile, &full[s]);
+            }
+            tc::bulk_g2s(st, hsrc + (size_t)kk * kXTile, kXTile, &full[s]);
+            tc::bulk_g2s(st + kXTile, lsrc + (size_t)kk * kXTile, kXTile, &full[s]);
+        }
+    } else if (warp == 1 && lane == 0) {
+        constexpr uint32_t idesc = tc::umma_idesc_bf16(64, NC);          // D[64 tokens x NC] += X[64 x 16] . W[NC x 16]^T
+        for (int kt = 0; kt < KT; kt++) {
+            const int s = kt % kTsStages;
+            tc::mbar_wait(&full[s], (kt / kTsStages) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t h0 = tc::smem_u32(tiles + s * kStage), l0 = h0 + kXTile, w0 = l0 + kXTile;
+#pragma unroll
+            for (int j = 0; j < tc::BK / 16; j++) {
+                tc::umma_bf16(tmem_base, tc::umma_desc_sw128(h0 + j * 32), tc::umma_desc_sw128(w0 + j * 32), idesc, (kt | j) != 0);
+                tc::umma_bf16(tmem_base, tc::umma_desc_sw128(l0 + j * 32), tc::umma_desc_sw128(w0 + j * 32), idesc, 1u);
+            }
+            tc::umma_commit(&empty[s]);
+        }
+        tc::umma_commit(acc_full);
+    }
+    if (warp >= 2) {
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        tc::mbar_wait(acc_full, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int q = warp & 3;                      // TMEM lane quarter of this warp; M = 64: rows 16 q .. 16 q + 15 on its lanes 0..15
+        const int m = 16 * q + lane;
+        if (SPLIT > 1 && rank > 0) {
+            uint32_t v[NC];
+            tmem_ld_cols<NC>(tmem_base + ((uint32_t)(q * 32) << 16), v);
+            if (lane < 16) {
+                const uint32_t local = tc::smem_u32(xbuf + ((size_t)(rank - 1) * 64 + m) * NC);
+                uint32_t remote;
+                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(0));
+#pragma unroll
+                for (int j = 0; j < NC / 4; j++)
+                    asm volatile("st.shared::cluster.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(remote + j * 16), "r"(v[4 * j]), "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3]) : "memory");
+            }
+            __syncwarp();
+        }
+    }
+    if (SPLIT > 1) {
+        __syncwarp();                                // (the producer / MMA lanes rejoin their warps before the aligned barrier)
+        asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    }
+    if (warp >= 2 && rank == 0) {
+        const int q = warp & 3;
+        const int m = 16 * q + lane;
+        uint32_t v[NC];
+        tmem_ld_cols<NC>(tmem_base + ((uint32_t)(q * 32) << 16), v);
+        if (lane < 16 && m < e.M && n0 < e.N) {
+            float y[NC];
+#pragma unroll
+            for (int j = 0; j < NC; j++) y[j] = __uint_as_float(v[j]);
+            if (SPLIT > 1) {
+#pragma unroll
+                for (int r = 0; r < SPLIT - 1; r++) {
+                    const float4 * pr = reinterpret_cast<const float4 *>(xbuf + ((size_t)r * 64 + m) * NC);
+#pragma unroll
+                    for (int j = 0; j < NC / 4; j++) { const float4 t = pr[j]; y[4 * j] += t.x; y[4 * j + 1] += t.y; y[4 * j + 2] += t.z; y[4 * j + 3] += t.w; }
+                }
+            }
+            if (EPI == TS_QKV) {
+                if (n0 < e.n_q) {
+                    float4 * dst = reinterpret_cast<float4 *>(e.Y + (size_t)m * e.ldy + n0);
+#pragma unroll
+                    for (int j = 0; j < NC / 4; j++) dst[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+                } else {
+                    const int cc = n0 - e.n_q;
+                    bf * dst = (cc < e.dkv ? e.kdst + cc : e.vdst + (cc - e.dkv)) + (size_t)e.tok_slot[m] * e.dkv;
+#pragma unroll
+                    for (int j = 0; j < NC / 8; j++) {
+                        uint32_t w[4];
+#pragma unroll
+                        for (int p = 0; p < 4; p++)
+                            w[p] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(y[8 * j + 2 * p])) |
+                                   ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(y[8 * j + 2 * p + 1])) << 16);
+                        reinterpret_cast<uint4 *>(dst)[j] = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                }
+            } else if (EPI == TS_RES) {
+                const float4 * rs = reinterpret_cast<const float4 *>(e.res + (size_t)m * e.ldr + n0);
+                float4 r[NC / 4];
+#pragma unroll
+                for (int j = 0; j < NC / 4; j++) r[j] = rs[j];
+                float4 * dst = reinterpret_cast<float4 *>(e.Y + (size_t)m * e.ldy + n0);
+#pragma unroll
+                for (int j = 0; j < NC / 4; j++)
+                    dst[j] = make_float4(y[4 * j] + r[j].x, y[4 * j + 1] + r[j].y, y[4 * j + 2] + r[j].z, y[4 * j + 3] + r[j].w);
+            } else {                                 // GELU + hi | lo tile images for the next GEMM (k tile n / 64, 16-byte chunk (n % 64) / 8)
+#pragma unroll
+                for (int j = 0; j < NC / 8; j++) {
+                    uint32_t h[4], l[4];
+#pragma unroll
+                    for (int p = 0; p < 4; p++) {
+                        const float a = gelu_ggml_fast(y[8 * j + 2 * p], e.gelu_f16), b = gelu_ggml_fast(y[8 * j + 2 * p + 1], e.gelu_f16);
+                        const bf ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
+                        const bf la = __float2bfloat16_rn(a - __bfloat162float(ha)), lb = __float2bfloat16_rn(b - __bfloat162float(hb));
+                        h[p] = (uint32_t)__bfloat16_as_ushort(ha) | ((uint32_t)__bfloat16_as_ushort(hb) << 16);
+                        l[p] = (uint32_t)__bfloat16_as_ushort(la) | ((uint32_t)__bfloat16_as_ushort(lb) << 16);
+                    }
+                    const int n = n0 + 8 * j;
+                    const size_t off = (size_t)(n >> 6) * kXTile + tc::swz_offset(m, n & 63);
+                    *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(e.pk_hi) + off) = make_uint4(h[0], h[1], h[2], h[3]);
+                    *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(e.pk_lo) + off) = make_uint4(l[0], l[1], l[2], l[3]);
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(NC < 32 ? 32 : NC));
+}
+
+template <int NC, int EPI, int SPLIT = 1, int STAGES = 8> bool launch_ts(const bf * Wt, const bf * hi, const bf * lo, int KT, const TsEpi & e, cudaStream_t stream) {
+    static DeviceOnce attr_done;
+    int dev = 0;
+    MGB_CUDA_TRY(cudaGetDevice(&dev));
+    constexpr int kWTile = NC * 128;
+    constexpr int smem = STAGES * (2 * kXTile + (kWTile < 1024 ? 1024 : kWTile)) + 1024 + 256 + (SPLIT - 1) * 64 * NC * 4;
+    static_assert(smem <= 227 * 1024, "ts_linear shared memory");
+    if (!attr_done.done(dev)) {
+        MGB_CUDA_TRY(cudaFuncSetAttribute(ts_linear_kernel<NC, EPI, SPLIT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_done.set(dev);
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(e.N / NC, SPLIT); cfg.blockDim = dim3(kTsThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    at[1].id = cudaLaunchAttributeClusterDimension;
+    at[1].val.clusterDim.x = 1; at[1].val.clusterDim.y = SPLIT; at[1].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = SPLIT > 1 ? 2 : 1;
+    MGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, ts_linear_kernel<NC, EPI, SPLIT, STAGES>, Wt, hi, lo, KT, e));
+    MGB_LAUNCH_CHECK();
+    return true;
+}
+
+}  // namespace
+
+// The three decoder-step uses with their epilogues; everything else stays on gemm_tc.cu.  hi / lo: packed activations (MT = 64).
+bool ts_linear_supported(const LinearArgs & a) {
+    if (getenv("MGB_NO_TS") != nullptr) return false;
+    if (a.M > 64 || a.W.taps != 1 || a.W.K % 64 != 0 || a.bias || a.W.N % 128 != 0) return false;
+    const bool qkv = a.n_q >= 0 && !a.res && a.act == ACT_NONE && !a.pack_out && a.Y && a.n_q % 16 == 0 && a.dkv % 16 == 0 && a.kdst && a.vdst && (a.ldy % 4) == 0;
+    const bool resid = a.n_q < 0 && a.res && a.act == ACT_NONE && !a.pack_out && a.Y && (a.ldr % 4) == 0 && (a.ldy % 4) == 0;
+    const bool gpack = a.n_q < 0 && !a.res && a.act == ACT_GELU && a.pack_out && !a.Y;
+    return qkv || resid || gpack;
+}
+
+bool launch_linear_ts(const LinearArgs & a, const void * hi, const void * lo, cudaStream_t stream) {
+    TsEpi e;
+    e.N = a.W.N; e.M = a.M; e.res = a.res; e.ldr = a.ldr; e.Y = a.Y; e.ldy = a.ldy; e.gelu_f16 = a.gelu_f16;
+    e.n_q = a.n_q; e.dkv = a.dkv; e.kdst = (bf *)a.kdst; e.vdst = (bf *)a.vdst; e.tok_slot = a.tok_slot;
+    e.pk_hi = nullptr; e.pk_lo = nullptr;
+    if (a.pack_out) { e.pk_hi = (bf *)a.pack_out; e.pk_lo = e.pk_hi + (size_t)64 * a.W.N; }
+    const int KT = a.W.K / 64;
+    const bf * W = (const bf *)a.W.tiles;
+    // One-CTA slices for the K = 768 GEMMs (QKV 144 CTAs, O 96, FF1 96).  The wide-K GEMM (FF2, K = 3072) is bound by how fast ONE
+    // SM ingests the 786 KB activation operand (the same 21 us with 24, 48 or 96 one-CTA slices), so its 32-row slices are shared
+    // by a 4-CTA cluster that divides the k tiles (10 us).  Measured at 64 utterances, us per step: no split 1331, FF2 split over
+    // 2 / 4 CTAs 1241 / 1201; cluster slices for the K = 768 GEMMs as well (64 rows x 4, 32 x 4, 64 x 3): 1343 -- the cluster
+    // launch and the DSMEM reduction cost more than the ingest they save (MGB_TS_SHAPE=2 keeps that variant for A/B, 0 = no split).
+    static const int shaped = getenv("MGB_TS_SHAPE") ? atoi(getenv("MGB_TS_SHAPE")) : 1;
+    const bf * h = (const bf *)hi, * l = (const bf *)lo;
+    if (a.n_q >= 0) {
+        if (shaped == 2 && KT % 4 == 0 && a.W.N % 64 == 0 && a.n_q % 64 == 0 && a.dkv % 64 == 0) return launch_ts<64, TS_QKV, 4, 4>(W, h, l, KT, e, stream);
+        return launch_ts<16, TS_QKV>(W, h, l, KT, e, stream);
+    }
+    if (a.res) {
+        if (shaped && KT >= 32 && KT % 4 == 0) return launch_ts<32, TS_RES, 4, 8>(W, h, l, KT, e, stream);        // FF2: 24 slices x 4 CTAs, 12 k tiles each
+        if (shaped == 2 && KT % 4 == 0) return launch_ts<32, TS_RES, 4, 4>(W, h, l, KT, e, stream);
+        return launch_ts<8, TS_RES>(W, h, l, KT, e, stream);
+    }
+    if (shaped == 2 && KT % 3 == 0 && a.W.N % 64 == 0) return launch_ts<64, TS_GELU_PACK, 3, 4>(W, h, l, KT, e, stream);
+    return launch_ts<32, TS_GELU_PACK>(W, h, l, KT, e, stream);
+}
+
+}  // namespace mgb

@@ -48,6 +48,9 @@ bool   tc_pack_weights(const void * W, int N, int K, void * Wt, cudaStream_t str
 size_t tc_scratch_bytes(int M, int K);
 bool   tc_linear_supported(const LinearArgs & a);
 bool   launch_linear_tc(const LinearArgs & a, cudaStream_t stream);
+// token-stationary variant for <= 64 tokens (gemm_ts.cu): tokens on the MMA M side, 8..32 weight rows per CTA, 96-144 CTAs per GEMM
+bool   ts_linear_supported(const LinearArgs & a);
+bool   launch_linear_ts(const LinearArgs & a, const void * hi, const void * lo, cudaStream_t stream);
 
 struct AttnArgs {
     int precision = 0;
