@@ -408,7 +408,7 @@ mgb_session * mgb_session_new_paged(mgb_model * mm, int batch, int max_text, int
     }
     // (launch_xattn_folded holds one score per text position in shared memory: up to 512 positions; longer text capacities keep
     //  the q GEMM + attention + o GEMM kernels)
-    if (m->precision == MGB_PREC_BF16 && batch >= 2 && dxa == 128 && max_text <= 512 && getenv("MGB_NO_XFOLD") == nullptr &&
+    if (m->precision == MGB_PREC_BF16 && batch >= 2 && dxa == 128 && max_text <= 512 && d % 256 == 0 && d <= 768 && getenv("MGB_NO_XFOLD") == nullptr &&
         (size_t)L * batch * max_text * d * 8 <= ((size_t)8 << 30)) {
         const size_t tab = (size_t)L * batch * max_text * d;
         if (!s->alloc(s->fold_xm, tab) || !s->alloc(s->fold_xn, tab)) return nullptr;

@@ -663,21 +663,28 @@ __device__ __forceinline__ void dsmem_store(float * local, int rank, float v) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(rank));
     asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(v) : "memory");
 }
+// Written for LATENCY (the kernel sits in the dependent chain of the step, 12 times): every pass over a table issues all of a
+// thread's loads before it uses any (one L2 round trip per pass instead of one per row), LayerNorm statistics are taken in one
+// pass (sum and sum of squares together), and the second LayerNorm's two statistics cross the cluster in ONE exchange.
+constexpr int kXRowsPerWarp = 16;      // score rows a warp keeps in flight (E <= 8 warps x 16 = 128 per round)
+constexpr int kXRG = 5;                // row groups of the N pass: 5 x 48 float4 column groups = 240 threads
 __global__ void __launch_bounds__(kXT) xattn_folded_kernel(const XFoldParams p) {
-    __shared__ float xl[256];                 // this CTA's columns: LN(x), later the updated row
-    __shared__ float part[kXC][512];          // partial scores of every rank (written through DSMEM)
+    __shared__ __align__(16) float xl[256];         // this CTA's columns: LN(x), later LN2(updated row)
+    __shared__ float part[kXC][512];                // partial scores of every rank (written through DSMEM)
     __shared__ float prob[512];
-    __shared__ float stat[2][kXC];            // partial sums for the second LayerNorm
-    __shared__ float red[32];
+    __shared__ __align__(16) float opart[kXRG][256]; // N pass: partial outputs of the row groups
+    __shared__ float stat[2][kXC];                  // partial (sum, sum of squares) of the updated row, per rank
+    __shared__ float red[2][8];
     const int u = blockIdx.x / kXC, rank = blockIdx.x % kXC;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int d = p.d, dc = d / kXC, c0 = rank * dc, E = p.n_ctx[u];
     float * xr = p.x + (size_t)u * d;
+    const float * xm = p.xm + (size_t)u * p.max_text * d + c0, * xn = p.xn + (size_t)u * p.max_text * d + c0;
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");      // the following GEMM may start prefetching its weights
     {
         // programmatic dependent of the O-projection GEMM: this CTA's quarter of the (static) tables is pulled into L2 while
         // that kernel is still running
-        const char * m0 = (const char *)(p.xm + (size_t)u * p.max_text * d + c0), * n0 = (const char *)(p.xn + (size_t)u * p.max_text * d + c0);
+        const char * m0 = (const char *)xm, * n0 = (const char *)xn;
         const int lines = dc * 4 / 128;                 // 128-byte lines per table row quarter
         for (int i = tid; i < E * lines; i += kXT) {
             const size_t off = (size_t)(i / lines) * d * 4 + (size_t)(i % lines) * 128;
@@ -686,68 +693,105 @@ __global__ void __launch_bounds__(kXT) xattn_folded_kernel(const XFoldParams p) 
         }
         asm volatile("griddepcontrol.wait;" ::: "memory");
     }
-    // LayerNorm statistics over the whole row, redundantly in every CTA (magpie.cpp:2237-2259)
-    float s = 0.0f;
-    for (int i = tid; i < d; i += kXT) s += xr[i];
-    const float mean = block_sum(s, red) / (float)d;
-    float s2 = 0.0f;
-    for (int i = tid; i < d; i += kXT) { const float c = xr[i] - mean; s2 += c * c; }
-    const float scale = 1.0f / sqrtf(block_sum(s2, red) / (float)d + p.eps);
+    // LayerNorm statistics over the whole row in one pass, redundantly in every CTA (magpie.cpp:2237-2259)
+    float xv[4], s = 0.0f, ss = 0.0f;
+#pragma unroll
+    for (int q = 0; q < 4; q++) { const int i = tid + q * kXT; xv[q] = i < d ? xr[i] : 0.0f; s += xv[q]; ss = fmaf(xv[q], xv[q], ss); }
     const float xraw = tid < dc ? xr[c0 + tid] : 0.0f;
-    if (tid < dc) xl[tid] = ((xraw - mean) * scale) * p.ln_w[c0 + tid];
+    const float lw = tid < dc ? p.ln_w[c0 + tid] : 0.0f;
+    s = warp_sum(s); ss = warp_sum(ss);
+    if (lane == 0) { red[0][warp] = s; red[1][warp] = ss; }
     __syncthreads();
-    const float * xm = p.xm + (size_t)u * p.max_text * d + c0, * xn = p.xn + (size_t)u * p.max_text * d + c0;
-    // partial scores over this CTA's columns, broadcast to the cluster
-    for (int j = warp; j < E; j += kXT / 32) {
-        const float * mr = xm + (size_t)j * d;
-        float a = 0.0f;
-        for (int i = lane * 2; i < dc; i += 64) {
-            const float2 m2 = *reinterpret_cast<const float2 *>(mr + i);
-            a = fmaf(m2.x, xl[i], a); a = fmaf(m2.y, xl[i + 1], a);
+    s = ((red[0][0] + red[0][1]) + (red[0][2] + red[0][3])) + ((red[0][4] + red[0][5]) + (red[0][6] + red[0][7]));
+    ss = ((red[1][0] + red[1][1]) + (red[1][2] + red[1][3])) + ((red[1][4] + red[1][5]) + (red[1][6] + red[1][7]));
+    const float mean = s / (float)d;
+    const float scale = 1.0f / sqrtf(fmaxf(ss / (float)d - mean * mean, 0.0f) + p.eps);
+    if (tid < dc) xl[tid] = ((xraw - mean) * scale) * lw;
+    __syncthreads();
+    // partial scores over this CTA's columns, broadcast to the cluster: warp w owns rows w, w + 8, ...; the loads of up to 16 of
+    // its rows are all issued before the first is used
+    const int nf2 = dc / 64;                            // float2 per lane and row (dc = 192: 3)
+    for (int jb = 0; jb < E; jb += 8 * kXRowsPerWarp) {
+        float2 mv[kXRowsPerWarp][3];
+#pragma unroll
+        for (int r = 0; r < kXRowsPerWarp; r++) {
+            const int j = jb + warp + 8 * r;
+#pragma unroll
+            for (int q = 0; q < 3; q++)
+                mv[r][q] = (j < E && q < nf2) ? *reinterpret_cast<const float2 *>(xm + (size_t)j * d + lane * 2 + q * 64) : make_float2(0.0f, 0.0f);
         }
-        a = warp_sum(a);
-        if (lane < kXC) dsmem_store(&part[rank][j], lane, a);
+#pragma unroll
+        for (int r = 0; r < kXRowsPerWarp; r++) {
+            const int j = jb + warp + 8 * r;
+            if (j >= E) break;                          // warp-uniform
+            float a = 0.0f;
+#pragma unroll
+            for (int q = 0; q < 3; q++) { a = fmaf(mv[r][q].x, xl[lane * 2 + q * 64], a); a = fmaf(mv[r][q].y, xl[lane * 2 + q * 64 + 1], a); }
+            a = warp_sum(a);
+            if (lane < kXC) dsmem_store(&part[rank][j], lane, a);
+        }
     }
     cluster_sync_all();
+    // softmax over the E scores (each the sum of the four ranks' partials, in rank order): every warp redundantly, shuffles only
     float mx = -INFINITY;
-    for (int j = tid; j < E; j += kXT) {
-        float sc = 0.0f;
-#pragma unroll
-        for (int r = 0; r < kXC; r++) sc += part[r][j];
-        prob[j] = sc;
-        mx = fmaxf(mx, sc);
-    }
-    // block max / sum of exp (E <= 512: at most two entries per thread)
+    for (int j = lane; j < E; j += 32) mx = fmaxf(mx, ((part[0][j] + part[1][j]) + part[2][j]) + part[3][j]);
     mx = warp_max(mx);
-    __syncthreads();
-    if (lane == 0) red[warp] = mx;
-    __syncthreads();
-    mx = red[0];
-    for (int w = 1; w < kXT / 32; w++) mx = fmaxf(mx, red[w]);
     float se = 0.0f;
-    for (int j = tid; j < E; j += kXT) { const float e = expf(prob[j] - mx); prob[j] = e; se += e; }
-    const float inv = 1.0f / block_sum(se, red);
+    for (int j = lane; j < E; j += 32) {
+        const float e = expf((((part[0][j] + part[1][j]) + part[2][j]) + part[3][j]) - mx);
+        if (warp == 0) prob[j] = e;
+        se += e;
+    }
+    const float inv = 1.0f / warp_sum(se);
+    __syncthreads();
+    // out[c] = sum_j p_j N[j][c]: thread = (float4 column group cg, row group rg); rows rg, rg + 5, ... of the group are all
+    // requested before the first is used; the 5 row groups are then added in a fixed order
+    {
+        const int ncg = dc / 4;                         // 48
+        const int cg = tid % ncg, rg = tid / ncg;
+        float4 o = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (rg < kXRG) {
+            for (int jb = rg; jb < E; jb += kXRG * 8) {
+                float4 nv[8];
+#pragma unroll
+                for (int r = 0; r < 8; r++) {
+                    const int j = jb + r * kXRG;
+                    nv[r] = j < E ? *reinterpret_cast<const float4 *>(xn + (size_t)j * d + cg * 4) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                }
+#pragma unroll
+                for (int r = 0; r < 8; r++) {
+                    const int j = jb + r * kXRG;
+                    const float pj = j < E ? prob[j] * inv : 0.0f;
+                    o.x = fmaf(pj, nv[r].x, o.x); o.y = fmaf(pj, nv[r].y, o.y); o.z = fmaf(pj, nv[r].z, o.z); o.w = fmaf(pj, nv[r].w, o.w);
+                }
+            }
+            *reinterpret_cast<float4 *>(&opart[rg][cg * 4]) = o;
+        }
+    }
     __syncthreads();
     float v = 0.0f;
     if (tid < dc) {
-        float o = 0.0f;
-        for (int j = 0; j < E; j++) o = fmaf(prob[j] * inv, xn[(size_t)j * d + tid], o);
-        v = xraw + o;
+        v = xraw + ((((opart[0][tid] + opart[1][tid]) + opart[2][tid]) + opart[3][tid]) + opart[4][tid]);
         xr[c0 + tid] = v;
     }
     if (!p.pk_hi) { cluster_sync_all(); return; }         // (no CTA may exit while a peer can still write into its shared memory)
     // LayerNorm of the updated row with the NEXT sub-block's weight -> bf16 hi | lo tile images (gemm_tc.cu layout, one
     // 64-token tile): the packing kernel in front of the FFN's first GEMM is not needed
-    const float ps = block_sum(tid < dc ? v : 0.0f, red);
-    if (tid < kXC) dsmem_store(&stat[0][rank], tid, ps);
+    const float pw = tid < dc ? p.pack_ln_w[c0 + tid] : 0.0f;
+    float ps = warp_sum(tid < dc ? v : 0.0f), pq = warp_sum(tid < dc ? v * v : 0.0f);
+    __syncthreads();                                      // (red is reused)
+    if (lane == 0) { red[0][warp] = ps; red[1][warp] = pq; }
+    __syncthreads();
+    if (tid < 2 * kXC) {
+        const int which = tid / kXC, dst = tid % kXC;
+        const float * r8 = red[which];
+        dsmem_store(&stat[which][rank], dst, ((r8[0] + r8[1]) + (r8[2] + r8[3])) + ((r8[4] + r8[5]) + (r8[6] + r8[7])));
+    }
     cluster_sync_all();
-    const float mean2 = (stat[0][0] + stat[0][1] + stat[0][2] + stat[0][3]) / (float)d;
-    const float cv = tid < dc ? v - mean2 : 0.0f;
-    const float pq = block_sum(cv * cv, red);
-    if (tid < kXC) dsmem_store(&stat[1][rank], tid, pq);
-    cluster_sync_all();
-    const float scale2 = 1.0f / sqrtf((stat[1][0] + stat[1][1] + stat[1][2] + stat[1][3]) / (float)d + p.eps);
-    if (tid < dc) xl[tid] = (cv * scale2) * p.pack_ln_w[c0 + tid];
+    const float mean2 = (((stat[0][0] + stat[0][1]) + stat[0][2]) + stat[0][3]) / (float)d;
+    const float ex2 = (((stat[1][0] + stat[1][1]) + stat[1][2]) + stat[1][3]) / (float)d;
+    const float scale2 = 1.0f / sqrtf(fmaxf(ex2 - mean2 * mean2, 0.0f) + p.eps);
+    if (tid < dc) xl[tid] = ((v - mean2) * scale2) * pw;
     __syncthreads();
     for (int kc = tid; kc < dc / 8; kc += kXT) {
         uint32_t h[4], l[4];
@@ -768,7 +812,8 @@ __global__ void __launch_bounds__(kXT) xattn_folded_kernel(const XFoldParams p) 
 
 bool launch_xattn_folded(float * x, const float * ln_w, float eps, const float * xm, const float * xn, const int32_t * n_ctx, int B, int d,
                          int max_text, const float * pack_ln_w, void * pack_out, cudaStream_t stream) {
-    if (d > 1024 || max_text > 512 || d % (kXC * 8) != 0) { set_error("xattn_folded: shape not supported"); return false; }
+    // (columns per rank: <= 256 with whole float4 / 64-column groups, at most 3 float2 per lane and row, 5 x dc / 4 <= 256 threads)
+    if (d > 768 || max_text > 512 || d % (kXC * 64) != 0 || kXRG * (d / kXC / 4) > kXT) { set_error("xattn_folded: shape not supported"); return false; }
     if (pack_out && B > 64) { set_error("xattn_folded: packed output needs one token tile"); return false; }
     XFoldParams p{x, ln_w, eps, xm, xn, n_ctx, d, max_text, pack_ln_w, (__nv_bfloat16 *)pack_out,
                   pack_out ? (__nv_bfloat16 *)pack_out + (size_t)64 * d : nullptr};
