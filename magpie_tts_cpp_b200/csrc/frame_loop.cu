@@ -506,7 +506,118 @@ __device__ __noinline__ int cta_sample_top_k(LoopSmem & S, float * logits, int V
 // Latency structure: the K / V rows of the OLD keys do not depend on this step, so their loads are issued before the
 // wait for q; the new key (position pos, last split only) is taken from the exchange, not from the cache, and its
 // cache rows are written off the critical path.
-__device__ __forceinline__ void attention_item(LoopSmem & S, const FrameLoopParams & p, Ctx & c, bf * kcl, bf * vcl,
+__device__ __forceinline__ void attention_item_small(LoopSmem & S, const FrameLoopParams & p, Ctx & c, bf * kcl, bf * vcl,
+                                               int h, int k0, int k1, int pos) {
+    const int cw = c.cw, lane = c.lane, ctid = c.ctid;
+    const unsigned flag = c.seq - 1;
+    const bool has_new = pos >= k0 && pos < k1;
+    const int ke = has_new ? k1 - 1 : k1;                       // old keys [k0, ke); pos == k1 - 1 when has_new
+    const int nw = min(kCW, (ke - k0 + 31) / 32);                // warps holding a chunk (one chunk per warp: per <= 480)
+    // 1. old keys: this warp's chunk of 32 keys; loads in flight while q is awaited
+    const int c0 = k0 + cw * 32, j = c0 + lane;
+    const int cnt = max(0, min(32, ke - c0));
+    uint4 kv[8];
+    uint32_t vraw[32];
+    if (j < ke) {
+        const bf * kr = kcl + (size_t)j * D + h * DH;
+#pragma unroll
+        for (int q = 0; q < 8; q++) kv[q] = __ldcg(reinterpret_cast<const uint4 *>(kr) + q);
+    } else {
+#pragma unroll
+        for (int q = 0; q < 8; q++) kv[q] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    {
+        const bf * vbase = vcl + (size_t)c0 * D + h * DH + lane * 2;
+#pragma unroll
+        for (int jj = 0; jj < 32; jj++) vraw[jj] = jj < cnt ? __ldcg(reinterpret_cast<const uint32_t *>(vbase + (size_t)jj * D)) : 0u;
+    }
+    // 2. q_h (all items) and k_h / v_h of this step (last split): warps 0..2 poll <= 23 packets each
+    if (cw < 3 && (cw == 0 || has_new)) {
+        const int f0 = cw * D + h * DH;
+        const int p0 = f0 / 3, p1 = (f0 + DH - 1) / 3;
+        if (lane <= p1 - p0) {
+            const uint4 v = poll_pkt(c.xin + p.xoff[X_QKV] + p0 + lane, flag);
+            const int g = 3 * (p0 + lane) - f0;
+            const float vv[3] = {__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z)};
+#pragma unroll
+            for (int q3 = 0; q3 < 3; q3++) {
+                const int gi = g + q3;
+                if (gi >= 0 && gi < DH) {
+                    if (cw == 0) S.qh[gi] = vv[q3];
+                    else {          // the cache holds bf16: use the rounded value now, as later steps will
+                        const bf r = __float2bfloat16_rn(vv[q3]);
+                        (cw == 1 ? S.knew : S.vnew)[gi] = __bfloat162float(r);
+                        (cw == 1 ? kcl : vcl)[(size_t)pos * D + h * DH + gi] = r;
+                    }
+                }
+            }
+        }
+    }
+    cbar();
+    LOOP_STAMP();
+    float mx = -INFINITY, lsum = 0.0f, acc0 = 0.0f, acc1 = 0.0f;       // lane owns dims 2*lane, 2*lane+1
+    if (cw < nw) {
+        float s = -INFINITY;
+        if (j < ke) {
+            float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f, d3 = 0.0f;
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const float4 qa = *reinterpret_cast<const float4 *>(S.qh + q * 8), qb = *reinterpret_cast<const float4 *>(S.qh + q * 8 + 4);
+                d0 = fmaf(bf16lo(kv[q].x), qa.x, d0); d1 = fmaf(bf16hi(kv[q].x), qa.y, d1);
+                d2 = fmaf(bf16lo(kv[q].y), qa.z, d2); d3 = fmaf(bf16hi(kv[q].y), qa.w, d3);
+                d0 = fmaf(bf16lo(kv[q].z), qb.x, d0); d1 = fmaf(bf16hi(kv[q].z), qb.y, d1);
+                d2 = fmaf(bf16lo(kv[q].w), qb.z, d2); d3 = fmaf(bf16hi(kv[q].w), qb.w, d3);
+            }
+            s = ((d0 + d1) + (d2 + d3)) * 0.125f;                     // 1/sqrt(64)
+        }
+        mx = warp_max(s);
+        const float pj = (j < ke) ? expf(s - mx) : 0.0f;
+        lsum = warp_sum(pj);
+        float a0 = 0.0f, a1 = 0.0f, b0 = 0.0f, b1 = 0.0f;
+#pragma unroll
+        for (int jj = 0; jj < 32; jj += 2) {
+            const float pa = __shfl_sync(0xffffffffu, pj, jj), pb = __shfl_sync(0xffffffffu, pj, jj + 1);
+            a0 = fmaf(pa, bf16lo(vraw[jj]), a0); a1 = fmaf(pa, bf16hi(vraw[jj]), a1);
+            b0 = fmaf(pb, bf16lo(vraw[jj + 1]), b0); b1 = fmaf(pb, bf16hi(vraw[jj + 1]), b1);
+        }
+        acc0 = a0 + b0; acc1 = a1 + b1;
+    }
+    if (has_new && cw == nw % kCW) {          // the new key: one more online-softmax update on a warp of its own if there is one
+        const float s = warp_sum(fmaf(S.knew[lane], S.qh[lane], S.knew[lane + 32] * S.qh[lane + 32])) * 0.125f;
+        const float mnew = fmaxf(mx, s);
+        const float corr = (mx == -INFINITY) ? 0.0f : expf(mx - mnew);
+        const float pn = expf(s - mnew);
+        lsum = lsum * corr + pn;
+        acc0 = fmaf(pn, S.vnew[lane * 2], acc0 * corr); acc1 = fmaf(pn, S.vnew[lane * 2 + 1], acc1 * corr);
+        mx = mnew;
+    }
+    const int nm = has_new ? max(nw, nw % kCW + 1) : nw;        // warps that hold a partial
+    if (cw < nm) {
+        if (lane == 0) { S.am[cw] = mx; S.al[cw] = lsum; }
+        S.aacc[cw * 64 + lane * 2] = acc0; S.aacc[cw * 64 + lane * 2 + 1] = acc1;
+    }
+    cbar();
+    if (ctid < 64) {
+        float M = S.am[0];
+        for (int w = 1; w < nm; w++) M = fmaxf(M, S.am[w]);
+        float Ls = 0.0f, o = 0.0f;
+        for (int w = 0; w < nm; w++) {
+            const float fct = (S.am[w] == -INFINITY) ? 0.0f : expf(S.am[w] - M);
+            Ls += fct * S.al[w]; o += fct * S.aacc[w * 64 + ctid];
+        }
+        S.aout[2 + ctid] = o;
+        if (ctid == 0) { S.aout[0] = M; S.aout[1] = Ls; }
+    }
+    cbar();
+    if (ctid < 22 * kR) {
+        const int pk = ctid % 22, r = ctid / 22;
+        st_pkt(p.xbuf + (size_t)r * c.rstride + p.xoff[X_ATT] + c.b * 22 + pk, S.aout[3 * pk], S.aout[3 * pk + 1], S.aout[3 * pk + 2], c.seq);
+    }
+}
+
+// items longer than 480 keys (KV beyond 2 880 cached keys, or fewer key splits): the same partial with the warps scanning further
+// 32-key chunks after the wait for q (online-softmax merge per warp); a separate branch, the common case keeps its instruction sequence
+__device__ __forceinline__ void attention_item_long(LoopSmem & S, const FrameLoopParams & p, Ctx & c, bf * kcl, bf * vcl,
                                                int h, int k0, int k1, int pos) {
     const int cw = c.cw, lane = c.lane, ctid = c.ctid;
     const unsigned flag = c.seq - 1;
@@ -634,6 +745,13 @@ __device__ __forceinline__ void attention_item(LoopSmem & S, const FrameLoopPara
     }
 }
 
+__device__ __forceinline__ void attention_item(LoopSmem & S, const FrameLoopParams & p, Ctx & c, bf * kcl, bf * vcl,
+                                               int h, int k0, int k1, int pos) {
+    const int ke = (pos >= k0 && pos < k1) ? k1 - 1 : k1;
+    if (ke - k0 <= 32 * kCW) attention_item_small(S, p, c, kcl, vcl, h, k0, k1, pos);
+    else attention_item_long(S, p, c, kcl, vcl, h, k0, k1, pos);
+}
+
 // ---- combine the attention partials of all (head, split) items -> S.av ------------------------------------------------
 __device__ __forceinline__ void attention_combine(LoopSmem & S, const FrameLoopParams & p, Ctx & c, int S_split) {
     poll_vec(c.xin + p.xoff[X_ATT], H * S_split * 22, c.seq - 1, S.vec, H * S_split * 66, c.ctid);
@@ -659,8 +777,58 @@ __device__ __forceinline__ void attention_combine(LoopSmem & S, const FrameLoopP
 // Text tokens are handled 30 at a time (two table rows per warp).  The first 30 rows are activation independent and are
 // fetched BEFORE the wait for x (all of a "Hello, world!"-sized text); longer texts (up to kLoopMaxCtx tokens) stream the
 // remaining rows from L2 after it, 2 x 3 KB per warp and round.
+// E <= 30 (two table rows per warp, everything in registers before the wait for x): the latency-critical common case
+__device__ __forceinline__ void cross_attention_small(LoopSmem & S, const FrameLoopParams & p, Ctx & c, const LoopLayer & Ly) {
+    const int cw = c.cw, lane = c.lane, E = p.E;
+    float w3[3], v[3];
+    ln_weights3<D>(Ly.n_xq, c.ctid, w3);
+    const int r0 = c.b * RO, nr = max(0, min(RO, D - r0));
+    // the tables are activation independent: fetch this warp's rows before waiting for x
+    const int j0 = cw, j1 = cw + kCW;
+    float4 m0[6], m1[6];
+#pragma unroll
+    for (int q = 0; q < 6; q++) {
+        m0[q] = j0 < E ? __ldg(reinterpret_cast<const float4 *>(Ly.xm + (size_t)j0 * D + q * 128 + lane * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        m1[q] = j1 < E ? __ldg(reinterpret_cast<const float4 *>(Ly.xm + (size_t)j1 * D + q * 128 + lane * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float nval = 0.0f;
+    if (cw < nr && lane < E) nval = __ldg(Ly.xn + (size_t)lane * D + r0 + cw);
+    load3_poll<D>(c.xin + p.xoff[X_XA], c.seq - 1, S.xs, c.ctid, v);
+    LOOP_STAMP();
+    ln3<D>(S, v, w3, S.vec, p.eps, c);
+    float d0 = 0.0f, d1 = 0.0f;
+#pragma unroll
+    for (int q = 0; q < 6; q++) {
+        const float4 xv = *reinterpret_cast<const float4 *>(S.vec + q * 128 + lane * 4);
+        d0 = fmaf(m0[q].x, xv.x, d0); d0 = fmaf(m0[q].y, xv.y, d0); d0 = fmaf(m0[q].z, xv.z, d0); d0 = fmaf(m0[q].w, xv.w, d0);
+        d1 = fmaf(m1[q].x, xv.x, d1); d1 = fmaf(m1[q].y, xv.y, d1); d1 = fmaf(m1[q].z, xv.z, d1); d1 = fmaf(m1[q].w, xv.w, d1);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { d0 += __shfl_xor_sync(0xffffffffu, d0, o); d1 += __shfl_xor_sync(0xffffffffu, d1, o); }
+    if (lane == 0) { if (j0 < E) S.sc[j0] = d0; if (j1 < E) S.sc[j1] = d1; }
+    cbar();
+    // softmax over the E tokens and this CTA's output rows: warp r < nr computes row r, warp 0 emits
+    if (cw < nr) {
+        const float sj = lane < E ? S.sc[lane] : -INFINITY;
+        const float mxs = warp_max(sj);
+        const float e = lane < E ? expf(sj - mxs) : 0.0f;
+        float sum = e, o = e * nval;
+#pragma unroll
+        for (int of = 16; of > 0; of >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, of); o += __shfl_xor_sync(0xffffffffu, o, of); }
+        if (lane == 0) S.outv[cw] = o * (1.0f / sum) + S.xs[r0 + cw];
+    }
+    cbar();
+    const int npk = (nr + 2) / 3;
+    if (c.ctid < npk * kR) {
+        const int pk = c.ctid % npk, r = c.ctid / npk;
+        st_pkt(p.xbuf + (size_t)r * c.rstride + p.xoff[X_XB] + r0 / 3 + pk, S.outv[3 * pk], S.outv[3 * pk + 1], S.outv[3 * pk + 2], c.seq);
+    }
+}
+
+// longer texts: the same phase with the table rows beyond the first 30 streamed from L2 after the wait (a separate branch: the
+// common case keeps the round-1 instruction sequence)
 constexpr int kScOff = 1024;             // scores live in S.vec[kScOff .. kScOff + kLoopMaxCtx) (LN(x) occupies [0, D))
-__device__ __forceinline__ void cross_attention(LoopSmem & S, const FrameLoopParams & p, Ctx & c, const LoopLayer & Ly) {
+__device__ __forceinline__ void cross_attention_long(LoopSmem & S, const FrameLoopParams & p, Ctx & c, const LoopLayer & Ly) {
     const int cw = c.cw, lane = c.lane, E = p.E;
     float * sc = S.vec + kScOff;
     float w3[3], v[3];
@@ -723,6 +891,11 @@ __device__ __forceinline__ void cross_attention(LoopSmem & S, const FrameLoopPar
         const int pk = c.ctid % npk, r = c.ctid / npk;
         st_pkt(p.xbuf + (size_t)r * c.rstride + p.xoff[X_XB] + r0 / 3 + pk, S.outv[3 * pk], S.outv[3 * pk + 1], S.outv[3 * pk + 2], c.seq);
     }
+}
+
+__device__ __forceinline__ void cross_attention(LoopSmem & S, const FrameLoopParams & p, Ctx & c, const LoopLayer & Ly) {
+    if (p.E <= 2 * kCW) cross_attention_small(S, p, c, Ly);
+    else cross_attention_long(S, p, c, Ly);
 }
 
 __global__ void __launch_bounds__(kThreads, 1) frame_loop_kernel(const FrameLoopParams p) {

@@ -199,15 +199,15 @@ __device__ __forceinline__ void attn_dsmem_store(float * local, unsigned rank, f
 }
 constexpr int kAttnMaxSplit = 8;
 
-template <typename T, int DH, int SPLIT = 0>      // SPLIT: 0 = one CTA per (head, token); 1 / 2 = pipelined scan + cluster key split compiled for 2 / 3 resident CTAs per SM
-__global__ void __launch_bounds__(kAttnWarps * 32, SPLIT == 2 ? 3 : 0) attention_kernel(const AttnParams p) {
+template <typename T, int DH, int SPLIT = 0, int NW = kAttnWarps>      // NW warps per CTA; SPLIT: 0 = one CTA per (head, token); 1 / 2 = pipelined scan + cluster key split compiled for 2 / 3 resident CTAs per SM
+__global__ void __launch_bounds__(NW * 32, SPLIT == 2 ? 3 : 0) attention_kernel(const AttnParams p) {
     constexpr int VEC = WT<T>::VEC;
     constexpr int LPK = DH / VEC;            // lanes per key row
     constexpr int KPI = 32 / LPK;            // keys per warp instruction
     constexpr int U = 4;                     // key slots in flight per lane
     static_assert(LPK >= 1 && LPK <= 32 && (LPK & (LPK - 1)) == 0, "head dim / vector width must be a power of two <= 32");
-    __shared__ float s_m[kAttnWarps], s_l[kAttnWarps];
-    __shared__ float s_acc[kAttnWarps][DH];
+    __shared__ float s_m[NW], s_l[NW];
+    __shared__ float s_acc[NW][DH];
     __shared__ float x_m[SPLIT ? kAttnMaxSplit : 1], x_l[SPLIT ? kAttnMaxSplit : 1], x_o[SPLIT ? kAttnMaxSplit : 1][DH];   // rank 0: the peers' partials
     const int t = blockIdx.y, h = blockIdx.x;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(kAttnWarps * 32, SPLIT == 2 ? 3 : 0) attention
         // pulled into L2 while that kernel is still running; q and the new key's row are read after the wait
         const char * Kp = (const char *)p.K + (size_t)(h * DH) * sizeof(T);
         const char * Vp = (const char *)p.V + (size_t)(h * DH) * sizeof(T);
-        for (int j = k0 + tid; j < min(min(k1, nk - 1), k0 + p.pf_keys); j += kAttnWarps * 32) {
+        for (int j = k0 + tid; j < min(min(k1, nk - 1), k0 + p.pf_keys); j += NW * 32) {
             asm volatile("prefetch.global.L2 [%0];" ::"l"(Kp + krow(j) * ld * sizeof(T)));
             asm volatile("prefetch.global.L2 [%0];" ::"l"(Vp + krow(j) * ld * sizeof(T)));
         }
@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(kAttnWarps * 32, SPLIT == 2 ? 3 : 0) attention
         // long KV: software-pipelined scan.  The raw 16-byte K / V words of the NEXT 16 keys of the warp are requested before the
         // current ones are used (twice the bytes in flight per warp, loads overlap the softmax arithmetic); same arithmetic and
         // order per key as the loop below.
-        constexpr int STEP = kAttnWarps * KPI * U;
+        constexpr int STEP = NW * KPI * U;
         uint4 kr[U], vr[U];
         int base = k0 + warp * (KPI * U);
 #pragma unroll
@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(kAttnWarps * 32, SPLIT == 2 ? 3 : 0) attention
             }
         }
     } else {
-    for (int base = k0 + warp * (KPI * U); base < k1; base += kAttnWarps * KPI * U) {
+    for (int base = k0 + warp * (KPI * U); base < k1; base += NW * KPI * U) {
         float kk[U][VEC], vv[U][VEC], sc[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
@@ -372,9 +372,9 @@ __global__ void __launch_bounds__(kAttnWarps * 32, SPLIT == 2 ? 3 : 0) attention
     if (tid < DH) {
         M = s_m[0];
 #pragma unroll
-        for (int w = 1; w < kAttnWarps; w++) M = fmaxf(M, s_m[w]);
+        for (int w = 1; w < NW; w++) M = fmaxf(M, s_m[w]);
 #pragma unroll
-        for (int w = 0; w < kAttnWarps; w++) {
+        for (int w = 0; w < NW; w++) {
             const float f = s_m[w] == -INFINITY ? 0.0f : expf(s_m[w] - M);
             L += f * s_l[w];
             o += f * s_acc[w][tid];
@@ -629,7 +629,13 @@ bool launch_attention(const AttnArgs & a, cudaStream_t stream) {
         at[1].val.clusterDim.x = 1; at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = std::max(S, 1);
         cfg.attrs = at; cfg.numAttrs = S >= 1 ? 2 : 1;
         const bool occ3 = getenv("MGB_ATTN_OCC3") != nullptr;
+        const bool nw4 = getenv("MGB_ATTN_NW8") == nullptr && a.H * a.tok.M >= 512;      // (1040 -> 1012 us per step at 64 utterances)
         if (S >= 1 && occ3) MGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, attention_kernel<__nv_bfloat16, 64, 2>, p));
+        else if (S == 1 && nw4) {
+            // short KV, many (head, utterance) items: 4-warp CTAs -- 768 items fit the resident slots in about one wave instead of 2.6
+            cfg.blockDim = dim3(4 * 32);
+            MGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, attention_kernel<__nv_bfloat16, 64, 1, 4>, p));
+        }
         else if (S >= 1) MGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, attention_kernel<__nv_bfloat16, 64, 1>, p));
         else MGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, attention_kernel<__nv_bfloat16, 64>, p));
         MGB_LAUNCH_CHECK();
