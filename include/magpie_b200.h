@@ -179,6 +179,20 @@ MGB_API int64_t mgb_session_last_loop_launches(const mgb_session * s);
  * megakernel took around every grid barrier of the last step (16 per layer + 2) */
 MGB_API int mgb_session_debug_stamps(mgb_session * s, uint64_t * out, int n);
 
+/* ---- batched streaming synthesis --------------------------------------------------------------------
+ * magpie_synthesize_sentence_streaming (magpie.cpp:4502-4829; chunk decode 4483-4500) for all B utterances of a prefilled
+ * session at once (BASELINE configs[4]: long-form streaming): the device loop runs frames_per_chunk frames (reference default 4),
+ * the chunks of all utterances are decoded by the codec in ONE batched launch sequence and every utterance's new samples are
+ * handed to the callback (utterance, pcm, n_samples, frames so far, is_last, user); a non-zero return stops the call.
+ * codec_context_frames = 0 decodes every chunk with zero causal history, as the reference does (audible seam per chunk);
+ * N > 0 decodes each chunk together with the utterance's previous N frames and emits only the new samples (overlap-save;
+ * N >= 25 covers the codec's 24.8-frame receptive field, so the stream equals a whole-utterance decode).  As in the reference's
+ * streaming path the EOS frame's codes are decoded too (magpie.cpp:4733-4742).  n_frames_out [B] optional. */
+typedef int (*mgb_stream_callback)(int utterance, const float * pcm, int n_samples, int frames_done, int is_last, void * user);
+MGB_API int mgb_stream_generate(mgb_session * s, mgb_codec * codec, int max_steps, float temperature, int top_k, uint64_t seed,
+                                int ignore_eos, int frames_per_chunk, int codec_context_frames, mgb_stream_callback cb, void * user,
+                                int32_t * n_frames_out);
+
 /* ---- in-process multi-GPU pool ---------------------------------------------------------------------
  * The reference is single-device (src/magpie.cpp:14-67 picks ONE backend; magpie_synthesize_codes_graph_reuse,
  * magpie.cpp:4063-4432, synthesises one utterance).  Independent utterances shard with no collective: a pool

@@ -28,6 +28,9 @@ class HParams(C.Structure):
     _fields_ = [(k, C.c_int32) for k in HP_FIELDS] + [("eps", C.c_float)]
 
 
+STREAM_CB = C.CFUNCTYPE(C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int, C.c_void_p)
+
+
 class CodecHParams(C.Structure):
     _fields_ = [(k, C.c_int32) for k in ("sample_rate", "num_codebooks", "codebook_size", "hop_length", "latent_dim")]
 
@@ -38,7 +41,7 @@ SYMBOLS = [
     "mgb_model_load", "mgb_model_free", "mgb_model_get_hparams", "mgb_model_set_max_dec_steps",
     "mgb_model_set_gelu_f16", "mgb_model_precision", "mgb_model_device", "mgb_model_step_weight_bytes",
     "mgb_model_meta_str", "mgb_model_meta_u32",
-    "mgb_session_new", "mgb_session_new_paged", "mgb_session_kv_pages", "mgb_generate_queue", "mgb_session_free", "mgb_session_batch", "mgb_session_max_seq", "mgb_session_positions",
+    "mgb_session_new", "mgb_session_new_paged", "mgb_session_kv_pages", "mgb_generate_queue", "mgb_stream_generate", "mgb_session_free", "mgb_session_batch", "mgb_session_max_seq", "mgb_session_positions",
     "mgb_encode_text", "mgb_prefill", "mgb_decoder_step", "mgb_final_proj", "mgb_lt_sample",
     "mgb_generate", "mgb_teacher_forced", "mgb_session_last_loop_ms", "mgb_session_last_loop_launches",
     "mgb_session_debug_stamps",
@@ -94,6 +97,7 @@ def lib():
     L.mgb_session_new_paged.restype = vp
     L.mgb_session_new_paged.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int]
     L.mgb_session_kv_pages.argtypes = [vp, vp, vp]
+    L.mgb_stream_generate.argtypes = [vp, vp, C.c_int, C.c_float, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int, STREAM_CB, vp, vp]
     L.mgb_generate_queue.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp, vp, C.c_int, C.c_float, C.c_int, C.c_uint64, vp, vp, vp]
     L.mgb_session_batch.argtypes = [vp]
     L.mgb_session_max_seq.argtypes = [vp]
@@ -327,6 +331,23 @@ class Session:
         _chk(lib().mgb_generate_queue(self._h, n, _p(tok), _p(nt), mt, _p(spk), _p(lim), int(T), float(temperature), int(top_k),
                                       C.c_uint64(seed), _p(codes), _p(nf), C.byref(steps)), "mgb_generate_queue")
         return [codes[i, :nf[i]].copy() for i in range(n)], int(steps.value)
+
+    def stream_generate(self, codec: "Codec", on_audio, max_steps=0, temperature=0.0, top_k=80, seed=0, ignore_eos=False,
+                        frames_per_chunk=4, codec_context_frames=0):
+        """Batched streaming synthesis: on_audio(utterance, pcm ndarray, frames_done, is_last) per utterance and chunk
+        (return True to stop).  Returns frames per utterance."""
+        def tramp(u, ptr, n, fd, last, _user):
+            try:
+                return 1 if on_audio(int(u), np.ctypeslib.as_array(ptr, shape=(n,)).copy(), int(fd), bool(last)) else 0
+            except Exception:      # noqa: BLE001 -- an exception must not unwind through the C frames
+                import traceback
+                traceback.print_exc()
+                return 1
+        cbf = STREAM_CB(tramp)
+        nf = np.zeros(self.B, np.int32)
+        _chk(lib().mgb_stream_generate(self._h, codec._h, int(max_steps), float(temperature), int(top_k), C.c_uint64(seed), int(ignore_eos),
+                                       int(frames_per_chunk), int(codec_context_frames), cbf, None, _p(nf)), "mgb_stream_generate")
+        return nf
 
     def teacher_forced(self, codes_in, want_hidden=True, want_logits=True, want_greedy=True):
         hp = self.model.hp

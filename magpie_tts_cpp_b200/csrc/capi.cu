@@ -777,6 +777,7 @@ struct LoopCfg {
     float temperature = 0.0f; int top_k = 80; uint64_t seed = 0;
     bool teacher = false, want_logits = false, want_hidden = false, ignore_eos = false;
     bool have_uniforms = false;
+    int n = -1, step0 = 0;     // persistent batch-1 kernel only: run n steps (default T) starting at step / output row step0 (streaming chunks)
 };
 
 // One loop iteration = decoder step on d_codes -> LT (+sampling) -> advance; all per-step indexing is
@@ -815,7 +816,7 @@ static int run_loop_persistent(Session & s, const LoopCfg & c, int * steps_run) 
     p.V = hp.vocab_per_cb;
     p.lt_in_w = m.lt_in_w.w; p.lt_in_b = m.lt_in_b; p.lt_pos = m.lt_pos; p.lt_norm_self = m.lt_norm_self; p.lt_norm_ff = m.lt_norm_ff;
     p.lt_qkvo = m.lt_qkvo; p.lt_qkv_tab = m.lt_qkv_tab; p.lt_ff1 = m.lt_ff1.w; p.lt_ff2 = m.lt_ff2.w;
-    p.n_steps = c.T; p.pos0 = s.pos; p.step0 = 0; p.row0 = 0; p.min_frames = c.teacher ? 0 : 4;       // magpie.cpp:4267, 4325
+    p.n_steps = c.n >= 0 ? c.n : c.T; p.pos0 = s.pos; p.step0 = c.step0; p.row0 = c.step0; p.min_frames = c.teacher ? 0 : 4;       // magpie.cpp:4267, 4325
     p.teacher = c.teacher ? 1 : 0; p.ignore_eos = c.ignore_eos ? 1 : 0;
     p.temperature = c.temperature; p.top_k = c.top_k; p.seed = c.seed;
     p.uniforms = c.have_uniforms ? s.l_uniforms : nullptr;
@@ -1172,6 +1173,142 @@ int mgb_generate_queue(mgb_session * ss, int n_utt, const int32_t * tokens, cons
     return MGB_OK;
 }
 
+static int codec_upload(Codec & c, const int32_t * codes, int B, int T) {
+    const size_t n = (size_t)B * 8 * T;
+    if (!grow((void **)&c.d_codes, &c.codes_cap, n * 4)) return MGB_ECUDA;
+    if (cudaMemcpyAsync(c.d_codes, codes, n * 4, cudaMemcpyHostToDevice, (cudaStream_t)c.stream) != cudaSuccess) { set_error("codec: H2D failed"); return MGB_ECUDA; }
+    return MGB_OK;
+}
+
+// ---- batched streaming synthesis ----------------------------------------------------------------------------------
+// magpie_synthesize_sentence_streaming (magpie.cpp:4502-4829) for all B utterances of a session at once: the device loop runs
+// `frames_per_chunk` frames, the new codes of every utterance come back in one copy, the codec decodes all utterances' chunks in
+// ONE batched launch sequence and each utterance's new samples are handed to the callback.  The reference decodes every chunk
+// with zero causal history (magpie.cpp:4483-4500: audible seams); codec_context_frames = N decodes each chunk together with the
+// utterance's previous N frames and emits only the new samples (N >= 25 covers the codec's 24.8-frame receptive field).  As in
+// the reference's streaming path the EOS frame's codes ARE decoded (magpie.cpp:4733-4742).
+int mgb_stream_generate(mgb_session * ss, mgb_codec * cc, int max_steps, float temperature, int top_k, uint64_t seed, int ignore_eos,
+                        int frames_per_chunk, int codec_context_frames, mgb_stream_callback cb, void * user, int32_t * n_frames_out) {
+    Session * s = reinterpret_cast<Session *>(ss);
+    Codec * c = reinterpret_cast<Codec *>(cc);
+    if (!check_ready(s, true)) return MGB_EINVAL;
+    if (!c || !cb) { set_error("mgb_stream_generate: null codec / callback"); return MGB_EINVAL; }
+    if (c->device != s->m->device) { set_error("mgb_stream_generate: model and codec live on different devices"); return MGB_EINVAL; }
+    const mgb_hparams & hp = s->m->hp;
+    if (max_steps <= 0) max_steps = hp.max_dec_steps;
+    if (temperature >= 0.01f && top_k < 1) { set_error("mgb_stream_generate: top_k must be >= 1 when sampling"); return MGB_EINVAL; }
+    const int B = s->B, chunk = frames_per_chunk > 0 ? frames_per_chunk : 4, ctx = std::max(0, codec_context_frames), hop = c->hp.hop_length;
+    if (s->pos + max_steps > s->max_seq) { set_error("mgb_stream_generate: KV cache too small for the requested steps"); return MGB_ERANGE; }
+    LoopCfg lc;
+    lc.T = max_steps; lc.temperature = temperature; lc.top_k = top_k; lc.seed = seed; lc.ignore_eos = ignore_eos != 0;
+    if (!prepare_loop_buffers(*s, lc)) return MGB_ECUDA;
+    cudaStream_t st = s->stream, cst = (cudaStream_t)c->stream;
+    std::vector<int32_t> bos((size_t)B * 8, hp.audio_bos_id), neg(B, -1);
+    if (cudaMemcpyAsync(s->d_codes, bos.data(), bos.size() * 4, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+        cudaMemsetAsync(s->d_step, 0, 4, st) != cudaSuccess ||
+        cudaMemcpyAsync(s->d_done, neg.data(), B * 4, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess) { set_error("mgb_stream_generate: init failed"); return MGB_ECUDA; }
+    const bool persistent = s->loop_grid > 0 && s->loop_tables;
+    if (persistent || s->mega_grid > 0) {
+        if (!ensure_pages_all(*s, std::min(s->pos + max_steps + 1, s->max_seq)) || !pages_contiguous(*s, s->pos + max_steps)) {
+            set_error("mgb_stream_generate: the batch-1 kernel needs contiguous cache pages"); return MGB_ERANGE;
+        }
+    }
+    cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
+    auto cleanup = [&]() { if (exec) cudaGraphExecDestroy(exec); if (graph) cudaGraphDestroy(graph); };
+    if (!persistent) {
+        s->attn_split = attention_plan_kv_split(hp.dec_sa_heads * B, s->pos + max_steps);
+        if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { set_error("graph capture begin failed"); return MGB_ECUDA; }
+        const bool okq = enqueue_iteration(*s, lc);
+        const cudaError_t e = cudaStreamEndCapture(st, &graph);
+        if (!okq || e != cudaSuccess || !graph) { cleanup(); if (okq) set_error("graph capture failed"); return MGB_ECUDA; }
+        if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) { cleanup(); set_error("graph instantiate failed"); return MGB_ECUDA; }
+    }
+    std::vector<std::vector<int32_t>> hist(B);          // per utterance: the last <= ctx frames already emitted, frame-major
+    std::vector<int> frames(B, 0), finished(B, 0);
+    std::vector<int32_t> h_codes((size_t)B * chunk * 8), h_done(B, -1), cbm;
+    std::vector<float> pcm;
+    int t = 0, rc = MGB_OK, n_done = 0;
+    float loop_ms = 0.0f;
+    while (t < max_steps && n_done < B && rc == MGB_OK) {
+        const int n = std::min(chunk, max_steps - t);
+        int ran = n;
+        if (persistent) {
+            lc.n = n; lc.step0 = t;
+            rc = run_loop_persistent(*s, lc, &ran);
+            loop_ms += s->last_ms;
+            if (rc != MGB_OK) break;
+            if (cudaMemcpyAsync(h_done.data(), s->d_done, 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) { set_error("D2H failed"); rc = MGB_ECUDA; break; }
+        } else {
+            if (!ensure_pages_all(*s, std::min(s->pos + n + 1, s->max_seq))) { rc = MGB_ERANGE; break; }
+            cudaEventRecord(s->ev0, st);
+            for (int i = 0; i < n && rc == MGB_OK; i++) if (cudaGraphLaunch(exec, st) != cudaSuccess) { set_error("graph launch failed"); rc = MGB_ECUDA; }
+            cudaEventRecord(s->ev1, st);
+            if (rc != MGB_OK) break;
+            if (cudaMemcpyAsync(h_done.data(), s->d_done, B * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) { set_error("D2H failed"); rc = MGB_ECUDA; break; }
+        }
+        // the chunk's sampled codes of every utterance: rows [b][t .. t + n) of the loop buffer
+        if (cudaMemcpy2DAsync(h_codes.data(), (size_t)chunk * 32, s->l_sampled + (size_t)t * 8, (size_t)max_steps * 32, (size_t)n * 32, B,
+                              cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) {
+            set_error(std::string("mgb_stream_generate: ") + cudaGetErrorString(cudaGetLastError())); rc = MGB_ECUDA; break;
+        }
+        if (!persistent) { float ms = 0.0f; cudaEventElapsedTime(&ms, s->ev0, s->ev1); loop_ms += ms; s->pos += n; }
+        if (persistent && h_done[0] >= 0) h_done[0] += t;              // the kernel reports the EOS step relative to its launch
+        // new frames per utterance (EOS frame included, then the utterance is finished); group equal (history, new) lengths into
+        // one batched codec call -- in lock step that is every active utterance
+        std::vector<int> nnew(B, 0);
+        for (int b = 0; b < B; b++) {
+            if (finished[b]) continue;
+            const bool eos = !ignore_eos && h_done[b] >= 0 && h_done[b] < t + ran;
+            nnew[b] = eos ? h_done[b] - t + 1 : ran;
+            if (eos || t + ran >= max_steps) finished[b] = 1;
+        }
+        std::vector<char> handled(B, 0);
+        for (int b0 = 0; b0 < B && rc == MGB_OK; b0++) {
+            if (handled[b0] || nnew[b0] <= 0) { handled[b0] = 1; continue; }
+            const int nh = (int)hist[b0].size() / 8, nn = nnew[b0], T = nh + nn;
+            std::vector<int> grp;
+            for (int b = b0; b < B; b++) if (!handled[b] && nnew[b] == nn && (int)hist[b].size() / 8 == nh) { grp.push_back(b); handled[b] = 1; }
+            const int G = (int)grp.size();
+            cbm.assign((size_t)G * 8 * T, 0);
+            for (int g = 0; g < G; g++) {
+                const int b = grp[g];
+                for (int f = 0; f < T; f++) {
+                    const int32_t * src = f < nh ? &hist[b][(size_t)f * 8] : &h_codes[((size_t)b * chunk + (f - nh)) * 8];
+                    for (int q = 0; q < 8; q++) cbm[((size_t)g * 8 + q) * T + f] = src[q];
+                }
+            }
+            if (codec_upload(*c, cbm.data(), G, T) != MGB_OK) { rc = MGB_ECUDA; break; }
+            const size_t ns = (size_t)G * T * hop;
+            if (!grow((void **)&c->d_pcm, &c->pcm_cap, ns * 4)) { rc = MGB_ECUDA; break; }
+            if (!codec_decode_device(*c, c->d_codes, G, T, c->d_pcm, cst)) { rc = MGB_ECUDA; break; }
+            pcm.resize((size_t)G * nn * hop);
+            // only the new samples of every utterance come back (the context part was emitted with earlier chunks)
+            if (cudaMemcpy2DAsync(pcm.data(), (size_t)nn * hop * 4, c->d_pcm + (size_t)nh * hop, (size_t)T * hop * 4, (size_t)nn * hop * 4, G,
+                                  cudaMemcpyDeviceToHost, cst) != cudaSuccess || cudaStreamSynchronize(cst) != cudaSuccess) {
+                set_error(std::string("mgb_stream_generate (codec): ") + cudaGetErrorString(cudaGetLastError())); rc = MGB_ECUDA; break;
+            }
+            for (int g = 0; g < G && rc == MGB_OK; g++) {
+                const int b = grp[g];
+                frames[b] += nn;
+                if (ctx > 0) {
+                    hist[b].insert(hist[b].end(), &h_codes[(size_t)b * chunk * 8], &h_codes[((size_t)b * chunk + nn) * 8]);
+                    if ((int)hist[b].size() > ctx * 8) hist[b].erase(hist[b].begin(), hist[b].end() - (size_t)ctx * 8);
+                }
+                if (cb(b, pcm.data() + (size_t)g * nn * hop, nn * hop, frames[b], finished[b], user) != 0) { set_error("mgb_stream_generate: stopped by the callback"); rc = MGB_EINVAL; }
+            }
+        }
+        n_done = 0;
+        for (int b = 0; b < B; b++) n_done += finished[b];
+        t += ran;
+        if (ran < n) break;                                            // (persistent kernel: stopped at EOS)
+    }
+    cleanup();
+    s->last_ms = loop_ms;
+    if (n_frames_out) for (int b = 0; b < B; b++) n_frames_out[b] = frames[b];
+    return rc;
+}
+
 // ---- codec ------------------------------------------------------------------------------------------
 mgb_codec * mgb_codec_load(const char * path, int device) {
     if (!path) { set_error("null path"); return nullptr; }
@@ -1186,13 +1323,6 @@ int mgb_codec_get_hparams(const mgb_codec * c, mgb_codec_hparams * out) {
 }
 float mgb_codec_last_ms(const mgb_codec * c) { return c ? reinterpret_cast<const Codec *>(c)->last_ms : 0.0f; }
 int64_t mgb_codec_last_launches(const mgb_codec * c) { return c ? reinterpret_cast<const Codec *>(c)->last_launches : 0; }
-
-static int codec_upload(Codec & c, const int32_t * codes, int B, int T) {
-    const size_t n = (size_t)B * 8 * T;
-    if (!grow((void **)&c.d_codes, &c.codes_cap, n * 4)) return MGB_ECUDA;
-    if (cudaMemcpyAsync(c.d_codes, codes, n * 4, cudaMemcpyHostToDevice, (cudaStream_t)c.stream) != cudaSuccess) { set_error("codec: H2D failed"); return MGB_ECUDA; }
-    return MGB_OK;
-}
 
 int mgb_codec_decode(mgb_codec * cc, const int32_t * codes, int batch, int n_frames, float * pcm_out) {
     Codec * c = reinterpret_cast<Codec *>(cc);

@@ -206,14 +206,6 @@ std::vector<int32_t> synthesize(magpie_context * ctx, const int32_t * tokens, in
     return out;
 }
 
-std::vector<float> decode_chunk(magpie_codec * codec, const std::vector<int32_t> & frame_major, int n_frames) {
-    if (n_frames <= 0 || frame_major.size() < (size_t)n_frames * 8) return {};
-    std::vector<int32_t> cbm((size_t)n_frames * 8);
-    for (int t = 0; t < n_frames; t++)
-        for (int cb = 0; cb < 8; cb++) cbm[(size_t)cb * n_frames + t] = frame_major[(size_t)t * 8 + cb];
-    return magpie_codec_decode(codec, cbm.data(), n_frames);
-}
-
 }  // namespace
 
 // ---- tokenizer --------------------------------------------------------------------------------------
@@ -368,61 +360,41 @@ std::vector<std::string> magpie_split_sentences(const char * text) {
     return out;
 }
 
+namespace {
+struct stream_bridge { const magpie_stream_params * params; int total = 0; bool stopped = false; };
+// C-ABI chunk callback -> the reference's on_audio / on_progress callbacks (magpie.h:604-617)
+int stream_chunk(int /*utterance*/, const float * pcm, int n_samples, int frames_done, int /*is_last*/, void * user) {
+    stream_bridge * br = static_cast<stream_bridge *>(user);
+    br->total += n_samples;
+    if (br->params->on_audio && !br->params->on_audio(pcm, n_samples, br->params->user_data)) br->stopped = true;
+    if (br->params->on_progress) br->params->on_progress(frames_done - 1, 0, 1, br->params->user_data);
+    return br->stopped ? 1 : 0;
+}
+}  // namespace
+
+// magpie.cpp:4502-4829.  The whole loop stays on the device: the batch-1 persistent kernel runs frames_per_chunk frames per
+// launch, the codec decodes each chunk (mgb_stream_generate); nothing is synchronised per frame.
 int magpie_synthesize_sentence_streaming(magpie_context * ctx, magpie_codec * codec, const int32_t * tokens, int n_tokens,
                                          const magpie_stream_params & params) {
-    if (!ctx || !codec || !tokens || n_tokens <= 0) return -1;
+    if (!ctx || !codec || !codec->impl || !tokens || n_tokens <= 0) return -1;
     const magpie_hparams & hp = ctx->model.hparams;
     ctx->temperature = params.temperature; ctx->top_k = params.top_k; ctx->speaker_id = params.speaker_id;
     mgb_session * s = start_utterance(ctx, tokens, n_tokens, hp.max_dec_steps, false);
     if (!s) return -1;
     magpie_model_impl * im = ctx->model.impl;
-    const int per_chunk = params.frames_per_chunk > 0 ? params.frames_per_chunk : 4;
-    std::vector<int32_t> bos(8, hp.audio_bos_id), pending, history;      // history: last codec_context_frames frames already emitted
-    const int n_ctx = std::max(0, params.codec_context_frames);
-    const int hop = codec->hparams.hop_length;
-    // decode `pending` (np frames); with a context, together with the previous frames, keeping only the new samples
-    auto decode_pending = [&](int np) {
-        if (n_ctx == 0) return decode_chunk(codec, pending, np);                // reference behaviour: zero causal history
-        std::vector<int32_t> both(history);
-        both.insert(both.end(), pending.begin(), pending.begin() + (size_t)np * 8);
-        const int nh = (int)history.size() / 8;
-        std::vector<float> audio = decode_chunk(codec, both, nh + np);
-        if (audio.size() == (size_t)(nh + np) * hop) audio.erase(audio.begin(), audio.begin() + (size_t)nh * hop);
-        else audio.clear();
-        const size_t keep = std::min(both.size(), (size_t)n_ctx * 8);
-        history.assign(both.end() - keep, both.end());
-        return audio;
-    };
-    int total = 0, frames = 0;
-    bool ok = mgb_decoder_step(s, bos.data(), nullptr) == MGB_OK;
-    for (int step = 0; ok && step < hp.max_dec_steps; step++) {
-        int32_t smp[8], am[8];
-        const uint8_t fe = step < 4 ? 1 : 0;                                   // min 4 frames before EOS (magpie.cpp:4714-4716)
-        int k = ctx->top_k;
-        if (ctx->temperature >= 0.01f && k < 1) k = 1;
-        if (mgb_lt_sample(s, nullptr, ctx->temperature, k, &fe, nullptr, nullptr, im->seed + (im->draws++), smp, am, nullptr) != MGB_OK) { ok = false; break; }
-        bool eos = magpie_is_eos(smp, 8, hp.audio_eos_id) || magpie_is_eos(am, 8, hp.audio_eos_id);
-        pending.insert(pending.end(), smp, smp + 8);      // the EOS frame IS streamed, as in the reference (magpie.cpp:4733-4742)
-        frames++;
-        const int np = (int)pending.size() / 8;
-        if (np >= per_chunk || eos) {
-            std::vector<float> audio = decode_pending(np);
-            if (!audio.empty() && params.on_audio && !params.on_audio(audio.data(), (int)audio.size(), params.user_data)) eos = true;
-            total += (int)audio.size();
-            pending.clear();
-            if (params.on_progress) params.on_progress(frames - 1, 0, 1, params.user_data);
-        }
-        if (eos || step + 1 >= hp.max_dec_steps) break;
-        if (mgb_decoder_step(s, nullptr, nullptr) != MGB_OK) { ok = false; break; }      // consumes the sampled codes left on the device
-    }
-    if (ok && !pending.empty()) {
-        std::vector<float> audio = decode_pending((int)pending.size() / 8);
-        if (!audio.empty() && params.on_audio) params.on_audio(audio.data(), (int)audio.size(), params.user_data);
-        total += (int)audio.size();
-    }
+    int k = ctx->top_k;
+    if (ctx->temperature >= 0.01f && k < 1) k = 1;
+    stream_bridge br;
+    br.params = &params;
+    int32_t n_frames = 0;
+    const int rc = mgb_stream_generate(s, codec->impl->codec, hp.max_dec_steps, ctx->temperature, k, im->seed + (im->draws++), 0,
+                                       params.frames_per_chunk > 0 ? params.frames_per_chunk : 4, std::max(0, params.codec_context_frames),
+                                       stream_chunk, &br, &n_frames);
+    const bool ok = rc == MGB_OK || br.stopped;          // a callback that asks to stop ends the sentence, it is not an error
     if (!ok) fprintf(stderr, "magpie: [streaming] %s\n", mgb_last_error());
     mgb_session_free(s);
-    return ok ? total : -1;
+    ctx->state.n_generated_frames = n_frames;
+    return ok ? br.total : -1;
 }
 
 int magpie_synthesize_streaming(magpie_context * ctx, magpie_codec * codec, const char * text, const magpie_stream_params & params) {
