@@ -452,7 +452,27 @@ def extra_measurements(binding, fixtures, m, args):
         out["decoder_q8_long_b32_frames_per_s"] = B * frames / (s.last_loop_ms * 1e-3)
         out["decoder_q8_long_sample"] = "config 5 per-GPU share: Q8_0 GGUF, 32 utterances x 2600 frames"
         out["decoder_q8_long_roofline"] = step_roofline(mq, B, mq.hp["context_frames"], frames, len(HELLO), s.last_loop_ms * 1e-3 / frames)
-        s.close(); mq.close()
+        s.close()
+        # the same share as STREAMING synthesis (callback every 4 frames, each chunk decoded by the codec with 25 frames of
+        # context = seamless audio), bounded to the first 400 of the 2600 frames
+        c5 = binding.Codec(fixtures.ensure_fixture("codec-f32"), 0)
+        sf, got = 400, [0]
+        s = mq.session(batch=B, max_text=32, max_seq=mq.hp["context_frames"] + sf + 16)
+
+        def on_audio(u, pcm, frames_done, is_last):
+            got[0] += len(pcm)
+            return False
+        for steps_ in (16, sf):
+            s.encode_text([HELLO] * B, want_output=False); s.prefill([b % 5 for b in range(B)])
+            got[0] = 0
+            t0 = time.perf_counter()
+            s.stream_generate(c5, on_audio, max_steps=steps_, frames_per_chunk=4, codec_context_frames=25, ignore_eos=True)
+            wall = time.perf_counter() - t0
+        out["stream_q8_b32_frames_per_s"] = B * sf / wall
+        out["stream_q8_b32_audio_s_per_s"] = got[0] / 22050.0 / wall
+        out["stream_q8_b32_sample"] = ("config 5 per-GPU share as streaming: 32 utterances in lock step, first 400 frames, chunks of 4 frames, every chunk "
+                                       "decoded with 25 context frames (29 frames per utterance and chunk through the codec) and copied to the host callback; wall clock")
+        s.close(); c5.close(); mq.close()
     except Exception as e:  # noqa: BLE001
         out["decoder_q8_long_error"] = str(e)
     try:

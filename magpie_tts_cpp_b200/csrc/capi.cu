@@ -1230,6 +1230,7 @@ int mgb_stream_generate(mgb_session * ss, mgb_codec * cc, int max_steps, float t
     std::vector<float> pcm;
     int t = 0, rc = MGB_OK, n_done = 0;
     float loop_ms = 0.0f;
+    bool prelaunched = false;
     while (t < max_steps && n_done < B && rc == MGB_OK) {
         const int n = std::min(chunk, max_steps - t);
         int ran = n;
@@ -1240,11 +1241,14 @@ int mgb_stream_generate(mgb_session * ss, mgb_codec * cc, int max_steps, float t
             if (rc != MGB_OK) break;
             if (cudaMemcpyAsync(h_done.data(), s->d_done, 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) { set_error("D2H failed"); rc = MGB_ECUDA; break; }
         } else {
-            if (!ensure_pages_all(*s, std::min(s->pos + n + 1, s->max_seq))) { rc = MGB_ERANGE; break; }
-            cudaEventRecord(s->ev0, st);
-            for (int i = 0; i < n && rc == MGB_OK; i++) if (cudaGraphLaunch(exec, st) != cudaSuccess) { set_error("graph launch failed"); rc = MGB_ECUDA; }
-            cudaEventRecord(s->ev1, st);
-            if (rc != MGB_OK) break;
+            if (!prelaunched) {
+                if (!ensure_pages_all(*s, std::min(s->pos + n + 1, s->max_seq))) { rc = MGB_ERANGE; break; }
+                cudaEventRecord(s->ev0, st);
+                for (int i = 0; i < n && rc == MGB_OK; i++) if (cudaGraphLaunch(exec, st) != cudaSuccess) { set_error("graph launch failed"); rc = MGB_ECUDA; }
+                cudaEventRecord(s->ev1, st);
+                if (rc != MGB_OK) break;
+            }
+            prelaunched = false;
             if (cudaMemcpyAsync(h_done.data(), s->d_done, B * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) { set_error("D2H failed"); rc = MGB_ECUDA; break; }
         }
         // the chunk's sampled codes of every utterance: rows [b][t .. t + n) of the loop buffer
@@ -1262,6 +1266,20 @@ int mgb_stream_generate(mgb_session * ss, mgb_codec * cc, int max_steps, float t
             const bool eos = !ignore_eos && h_done[b] >= 0 && h_done[b] < t + ran;
             nnew[b] = eos ? h_done[b] - t + 1 : ran;
             if (eos || t + ran >= max_steps) finished[b] = 1;
+        }
+        // the NEXT chunk's frames are generated (session stream) while this chunk is decoded by the codec (codec stream)
+        {
+            int nd = 0;
+            for (int b = 0; b < B; b++) nd += finished[b];
+            const int n2 = std::min(chunk, max_steps - (t + ran));
+            if (!persistent && nd < B && n2 > 0 && ran == n) {
+                if (!ensure_pages_all(*s, std::min(s->pos + n2 + 1, s->max_seq))) { rc = MGB_ERANGE; break; }
+                cudaEventRecord(s->ev0, st);
+                for (int i = 0; i < n2 && rc == MGB_OK; i++) if (cudaGraphLaunch(exec, st) != cudaSuccess) { set_error("graph launch failed"); rc = MGB_ECUDA; }
+                cudaEventRecord(s->ev1, st);
+                if (rc != MGB_OK) break;
+                prelaunched = true;
+            }
         }
         std::vector<char> handled(B, 0);
         for (int b0 = 0; b0 < B && rc == MGB_OK; b0++) {
@@ -1303,6 +1321,7 @@ int mgb_stream_generate(mgb_session * ss, mgb_codec * cc, int max_steps, float t
         t += ran;
         if (ran < n) break;                                            // (persistent kernel: stopped at EOS)
     }
+    if (prelaunched) cudaStreamSynchronize(st);        // (stopped by the callback with a chunk still in flight)
     cleanup();
     s->last_ms = loop_ms;
     if (n_frames_out) for (int b = 0; b < B; b++) n_frames_out[b] = frames[b];
