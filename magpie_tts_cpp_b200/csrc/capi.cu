@@ -397,7 +397,7 @@ mgb_session * mgb_session_new_paged(mgb_model * mm, int batch, int max_text, int
         for (int b = 0; b < batch; b++) if (!ensure_pages(*s, b, max_seq)) return nullptr;
     s->pt_dirty = true;
     if (!flush_page_table(*s) || cudaStreamSynchronize(s->stream) != cudaSuccess) { set_error("mgb_session_new: page table upload failed"); return nullptr; }
-    if (m->precision == MGB_PREC_BF16 && s->Mcap >= 16 && m->dec.size() && m->dec[0].qkv.tiles) {
+    if (m->precision == MGB_PREC_BF16 && s->Mcap >= 2 && m->dec.size() && m->dec[0].qkv.tiles) {
         const size_t tb = tc_scratch_bytes(s->Mcap, std::max(hp.d_ffn, hp.d_model));
         char * tp = nullptr;
         if (!s->alloc(tp, tb)) return nullptr;

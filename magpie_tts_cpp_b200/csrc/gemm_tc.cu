@@ -237,7 +237,10 @@ bool tc_pack_weights(const void * W, int N, int K, void * Wt, cudaStream_t strea
 size_t tc_scratch_bytes(int M, int K) { return 2 * (size_t)((M + 127) / 128) * 128 * K * sizeof(bf); }
 
 bool tc_linear_supported(const LinearArgs & a) {
-    return a.precision == MGB_PREC_BF16 && a.W.tiles != nullptr && (a.W.taps == 1 || a.tok_pos != nullptr) && a.M >= 16 && a.W.K % 64 == 0 &&
+    // fewer tokens: CUDA-core skinny GEMM (linear_kernel).  Measured per decoder step, CUDA-core vs tensor-core chain: 2 utterances
+    // 676 vs 704 us, 4: 834 vs 704, 8: 1467 vs 824, 12: 1341 vs 773 (round 1 switched at 16)
+    static const int min_m = getenv("MGB_TC_MIN_M") ? atoi(getenv("MGB_TC_MIN_M")) : 4;
+    return a.precision == MGB_PREC_BF16 && a.W.tiles != nullptr && (a.W.taps == 1 || a.tok_pos != nullptr) && a.M >= min_m && a.W.K % 64 == 0 &&
            a.tc_scratch != nullptr && tc_scratch_bytes(a.M, a.W.K * a.W.taps) <= a.tc_scratch_bytes && (a.ldx % 4) == 0;
 }
 

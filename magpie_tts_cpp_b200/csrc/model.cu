@@ -18,9 +18,16 @@ const std::string & get_error() { return g_error; }
 
 namespace {
 
+// f32 -> bf16 (round to nearest even) on the device: the host loop took 2.1 of the 2.8 s a bf16 load of the 858 MB f32 file needs
+__global__ void f32_to_bf16_kernel(const float * __restrict__ src, __nv_bfloat16 * __restrict__ dst, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = __float2bfloat16_rn(src[i]);
+}
+
 struct Uploader {
     std::vector<void *> & allocs;
     bool ok = true;
+    float * stage = nullptr; size_t stage_elems = 0;       // device staging buffer for the f32 image of a bf16 tensor
+    ~Uploader() { if (stage) cudaFree(stage); }
     void * raw(const void * host, size_t bytes) {
         void * d = nullptr;
         if (cudaMalloc(&d, bytes ? bytes : 16) != cudaSuccess) { ok = false; set_error("cudaMalloc failed"); return nullptr; }
@@ -34,9 +41,21 @@ struct Uploader {
     // weight matrix in the model dtype
     void * weights(const std::vector<float> & v, int precision) {
         if (precision == MGB_PREC_F32) return raw(v.data(), v.size() * 4);
-        std::vector<__nv_bfloat16> h(v.size());
-        for (size_t i = 0; i < v.size(); i++) h[i] = __float2bfloat16_rn(v[i]);
-        return raw(h.data(), h.size() * 2);
+        if (v.size() > stage_elems) {
+            if (stage) cudaFree(stage);
+            stage = nullptr; stage_elems = 0;
+            if (cudaMalloc((void **)&stage, v.size() * 4) != cudaSuccess) { ok = false; set_error("cudaMalloc failed (staging)"); return nullptr; }
+            stage_elems = v.size();
+        }
+        void * d = nullptr;
+        if (cudaMalloc(&d, v.size() ? v.size() * 2 : 16) != cudaSuccess) { ok = false; set_error("cudaMalloc failed"); return nullptr; }
+        allocs.push_back(d);
+        if (v.empty()) return d;
+        // (legacy default stream: the copy waits for the previous tensor's conversion kernel, the kernel for the copy)
+        if (cudaMemcpy(stage, v.data(), v.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) { ok = false; set_error("cudaMemcpy H2D failed"); return nullptr; }
+        f32_to_bf16_kernel<<<592, 256>>>(stage, (__nv_bfloat16 *)d, v.size());
+        if (cudaGetLastError() != cudaSuccess) { ok = false; set_error("bf16 conversion kernel failed"); return nullptr; }
+        return d;
     }
 };
 
