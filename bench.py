@@ -396,7 +396,7 @@ def run_inproc(args):
                    "launch": "ONE process: mgb_pool (C++), one model replica + one submission thread + one stream per GPU, "
                              "no torch.distributed, no NCCL; value = frames / max-over-devices loop time (CUDA events per device)"},
         "e2e": {"value": total / wall_t, "unit": UNIT, "h2d_bytes_per_step": int(codes.nbytes), "d2h_bytes_per_step": int(gr.nbytes),
-                "note": "wall clock around mgb_pool_teacher_forced: includes session creation, text encoder and the 110-frame prefill of every device"},
+                "note": "wall clock around mgb_pool_teacher_forced: includes the text encoder and the 110-frame prefill of every device (sessions are cached by the pool)"},
         "clocks": clk.summary(),
     }
     print(json.dumps(line), flush=True)

@@ -40,6 +40,12 @@ struct LtParams {
     const float * in_table[8];      // P_cb = E_cb . Win^T + b, [V][L] f32 (resident kernel: feedback is a row gather)
 };
 
+}  // namespace lt
+// lt_cluster.cu: utterances per 16-CTA cluster for a batch of B (0 = not supported) / launch
+int  lt_cluster_plan(const Model & m, int B);
+bool launch_lt_cluster(const Model & m, const lt::LtParams & p, int U, cudaStream_t stream);
+namespace lt {
+
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
                                               uint32_t (&out)[4]) {
 #pragma unroll

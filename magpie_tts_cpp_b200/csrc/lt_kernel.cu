@@ -282,6 +282,8 @@ bool launch_local_transformer(const Model & m, const LtArgs & a, cudaStream_t st
     for (int cb = 0; cb < 8; cb++) p.in_table[cb] = m.lt_in_table[cb];
     // MGB_LT_STREAM keeps the independent (GEMV) formulation alive for the parity tests; f32 models always use it
     p.stream_feedback = (getenv("MGB_LT_STREAM") != nullptr || m.precision == MGB_PREC_F32) ? 1 : 0;
+    // 4..64 utterances, bf16: one 16-CTA cluster per group of <= 8 utterances, weights resident in the cluster (lt_cluster.cu)
+    if (const int U = lt_cluster_plan(m, a.B)) return launch_lt_cluster(m, p, U, stream);
     // many utterances, bf16: weight-stationary persistent kernel over all utterances (lt_batch.cu)
     if (a.lt_scratch && lt_batch_supported(m, a.B) && getenv("MGB_LT_STREAM") == nullptr)
         return launch_lt_batch(m, p, a.lt_scratch, a.lt_scratch_bytes, stream);

@@ -22,7 +22,14 @@ struct mgb_pool {
     std::vector<mgb_model *> models;
     std::vector<int> devices;
     std::vector<float> last_ms;
-    ~mgb_pool() { for (mgb_model * m : models) if (m) mgb_model_free(m); }
+    // one cached session per device, reused while the share's shape (utterances, text capacity, cache length) stays the same:
+    // creating a session allocates the K/V pool and the loop buffers (tens of ms), which a serving loop must not pay per call
+    struct Cached { mgb_session * s = nullptr; int nb = 0, max_text = 0, max_seq = 0; };
+    std::vector<Cached> sessions;
+    ~mgb_pool() {
+        for (Cached & c : sessions) if (c.s) mgb_session_free(c.s);
+        for (mgb_model * m : models) if (m) mgb_model_free(m);
+    }
 };
 
 namespace {
@@ -50,7 +57,14 @@ std::string run_share(mgb_pool * p, int di, const Job & j, float * ms_out) {
     mgb_model_get_hparams(p->models[di], &hp);
     int local_text = 1;
     for (int i : idx) local_text = std::max(local_text, j.n_tokens[i]);
-    mgb_session * s = mgb_session_new(p->models[di], nb, local_text, hp.context_frames + j.T + 16);
+    mgb_pool::Cached & cs = p->sessions[di];
+    const int max_seq = hp.context_frames + j.T + 16;
+    if (!cs.s || cs.nb != nb || cs.max_text != local_text || cs.max_seq != max_seq) {
+        if (cs.s) mgb_session_free(cs.s);
+        cs.s = mgb_session_new(p->models[di], nb, local_text, max_seq);
+        cs.nb = nb; cs.max_text = local_text; cs.max_seq = max_seq;
+    }
+    mgb_session * s = cs.s;
     if (!s) return mgb_last_error();
     std::string err;
     std::vector<int32_t> tok((size_t)nb * local_text, 0), nt(nb), spk(nb);
@@ -76,7 +90,7 @@ std::string run_share(mgb_pool * p, int di, const Job & j, float * ms_out) {
         }
         *ms_out = mgb_session_last_loop_ms(s);
     }
-    mgb_session_free(s);
+    if (!err.empty()) { mgb_session_free(s); cs.s = nullptr; }      // do not reuse a session that failed
     return err;
 }
 
@@ -120,6 +134,7 @@ mgb_pool * mgb_pool_new(const char * gguf_path, const int * devices, int n_devic
         mgb_pool * p = new mgb_pool();
         p->devices = devs;
         p->models.assign(devs.size(), nullptr);
+        p->sessions.assign(devs.size(), mgb_pool::Cached());
         // replicas are loaded concurrently (each load parses the file and uploads ~0.2-0.9 GB to its own device)
         std::vector<std::string> errs(devs.size());
         std::vector<std::thread> th;

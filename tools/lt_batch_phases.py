@@ -1,10 +1,10 @@
 import os, sys
 import numpy as np
 sys.path.insert(0, '/root/repo')
-os.environ["MGB_LT_DBG"]="1"
+os.environ.setdefault("MGB_LT_DBG", "1")
 from magpie_tts_cpp_b200 import binding, fixtures
 m = binding.Model(fixtures.ensure_fixture("model-f32"), 0, binding.PREC_BF16)
-B=64
+B=int(os.environ.get("B64_B", "64"))
 s = m.session(batch=B, max_text=32)
 hid = np.random.default_rng(0).standard_normal((B,768)).astype(np.float32)
 for i in range(3): s.lt_sample(hid, temperature=0.0, want_logits=False)
