@@ -6,18 +6,24 @@
 // GRID barriers; every phase there re-stages the activations of all utterances into every CTA (64 x 256 floats = 65 KB through L2 per
 // CTA and pass): 4.4-9.8 us of work + 1.5 us of barrier per phase, 304 us per step at 64 utterances (profiles/r1_lt_batch_phase_timeline.txt).
 // Here a cluster owns its utterances end to end:
-//   * every CTA keeps its slices of the FFN matrices and of the current codebook's output projection in shared memory (bf16, 128 KB,
-//     one bulk copy per slice; rows are read with a per-row rotation of the 16-byte chunk order instead of padding);
+//   * every CTA keeps its slices of the FFN matrices and of the current codebook's output projection in shared memory as tcgen05
+//     operand images (bf16 SWIZZLE_128B K-major tiles, the 128-row images model.cu packs for gemm_tc.cu: 128 KB, bulk copies);
+//   * the three matrix products of a codebook run on the tensor cores: weights = MMA "A" (M = 64 / 128 rows), the cluster's utterances
+//     = MMA "B" (N = 16 columns, bf16 hi + lo halves of the f32 activations, two MMAs per k slice), accumulators in TMEM (64 columns);
+//     one elected thread issues 16-32 MMAs per product, all 16 warps read the accumulators back (tcgen05.ld) for the epilogues.  (The
+//     CUDA-core version of these products was issue-bound: 13.6 us per codebook for 650 k FMAs per CTA; profiles/r2_lt_cluster_phases.txt);
 //   * FF1 and FF2 are FUSED without an exchange: CTA r computes FFN-hidden rows [64 r, 64 r + 64) and multiplies them straight into
-//     the matching 64 COLUMNS of W2 (a per-rank column slice prepared at load, model.cu); the 16 partial sums per output are
-//     reduce-scattered through DSMEM (16-byte stores) and added in rank order (deterministic);
-//   * results go only where they are needed: activations to all 16 CTAs, logits / q / k / vo rows to the utterance's owner CTA;
+//     the matching 64 COLUMNS of W2 (= k tile r of the packed W2); the 16 partial sums per output are reduce-scattered through DSMEM
+//     and added in rank order (deterministic);
+//   * results go only where they are needed: activations (as operand images) to all 16 CTAs, logits / q / k / vo rows to the
+//     utterance's owner CTA;
 //   * the phase boundaries are cluster barriers (~0.6-2 us) instead of grid barriers.
 // A GPU schedules 7 or 8 such clusters side by side (one per GPC with >= 16 SMs), so 64 utterances are 8 x 8 or 7 x 10.
 //   per codebook:  FF1 (LN prologue, GELU) + FF2 partials | reduce + residual, gather | out-projection + bias | owner CTA: mask /
 //                  argmax / top-k sample, gather of the next position's [q | k | vo] row (model.cu table), its attention, x1 broadcast
 #include <cstdlib>
 
+#include "gemm_tc.cuh"
 #include "lt_common.cuh"
 
 namespace mgb {
@@ -35,14 +41,19 @@ constexpr int kXL = kL + 4;                              // padded activation ro
 constexpr int kDm = 768, kHS = kDm + 4;                  // decoder width this kernel is built for; padded hidden-state row stride
 constexpr int kScratch = 10 * kHS;                       // floats: hidden states of <= 10 utterances (prologue) / sampler scratch (owner phase)
 
-template <int U> struct alignas(128) ClSmem {
-    bf w_ff1[kF1Rows * kL];            // FF1 rows [64 r, 64 r + 64)
-    bf w_ff2[kL * kF1Rows];            // W2[:, 64 r .. 64 r + 64): [256 rows][64 columns]; in the prologue: the vo "lo" rows of position 0
-    bf w_out[kOutRows * kL];           // current codebook's output-projection rows; in the prologue: in-projection + [q | k | vo-hi] rows
-    float scratch[kScratch];           // prologue: decoder hidden states [U][772]; owner phase: the sampler's scratch
+constexpr int kBTile = 16 * 128;                         // one k tile of the utterance operand: 16 rows (utterances) x 64 k, bf16
+constexpr int kTmemCols = 128;                           // accumulators (hi | lo column halves): FF1 [0, 32), FF2 partials [32, 96), out-projection [96, 128)
+
+template <int U> struct alignas(1024) ClSmem {
+    // tcgen05 operand images (every one starts on a 1024-byte boundary)
+    bf w_ff1[kF1Rows * kL];            // FF1 rows [64 r, 64 r + 64): 4 k tiles of [64 rows x 128 B]
+    bf w_ff2[kL * kF1Rows];            // W2[:, 64 r .. 64 r + 64): 2 tiles of [128 rows x 128 B]; in the prologue: the vo "lo" rows of position 0 (row-major)
+    bf w_out[kOutRows * kL];           // current codebook's output-projection rows [128 r, 128 r + 128): 4 k tiles of [128 rows x 128 B];
+                                       // in the prologue: in-projection + [q | k | vo-hi] rows (row-major)
+    unsigned char b_act[kL / 64][2][kBTile];   // [k tile][hi | lo][16 utterances x 128 B] = 32-row operand images: LN(x1) for FF1, then the layer output for the out-projection
+    unsigned char b_ffh[2][kBTile];            // [hi | lo] this CTA's 64 GELU'd FFN-hidden values per utterance
+    float scratch[kScratch];           // prologue: decoder hidden states [U][772], then LN(seq) [U][260]; owner phase: the sampler's scratch
     float x1[U][kXL];                  // residual stream entering the FFN (replicated in every CTA)
-    float hn[U][kXL];                  // LayerNorm'd GEMV input; after the reduce: the layer output (replicated)
-    float ffh[U][kF1Rows + 4];         // this CTA's 64 FFN-hidden values per utterance (local)
     float recv[kCS][U][kF2Rows];       // FF2 partial sums of this CTA's 16 output rows from every rank
     // owner CTA of an utterance (rank u owns utterance u of the cluster)
     float logits[kV];
@@ -50,7 +61,8 @@ template <int U> struct alignas(128) ClSmem {
     float kc[8][kL], vc[8][kL];
     float red[32]; int redi[32];
     float scores[8];
-    uint64_t mbar[3];
+    uint64_t mbar[4];                  // 0: FFN images, 1: out-projection image, 2: prologue rows, 3: MMA completion
+    uint32_t tmem_slot;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void * p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -90,6 +102,25 @@ __device__ __forceinline__ void dsmem_st4_all(float * local, float4 v) {
 #pragma unroll
     for (int r = 0; r < kCS; r++) dsmem_st4(local, r, v);
 }
+
+__device__ __forceinline__ void dsmem_st2u(void * local, int rank, uint32_t a, uint32_t b) {
+    asm volatile("st.shared::cluster.v2.u32 [%0], {%1,%2};" ::"r"(dsmem_addr(local, rank)), "r"(a), "r"(b) : "memory");
+}
+// x = hi + lo (bf16 each, |x - hi - lo| <= 2^-17 |x|): the activation operand of the tensor-core products (gemm_tc.cuh)
+__device__ __forceinline__ void split_bf(float x, uint32_t & h, uint32_t & l) {
+    const bf hb = __float2bfloat16_rn(x);
+    h = __bfloat16_as_ushort(hb);
+    l = __bfloat16_as_ushort(__float2bfloat16_rn(x - __bfloat162float(hb)));
+}
+__device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void tc_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
+    uint32_t v;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
+    return __uint_as_float(v);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // lanes of a dot product for `items` (row, utterance) pairs on 512 threads: the largest power of two <= 512 / items, at most 32
 __host__ __device__ constexpr int ks_for(int items) {
@@ -162,6 +193,39 @@ template <int U> __device__ __forceinline__ void warp_ln_rows(const float (*x)[k
     __syncthreads();
 }
 
+// Same LayerNorm, written as the tensor-core "B" operand: row u of the [16 x K] K-major SWIZZLE_128B images (hi | lo halves).
+// Lane l owns the 16-byte chunk of elements 8 l .. 8 l + 7.  Ends with the generic -> async proxy fence + __syncthreads.
+template <int U> __device__ __forceinline__ void warp_ln_image(const float (*x)[kXL], const float * w, unsigned char (*img)[2][kBTile], float eps) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp < U) {
+        const float4 a = *reinterpret_cast<const float4 *>(&x[warp][8 * lane]), b = *reinterpret_cast<const float4 *>(&x[warp][8 * lane + 4]);
+        float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        float s = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 8; k++) s += v[k];
+        const float mean = warp_sum(s) / (float)kL;
+        float s2 = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 8; k++) { v[k] -= mean; s2 += v[k] * v[k]; }
+        const float scale = 1.0f / sqrtf(warp_sum(s2) / (float)kL + eps);
+        const float4 wa = *reinterpret_cast<const float4 *>(w + 8 * lane), wb = *reinterpret_cast<const float4 *>(w + 8 * lane + 4);
+        const float ww[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            uint32_t h0, l0, h1, l1;
+            split_bf((v[2 * k] * scale) * ww[2 * k], h0, l0);
+            split_bf((v[2 * k + 1] * scale) * ww[2 * k + 1], h1, l1);
+            h[k] = h0 | (h1 << 16); l[k] = l0 | (l1 << 16);
+        }
+        const int off = tc::swz_offset(warp, (lane & 7) * 8);
+        *reinterpret_cast<uint4 *>(&img[lane >> 3][0][off]) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4 *>(&img[lane >> 3][1][off]) = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+    tc_before_sync();
+    __syncthreads();
+}
+
 // the sampler of lt_common.cuh works on any object with these members; here they point into shared memory
 struct SampView {
     float * logits, * sel_v, * srt_v; uint16_t * sel_i, * srt_i; unsigned * hist; int * misc;
@@ -174,13 +238,14 @@ struct ClParams {
     LtParams p;
     const void * qkvo;               // [4L][L] bf16: [Wq; Wk; hi(Wo Wv); lo(Wo Wv)]
     const float * qkv_tab;           // [7][V][3L] f32: [q | k | vo] of position cb+1 per fed code of codebook cb
-    const void * ff2_sl;             // [16][L][F / 16] bf16: per-rank column slices of W2 (model.cu)
+    const void * ff1_t, * ff2_t;     // packed 128-row tile images of W1 [F][L] and W2 [L][F] (gemm_tc.cu pack_w_kernel)
+    const void * out_t[8];           // same for the 8 output projections [V -> 128-row tiles][L]
 };
 
 template <int U>
 __global__ void __launch_bounds__(kLtThreads, 1) lt_cluster_kernel(const ClParams cp) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    ClSmem<U> & S = *reinterpret_cast<ClSmem<U> *>(smem_raw);
+    extern __shared__ unsigned char smem_raw[];
+    ClSmem<U> & S = *reinterpret_cast<ClSmem<U> *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const LtParams & p = cp.p;
     unsigned rank_u;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank_u));
@@ -191,26 +256,43 @@ __global__ void __launch_bounds__(kLtThreads, 1) lt_cluster_kernel(const ClParam
     const float att_scale = 1.0f / sqrtf((float)L);
     const bool owner = rank < U && u0 + rank < B;            // this CTA samples / attends for utterance u0 + rank
     const int my_utt = u0 + rank;
+    if (warp == 0) {                                         // TMEM: 64 fp32 columns for the three accumulators
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_slot)), "n"(kTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
 
-    const int out_rpc = (V + kCS - 1) / kCS, out_r0 = rank * out_rpc, out_nr = max(0, min(out_rpc, V - out_r0));
+    // output-projection rows of this CTA: vocabulary ids [128 r, 128 r + 128) = row tile r of the packed matrix (zero rows beyond V)
+    const int out_r0 = rank * kOutRows;
+    const bool has_out = out_r0 < V;
     // prologue rows: in-projection rows [16 r, 16 r + 16) and the 48 logical [q | k | vo] outputs [48 r, 48 r + 48) of position 0
     const int in_r0 = rank * (kL / kCS), qkv_r0 = rank * 48;
     const int lo_first = max(qkv_r0, 2 * L), lo_n = max(0, qkv_r0 + 48 - lo_first);          // outputs that also need their "lo" row
     bf * w_in = S.w_out;                                     // [16][768]
     bf * w_qkv = S.w_out + (kL / kCS) * kDm;                 // [48][256]
-    bf * w_lo = S.w_ff2;                                     // [<= 48][256] (the W2 slice is loaded after the prologue)
+    bf * w_lo = S.w_ff2;                                     // [<= 48][256] (the W2 tiles are loaded after the prologue)
+    float (*hn)[kXL] = reinterpret_cast<float (*)[kXL]>(S.scratch);      // prologue only: LN(seq[0] + pos[0]) (after the hidden states are consumed)
     if (tid == 0) {
-        mbar_init(&S.mbar[0], 1); mbar_init(&S.mbar[1], 1); mbar_init(&S.mbar[2], 1);
+        mbar_init(&S.mbar[0], 1); mbar_init(&S.mbar[1], 1); mbar_init(&S.mbar[2], 1); mbar_init(&S.mbar[3], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    // operand rows of utterances >= U are never written again: zero them once (their accumulator columns are ignored)
+    for (int i = tid; i < (int)(sizeof(S.b_act) + sizeof(S.b_ffh)) / 16; i += kLtThreads) reinterpret_cast<uint4 *>(&S.b_act[0][0][0])[i] = make_uint4(0u, 0u, 0u, 0u);
+    tc_before_sync();
     __syncthreads();
+    tc_after_sync();
+    const uint32_t tmem = S.tmem_slot;
+    constexpr uint32_t kTile128 = tc::BM * 128;              // bytes of one packed [128 rows x 64 k] weight tile
     if (tid == 0) {
         mbar_expect_tx(&S.mbar[2], (uint32_t)((kL / kCS) * d + 48 * L + lo_n * L) * 2u);
         bulk_g2s(w_in, (const bf *)p.in_w + (size_t)in_r0 * d, (uint32_t)(kL / kCS) * d * 2u, &S.mbar[2]);
         bulk_g2s(w_qkv, (const bf *)cp.qkvo + (size_t)qkv_r0 * L, 48u * L * 2u, &S.mbar[2]);
         if (lo_n) bulk_g2s(w_lo, (const bf *)cp.qkvo + (size_t)(lo_first + L) * L, (uint32_t)lo_n * L * 2u, &S.mbar[2]);
         mbar_expect_tx(&S.mbar[0], (uint32_t)(kF1Rows * L + L * kF1Rows) * 2u);        // (the W2 half is issued after the prologue)
-        bulk_g2s(S.w_ff1, (const bf *)p.ff1_w + (size_t)rank * kF1Rows * L, (uint32_t)kF1Rows * L * 2u, &S.mbar[0]);
+        // W1 rows [64 r, 64 r + 64) of k tile kt: the upper or lower half of packed tile (r / 2, kt)
+        for (int kt = 0; kt < kL / 64; kt++)
+            bulk_g2s(reinterpret_cast<unsigned char *>(S.w_ff1) + kt * (kF1Rows * 128),
+                     reinterpret_cast<const unsigned char *>(cp.ff1_t) + ((size_t)(rank / 2) * (kL / 64) + kt) * kTile128 + (size_t)(rank % 2) * (kF1Rows * 128),
+                     (uint32_t)kF1Rows * 128u, &S.mbar[0]);
     }
     int n_stamp = 0;
     auto stamp = [&]() {
@@ -240,23 +322,25 @@ __global__ void __launch_bounds__(kLtThreads, 1) lt_cluster_kernel(const ClParam
     stamp(); cluster_sync_all(); stamp();
     // position 0: [q | k | vo] = [Wq; Wk; Wo Wv] . LN(seq + pos[0])  (magpie.cpp:1026-1030, 1501-1503) -> the utterance's owner CTA.
     // vo = hi + lo rows of the folded matrix (model.cu); logical output n < 3L: q (n < L), k (n < 2L), vo (else)
-    warp_ln_rows<U>(S.x1, p.pos, p.norm_self, S.hn, p.eps, L);
+    warp_ln_rows<U>(S.x1, p.pos, p.norm_self, hn, p.eps, L);
     // (48 consecutive logical outputs never straddle q / k / vo inside a group of 4: 48 r and the region bounds are multiples of 4)
-    tile_dots<48, U, kL, true>(w_qkv, 48, &S.hn[0][0], kXL, [&](int r0, int u, const float (&v)[4]) {
+    tile_dots<48, U, kL, true>(w_qkv, 48, &hn[0][0], kXL, [&](int r0, int u, const float (&v)[4]) {
         const int n = qkv_r0 + r0;
         float * dst = n < L ? &S.q[n] : (n < 2 * L ? &S.kc[0][n - L] : &S.vc[0][n - 2 * L]);
         dsmem_st4(dst, u, make_float4(v[0], v[1], v[2], v[3]));                  // owner of utterance u = CTA u
     });
     if (lo_n > 0)                                            // CTA-uniform
-        tile_dots<48, U, kL, true>(w_lo, lo_n, &S.hn[0][0], kXL, [&](int r0, int u, const float (&v)[4]) {
+        tile_dots<48, U, kL, true>(w_lo, lo_n, &hn[0][0], kXL, [&](int r0, int u, const float (&v)[4]) {
             if (r0 < lo_n) dsmem_st4(&S.vlo[lo_first - 2 * L + r0], u, make_float4(v[0], v[1], v[2], v[3]));
         });
     __syncthreads();
-    if (tid == 0) {                                          // the prologue rows are consumed: the W2 slice and codebook 0's output-projection slice may land
+    if (tid == 0) {                                          // the prologue rows are consumed: the W2 tiles and codebook 0's output-projection tiles may land
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        bulk_g2s(S.w_ff2, (const bf *)cp.ff2_sl + (size_t)rank * L * kF1Rows, (uint32_t)L * kF1Rows * 2u, &S.mbar[0]);
-        mbar_expect_tx(&S.mbar[1], (uint32_t)(out_nr * L) * 2u);
-        if (out_nr) bulk_g2s(S.w_out, (const bf *)p.out_w[0] + (size_t)out_r0 * L, (uint32_t)(out_nr * L) * 2u, &S.mbar[1]);
+        for (int t = 0; t < 2; t++)                          // W2 rows [128 t, 128 t + 128), columns [64 r, 64 r + 64) = packed tile (t, r)
+            bulk_g2s(reinterpret_cast<unsigned char *>(S.w_ff2) + t * kTile128,
+                     reinterpret_cast<const unsigned char *>(cp.ff2_t) + ((size_t)t * (kF / 64) + rank) * kTile128, kTile128, &S.mbar[0]);
+        mbar_expect_tx(&S.mbar[1], has_out ? 4u * kTile128 : 0u);
+        if (has_out) bulk_g2s(S.w_out, reinterpret_cast<const unsigned char *>(cp.out_t[0]) + (size_t)rank * 4 * kTile128, 4u * kTile128, &S.mbar[1]);
     }
     stamp(); cluster_sync_all(); stamp();
     // owner: attention over position 0 alone is the identity on vo_0: x1 = (seq + pos[0]) + vo_0; broadcast
@@ -271,6 +355,9 @@ __global__ void __launch_bounds__(kLtThreads, 1) lt_cluster_kernel(const ClParam
     mbar_wait(&S.mbar[0], 0);
 
     bool hit_eos = false;
+    uint32_t mma_par = 0;                                    // phase parity of the MMA-completion barrier
+    const int wq = warp & 3, wg = warp >> 2;                 // epilogues: TMEM lane quarter of this warp; utterances wg, wg + 4, wg + 8
+    static_assert(U <= 12, "epilogue utterance mapping");
     const int my_step = owner ? step_of(my_utt) : 0;
     const size_t my_row = loop ? (size_t)my_utt * p.T_total + my_step : (size_t)my_utt;
     const int32_t * forced = (owner && p.forced) ? p.forced + my_row * 8 : nullptr;
@@ -278,48 +365,159 @@ __global__ void __launch_bounds__(kLtThreads, 1) lt_cluster_kernel(const ClParam
 
     for (int cb = 0; cb < 8; cb++) {
         // ---- FF1 (this CTA's 64 hidden rows, all utterances) fused with FF2's partial sums over those 64 columns ----
-        warp_ln_rows<U>(S.x1, nullptr, p.norm_ff, S.hn, p.eps, L);
+        warp_ln_image<U>(S.x1, p.norm_ff, S.b_act, p.eps);
         if (cp.dbg_fine) stamp();
-        tile_dots<kF1Rows, U, kL, true>(S.w_ff1, kF1Rows, &S.hn[0][0], kXL, [&](int r0, int u, const float (&v)[4]) {
-            *reinterpret_cast<float4 *>(&S.ffh[u][r0]) = make_float4(gelu_ggml(v[0], p.gelu_f16), gelu_ggml(v[1], p.gelu_f16),
-                                                                      gelu_ggml(v[2], p.gelu_f16), gelu_ggml(v[3], p.gelu_f16));
-        });
+        if (tid == 0) {                                      // D[64 x (16 hi | 16 lo)] = W1[64 r .., :] . LN(x1)^T
+            fence_async_proxy();                             // the operand rows were written through the generic proxy (this CTA's warps)
+            tc_after_sync();
+            constexpr uint32_t idesc = tc::umma_idesc_bf16(kF1Rows, 32);
+            const uint32_t a0 = smem_u32(S.w_ff1), b0 = smem_u32(&S.b_act[0][0][0]);
+#pragma unroll
+            for (int kt = 0; kt < kL / 64; kt++)
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    tc::umma_bf16(tmem, tc::umma_desc_sw128(a0 + kt * (kF1Rows * 128) + j * 32), tc::umma_desc_sw128(b0 + kt * 2 * kBTile + j * 32), idesc, (kt | j) != 0);
+            tc::umma_commit(&S.mbar[3]);
+        }
+        mbar_wait(&S.mbar[3], mma_par); mma_par ^= 1u;
+        tc_after_sync();
         if (cp.dbg_fine) stamp();
+        {   // GELU -> this CTA's [16 x 64] operand of the second product.  M = 64: row m on TMEM lane 32 (m / 16) + m % 16
+            float v[3], vl[3];
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                const int u = wg + 4 * j;
+                v[j] = u < U ? tmem_ld1(tmem + ((uint32_t)(32 * wq) << 16) + (uint32_t)u) : 0.0f;
+                vl[j] = u < U ? tmem_ld1(tmem + ((uint32_t)(32 * wq) << 16) + (uint32_t)(16 + u)) : 0.0f;
+            }
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 3; j++) v[j] += vl[j];
+            if (lane < 16) {
+                const int m = 16 * wq + lane;
+#pragma unroll
+                for (int j = 0; j < 3; j++) {
+                    const int u = wg + 4 * j;
+                    if (u < U) {
+                        uint32_t h, l;
+                        split_bf(gelu_ggml(v[j], p.gelu_f16), h, l);
+                        const int off = tc::swz_offset(u, m);
+                        *reinterpret_cast<uint16_t *>(&S.b_ffh[0][off]) = (uint16_t)h;
+                        *reinterpret_cast<uint16_t *>(&S.b_ffh[1][off]) = (uint16_t)l;
+                    }
+                }
+            }
+        }
+        tc_before_sync();
         __syncthreads();
         if (cp.dbg_fine) stamp();
-        // partial[n][u] = sum_{k < 64} W2[n][64 r + k] ffh[u][k]: 4 consecutive n per store, to the rank that reduces them (n / 16)
-        tile_dots<kL, U, kF1Rows, true>(S.w_ff2, kL, &S.ffh[0][0], kF1Rows + 4, [&](int r0, int u, const float (&v)[4]) {
-            dsmem_st4(&S.recv[rank][u][r0 % kF2Rows], r0 / kF2Rows, make_float4(v[0], v[1], v[2], v[3]));
-        });
-        stamp(); cluster_sync_all(); stamp();
-        // ---- reduce the 16 partial sums of this CTA's 16 output rows (rank order), add the residual, gather the layer output ----
-        if (tid < (kF2Rows / 4) * U) {
-            const int u = tid % U, g = tid / U, n = rank * kF2Rows + 4 * g;
-            float4 a = *reinterpret_cast<const float4 *>(&S.x1[u][n]);
+        if (tid == 0) {                                      // partial[n][u] = sum_{k < 64} W2[n][64 r + k] ffh[u][k]: two 128-row tiles
+            fence_async_proxy();
+            tc_after_sync();
+            constexpr uint32_t idesc = tc::umma_idesc_bf16(128, 32);
+            const uint32_t a0 = smem_u32(S.w_ff2), b0 = smem_u32(&S.b_ffh[0][0]);
 #pragma unroll
-            for (int src = 0; src < kCS; src++) {
-                const float4 t = *reinterpret_cast<const float4 *>(&S.recv[src][u][4 * g]);
-                a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+            for (int t = 0; t < 2; t++)
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    tc::umma_bf16(tmem + 32 + 32 * t, tc::umma_desc_sw128(a0 + t * kTile128 + j * 32), tc::umma_desc_sw128(b0 + j * 32), idesc, j != 0);
+            tc::umma_commit(&S.mbar[3]);
+        }
+        mbar_wait(&S.mbar[3], mma_par); mma_par ^= 1u;
+        tc_after_sync();
+        {   // partial sums of output n = 128 t + 32 wq + lane go to the rank that reduces it (n / 16)
+            float v[2][3], vl[2][3];
+#pragma unroll
+            for (int t = 0; t < 2; t++)
+#pragma unroll
+                for (int j = 0; j < 3; j++) {
+                    const int u = wg + 4 * j;
+                    v[t][j] = u < U ? tmem_ld1(tmem + ((uint32_t)(32 * wq) << 16) + (uint32_t)(32 + 32 * t + u)) : 0.0f;
+                    vl[t][j] = u < U ? tmem_ld1(tmem + ((uint32_t)(32 * wq) << 16) + (uint32_t)(48 + 32 * t + u)) : 0.0f;
+                }
+            tmem_ld_wait();
+#pragma unroll
+            for (int t = 0; t < 2; t++) {
+                const int n = 128 * t + 32 * wq + lane;
+#pragma unroll
+                for (int j = 0; j < 3; j++) { const int u = wg + 4 * j; if (u < U) dsmem_st(&S.recv[rank][u][n % kF2Rows], n / kF2Rows, v[t][j] + vl[t][j]); }
             }
-            dsmem_st4_all(&S.hn[u][n], a);
+        }
+        tc_before_sync();
+        stamp(); cluster_sync_all(); stamp();
+        // ---- reduce the 16 partial sums of this CTA's 16 output rows (rank order), add the residual, gather the layer output as the
+        //      next product's operand (hi | lo images) in every CTA ----
+        //      Four lanes per (utterance, 4 outputs): each adds 4 source ranks, a fixed shuffle tree joins them (deterministic), each
+        //      stores to 4 destination ranks.
+        {
+            const int item = tid >> 2, part = tid & 3;
+            const bool act = item < (kF2Rows / 4) * U;       // (U <= 10: 160 threads = whole warps, the shuffles below see full warps)
+            const int itc = act ? item : 0, u = itc % U, g = itc / U, n = rank * kF2Rows + 4 * g;
+            float4 a = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            if (tid < ((kF2Rows / 4) * U * 4 + 31) / 32 * 32) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const float4 t = *reinterpret_cast<const float4 *>(&S.recv[4 * part + i][u][4 * g]);
+                    a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+                }
+#pragma unroll
+                for (int o = 1; o <= 2; o <<= 1) {
+                    a.x += __shfl_xor_sync(0xffffffffu, a.x, o); a.y += __shfl_xor_sync(0xffffffffu, a.y, o);
+                    a.z += __shfl_xor_sync(0xffffffffu, a.z, o); a.w += __shfl_xor_sync(0xffffffffu, a.w, o);
+                }
+                if (act) {
+                    const float4 r = *reinterpret_cast<const float4 *>(&S.x1[u][n]);
+                    a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
+                    uint32_t h[4], l[4];
+                    split_bf(a.x, h[0], l[0]); split_bf(a.y, h[1], l[1]); split_bf(a.z, h[2], l[2]); split_bf(a.w, h[3], l[3]);
+                    const int off = tc::swz_offset(u, n & 63);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        dsmem_st2u(&S.b_act[n >> 6][0][off], 4 * part + i, h[0] | (h[1] << 16), h[2] | (h[3] << 16));
+                        dsmem_st2u(&S.b_act[n >> 6][1][off], 4 * part + i, l[0] | (l[1] << 16), l[2] | (l[3] << 16));
+                    }
+                }
+            }
         }
         stamp(); cluster_sync_all(); stamp();
-        // ---- out-projection of codebook cb (+bias): 127 rows x U utterances -> the utterance's owner CTA (magpie.cpp:1037-1048) ----
-        mbar_wait(&S.mbar[1], (uint32_t)(cb & 1));
-        if (cp.dbg_fine) stamp();
-        {
-            const float * ob = p.out_b[cb];
-            tile_dots<kOutRows, U, kL, true>(S.w_out, out_nr, &S.hn[0][0], kXL, [&](int r0, int u, const float (&v)[4]) {
+        // ---- out-projection of codebook cb (+bias): 128 rows x U utterances -> the utterance's owner CTA (magpie.cpp:1037-1048) ----
+        if (has_out) {                                       // (CTA-uniform)
+            if (tid == 0) {
+                mbar_wait(&S.mbar[1], (uint32_t)(cb & 1));
+                fence_async_proxy();
+                tc_after_sync();
+                constexpr uint32_t idesc = tc::umma_idesc_bf16(128, 32);
+                const uint32_t a0 = smem_u32(S.w_out), b0 = smem_u32(&S.b_act[0][0][0]);
 #pragma unroll
-                for (int i = 0; i < 4; i++)
-                    if (r0 + i < out_nr) dsmem_st(&S.logits[out_r0 + r0 + i], u, v[i] + ob[out_r0 + r0 + i]);
-            });
-        }
-        __syncthreads();                                     // this CTA is done reading w_out: prefetch the next codebook's slice
+                for (int kt = 0; kt < kL / 64; kt++)
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        tc::umma_bf16(tmem + 96, tc::umma_desc_sw128(a0 + kt * kTile128 + j * 32), tc::umma_desc_sw128(b0 + kt * 2 * kBTile + j * 32), idesc, (kt | j) != 0);
+                tc::umma_commit(&S.mbar[3]);
+            }
+            mbar_wait(&S.mbar[3], mma_par); mma_par ^= 1u;
+            tc_after_sync();
+            if (cp.dbg_fine) stamp();
+            float v[3], vl[3];
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                const int u = wg + 4 * j;
+                v[j] = u < U ? tmem_ld1(tmem + ((uint32_t)(32 * wq) << 16) + (uint32_t)(96 + u)) : 0.0f;
+                vl[j] = u < U ? tmem_ld1(tmem + ((uint32_t)(32 * wq) << 16) + (uint32_t)(112 + u)) : 0.0f;
+            }
+            tmem_ld_wait();
+            const int id = out_r0 + 32 * wq + lane;
+            if (id < V) {
+                const float bias = p.out_b[cb][id];
+#pragma unroll
+                for (int j = 0; j < 3; j++) { const int u = wg + 4 * j; if (u < U) dsmem_st(&S.logits[id], u, (v[j] + vl[j]) + bias); }
+            }
+            tc_before_sync();
+        } else if (tid == 0) mbar_wait(&S.mbar[1], (uint32_t)(cb & 1));
+        __syncthreads();                                     // the MMAs have consumed w_out: prefetch the next codebook's tiles
         if (tid == 0 && cb < 7) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_expect_tx(&S.mbar[1], (uint32_t)(out_nr * L) * 2u);
-            if (out_nr) bulk_g2s(S.w_out, (const bf *)p.out_w[cb + 1] + (size_t)out_r0 * L, (uint32_t)(out_nr * L) * 2u, &S.mbar[1]);
+            mbar_expect_tx(&S.mbar[1], has_out ? 4u * kTile128 : 0u);
+            if (has_out) bulk_g2s(S.w_out, reinterpret_cast<const unsigned char *>(cp.out_t[cb + 1]) + (size_t)rank * 4 * kTile128, 4u * kTile128, &S.mbar[1]);
         }
         stamp(); cluster_sync_all(); stamp();
         // ---- owner: mask, argmax, top-k sample, feedback gather, attention of position cb + 1, x1 broadcast ----
@@ -398,15 +596,18 @@ __global__ void __launch_bounds__(kLtThreads, 1) lt_cluster_kernel(const ClParam
         }
         stamp(); cluster_sync_all(); stamp();
     }
+    tc_before_sync();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols));
 }
 
 template <int U> bool launch_cl(const ClParams & cp, int n_clusters, cudaStream_t stream) {
-    static_assert(sizeof(ClSmem<U>) + 128 <= 227 * 1024, "lt_cluster shared memory");
+    static_assert(sizeof(ClSmem<U>) + 1024 <= 227 * 1024, "lt_cluster shared memory");
     static_assert(U <= 10, "hidden-state scratch holds 10 utterances");
     static DeviceOnce attr_done;
     int dev = 0;
     MGB_CUDA_TRY(cudaGetDevice(&dev));
-    const size_t smem = sizeof(ClSmem<U>) + 128;
+    const size_t smem = sizeof(ClSmem<U>) + 1024;
     if (!attr_done.done(dev)) {
         MGB_CUDA_TRY(cudaFuncSetAttribute(lt_cluster_kernel<U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         MGB_CUDA_TRY(cudaFuncSetAttribute(lt_cluster_kernel<U>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
@@ -427,12 +628,12 @@ template <int U> bool launch_cl(const ClParams & cp, int n_clusters, cudaStream_
 template <int U> int max_clusters() {
     int ncl = 0;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(kCS * 8); cfg.blockDim = dim3(kLtThreads); cfg.dynamicSmemBytes = sizeof(ClSmem<U>) + 128;
+    cfg.gridDim = dim3(kCS * 8); cfg.blockDim = dim3(kLtThreads); cfg.dynamicSmemBytes = sizeof(ClSmem<U>) + 1024;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = kCS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    const bool ok = cudaFuncSetAttribute(lt_cluster_kernel<U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(ClSmem<U>) + 128)) == cudaSuccess &&
+    const bool ok = cudaFuncSetAttribute(lt_cluster_kernel<U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(ClSmem<U>) + 1024)) == cudaSuccess &&
                     cudaFuncSetAttribute(lt_cluster_kernel<U>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
                     cudaOccupancyMaxActiveClusters(&ncl, lt_cluster_kernel<U>, &cfg) == cudaSuccess;
     cudaGetLastError();
@@ -445,7 +646,7 @@ template <int U> int max_clusters() {
 int lt_cluster_plan(const Model & m, int B) {
     const mgb_hparams & hp = m.hp;
     if (getenv("MGB_NO_LT_CLUSTER") != nullptr || getenv("MGB_LT_STREAM") != nullptr || getenv("MGB_NO_LT_BATCH") != nullptr) return 0;
-    if (m.precision != MGB_PREC_BF16 || !m.lt_in_table[0] || !m.lt_qkvo || !m.lt_qkv_tab || !m.lt_ff2_sl || B < 4) return 0;
+    if (m.precision != MGB_PREC_BF16 || !m.lt_in_table[0] || !m.lt_qkvo || !m.lt_qkv_tab || !m.lt_ff1.tiles || !m.lt_ff2.tiles || B < 4) return 0;
     if (hp.lt_dim != kL || hp.lt_ffn_dim != kF || hp.d_model != kDm || hp.vocab_per_cb > kV || hp.vocab_per_cb < 16) return 0;
     static std::atomic<int> cap[64];                     // co-resident clusters per device (+1; 0 = not probed yet)
     int dev = 0;
@@ -460,7 +661,8 @@ int lt_cluster_plan(const Model & m, int B) {
 
 bool launch_lt_cluster(const Model & m, const lt::LtParams & p, int U, cudaStream_t stream) {
     ClParams cp;
-    cp.p = p; cp.qkvo = m.lt_qkvo; cp.qkv_tab = m.lt_qkv_tab; cp.ff2_sl = m.lt_ff2_sl;
+    cp.p = p; cp.qkvo = m.lt_qkvo; cp.qkv_tab = m.lt_qkv_tab; cp.ff1_t = m.lt_ff1.tiles; cp.ff2_t = m.lt_ff2.tiles;
+    for (int cb = 0; cb < 8; cb++) { cp.out_t[cb] = m.lt_out_w[cb].tiles; if (!cp.out_t[cb]) { set_error("lt_cluster: output projection tiles missing"); return false; } }
     static unsigned long long * dbg = nullptr;
     if (getenv("MGB_LT_DBG") && !dbg) { MGB_CUDA_TRY(cudaMalloc((void **)&dbg, 256 * 8)); MGB_CUDA_TRY(cudaMemset(dbg, 0, 256 * 8)); }
     cp.dbg = dbg; cp.dbg_fine = getenv("MGB_LT_DBG") && atoi(getenv("MGB_LT_DBG")) >= 2;

@@ -23,16 +23,6 @@ __global__ void f32_to_bf16_kernel(const float * __restrict__ src, __nv_bfloat16
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = __float2bfloat16_rn(src[i]);
 }
 
-// W2 [N][K] -> [16][N][K / 16]: slice r holds columns [r K / 16, (r + 1) K / 16) of every row, contiguous (lt_cluster.cu fuses FF1 and FF2:
-// CTA r multiplies its own 64 FFN-hidden values into exactly these columns)
-__global__ void slice_columns_kernel(const __nv_bfloat16 * __restrict__ W, int N, int K, int parts, __nv_bfloat16 * __restrict__ out) {
-    const int kc = K / parts;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)N * K; i += (size_t)gridDim.x * blockDim.x) {
-        const int n = (int)(i / K), k = (int)(i % K), r = k / kc;
-        out[((size_t)r * N + n) * kc + (k - r * kc)] = W[i];
-    }
-}
-
 struct Uploader {
     std::vector<void *> & allocs;
     bool ok = true;
@@ -290,14 +280,6 @@ Model * load_model(const char * path, int device, int precision) {
         if (!launch_lt_fold_ov(M->lt_qkv.w, M->lt_o.w, L, t, nullptr) || cudaDeviceSynchronize() != cudaSuccess) {
             set_error("magpie_init: folding the LT output projection failed"); return nullptr;
         }
-        if (hp.lt_ffn_dim % 16 == 0) {
-            void * sl = nullptr;
-            if (cudaMalloc(&sl, (size_t)L * hp.lt_ffn_dim * 2) != cudaSuccess) { set_error("cudaMalloc failed"); return nullptr; }
-            M->allocations.push_back(sl);
-            slice_columns_kernel<<<128, 256>>>((const __nv_bfloat16 *)M->lt_ff2.w, L, hp.lt_ffn_dim, 16, (__nv_bfloat16 *)sl);
-            if (cudaGetLastError() != cudaSuccess) { set_error("magpie_init: slicing the LT FFN matrix failed"); return nullptr; }
-            M->lt_ff2_sl = sl;
-        }
         // LT positions 1..7 see x = P_cb[code] + pos[cb+1], a function of (cb, code) only: their [q | k | vo] rows are tabulated
         // (7 x V x 3L f32 = 43.5 MB), so those positions need neither LayerNorm + QKV GEMV nor the exchange of its result
         void * tb = nullptr;
@@ -317,6 +299,8 @@ Model * load_model(const char * path, int device, int precision) {
         for (auto & L : M->dec) for (DevMat * m : {&L.qkv, &L.o, &L.xq, &L.xkv, &L.xo, &L.ff1, &L.ff2}) mats.push_back(m);
         for (auto & L : M->enc) for (DevMat * m : {&L.qkv, &L.o, &L.ff1, &L.ff2}) mats.push_back(m);      // (ff1 / ff2: k = 3 causal convs, taps concatenated along k)
         mats.push_back(&M->final_w);
+        mats.push_back(&M->lt_ff1); mats.push_back(&M->lt_ff2);                      // lt_cluster.cu: FFN and output projections on tcgen05
+        for (int cb = 0; cb < 8; cb++) mats.push_back(&M->lt_out_w[cb]);
         for (DevMat * m : mats) {
             if (m->w == nullptr || m->K % 64 != 0) continue;
             void * t = nullptr;

@@ -50,7 +50,6 @@ struct Model {
     DevMat lt_out_w[8]; float * lt_out_b[8] = {};
     float * lt_qkv_tab = nullptr;           // f32 [7][V][3*lt_dim]: [q | k | Wo Wv n] of LT position cb+1 for every fed code of codebook cb (row gather instead of LN + QKV GEMV)
     void * lt_qkvo = nullptr;               // bf16 [4*lt_dim][lt_dim]: [Wq; Wk; hi(Wo Wv); lo(Wo Wv)] (frame_loop.cu: the O-projection folded into V)
-    void * lt_ff2_sl = nullptr;             // bf16 [16][lt_dim][lt_ffn_dim / 16]: column slice r of W2 (rows x 64 columns) contiguous, one per CTA rank of lt_cluster.cu
     float * lt_in_table[8] = {};            // P_cb = E_cb . Win^T + b  [V][lt_dim] f32 (built on the device at load)
 
     std::map<std::string, std::string> meta_str;    // tokenizer strings etc.

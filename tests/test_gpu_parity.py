@@ -569,9 +569,11 @@ def test_batched_generation_loop_with_both_local_transformer_kernels(B, full_mod
 
 
 def test_batched_local_transformer_matches_per_utterance_kernel(B, full_model_path, full_oracle, monkeypatch):
-    """bf16, 20 utterances: the weight-stationary persistent LT (lt_batch.cu, default for >= 16 utterances) against the
-    one-cluster-per-utterance kernel (MGB_NO_LT_BATCH=1) and the oracle; same bf16 weights and f32 arithmetic, so the two
-    kernels differ by summation order only."""
+    """bf16, 20 utterances: the cluster-resident batched LT (lt_cluster.cu, default from 4 utterances) against the
+    one-cluster-per-utterance kernel (MGB_NO_LT_BATCH=1) and the oracle.  Same bf16 weights; the batched kernel multiplies on the
+    tensor cores with the f32 activations split into bf16 hi + lo halves (2^-17 relative) and the f16 GELU table rounding of ggml
+    can flip on such a difference, so the two kernels agree to a few 1e-4 of the logits' rms -- two orders below the bf16
+    precision's own 2e-2 band against the oracle (measured: max abs diff 7.6e-5 at rms 0.38)."""
     nb = 20
     m = B.Model(full_model_path, 0, B.PREC_BF16)
     s = m.session(batch=nb, max_text=32)
@@ -593,7 +595,7 @@ def test_batched_local_transformer_matches_per_utterance_kernel(B, full_model_pa
     # teacher-forced: logits of all 8 codebooks
     sa, aa, la = run(False, temperature=0.0, forced_codes=forced)
     sb, ab, lb = run(True, temperature=0.0, forced_codes=forced)
-    close(la, lb, 1e-4)
+    close(la, lb, 3e-4)
     assert np.mean(aa == ab) >= 0.99
     # against the oracle for the rows that carry the oracle's own hidden states and forced codes
     o = full_oracle["o"]
