@@ -68,6 +68,7 @@ struct Session {
     unsigned long long * d_loop_dbg = nullptr;
     void * tc_scratch = nullptr; size_t tc_scratch_bytes = 0;     // tensor-core path: activation tile images
     void * tc_scratch2 = nullptr;                                  // second image buffer (FF1 epilogue -> FF2 input)
+    float * ln_stats = nullptr; bool ln_fold = false;              // LayerNorm folded through the QKV GEMM: row statistics [<= 96 slices][64][2] (kernels.cuh)
     void * lt_scratch = nullptr; size_t lt_scratch_bytes = 0;     // batched local transformer: activation scratch
     int prefill_len = 0;                                            // > 0 while mgb_prefill runs decoder_layers on the context frames
     float * fold_xm = nullptr, * fold_xn = nullptr; bool fold_ready = false;     // batched decode: folded cross-attention tables [L][B][max_text][d]
@@ -158,6 +159,7 @@ static bool decoder_layers(Session & s, Tokens tok, bool want_hidden) {
     static const int skip = getenv("MGB_STEP_SKIP") ? atoi(getenv("MGB_STEP_SKIP")) : 0;
     const int d = hp.d_model, dxa = hp.dec_xa_heads * hp.dec_xa_d_head, M = tok.M;
     const size_t kv_layer = s.kv_rows * d * m.wsize, xkv_layer = (size_t)s.B * s.max_text * dxa * m.wsize;
+    bool ln_folded = false;              // the previous layer's FF2 has written this layer's QKV operand (x .* norm_self) + row statistics
     for (int l = 0; l < hp.dec_layers; l++) {
         const DecLayer & L = m.dec[l];
         char * kl = (char *)s.kc + l * kv_layer, * vl = (char *)s.vc + l * kv_layer;
@@ -167,6 +169,9 @@ static bool decoder_layers(Session & s, Tokens tok, bool want_hidden) {
         // self-attention: LN -> QKV (K,V written straight into the cache) -> attention -> O + residual
         a.W = L.qkv; a.X = s.x; a.ldx = d; a.ln_w = L.norm_self; a.Y = s.qbuf; a.ldy = d;
         a.n_q = d; a.dkv = d; a.kdst = kl; a.vdst = vl; a.tok_slot = tok.slot;
+        if (ln_folded) {
+            a.x_prepacked = true; a.ln_fold_stats = s.ln_stats; a.ln_fold_slices = d / ts_resid_nc(hp.d_ffn); a.ln_fold_csum = L.qkv_csum;
+        }
         if (!(skip & 4) && !launch_linear(a, s.stream)) return false;
         LinearArgs o;
         o.tc_scratch = s.tc_scratch; o.tc_scratch_bytes = s.tc_scratch_bytes;
@@ -219,6 +224,13 @@ static bool decoder_layers(Session & s, Tokens tok, bool want_hidden) {
         }
         // conv-FFN (kernel 1): LN -> W1 -> GELU -> W2 + residual
         if (chain) { f1.pack_out = s.tc_scratch2; f1.Y = nullptr; f2.tc_scratch = s.tc_scratch2; f2.x_prepacked = true; }
+        // ... and FF2's epilogue emits the NEXT layer's QKV operand with the LayerNorm folded through that GEMM (kernels.cuh)
+        ln_folded = false;
+        if (chain && !skip && s.ln_stats && l + 1 < hp.dec_layers && m.dec[l + 1].qkv_csum && s.ln_fold) {
+            f2.pack_out = s.tc_scratch; f2.next_ln_w = m.dec[l + 1].norm_self; f2.stats_out = s.ln_stats;
+            if (ts_linear_supported(f2)) ln_folded = true;
+            else { f2.pack_out = nullptr; f2.next_ln_w = nullptr; f2.stats_out = nullptr; }
+        }
         if (!(skip & 16) && !launch_linear(f1, s.stream)) return false;
         if (!(skip & 32) && !launch_linear(f2, s.stream)) return false;
     }
@@ -405,6 +417,8 @@ mgb_session * mgb_session_new_paged(mgb_model * mm, int batch, int max_text, int
         char * tp2 = nullptr;
         if (!s->alloc(tp2, tb)) return nullptr;
         s->tc_scratch2 = tp2;
+        if (!s->alloc(s->ln_stats, (size_t)96 * 64 * 2)) return nullptr;
+        s->ln_fold = getenv("MGB_NO_LNFOLD") == nullptr;
     }
     // (launch_xattn_folded holds one score per text position in shared memory: up to 512 positions; longer text capacities keep
     //  the q GEMM + attention + o GEMM kernels)

@@ -270,6 +270,7 @@ bool launch_linear_tc(const LinearArgs & a, cudaStream_t stream) {
     e.N = a.W.N; e.M = M; e.bias = a.bias; e.res = a.res; e.ldr = a.ldr; e.Y = a.Y; e.ldy = a.ldy; e.act = a.act; e.gelu_f16 = a.gelu_f16;
     e.n_q = a.n_q; e.dkv = a.dkv; e.kdst = (bf *)a.kdst; e.vdst = (bf *)a.vdst; e.tok_slot = a.tok_slot;
     if (MT == 64 && ts_linear_supported(a)) return launch_linear_ts(a, hi, lo, stream);      // decoder-step GEMMs: token-stationary kernel (gemm_ts.cu)
+    if (a.ln_fold_stats || a.next_ln_w) { set_error("linear: a folded LayerNorm needs the token-stationary GEMM (gemm_ts.cu)"); return false; }
     if (MT == 64) {
         // one token tile: split K over a cluster (deterministic DSMEM reduction) to shorten the per-SM ingest chain
         const int KT = K / 64;

@@ -31,6 +31,8 @@ struct TsEpi {
     int gelu_f16;
     int n_q, dkv; bf * kdst; bf * vdst; const int32_t * tok_slot;
     bf * pk_hi; bf * pk_lo;
+    const float * next_w; float * stats_out;                       // TS_RES producer of a folded LayerNorm (kernels.cuh)
+    const float * ln_stats; int ln_slices; const float * ln_csum; float eps; int K;     // TS_QKV consumer
 };
 
 enum { TS_QKV = 1, TS_RES = 2, TS_GELU_PACK = 3 };
@@ -174,6 +176,17 @@ __global__ void __launch_bounds__(kTsThreads, 1) ts_linear_kernel(const bf * Wt,
                 }
             }
             if (EPI == TS_QKV) {
+                if (e.ln_stats) {                    // LayerNorm folded through this GEMM: y = (acc - mean * csum[n]) * rstd
+                    float s1 = 0.0f, s2 = 0.0f;
+                    for (int sl = 0; sl < e.ln_slices; sl++) {
+                        const float2 st = *reinterpret_cast<const float2 *>(e.ln_stats + ((size_t)sl * 64 + m) * 2);
+                        s1 += st.x; s2 += st.y;
+                    }
+                    const float mean = s1 / (float)e.K, var = fmaxf(s2 / (float)e.K - mean * mean, 0.0f);
+                    const float rstd = 1.0f / sqrtf(var + e.eps);
+#pragma unroll
+                    for (int j = 0; j < NC; j++) y[j] = (y[j] - mean * e.ln_csum[n0 + j]) * rstd;
+                }
                 if (n0 < e.n_q) {
                     float4 * dst = reinterpret_cast<float4 *>(e.Y + (size_t)m * e.ldy + n0);
 #pragma unroll
@@ -198,8 +211,32 @@ __global__ void __launch_bounds__(kTsThreads, 1) ts_linear_kernel(const bf * Wt,
                 for (int j = 0; j < NC / 4; j++) r[j] = rs[j];
                 float4 * dst = reinterpret_cast<float4 *>(e.Y + (size_t)m * e.ldy + n0);
 #pragma unroll
-                for (int j = 0; j < NC / 4; j++)
-                    dst[j] = make_float4(y[4 * j] + r[j].x, y[4 * j + 1] + r[j].y, y[4 * j + 2] + r[j].z, y[4 * j + 3] + r[j].w);
+                for (int j = 0; j < NC / 4; j++) {
+                    y[4 * j] += r[j].x; y[4 * j + 1] += r[j].y; y[4 * j + 2] += r[j].z; y[4 * j + 3] += r[j].w;
+                    dst[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+                }
+                if (e.next_w) {                      // the next GEMM's operand: (y .* w) as hi | lo images + this slice's row statistics
+                    float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll
+                    for (int j = 0; j < NC; j++) { s1 += y[j]; s2 = fmaf(y[j], y[j], s2); }
+                    *reinterpret_cast<float2 *>(e.stats_out + ((size_t)blockIdx.x * 64 + m) * 2) = make_float2(s1, s2);
+#pragma unroll
+                    for (int j = 0; j < NC / 8; j++) {
+                        uint32_t h[4], l[4];
+#pragma unroll
+                        for (int p = 0; p < 4; p++) {
+                            const float a = y[8 * j + 2 * p] * e.next_w[n0 + 8 * j + 2 * p], b = y[8 * j + 2 * p + 1] * e.next_w[n0 + 8 * j + 2 * p + 1];
+                            const bf ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
+                            const bf la = __float2bfloat16_rn(a - __bfloat162float(ha)), lb = __float2bfloat16_rn(b - __bfloat162float(hb));
+                            h[p] = (uint32_t)__bfloat16_as_ushort(ha) | ((uint32_t)__bfloat16_as_ushort(hb) << 16);
+                            l[p] = (uint32_t)__bfloat16_as_ushort(la) | ((uint32_t)__bfloat16_as_ushort(lb) << 16);
+                        }
+                        const int n = n0 + 8 * j;
+                        const size_t off = (size_t)(n >> 6) * kXTile + tc::swz_offset(m, n & 63);
+                        *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(e.pk_hi) + off) = make_uint4(h[0], h[1], h[2], h[3]);
+                        *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(e.pk_lo) + off) = make_uint4(l[0], l[1], l[2], l[3]);
+                    }
+                }
             } else {                                 // GELU + hi | lo tile images for the next GEMM (k tile n / 64, 16-byte chunk (n % 64) / 8)
 #pragma unroll
                 for (int j = 0; j < NC / 8; j++) {
@@ -251,12 +288,42 @@ template <int NC, int EPI, int SPLIT = 1, int STAGES = 8> bool launch_ts(const b
 
 }  // namespace
 
+static int ts_shape() {
+    static const int shaped = getenv("MGB_TS_SHAPE") ? atoi(getenv("MGB_TS_SHAPE")) : 1;
+    return shaped;
+}
+
+// columns per CTA of the residual-epilogue GEMM (mirrors the dispatch in launch_linear_ts below)
+int ts_resid_nc(int K) {
+    const int KT = K / 64, shaped = ts_shape();
+    if (shaped && KT >= 32 && KT % 4 == 0) return 32;
+    if (shaped == 2 && KT % 4 == 0) return 32;
+    return 8;
+}
+
+__global__ void row_dots_kernel(const bf * __restrict__ W, const float * __restrict__ v, int N, int K, float * __restrict__ out) {
+    const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (n >= N) return;
+    float s = 0.0f;
+    for (int k = lane; k < K; k += 32) s = fmaf(__bfloat162float(W[(size_t)n * K + k]), v[k], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[n] = s;
+}
+bool launch_row_dots(const void * W, const float * v, int N, int K, float * out, cudaStream_t stream) {
+    row_dots_kernel<<<(N + 7) / 8, 256, 0, stream>>>((const bf *)W, v, N, K, out);
+    MGB_LAUNCH_CHECK();
+    return true;
+}
+
 // The three decoder-step uses with their epilogues; everything else stays on gemm_tc.cu.  hi / lo: packed activations (MT = 64).
 bool ts_linear_supported(const LinearArgs & a) {
     if (getenv("MGB_NO_TS") != nullptr) return false;
     if (a.M > 64 || a.W.taps != 1 || a.W.K % 64 != 0 || a.bias || a.W.N % 128 != 0) return false;
+    if (a.ln_fold_stats && (!a.x_prepacked || !a.ln_fold_csum || a.ln_fold_slices <= 0 || a.n_q < 0)) return false;
     const bool qkv = a.n_q >= 0 && !a.res && a.act == ACT_NONE && !a.pack_out && a.Y && a.n_q % 16 == 0 && a.dkv % 16 == 0 && a.kdst && a.vdst && (a.ldy % 4) == 0;
-    const bool resid = a.n_q < 0 && a.res && a.act == ACT_NONE && !a.pack_out && a.Y && (a.ldr % 4) == 0 && (a.ldy % 4) == 0;
+    const bool resid = a.n_q < 0 && a.res && a.act == ACT_NONE && a.Y && (a.ldr % 4) == 0 && (a.ldy % 4) == 0 &&
+                       (a.pack_out ? (a.next_ln_w && a.stats_out && a.W.N % 64 == 0) : !a.next_ln_w);
     const bool gpack = a.n_q < 0 && !a.res && a.act == ACT_GELU && a.pack_out && !a.Y;
     return qkv || resid || gpack;
 }
@@ -267,6 +334,8 @@ bool launch_linear_ts(const LinearArgs & a, const void * hi, const void * lo, cu
     e.n_q = a.n_q; e.dkv = a.dkv; e.kdst = (bf *)a.kdst; e.vdst = (bf *)a.vdst; e.tok_slot = a.tok_slot;
     e.pk_hi = nullptr; e.pk_lo = nullptr;
     if (a.pack_out) { e.pk_hi = (bf *)a.pack_out; e.pk_lo = e.pk_hi + (size_t)64 * a.W.N; }
+    e.next_w = a.next_ln_w; e.stats_out = a.stats_out;
+    e.ln_stats = a.ln_fold_stats; e.ln_slices = a.ln_fold_slices; e.ln_csum = a.ln_fold_csum; e.eps = a.eps; e.K = a.W.K;
     const int KT = a.W.K / 64;
     const bf * W = (const bf *)a.W.tiles;
     // One-CTA slices for the K = 768 GEMMs (QKV 144 CTAs, O 96, FF1 96).  The wide-K GEMM (FF2, K = 3072) is bound by how fast ONE
@@ -274,7 +343,7 @@ bool launch_linear_ts(const LinearArgs & a, const void * hi, const void * lo, cu
     // by a 4-CTA cluster that divides the k tiles (10 us).  Measured at 64 utterances, us per step: no split 1331, FF2 split over
     // 2 / 4 CTAs 1241 / 1201; cluster slices for the K = 768 GEMMs as well (64 rows x 4, 32 x 4, 64 x 3): 1343 -- the cluster
     // launch and the DSMEM reduction cost more than the ingest they save (MGB_TS_SHAPE=2 keeps that variant for A/B, 0 = no split).
-    static const int shaped = getenv("MGB_TS_SHAPE") ? atoi(getenv("MGB_TS_SHAPE")) : 1;
+    const int shaped = ts_shape();
     const bf * h = (const bf *)hi, * l = (const bf *)lo;
     if (a.n_q >= 0) {
         if (shaped == 2 && KT % 4 == 0 && a.W.N % 64 == 0 && a.n_q % 64 == 0 && a.dkv % 64 == 0) return launch_ts<64, TS_QKV, 4, 4>(W, h, l, KT, e, stream);

@@ -40,6 +40,13 @@ struct LinearArgs {
     void * tc_scratch = nullptr; size_t tc_scratch_bytes = 0;     // activation tile images of the tensor-core path (gemm_tc.cu)
     bool x_prepacked = false;        // tc_scratch already holds the hi | lo tile images of X (written by the producing kernel)
     void * pack_out = nullptr;       // tensor-core path, M <= 64: write the output as hi | lo tile images here (Y may be null)
+    // LayerNorm folded THROUGH the next GEMM (batched decoder step, gemm_ts.cu; removes the LN + pack launch between two layers):
+    //   producer (res + pack_out + next_ln_w + stats_out): besides Y = acc + res it writes (Y .* next_ln_w) as hi | lo images into
+    //     pack_out and every row's (sum, sum of squares) over the CTA's column slice into stats_out [N / ts_resid_nc(K)][64][2];
+    //   consumer (x_prepacked + ln_fold_*): W . LN(x) = ((W . (x .* w)) - mean * csum) * rstd with csum[n] = sum_k W[n][k] w[k]
+    //     (model.cu), mean / rstd from the slices' sums added in slice order (deterministic).
+    const float * next_ln_w = nullptr; float * stats_out = nullptr;
+    const float * ln_fold_stats = nullptr; int ln_fold_slices = 0; const float * ln_fold_csum = nullptr;
 };
 bool launch_linear(const LinearArgs & a, cudaStream_t stream);
 // tcgen05 path (bf16, >= 16 tokens): gemm_tc.cu
@@ -51,6 +58,8 @@ bool   launch_linear_tc(const LinearArgs & a, cudaStream_t stream);
 // token-stationary variant for <= 64 tokens (gemm_ts.cu): tokens on the MMA M side, 8..32 weight rows per CTA, 96-144 CTAs per GEMM
 bool   ts_linear_supported(const LinearArgs & a);
 bool   launch_linear_ts(const LinearArgs & a, const void * hi, const void * lo, cudaStream_t stream);
+int    ts_resid_nc(int K);          // columns per CTA slice of the residual-epilogue GEMM with contraction width K (the granularity of stats_out)
+bool   launch_row_dots(const void * W_bf16, const float * v, int N, int K, float * out, cudaStream_t stream);    // out[n] = sum_k W[n][k] v[k]
 
 struct AttnArgs {
     int precision = 0;

@@ -309,6 +309,13 @@ Model * load_model(const char * path, int device, int precision) {
             if (!tc_pack_weights(m->w, m->N, m->K, t, nullptr, m->taps)) return nullptr;
             m->tiles = t;
         }
+        for (auto & L : M->dec) {
+            void * c = nullptr;
+            if (cudaMalloc(&c, (size_t)L.qkv.N * sizeof(float)) != cudaSuccess) { set_error("cudaMalloc failed"); return nullptr; }
+            M->allocations.push_back(c);
+            if (!launch_row_dots(L.qkv.w, L.norm_self, L.qkv.N, L.qkv.K, (float *)c, nullptr)) return nullptr;
+            L.qkv_csum = (float *)c;
+        }
         if (cudaDeviceSynchronize() != cudaSuccess) { set_error("magpie_init: packing the weight tiles failed"); return nullptr; }
     }
 

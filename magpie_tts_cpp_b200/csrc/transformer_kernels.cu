@@ -470,6 +470,7 @@ __global__ void add_one_kernel(int32_t * v, int n) {
 bool launch_linear(const LinearArgs & a, cudaStream_t stream) {
     if (a.M <= 0) return true;
     if (tc_linear_supported(a)) return launch_linear_tc(a, stream);
+    if (a.ln_fold_stats || a.next_ln_w) { set_error("linear: a folded LayerNorm needs the tensor-core path"); return false; }
     LinParams p;
     p.W = a.W.w; p.N = a.W.N; p.K = a.W.K; p.taps = a.W.taps;
     p.X = a.X; p.ldx = a.ldx; p.ln_w = a.ln_w; p.eps = a.eps; p.bias = a.bias;
