@@ -9,6 +9,7 @@
 // Operands are the same shared-memory images gemm_tc.cu uses (SWIZZLE_128B K-major tiles of 64 k): an 8-row-aligned run of n
 // rows inside a packed 128-row weight tile is itself a valid n-row tile, so no second weight layout is needed.
 // Replaces ggml_mul_mat at src/magpie.cpp:3415, 3472, 1796, 1805 for the batched step.
+#include <cstdio>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -24,6 +25,11 @@ using bf = __nv_bfloat16;
 constexpr int kTsThreads = 192;          // warp 0 producer, warp 1 TMEM + MMA issue, warps 2..5 epilogue
 constexpr int kXTile = 64 * 128;         // one 64-token x 64-k bf16 image
 
+// MGB_TS_DBG: globaltimer stamps of CTA (0, 0) of every launch (entry | dependency wait over | first stage landed | last MMA issued |
+// accumulator complete | epilogue done | kernel id), a ring of 1024 launches; dumped by tools/ts_timeline.py through MGB_TS_DBG_DUMP
+__device__ unsigned long long g_ts_dbg[1024 * 8];
+__device__ unsigned g_ts_dbg_n;
+
 struct TsEpi {
     int N, M;
     const float * res; int ldr;
@@ -31,6 +37,7 @@ struct TsEpi {
     int gelu_f16;
     int n_q, dkv; bf * kdst; bf * vdst; const int32_t * tok_slot;
     bf * pk_hi; bf * pk_lo;
+    int dbg;
     const float * next_w; float * stats_out;                       // TS_RES producer of a folded LayerNorm (kernels.cuh)
     const float * ln_stats; int ln_slices; const float * ln_csum; float eps; int K;     // TS_QKV consumer
 };
@@ -73,6 +80,10 @@ __global__ void __launch_bounds__(kTsThreads, 1) ts_linear_kernel(const bf * Wt,
     uint64_t * full = bars, * empty = bars + kTsStages, * acc_full = bars + 2 * kTsStages;
     uint32_t * tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kTsStages + 1);
     const int n0 = blockIdx.x * NC;                                      // first output feature of this CTA
+    __shared__ unsigned dbg_slot;
+    const bool dbg = e.dbg && blockIdx.x == 0 && blockIdx.y == 0;
+    auto stamp = [&](int i) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); g_ts_dbg[(size_t)dbg_slot * 8 + i] = t; };
+    if (dbg && threadIdx.x == 0) { dbg_slot = atomicAdd(&g_ts_dbg_n, 1u) % 1024u; stamp(0); g_ts_dbg[(size_t)dbg_slot * 8 + 6] = NC * 100 + EPI * 10 + SPLIT; }
     const int rank = SPLIT > 1 ? (int)blockIdx.y : 0;
     const int kt_lo = rank * KT_all / SPLIT, KT = (rank + 1) * KT_all / SPLIT - kt_lo;      // this CTA's k tiles [kt_lo, kt_lo + KT)
     float * xbuf = reinterpret_cast<float *>(tiles + kTsStages * kStage + 256);             // rank 0: [SPLIT - 1][64][NC] partial accumulators
@@ -94,49 +105,64 @@ __global__ void __launch_bounds__(kTsThreads, 1) ts_linear_kernel(const bf * Wt,
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0 && lane == 0) {
+    // Producer and MMA roles run their loops WARP-UNIFORMLY (all lanes poll the barriers, one elected lane issues): addresses and
+    // descriptors then live in uniform registers.  Issued from a divergent single lane every tcgen05.mma cost ~60 cycles of register ->
+    // uniform-register moves: 96 MMAs = 3 us of the 4.6 us this loop took per GEMM (profiles/r2_b64_step_timeline.txt).
+    if (warp == 0) {
+        const bool leader = tc::elect_one();
         // weight rows n0 .. n0 + NC - 1 of k tile kt: an 8-row-aligned run inside the packed 128-row tile (n0 / 128, kt)
         const unsigned char * wsrc = reinterpret_cast<const unsigned char *>(Wt) + ((size_t)(n0 / tc::BM) * KTW + kt_lo) * (tc::BM * 128) + (size_t)(n0 % tc::BM) * 128;
         const unsigned char * hsrc = reinterpret_cast<const unsigned char *>(Xhi) + (size_t)kt_lo * kXTile, * lsrc = reinterpret_cast<const unsigned char *>(Xlo) + (size_t)kt_lo * kXTile;
         // programmatic dependent launch: the weights do not depend on the preceding kernel (which produces the activations)
         const int npre = KT < kTsStages ? KT : kTsStages;
-        for (int kt = 0; kt < npre; kt++) {
-            int kk = kt + kt_first; kk = kk >= KT ? kk - KT : kk;
-            tc::mbar_expect_tx(&full[kt], 2 * kXTile + kWTile);
-            tc::bulk_g2s(tiles + kt * kStage + 2 * kXTile, wsrc + (size_t)kk * (tc::BM * 128), kWTile, &full[kt]);
-        }
+        if (leader)
+            for (int kt = 0; kt < npre; kt++) {
+                int kk = kt + kt_first; kk = kk >= KT ? kk - KT : kk;
+                tc::mbar_expect_tx(&full[kt], 2 * kXTile + kWTile);
+                tc::bulk_g2s(tiles + kt * kStage + 2 * kXTile, wsrc + (size_t)kk * (tc::BM * 128), kWTile, &full[kt]);
+            }
         asm volatile("griddepcontrol.wait;" ::: "memory");
+        if (dbg && leader) stamp(1);
         for (int kt = 0; kt < KT; kt++) {
             const int s = kt % kTsStages;
             int kk = kt + kt_first; kk = kk >= KT ? kk - KT : kk;
             unsigned char * st = tiles + s * kStage;
-            if (kt >= npre) {
-                tc::mbar_wait(&empty[s], ((kt / kTsStages) & 1) ^ 1);
-                tc::mbar_expect_tx(&full[s], 2 * kXTile + kWTile);
-                tc::bulk_g2s(st + 2 * kXTile, wsrc + (size_t)kk * (tc::BM * 128), kWTile, &full[s]);
+            if (kt >= npre) tc::mbar_wait(&empty[s], ((kt / kTsStages) & 1) ^ 1);
+            if (leader) {
+                if (kt >= npre) {
+                    tc::mbar_expect_tx(&full[s], 2 * kXTile + kWTile);
+                    tc::bulk_g2s(st + 2 * kXTile, wsrc + (size_t)kk * (tc::BM * 128), kWTile, &full[s]);
+                }
+                tc::bulk_g2s(st, hsrc + (size_t)kk * kXTile, kXTile, &full[s]);
+                tc::bulk_g2s(st + kXTile, lsrc + (size_t)kk * kXTile, kXTile, &full[s]);
             }
-            tc::bulk_g2s(st, hsrc + (size_t)kk * kXTile, kXTile, &full[s]);
-            tc::bulk_g2s(st + kXTile, lsrc + (size_t)kk * kXTile, kXTile, &full[s]);
         }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1) {
         constexpr uint32_t idesc = tc::umma_idesc_bf16(64, NC);          // D[64 tokens x NC] += X[64 x 16] . W[NC x 16]^T
+        const bool leader = tc::elect_one();
+        const uint32_t tiles_d = tc::desc_lo(tc::smem_u32(tiles));       // descriptor address units are 16 bytes
         for (int kt = 0; kt < KT; kt++) {
             const int s = kt % kTsStages;
             tc::mbar_wait(&full[s], (kt / kTsStages) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t h0 = tc::smem_u32(tiles + s * kStage), l0 = h0 + kXTile, w0 = l0 + kXTile;
+            const uint32_t h0 = tiles_d + (uint32_t)s * (kStage >> 4), l0 = h0 + (kXTile >> 4), w0 = l0 + (kXTile >> 4);
+            if (leader) {
+                if (dbg && kt == 0) stamp(2);
 #pragma unroll
-            for (int j = 0; j < tc::BK / 16; j++) {
-                tc::umma_bf16(tmem_base, tc::umma_desc_sw128(h0 + j * 32), tc::umma_desc_sw128(w0 + j * 32), idesc, (kt | j) != 0);
-                tc::umma_bf16(tmem_base, tc::umma_desc_sw128(l0 + j * 32), tc::umma_desc_sw128(w0 + j * 32), idesc, 1u);
+                for (int j = 0; j < tc::BK / 16; j++) {                  // 16 k-elements = 32 bytes = 2 descriptor units inside the swizzle row
+                    tc::umma_lo(tmem_base, h0 + 2 * j, w0 + 2 * j, idesc, (kt | j) != 0);
+                    tc::umma_lo(tmem_base, l0 + 2 * j, w0 + 2 * j, idesc, 1u);
+                }
+                if (kt + kTsStages < KT) tc::umma_commit(&empty[s]);      // only a stage that is refilled needs its release
             }
-            tc::umma_commit(&empty[s]);
         }
-        tc::umma_commit(acc_full);
+        if (leader) { tc::umma_commit(acc_full); if (dbg) stamp(3); }
+        __syncwarp();
     }
     if (warp >= 2) {
         asm volatile("griddepcontrol.wait;" ::: "memory");
         tc::mbar_wait(acc_full, 0);
+        if (dbg && threadIdx.x == 64) stamp(4);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int q = warp & 3;                      // TMEM lane quarter of this warp; M = 64: rows 16 q .. 16 q + 15 on its lanes 0..15
         const int m = 16 * q + lane;
@@ -257,6 +283,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) ts_linear_kernel(const bf * Wt,
             }
         }
     }
+    if (dbg && threadIdx.x == 64) stamp(5);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(NC < 32 ? 32 : NC));
@@ -335,6 +362,31 @@ bool launch_linear_ts(const LinearArgs & a, const void * hi, const void * lo, cu
     e.pk_hi = nullptr; e.pk_lo = nullptr;
     if (a.pack_out) { e.pk_hi = (bf *)a.pack_out; e.pk_lo = e.pk_hi + (size_t)64 * a.W.N; }
     e.next_w = a.next_ln_w; e.stats_out = a.stats_out;
+    static const bool dbg_on = getenv("MGB_TS_DBG") != nullptr;
+    e.dbg = dbg_on ? 1 : 0;
+    if (dbg_on && getenv("MGB_TS_DBG_DUMP")) {           // dump at the given call of this function (direct launches, not graph replays)
+        static int calls = 0;
+        cudaStreamCaptureStatus cst = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(stream, &cst);
+        static bool dumped = false;
+        if (++calls >= atoi(getenv("MGB_TS_DBG_DUMP")) && cst == cudaStreamCaptureStatusNone && !dumped) {
+            dumped = true;
+            static unsigned long long h[1024 * 8];
+            unsigned n = 0;
+            cudaDeviceSynchronize();
+            cudaMemcpyFromSymbol(h, g_ts_dbg, sizeof(h));
+            cudaMemcpyFromSymbol(&n, g_ts_dbg_n, sizeof(n));
+            const unsigned first = n > 160 ? n - 160 : 0;
+            unsigned long long prev_end = 0;
+            for (unsigned i = first; i < n; i++) {
+                const unsigned long long * r = h + (size_t)(i % 1024) * 8;
+                fprintf(stderr, "ts %4u id %4llu  gap_from_prev_end %6lld | entry->dep %6lld | dep->first_stage %6lld | ->last_mma %6lld | ->acc %6lld | epilogue %6lld | total %6lld ns\n",
+                        i, r[6], prev_end ? (long long)(r[0] - prev_end) : 0LL, (long long)(r[1] - r[0]), (long long)(r[2] - r[1]), (long long)(r[3] - r[2]),
+                        (long long)(r[4] - r[3]), (long long)(r[5] - r[4]), (long long)(r[5] - r[0]));
+                prev_end = r[5];
+            }
+        }
+    }
     e.ln_stats = a.ln_fold_stats; e.ln_slices = a.ln_fold_slices; e.ln_csum = a.ln_fold_csum; e.eps = a.eps; e.K = a.W.K;
     const int KT = a.W.K / 64;
     const bf * W = (const bf *)a.W.tiles;

@@ -175,6 +175,7 @@ struct AttnParams {
     // paged K / V (decoder self-attention cache): key j of utterance u lives in row page_table[u * max_pages + j / 128] * 128 + j % 128
     // of the layer's page pool; null = contiguous rows u * rows_per_utt + j (cross-attention K / V, encoder scratch)
     const int32_t * page_table; int max_pages;
+    int dbg;
 };
 constexpr int kPageShift = 7, kPageRows = 1 << kPageShift;     // = kKvPageRows (kernels.cuh)
 
@@ -199,8 +200,13 @@ __device__ __forceinline__ void attn_dsmem_store(float * local, unsigned rank, f
 }
 constexpr int kAttnMaxSplit = 8;
 
+// MGB_ATTN_DBG: globaltimer stamps of CTA (0, 0, 0) of every pdl launch (entry | dependency wait over | q loaded | key scan done |
+// warps merged | output stored), a ring of 1024 launches; dumped at the MGB_ATTN_DBG_DUMP-th launch_attention call (tools/ts_timeline.py)
+__device__ unsigned long long g_attn_dbg[1024 * 8];
+__device__ unsigned g_attn_dbg_n;
+
 template <typename T, int DH, int SPLIT = 0, int NW = kAttnWarps>      // NW warps per CTA; SPLIT: 0 = one CTA per (head, token); 1 / 2 = pipelined scan + cluster key split compiled for 2 / 3 resident CTAs per SM
-__global__ void __launch_bounds__(NW * 32, SPLIT == 2 ? 3 : 0) attention_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(NW * 32, SPLIT == 2 ? (NW == 4 ? 6 : 3) : 0) attention_kernel(const AttnParams p) {
     constexpr int VEC = WT<T>::VEC;
     constexpr int LPK = DH / VEC;            // lanes per key row
     constexpr int KPI = 32 / LPK;            // keys per warp instruction
@@ -228,6 +234,10 @@ __global__ void __launch_bounds__(NW * 32, SPLIT == 2 ? 3 : 0) attention_kernel(
         const int chunk = (((nk + se - 1) / se) + 127) & ~127;
         k0 = min(nk, (int)crank * chunk); k1 = (int)crank < se ? min(nk, k0 + chunk) : k0;
     }
+    __shared__ unsigned dbg_slot;
+    const bool dbg = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0;
+    auto stamp = [&](int i) { unsigned long long tt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt)); g_attn_dbg[(size_t)dbg_slot * 8 + i] = tt; };
+    if (dbg) { dbg_slot = atomicAdd(&g_attn_dbg_n, 1u) % 1024u; stamp(0); }
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");      // the following GEMM may start prefetching its weights
     if (p.pdl) {
         // launched as a programmatic dependent of the QKV GEMM: the old keys' K / V rows do not depend on it, so they are
@@ -240,6 +250,7 @@ __global__ void __launch_bounds__(NW * 32, SPLIT == 2 ? 3 : 0) attention_kernel(
         }
         asm volatile("griddepcontrol.wait;" ::: "memory");
     }
+    if (dbg) stamp(1);
     float qv[VEC];
     {
         const float * qp = p.q + (size_t)t * p.ldq + h * DH + sub * VEC;
@@ -248,6 +259,7 @@ __global__ void __launch_bounds__(NW * 32, SPLIT == 2 ? 3 : 0) attention_kernel(
     }
     const T * Kb = (const T *)p.K + h * DH + sub * VEC;
     const T * Vb = (const T *)p.V + h * DH + sub * VEC;
+    if (dbg) { if (qv[0] == 123456.0f) stamp(7); stamp(2); }      // (the comparison makes the stamp wait for q)
 
     float mx = -INFINITY, l = 0.0f, acc[VEC];
 #pragma unroll
@@ -348,6 +360,7 @@ __global__ void __launch_bounds__(NW * 32, SPLIT == 2 ? 3 : 0) attention_kernel(
         }
     }
     }
+    if (dbg) { if (l == -1.0f) stamp(7); stamp(3); }
     // merge the key groups of the warp
 #pragma unroll
     for (int o = LPK; o < 32; o <<= 1) {
@@ -368,6 +381,7 @@ __global__ void __launch_bounds__(NW * 32, SPLIT == 2 ? 3 : 0) attention_kernel(
         for (int v = 0; v < VEC; v++) s_acc[warp][sub * VEC + v] = acc[v];
     }
     __syncthreads();
+    if (dbg) stamp(4);
     float M = -INFINITY, L = 0.0f, o = 0.0f;
     if (tid < DH) {
         M = s_m[0];
@@ -411,6 +425,7 @@ __global__ void __launch_bounds__(NW * 32, SPLIT == 2 ? 3 : 0) attention_kernel(
             p.out[(size_t)t * p.ldo + h * DH + tid] = y;
         }
     }
+    if (dbg) stamp(5);
 }
 
 // ---- embeddings / LayerNorm -----------------------------------------------------------------------
@@ -614,6 +629,28 @@ bool launch_attention(const AttnArgs & a, cudaStream_t stream) {
     }
     dim3 grid(a.H, a.tok.M);
     p.pdl = (a.pack_out && !f32 && a.dh == 64) ? 1 : 0;       // decoder-step chain only
+    static const bool dbg_on = getenv("MGB_ATTN_DBG") != nullptr;
+    p.dbg = dbg_on && p.pdl;
+    if (dbg_on && getenv("MGB_ATTN_DBG_DUMP")) {
+        static int calls = 0;
+        cudaStreamCaptureStatus cst = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(stream, &cst);
+        static bool dumped = false;
+        if (++calls >= atoi(getenv("MGB_ATTN_DBG_DUMP")) && cst == cudaStreamCaptureStatusNone && !dumped) {
+            dumped = true;
+            static unsigned long long h[1024 * 8];
+            unsigned n = 0;
+            cudaDeviceSynchronize();
+            cudaMemcpyFromSymbol(h, g_attn_dbg, sizeof(h));
+            cudaMemcpyFromSymbol(&n, g_attn_dbg_n, sizeof(n));
+            for (unsigned i = n > 36 ? n - 36 : 0; i < n; i++) {
+                const unsigned long long * r = h + (size_t)(i % 1024) * 8;
+                fprintf(stderr, "attn %4u  entry->dep %6lld | q loaded %6lld | key scan %6lld | merge %6lld | finish %6lld | after dep %6lld ns  (t0 %llu)\n", i,
+                        (long long)(r[1] - r[0]), (long long)(r[2] - r[1]), (long long)(r[3] - r[2]), (long long)(r[4] - r[3]), (long long)(r[5] - r[4]),
+                        (long long)(r[5] - r[1]), r[0]);
+            }
+        }
+    }
     p.split_min_keys = 256; p.pf_keys = 0;
     if (p.pdl) {
         const int S = std::max(0, std::min(a.kv_split, kAttnMaxSplit));       // 0: one-CTA kernel; >= 1: long-KV kernels, cluster of S
@@ -635,7 +672,11 @@ bool launch_attention(const AttnArgs & a, cudaStream_t stream) {
         else if (S == 1 && nw4) {
             // short KV, many (head, utterance) items: 4-warp CTAs -- 768 items fit the resident slots in about one wave instead of 2.6
             cfg.blockDim = dim3(4 * 32);
-            MGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, attention_kernel<__nv_bfloat16, 64, 1, 4>, p));
+            // ... and compiled for 6 resident CTAs per SM (<= 80 registers) when the items would otherwise need a second, partial wave
+            // (111 registers = 4 per SM = 592 slots < 768 items at 64 utterances)
+            static const bool occ6 = getenv("MGB_ATTN_NO_OCC6") == nullptr;
+            if (occ6 && a.H * a.tok.M > 592) MGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, attention_kernel<__nv_bfloat16, 64, 2, 4>, p));
+            else MGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, attention_kernel<__nv_bfloat16, 64, 1, 4>, p));
         }
         else if (S >= 1) MGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, attention_kernel<__nv_bfloat16, 64, 1>, p));
         else MGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, attention_kernel<__nv_bfloat16, 64>, p));
