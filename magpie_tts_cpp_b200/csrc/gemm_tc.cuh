@@ -130,44 +130,55 @@ __device__ __forceinline__ uint32_t mainloop(unsigned char * smem_raw, const voi
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0 && lane == 0) {
+    // both roles run their loops warp-uniformly, one elected lane issues (see umma_lo above)
+    if (warp == 0) {
+        const bool leader = elect_one();
         const unsigned char * wsrc = reinterpret_cast<const unsigned char *>(Wt) + ((size_t)nt * KT + kt_begin) * (BM * 128);
         const unsigned char * hsrc = reinterpret_cast<const unsigned char *>(Xhi) + ((size_t)mt * KT + kt_begin) * (MT * 128);
         const unsigned char * lsrc = reinterpret_cast<const unsigned char *>(Xlo) + ((size_t)mt * KT + kt_begin) * (MT * 128);
         // Programmatic dependent launch: the weight tiles do not depend on the preceding kernel (which packs the
         // activations), so the first ring-full of them is requested BEFORE waiting for that kernel to complete.
         const int npre = PDL ? (NK < S ? NK : S) : 0;
-        for (int kt = 0; kt < npre; kt++) {
-            mbar_expect_tx(&full[kt], SB);
-            bulk_g2s(tiles + kt * SB, wsrc + (size_t)kt * (BM * 128), BM * 128, &full[kt]);
-        }
+        if (leader)
+            for (int kt = 0; kt < npre; kt++) {
+                mbar_expect_tx(&full[kt], SB);
+                bulk_g2s(tiles + kt * SB, wsrc + (size_t)kt * (BM * 128), BM * 128, &full[kt]);
+            }
         if (PDL) asm volatile("griddepcontrol.wait;" ::: "memory");
         for (int kt = 0; kt < NK; kt++) {
             const int s = kt % S;
             unsigned char * st = tiles + s * SB;
-            if (kt >= npre) {
-                mbar_wait(&empty[s], ((kt / S) & 1) ^ 1);
-                mbar_expect_tx(&full[s], SB);
-                bulk_g2s(st, wsrc + (size_t)kt * (BM * 128), BM * 128, &full[s]);
+            if (kt >= npre) mbar_wait(&empty[s], ((kt / S) & 1) ^ 1);
+            if (leader) {
+                if (kt >= npre) {
+                    mbar_expect_tx(&full[s], SB);
+                    bulk_g2s(st, wsrc + (size_t)kt * (BM * 128), BM * 128, &full[s]);
+                }
+                bulk_g2s(st + BM * 128, hsrc + (size_t)kt * (MT * 128), MT * 128, &full[s]);
+                if (NB == 2) bulk_g2s(st + BM * 128 + MT * 128, lsrc + (size_t)kt * (MT * 128), MT * 128, &full[s]);
             }
-            bulk_g2s(st + BM * 128, hsrc + (size_t)kt * (MT * 128), MT * 128, &full[s]);
-            if (NB == 2) bulk_g2s(st + BM * 128 + MT * 128, lsrc + (size_t)kt * (MT * 128), MT * 128, &full[s]);
         }
-    } else if (warp == 1 && lane == 0) {
+        __syncwarp();
+    } else if (warp == 1) {
         constexpr uint32_t idesc = F16 ? umma_idesc_f16(BM, MT) : umma_idesc_bf16(BM, MT);
+        const bool leader = elect_one();
+        const uint32_t tiles_d = desc_lo(smem_u32(tiles));
         for (int kt = 0; kt < NK; kt++) {
             const int s = kt % S;
             mbar_wait(&full[s], (kt / S) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t a0 = smem_u32(tiles + s * SB), h0 = a0 + BM * 128, l0 = h0 + MT * 128;
+            const uint32_t a0 = tiles_d + (uint32_t)s * (SB >> 4), h0 = a0 + ((BM * 128) >> 4), l0 = h0 + ((MT * 128) >> 4);
+            if (leader) {
 #pragma unroll
-            for (int j = 0; j < BK / 16; j++) {      // 16 k-elements = 32 bytes inside the swizzle row
-                umma_bf16(tmem_base, umma_desc_sw128(a0 + j * 32), umma_desc_sw128(h0 + j * 32), idesc, (kt | j) != 0);
-                if (NB == 2) umma_bf16(tmem_base, umma_desc_sw128(a0 + j * 32), umma_desc_sw128(l0 + j * 32), idesc, 1u);
+                for (int j = 0; j < BK / 16; j++) {      // 16 k-elements = 32 bytes = 2 descriptor units inside the swizzle row
+                    umma_lo(tmem_base, a0 + 2 * j, h0 + 2 * j, idesc, (kt | j) != 0);
+                    if (NB == 2) umma_lo(tmem_base, a0 + 2 * j, l0 + 2 * j, idesc, 1u);
+                }
+                umma_commit(&empty[s]);                  // frees the stage when the MMAs above have read it
             }
-            umma_commit(&empty[s]);                  // frees the stage when the MMAs above have read it
         }
-        umma_commit(acc_full);                       // accumulator complete
+        if (leader) umma_commit(acc_full);               // accumulator complete
+        __syncwarp();
     }
     if (warp >= 2) {
         if (PDL) asm volatile("griddepcontrol.wait;" ::: "memory");

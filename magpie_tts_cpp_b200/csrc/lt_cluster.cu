@@ -356,6 +356,7 @@ __global__ void __launch_bounds__(kLtThreads, 1) lt_cluster_kernel(const ClParam
 
     bool hit_eos = false;
     uint32_t mma_par = 0;                                    // phase parity of the MMA-completion barrier
+    const bool leader = tc::elect_one();                     // (every warp elects; only warp 0's leader issues MMAs)
     const int wq = warp & 3, wg = warp >> 2;                 // epilogues: TMEM lane quarter of this warp; utterances wg, wg + 4, wg + 8
     static_assert(U <= 12, "epilogue utterance mapping");
     const int my_step = owner ? step_of(my_utt) : 0;
@@ -367,17 +368,21 @@ __global__ void __launch_bounds__(kLtThreads, 1) lt_cluster_kernel(const ClParam
         // ---- FF1 (this CTA's 64 hidden rows, all utterances) fused with FF2's partial sums over those 64 columns ----
         warp_ln_image<U>(S.x1, p.norm_ff, S.b_act, p.eps);
         if (cp.dbg_fine) stamp();
-        if (tid == 0) {                                      // D[64 x (16 hi | 16 lo)] = W1[64 r .., :] . LN(x1)^T
+        if (warp == 0) {                                     // D[64 x (16 hi | 16 lo)] = W1[64 r .., :] . LN(x1)^T
+            // (issued warp-uniformly by one elected lane: descriptors stay in uniform registers, gemm_tc.cuh)
             fence_async_proxy();                             // the operand rows were written through the generic proxy (this CTA's warps)
             tc_after_sync();
             constexpr uint32_t idesc = tc::umma_idesc_bf16(kF1Rows, 32);
-            const uint32_t a0 = smem_u32(S.w_ff1), b0 = smem_u32(&S.b_act[0][0][0]);
+            const uint32_t a0 = tc::desc_lo(smem_u32(S.w_ff1)), b0 = tc::desc_lo(smem_u32(&S.b_act[0][0][0]));
+            if (leader) {
 #pragma unroll
-            for (int kt = 0; kt < kL / 64; kt++)
+                for (int kt = 0; kt < kL / 64; kt++)
 #pragma unroll
-                for (int j = 0; j < 4; j++)
-                    tc::umma_bf16(tmem, tc::umma_desc_sw128(a0 + kt * (kF1Rows * 128) + j * 32), tc::umma_desc_sw128(b0 + kt * 2 * kBTile + j * 32), idesc, (kt | j) != 0);
-            tc::umma_commit(&S.mbar[3]);
+                    for (int j = 0; j < 4; j++)
+                        tc::umma_lo(tmem, a0 + (uint32_t)(kt * (kF1Rows * 128) + j * 32) / 16, b0 + (uint32_t)(kt * 2 * kBTile + j * 32) / 16, idesc, (kt | j) != 0);
+                tc::umma_commit(&S.mbar[3]);
+            }
+            __syncwarp();
         }
         mbar_wait(&S.mbar[3], mma_par); mma_par ^= 1u;
         tc_after_sync();
@@ -411,17 +416,20 @@ __global__ void __launch_bounds__(kLtThreads, 1) lt_cluster_kernel(const ClParam
         tc_before_sync();
         __syncthreads();
         if (cp.dbg_fine) stamp();
-        if (tid == 0) {                                      // partial[n][u] = sum_{k < 64} W2[n][64 r + k] ffh[u][k]: two 128-row tiles
+        if (warp == 0) {                                     // partial[n][u] = sum_{k < 64} W2[n][64 r + k] ffh[u][k]: two 128-row tiles
             fence_async_proxy();
             tc_after_sync();
             constexpr uint32_t idesc = tc::umma_idesc_bf16(128, 32);
-            const uint32_t a0 = smem_u32(S.w_ff2), b0 = smem_u32(&S.b_ffh[0][0]);
+            const uint32_t a0 = tc::desc_lo(smem_u32(S.w_ff2)), b0 = tc::desc_lo(smem_u32(&S.b_ffh[0][0]));
+            if (leader) {
 #pragma unroll
-            for (int t = 0; t < 2; t++)
+                for (int t = 0; t < 2; t++)
 #pragma unroll
-                for (int j = 0; j < 4; j++)
-                    tc::umma_bf16(tmem + 32 + 32 * t, tc::umma_desc_sw128(a0 + t * kTile128 + j * 32), tc::umma_desc_sw128(b0 + j * 32), idesc, j != 0);
-            tc::umma_commit(&S.mbar[3]);
+                    for (int j = 0; j < 4; j++)
+                        tc::umma_lo(tmem + 32 + 32 * t, a0 + (uint32_t)(t * kTile128 + j * 32) / 16, b0 + (uint32_t)(j * 32) / 16, idesc, j != 0);
+                tc::umma_commit(&S.mbar[3]);
+            }
+            __syncwarp();
         }
         mbar_wait(&S.mbar[3], mma_par); mma_par ^= 1u;
         tc_after_sync();
@@ -482,18 +490,21 @@ __global__ void __launch_bounds__(kLtThreads, 1) lt_cluster_kernel(const ClParam
         stamp(); cluster_sync_all(); stamp();
         // ---- out-projection of codebook cb (+bias): 128 rows x U utterances -> the utterance's owner CTA (magpie.cpp:1037-1048) ----
         if (has_out) {                                       // (CTA-uniform)
-            if (tid == 0) {
+            if (warp == 0) {
                 mbar_wait(&S.mbar[1], (uint32_t)(cb & 1));
                 fence_async_proxy();
                 tc_after_sync();
                 constexpr uint32_t idesc = tc::umma_idesc_bf16(128, 32);
-                const uint32_t a0 = smem_u32(S.w_out), b0 = smem_u32(&S.b_act[0][0][0]);
+                const uint32_t a0 = tc::desc_lo(smem_u32(S.w_out)), b0 = tc::desc_lo(smem_u32(&S.b_act[0][0][0]));
+                if (leader) {
 #pragma unroll
-                for (int kt = 0; kt < kL / 64; kt++)
+                    for (int kt = 0; kt < kL / 64; kt++)
 #pragma unroll
-                    for (int j = 0; j < 4; j++)
-                        tc::umma_bf16(tmem + 96, tc::umma_desc_sw128(a0 + kt * kTile128 + j * 32), tc::umma_desc_sw128(b0 + kt * 2 * kBTile + j * 32), idesc, (kt | j) != 0);
-                tc::umma_commit(&S.mbar[3]);
+                        for (int j = 0; j < 4; j++)
+                            tc::umma_lo(tmem + 96, a0 + (uint32_t)(kt * kTile128 + j * 32) / 16, b0 + (uint32_t)(kt * 2 * kBTile + j * 32) / 16, idesc, (kt | j) != 0);
+                    tc::umma_commit(&S.mbar[3]);
+                }
+                __syncwarp();
             }
             mbar_wait(&S.mbar[3], mma_par); mma_par ^= 1u;
             tc_after_sync();
@@ -513,7 +524,7 @@ __global__ void __launch_bounds__(kLtThreads, 1) lt_cluster_kernel(const ClParam
                 for (int j = 0; j < 3; j++) { const int u = wg + 4 * j; if (u < U) dsmem_st(&S.logits[id], u, (v[j] + vl[j]) + bias); }
             }
             tc_before_sync();
-        } else if (tid == 0) mbar_wait(&S.mbar[1], (uint32_t)(cb & 1));
+        } else if (warp == 0) mbar_wait(&S.mbar[1], (uint32_t)(cb & 1));
         __syncthreads();                                     // the MMAs have consumed w_out: prefetch the next codebook's tiles
         if (tid == 0 && cb < 7) {
             mbar_expect_tx(&S.mbar[1], has_out ? 4u * kTile128 : 0u);
