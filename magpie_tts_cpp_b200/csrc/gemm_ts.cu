@@ -22,7 +22,7 @@ namespace {
 
 using bf = __nv_bfloat16;
 
-constexpr int kTsThreads = 192;          // warp 0 producer, warp 1 TMEM + MMA issue, warps 2..5 epilogue
+constexpr int kTsThreads = 320;          // warp 0 producer, warp 1 TMEM + MMA issue, warps 2..9 epilogue
 constexpr int kXTile = 64 * 128;         // one 64-token x 64-k bf16 image
 
 // MGB_TS_DBG: globaltimer stamps of CTA (0, 0) of every launch (entry | dependency wait over | first stage landed | last MMA issued |
@@ -80,6 +80,12 @@ __global__ void __launch_bounds__(kTsThreads, 1) ts_linear_kernel(const bf * Wt,
     uint64_t * full = bars, * empty = bars + kTsStages, * acc_full = bars + 2 * kTsStages;
     uint32_t * tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kTsStages + 1);
     const int n0 = blockIdx.x * NC;                                      // first output feature of this CTA
+    // epilogue: two warps per TMEM lane quarter, each takes half of the CTA's columns (NC >= 16; with M = 64 only lanes 0..15 of a
+    // warp hold rows, so the epilogues -- GELU + packing of up to 32 columns per row -- were serial tails of 3.5-4.2 us on 64 threads)
+    constexpr int NH = NC >= 16 ? NC / 2 : NC;
+    const int half = warp >= 6 ? 1 : 0;
+    const bool epi_on = NC >= 16 || half == 0;
+    const int c0 = NC >= 16 ? half * NH : 0, nb = n0 + c0;
     __shared__ unsigned dbg_slot;
     const bool dbg = e.dbg && blockIdx.x == 0 && blockIdx.y == 0;
     auto stamp = [&](int i) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); g_ts_dbg[(size_t)dbg_slot * 8 + i] = t; };
@@ -166,15 +172,15 @@ __global__ void __launch_bounds__(kTsThreads, 1) ts_linear_kernel(const bf * Wt,
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int q = warp & 3;                      // TMEM lane quarter of this warp; M = 64: rows 16 q .. 16 q + 15 on its lanes 0..15
         const int m = 16 * q + lane;
-        if (SPLIT > 1 && rank > 0) {
-            uint32_t v[NC];
-            tmem_ld_cols<NC>(tmem_base + ((uint32_t)(q * 32) << 16), v);
+        if (SPLIT > 1 && rank > 0 && epi_on) {
+            uint32_t v[NH];
+            tmem_ld_cols<NH>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
             if (lane < 16) {
-                const uint32_t local = tc::smem_u32(xbuf + ((size_t)(rank - 1) * 64 + m) * NC);
+                const uint32_t local = tc::smem_u32(xbuf + ((size_t)(rank - 1) * 64 + m) * NC + c0);
                 uint32_t remote;
                 asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(0));
 #pragma unroll
-                for (int j = 0; j < NC / 4; j++)
+                for (int j = 0; j < NH / 4; j++)
                     asm volatile("st.shared::cluster.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(remote + j * 16), "r"(v[4 * j]), "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3]) : "memory");
             }
             __syncwarp();
@@ -184,26 +190,27 @@ __global__ void __launch_bounds__(kTsThreads, 1) ts_linear_kernel(const bf * Wt,
         __syncwarp();                                // (the producer / MMA lanes rejoin their warps before the aligned barrier)
         asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
     }
-    if (warp >= 2 && rank == 0) {
+    if (warp >= 2 && rank == 0 && epi_on) {
         const int q = warp & 3;
         const int m = 16 * q + lane;
-        uint32_t v[NC];
-        tmem_ld_cols<NC>(tmem_base + ((uint32_t)(q * 32) << 16), v);
-        if (lane < 16 && m < e.M && n0 < e.N) {
-            float y[NC];
+        uint32_t v[NH];
+        tmem_ld_cols<NH>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+        if (lane < 16 && m < e.M && nb < e.N) {
+            float y[NH];
 #pragma unroll
-            for (int j = 0; j < NC; j++) y[j] = __uint_as_float(v[j]);
+            for (int j = 0; j < NH; j++) y[j] = __uint_as_float(v[j]);
             if (SPLIT > 1) {
 #pragma unroll
                 for (int r = 0; r < SPLIT - 1; r++) {
-                    const float4 * pr = reinterpret_cast<const float4 *>(xbuf + ((size_t)r * 64 + m) * NC);
+                    const float4 * pr = reinterpret_cast<const float4 *>(xbuf + ((size_t)r * 64 + m) * NC + c0);
 #pragma unroll
-                    for (int j = 0; j < NC / 4; j++) { const float4 t = pr[j]; y[4 * j] += t.x; y[4 * j + 1] += t.y; y[4 * j + 2] += t.z; y[4 * j + 3] += t.w; }
+                    for (int j = 0; j < NH / 4; j++) { const float4 t = pr[j]; y[4 * j] += t.x; y[4 * j + 1] += t.y; y[4 * j + 2] += t.z; y[4 * j + 3] += t.w; }
                 }
             }
             if (EPI == TS_QKV) {
                 if (e.ln_stats) {                    // LayerNorm folded through this GEMM: y = (acc - mean * csum[n]) * rstd
                     float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll 8
                     for (int sl = 0; sl < e.ln_slices; sl++) {
                         const float2 st = *reinterpret_cast<const float2 *>(e.ln_stats + ((size_t)sl * 64 + m) * 2);
                         s1 += st.x; s2 += st.y;
@@ -211,17 +218,17 @@ __global__ void __launch_bounds__(kTsThreads, 1) ts_linear_kernel(const bf * Wt,
                     const float mean = s1 / (float)e.K, var = fmaxf(s2 / (float)e.K - mean * mean, 0.0f);
                     const float rstd = 1.0f / sqrtf(var + e.eps);
 #pragma unroll
-                    for (int j = 0; j < NC; j++) y[j] = (y[j] - mean * e.ln_csum[n0 + j]) * rstd;
+                    for (int j = 0; j < NH; j++) y[j] = (y[j] - mean * e.ln_csum[nb + j]) * rstd;
                 }
-                if (n0 < e.n_q) {
-                    float4 * dst = reinterpret_cast<float4 *>(e.Y + (size_t)m * e.ldy + n0);
+                if (nb < e.n_q) {
+                    float4 * dst = reinterpret_cast<float4 *>(e.Y + (size_t)m * e.ldy + nb);
 #pragma unroll
-                    for (int j = 0; j < NC / 4; j++) dst[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+                    for (int j = 0; j < NH / 4; j++) dst[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
                 } else {
-                    const int cc = n0 - e.n_q;
+                    const int cc = nb - e.n_q;
                     bf * dst = (cc < e.dkv ? e.kdst + cc : e.vdst + (cc - e.dkv)) + (size_t)e.tok_slot[m] * e.dkv;
 #pragma unroll
-                    for (int j = 0; j < NC / 8; j++) {
+                    for (int j = 0; j < NH / 8; j++) {
                         uint32_t w[4];
 #pragma unroll
                         for (int p = 0; p < 4; p++)
@@ -231,33 +238,33 @@ __global__ void __launch_bounds__(kTsThreads, 1) ts_linear_kernel(const bf * Wt,
                     }
                 }
             } else if (EPI == TS_RES) {
-                const float4 * rs = reinterpret_cast<const float4 *>(e.res + (size_t)m * e.ldr + n0);
-                float4 r[NC / 4];
+                const float4 * rs = reinterpret_cast<const float4 *>(e.res + (size_t)m * e.ldr + nb);
+                float4 r[NH / 4];
 #pragma unroll
-                for (int j = 0; j < NC / 4; j++) r[j] = rs[j];
-                float4 * dst = reinterpret_cast<float4 *>(e.Y + (size_t)m * e.ldy + n0);
+                for (int j = 0; j < NH / 4; j++) r[j] = rs[j];
+                float4 * dst = reinterpret_cast<float4 *>(e.Y + (size_t)m * e.ldy + nb);
 #pragma unroll
-                for (int j = 0; j < NC / 4; j++) {
+                for (int j = 0; j < NH / 4; j++) {
                     y[4 * j] += r[j].x; y[4 * j + 1] += r[j].y; y[4 * j + 2] += r[j].z; y[4 * j + 3] += r[j].w;
                     dst[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
                 }
                 if (e.next_w) {                      // the next GEMM's operand: (y .* w) as hi | lo images + this slice's row statistics
                     float s1 = 0.0f, s2 = 0.0f;
 #pragma unroll
-                    for (int j = 0; j < NC; j++) { s1 += y[j]; s2 = fmaf(y[j], y[j], s2); }
-                    *reinterpret_cast<float2 *>(e.stats_out + ((size_t)blockIdx.x * 64 + m) * 2) = make_float2(s1, s2);
+                    for (int j = 0; j < NH; j++) { s1 += y[j]; s2 = fmaf(y[j], y[j], s2); }
+                    *reinterpret_cast<float2 *>(e.stats_out + ((size_t)(blockIdx.x * (NC / NH) + half) * 64 + m) * 2) = make_float2(s1, s2);
 #pragma unroll
-                    for (int j = 0; j < NC / 8; j++) {
+                    for (int j = 0; j < NH / 8; j++) {
                         uint32_t h[4], l[4];
 #pragma unroll
                         for (int p = 0; p < 4; p++) {
-                            const float a = y[8 * j + 2 * p] * e.next_w[n0 + 8 * j + 2 * p], b = y[8 * j + 2 * p + 1] * e.next_w[n0 + 8 * j + 2 * p + 1];
+                            const float a = y[8 * j + 2 * p] * e.next_w[nb + 8 * j + 2 * p], b = y[8 * j + 2 * p + 1] * e.next_w[nb + 8 * j + 2 * p + 1];
                             const bf ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
                             const bf la = __float2bfloat16_rn(a - __bfloat162float(ha)), lb = __float2bfloat16_rn(b - __bfloat162float(hb));
                             h[p] = (uint32_t)__bfloat16_as_ushort(ha) | ((uint32_t)__bfloat16_as_ushort(hb) << 16);
                             l[p] = (uint32_t)__bfloat16_as_ushort(la) | ((uint32_t)__bfloat16_as_ushort(lb) << 16);
                         }
-                        const int n = n0 + 8 * j;
+                        const int n = nb + 8 * j;
                         const size_t off = (size_t)(n >> 6) * kXTile + tc::swz_offset(m, n & 63);
                         *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(e.pk_hi) + off) = make_uint4(h[0], h[1], h[2], h[3]);
                         *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(e.pk_lo) + off) = make_uint4(l[0], l[1], l[2], l[3]);
@@ -265,7 +272,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) ts_linear_kernel(const bf * Wt,
                 }
             } else {                                 // GELU + hi | lo tile images for the next GEMM (k tile n / 64, 16-byte chunk (n % 64) / 8)
 #pragma unroll
-                for (int j = 0; j < NC / 8; j++) {
+                for (int j = 0; j < NH / 8; j++) {
                     uint32_t h[4], l[4];
 #pragma unroll
                     for (int p = 0; p < 4; p++) {
@@ -275,7 +282,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) ts_linear_kernel(const bf * Wt,
                         h[p] = (uint32_t)__bfloat16_as_ushort(ha) | ((uint32_t)__bfloat16_as_ushort(hb) << 16);
                         l[p] = (uint32_t)__bfloat16_as_ushort(la) | ((uint32_t)__bfloat16_as_ushort(lb) << 16);
                     }
-                    const int n = n0 + 8 * j;
+                    const int n = nb + 8 * j;
                     const size_t off = (size_t)(n >> 6) * kXTile + tc::swz_offset(m, n & 63);
                     *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(e.pk_hi) + off) = make_uint4(h[0], h[1], h[2], h[3]);
                     *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(e.pk_lo) + off) = make_uint4(l[0], l[1], l[2], l[3]);
@@ -323,8 +330,8 @@ static int ts_shape() {
 // columns per CTA of the residual-epilogue GEMM (mirrors the dispatch in launch_linear_ts below)
 int ts_resid_nc(int K) {
     const int KT = K / 64, shaped = ts_shape();
-    if (shaped && KT >= 32 && KT % 4 == 0) return 32;
-    if (shaped == 2 && KT % 4 == 0) return 32;
+    if (shaped && KT >= 32 && KT % 4 == 0) return 16;     // (32-column CTAs, two epilogue warps of 16 columns each per row)
+    if (shaped == 2 && KT % 4 == 0) return 16;
     return 8;
 }
 
