@@ -68,7 +68,7 @@ struct Session {
     unsigned long long * d_loop_dbg = nullptr;
     void * tc_scratch = nullptr; size_t tc_scratch_bytes = 0;     // tensor-core path: activation tile images
     void * tc_scratch2 = nullptr;                                  // second image buffer (FF1 epilogue -> FF2 input)
-    float * ln_stats = nullptr; bool ln_fold = false;              // LayerNorm folded through the QKV GEMM: row statistics [<= 96 slices][64][2] (kernels.cuh)
+    float * ln_stats = nullptr; bool ln_fold = false, act_f16 = false;              // LayerNorm folded through the QKV GEMM: row statistics [<= 96 slices][64][2] (kernels.cuh)
     void * lt_scratch = nullptr; size_t lt_scratch_bytes = 0;     // batched local transformer: activation scratch
     int prefill_len = 0;                                            // > 0 while mgb_prefill runs decoder_layers on the context frames
     float * fold_xm = nullptr, * fold_xn = nullptr; bool fold_ready = false;     // batched decode: folded cross-attention tables [L][B][max_text][d]
@@ -160,6 +160,9 @@ static bool decoder_layers(Session & s, Tokens tok, bool want_hidden) {
     const int d = hp.d_model, dxa = hp.dec_xa_heads * hp.dec_xa_d_head, M = tok.M;
     const size_t kv_layer = s.kv_rows * d * m.wsize, xkv_layer = (size_t)s.B * s.max_text * dxa * m.wsize;
     bool ln_folded = false;              // the previous layer's FF2 has written this layer's QKV operand (x .* norm_self) + row statistics
+    // f16 activation images through the whole chain of a batched step (gemm_tc.cuh pack_act2): every producer / consumer pair below agrees
+    const bool f16a = s.act_f16 && M == s.B && tok.utt == s.dec_utt && M <= 64 && M >= 4 && s.tc_scratch2 && s.fold_ready && m.precision == MGB_PREC_BF16 &&
+                      hp.d_ffn % 64 == 0 && d / hp.dec_sa_heads == 64 && getenv("MGB_NO_CHAIN") == nullptr && getenv("MGB_NO_TS") == nullptr && !skip;
     for (int l = 0; l < hp.dec_layers; l++) {
         const DecLayer & L = m.dec[l];
         char * kl = (char *)s.kc + l * kv_layer, * vl = (char *)s.vc + l * kv_layer;
@@ -169,6 +172,7 @@ static bool decoder_layers(Session & s, Tokens tok, bool want_hidden) {
         // self-attention: LN -> QKV (K,V written straight into the cache) -> attention -> O + residual
         a.W = L.qkv; a.X = s.x; a.ldx = d; a.ln_w = L.norm_self; a.Y = s.qbuf; a.ldy = d;
         a.n_q = d; a.dkv = d; a.kdst = kl; a.vdst = vl; a.tok_slot = tok.slot;
+        a.act_f16 = f16a; 
         if (ln_folded) {
             a.x_prepacked = true; a.ln_fold_stats = s.ln_stats; a.ln_fold_slices = d / ts_resid_nc(hp.d_ffn); a.ln_fold_csum = L.qkv_csum;
         }
@@ -184,6 +188,7 @@ static bool decoder_layers(Session & s, Tokens tok, bool want_hidden) {
         // batched decoder step on the tensor-core path: the attention kernel writes the O-projection's packed input itself
         if (M == s.B && tok.utt == s.dec_utt && M <= 64 && at.dh == 64 && tc_linear_supported(o) && getenv("MGB_NO_CHAIN") == nullptr) {
             at.pack_out = s.tc_scratch; o.x_prepacked = true; at.kv_split = s.attn_split;
+            at.pack_f16 = f16a; o.act_f16 = f16a;
         }
         if (!(skip & 2) && !launch_attention(at, s.stream)) return false;
         if (!(skip & 8) && !launch_linear(o, s.stream)) return false;
@@ -205,8 +210,8 @@ static bool decoder_layers(Session & s, Tokens tok, bool want_hidden) {
             const size_t tab = (size_t)s.B * s.max_text * d;
             const bool pk = chain;
             if (!(skip & 1) && !launch_xattn_folded(s.x, L.norm_xa_q, hp.eps, s.fold_xm + l * tab, s.fold_xn + l * tab, s.d_ntext, s.B, d, s.max_text,
-                                                    pk ? L.norm_ff : nullptr, pk ? s.tc_scratch : nullptr, s.stream)) return false;
-            if (pk) f1.x_prepacked = true;
+                                                    pk ? L.norm_ff : nullptr, pk ? s.tc_scratch : nullptr, s.stream, pk && f16a)) return false;
+            if (pk) { f1.x_prepacked = true; f1.act_f16 = f16a; }
         } else {
         LinearArgs q;
         q.tc_scratch = s.tc_scratch; q.tc_scratch_bytes = s.tc_scratch_bytes;
@@ -223,13 +228,14 @@ static bool decoder_layers(Session & s, Tokens tok, bool want_hidden) {
         if (!launch_linear(xo, s.stream)) return false;
         }
         // conv-FFN (kernel 1): LN -> W1 -> GELU -> W2 + residual
-        if (chain) { f1.pack_out = s.tc_scratch2; f1.Y = nullptr; f2.tc_scratch = s.tc_scratch2; f2.x_prepacked = true; }
+        if (chain) { f1.pack_out = s.tc_scratch2; f1.Y = nullptr; f2.tc_scratch = s.tc_scratch2; f2.x_prepacked = true; f1.pack_f16 = f16a; f2.act_f16 = f16a; }
+        else if (f16a) { set_error("decoder step: f16 activation images need the chained tensor-core path"); return false; }
         // ... and FF2's epilogue emits the NEXT layer's QKV operand with the LayerNorm folded through that GEMM (kernels.cuh)
         ln_folded = false;
         if (chain && !skip && s.ln_stats && l + 1 < hp.dec_layers && m.dec[l + 1].qkv_csum && s.ln_fold) {
-            f2.pack_out = s.tc_scratch; f2.next_ln_w = m.dec[l + 1].norm_self; f2.stats_out = s.ln_stats;
+            f2.pack_out = s.tc_scratch; f2.next_ln_w = m.dec[l + 1].norm_self; f2.stats_out = s.ln_stats; f2.pack_f16 = f16a;
             if (ts_linear_supported(f2)) ln_folded = true;
-            else { f2.pack_out = nullptr; f2.next_ln_w = nullptr; f2.stats_out = nullptr; }
+            else { f2.pack_out = nullptr; f2.next_ln_w = nullptr; f2.stats_out = nullptr; f2.pack_f16 = false; }
         }
         if (!(skip & 16) && !launch_linear(f1, s.stream)) return false;
         if (!(skip & 32) && !launch_linear(f2, s.stream)) return false;
@@ -419,6 +425,7 @@ mgb_session * mgb_session_new_paged(mgb_model * mm, int batch, int max_text, int
         s->tc_scratch2 = tp2;
         if (!s->alloc(s->ln_stats, (size_t)96 * 64 * 2)) return nullptr;
         s->ln_fold = getenv("MGB_NO_LNFOLD") == nullptr;
+        s->act_f16 = m->dec[0].qkv.tiles16 != nullptr;             // (MGB_ACT_F16 at model load)
     }
     // (launch_xattn_folded holds one score per text position in shared memory: up to 512 positions; longer text capacities keep
     //  the q GEMM + attention + o GEMM kernels)

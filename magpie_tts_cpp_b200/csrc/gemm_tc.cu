@@ -5,6 +5,7 @@
 // (reference: ggml_mul_mat call sites src/magpie.cpp:3415, 3464-3479, 1733, 1764, 1796, 1805).
 #include <cstdlib>
 
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "gemm_tc.cuh"
 #include "kernels.cuh"
@@ -17,7 +18,7 @@ using bf = __nv_bfloat16;
 
 // row-major bf16 [N][K] -> [ceil(N/128)][K/64] tiles of 128 x 64 in the SWIZZLE_128B K-major image; one thread per 16 bytes
 // taps > 1 (causal conv weights stored tap-major [taps][N][K]): the taps are concatenated along k, k' = tap * K + k
-__global__ void pack_w_kernel(const bf * W, int N, int Ktap, int taps, bf * Wt) {
+__global__ void pack_w_kernel(const bf * W, int N, int Ktap, int taps, bf * Wt, int as_f16) {
     const int K = Ktap * taps;
     const int KT = K / 64, NT = (N + tc::BM - 1) / tc::BM;
     const size_t total = (size_t)NT * tc::BM * (K / 8);
@@ -26,6 +27,15 @@ __global__ void pack_w_kernel(const bf * W, int N, int Ktap, int taps, bf * Wt) 
         uint4 v = make_uint4(0u, 0u, 0u, 0u);
         const int tap = (kc * 8) / Ktap, kk = kc * 8 - tap * Ktap;
         if (r < N) v = *reinterpret_cast<const uint4 *>(W + ((size_t)tap * N + r) * Ktap + kk);
+        if (as_f16) {                               // bf16 -> f16: exact for normal f16 magnitudes (8 mantissa bits fit into 11)
+            uint32_t * w = reinterpret_cast<uint32_t *>(&v);
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const float lo = __uint_as_float(w[q] << 16), hi = __uint_as_float(w[q] & 0xffff0000u);
+                const __half2 h = __floats2half2_rn(lo, hi);
+                w[q] = *reinterpret_cast<const uint32_t *>(&h);
+            }
+        }
         const size_t tile = (size_t)(r / tc::BM) * KT + kc / 8;
         unsigned char * dst = reinterpret_cast<unsigned char *>(Wt) + tile * (tc::BM * 128) + tc::swz_offset(r % tc::BM, (kc % 8) * 8);
         *reinterpret_cast<uint4 *>(dst) = v;
@@ -37,7 +47,7 @@ __global__ void pack_w_kernel(const bf * W, int N, int Ktap, int taps, bf * Wt) 
 // taps > 1: row m of the packed operand is [x(m - (taps-1)) | ... | x(m)] (each LayerNorm'd on its own), a shifted row being
 // zero when it would cross the start of the utterance (tok_pos[m] < shift): the k = 3 causal conv as ONE GEMM over 3 K.
 __global__ void __launch_bounds__(256) pack_x_kernel(const float * X, int ldx, int M, int K, const float * ln_w, float eps, int MT,
-                                                     bf * hi, bf * lo, int taps, const int32_t * tok_pos) {
+                                                     bf * hi, bf * lo, int taps, const int32_t * tok_pos, int f16) {
     __shared__ float red[32];
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");     // let the GEMM's CTAs start prefetching weights
     asm volatile("griddepcontrol.wait;" ::: "memory");                  // (itself launched as a programmatic dependent of the previous kernel)
@@ -73,16 +83,11 @@ __global__ void __launch_bounds__(256) pack_x_kernel(const float * X, int ldx, i
             }
             uint32_t h[4], l[4];
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const bf h0 = __float2bfloat16_rn(v[2 * q]), h1 = __float2bfloat16_rn(v[2 * q + 1]);
-                const bf l0 = __float2bfloat16_rn(v[2 * q] - __bfloat162float(h0)), l1 = __float2bfloat16_rn(v[2 * q + 1] - __bfloat162float(h1));
-                h[q] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                l[q] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-            }
+            for (int q = 0; q < 4; q++) tc::pack_act2(v[2 * q], v[2 * q + 1], f16 != 0, h[q], l[q]);
             const int kg = tap * (K / 8) + kc;                       // 8-column group of the concatenated row
             const size_t off = (tile_row + kg / 8) * ((size_t)MT * 128) + tc::swz_offset(m % MT, (kg % 8) * 8);
             *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(hi) + off) = make_uint4(h[0], h[1], h[2], h[3]);
-            *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(lo) + off) = make_uint4(l[0], l[1], l[2], l[3]);
+            if (!f16) *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(lo) + off) = make_uint4(l[0], l[1], l[2], l[3]);
         }
     }
 }
@@ -228,8 +233,8 @@ template <int MT, int SPLIT, int EPI> bool launch_tc(const bf * Wt, const bf * h
 
 size_t tc_weight_tile_bytes(int N, int K) { return (size_t)((N + tc::BM - 1) / tc::BM) * tc::BM * K * sizeof(bf); }      // K = taps * K_tap
 
-bool tc_pack_weights(const void * W, int N, int K, void * Wt, cudaStream_t stream, int taps) {
-    pack_w_kernel<<<592, 256, 0, stream>>>((const bf *)W, N, K, taps, (bf *)Wt);
+bool tc_pack_weights(const void * W, int N, int K, void * Wt, cudaStream_t stream, int taps, bool as_f16) {
+    pack_w_kernel<<<592, 256, 0, stream>>>((const bf *)W, N, K, taps, (bf *)Wt, as_f16 ? 1 : 0);
     MGB_LAUNCH_CHECK();
     return true;
 }
@@ -258,7 +263,7 @@ bool launch_linear_tc(const LinearArgs & a, cudaStream_t stream) {
         pa[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         pa[0].val.programmaticStreamSerializationAllowed = 1;
         pc.attrs = pa; pc.numAttrs = 1;
-        MGB_CUDA_TRY(cudaLaunchKernelEx(&pc, pack_x_kernel, a.X, a.ldx, M, Ktap, a.ln_w, a.eps, MT, hi, lo, taps, a.tok_pos));
+        MGB_CUDA_TRY(cudaLaunchKernelEx(&pc, pack_x_kernel, a.X, a.ldx, M, Ktap, a.ln_w, a.eps, MT, hi, lo, taps, a.tok_pos, a.act_f16 ? 1 : 0));
         MGB_LAUNCH_CHECK();
     }
     TcEpi e;
@@ -270,7 +275,7 @@ bool launch_linear_tc(const LinearArgs & a, cudaStream_t stream) {
     e.N = a.W.N; e.M = M; e.bias = a.bias; e.res = a.res; e.ldr = a.ldr; e.Y = a.Y; e.ldy = a.ldy; e.act = a.act; e.gelu_f16 = a.gelu_f16;
     e.n_q = a.n_q; e.dkv = a.dkv; e.kdst = (bf *)a.kdst; e.vdst = (bf *)a.vdst; e.tok_slot = a.tok_slot;
     if (MT == 64 && ts_linear_supported(a)) return launch_linear_ts(a, hi, lo, stream);      // decoder-step GEMMs: token-stationary kernel (gemm_ts.cu)
-    if (a.ln_fold_stats || a.next_ln_w) { set_error("linear: a folded LayerNorm needs the token-stationary GEMM (gemm_ts.cu)"); return false; }
+    if (a.ln_fold_stats || a.next_ln_w || a.act_f16 || a.pack_f16) { set_error("linear: a folded LayerNorm / f16 activation images need the token-stationary GEMM (gemm_ts.cu)"); return false; }
     if (MT == 64) {
         // one token tile: split K over a cluster (deterministic DSMEM reduction) to shorten the per-SM ingest chain
         const int KT = K / 64;

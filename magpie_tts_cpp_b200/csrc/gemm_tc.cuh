@@ -13,6 +13,7 @@
 // tcgen05.commit releases a stage / publishes the accumulator.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <cstdint>
 
@@ -44,6 +45,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t * bar, uint32_t parity) {
 __device__ __forceinline__ void bulk_g2s(void * dst, const void * src, uint32_t bytes, uint64_t * bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// Two f32 activations -> one 32-bit word of an operand image.  Default: bf16 hi word + bf16 lo word (x = hi + lo to 2^-17, two MMAs per
+// k slice).  f16 = true (MGB_ACT_F16, batched decoder step): ONE f16 image (11-bit mantissa: the rounding ggml's CPU path applies to the
+// activations of f16-weight matmuls; 1/8 of the bf16 weights' own rounding step), half the operand bytes every CTA of a GEMM pulls from
+// L2; values are clamped to the f16 range.  tcgen05 kind::f16 does NOT mix an f16 A with a bf16 B (illegal instruction on sm_100a), so
+// the weights get an f16 twin of their images (model.cu: bf16 -> f16 is exact for |w| >= 6.1e-5, absolute error <= 3e-8 below).
+__device__ __forceinline__ void pack_act2(float a, float b, bool f16, uint32_t & h, uint32_t & l) {
+    if (f16) {
+        const __half2 v = __floats2half2_rn(fminf(fmaxf(a, -65504.0f), 65504.0f), fminf(fmaxf(b, -65504.0f), 65504.0f));
+        h = *reinterpret_cast<const uint32_t *>(&v); l = 0u;
+    } else {
+        const __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
+        const __nv_bfloat16 la = __float2bfloat16_rn(a - __bfloat162float(ha)), lb = __float2bfloat16_rn(b - __bfloat162float(hb));
+        h = (uint32_t)__bfloat16_as_ushort(ha) | ((uint32_t)__bfloat16_as_ushort(hb) << 16);
+        l = (uint32_t)__bfloat16_as_ushort(la) | ((uint32_t)__bfloat16_as_ushort(lb) << 16);
+    }
 }
 
 // shared-memory matrix descriptor, K-major, SWIZZLE_128B: start address (>>4), LBO = 1 (unused for swizzled K-major),

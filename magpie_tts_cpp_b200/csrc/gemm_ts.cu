@@ -38,6 +38,7 @@ struct TsEpi {
     int n_q, dkv; bf * kdst; bf * vdst; const int32_t * tok_slot;
     bf * pk_hi; bf * pk_lo;
     int dbg;
+    int x_f16, pack_f16;                                           // f16 activation images (gemm_tc.cuh pack_act2): operand / epilogue output
     const float * next_w; float * stats_out;                       // TS_RES producer of a folded LayerNorm (kernels.cuh)
     const float * ln_stats; int ln_slices; const float * ln_csum; float eps; int K;     // TS_QKV consumer
 };
@@ -71,12 +72,13 @@ template <> __device__ __forceinline__ void tmem_ld_cols<64>(uint32_t taddr, uin
 template <int NC, int EPI, int SPLIT, int kTsStages>
 __global__ void __launch_bounds__(kTsThreads, 1) ts_linear_kernel(const bf * Wt, const bf * Xhi, const bf * Xlo, int KT_all, const TsEpi e) {
     constexpr int kWTile = NC * 128;
-    constexpr int kStage = 2 * kXTile + (kWTile < 1024 ? 1024 : kWTile);
+    const int kXBytes = e.x_f16 ? kXTile : 2 * kXTile;                  // activation bytes per stage: one f16 image or bf16 hi | lo
+    const int kStage = kXBytes + (kWTile < 1024 ? 1024 : kWTile);
     extern __shared__ unsigned char ts_smem[];
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");      // let the dependent kernel start its own prefetching
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char * tiles = reinterpret_cast<unsigned char *>(((uintptr_t)ts_smem + 1023) & ~(uintptr_t)1023);
-    uint64_t * bars = reinterpret_cast<uint64_t *>(tiles + kTsStages * kStage);
+    uint64_t * bars = reinterpret_cast<uint64_t *>(tiles + kTsStages * (2 * kXTile + (kWTile < 1024 ? 1024 : kWTile)));   // (fixed place: the f16 mode leaves a gap)
     uint64_t * full = bars, * empty = bars + kTsStages, * acc_full = bars + 2 * kTsStages;
     uint32_t * tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kTsStages + 1);
     const int n0 = blockIdx.x * NC;                                      // first output feature of this CTA
@@ -92,7 +94,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) ts_linear_kernel(const bf * Wt,
     if (dbg && threadIdx.x == 0) { dbg_slot = atomicAdd(&g_ts_dbg_n, 1u) % 1024u; stamp(0); g_ts_dbg[(size_t)dbg_slot * 8 + 6] = NC * 100 + EPI * 10 + SPLIT; }
     const int rank = SPLIT > 1 ? (int)blockIdx.y : 0;
     const int kt_lo = rank * KT_all / SPLIT, KT = (rank + 1) * KT_all / SPLIT - kt_lo;      // this CTA's k tiles [kt_lo, kt_lo + KT)
-    float * xbuf = reinterpret_cast<float *>(tiles + kTsStages * kStage + 256);             // rank 0: [SPLIT - 1][64][NC] partial accumulators
+    float * xbuf = reinterpret_cast<float *>(tiles + kTsStages * (2 * kXTile + (kWTile < 1024 ? 1024 : kWTile)) + 256);             // rank 0: [SPLIT - 1][64][NC] partial accumulators
     // every CTA reads the SAME activation tiles: with all of them walking k = 0, 1, 2, ... in lock step the 96-144 SMs would hit
     // the same few L2 slices at the same time, so CTA c starts its walk at k tile (5 c) mod KT (a fixed order per CTA: deterministic)
     const int kt_first = (int)((blockIdx.x * 5u) % (unsigned)KT);
@@ -124,8 +126,8 @@ __global__ void __launch_bounds__(kTsThreads, 1) ts_linear_kernel(const bf * Wt,
         if (leader)
             for (int kt = 0; kt < npre; kt++) {
                 int kk = kt + kt_first; kk = kk >= KT ? kk - KT : kk;
-                tc::mbar_expect_tx(&full[kt], 2 * kXTile + kWTile);
-                tc::bulk_g2s(tiles + kt * kStage + 2 * kXTile, wsrc + (size_t)kk * (tc::BM * 128), kWTile, &full[kt]);
+                tc::mbar_expect_tx(&full[kt], kXBytes + kWTile);
+                tc::bulk_g2s(tiles + kt * kStage + kXBytes, wsrc + (size_t)kk * (tc::BM * 128), kWTile, &full[kt]);
             }
         asm volatile("griddepcontrol.wait;" ::: "memory");
         if (dbg && leader) stamp(1);
@@ -136,28 +138,34 @@ __global__ void __launch_bounds__(kTsThreads, 1) ts_linear_kernel(const bf * Wt,
             if (kt >= npre) tc::mbar_wait(&empty[s], ((kt / kTsStages) & 1) ^ 1);
             if (leader) {
                 if (kt >= npre) {
-                    tc::mbar_expect_tx(&full[s], 2 * kXTile + kWTile);
-                    tc::bulk_g2s(st + 2 * kXTile, wsrc + (size_t)kk * (tc::BM * 128), kWTile, &full[s]);
+                    tc::mbar_expect_tx(&full[s], kXBytes + kWTile);
+                    tc::bulk_g2s(st + kXBytes, wsrc + (size_t)kk * (tc::BM * 128), kWTile, &full[s]);
                 }
                 tc::bulk_g2s(st, hsrc + (size_t)kk * kXTile, kXTile, &full[s]);
-                tc::bulk_g2s(st + kXTile, lsrc + (size_t)kk * kXTile, kXTile, &full[s]);
+                if (!e.x_f16) tc::bulk_g2s(st + kXTile, lsrc + (size_t)kk * kXTile, kXTile, &full[s]);
             }
         }
     } else if (warp == 1) {
         constexpr uint32_t idesc = tc::umma_idesc_bf16(64, NC);          // D[64 tokens x NC] += X[64 x 16] . W[NC x 16]^T
+        constexpr uint32_t idesc_h = tc::umma_idesc_f16(64, NC);         // ... activations as one f16 image against the f16 twin of the weights
         const bool leader = tc::elect_one();
         const uint32_t tiles_d = tc::desc_lo(tc::smem_u32(tiles));       // descriptor address units are 16 bytes
         for (int kt = 0; kt < KT; kt++) {
             const int s = kt % kTsStages;
             tc::mbar_wait(&full[s], (kt / kTsStages) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t h0 = tiles_d + (uint32_t)s * (kStage >> 4), l0 = h0 + (kXTile >> 4), w0 = l0 + (kXTile >> 4);
+            const uint32_t h0 = tiles_d + (uint32_t)s * (uint32_t)(kStage >> 4), l0 = h0 + (kXTile >> 4), w0 = h0 + (uint32_t)(kXBytes >> 4);
             if (leader) {
                 if (dbg && kt == 0) stamp(2);
+                if (e.x_f16) {
 #pragma unroll
-                for (int j = 0; j < tc::BK / 16; j++) {                  // 16 k-elements = 32 bytes = 2 descriptor units inside the swizzle row
-                    tc::umma_lo(tmem_base, h0 + 2 * j, w0 + 2 * j, idesc, (kt | j) != 0);
-                    tc::umma_lo(tmem_base, l0 + 2 * j, w0 + 2 * j, idesc, 1u);
+                    for (int j = 0; j < tc::BK / 16; j++) tc::umma_lo(tmem_base, h0 + 2 * j, w0 + 2 * j, idesc_h, (kt | j) != 0);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < tc::BK / 16; j++) {              // 16 k-elements = 32 bytes = 2 descriptor units inside the swizzle row
+                        tc::umma_lo(tmem_base, h0 + 2 * j, w0 + 2 * j, idesc, (kt | j) != 0);
+                        tc::umma_lo(tmem_base, l0 + 2 * j, w0 + 2 * j, idesc, 1u);
+                    }
                 }
                 if (kt + kTsStages < KT) tc::umma_commit(&empty[s]);      // only a stage that is refilled needs its release
             }
@@ -257,17 +265,12 @@ __global__ void __launch_bounds__(kTsThreads, 1) ts_linear_kernel(const bf * Wt,
                     for (int j = 0; j < NH / 8; j++) {
                         uint32_t h[4], l[4];
 #pragma unroll
-                        for (int p = 0; p < 4; p++) {
-                            const float a = y[8 * j + 2 * p] * e.next_w[nb + 8 * j + 2 * p], b = y[8 * j + 2 * p + 1] * e.next_w[nb + 8 * j + 2 * p + 1];
-                            const bf ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
-                            const bf la = __float2bfloat16_rn(a - __bfloat162float(ha)), lb = __float2bfloat16_rn(b - __bfloat162float(hb));
-                            h[p] = (uint32_t)__bfloat16_as_ushort(ha) | ((uint32_t)__bfloat16_as_ushort(hb) << 16);
-                            l[p] = (uint32_t)__bfloat16_as_ushort(la) | ((uint32_t)__bfloat16_as_ushort(lb) << 16);
-                        }
+                        for (int p = 0; p < 4; p++)
+                            tc::pack_act2(y[8 * j + 2 * p] * e.next_w[nb + 8 * j + 2 * p], y[8 * j + 2 * p + 1] * e.next_w[nb + 8 * j + 2 * p + 1], e.pack_f16 != 0, h[p], l[p]);
                         const int n = nb + 8 * j;
                         const size_t off = (size_t)(n >> 6) * kXTile + tc::swz_offset(m, n & 63);
                         *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(e.pk_hi) + off) = make_uint4(h[0], h[1], h[2], h[3]);
-                        *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(e.pk_lo) + off) = make_uint4(l[0], l[1], l[2], l[3]);
+                        if (!e.pack_f16) *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(e.pk_lo) + off) = make_uint4(l[0], l[1], l[2], l[3]);
                     }
                 }
             } else {                                 // GELU + hi | lo tile images for the next GEMM (k tile n / 64, 16-byte chunk (n % 64) / 8)
@@ -275,17 +278,12 @@ __global__ void __launch_bounds__(kTsThreads, 1) ts_linear_kernel(const bf * Wt,
                 for (int j = 0; j < NH / 8; j++) {
                     uint32_t h[4], l[4];
 #pragma unroll
-                    for (int p = 0; p < 4; p++) {
-                        const float a = gelu_ggml_fast(y[8 * j + 2 * p], e.gelu_f16), b = gelu_ggml_fast(y[8 * j + 2 * p + 1], e.gelu_f16);
-                        const bf ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
-                        const bf la = __float2bfloat16_rn(a - __bfloat162float(ha)), lb = __float2bfloat16_rn(b - __bfloat162float(hb));
-                        h[p] = (uint32_t)__bfloat16_as_ushort(ha) | ((uint32_t)__bfloat16_as_ushort(hb) << 16);
-                        l[p] = (uint32_t)__bfloat16_as_ushort(la) | ((uint32_t)__bfloat16_as_ushort(lb) << 16);
-                    }
+                    for (int p = 0; p < 4; p++)
+                        tc::pack_act2(gelu_ggml_fast(y[8 * j + 2 * p], e.gelu_f16), gelu_ggml_fast(y[8 * j + 2 * p + 1], e.gelu_f16), e.pack_f16 != 0, h[p], l[p]);
                     const int n = nb + 8 * j;
                     const size_t off = (size_t)(n >> 6) * kXTile + tc::swz_offset(m, n & 63);
                     *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(e.pk_hi) + off) = make_uint4(h[0], h[1], h[2], h[3]);
-                    *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(e.pk_lo) + off) = make_uint4(l[0], l[1], l[2], l[3]);
+                    if (!e.pack_f16) *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(e.pk_lo) + off) = make_uint4(l[0], l[1], l[2], l[3]);
                 }
             }
         }
@@ -369,6 +367,7 @@ bool launch_linear_ts(const LinearArgs & a, const void * hi, const void * lo, cu
     e.pk_hi = nullptr; e.pk_lo = nullptr;
     if (a.pack_out) { e.pk_hi = (bf *)a.pack_out; e.pk_lo = e.pk_hi + (size_t)64 * a.W.N; }
     e.next_w = a.next_ln_w; e.stats_out = a.stats_out;
+    e.x_f16 = a.act_f16 ? 1 : 0; e.pack_f16 = a.pack_f16 ? 1 : 0;
     static const bool dbg_on = getenv("MGB_TS_DBG") != nullptr;
     e.dbg = dbg_on ? 1 : 0;
     if (dbg_on && getenv("MGB_TS_DBG_DUMP")) {           // dump at the given call of this function (direct launches, not graph replays)
@@ -396,7 +395,8 @@ bool launch_linear_ts(const LinearArgs & a, const void * hi, const void * lo, cu
     }
     e.ln_stats = a.ln_fold_stats; e.ln_slices = a.ln_fold_slices; e.ln_csum = a.ln_fold_csum; e.eps = a.eps; e.K = a.W.K;
     const int KT = a.W.K / 64;
-    const bf * W = (const bf *)a.W.tiles;
+    if (a.act_f16 && !a.W.tiles16) { set_error("linear: f16 activation images need the f16 weight images (MGB_ACT_F16 at model load)"); return false; }
+    const bf * W = (const bf *)(a.act_f16 ? a.W.tiles16 : a.W.tiles);
     // One-CTA slices for the K = 768 GEMMs (QKV 144 CTAs, O 96, FF1 96).  The wide-K GEMM (FF2, K = 3072) is bound by how fast ONE
     // SM ingests the 786 KB activation operand (the same 21 us with 24, 48 or 96 one-CTA slices), so its 32-row slices are shared
     // by a 4-CTA cluster that divides the k tiles (10 us).  Measured at 64 utterances, us per step: no split 1331, FF2 split over
@@ -406,6 +406,9 @@ bool launch_linear_ts(const LinearArgs & a, const void * hi, const void * lo, cu
     const bf * h = (const bf *)hi, * l = (const bf *)lo;
     if (a.n_q >= 0) {
         if (shaped == 2 && KT % 4 == 0 && a.W.N % 64 == 0 && a.n_q % 64 == 0 && a.dkv % 64 == 0) return launch_ts<64, TS_QKV, 4, 4>(W, h, l, KT, e, stream);
+        static const int qkv_nc = getenv("MGB_TS_QKV_NC") ? atoi(getenv("MGB_TS_QKV_NC")) : 16;
+        if (qkv_nc == 32 && a.W.N % 32 == 0 && a.n_q % 32 == 0 && a.dkv % 32 == 0) return launch_ts<32, TS_QKV>(W, h, l, KT, e, stream);
+        if (qkv_nc == 8) return launch_ts<8, TS_QKV>(W, h, l, KT, e, stream);
         return launch_ts<16, TS_QKV>(W, h, l, KT, e, stream);
     }
     if (a.res) {

@@ -47,11 +47,14 @@ struct LinearArgs {
     //     (model.cu), mean / rstd from the slices' sums added in slice order (deterministic).
     const float * next_ln_w = nullptr; float * stats_out = nullptr;
     const float * ln_fold_stats = nullptr; int ln_fold_slices = 0; const float * ln_fold_csum = nullptr;
+    // batched decoder step with f16 activation images (gemm_tc.cuh pack_act2): act_f16 = the X images of this GEMM are ONE f16 image
+    // (its packing kernel writes that, its MMAs read A as f16); pack_f16 = the epilogue writes pack_out that way
+    bool act_f16 = false, pack_f16 = false;
 };
 bool launch_linear(const LinearArgs & a, cudaStream_t stream);
 // tcgen05 path (bf16, >= 16 tokens): gemm_tc.cu
 size_t tc_weight_tile_bytes(int N, int K);
-bool   tc_pack_weights(const void * W, int N, int K, void * Wt, cudaStream_t stream, int taps = 1);     // W: [taps][N][K]
+bool   tc_pack_weights(const void * W, int N, int K, void * Wt, cudaStream_t stream, int taps = 1, bool as_f16 = false);     // W: [taps][N][K]
 size_t tc_scratch_bytes(int M, int K);
 bool   tc_linear_supported(const LinearArgs & a);
 bool   launch_linear_tc(const LinearArgs & a, cudaStream_t stream);
@@ -72,6 +75,7 @@ struct AttnArgs {
     Tokens tok;
     float * out = nullptr; int ldo = 0;
     void * pack_out = nullptr;                   // dh == 64, <= 64 tokens: write hi | lo tile images for the next GEMM instead of `out`
+    bool pack_f16 = false;                       // ... as ONE f16 image (LinearArgs::act_f16 of the consumer)
     int prefill_len = 0;                         // > 0: tokens are utterance-major runs of positions 0..prefill_len-1 (context prefill)
     const int32_t * page_table = nullptr; int max_pages = 0;   // paged K / V: [utterances][max_pages] page ids (pages of kKvPageRows rows); null = contiguous
     int kv_split = 0;                            // packed-output decoder step only: >= 1 = long-KV kernel, keys of a (head, token) divided over a cluster of this many CTAs
@@ -81,7 +85,7 @@ int attention_plan_kv_split(int items, int max_keys);   // cluster size for a de
 // batched decoder step: folded cross-attention x += softmax(M LN(x)) N (tables from launch_xattn_fold, frame_loop.cu)
 // pack_ln_w / pack_out (optional, B <= 64): additionally emit LN(x_new; pack_ln_w) as hi | lo tile images for the next GEMM
 bool launch_xattn_folded(float * x, const float * ln_w, float eps, const float * xm, const float * xn, const int32_t * n_ctx, int B, int d,
-                         int max_text, const float * pack_ln_w, void * pack_out, cudaStream_t stream);
+                         int max_text, const float * pack_ln_w, void * pack_out, cudaStream_t stream, bool pack_f16 = false);
 
 // x[t] = (sum_cb E_cb[codes[utt][cb]]) * 1/8 + dec_pos[pos]        (magpie.cpp:2746-2787, 4376-4379)
 bool launch_audio_embed(const Model & m, const int32_t * codes /*[B][8] device*/, const int32_t * pos /*[B]*/,

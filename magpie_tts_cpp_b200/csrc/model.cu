@@ -309,6 +309,16 @@ Model * load_model(const char * path, int device, int precision) {
             if (!tc_pack_weights(m->w, m->N, m->K, t, nullptr, m->taps)) return nullptr;
             m->tiles = t;
         }
+        // f16 activation images in the batched decoder step (gemm_tc.cuh pack_act2): f16 twins of the four decoder-step matrices (+175 MB)
+        if (getenv("MGB_ACT_F16") == nullptr || atoi(getenv("MGB_ACT_F16")) != 0)      // default on; MGB_ACT_F16=0: bf16 hi | lo image pairs (A/B)
+            for (auto & L : M->dec) for (DevMat * m : {&L.qkv, &L.o, &L.ff1, &L.ff2}) {
+                if (!m->tiles || m->taps != 1) continue;
+                void * t = nullptr;
+                if (cudaMalloc(&t, tc_weight_tile_bytes(m->N, m->K)) != cudaSuccess) { set_error("cudaMalloc failed (f16 weight tiles)"); return nullptr; }
+                M->allocations.push_back(t);
+                if (!tc_pack_weights(m->w, m->N, m->K, t, nullptr, 1, true)) return nullptr;
+                m->tiles16 = t;
+            }
         for (auto & L : M->dec) {
             void * c = nullptr;
             if (cudaMalloc(&c, (size_t)L.qkv.N * sizeof(float)) != cudaSuccess) { set_error("cudaMalloc failed"); return nullptr; }

@@ -19,6 +19,7 @@ struct DevMat {
     void * w = nullptr;
     int    N = 0, K = 0, taps = 1;
     void * tiles = nullptr;      // bf16 models: [ceil(N/128)][K/64] tiles of 128 x 64 in the tcgen05 shared-memory image (gemm_tc.cuh)
+    void * tiles16 = nullptr;    // the same image with the bf16 values re-encoded as f16 (exact above 6.1e-5): operands of the f16-activation GEMMs
 };
 
 struct EncLayer { float * norm_self = nullptr, * norm_ff = nullptr; DevMat qkv, o, ff1, ff2; };

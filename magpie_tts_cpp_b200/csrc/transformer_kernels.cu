@@ -9,6 +9,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "gemm_tc.cuh"
 #include "kernels.cuh"
 
 namespace mgb {
@@ -176,6 +177,7 @@ struct AttnParams {
     // of the layer's page pool; null = contiguous rows u * rows_per_utt + j (cross-attention K / V, encoder scratch)
     const int32_t * page_table; int max_pages;
     int dbg;
+    int pk_f16;                                        // packed output as one f16 image (gemm_tc.cuh pack_act2)
 };
 constexpr int kPageShift = 7, kPageRows = 1 << kPageShift;     // = kKvPageRows (kernels.cuh)
 
@@ -399,7 +401,7 @@ __global__ void __launch_bounds__(NW * 32, SPLIT == 2 ? (NW == 4 ? 6 : 3) : 0) a
             if (tid == 0) { attn_dsmem_store(&x_m[crank], 0, M); attn_dsmem_store(&x_l[crank], 0, L); }
             attn_dsmem_store(&x_o[crank][tid], 0, o);
         }
-        attn_cluster_sync();               // every thread of every CTA of the cluster; rank 0's shared memory is written before it
+        if (csize > 1) attn_cluster_sync();   // every thread of every CTA of the cluster; rank 0's shared memory is written before it
         if (crank != 0) return;
         if (tid < DH) {
             for (unsigned r = 1; r < csize; r++) {          // fixed rank order: deterministic
@@ -417,10 +419,14 @@ __global__ void __launch_bounds__(NW * 32, SPLIT == 2 ? (NW == 4 ? 6 : 3) : 0) a
         const float y = o * (1.0f / L);
         if (p.pk_hi) {
             // head h is exactly k tile h of the following GEMM (64 columns = one 128-byte swizzle row): gemm_tc.cu layout
-            const __nv_bfloat16 hv = __float2bfloat16_rn(y);
             const size_t off = (size_t)h * (64 * 128) + (size_t)t * 128 + (((((tid >> 3) ^ (t & 7)) & 7) << 4) + ((tid & 7) << 1));
-            *reinterpret_cast<__nv_bfloat16 *>(reinterpret_cast<unsigned char *>(p.pk_hi) + off) = hv;
-            *reinterpret_cast<__nv_bfloat16 *>(reinterpret_cast<unsigned char *>(p.pk_lo) + off) = __float2bfloat16_rn(y - __bfloat162float(hv));
+            if (p.pk_f16) {
+                *reinterpret_cast<__half *>(reinterpret_cast<unsigned char *>(p.pk_hi) + off) = __float2half_rn(fminf(fmaxf(y, -65504.0f), 65504.0f));
+            } else {
+                const __nv_bfloat16 hv = __float2bfloat16_rn(y);
+                *reinterpret_cast<__nv_bfloat16 *>(reinterpret_cast<unsigned char *>(p.pk_hi) + off) = hv;
+                *reinterpret_cast<__nv_bfloat16 *>(reinterpret_cast<unsigned char *>(p.pk_lo) + off) = __float2bfloat16_rn(y - __bfloat162float(hv));
+            }
         } else {
             p.out[(size_t)t * p.ldo + h * DH + tid] = y;
         }
@@ -599,7 +605,7 @@ bool launch_attention(const AttnArgs & a, cudaStream_t stream) {
     AttnParams p;
     p.q = a.q; p.ldq = a.ldq; p.K = a.K; p.V = a.V; p.rows_per_utt = a.rows_per_utt; p.H = a.H;
     p.causal = a.causal; p.n_ctx = a.n_ctx; p.utt = a.tok.utt; p.pos = a.tok.pos; p.out = a.out; p.ldo = a.ldo;
-    p.pk_hi = nullptr; p.pk_lo = nullptr;
+    p.pk_hi = nullptr; p.pk_lo = nullptr; p.pk_f16 = a.pack_f16 ? 1 : 0;
     p.page_table = a.page_table; p.max_pages = a.max_pages;
     if (a.pack_out) {
         if (a.dh != 64 || a.tok.M > 64) { set_error("attention: packed output needs head dim 64 and one token tile"); return false; }
@@ -699,7 +705,7 @@ bool launch_attention(const AttnArgs & a, cudaStream_t stream) {
 // prefill (frame_loop.cu xattn_fold_kernel): the reference's q_net GEMV, 1-head attention over E text tokens and o_net GEMV
 // (magpie.cpp:1713-1767, 3513) in ONE launch instead of five.  One CTA per utterance, 512 threads.
 struct XFoldParams { float * x; const float * ln_w; float eps; const float * xm; const float * xn; const int32_t * n_ctx; int d, max_text;
-                     const float * pack_ln_w; __nv_bfloat16 * pk_hi; __nv_bfloat16 * pk_lo; };
+                     const float * pack_ln_w; __nv_bfloat16 * pk_hi; __nv_bfloat16 * pk_lo; int pk_f16; };
 // One CLUSTER of kXC CTAs per utterance; CTA rank r owns the d / kXC columns [r * dc, (r + 1) * dc) of the row, i.e. a
 // quarter of both tables: partial scores and the LayerNorm statistics of the updated row are exchanged through DSMEM.
 constexpr int kXC = 4, kXT = 256;
@@ -844,27 +850,21 @@ __global__ void __launch_bounds__(kXT) xattn_folded_kernel(const XFoldParams p) 
     for (int kc = tid; kc < dc / 8; kc += kXT) {
         uint32_t h[4], l[4];
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const float v0 = xl[kc * 8 + 2 * q], v1 = xl[kc * 8 + 2 * q + 1];
-            const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
-            const __nv_bfloat16 l0 = __float2bfloat16_rn(v0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(v1 - __bfloat162float(h1));
-            h[q] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-            l[q] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-        }
+        for (int q = 0; q < 4; q++) tc::pack_act2(xl[kc * 8 + 2 * q], xl[kc * 8 + 2 * q + 1], p.pk_f16 != 0, h[q], l[q]);
         const int kg = (c0 >> 3) + kc;                       // 8-column group index in the row
         const size_t off = (size_t)(kg / 8) * (64 * 128) + (size_t)u * 128 + ((((kg % 8) ^ (u & 7)) & 7) << 4);
         *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(p.pk_hi) + off) = make_uint4(h[0], h[1], h[2], h[3]);
-        *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(p.pk_lo) + off) = make_uint4(l[0], l[1], l[2], l[3]);
+        if (!p.pk_f16) *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(p.pk_lo) + off) = make_uint4(l[0], l[1], l[2], l[3]);
     }
 }
 
 bool launch_xattn_folded(float * x, const float * ln_w, float eps, const float * xm, const float * xn, const int32_t * n_ctx, int B, int d,
-                         int max_text, const float * pack_ln_w, void * pack_out, cudaStream_t stream) {
+                         int max_text, const float * pack_ln_w, void * pack_out, cudaStream_t stream, bool pack_f16) {
     // (columns per rank: <= 256 with whole float4 / 64-column groups, at most 3 float2 per lane and row, 5 x dc / 4 <= 256 threads)
     if (d > 768 || max_text > 512 || d % (kXC * 64) != 0 || kXRG * (d / kXC / 4) > kXT) { set_error("xattn_folded: shape not supported"); return false; }
     if (pack_out && B > 64) { set_error("xattn_folded: packed output needs one token tile"); return false; }
     XFoldParams p{x, ln_w, eps, xm, xn, n_ctx, d, max_text, pack_ln_w, (__nv_bfloat16 *)pack_out,
-                  pack_out ? (__nv_bfloat16 *)pack_out + (size_t)64 * d : nullptr};
+                  pack_out ? (__nv_bfloat16 *)pack_out + (size_t)64 * d : nullptr, pack_f16 ? 1 : 0};
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(B * kXC); cfg.blockDim = dim3(kXT); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
     cudaLaunchAttribute at[2];
