@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) ts_linear_kernel(const bf * Wt,
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");      // let the dependent kernel start its own prefetching
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char * tiles = reinterpret_cast<unsigned char *>(((uintptr_t)ts_smem + 1023) & ~(uintptr_t)1023);
-    uint64_t * bars = reinterpret_cast<uint64_t *>(tiles + kTsStages * (2 * kXTile + (kWTile < 1024 ? 1024 : kWTile)));   // (fixed place: the f16 mode leaves a gap)
+    uint64_t * bars = reinterpret_cast<uint64_t *>(tiles + kTsStages * kStage);
     uint64_t * full = bars, * empty = bars + kTsStages, * acc_full = bars + 2 * kTsStages;
     uint32_t * tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kTsStages + 1);
     const int n0 = blockIdx.x * NC;                                      // first output feature of this CTA
@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) ts_linear_kernel(const bf * Wt,
     if (dbg && threadIdx.x == 0) { dbg_slot = atomicAdd(&g_ts_dbg_n, 1u) % 1024u; stamp(0); g_ts_dbg[(size_t)dbg_slot * 8 + 6] = NC * 100 + EPI * 10 + SPLIT; }
     const int rank = SPLIT > 1 ? (int)blockIdx.y : 0;
     const int kt_lo = rank * KT_all / SPLIT, KT = (rank + 1) * KT_all / SPLIT - kt_lo;      // this CTA's k tiles [kt_lo, kt_lo + KT)
-    float * xbuf = reinterpret_cast<float *>(tiles + kTsStages * (2 * kXTile + (kWTile < 1024 ? 1024 : kWTile)) + 256);             // rank 0: [SPLIT - 1][64][NC] partial accumulators
+    float * xbuf = reinterpret_cast<float *>(tiles + kTsStages * kStage + 256);             // rank 0: [SPLIT - 1][64][NC] partial accumulators
     // every CTA reads the SAME activation tiles: with all of them walking k = 0, 1, 2, ... in lock step the 96-144 SMs would hit
     // the same few L2 slices at the same time, so CTA c starts its walk at k tile (5 c) mod KT (a fixed order per CTA: deterministic)
     const int kt_first = (int)((blockIdx.x * 5u) % (unsigned)KT);
@@ -299,10 +299,13 @@ template <int NC, int EPI, int SPLIT = 1, int STAGES = 8> bool launch_ts(const b
     int dev = 0;
     MGB_CUDA_TRY(cudaGetDevice(&dev));
     constexpr int kWTile = NC * 128;
-    constexpr int smem = STAGES * (2 * kXTile + (kWTile < 1024 ? 1024 : kWTile)) + 1024 + 256 + (SPLIT - 1) * 64 * NC * 4;
-    static_assert(smem <= 227 * 1024, "ts_linear shared memory");
+    constexpr int smem_max = STAGES * (2 * kXTile + (kWTile < 1024 ? 1024 : kWTile)) + 1024 + 256 + (SPLIT - 1) * 64 * NC * 4;
+    static_assert(smem_max <= 227 * 1024, "ts_linear shared memory");
+    // (the f16 mode needs only half of the activation bytes per stage, but shrinking the allocation to 80-96 KB lets the CTAs of two
+    //  consecutive GEMMs share an SM, and the early-resident successor slows its predecessor: 679 vs 664 us per step -- keep the footprint)
+    constexpr int smem = smem_max;
     if (!attr_done.done(dev)) {
-        MGB_CUDA_TRY(cudaFuncSetAttribute(ts_linear_kernel<NC, EPI, SPLIT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        MGB_CUDA_TRY(cudaFuncSetAttribute(ts_linear_kernel<NC, EPI, SPLIT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
         attr_done.set(dev);
     }
     cudaLaunchConfig_t cfg = {};
