@@ -515,14 +515,18 @@ def extra_measurements(binding, fixtures, m, args):
             cmd = [cli, "-m", fixtures.ensure_fixture("model-f32"), "-c", fixtures.ensure_fixture("codec-f32"), "-t", "Hello, world!",
                    "--temp", "0", "-o", wav, "-q"]
             subprocess.run(cmd, capture_output=True, text=True, timeout=300)          # page the files in
-            t0 = time.perf_counter()
-            pr = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
-            wall = time.perf_counter() - t0
+            walls = []
+            for _ in range(3):     # process start, CUDA context, GGUF load and teardown vary by seconds between runs on a shared host: all samples reported
+                t0 = time.perf_counter()
+                pr = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+                walls.append(time.perf_counter() - t0)
+            wall = min(walls)
             if pr.returncode == 0 and os.path.exists(wav):
                 n_frames = (os.path.getsize(wav) - 44) // 2048
                 out["cli_wall_s"] = wall
+                out["cli_wall_samples_s"] = [round(w, 2) for w in walls]
                 out["cli_frames"] = int(n_frames)
-                out["cli_sample"] = ("magpie-tts -t 'Hello, world!' --temp 0 (bf16 default): whole process incl. loading the 858 MB f32 GGUF and "
+                out["cli_sample"] = ("magpie-tts -t 'Hello, world!' --temp 0 (bf16 default), best of 3: whole process incl. CUDA context, loading the 906 MB f32 GGUF and "
                                      "the codec; audio seconds produced = frames x 1024 / 22050")
                 for ln in pr.stderr.splitlines():
                     if "frames/s" in ln:
