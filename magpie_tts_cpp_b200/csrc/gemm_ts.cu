@@ -81,6 +81,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) ts_linear_kernel(const bf * Wt,
     uint64_t * bars = reinterpret_cast<uint64_t *>(tiles + kTsStages * kStage);
     uint64_t * full = bars, * empty = bars + kTsStages, * acc_full = bars + 2 * kTsStages;
     uint32_t * tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kTsStages + 1);
+    __shared__ float2 s_part[4][64];                                     // TS_QKV with a folded LayerNorm: partial row statistics (see the epilogue warps)
     const int n0 = blockIdx.x * NC;                                      // first output feature of this CTA
     // epilogue: two warps per TMEM lane quarter, each takes half of the CTA's columns (NC >= 16; with M = 64 only lanes 0..15 of a
     // warp hold rows, so the epilogues -- GELU + packing of up to 32 columns per row -- were serial tails of 3.5-4.2 us on 64 threads)
@@ -175,6 +176,20 @@ __global__ void __launch_bounds__(kTsThreads, 1) ts_linear_kernel(const bf * Wt,
     }
     if (warp >= 2) {
         asm volatile("griddepcontrol.wait;" ::: "memory");
+        if (EPI == TS_QKV && e.ln_stats) {
+            // LayerNorm folded through this GEMM: while the MMAs run, the 256 epilogue threads add the row statistics of the e.ln_slices column
+            // slices the preceding FF2 wrote: 4 threads per row, a contiguous quarter of the slices each (fixed order: deterministic)
+            const int t = (int)threadIdx.x - 64, m = t & 63, part = t >> 6, per = (e.ln_slices + 3) >> 2;
+            const int s_lo = part * per, s_hi = min(e.ln_slices, s_lo + per);
+            float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll 4
+            for (int sl = s_lo; sl < s_hi; sl++) {
+                const float2 st = *reinterpret_cast<const float2 *>(e.ln_stats + ((size_t)sl * 64 + m) * 2);
+                s1 += st.x; s2 += st.y;
+            }
+            s_part[part][m] = make_float2(s1, s2);
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
         tc::mbar_wait(acc_full, 0);
         if (dbg && threadIdx.x == 64) stamp(4);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -217,12 +232,8 @@ __global__ void __launch_bounds__(kTsThreads, 1) ts_linear_kernel(const bf * Wt,
             }
             if (EPI == TS_QKV) {
                 if (e.ln_stats) {                    // LayerNorm folded through this GEMM: y = (acc - mean * csum[n]) * rstd
-                    float s1 = 0.0f, s2 = 0.0f;
-#pragma unroll 8
-                    for (int sl = 0; sl < e.ln_slices; sl++) {
-                        const float2 st = *reinterpret_cast<const float2 *>(e.ln_stats + ((size_t)sl * 64 + m) * 2);
-                        s1 += st.x; s2 += st.y;
-                    }
+                    const float s1 = ((s_part[0][m].x + s_part[1][m].x) + s_part[2][m].x) + s_part[3][m].x;
+                    const float s2 = ((s_part[0][m].y + s_part[1][m].y) + s_part[2][m].y) + s_part[3][m].y;
                     const float mean = s1 / (float)e.K, var = fmaxf(s2 / (float)e.K - mean * mean, 0.0f);
                     const float rstd = 1.0f / sqrtf(var + e.eps);
 #pragma unroll
