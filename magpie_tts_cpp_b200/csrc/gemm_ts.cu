@@ -88,12 +88,15 @@ __global__ void __launch_bounds__(kTsThreads, 1) ts_linear_kernel(const bf * Wt,
     constexpr int NH = NC >= 16 ? NC / 2 : NC;
     const int half = warp >= 6 ? 1 : 0;
     const bool epi_on = NC >= 16 || half == 0;
-    const int c0 = NC >= 16 ? half * NH : 0, nb = n0 + c0;
+    const int c0 = NC >= 16 ? half * NH : 0;
     __shared__ unsigned dbg_slot;
     const bool dbg = e.dbg && blockIdx.x == 0 && blockIdx.y == 0;
     auto stamp = [&](int i) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); g_ts_dbg[(size_t)dbg_slot * 8 + i] = t; };
     if (dbg && threadIdx.x == 0) { dbg_slot = atomicAdd(&g_ts_dbg_n, 1u) % 1024u; stamp(0); g_ts_dbg[(size_t)dbg_slot * 8 + 6] = NC * 100 + EPI * 10 + SPLIT; }
     const int rank = SPLIT > 1 ? (int)blockIdx.y : 0;
+    constexpr int CR = NC / SPLIT;                                       // split-K: columns a rank finishes (reduce-scatter epilogue)
+    constexpr int NE = SPLIT > 1 ? CR : NH;                              // columns per epilogue thread
+    const int nb = n0 + (SPLIT > 1 ? CR * rank : c0);                    // first output feature of this thread
     const int kt_lo = rank * KT_all / SPLIT, KT = (rank + 1) * KT_all / SPLIT - kt_lo;      // this CTA's k tiles [kt_lo, kt_lo + KT)
     float * xbuf = reinterpret_cast<float *>(tiles + kTsStages * kStage + 256);             // rank 0: [SPLIT - 1][64][NC] partial accumulators
     // every CTA reads the SAME activation tiles: with all of them walking k = 0, 1, 2, ... in lock step the 96-144 SMs would hit
@@ -195,16 +198,28 @@ __global__ void __launch_bounds__(kTsThreads, 1) ts_linear_kernel(const bf * Wt,
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int q = warp & 3;                      // TMEM lane quarter of this warp; M = 64: rows 16 q .. 16 q + 15 on its lanes 0..15
         const int m = 16 * q + lane;
-        if (SPLIT > 1 && rank > 0 && epi_on) {
-            uint32_t v[NH];
-            tmem_ld_cols<NH>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+        if (SPLIT > 1) {
+            // split-K: REDUCE-SCATTER.  Rank r finishes columns [CR r, CR r + CR) of the slice: every rank sends the other ranks their
+            // column blocks of its partial accumulator through DSMEM (this thread: 16 columns = the blocks of ranks 2 half, 2 half + 1),
+            // so the epilogue's work (residual, stores, next operand, statistics) is spread over the cluster instead of rank 0 alone.
+            static_assert(SPLIT == 1 || (SPLIT == 4 && NC == 32), "split-K epilogue is written for 4 ranks x 8 columns");
+            uint32_t v[16];
+            tmem_ld_cols<16>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(16 * half), v);
             if (lane < 16) {
-                const uint32_t local = tc::smem_u32(xbuf + ((size_t)(rank - 1) * 64 + m) * NC + c0);
-                uint32_t remote;
-                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(0));
 #pragma unroll
-                for (int j = 0; j < NH / 4; j++)
-                    asm volatile("st.shared::cluster.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(remote + j * 16), "r"(v[4 * j]), "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3]) : "memory");
+                for (int dd = 0; dd < 2; dd++) {
+                    const int dest = 2 * half + dd;
+                    if (dest != rank) {
+                        const int slot = rank < dest ? rank : rank - 1;          // position among the destination's 3 sources (rank order)
+                        const uint32_t local = tc::smem_u32(xbuf + ((size_t)slot * 64 + m) * CR);
+                        uint32_t remote;
+                        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(dest));
+#pragma unroll
+                        for (int j = 0; j < CR / 4; j++)
+                            asm volatile("st.shared::cluster.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(remote + j * 16), "r"(v[8 * dd + 4 * j]), "r"(v[8 * dd + 4 * j + 1]),
+                                         "r"(v[8 * dd + 4 * j + 2]), "r"(v[8 * dd + 4 * j + 3]) : "memory");
+                    }
+                }
             }
             __syncwarp();
         }
@@ -213,22 +228,34 @@ __global__ void __launch_bounds__(kTsThreads, 1) ts_linear_kernel(const bf * Wt,
         __syncwarp();                                // (the producer / MMA lanes rejoin their warps before the aligned barrier)
         asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
     }
-    if (warp >= 2 && rank == 0 && epi_on) {
+    if (warp >= 2 && (SPLIT > 1 ? half == 0 : epi_on)) {
         const int q = warp & 3;
         const int m = 16 * q + lane;
-        uint32_t v[NH];
-        tmem_ld_cols<NH>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+        uint32_t v[NE];
+        tmem_ld_cols<NE>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(SPLIT > 1 ? CR * rank : c0), v);
         if (lane < 16 && m < e.M && nb < e.N) {
-            float y[NH];
+            float y[NE];
+            if (SPLIT > 1) {                         // partial sums added in rank order (deterministic); this rank's own comes from TMEM
 #pragma unroll
-            for (int j = 0; j < NH; j++) y[j] = __uint_as_float(v[j]);
-            if (SPLIT > 1) {
+                for (int j = 0; j < NE; j++) y[j] = 0.0f;
 #pragma unroll
-                for (int r = 0; r < SPLIT - 1; r++) {
-                    const float4 * pr = reinterpret_cast<const float4 *>(xbuf + ((size_t)r * 64 + m) * NC + c0);
+                for (int r = 0; r < SPLIT; r++) {
+                    if (r == rank) {
 #pragma unroll
-                    for (int j = 0; j < NH / 4; j++) { const float4 t = pr[j]; y[4 * j] += t.x; y[4 * j + 1] += t.y; y[4 * j + 2] += t.z; y[4 * j + 3] += t.w; }
+                        for (int j = 0; j < NE; j++) y[j] = r == 0 ? __uint_as_float(v[j]) : y[j] + __uint_as_float(v[j]);
+                    } else {
+                        const float4 * pr = reinterpret_cast<const float4 *>(xbuf + ((size_t)(r < rank ? r : r - 1) * 64 + m) * CR);
+#pragma unroll
+                        for (int j = 0; j < NE / 4; j++) {
+                            const float4 t = pr[j];
+                            if (r == 0) { y[4 * j] = t.x; y[4 * j + 1] = t.y; y[4 * j + 2] = t.z; y[4 * j + 3] = t.w; }
+                            else { y[4 * j] += t.x; y[4 * j + 1] += t.y; y[4 * j + 2] += t.z; y[4 * j + 3] += t.w; }
+                        }
+                    }
                 }
+            } else {
+#pragma unroll
+                for (int j = 0; j < NE; j++) y[j] = __uint_as_float(v[j]);
             }
             if (EPI == TS_QKV) {
                 if (e.ln_stats) {                    // LayerNorm folded through this GEMM: y = (acc - mean * csum[n]) * rstd
@@ -237,17 +264,17 @@ __global__ void __launch_bounds__(kTsThreads, 1) ts_linear_kernel(const bf * Wt,
                     const float mean = s1 / (float)e.K, var = fmaxf(s2 / (float)e.K - mean * mean, 0.0f);
                     const float rstd = 1.0f / sqrtf(var + e.eps);
 #pragma unroll
-                    for (int j = 0; j < NH; j++) y[j] = (y[j] - mean * e.ln_csum[nb + j]) * rstd;
+                    for (int j = 0; j < NE; j++) y[j] = (y[j] - mean * e.ln_csum[nb + j]) * rstd;
                 }
                 if (nb < e.n_q) {
                     float4 * dst = reinterpret_cast<float4 *>(e.Y + (size_t)m * e.ldy + nb);
 #pragma unroll
-                    for (int j = 0; j < NH / 4; j++) dst[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+                    for (int j = 0; j < NE / 4; j++) dst[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
                 } else {
                     const int cc = nb - e.n_q;
                     bf * dst = (cc < e.dkv ? e.kdst + cc : e.vdst + (cc - e.dkv)) + (size_t)e.tok_slot[m] * e.dkv;
 #pragma unroll
-                    for (int j = 0; j < NH / 8; j++) {
+                    for (int j = 0; j < NE / 8; j++) {
                         uint32_t w[4];
 #pragma unroll
                         for (int p = 0; p < 4; p++)
@@ -258,22 +285,22 @@ __global__ void __launch_bounds__(kTsThreads, 1) ts_linear_kernel(const bf * Wt,
                 }
             } else if (EPI == TS_RES) {
                 const float4 * rs = reinterpret_cast<const float4 *>(e.res + (size_t)m * e.ldr + nb);
-                float4 r[NH / 4];
+                float4 r[NE / 4];
 #pragma unroll
-                for (int j = 0; j < NH / 4; j++) r[j] = rs[j];
+                for (int j = 0; j < NE / 4; j++) r[j] = rs[j];
                 float4 * dst = reinterpret_cast<float4 *>(e.Y + (size_t)m * e.ldy + nb);
 #pragma unroll
-                for (int j = 0; j < NH / 4; j++) {
+                for (int j = 0; j < NE / 4; j++) {
                     y[4 * j] += r[j].x; y[4 * j + 1] += r[j].y; y[4 * j + 2] += r[j].z; y[4 * j + 3] += r[j].w;
                     dst[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
                 }
                 if (e.next_w) {                      // the next GEMM's operand: (y .* w) as hi | lo images + this slice's row statistics
                     float s1 = 0.0f, s2 = 0.0f;
 #pragma unroll
-                    for (int j = 0; j < NH; j++) { s1 += y[j]; s2 = fmaf(y[j], y[j], s2); }
-                    *reinterpret_cast<float2 *>(e.stats_out + ((size_t)(blockIdx.x * (NC / NH) + half) * 64 + m) * 2) = make_float2(s1, s2);
+                    for (int j = 0; j < NE; j++) { s1 += y[j]; s2 = fmaf(y[j], y[j], s2); }
+                    *reinterpret_cast<float2 *>(e.stats_out + ((size_t)(SPLIT > 1 ? blockIdx.x * SPLIT + rank : blockIdx.x * (NC / NE) + half) * 64 + m) * 2) = make_float2(s1, s2);
 #pragma unroll
-                    for (int j = 0; j < NH / 8; j++) {
+                    for (int j = 0; j < NE / 8; j++) {
                         uint32_t h[4], l[4];
 #pragma unroll
                         for (int p = 0; p < 4; p++)
@@ -286,7 +313,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) ts_linear_kernel(const bf * Wt,
                 }
             } else {                                 // GELU + hi | lo tile images for the next GEMM (k tile n / 64, 16-byte chunk (n % 64) / 8)
 #pragma unroll
-                for (int j = 0; j < NH / 8; j++) {
+                for (int j = 0; j < NE / 8; j++) {
                     uint32_t h[4], l[4];
 #pragma unroll
                     for (int p = 0; p < 4; p++)
@@ -340,11 +367,8 @@ static int ts_shape() {
 }
 
 // columns per CTA of the residual-epilogue GEMM (mirrors the dispatch in launch_linear_ts below)
-int ts_resid_nc(int K) {
-    const int KT = K / 64, shaped = ts_shape();
-    if (shaped && KT >= 32 && KT % 4 == 0) return 16;     // (32-column CTAs, two epilogue warps of 16 columns each per row)
-    if (shaped == 2 && KT % 4 == 0) return 16;
-    return 8;
+int ts_resid_nc(int /*K*/) {
+    return 8;         // 8-row CTAs, and the split-K kernel's four ranks finish 8 columns each
 }
 
 __global__ void row_dots_kernel(const bf * __restrict__ W, const float * __restrict__ v, int N, int K, float * __restrict__ out) {
@@ -419,7 +443,6 @@ bool launch_linear_ts(const LinearArgs & a, const void * hi, const void * lo, cu
     const int shaped = ts_shape();
     const bf * h = (const bf *)hi, * l = (const bf *)lo;
     if (a.n_q >= 0) {
-        if (shaped == 2 && KT % 4 == 0 && a.W.N % 64 == 0 && a.n_q % 64 == 0 && a.dkv % 64 == 0) return launch_ts<64, TS_QKV, 4, 4>(W, h, l, KT, e, stream);
         static const int qkv_nc = getenv("MGB_TS_QKV_NC") ? atoi(getenv("MGB_TS_QKV_NC")) : 16;
         if (qkv_nc == 32 && a.W.N % 32 == 0 && a.n_q % 32 == 0 && a.dkv % 32 == 0) return launch_ts<32, TS_QKV>(W, h, l, KT, e, stream);
         if (qkv_nc == 8) return launch_ts<8, TS_QKV>(W, h, l, KT, e, stream);
@@ -427,10 +450,8 @@ bool launch_linear_ts(const LinearArgs & a, const void * hi, const void * lo, cu
     }
     if (a.res) {
         if (shaped && KT >= 32 && KT % 4 == 0) return launch_ts<32, TS_RES, 4, 8>(W, h, l, KT, e, stream);        // FF2: 24 slices x 4 CTAs, 12 k tiles each
-        if (shaped == 2 && KT % 4 == 0) return launch_ts<32, TS_RES, 4, 4>(W, h, l, KT, e, stream);
         return launch_ts<8, TS_RES>(W, h, l, KT, e, stream);
     }
-    if (shaped == 2 && KT % 3 == 0 && a.W.N % 64 == 0) return launch_ts<64, TS_GELU_PACK, 3, 4>(W, h, l, KT, e, stream);
     return launch_ts<32, TS_GELU_PACK>(W, h, l, KT, e, stream);
 }
 
