@@ -448,6 +448,42 @@ def test_tensor_core_linear_matches_cuda_core_kernels(B, full_model_path, full_o
     np.testing.assert_array_equal(gr_t[0], gr_t[23])     # batch rows are independent and deterministic
 
 
+def test_batched_step_chain_modes_agree(B, full_model_path, full_oracle, monkeypatch):
+    """bf16, 24 utterances x 6 teacher-forced steps: the default chain of the batched decoder step (ONE f16 activation image per GEMM
+    operand against f16 twins of the bf16 weight images; LayerNorm folded through the QKV GEMM: FF2 emits `x .* w` + row statistics)
+    against (a) bf16 hi + lo image pairs (MGB_ACT_F16=0 at model load: f32-accurate activations), (b) the LayerNorm + pack launch in
+    front of every QKV GEMM (MGB_NO_LNFOLD=1 at session creation), and against the oracle.  f16 activations round at 2^-12 relative,
+    an eighth of the bf16 weights' own step: the modes agree to a few 1e-3 of the rms, every mode keeps the 2e-2 bar."""
+    codes = np.repeat(full_oracle["codes"][None, :6], 24, axis=0)
+
+    def run(env):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        m = B.Model(full_model_path, 0, B.PREC_BF16)
+        s = m.session(batch=24, max_text=32)
+        for k in env:
+            monkeypatch.delenv(k, raising=False)
+        s.encode_text([HELLO] * 24, want_output=False)
+        s.prefill([0] * 24)
+        hid, lg, gr = s.teacher_forced(codes)
+        n = s.last_loop_launches
+        s.close(); m.close()
+        return hid, lg, n
+
+    hid_d, lg_d, n_d = run({})
+    hid_a, lg_a, n_a = run({"MGB_ACT_F16": "0"})
+    hid_l, lg_l, n_l = run({"MGB_NO_LNFOLD": "1"})
+    assert n_l == n_d + 11 * 6 and n_a == n_d            # the fold removes the packing launch of layers 1..11, every step
+    for b in (0, 11, 23):
+        close(hid_d[b], hid_a[b], 3e-3)
+        close(lg_d[b], lg_a[b], 3e-3)
+        close(hid_d[b], hid_l[b], 3e-3)
+        close(lg_d[b], lg_l[b], 3e-3)
+        for hid, lg in ((hid_d, lg_d), (hid_a, lg_a), (hid_l, lg_l)):
+            close(hid[b], full_oracle["hid"][:6], 2e-2)
+            close(lg[b], full_oracle["lg"][:6], 2e-2)
+
+
 def test_folded_cross_attention_matches_unfolded_kernels(B, full_model_path, full_oracle, monkeypatch):
     """bf16, 5 utterances with different texts: batched decoder steps with the folded cross-attention tables (one launch per
     layer) against the q_net GEMM + attention + o_net GEMM kernels (MGB_NO_XFOLD=1 at session creation) and the oracle."""
