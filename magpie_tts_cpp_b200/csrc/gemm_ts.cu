@@ -229,33 +229,41 @@ __global__ void __launch_bounds__(kTsThreads, 1) ts_linear_kernel(const bf * Wt,
         asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
     }
     if (warp >= 2 && (SPLIT > 1 ? half == 0 : epi_on)) {
-        const int q = warp & 3;
-        const int m = 16 * q + lane;
+        // M = 64 puts the accumulator rows on lanes 0..15 of each warp: lanes 16..31 take the upper half of their row's columns over
+        // (one shuffle per column), so every lane finishes NE2 columns of row m
+        constexpr int NE2 = NE / 2;
+        static_assert(NE2 % 4 == 0, "epilogue works in units of 4 columns");
+        const int q = warp & 3, lh = lane >> 4, ml = lane & 15;
+        const int m = 16 * q + ml;
+        const int nc = nb + lh * NE2;                // first output feature of this lane
         uint32_t v[NE];
         tmem_ld_cols<NE>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(SPLIT > 1 ? CR * rank : c0), v);
-        if (lane < 16 && m < e.M && nb < e.N) {
-            float y[NE];
-            if (SPLIT > 1) {                         // partial sums added in rank order (deterministic); this rank's own comes from TMEM
+        float y[NE2];
 #pragma unroll
-                for (int j = 0; j < NE; j++) y[j] = 0.0f;
+        for (int j = 0; j < NE2; j++) {
+            const uint32_t up = __shfl_sync(0xffffffffu, v[NE2 + j], ml);
+            y[j] = __uint_as_float(lh ? up : v[j]);
+        }
+        if (m < e.M && nb < e.N) {
+            if (SPLIT > 1) {                         // partial sums added in rank order (deterministic); this rank's own comes from TMEM
+                float own[NE2];
+#pragma unroll
+                for (int j = 0; j < NE2; j++) { own[j] = y[j]; y[j] = 0.0f; }
 #pragma unroll
                 for (int r = 0; r < SPLIT; r++) {
                     if (r == rank) {
 #pragma unroll
-                        for (int j = 0; j < NE; j++) y[j] = r == 0 ? __uint_as_float(v[j]) : y[j] + __uint_as_float(v[j]);
+                        for (int j = 0; j < NE2; j++) y[j] = r == 0 ? own[j] : y[j] + own[j];
                     } else {
-                        const float4 * pr = reinterpret_cast<const float4 *>(xbuf + ((size_t)(r < rank ? r : r - 1) * 64 + m) * CR);
+                        const float4 * pr = reinterpret_cast<const float4 *>(xbuf + ((size_t)(r < rank ? r : r - 1) * 64 + m) * CR + lh * NE2);
 #pragma unroll
-                        for (int j = 0; j < NE / 4; j++) {
+                        for (int j = 0; j < NE2 / 4; j++) {
                             const float4 t = pr[j];
                             if (r == 0) { y[4 * j] = t.x; y[4 * j + 1] = t.y; y[4 * j + 2] = t.z; y[4 * j + 3] = t.w; }
                             else { y[4 * j] += t.x; y[4 * j + 1] += t.y; y[4 * j + 2] += t.z; y[4 * j + 3] += t.w; }
                         }
                     }
                 }
-            } else {
-#pragma unroll
-                for (int j = 0; j < NE; j++) y[j] = __uint_as_float(v[j]);
             }
             if (EPI == TS_QKV) {
                 if (e.ln_stats) {                    // LayerNorm folded through this GEMM: y = (acc - mean * csum[n]) * rstd
@@ -264,64 +272,68 @@ __global__ void __launch_bounds__(kTsThreads, 1) ts_linear_kernel(const bf * Wt,
                     const float mean = s1 / (float)e.K, var = fmaxf(s2 / (float)e.K - mean * mean, 0.0f);
                     const float rstd = 1.0f / sqrtf(var + e.eps);
 #pragma unroll
-                    for (int j = 0; j < NE; j++) y[j] = (y[j] - mean * e.ln_csum[nb + j]) * rstd;
+                    for (int j = 0; j < NE2; j++) y[j] = (y[j] - mean * e.ln_csum[nc + j]) * rstd;
                 }
-                if (nb < e.n_q) {
-                    float4 * dst = reinterpret_cast<float4 *>(e.Y + (size_t)m * e.ldy + nb);
+                if (nc < e.n_q) {
+                    float4 * dst = reinterpret_cast<float4 *>(e.Y + (size_t)m * e.ldy + nc);
 #pragma unroll
-                    for (int j = 0; j < NE / 4; j++) dst[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+                    for (int j = 0; j < NE2 / 4; j++) dst[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
                 } else {
-                    const int cc = nb - e.n_q;
+                    const int cc = nc - e.n_q;
                     bf * dst = (cc < e.dkv ? e.kdst + cc : e.vdst + (cc - e.dkv)) + (size_t)e.tok_slot[m] * e.dkv;
 #pragma unroll
-                    for (int j = 0; j < NE / 8; j++) {
-                        uint32_t w[4];
+                    for (int j = 0; j < NE2 / 4; j++) {
+                        uint32_t w[2];
 #pragma unroll
-                        for (int p = 0; p < 4; p++)
-                            w[p] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(y[8 * j + 2 * p])) |
-                                   ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(y[8 * j + 2 * p + 1])) << 16);
-                        reinterpret_cast<uint4 *>(dst)[j] = make_uint4(w[0], w[1], w[2], w[3]);
+                        for (int p = 0; p < 2; p++)
+                            w[p] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(y[4 * j + 2 * p])) |
+                                   ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(y[4 * j + 2 * p + 1])) << 16);
+                        reinterpret_cast<uint2 *>(dst)[j] = make_uint2(w[0], w[1]);
                     }
                 }
             } else if (EPI == TS_RES) {
-                const float4 * rs = reinterpret_cast<const float4 *>(e.res + (size_t)m * e.ldr + nb);
-                float4 r[NE / 4];
+                const float4 * rs = reinterpret_cast<const float4 *>(e.res + (size_t)m * e.ldr + nc);
+                float4 r[NE2 / 4];
 #pragma unroll
-                for (int j = 0; j < NE / 4; j++) r[j] = rs[j];
-                float4 * dst = reinterpret_cast<float4 *>(e.Y + (size_t)m * e.ldy + nb);
+                for (int j = 0; j < NE2 / 4; j++) r[j] = rs[j];
+                float4 * dst = reinterpret_cast<float4 *>(e.Y + (size_t)m * e.ldy + nc);
 #pragma unroll
-                for (int j = 0; j < NE / 4; j++) {
+                for (int j = 0; j < NE2 / 4; j++) {
                     y[4 * j] += r[j].x; y[4 * j + 1] += r[j].y; y[4 * j + 2] += r[j].z; y[4 * j + 3] += r[j].w;
                     dst[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
                 }
-                if (e.next_w) {                      // the next GEMM's operand: (y .* w) as hi | lo images + this slice's row statistics
+                if (e.next_w) {                      // the next GEMM's operand: (y .* w) as operand image(s) + this slice's row statistics
                     float s1 = 0.0f, s2 = 0.0f;
 #pragma unroll
-                    for (int j = 0; j < NE; j++) { s1 += y[j]; s2 = fmaf(y[j], y[j], s2); }
-                    *reinterpret_cast<float2 *>(e.stats_out + ((size_t)(SPLIT > 1 ? blockIdx.x * SPLIT + rank : blockIdx.x * (NC / NE) + half) * 64 + m) * 2) = make_float2(s1, s2);
+                    for (int j = 0; j < NE2; j++) { s1 += y[j]; s2 = fmaf(y[j], y[j], s2); }
+                    // (the row's two lanes: lower + upper half of the columns; both lanes of a pair are in this branch)
+                    const unsigned am = __activemask();
+                    const float o1 = __shfl_xor_sync(am, s1, 16), o2 = __shfl_xor_sync(am, s2, 16);
+                    if (lh == 0)
+                        *reinterpret_cast<float2 *>(e.stats_out + ((size_t)(SPLIT > 1 ? blockIdx.x * SPLIT + rank : blockIdx.x * (NC / NE) + half) * 64 + m) * 2) = make_float2(s1 + o1, s2 + o2);
 #pragma unroll
-                    for (int j = 0; j < NE / 8; j++) {
-                        uint32_t h[4], l[4];
+                    for (int j = 0; j < NE2 / 4; j++) {
+                        uint32_t h[2], l[2];
 #pragma unroll
-                        for (int p = 0; p < 4; p++)
-                            tc::pack_act2(y[8 * j + 2 * p] * e.next_w[nb + 8 * j + 2 * p], y[8 * j + 2 * p + 1] * e.next_w[nb + 8 * j + 2 * p + 1], e.pack_f16 != 0, h[p], l[p]);
-                        const int n = nb + 8 * j;
+                        for (int p = 0; p < 2; p++)
+                            tc::pack_act2(y[4 * j + 2 * p] * e.next_w[nc + 4 * j + 2 * p], y[4 * j + 2 * p + 1] * e.next_w[nc + 4 * j + 2 * p + 1], e.pack_f16 != 0, h[p], l[p]);
+                        const int n = nc + 4 * j;
                         const size_t off = (size_t)(n >> 6) * kXTile + tc::swz_offset(m, n & 63);
-                        *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(e.pk_hi) + off) = make_uint4(h[0], h[1], h[2], h[3]);
-                        if (!e.pack_f16) *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(e.pk_lo) + off) = make_uint4(l[0], l[1], l[2], l[3]);
+                        *reinterpret_cast<uint2 *>(reinterpret_cast<unsigned char *>(e.pk_hi) + off) = make_uint2(h[0], h[1]);
+                        if (!e.pack_f16) *reinterpret_cast<uint2 *>(reinterpret_cast<unsigned char *>(e.pk_lo) + off) = make_uint2(l[0], l[1]);
                     }
                 }
-            } else {                                 // GELU + hi | lo tile images for the next GEMM (k tile n / 64, 16-byte chunk (n % 64) / 8)
+            } else {                                 // GELU + operand image(s) for the next GEMM (k tile n / 64, 16-byte chunk (n % 64) / 8)
 #pragma unroll
-                for (int j = 0; j < NE / 8; j++) {
-                    uint32_t h[4], l[4];
+                for (int j = 0; j < NE2 / 4; j++) {
+                    uint32_t h[2], l[2];
 #pragma unroll
-                    for (int p = 0; p < 4; p++)
-                        tc::pack_act2(gelu_ggml_fast(y[8 * j + 2 * p], e.gelu_f16), gelu_ggml_fast(y[8 * j + 2 * p + 1], e.gelu_f16), e.pack_f16 != 0, h[p], l[p]);
-                    const int n = nb + 8 * j;
+                    for (int p = 0; p < 2; p++)
+                        tc::pack_act2(gelu_ggml_fast(y[4 * j + 2 * p], e.gelu_f16), gelu_ggml_fast(y[4 * j + 2 * p + 1], e.gelu_f16), e.pack_f16 != 0, h[p], l[p]);
+                    const int n = nc + 4 * j;
                     const size_t off = (size_t)(n >> 6) * kXTile + tc::swz_offset(m, n & 63);
-                    *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(e.pk_hi) + off) = make_uint4(h[0], h[1], h[2], h[3]);
-                    if (!e.pack_f16) *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(e.pk_lo) + off) = make_uint4(l[0], l[1], l[2], l[3]);
+                    *reinterpret_cast<uint2 *>(reinterpret_cast<unsigned char *>(e.pk_hi) + off) = make_uint2(h[0], h[1]);
+                    if (!e.pack_f16) *reinterpret_cast<uint2 *>(reinterpret_cast<unsigned char *>(e.pk_lo) + off) = make_uint2(l[0], l[1]);
                 }
             }
         }
