@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) ts_linear_kernel(const bf * Wt,
                     }
                 }
             }
-            if (EPI == TS_QKV) {
+            if constexpr (EPI == TS_QKV) {
                 if (e.ln_stats) {                    // LayerNorm folded through this GEMM: y = (acc - mean * csum[n]) * rstd
                     const float s1 = ((s_part[0][m].x + s_part[1][m].x) + s_part[2][m].x) + s_part[3][m].x;
                     const float s2 = ((s_part[0][m].y + s_part[1][m].y) + s_part[2][m].y) + s_part[3][m].y;
@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) ts_linear_kernel(const bf * Wt,
                         reinterpret_cast<uint2 *>(dst)[j] = make_uint2(w[0], w[1]);
                     }
                 }
-            } else if (EPI == TS_RES) {
+            } else if constexpr (EPI == TS_RES) {
                 const float4 * rs = reinterpret_cast<const float4 *>(e.res + (size_t)m * e.ldr + nc);
                 float4 r[NE2 / 4];
 #pragma unroll
@@ -311,29 +311,49 @@ __global__ void __launch_bounds__(kTsThreads, 1) ts_linear_kernel(const bf * Wt,
                     const float o1 = __shfl_xor_sync(am, s1, 16), o2 = __shfl_xor_sync(am, s2, 16);
                     if (lh == 0)
                         *reinterpret_cast<float2 *>(e.stats_out + ((size_t)(SPLIT > 1 ? blockIdx.x * SPLIT + rank : blockIdx.x * (NC / NE) + half) * 64 + m) * 2) = make_float2(s1 + o1, s2 + o2);
-#pragma unroll
-                    for (int j = 0; j < NE2 / 4; j++) {
+                    // operand image stores: a lane's row is 128 bytes away from its neighbour's, so nothing coalesces across the warp and an
+                    // 8-byte store leaves a quarter-written sector that the consuming GEMM's bulk copies then read slowly (its main loop:
+                    // 2.6 -> 3.7 us); the row's lower lane collects the pair's words and stores whole 16-byte chunks
+                    static_assert(NE2 == 4, "residual epilogue with a following operand image: 8 columns per lane pair");
+                    {
                         uint32_t h[2], l[2];
 #pragma unroll
                         for (int p = 0; p < 2; p++)
-                            tc::pack_act2(y[4 * j + 2 * p] * e.next_w[nc + 4 * j + 2 * p], y[4 * j + 2 * p + 1] * e.next_w[nc + 4 * j + 2 * p + 1], e.pack_f16 != 0, h[p], l[p]);
-                        const int n = nc + 4 * j;
-                        const size_t off = (size_t)(n >> 6) * kXTile + tc::swz_offset(m, n & 63);
-                        *reinterpret_cast<uint2 *>(reinterpret_cast<unsigned char *>(e.pk_hi) + off) = make_uint2(h[0], h[1]);
-                        if (!e.pack_f16) *reinterpret_cast<uint2 *>(reinterpret_cast<unsigned char *>(e.pk_lo) + off) = make_uint2(l[0], l[1]);
+                            tc::pack_act2(y[2 * p] * e.next_w[nc + 2 * p], y[2 * p + 1] * e.next_w[nc + 2 * p + 1], e.pack_f16 != 0, h[p], l[p]);
+                        const uint32_t h2 = __shfl_xor_sync(am, h[0], 16), h3 = __shfl_xor_sync(am, h[1], 16);
+                        const uint32_t l2 = __shfl_xor_sync(am, l[0], 16), l3 = __shfl_xor_sync(am, l[1], 16);
+                        if (lh == 0) {
+                            const size_t off = (size_t)(nb >> 6) * kXTile + tc::swz_offset(m, nb & 63);
+                            *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(e.pk_hi) + off) = make_uint4(h[0], h[1], h2, h3);
+                            if (!e.pack_f16) *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(e.pk_lo) + off) = make_uint4(l[0], l[1], l2, l3);
+                        }
                     }
                 }
             } else {                                 // GELU + operand image(s) for the next GEMM (k tile n / 64, 16-byte chunk (n % 64) / 8)
+                // (whole 32-byte sectors per store, see above: the pair's 16 columns are two 16-byte chunks whose swizzled places c ^ (m & 7)
+                //  and (c + 1) ^ (m & 7) share a sector, swapped when m is odd; the lower lane stores both)
+                static_assert(NE2 == 8, "GELU epilogue: 16 columns per lane pair");
+                {
+                    const unsigned am = __activemask();
+                    uint32_t h[4], l[4], hp[4], lp[4];
 #pragma unroll
-                for (int j = 0; j < NE2 / 4; j++) {
-                    uint32_t h[2], l[2];
+                    for (int p = 0; p < 4; p++)
+                        tc::pack_act2(gelu_ggml_fast(y[2 * p], e.gelu_f16), gelu_ggml_fast(y[2 * p + 1], e.gelu_f16), e.pack_f16 != 0, h[p], l[p]);
 #pragma unroll
-                    for (int p = 0; p < 2; p++)
-                        tc::pack_act2(gelu_ggml_fast(y[4 * j + 2 * p], e.gelu_f16), gelu_ggml_fast(y[4 * j + 2 * p + 1], e.gelu_f16), e.pack_f16 != 0, h[p], l[p]);
-                    const int n = nc + 4 * j;
-                    const size_t off = (size_t)(n >> 6) * kXTile + tc::swz_offset(m, n & 63);
-                    *reinterpret_cast<uint2 *>(reinterpret_cast<unsigned char *>(e.pk_hi) + off) = make_uint2(h[0], h[1]);
-                    if (!e.pack_f16) *reinterpret_cast<uint2 *>(reinterpret_cast<unsigned char *>(e.pk_lo) + off) = make_uint2(l[0], l[1]);
+                    for (int p = 0; p < 4; p++) { hp[p] = __shfl_xor_sync(am, h[p], 16); lp[p] = __shfl_xor_sync(am, l[p], 16); }
+                    if (lh == 0) {
+                        const int c = (nb & 63) >> 3, sw = m & 7;                      // chunk index of the pair's lower 8 columns (even)
+                        const size_t off = (size_t)(nb >> 6) * kXTile + (size_t)m * 128 + (size_t)(((c ^ sw) & 6) << 4);
+                        const bool swp = (sw & 1) != 0;                                // odd rows: the upper chunk comes first in the sector
+                        uint4 * dh = reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(e.pk_hi) + off);
+                        const uint4 a = make_uint4(h[0], h[1], h[2], h[3]), b = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+                        dh[0] = swp ? b : a; dh[1] = swp ? a : b;
+                        if (!e.pack_f16) {
+                            uint4 * dl = reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(e.pk_lo) + off);
+                            const uint4 a2 = make_uint4(l[0], l[1], l[2], l[3]), b2 = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+                            dl[0] = swp ? b2 : a2; dl[1] = swp ? a2 : b2;
+                        }
+                    }
                 }
             }
         }
