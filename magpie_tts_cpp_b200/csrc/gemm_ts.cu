@@ -57,13 +57,6 @@ template <> __device__ __forceinline__ void tmem_ld_cols<16>(uint32_t taddr, uin
                    "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]) : "r"(taddr) : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-template <> __device__ __forceinline__ void tmem_ld_cols<32>(uint32_t taddr, uint32_t (&v)[32]) { tc::tmem_ld32(taddr, v); }
-template <> __device__ __forceinline__ void tmem_ld_cols<64>(uint32_t taddr, uint32_t (&v)[64]) {
-    uint32_t a[32], b[32];
-    tc::tmem_ld32(taddr, a); tc::tmem_ld32(taddr + 32, b);
-#pragma unroll
-    for (int j = 0; j < 32; j++) { v[j] = a[j]; v[32 + j] = b[j]; }
-}
 
 // NC = weight rows (output features) per CTA.  SPLIT > 1 (wide K: the FFN's second GEMM, K = 3072): a cluster of SPLIT CTAs
 // (grid y) shares one slice of NC rows and divides the k tiles; at 64 tokens a CTA is bound by how fast its SM ingests the
@@ -97,6 +90,9 @@ __global__ void __launch_bounds__(kTsThreads, 1) ts_linear_kernel(const bf * Wt,
     constexpr int CR = NC / SPLIT;                                       // split-K: columns a rank finishes (reduce-scatter epilogue)
     constexpr int NE = SPLIT > 1 ? CR : NH;                              // columns per epilogue thread
     const int nb = n0 + (SPLIT > 1 ? CR * rank : c0);                    // first output feature of this thread
+    float4 pre0 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), pre1 = pre0;      // epilogue operands fetched ahead of the accumulator (see the epilogue warps)
+    int pre_slot = 0;
+    static_assert(NE == 8 || EPI == TS_GELU_PACK, "prefetched epilogue operands: 4 columns per lane");
     const int kt_lo = rank * KT_all / SPLIT, KT = (rank + 1) * KT_all / SPLIT - kt_lo;      // this CTA's k tiles [kt_lo, kt_lo + KT)
     float * xbuf = reinterpret_cast<float *>(tiles + kTsStages * kStage + 256);             // rank 0: [SPLIT - 1][64][NC] partial accumulators
     // every CTA reads the SAME activation tiles: with all of them walking k = 0, 1, 2, ... in lock step the 96-144 SMs would hit
@@ -193,6 +189,20 @@ __global__ void __launch_bounds__(kTsThreads, 1) ts_linear_kernel(const bf * Wt,
             s_part[part][m] = make_float2(s1, s2);
             asm volatile("bar.sync 1, 256;" ::: "memory");
         }
+        // the epilogue's global operands (folded-LayerNorm column sums / residual row, next LayerNorm weight, cache slot) are requested
+        // BEFORE the wait for the accumulator, so that their L2 round trip is behind the main loop instead of behind the last MMA
+        {
+            const int q_ = warp & 3, lh_ = lane >> 4, m_ = 16 * q_ + (lane & 15), nc_ = nb + lh_ * (NE / 2);
+            if ((SPLIT > 1 ? half == 0 : epi_on) && m_ < e.M && nb < e.N) {
+                if constexpr (EPI == TS_QKV) {
+                    if (e.ln_stats) pre0 = *reinterpret_cast<const float4 *>(e.ln_csum + nc_);
+                    if (nc_ >= e.n_q) pre_slot = e.tok_slot[m_];
+                } else if constexpr (EPI == TS_RES) {
+                    pre0 = *reinterpret_cast<const float4 *>(e.res + (size_t)m_ * e.ldr + nc_);
+                    if (e.next_w) pre1 = *reinterpret_cast<const float4 *>(e.next_w + nc_);
+                }
+            }
+        }
         tc::mbar_wait(acc_full, 0);
         if (dbg && threadIdx.x == 64) stamp(4);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -271,8 +281,9 @@ __global__ void __launch_bounds__(kTsThreads, 1) ts_linear_kernel(const bf * Wt,
                     const float s2 = ((s_part[0][m].y + s_part[1][m].y) + s_part[2][m].y) + s_part[3][m].y;
                     const float mean = s1 / (float)e.K, var = fmaxf(s2 / (float)e.K - mean * mean, 0.0f);
                     const float rstd = 1.0f / sqrtf(var + e.eps);
+                    const float cs[4] = {pre0.x, pre0.y, pre0.z, pre0.w};
 #pragma unroll
-                    for (int j = 0; j < NE2; j++) y[j] = (y[j] - mean * e.ln_csum[nc + j]) * rstd;
+                    for (int j = 0; j < NE2; j++) y[j] = (y[j] - mean * cs[j]) * rstd;
                 }
                 if (nc < e.n_q) {
                     float4 * dst = reinterpret_cast<float4 *>(e.Y + (size_t)m * e.ldy + nc);
@@ -280,7 +291,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) ts_linear_kernel(const bf * Wt,
                     for (int j = 0; j < NE2 / 4; j++) dst[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
                 } else {
                     const int cc = nc - e.n_q;
-                    bf * dst = (cc < e.dkv ? e.kdst + cc : e.vdst + (cc - e.dkv)) + (size_t)e.tok_slot[m] * e.dkv;
+                    bf * dst = (cc < e.dkv ? e.kdst + cc : e.vdst + (cc - e.dkv)) + (size_t)pre_slot * e.dkv;
 #pragma unroll
                     for (int j = 0; j < NE2 / 4; j++) {
                         uint32_t w[2];
@@ -292,10 +303,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) ts_linear_kernel(const bf * Wt,
                     }
                 }
             } else if constexpr (EPI == TS_RES) {
-                const float4 * rs = reinterpret_cast<const float4 *>(e.res + (size_t)m * e.ldr + nc);
-                float4 r[NE2 / 4];
-#pragma unroll
-                for (int j = 0; j < NE2 / 4; j++) r[j] = rs[j];
+                const float4 r[1] = {pre0};
                 float4 * dst = reinterpret_cast<float4 *>(e.Y + (size_t)m * e.ldy + nc);
 #pragma unroll
                 for (int j = 0; j < NE2 / 4; j++) {
@@ -319,7 +327,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) ts_linear_kernel(const bf * Wt,
                         uint32_t h[2], l[2];
 #pragma unroll
                         for (int p = 0; p < 2; p++)
-                            tc::pack_act2(y[2 * p] * e.next_w[nc + 2 * p], y[2 * p + 1] * e.next_w[nc + 2 * p + 1], e.pack_f16 != 0, h[p], l[p]);
+                            tc::pack_act2(y[2 * p] * (p ? pre1.z : pre1.x), y[2 * p + 1] * (p ? pre1.w : pre1.y), e.pack_f16 != 0, h[p], l[p]);
                         const uint32_t h2 = __shfl_xor_sync(am, h[0], 16), h3 = __shfl_xor_sync(am, h[1], 16);
                         const uint32_t l2 = __shfl_xor_sync(am, l[0], 16), l3 = __shfl_xor_sync(am, l[1], 16);
                         if (lh == 0) {
@@ -475,9 +483,7 @@ bool launch_linear_ts(const LinearArgs & a, const void * hi, const void * lo, cu
     const int shaped = ts_shape();
     const bf * h = (const bf *)hi, * l = (const bf *)lo;
     if (a.n_q >= 0) {
-        static const int qkv_nc = getenv("MGB_TS_QKV_NC") ? atoi(getenv("MGB_TS_QKV_NC")) : 16;
-        if (qkv_nc == 32 && a.W.N % 32 == 0 && a.n_q % 32 == 0 && a.dkv % 32 == 0) return launch_ts<32, TS_QKV>(W, h, l, KT, e, stream);
-        if (qkv_nc == 8) return launch_ts<8, TS_QKV>(W, h, l, KT, e, stream);
+        // (16 rows per CTA = 144 CTAs; measured: 32 rows / 72 CTAs the same within 1 %, 8 rows / 288 CTAs = two waves, -11 %)
         return launch_ts<16, TS_QKV>(W, h, l, KT, e, stream);
     }
     if (a.res) {
