@@ -506,6 +506,8 @@ __global__ void __launch_bounds__(kLtThreads, 1) lt_cluster_kernel(const ClParam
                 }
                 __syncwarp();
             }
+            const int id = out_r0 + 32 * wq + lane;
+            const float bias = id < V ? p.out_b[cb][id] : 0.0f;      // (requested before the wait: off the dependent chain)
             mbar_wait(&S.mbar[3], mma_par); mma_par ^= 1u;
             tc_after_sync();
             if (cp.dbg_fine) stamp();
@@ -517,9 +519,7 @@ __global__ void __launch_bounds__(kLtThreads, 1) lt_cluster_kernel(const ClParam
                 vl[j] = u < U ? tmem_ld1(tmem + ((uint32_t)(32 * wq) << 16) + (uint32_t)(112 + u)) : 0.0f;
             }
             tmem_ld_wait();
-            const int id = out_r0 + 32 * wq + lane;
             if (id < V) {
-                const float bias = p.out_b[cb][id];
 #pragma unroll
                 for (int j = 0; j < 3; j++) { const int u = wg + 4 * j; if (u < U) dsmem_st(&S.logits[id], u, (v[j] + vl[j]) + bias); }
             }
@@ -539,6 +539,13 @@ __global__ void __launch_bounds__(kLtThreads, 1) lt_cluster_kernel(const ClParam
                 if (id >= 0 && id < V) S.logits[id] = -INFINITY;
             }
             __syncthreads();
+            // teacher forcing: the code fed to the next position is known, so its table rows are requested ahead of the argmax / sampler
+            float g_seq = 0.0f, g_q = 0.0f, g_k = 0.0f, g_v = 0.0f;
+            if (forced && cb < 7 && tid < L) {
+                const int fed = forced[cb];
+                const float * row = cp.qkv_tab + ((size_t)cb * V + fed) * (3 * L);
+                g_seq = p.in_table[cb][(size_t)fed * L + tid]; g_q = row[tid]; g_k = row[L + tid]; g_v = row[2 * L + tid];
+            }
             if (p.logits)
                 for (int i = tid; i < V; i += kLtThreads) p.logits[(my_row * 8 + cb) * V + i] = S.logits[i];
             const int am = block_argmax(S.logits, V, S.red, S.redi);
@@ -571,11 +578,14 @@ __global__ void __launch_bounds__(kLtThreads, 1) lt_cluster_kernel(const ClParam
                 // seq[cb+1] = in_proj . E_cb[code] + b and its [q | k | vo] row, both tabulated at load (model.cu); no 1/8 scale (magpie.cpp:1285-1291)
                 const int fed = forced ? forced[cb] : pick;
                 if (tid < L) {
-                    const float * row = cp.qkv_tab + ((size_t)cb * V + fed) * (3 * L);
-                    S.seq[tid] = p.in_table[cb][(size_t)fed * L + tid];
-                    S.q[tid] = row[tid];
-                    S.kc[cb + 1][tid] = row[L + tid];
-                    S.vc[cb + 1][tid] = row[2 * L + tid];
+                    if (!forced) {
+                        const float * row = cp.qkv_tab + ((size_t)cb * V + fed) * (3 * L);
+                        g_seq = p.in_table[cb][(size_t)fed * L + tid]; g_q = row[tid]; g_k = row[L + tid]; g_v = row[2 * L + tid];
+                    }
+                    S.seq[tid] = g_seq;
+                    S.q[tid] = g_q;
+                    S.kc[cb + 1][tid] = g_k;
+                    S.vc[cb + 1][tid] = g_v;
                 }
                 __syncthreads();
                 if (warp <= cb + 1) {
