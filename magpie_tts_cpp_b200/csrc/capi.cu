@@ -848,6 +848,7 @@ static int run_loop_persistent(Session & s, const LoopCfg & c, int * steps_run) 
     p.result = s.d_result; p.xbuf = s.d_xbuf; memcpy(p.xoff, s.xoff, sizeof(p.xoff)); p.seq = s.d_seq; p.dbg = s.d_loop_dbg;
     p.dbg_flags = getenv("MGB_LOOP_FLAGS") ? atoi(getenv("MGB_LOOP_FLAGS")) : 0;
     p.max_split = getenv("MGB_LOOP_MAXSPLIT") ? std::max(1, std::min(6, atoi(getenv("MGB_LOOP_MAXSPLIT")))) : 6;
+    p.no_defer_amax = getenv("MGB_LOOP_NO_DEFER") != nullptr ? 1 : 0;
     const int64_t l0 = g_launch_counter;
     cudaEventRecord(s.ev0, st);
     if (!launch_frame_loop(p, s.loop_grid, st)) return MGB_ECUDA;

@@ -39,6 +39,7 @@ constexpr int kThreads = 512, kCW = 15, kCT = kCW * 32;      // warp 15 = weight
 constexpr int kR = 4;                                        // exchange replicas
 constexpr int kQD = 8;                                       // ring slots
 constexpr int kRingBytes = 112 * 1024;
+constexpr int kAmaxSlots = 160;          // argmax packets of one codebook (one per producing CTA)
 constexpr int D = 768, F = 3072, H = 12, DH = 64, LD = 256, LF = 1024;
 constexpr int kMaxSplit = 6;
 // rows per CTA (multiples of 3 = one packet)
@@ -1075,6 +1076,8 @@ __global__ void __launch_bounds__(kThreads, 1) frame_loop_kernel(const FrameLoop
             c.seq++;
         }
         float fb[3] = {0.0f, 0.0f, 0.0f};     // feedback row elements 3i .. 3i+2 for the next codebook
+        unsigned amax_seq0 = 0u, amax_seq1 = 0u;   // exchange numbers of the two argmax regions
+        const bool defer_amax = p.forced != nullptr && !sampling && !p.no_defer_amax;
         int fed_prev = 0;                      // code fed back by the previous codebook
 #pragma unroll 1
         for (int cb = 0; cb < 8; cb++) {
@@ -1204,13 +1207,58 @@ __global__ void __launch_bounds__(kThreads, 1) frame_loop_kernel(const FrameLoop
                             const float ov = __shfl_xor_sync(0xffffffffu, bv, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
                             if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
                         }
-                        if (lane < kR) st_pkt(p.xbuf + (size_t)lane * c.rstride + p.xoff[T_AMAX] + b, bv, __int_as_float(bi), 0.0f, c.seq);
+                        if (lane < kR) st_pkt(p.xbuf + (size_t)lane * c.rstride + p.xoff[T_AMAX] + (defer_amax ? (cb & 1) * kAmaxSlots : 0) + b, bv, __int_as_float(bi), 0.0f, c.seq);
                     }
                 }
+                if (cb & 1) amax_seq1 = c.seq; else amax_seq0 = c.seq;
                 c.seq++;
             }
             LOOP_STAMP();
             // ---- F: global argmax / top-k sample; feedback ---------------------------------------------------------------
+            // Teacher forcing + greedy (BASELINE config 2): the code fed back is known, so nothing downstream waits for the argmax of
+            // this codebook.  Its packets (own region per codebook parity) are collected one codebook LATER, when they have long
+            // arrived, which takes this exchange's wait off the chain for codebooks 0..6; codebook 7 collects 6 and 7.  (A region is
+            // rewritten two codebooks later, after every CTA has emitted FF1 of the codebook in between, i.e. after its collection.)
+            auto collect_amax = [&](int cbx) -> int {
+                const int nprod = (V + ROUT - 1) / ROUT;
+                float bv = -INFINITY; int bi = 0x7fffffff;
+                if (ctid < nprod) {
+                    const uint4 v = poll_pkt(c.xin + p.xoff[T_AMAX] + (cbx & 1) * kAmaxSlots + ctid, (cbx & 1) ? amax_seq1 : amax_seq0);
+                    bv = __uint_as_float(v.x); bi = (int)v.y;
+                    if (c_poll_mask == 0u) bi = min(max(bi, 0), V - 1);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float ov = __shfl_xor_sync(0xffffffffu, bv, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                    if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+                }
+                if (lane == 0) { S.red[cw] = bv; S.redi[cw] = bi; }
+                cbar();
+                bv = S.red[0]; bi = S.redi[0];
+                for (int w = 1; w < kCW; w++) if (better(S.red[w], S.redi[w], bv, bi)) { bv = S.red[w]; bi = S.redi[w]; }
+                cbar();
+                return bi;
+            };
+            if (defer_amax) {
+                const int fedd = p.forced[row * 8 + cb];
+                for (int cbx = (cb == 0 ? 1 : cb - 1); cbx <= (cb == 7 ? 7 : cb - 1); cbx++) {      // cb 0: none; cb 1..6: cb - 1; cb 7: 6 and 7
+                    const int amx = collect_amax(cbx);
+                    hit_eos = hit_eos || amx == p.eos_id;
+                    if (b == 0 && ctid == 0) { p.argmax[row * 8 + cbx] = amx; p.sampled[row * 8 + cbx] = amx; }
+                }
+                if (b == 0 && ctid == 0) p.result[2 + cb] = fedd;
+                fed_prev = fedd;
+                if (cb < 7 && own3l) {
+#pragma unroll
+                    for (int q = 0; q < 3; q++) if (3 * ctid + q < LD) fb[q] = __ldg(p.lt_in_table[cb] + (size_t)fedd * LD + 3 * ctid + q);
+                }
+                if (own3) {
+#pragma unroll
+                    for (int q = 0; q < 3; q++) { const float a = __ldg(p.audio_emb[cb] + (size_t)fedd * D + 3 * ctid + q); emb[q] = cb == 0 ? a : emb[q] + a; }
+                }
+                LOOP_STAMP(); LOOP_STAMP();
+                continue;
+            }
             int am, pick;
             if (!sampling) {
                 const int nprod = (V + ROUT - 1) / ROUT;
@@ -1309,7 +1357,7 @@ bool frame_loop_shape_ok(int d, int f, int h, int ld, int lf, int V, int L) {
 
 void frame_loop_xchg_layout(int V, int * xoff) {
     const int n[X_COUNT] = {3 * D / 3, H * kMaxSplit * 22, D / 3, D / 3, F / 3, D / 3, (LD + 2) / 3, (LQ + 2) / 3, (LD + 2) / 3, (LF + 2) / 3,
-                            (LD + 2) / 3, 160, (V + 2) / 3 + 8};
+                            (LD + 2) / 3, 2 * kAmaxSlots, (V + 2) / 3 + 8};      // (T_AMAX: two regions, see the deferred argmax in the LT)
     int o = 0;
     for (int i = 0; i < X_COUNT; i++) { xoff[i] = o; o += (n[i] + 7) & ~7; }     // 128-byte aligned starts
     xoff[X_COUNT] = o;

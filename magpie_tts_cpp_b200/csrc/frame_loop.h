@@ -51,6 +51,7 @@ struct FrameLoopParams {
     unsigned long long * dbg;            // optional: globaltimer stamps of CTA 0 for the last frame
     int dbg_flags;                       // profiling aids, see frame_loop.cu (0 in production)
     int max_split;                       // key splits per head, 1..6 (6 in production; smaller values exercise the multi-round scan in tests)
+    int no_defer_amax;                   // 1 (MGB_LOOP_NO_DEFER): teacher forcing collects every codebook's argmax at once, as free-running generation must (A/B)
 };
 
 bool   frame_loop_shape_ok(int d, int f, int H, int ld, int lf, int V, int L);
