@@ -1077,6 +1077,7 @@ __global__ void __launch_bounds__(kThreads, 1) frame_loop_kernel(const FrameLoop
         }
         float fb[3] = {0.0f, 0.0f, 0.0f};     // feedback row elements 3i .. 3i+2 for the next codebook
         unsigned amax_seq0 = 0u, amax_seq1 = 0u;   // exchange numbers of the two argmax regions
+        float4 row_pf = make_float4(0.0f, 0.0f, 0.0f, 0.0f); bool have_row_pf = false;      // (teacher forcing: next position's table row, see E)
         const bool defer_amax = p.forced != nullptr && !sampling && !p.no_defer_amax;
         int fed_prev = 0;                      // code fed back by the previous codebook
 #pragma unroll 1
@@ -1113,7 +1114,7 @@ __global__ void __launch_bounds__(kThreads, 1) frame_loop_kernel(const FrameLoop
                 } else {
                     const float4 * row = reinterpret_cast<const float4 *>(p.lt_qkv_tab + ((size_t)(cb - 1) * V + fed_prev) * (3 * LD));
                     if (ctid < 3 * LD / 4) {
-                        const float4 f = __ldg(row + ctid);
+                        const float4 f = have_row_pf ? row_pf : __ldg(row + ctid);
                         S.vec[4 * ctid] = f.x; S.vec[4 * ctid + 1] = f.y; S.vec[4 * ctid + 2] = f.z; S.vec[4 * ctid + 3] = f.w;
                     }
                     if (ctid < LD) S.vec[3 * LD + ctid] = 0.0f;       // no separate lo part: the table holds hi + lo
@@ -1175,6 +1176,24 @@ __global__ void __launch_bounds__(kThreads, 1) frame_loop_kernel(const FrameLoop
             }
             LOOP_STAMP();
             // ---- E: output projection of codebook cb (+bias, forbidden-token mask); local argmax ---------------------
+            // (teacher forcing: the code fed to position cb + 1 is known, so its feedback row, its [q | k | vo] table row and the next
+            //  frame's embedding rows are requested HERE, ahead of the wait for FFN2, instead of on the chain after the argmax)
+            float4 pf_row = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            float pf_fb[3] = {0.0f, 0.0f, 0.0f}, pf_emb[3] = {0.0f, 0.0f, 0.0f};
+            if (defer_amax) {
+                const int fedn = p.forced[row * 8 + cb];
+                if (cb < 7) {
+                    if (ctid < 3 * LD / 4) pf_row = __ldg(reinterpret_cast<const float4 *>(p.lt_qkv_tab + ((size_t)cb * V + fedn) * (3 * LD)) + ctid);
+                    if (own3l) {
+#pragma unroll
+                        for (int q = 0; q < 3; q++) if (3 * ctid + q < LD) pf_fb[q] = __ldg(p.lt_in_table[cb] + (size_t)fedn * LD + 3 * ctid + q);
+                    }
+                }
+                if (own3) {
+#pragma unroll
+                    for (int q = 0; q < 3; q++) pf_emb[q] = __ldg(p.audio_emb[cb] + (size_t)fedn * D + 3 * ctid + q);
+                }
+            }
             {
                 poll_vec(c.xin + p.xoff[T_HOUT], (LD + 2) / 3, c.seq - 1, S.lhout, LD, ctid);
                 cbar();
@@ -1250,12 +1269,13 @@ __global__ void __launch_bounds__(kThreads, 1) frame_loop_kernel(const FrameLoop
                 fed_prev = fedd;
                 if (cb < 7 && own3l) {
 #pragma unroll
-                    for (int q = 0; q < 3; q++) if (3 * ctid + q < LD) fb[q] = __ldg(p.lt_in_table[cb] + (size_t)fedd * LD + 3 * ctid + q);
+                    for (int q = 0; q < 3; q++) fb[q] = pf_fb[q];
                 }
                 if (own3) {
 #pragma unroll
-                    for (int q = 0; q < 3; q++) { const float a = __ldg(p.audio_emb[cb] + (size_t)fedd * D + 3 * ctid + q); emb[q] = cb == 0 ? a : emb[q] + a; }
+                    for (int q = 0; q < 3; q++) emb[q] = cb == 0 ? pf_emb[q] : emb[q] + pf_emb[q];
                 }
+                row_pf = pf_row; have_row_pf = true;
                 LOOP_STAMP(); LOOP_STAMP();
                 continue;
             }
