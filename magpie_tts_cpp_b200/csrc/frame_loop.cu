@@ -1199,6 +1199,7 @@ __global__ void __launch_bounds__(kThreads, 1) frame_loop_kernel(const FrameLoop
                 cbar();
                 LOOP_STAMP();
                 const int r0 = b * ROUT, nr = max(0, min(ROUT, V - r0));
+                const float obias = (cw == 0 && lane < nr) ? __ldg(p.lt_out_b[cb] + r0 + lane) : 0.0f;      // (requested ahead of the GEMV)
                 if (nr > 0) {
                     const bf * w = ring_wait(S, c);
                     gemv_rows<1, 1>(w, nr, S.lhout, S.part, c);
@@ -1209,7 +1210,7 @@ __global__ void __launch_bounds__(kThreads, 1) frame_loop_kernel(const FrameLoop
                     float v = -INFINITY;
                     if (lane < nr) {
                         const int n = r0 + lane;
-                        v = S.part[lane * kPartStride] + __ldg(p.lt_out_b[cb] + n);
+                        v = S.part[lane * kPartStride] + obias;
                         const bool masked = n == p.bos_id || (n >= p.bos_id + 2 && n <= p.bos_id + 7) || (forbid_eos && n == p.eos_id);
                         if (masked) v = -INFINITY;                                // magpie.cpp:1131-1145, 1243-1248
                         if (p.logits) p.logits[(row * 8 + cb) * V + n] = v;
