@@ -206,12 +206,16 @@ static bool decoder_layers(Session & s, Tokens tok, bool want_hidden) {
         const bool step = M == s.B && tok.utt == s.dec_utt;
         const bool chain = step && M <= 64 && s.tc_scratch2 && tc_linear_supported(f1) && tc_linear_supported(f2) && hp.d_ffn % 64 == 0 &&
                            getenv("MGB_NO_CHAIN") == nullptr;
+        // (the folded cross-attention then emits x .* norm_ff + 4 statistics slices and FF1's epilogue applies the LayerNorm: no second cluster barrier)
+        const bool ff1_fold = chain && !skip && s.ln_fold && s.ln_stats && L.ff1_csum && getenv("MGB_NO_TS") == nullptr;
         if (s.fold_ready && step) {
             const size_t tab = (size_t)s.B * s.max_text * d;
             const bool pk = chain;
             if (!(skip & 1) && !launch_xattn_folded(s.x, L.norm_xa_q, hp.eps, s.fold_xm + l * tab, s.fold_xn + l * tab, s.d_ntext, s.B, d, s.max_text,
-                                                    pk ? L.norm_ff : nullptr, pk ? s.tc_scratch : nullptr, s.stream, pk && f16a)) return false;
+                                                    pk ? L.norm_ff : nullptr, pk ? s.tc_scratch : nullptr, s.stream, pk && f16a,
+                                                    (pk && ff1_fold) ? s.ln_stats + (size_t)96 * 64 * 2 : nullptr)) return false;
             if (pk) { f1.x_prepacked = true; f1.act_f16 = f16a; }
+            if (pk && ff1_fold) { f1.ln_fold_stats = s.ln_stats + (size_t)96 * 64 * 2; f1.ln_fold_slices = 4; f1.ln_fold_csum = L.ff1_csum; }
         } else {
         LinearArgs q;
         q.tc_scratch = s.tc_scratch; q.tc_scratch_bytes = s.tc_scratch_bytes;
@@ -423,7 +427,7 @@ mgb_session * mgb_session_new_paged(mgb_model * mm, int batch, int max_text, int
         char * tp2 = nullptr;
         if (!s->alloc(tp2, tb)) return nullptr;
         s->tc_scratch2 = tp2;
-        if (!s->alloc(s->ln_stats, (size_t)96 * 64 * 2)) return nullptr;
+        if (!s->alloc(s->ln_stats, (size_t)2 * 96 * 64 * 2)) return nullptr;      // [FF2 -> QKV: <= 96 slices | cross-attention -> FF1: 4 slices]
         s->ln_fold = getenv("MGB_NO_LNFOLD") == nullptr;
         s->act_f16 = m->dec[0].qkv.tiles16 != nullptr;             // (MGB_ACT_F16 at model load)
     }

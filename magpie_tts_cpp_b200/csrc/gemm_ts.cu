@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) ts_linear_kernel(const bf * Wt,
     }
     if (warp >= 2) {
         asm volatile("griddepcontrol.wait;" ::: "memory");
-        if (EPI == TS_QKV && e.ln_stats) {
+        if ((EPI == TS_QKV || EPI == TS_GELU_PACK) && e.ln_stats) {
             // LayerNorm folded through this GEMM: while the MMAs run, the 256 epilogue threads add the row statistics of the e.ln_slices column
             // slices the preceding FF2 wrote: 4 threads per row, a contiguous quarter of the slices each (fixed order: deterministic)
             const int t = (int)threadIdx.x - 64, m = t & 63, part = t >> 6, per = (e.ln_slices + 3) >> 2;
@@ -200,6 +200,8 @@ __global__ void __launch_bounds__(kTsThreads, 1) ts_linear_kernel(const bf * Wt,
                 } else if constexpr (EPI == TS_RES) {
                     pre0 = *reinterpret_cast<const float4 *>(e.res + (size_t)m_ * e.ldr + nc_);
                     if (e.next_w) pre1 = *reinterpret_cast<const float4 *>(e.next_w + nc_);
+                } else {
+                    if (e.ln_stats) { pre0 = *reinterpret_cast<const float4 *>(e.ln_csum + nc_); pre1 = *reinterpret_cast<const float4 *>(e.ln_csum + nc_ + 4); }
                 }
             }
         }
@@ -341,6 +343,15 @@ __global__ void __launch_bounds__(kTsThreads, 1) ts_linear_kernel(const bf * Wt,
                 // (whole 32-byte sectors per store, see above: the pair's 16 columns are two 16-byte chunks whose swizzled places c ^ (m & 7)
                 //  and (c + 1) ^ (m & 7) share a sector, swapped when m is odd; the lower lane stores both)
                 static_assert(NE2 == 8, "GELU epilogue: 16 columns per lane pair");
+                if (e.ln_stats) {                    // LayerNorm folded through this GEMM (the folded cross-attention emitted x .* w + statistics)
+                    const float s1 = ((s_part[0][m].x + s_part[1][m].x) + s_part[2][m].x) + s_part[3][m].x;
+                    const float s2 = ((s_part[0][m].y + s_part[1][m].y) + s_part[2][m].y) + s_part[3][m].y;
+                    const float mean = s1 / (float)e.K, var = fmaxf(s2 / (float)e.K - mean * mean, 0.0f);
+                    const float rstd = 1.0f / sqrtf(var + e.eps);
+                    const float cs[8] = {pre0.x, pre0.y, pre0.z, pre0.w, pre1.x, pre1.y, pre1.z, pre1.w};
+#pragma unroll
+                    for (int j = 0; j < NE2; j++) y[j] = (y[j] - mean * cs[j]) * rstd;
+                }
                 {
                     const unsigned am = __activemask();
                     uint32_t h[4], l[4], hp[4], lp[4];
@@ -430,7 +441,7 @@ bool launch_row_dots(const void * W, const float * v, int N, int K, float * out,
 bool ts_linear_supported(const LinearArgs & a) {
     if (getenv("MGB_NO_TS") != nullptr) return false;
     if (a.M > 64 || a.W.taps != 1 || a.W.K % 64 != 0 || a.bias || a.W.N % 128 != 0) return false;
-    if (a.ln_fold_stats && (!a.x_prepacked || !a.ln_fold_csum || a.ln_fold_slices <= 0 || a.n_q < 0)) return false;
+    if (a.ln_fold_stats && (!a.x_prepacked || !a.ln_fold_csum || a.ln_fold_slices <= 0 || (a.n_q < 0 && !(a.act == ACT_GELU && a.pack_out)))) return false;
     const bool qkv = a.n_q >= 0 && !a.res && a.act == ACT_NONE && !a.pack_out && a.Y && a.n_q % 16 == 0 && a.dkv % 16 == 0 && a.kdst && a.vdst && (a.ldy % 4) == 0;
     const bool resid = a.n_q < 0 && a.res && a.act == ACT_NONE && a.Y && (a.ldr % 4) == 0 && (a.ldy % 4) == 0 &&
                        (a.pack_out ? (a.next_ln_w && a.stats_out && a.W.N % 64 == 0) : !a.next_ln_w);

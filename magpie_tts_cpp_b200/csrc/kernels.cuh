@@ -85,7 +85,8 @@ int attention_plan_kv_split(int items, int max_keys);   // cluster size for a de
 // batched decoder step: folded cross-attention x += softmax(M LN(x)) N (tables from launch_xattn_fold, frame_loop.cu)
 // pack_ln_w / pack_out (optional, B <= 64): additionally emit LN(x_new; pack_ln_w) as hi | lo tile images for the next GEMM
 bool launch_xattn_folded(float * x, const float * ln_w, float eps, const float * xm, const float * xn, const int32_t * n_ctx, int B, int d,
-                         int max_text, const float * pack_ln_w, void * pack_out, cudaStream_t stream, bool pack_f16 = false);
+                         int max_text, const float * pack_ln_w, void * pack_out, cudaStream_t stream, bool pack_f16 = false,
+                         float * fold_stats = nullptr);      // fold_stats: LayerNorm folded through the consumer GEMM (LinearArgs::ln_fold_*), 4 slices
 
 // x[t] = (sum_cb E_cb[codes[utt][cb]]) * 1/8 + dec_pos[pos]        (magpie.cpp:2746-2787, 4376-4379)
 bool launch_audio_embed(const Model & m, const int32_t * codes /*[B][8] device*/, const int32_t * pos /*[B]*/,

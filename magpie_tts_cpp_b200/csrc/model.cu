@@ -325,6 +325,13 @@ Model * load_model(const char * path, int device, int precision) {
             M->allocations.push_back(c);
             if (!launch_row_dots(L.qkv.w, L.norm_self, L.qkv.N, L.qkv.K, (float *)c, nullptr)) return nullptr;
             L.qkv_csum = (float *)c;
+            void * c1 = nullptr;
+            if (L.ff1.taps == 1) {
+                if (cudaMalloc(&c1, (size_t)L.ff1.N * sizeof(float)) != cudaSuccess) { set_error("cudaMalloc failed"); return nullptr; }
+                M->allocations.push_back(c1);
+                if (!launch_row_dots(L.ff1.w, L.norm_ff, L.ff1.N, L.ff1.K, (float *)c1, nullptr)) return nullptr;
+                L.ff1_csum = (float *)c1;
+            }
         }
         if (cudaDeviceSynchronize() != cudaSuccess) { set_error("magpie_init: packing the weight tiles failed"); return nullptr; }
     }

@@ -27,6 +27,7 @@ struct DecLayer {
     float * norm_self = nullptr, * norm_xa_q = nullptr, * norm_xa_mem = nullptr, * norm_ff = nullptr;
     DevMat qkv, o, xq, xkv, xo, ff1, ff2;
     float * qkv_csum = nullptr;             // bf16 models: csum[n] = sum_k Wqkv[n][k] norm_self[k] (LayerNorm folded through the QKV GEMM, kernels.cuh)
+    float * ff1_csum = nullptr;             // same for W1 with norm_ff (LayerNorm folded through the FFN's first GEMM)
 };
 
 struct Model {

@@ -705,7 +705,8 @@ bool launch_attention(const AttnArgs & a, cudaStream_t stream) {
 // prefill (frame_loop.cu xattn_fold_kernel): the reference's q_net GEMV, 1-head attention over E text tokens and o_net GEMV
 // (magpie.cpp:1713-1767, 3513) in ONE launch instead of five.  One CTA per utterance, 512 threads.
 struct XFoldParams { float * x; const float * ln_w; float eps; const float * xm; const float * xn; const int32_t * n_ctx; int d, max_text;
-                     const float * pack_ln_w; __nv_bfloat16 * pk_hi; __nv_bfloat16 * pk_lo; int pk_f16; };
+                     const float * pack_ln_w; __nv_bfloat16 * pk_hi; __nv_bfloat16 * pk_lo; int pk_f16;
+                     float * fold_stats; };       // non-null: emit (x_new .* pack_ln_w) + this rank's (sum, sum of squares) [kXC][64][2] instead of LN(x_new) (kernels.cuh)
 // One CLUSTER of kXC CTAs per utterance; CTA rank r owns the d / kXC columns [r * dc, (r + 1) * dc) of the row, i.e. a
 // quarter of both tables: partial scores and the LayerNorm statistics of the updated row are exchanged through DSMEM.
 constexpr int kXC = 4, kXT = 256;
@@ -829,6 +830,31 @@ __global__ void __launch_bounds__(kXT) xattn_folded_kernel(const XFoldParams p) 
         xr[c0 + tid] = v;
     }
     if (!p.pk_hi) { cluster_sync_all(); return; }         // (no CTA may exit while a peer can still write into its shared memory)
+    if (p.fold_stats) {
+        // LayerNorm folded through the following GEMM: no statistics exchange, no second cluster barrier -- this rank's columns of
+        // (x_new .* w) go out as they are, with the rank's partial (sum, sum of squares) of the row for the GEMM's epilogue
+        const float pwf = tid < dc ? p.pack_ln_w[c0 + tid] : 0.0f;
+        float ps = warp_sum(tid < dc ? v : 0.0f), pq = warp_sum(tid < dc ? v * v : 0.0f);
+        __syncthreads();                                  // (red is reused)
+        if (lane == 0) { red[0][warp] = ps; red[1][warp] = pq; }
+        if (tid < dc) xl[tid] = v * pwf;
+        __syncthreads();
+        if (tid == 0) {
+            const float * a = red[0], * b = red[1];
+            *reinterpret_cast<float2 *>(p.fold_stats + ((size_t)rank * 64 + u) * 2) =
+                make_float2(((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7])), ((b[0] + b[1]) + (b[2] + b[3])) + ((b[4] + b[5]) + (b[6] + b[7])));
+        }
+        for (int kc = tid; kc < dc / 8; kc += kXT) {
+            uint32_t h[4], l[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) tc::pack_act2(xl[kc * 8 + 2 * q], xl[kc * 8 + 2 * q + 1], p.pk_f16 != 0, h[q], l[q]);
+            const int kg = (c0 >> 3) + kc;
+            const size_t off = (size_t)(kg / 8) * (64 * 128) + (size_t)u * 128 + ((((kg % 8) ^ (u & 7)) & 7) << 4);
+            *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(p.pk_hi) + off) = make_uint4(h[0], h[1], h[2], h[3]);
+            if (!p.pk_f16) *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(p.pk_lo) + off) = make_uint4(l[0], l[1], l[2], l[3]);
+        }
+        return;
+    }
     // LayerNorm of the updated row with the NEXT sub-block's weight -> bf16 hi | lo tile images (gemm_tc.cu layout, one
     // 64-token tile): the packing kernel in front of the FFN's first GEMM is not needed
     const float pw = tid < dc ? p.pack_ln_w[c0 + tid] : 0.0f;
@@ -859,12 +885,12 @@ __global__ void __launch_bounds__(kXT) xattn_folded_kernel(const XFoldParams p) 
 }
 
 bool launch_xattn_folded(float * x, const float * ln_w, float eps, const float * xm, const float * xn, const int32_t * n_ctx, int B, int d,
-                         int max_text, const float * pack_ln_w, void * pack_out, cudaStream_t stream, bool pack_f16) {
+                         int max_text, const float * pack_ln_w, void * pack_out, cudaStream_t stream, bool pack_f16, float * fold_stats) {
     // (columns per rank: <= 256 with whole float4 / 64-column groups, at most 3 float2 per lane and row, 5 x dc / 4 <= 256 threads)
     if (d > 768 || max_text > 512 || d % (kXC * 64) != 0 || kXRG * (d / kXC / 4) > kXT) { set_error("xattn_folded: shape not supported"); return false; }
     if (pack_out && B > 64) { set_error("xattn_folded: packed output needs one token tile"); return false; }
     XFoldParams p{x, ln_w, eps, xm, xn, n_ctx, d, max_text, pack_ln_w, (__nv_bfloat16 *)pack_out,
-                  pack_out ? (__nv_bfloat16 *)pack_out + (size_t)64 * d : nullptr, pack_f16 ? 1 : 0};
+                  pack_out ? (__nv_bfloat16 *)pack_out + (size_t)64 * d : nullptr, pack_f16 ? 1 : 0, pack_out ? fold_stats : nullptr};
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(B * kXC); cfg.blockDim = dim3(kXT); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
     cudaLaunchAttribute at[2];

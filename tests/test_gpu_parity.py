@@ -450,9 +450,10 @@ def test_tensor_core_linear_matches_cuda_core_kernels(B, full_model_path, full_o
 
 def test_batched_step_chain_modes_agree(B, full_model_path, full_oracle, monkeypatch):
     """bf16, 24 utterances x 6 teacher-forced steps: the default chain of the batched decoder step (ONE f16 activation image per GEMM
-    operand against f16 twins of the bf16 weight images; LayerNorm folded through the QKV GEMM: FF2 emits `x .* w` + row statistics)
+    operand against f16 twins of the bf16 weight images; LayerNorms folded through the QKV and FF1 GEMMs: FF2 / the folded cross-attention
+    emit `x .* w` + row statistics)
     against (a) bf16 hi + lo image pairs (MGB_ACT_F16=0 at model load: f32-accurate activations), (b) the LayerNorm + pack launch in
-    front of every QKV GEMM (MGB_NO_LNFOLD=1 at session creation), and against the oracle.  f16 activations round at 2^-12 relative,
+    front of every QKV GEMM (MGB_NO_LNFOLD=1 at session creation: LayerNorm + pack launches, statistics exchange in the cross-attention kernel), and against the oracle.  f16 activations round at 2^-12 relative,
     an eighth of the bf16 weights' own step: the modes agree to a few 1e-3 of the rms, every mode keeps the 2e-2 bar."""
     codes = np.repeat(full_oracle["codes"][None, :6], 24, axis=0)
 
