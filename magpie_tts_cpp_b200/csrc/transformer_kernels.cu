@@ -671,7 +671,7 @@ bool launch_attention(const AttnArgs & a, cudaStream_t stream) {
         at[0].val.programmaticStreamSerializationAllowed = 1;
         at[1].id = cudaLaunchAttributeClusterDimension;
         at[1].val.clusterDim.x = 1; at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = std::max(S, 1);
-        cfg.attrs = at; cfg.numAttrs = S >= 1 ? 2 : 1;
+        cfg.attrs = at; cfg.numAttrs = S > 1 ? 2 : 1;              // (one-CTA "clusters": a plain launch; the kernel skips its cluster barrier)
         const bool occ3 = getenv("MGB_ATTN_OCC3") != nullptr;
         const bool nw4 = getenv("MGB_ATTN_NW8") == nullptr && a.H * a.tok.M >= 512;      // (1040 -> 1012 us per step at 64 utterances)
         if (S >= 1 && occ3) MGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, attention_kernel<__nv_bfloat16, 64, 2>, p));
