@@ -5,9 +5,18 @@
 // idle (round-1 ncu: 117-320 GB/s per launch).  Here the roles are swapped: the <= 64 TOKENS are the MMA M side
 // (tcgen05.mma M = 64: accumulator rows on TMEM lanes 32 (m / 16) + m % 16) and every CTA owns a thin slice of n = 8 / 16 / 32
 // weight rows as the MMA N side, so a GEMM spreads over 96-144 CTAs, each streaming only its n x K weight bytes plus the
-// (L2-resident) activation tiles; no split-K, no cluster, no cross-CTA reduction: results are deterministic by construction.
-// Operands are the same shared-memory images gemm_tc.cu uses (SWIZZLE_128B K-major tiles of 64 k): an 8-row-aligned run of n
-// rows inside a packed 128-row weight tile is itself a valid n-row tile, so no second weight layout is needed.
+// (L2-resident) activation image.  The K = 768 GEMMs need no cross-CTA reduction; the FFN's second GEMM (K = 3072) splits k over a
+// 4-CTA cluster and reduce-scatters the partial accumulators through DSMEM in rank order: results are deterministic either way.
+// Operands are the shared-memory images gemm_tc.cu uses (SWIZZLE_128B K-major tiles of 64 k): an 8-row-aligned run of n rows inside
+// a packed 128-row weight tile is itself a valid n-row tile, so no second weight LAYOUT is needed; the activations arrive as ONE f16
+// image against f16 twins of the bf16 weight images (default) or as bf16 hi | lo image pairs (MGB_ACT_F16=0), written by the producing
+// kernel's epilogue.  What the round-2 timeline (profiles/r2_b64_step_timeline.txt) taught this file:
+//   * the producer and MMA roles run their loops warp-uniformly with one elected lane (a divergent single lane pays ~60 cycles per
+//     tcgen05.mma / bulk copy for register -> uniform-register moves);
+//   * epilogues use all 8 x 32 epilogue lanes (two warps per TMEM lane quarter, lanes 16..31 take half of their row's columns), fetch
+//     their global operands before waiting for the accumulator, and store operand images in whole 16 / 32-byte pieces;
+//   * a LayerNorm in front of a GEMM is folded THROUGH it: the producer emits x .* w and per-slice row statistics, the epilogue applies
+//     (acc - mean * csum[n]) * rstd with the statistics added while the MMAs run.
 // Replaces ggml_mul_mat at src/magpie.cpp:3415, 3472, 1796, 1805 for the batched step.
 #include <cstdio>
 #include <cstdlib>
