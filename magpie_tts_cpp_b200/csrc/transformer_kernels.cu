@@ -209,6 +209,8 @@ __device__ unsigned g_attn_dbg_n;
 
 template <typename T, int DH, int SPLIT = 0, int NW = kAttnWarps>      // NW warps per CTA; SPLIT: 0 = one CTA per (head, token); 1 / 2 = pipelined scan + cluster key split compiled for 2 / 3 resident CTAs per SM
 __global__ void __launch_bounds__(NW * 32, SPLIT == 2 ? (NW == 4 ? 6 : 3) : 0) attention_kernel(const AttnParams p) {
+    // (the bf16 decoder-step variants are instruction-issue bound: softmax exponentials on the SFU, 2 instructions instead of ~8)
+    auto fexp = [](float x) -> float { if constexpr (SPLIT >= 1) return __expf(x); else return expf(x); };
     constexpr int VEC = WT<T>::VEC;
     constexpr int LPK = DH / VEC;            // lanes per key row
     constexpr int KPI = 32 / LPK;            // keys per warp instruction
@@ -272,23 +274,30 @@ __global__ void __launch_bounds__(NW * 32, SPLIT == 2 ? (NW == 4 ? 6 : 3) : 0) a
         // current ones are used (twice the bytes in flight per warp, loads overlap the softmax arithmetic); same arithmetic and
         // order per key as the loop below.
         constexpr int STEP = NW * KPI * U;
+        static_assert((KPI * U) <= kPageRows && kPageRows % (KPI * U) == 0, "a warp's key group must not straddle a page");
         uint4 kr[U], vr[U];
         int base = k0 + warp * (KPI * U);
+        // One address computation per GROUP of KPI * U = 16 keys (k0 and the groups are 16-aligned, so a group lies inside one 128-row page):
+        // the kernel is instruction-issue bound at short KV (2 200 instructions per warp for ~130 keys, 24 warps per SM), and the per-key
+        // page-table lookup + 64-bit row arithmetic was a third of them.  32-bit element offsets: the K / V pools hold < 2^31 elements.
+        auto request = [&](int b0) {
+            if (b0 < k1) {                                               // (warp-uniform)
+                const unsigned e0 = (unsigned)(krow(b0) + (size_t)grp) * (unsigned)ld;
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            const int j = base + u * KPI + grp;
-            kr[u] = make_uint4(0u, 0u, 0u, 0u); vr[u] = make_uint4(0u, 0u, 0u, 0u);
-            if (j < k1) { kr[u] = ldg_stream(Kb + krow(j) * ld); vr[u] = ldg_stream(Vb + krow(j) * ld); }
-        }
+                for (int u = 0; u < U; u++) {
+                    const unsigned eo = e0 + (unsigned)(u * KPI) * (unsigned)ld;
+                    if (b0 + u * KPI + grp < k1) { kr[u] = ldg_stream(Kb + eo); vr[u] = ldg_stream(Vb + eo); }
+                }
+            }
+        };
+#pragma unroll
+        for (int u = 0; u < U; u++) { kr[u] = make_uint4(0u, 0u, 0u, 0u); vr[u] = make_uint4(0u, 0u, 0u, 0u); }
+        request(base);
         for (; base < k1; base += STEP) {
             uint4 kc[U], vc[U];
 #pragma unroll
             for (int u = 0; u < U; u++) { kc[u] = kr[u]; vc[u] = vr[u]; }
-#pragma unroll
-            for (int u = 0; u < U; u++) {
-                const int j = base + STEP + u * KPI + grp;
-                if (j < k1) { kr[u] = ldg_stream(Kb + krow(j) * ld); vr[u] = ldg_stream(Vb + krow(j) * ld); }
-            }
+            request(base + STEP);
             float sc[U], mnew = mx;
 #pragma unroll
             for (int u = 0; u < U; u++) {
@@ -303,13 +312,13 @@ __global__ void __launch_bounds__(NW * 32, SPLIT == 2 ? (NW == 4 ? 6 : 3) : 0) a
                 mnew = fmaxf(mnew, sc[u]);
             }
             if (mnew != -INFINITY) {
-                const float corr = expf(mx - mnew);
+                const float corr = fexp(mx - mnew);
                 float ps = 0.0f;
 #pragma unroll
                 for (int v = 0; v < VEC; v++) acc[v] *= corr;
 #pragma unroll
                 for (int u = 0; u < U; u++) {
-                    const float pj = expf(sc[u] - mnew);
+                    const float pj = fexp(sc[u] - mnew);
                     ps += pj;
                     float vv[VEC];
                     WT<T>::unpack(vc[u], vv);
@@ -346,13 +355,13 @@ __global__ void __launch_bounds__(NW * 32, SPLIT == 2 ? (NW == 4 ? 6 : 3) : 0) a
             mnew = fmaxf(mnew, sc[u]);
         }
         if (mnew != -INFINITY) {
-            const float corr = expf(mx - mnew);            // mx = -inf -> 0
+            const float corr = fexp(mx - mnew);            // mx = -inf -> 0
             float ps = 0.0f;
 #pragma unroll
             for (int v = 0; v < VEC; v++) acc[v] *= corr;
 #pragma unroll
             for (int u = 0; u < U; u++) {
-                const float pj = expf(sc[u] - mnew);       // -inf -> 0
+                const float pj = fexp(sc[u] - mnew);       // -inf -> 0
                 ps += pj;
 #pragma unroll
                 for (int v = 0; v < VEC; v++) acc[v] = fmaf(pj, vv[u][v], acc[v]);
@@ -368,7 +377,7 @@ __global__ void __launch_bounds__(NW * 32, SPLIT == 2 ? (NW == 4 ? 6 : 3) : 0) a
     for (int o = LPK; o < 32; o <<= 1) {
         const float om = __shfl_xor_sync(0xffffffffu, mx, o), ol = __shfl_xor_sync(0xffffffffu, l, o);
         const float mn = fmaxf(mx, om);
-        const float fa = mx == -INFINITY ? 0.0f : expf(mx - mn), fb = om == -INFINITY ? 0.0f : expf(om - mn);
+        const float fa = mx == -INFINITY ? 0.0f : fexp(mx - mn), fb = om == -INFINITY ? 0.0f : fexp(om - mn);
         l = l * fa + ol * fb;
 #pragma unroll
         for (int v = 0; v < VEC; v++) {
@@ -391,7 +400,7 @@ __global__ void __launch_bounds__(NW * 32, SPLIT == 2 ? (NW == 4 ? 6 : 3) : 0) a
         for (int w = 1; w < NW; w++) M = fmaxf(M, s_m[w]);
 #pragma unroll
         for (int w = 0; w < NW; w++) {
-            const float f = s_m[w] == -INFINITY ? 0.0f : expf(s_m[w] - M);
+            const float f = s_m[w] == -INFINITY ? 0.0f : fexp(s_m[w] - M);
             L += f * s_l[w];
             o += f * s_acc[w][tid];
         }
@@ -408,7 +417,7 @@ __global__ void __launch_bounds__(NW * 32, SPLIT == 2 ? (NW == 4 ? 6 : 3) : 0) a
                 const float om = x_m[r];
                 if (om == -INFINITY) continue;              // that rank had no keys
                 const float mn = fmaxf(M, om);
-                const float fa = M == -INFINITY ? 0.0f : expf(M - mn), fb = expf(om - mn);
+                const float fa = M == -INFINITY ? 0.0f : fexp(M - mn), fb = fexp(om - mn);
                 L = L * fa + x_l[r] * fb;
                 o = o * fa + x_o[r][tid] * fb;
                 M = mn;
