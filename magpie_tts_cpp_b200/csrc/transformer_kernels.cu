@@ -292,12 +292,21 @@ __global__ void __launch_bounds__(NW * 32, SPLIT == 2 ? (NW == 4 ? 6 : 3) : 0) a
         };
 #pragma unroll
         for (int u = 0; u < U; u++) { kr[u] = make_uint4(0u, 0u, 0u, 0u); vr[u] = make_uint4(0u, 0u, 0u, 0u); }
-        request(base);
+        // NW == 4 (short KV, 6 resident CTAs per SM = 24 warps): no software pipelining -- the other warps hide the latency, and the copy of
+        // the arrived words + the second register set cost instructions and spills the issue-bound kernel cannot afford
+        constexpr bool PIPE = NW != 4;
+        if (PIPE) request(base);
         for (; base < k1; base += STEP) {
             uint4 kc[U], vc[U];
+            if (PIPE) {
 #pragma unroll
-            for (int u = 0; u < U; u++) { kc[u] = kr[u]; vc[u] = vr[u]; }
-            request(base + STEP);
+                for (int u = 0; u < U; u++) { kc[u] = kr[u]; vc[u] = vr[u]; }
+                request(base + STEP);
+            } else {
+                request(base);
+#pragma unroll
+                for (int u = 0; u < U; u++) { kc[u] = kr[u]; vc[u] = vr[u]; kr[u] = make_uint4(0u, 0u, 0u, 0u); vr[u] = make_uint4(0u, 0u, 0u, 0u); }
+            }
             float sc[U], mnew = mx;
 #pragma unroll
             for (int u = 0; u < U; u++) {
