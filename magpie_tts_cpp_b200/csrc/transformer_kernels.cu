@@ -258,8 +258,14 @@ __global__ void __launch_bounds__(NW * 32, SPLIT == 2 ? (NW == 4 ? 6 : 3) : 0) a
     float qv[VEC];
     {
         const float * qp = p.q + (size_t)t * p.ldq + h * DH + sub * VEC;
+        if constexpr (VEC == 8) {
+            const float4 a = *reinterpret_cast<const float4 *>(qp), b = *reinterpret_cast<const float4 *>(qp + 4);
+            qv[0] = a.x * scale; qv[1] = a.y * scale; qv[2] = a.z * scale; qv[3] = a.w * scale;
+            qv[4] = b.x * scale; qv[5] = b.y * scale; qv[6] = b.z * scale; qv[7] = b.w * scale;
+        } else {
 #pragma unroll
-        for (int v = 0; v < VEC; v++) qv[v] = qp[v] * scale;
+            for (int v = 0; v < VEC; v++) qv[v] = qp[v] * scale;
+        }
     }
     const T * Kb = (const T *)p.K + h * DH + sub * VEC;
     const T * Vb = (const T *)p.V + h * DH + sub * VEC;
@@ -279,14 +285,24 @@ __global__ void __launch_bounds__(NW * 32, SPLIT == 2 ? (NW == 4 ? 6 : 3) : 0) a
         int base = k0 + warp * (KPI * U);
         // One address computation per GROUP of KPI * U = 16 keys (k0 and the groups are 16-aligned, so a group lies inside one 128-row page):
         // the kernel is instruction-issue bound at short KV (2 200 instructions per warp for ~130 keys, 24 warps per SM), and the per-key
-        // page-table lookup + 64-bit row arithmetic was a third of them.  32-bit element offsets: the K / V pools hold < 2^31 elements.
+        // page-table lookup + 64-bit row arithmetic was a third of them.
         auto request = [&](int b0) {
             if (b0 < k1) {                                               // (warp-uniform)
-                const unsigned e0 = (unsigned)(krow(b0) + (size_t)grp) * (unsigned)ld;
+                const size_t r0 = krow(b0);
+                if (b0 + KPI * U <= k1) {                                // (warp-uniform) whole group: one 64-bit base, constant strides
+                    const T * kp = Kb + (r0 + (size_t)grp) * ld, * vp = Vb + (r0 + (size_t)grp) * ld;
+                    const size_t st = (size_t)KPI * ld;
 #pragma unroll
-                for (int u = 0; u < U; u++) {
-                    const unsigned eo = e0 + (unsigned)(u * KPI) * (unsigned)ld;
-                    if (b0 + u * KPI + grp < k1) { kr[u] = ldg_stream(Kb + eo); vr[u] = ldg_stream(Vb + eo); }
+                    for (int u = 0; u < U; u++) { kr[u] = ldg_stream(kp); vr[u] = ldg_stream(vp); kp += st; vp += st; }
+                } else {
+                    // last, partial group: keys past the end are CLAMPED to the last one (no predicated loads, no zero fill); their scores
+                    // are masked to -inf below, so their probability is exactly 0 and the finite duplicate V row contributes nothing
+                    const unsigned last = (unsigned)(k1 - 1 - b0);
+#pragma unroll
+                    for (int u = 0; u < U; u++) {
+                        const size_t eo = (r0 + min((unsigned)(u * KPI + grp), last)) * (size_t)ld;
+                        kr[u] = ldg_stream(Kb + eo); vr[u] = ldg_stream(Vb + eo);
+                    }
                 }
             }
         };
@@ -305,7 +321,7 @@ __global__ void __launch_bounds__(NW * 32, SPLIT == 2 ? (NW == 4 ? 6 : 3) : 0) a
             } else {
                 request(base);
 #pragma unroll
-                for (int u = 0; u < U; u++) { kc[u] = kr[u]; vc[u] = vr[u]; kr[u] = make_uint4(0u, 0u, 0u, 0u); vr[u] = make_uint4(0u, 0u, 0u, 0u); }
+                for (int u = 0; u < U; u++) { kc[u] = kr[u]; vc[u] = vr[u]; }
             }
             float sc[U], mnew = mx;
 #pragma unroll
