@@ -759,7 +759,7 @@ constexpr int kXRowsPerWarp = 16;      // score rows a warp keeps in flight (E <
 constexpr int kXRG = 5;                // row groups of the N pass: 5 x 48 float4 column groups = 240 threads
 __global__ void __launch_bounds__(kXT) xattn_folded_kernel(const XFoldParams p) {
     __shared__ __align__(16) float xl[256];         // this CTA's columns: LN(x), later LN2(updated row)
-    __shared__ float part[kXC][512];                // partial scores of every rank (written through DSMEM)
+    __shared__ __align__(16) float part[kXC][512];  // partial scores of every rank (written through DSMEM)
     __shared__ float prob[512];
     __shared__ __align__(16) float opart[kXRG][256]; // N pass: partial outputs of the row groups
     __shared__ float stat[2][kXC];                  // partial (sum, sum of squares) of the updated row, per rank
@@ -817,7 +817,19 @@ __global__ void __launch_bounds__(kXT) xattn_folded_kernel(const XFoldParams p) 
 #pragma unroll
             for (int q = 0; q < 3; q++) { a = fmaf(mv[r][q].x, xl[lane * 2 + q * 64], a); a = fmaf(mv[r][q].y, xl[lane * 2 + q * 64 + 1], a); }
             a = warp_sum(a);
-            if (lane < kXC) dsmem_store(&part[rank][j], lane, a);
+            if (lane == 0) part[rank][j] = a;          // (own copy; pushed to the peers in 16-byte pieces below)
+        }
+    }
+    __syncthreads();
+    // this rank's partial scores to the three peers: E / 4 sixteen-byte DSMEM stores per peer instead of one 4-byte store per (row, peer)
+    {
+        const int n4 = (E + 3) / 4;
+        for (int i = tid; i < n4 * (kXC - 1); i += kXT) {
+            const int peer = (rank + 1 + i / n4) % kXC, c = i % n4;
+            const float4 v4 = *reinterpret_cast<const float4 *>(&part[rank][4 * c]);
+            uint32_t la = (uint32_t)__cvta_generic_to_shared(&part[rank][4 * c]), ra;
+            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(peer));
+            asm volatile("st.shared::cluster.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(ra), "f"(v4.x), "f"(v4.y), "f"(v4.z), "f"(v4.w) : "memory");
         }
     }
     cluster_sync_all();
