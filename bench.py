@@ -462,14 +462,18 @@ def extra_measurements(binding, fixtures, m, args):
         def on_audio(u, pcm, frames_done, is_last):
             got[0] += len(pcm)
             return False
-        for steps_ in (16, sf):
+        walls = []
+        for steps_ in (16, sf, sf):      # warm-up, then two timed runs (wall clock with 3 200 host callbacks: the best of two, both reported)
             s.encode_text([HELLO] * B, want_output=False); s.prefill([b % 5 for b in range(B)])
             got[0] = 0
             t0 = time.perf_counter()
             s.stream_generate(c5, on_audio, max_steps=steps_, frames_per_chunk=4, codec_context_frames=25, ignore_eos=True)
-            wall = time.perf_counter() - t0
+            if steps_ == sf:
+                walls.append(time.perf_counter() - t0)
+        wall = min(walls)
         out["stream_q8_b32_frames_per_s"] = B * sf / wall
         out["stream_q8_b32_audio_s_per_s"] = got[0] / 22050.0 / wall
+        out["stream_q8_b32_wall_samples_s"] = [round(w, 3) for w in walls]
         out["stream_q8_b32_sample"] = ("config 5 per-GPU share as streaming: 32 utterances in lock step, first 400 frames, chunks of 4 frames, every chunk "
                                        "decoded with 25 context frames (29 frames per utterance and chunk through the codec) and copied to the host callback; wall clock")
         s.close(); c5.close(); mq.close()
