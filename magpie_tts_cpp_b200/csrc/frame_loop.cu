@@ -438,39 +438,82 @@ __device__ __noinline__ int cta_sample_top_k(LoopSmem & S, float * logits, int V
     const int tid = threadIdx.x, s_cw = tid >> 5, s_lane = tid & 31;
     int k = top_k < V ? top_k : V;
     if (k < 1) k = 1;
+    // (same three changes as lt_common.cuh block_sample_top_k: warp-aggregated histogram atomics, the bin of a radix pass found by a
+    //  parallel suffix sum instead of one thread walking 256 bins, compaction by all warps around a prefix over the index chunks)
     unsigned prefix = 0, pmask = 0; int want = k;
     for (int pass = 0; pass < 4; pass++) {
         const int shift = 24 - 8 * pass;
         if (tid < 256) S.hist[tid] = 0;
         cbar();
-        for (int i = tid; i < V; i += kCT) {
-            const unsigned key = order_key(logits[i]);
-            if ((key & pmask) == prefix) atomicAdd(&S.hist[(key >> shift) & 255u], 1u);
+        for (int i0 = 0; i0 < V; i0 += kCT) {
+            const int i = i0 + tid;
+            const unsigned key = i < V ? order_key(logits[i]) : 0u;
+            const bool valid = i < V && (key & pmask) == prefix;
+            const unsigned bin = (key >> shift) & 255u;
+            const unsigned vm = __ballot_sync(0xffffffffu, valid);
+            if (valid) {
+                const unsigned peers = __match_any_sync(vm, bin);
+                if (s_lane == __ffs(peers) - 1) atomicAdd(&S.hist[bin], (unsigned)__popc(peers));
+            }
         }
         cbar();
-        if (tid == 0) {
-            int acc = 0, bb = 255;
-            for (; bb > 0; bb--) { if (acc + (int)S.hist[bb] >= want) break; acc += (int)S.hist[bb]; }
-            S.misc[0] = bb; S.misc[1] = want - acc;
+        unsigned c = 0, sfx = 0;
+        if (tid < 256) {
+            c = S.hist[tid]; sfx = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_down_sync(0xffffffffu, sfx, o); if (s_lane + o < 32) sfx += t; }
+        }
+        if (tid < 256 && s_lane == 0) reinterpret_cast<unsigned *>(S.sel_v)[s_cw] = sfx;      // (sel_v is free until the compaction)
+        cbar();
+        if (tid < 256) {
+            unsigned off = 0;
+            for (int w = s_cw + 1; w < 8; w++) off += reinterpret_cast<const unsigned *>(S.sel_v)[w];
+            const unsigned suf = sfx + off;
+            if (suf - c < (unsigned)want && (tid == 0 || suf >= (unsigned)want)) { S.misc[0] = tid; S.misc[1] = want - (int)(suf - c); }
         }
         cbar();
         prefix |= (unsigned)S.misc[0] << shift; pmask |= 255u << shift; want = S.misc[1];
-        cbar();
+        // (no barrier here: the next pass writes misc only after three more barriers, and hist was last read before the previous one)
     }
+    cbar();
     const unsigned thr = prefix;
+    const int nchunk = (V + 31) >> 5;              // <= 64: hist = [greater | equal | base | equal before], 64 entries each
+    for (int ch = s_cw; ch < nchunk; ch += kCW) {
+        const int i = ch * 32 + s_lane;
+        const unsigned key = i < V ? order_key(logits[i]) : 0u;
+        const unsigned gm = __ballot_sync(0xffffffffu, i < V && key > thr), em = __ballot_sync(0xffffffffu, i < V && key == thr);
+        if (s_lane == 0) { S.hist[ch] = (unsigned)__popc(gm); S.hist[64 + ch] = (unsigned)__popc(em); }
+    }
+    cbar();
     if (s_cw == 0) {
-        int cnt = 0, eq_taken = 0;
-        for (int i0 = 0; i0 < V; i0 += 32) {
-            const int i = i0 + s_lane;
-            const unsigned key = i < V ? order_key(logits[i]) : 0u;
-            const bool gt = i < V && key > thr, eq = i < V && key == thr;
-            const unsigned eqm = __ballot_sync(0xffffffffu, eq);
-            const int eq_rank = eq_taken + __popc(eqm & ((1u << s_lane) - 1u));
-            const bool take = gt || (eq && eq_rank < want);
-            const unsigned tm = __ballot_sync(0xffffffffu, take);
-            if (take) { const int pp = cnt + __popc(tm & ((1u << s_lane) - 1u)); S.sel_v[pp] = logits[i]; S.sel_i[pp] = (uint16_t)i; }
-            cnt += __popc(tm); eq_taken += __popc(eqm);
+        int carry_e = 0, carry_t = 0;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int ch = s_lane + 32 * h;
+            const int e = ch < nchunk ? (int)S.hist[64 + ch] : 0, g = ch < nchunk ? (int)S.hist[ch] : 0;
+            int pe = e;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, pe, o); if (s_lane >= o) pe += t; }
+            const int eqb = carry_e + pe - e;
+            const int te = min(max(want - eqb, 0), e), tk = g + te;
+            int pt = tk;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, pt, o); if (s_lane >= o) pt += t; }
+            const int base = carry_t + pt - tk;
+            carry_e += __shfl_sync(0xffffffffu, pe, 31); carry_t += __shfl_sync(0xffffffffu, pt, 31);
+            if (ch < nchunk) { S.hist[128 + ch] = (unsigned)base; S.hist[192 + ch] = (unsigned)eqb; }
         }
+    }
+    cbar();
+    for (int ch = s_cw; ch < nchunk; ch += kCW) {
+        const int i = ch * 32 + s_lane;
+        const unsigned key = i < V ? order_key(logits[i]) : 0u;
+        const bool gt = i < V && key > thr, eq = i < V && key == thr;
+        const unsigned eqm = __ballot_sync(0xffffffffu, eq);
+        const int eq_rank = (int)S.hist[192 + ch] + __popc(eqm & ((1u << s_lane) - 1u));
+        const bool take = gt || (eq && eq_rank < want);
+        const unsigned tm = __ballot_sync(0xffffffffu, take);
+        if (take) { const int pp = (int)S.hist[128 + ch] + __popc(tm & ((1u << s_lane) - 1u)); S.sel_v[pp] = logits[i]; S.sel_i[pp] = (uint16_t)i; }
     }
     cbar();
     float * srt_v = logits;
@@ -490,11 +533,21 @@ __device__ __noinline__ int cta_sample_top_k(LoopSmem & S, float * logits, int V
     cbar();
     { int n = 0; for (int a = tid; a < k; a += kCT, n++) S.sel_v[a] = ex[n]; }
     cbar();
-    if (tid == 0) {
+    if (tid == 0) {                                // sequential float accumulation, as the reference
         float sum = 0.0f;
+#pragma unroll 8
         for (int a = 0; a < k; a++) sum += S.sel_v[a];
+        S.misc[3] = __float_as_int(sum);
+    }
+    cbar();
+    {
+        const float sum = __int_as_float(S.misc[3]);
+        for (int a = tid; a < k; a += kCT) srt_v[a] = S.sel_v[a] / sum;        // (the sorted values are no longer needed)
+    }
+    cbar();
+    if (tid == 0) {
         float cum = 0.0f; int pick = S.srt_i[k - 1];
-        for (int a = 0; a < k; a++) { cum += S.sel_v[a] / sum; if (u < cum) { pick = S.srt_i[a]; break; } }
+        for (int a = 0; a < k; a++) { cum += srt_v[a]; if (u < cum) { pick = S.srt_i[a]; break; } }
         S.misc[2] = pick;
     }
     cbar();
