@@ -441,10 +441,10 @@ __device__ __noinline__ int cta_sample_top_k(LoopSmem & S, float * logits, int V
     // (same three changes as lt_common.cuh block_sample_top_k: warp-aggregated histogram atomics, the bin of a radix pass found by a
     //  parallel suffix sum instead of one thread walking 256 bins, compaction by all warps around a prefix over the index chunks)
     unsigned prefix = 0, pmask = 0; int want = k;
+    if (tid < 256) S.hist[tid] = 0;
+    cbar();
     for (int pass = 0; pass < 4; pass++) {
         const int shift = 24 - 8 * pass;
-        if (tid < 256) S.hist[tid] = 0;
-        cbar();
         for (int i0 = 0; i0 < V; i0 += kCT) {
             const int i = i0 + tid;
             const unsigned key = i < V ? order_key(logits[i]) : 0u;
@@ -452,14 +452,17 @@ __device__ __noinline__ int cta_sample_top_k(LoopSmem & S, float * logits, int V
             const unsigned bin = (key >> shift) & 255u;
             const unsigned vm = __ballot_sync(0xffffffffu, valid);
             if (valid) {
-                const unsigned peers = __match_any_sync(vm, bin);
-                if (s_lane == __ffs(peers) - 1) atomicAdd(&S.hist[bin], (unsigned)__popc(peers));
+                if (pass == 0) {                     // all V keys, two or three hot bins (sign + exponent byte): one atomic per bin and warp
+                    const unsigned peers = __match_any_sync(vm, bin);
+                    if (s_lane == __ffs(peers) - 1) atomicAdd(&S.hist[bin], (unsigned)__popc(peers));
+                } else atomicAdd(&S.hist[bin], 1u);  // later passes: only the keys of one bin of the previous pass
             }
         }
         cbar();
         unsigned c = 0, sfx = 0;
         if (tid < 256) {
             c = S.hist[tid]; sfx = c;
+            S.hist[tid] = 0;                       // (this thread's bin, ready for the next pass: no separate clearing step)
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_down_sync(0xffffffffu, sfx, o); if (s_lane + o < 32) sfx += t; }
         }
@@ -518,11 +521,28 @@ __device__ __noinline__ int cta_sample_top_k(LoopSmem & S, float * logits, int V
     cbar();
     float * srt_v = logits;
     // rank by counting -> sorted (value desc, index asc)
-    for (int a = tid; a < k; a += kCT) {
-        const float va = S.sel_v[a]; const int ia = S.sel_i[a];
-        int r = 0;
-        for (int q = 0; q < k; q++) { const float vb = S.sel_v[q]; r += (vb > va || (vb == va && (int)S.sel_i[q] < ia)) ? 1 : 0; }
-        S.rank[a] = (uint16_t)r;
+    // (k <= 128: element a = tid mod 128, a third of the k comparisons per thread, partial ranks added in shared memory)
+    if (k <= 128) {
+        if (tid < 128) S.hist[tid] = 0;
+        cbar();
+        const int a = tid & 127, part = tid >> 7, per = (k + 2) / 3;          // 480 threads: parts 0..2 of 128 elements (part 3 = 96 threads: unused)
+        if (a < k && part < 3) {
+            const float va = S.sel_v[a]; const int ia = S.sel_i[a];
+            int r = 0;
+            const int q1 = min(k, (part + 1) * per);
+#pragma unroll 4
+            for (int q = part * per; q < q1; q++) { const float vb = S.sel_v[q]; r += (vb > va || (vb == va && (int)S.sel_i[q] < ia)) ? 1 : 0; }
+            if (r) atomicAdd(&S.hist[a], (unsigned)r);
+        }
+        cbar();
+        if (tid < k) S.rank[tid] = (uint16_t)S.hist[tid];
+    } else {
+        for (int a = tid; a < k; a += kCT) {
+            const float va = S.sel_v[a]; const int ia = S.sel_i[a];
+            int r = 0;
+            for (int q = 0; q < k; q++) { const float vb = S.sel_v[q]; r += (vb > va || (vb == va && (int)S.sel_i[q] < ia)) ? 1 : 0; }
+            S.rank[a] = (uint16_t)r;
+        }
     }
     cbar();
     for (int a = tid; a < k; a += kCT) { const int r = S.rank[a]; srt_v[r] = S.sel_v[a]; S.srt_i[r] = S.sel_i[a]; }
@@ -546,9 +566,10 @@ __device__ __noinline__ int cta_sample_top_k(LoopSmem & S, float * logits, int V
     }
     cbar();
     if (tid == 0) {
-        float cum = 0.0f; int pick = S.srt_i[k - 1];
-        for (int a = 0; a < k; a++) { cum += srt_v[a]; if (u < cum) { pick = S.srt_i[a]; break; } }
-        S.misc[2] = pick;
+        float cum = 0.0f; int pa = k - 1; bool found = false;
+#pragma unroll 8
+        for (int a = 0; a < k; a++) { cum += srt_v[a]; if (!found && u < cum) { pa = a; found = true; } }
+        S.misc[2] = S.srt_i[pa];
     }
     cbar();
     const int r = S.misc[2];

@@ -549,6 +549,7 @@ __global__ void __launch_bounds__(kLtThreads, 1) lt_cluster_kernel(const ClParam
             if (p.logits)
                 for (int i = tid; i < V; i += kLtThreads) p.logits[(my_row * 8 + cb) * V + i] = S.logits[i];
             const int am = block_argmax(S.logits, V, S.red, S.redi);
+            if (cp.dbg_fine) stamp();
             int pick = am;
             if (p.temperature >= 0.01f) {
                 float uu;
@@ -564,6 +565,7 @@ __global__ void __launch_bounds__(kLtThreads, 1) lt_cluster_kernel(const ClParam
                 sv.hist = reinterpret_cast<unsigned *>(sv.srt_i + kV); sv.misc = reinterpret_cast<int *>(sv.hist + 256);
                 pick = block_sample_top_k(sv, V, p.temperature, p.top_k, uu);
             }
+            if (cp.dbg_fine) stamp();
             hit_eos = hit_eos || pick == p.eos_id || am == p.eos_id;
             if (tid == 0) {
                 p.argmax[my_row * 8 + cb] = am;
